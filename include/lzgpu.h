@@ -1,0 +1,222 @@
+/*
+ * lzgpu.h — C ABI of the B200-native erasure-coding + checksum engine (liblzgpu.so).
+ *
+ * This is the drop-in boundary for ONE hot path of lizardfs/lizardfs: xorN / ec(k,m) parity
+ * encode, degraded-read recover and per-64 KiB-block CRC32.  Plain pointers and
+ * sizes only; no CUDA or torch types.  All arithmetic runs in hand-written sm_100a CUDA kernels;
+ * there is NO CPU fallback: if no CUDA device / kernel image is usable every call fails loudly
+ * (status < 0, or abort() with a message for the void reference signatures).
+ *
+ * Reference interfaces replaced (paths relative to the lizardfs tree):
+ *   src/common/galois_field.h:35-88     gf_gen_rs_matrix, gf_gen_cauchy1_matrix, gf_invert_matrix,
+ *                                       ec_init_tables, ec_encode_data   (same names, extern "C",
+ *                                       identical to <isa-l/erasure_code.h>, the reference's existing
+ *                                       link-time plug point: src/common/CMakeLists.txt:12-15,40-42)
+ *   src/common/reed_solomon.h:87-155    ReedSolomon<>::recover / encode   -> lzgpu_rs_recover / _encode
+ *   src/common/block_xor.h:33           blockXor                          -> lzgpu_block_xor
+ *   src/common/crc.h:25-36              mycrc32, mycrc32_combine, mycrc32_init, macros,
+ *                                       recompute_crc_if_block_empty      -> lzgpu_mycrc32*, ...
+ *   src/mount/chunk_writer.cc:365-401,475-547   per-stripe parity + per-block CRC of a chunk
+ *                                                                         -> lzgpu_encode_chunks*
+ *   src/common/ec_read_plan.h:88-146, xor_read_plan.h:77-126, chunk_read_planner.h:36-70,
+ *   src/common/read_operation_executor.cc:257-269                         -> lzgpu_recover_chunks*
+ *   src/chunkserver/hddspacemgr.cc:2148-2210 (scrub), :1918, chunk_replicator.cc:186-192
+ *                                                                         -> lzgpu_crc_blocks*, lzgpu_verify_blocks*
+ * C++-linkage symbols with the reference's exact names (mycrc32, blockXor, ...) are exported too
+ * (lizardfs_b200/csrc/compat_cxx.cc) so the library can replace crc.cc / block_xor.cc /
+ * galois_field_*.cc at link time; see INTEGRATION.md.
+ */
+#ifndef LZGPU_H
+#define LZGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LZGPU_BLOCK_SIZE 65536u      /* MFSBLOCKSIZE */
+#define LZGPU_BLOCKS_IN_CHUNK 1024u  /* MFSBLOCKSINCHUNK */
+#define LZGPU_CHUNK_SIZE (LZGPU_BLOCK_SIZE * LZGPU_BLOCKS_IN_CHUNK)
+#define LZGPU_MAX_DATA 32            /* slice_traits::ec::kMaxDataCount */
+#define LZGPU_MAX_PARITY 32          /* slice_traits::ec::kMaxParityCount */
+#define LZGPU_MAX_PARTS 64
+
+/* status codes (0 = OK).  LZGPU_ERR_CRC is what callers map to LIZARDFS_ERROR_CRC
+ * (hddspacemgr.cc:1918-1920) / ChunkCrcException (read_operation_executor.cc:262-264). */
+#define LZGPU_OK 0
+#define LZGPU_ERR_ARG (-1)
+#define LZGPU_ERR_CUDA (-2)
+#define LZGPU_ERR_NOMEM (-3)
+#define LZGPU_ERR_CRC (-4)
+#define LZGPU_ERR_TOO_FEW_PARTS (-5)
+#define LZGPU_ERR_NO_DEVICE (-6)
+
+/* ---------------------------------------------------------------------------------------------
+ * Goals (src/common/goal.h:108-120, slice_traits.h:96-211).
+ * kind 0 = xorN (k = N data parts + 1 parity), kind 1 = ec(k,m).
+ * Part numbering in THIS API is uniform for both kinds: data 0..k-1, then parity k..k+m-1.
+ * (The reference numbers xor parts parity = 0, data = 1..N; lzgpu_ref_part_index converts.)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct lzgpu_goal {
+	int kind; /* 0 xor, 1 ec */
+	int k;    /* data parts: xor 2..9, ec 2..32 */
+	int m;    /* parity parts: xor 1, ec 1..32 */
+} lzgpu_goal;
+
+int lzgpu_goal_parse(const char *text, lzgpu_goal *out); /* "xor3", "$xor3", "ec(8,2)", "$ec(8,2)" (goal_config_loader.cc:228-245) */
+int lzgpu_goal_valid(const lzgpu_goal *g);                /* 1 / 0 */
+int lzgpu_goal_slice_type(const lzgpu_goal *g);           /* Goal::Slice::Type value: xorN -> 2+(N-2), ec -> 10+32(k-2)+(m-1) */
+int lzgpu_goal_from_slice_type(int slice_type, lzgpu_goal *out);
+int lzgpu_ref_part_index(const lzgpu_goal *g, int part);  /* this API's part index -> reference slice part number */
+int lzgpu_chunk_part_id(const lzgpu_goal *g, int part);   /* ChunkPartType id = type*64 + ref part (chunk_part_type.h:173) */
+uint32_t lzgpu_part_blocks(const lzgpu_goal *g, int part, uint32_t blocks_in_chunk); /* slice_traits.h:311-316 */
+uint32_t lzgpu_part_length(const lzgpu_goal *g, int part, uint32_t chunk_length);    /* slice_traits.h:332-349 */
+
+/* ---------------------------------------------------------------------------------------------
+ * Engine context: one per (process, device).  Owns streams, pinned staging and device scratch.
+ * lzgpu_default_ctx() lazily creates a context on the current device (LZGPU_DEVICE env or 0) for
+ * the reference-signature entry points, which carry no context argument.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct lzgpu_ctx lzgpu_ctx;
+
+int lzgpu_device_count(void);
+int lzgpu_ctx_create(int device, lzgpu_ctx **out);
+void lzgpu_ctx_destroy(lzgpu_ctx *ctx);
+lzgpu_ctx *lzgpu_default_ctx(void);
+const char *lzgpu_last_error(void); /* thread-local text of the last failure */
+const char *lzgpu_version(void);
+
+/* per-context counters (SURVEY.md §5 "metrics"): kernels launched, bytes, device ms of the last call */
+typedef struct lzgpu_stats {
+	uint64_t kernel_launches;
+	uint64_t bytes_h2d;
+	uint64_t bytes_d2h;
+	uint64_t chunks_encoded;
+	uint64_t chunks_recovered;
+	uint64_t blocks_crc;
+	double last_kernel_ms;
+} lzgpu_stats;
+void lzgpu_get_stats(lzgpu_ctx *ctx, lzgpu_stats *out);
+void lzgpu_reset_stats(lzgpu_ctx *ctx);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batched chunk API (what the GPU wants; hook points: ChunkWriter::startOperation,
+ * ReadPlan::postProcessData, hdd_int_test).  All chunks of a call share goal and chunk_len.
+ *
+ * Layouts:
+ *   data    chunk c at data + c*chunk_stride, chunk order (block b -> data part b%k, index b/k).
+ *           chunk_len bytes are meaningful; a trailing partial block is treated as zero-extended
+ *           to 64 KiB (what the chunkserver stores, hddspacemgr.cc:1983-1999).
+ *   parity  chunk c at parity + c*parity_stride: m parts, part r at + r*pb*65536, pb = ceil(nb/k).
+ *   crc     chunk c at crc + c*crc_stride (in uint32 elements): nb data-block CRCs in chunk order,
+ *           then for r < m the pb CRCs of parity part r.  Host byte order (callers put32bit them).
+ * The *_dev variants take device pointers of the context's device, enqueue on `stream`
+ * (a cudaStream_t passed as void*, NULL = the context's stream) and do not synchronise.
+ * The host variants stage through pinned memory (H2D, kernel, D2H) and return when results are
+ * in the caller's buffers.
+ * ------------------------------------------------------------------------------------------- */
+int lzgpu_encode_chunks(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t chunk_len,
+                        const uint8_t *data, size_t chunk_stride,
+                        uint8_t *parity, size_t parity_stride,
+                        uint32_t *crc, size_t crc_stride);
+int lzgpu_encode_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t chunk_len,
+                            const void *d_data, size_t chunk_stride,
+                            void *d_parity, size_t parity_stride,
+                            void *d_crc, size_t crc_stride, void *stream);
+
+/* Degraded read / rebuild of n_chunks chunks.
+ *   parts[i]    (i < k+m) part-major buffer of part i for all chunks: chunk c at + c*part_stride,
+ *               pb blocks each (short parts zero-padded, slice_read_plan.h:94-105); NULL = unavailable.
+ *   part_crc[i] stored CRCs of part i (chunk c at + c*pb), or NULL / part_crc == NULL to skip
+ *               verification.  Verification = mycrc32(0, block, 65536) == stored
+ *               (read_operation_executor.cc:257-269); a mismatch returns LZGPU_ERR_CRC and reports the
+ *               first bad (chunk, part, block) in bad[0..2]; recovered outputs are then undefined.
+ *   want[i]     non-zero: part i is requested.  Requested unavailable parts are rebuilt into out[i]
+ *               (same layout as parts[i]).  As in ECReadPlan::recoverParts (ec_read_plan.h:113-146)
+ *               the first k available parts (ascending index) are the inputs.
+ *   chunk_out   optional chunk-order image (BlockConverter, chunk_read_planner.h:36-70), chunk c at
+ *               + c*chunk_out_stride, nb blocks; available data parts are copied, missing ones rebuilt.
+ *               When non-NULL every data part is implicitly wanted.
+ * Returns LZGPU_ERR_TOO_FEW_PARTS when fewer than k parts are available. */
+int lzgpu_recover_chunks(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb,
+                         const uint8_t *const *parts, size_t part_stride,
+                         const uint32_t *const *part_crc,
+                         const uint8_t *want, uint8_t *const *out,
+                         uint8_t *chunk_out, size_t chunk_out_stride, int64_t *bad);
+int lzgpu_recover_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb,
+                             const void *const *d_parts, size_t part_stride,
+                             const void *const *d_part_crc,
+                             const uint8_t *want, void *const *d_out,
+                             void *d_chunk_out, size_t chunk_out_stride,
+                             int64_t *bad /* host; written after an internal sync only if non-NULL */,
+                             void *stream);
+
+/* CRC of n_blocks consecutive blocks of block_len bytes (block_len <= 65536, any value >= 1).
+ * crc_out[i] = mycrc32(0, data + i*block_stride, block_len). */
+int lzgpu_crc_blocks(lzgpu_ctx *ctx, const uint8_t *data, size_t n_blocks, uint32_t block_len,
+                     size_t block_stride, uint32_t *crc_out);
+int lzgpu_crc_blocks_dev(lzgpu_ctx *ctx, const void *d_data, size_t n_blocks, uint32_t block_len,
+                         size_t block_stride, void *d_crc_out, void *stream);
+/* Scrub (hdd_int_test, hddspacemgr.cc:2174-2190): compare against stored CRCs; returns LZGPU_OK or
+ * LZGPU_ERR_CRC with *first_bad = index of the first mismatching block.  A stored CRC of 0 on an
+ * all-zero block is accepted when sparse_rule != 0 (recompute_crc_if_block_empty, crc.cc:235-243). */
+int lzgpu_verify_blocks(lzgpu_ctx *ctx, const uint8_t *data, size_t n_blocks, uint32_t block_len,
+                        size_t block_stride, const uint32_t *stored_crc, int sparse_rule, int64_t *first_bad);
+/* On-disk chunk-file scrub: records of 4-byte big-endian CRC + 65536 data bytes
+ * (src/chunkserver/chunk.h:40, chunk.cc:195-209). */
+int lzgpu_verify_interleaved(lzgpu_ctx *ctx, const uint8_t *records, size_t n_blocks, int64_t *first_bad);
+
+/* ---------------------------------------------------------------------------------------------
+ * Reference-shaped single-call API (runs on the default context; every call is H2D + kernel + D2H).
+ * ------------------------------------------------------------------------------------------- */
+/* ReedSolomon<32,32>::encode / recover (reed_solomon.h:87-155).  in/out indexed by part;
+ * NULL available input = zeros, NULL output = skip; exactly m parts erased. */
+int lzgpu_rs_encode(int k, int m, const uint8_t *const *data, uint8_t *const *parity, size_t size);
+int lzgpu_rs_recover(int k, int m, const uint8_t *const *in, const uint8_t *erased,
+                     uint8_t *const *out, size_t size);
+/* host-side matrix logic of the above (no data touched): rows for the wanted parts over the k
+ * available parts; returns row count or < 0 (LZGPU_ERR_ARG; singular matrices are reported,
+ * the reference silently ignores them, reed_solomon.h:248-251). */
+int lzgpu_rs_generator(int k, int m, uint8_t *matrix /* (k+m)*k */);
+int lzgpu_rs_recovery_matrix(int k, int m, const uint8_t *erased, const uint8_t *wanted,
+                             uint8_t *matrix /* m*k */);
+
+void lzgpu_block_xor(uint8_t *dest, const uint8_t *source, size_t size);           /* blockXor */
+uint32_t lzgpu_mycrc32(uint32_t crc, const uint8_t *block, uint32_t leng);          /* mycrc32 */
+uint32_t lzgpu_mycrc32_combine(uint32_t crc1, uint32_t crc2, uint32_t leng2);       /* host scalar */
+void lzgpu_mycrc32_init(void);                                                      /* creates the default ctx */
+uint32_t lzgpu_mycrc32_zeroblock(uint32_t crc, uint32_t zeros);                     /* crc.h:27 */
+uint32_t lzgpu_mycrc32_zeroexpanded(uint32_t crc, const uint8_t *block, uint32_t leng, uint32_t zeros);
+uint32_t lzgpu_mycrc32_xorblocks(uint32_t crc, uint32_t crcblock1, uint32_t crcblock2, uint32_t leng);
+void lzgpu_recompute_crc_if_block_empty(const uint8_t *block, uint32_t *crc);       /* crc.cc:235-243 */
+
+/* ISA-L / galois_field.h names.  Matrix helpers are host scalar code (k <= 32: microseconds);
+ * ec_encode_data moves the fragments to the GPU, runs the GF(2^8) dot-product kernel and copies
+ * the results back.  The coefficient of table i is recovered from v[32*i + 1] (= c*1). */
+unsigned char gf_mul(unsigned char a, unsigned char b);
+unsigned char gf_inv(unsigned char a);
+void gf_gen_rs_matrix(unsigned char *a, int m, int k);
+void gf_gen_cauchy1_matrix(unsigned char *a, int m, int k);
+int gf_invert_matrix(unsigned char *in, unsigned char *out, const int n);
+void gf_vect_mul_init(unsigned char c, unsigned char *gftbl);
+void ec_init_tables(int k, int rows, unsigned char *a, unsigned char *gftbls);
+void ec_encode_data(int len, int srcs, int dests, unsigned char *v, unsigned char **src, unsigned char **dest);
+
+/* Synthetic data generator used by bench / tests (device side): fills chunks with the splitmix64
+ * counter stream documented in DESIGN.md §6 (same bytes as oracle lzo_fill_chunk). */
+int lzgpu_fill_chunks_dev(lzgpu_ctx *ctx, void *d_data, uint32_t n_chunks, size_t chunk_len,
+                          size_t chunk_stride, uint64_t seed, uint64_t first_chunk_index, void *stream);
+
+/* raw device helpers so hosts without a CUDA binding (ctypes, cgo) can keep data resident */
+int lzgpu_dev_alloc(lzgpu_ctx *ctx, size_t bytes, void **d_ptr);
+int lzgpu_dev_free(lzgpu_ctx *ctx, void *d_ptr);
+int lzgpu_dev_upload(lzgpu_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
+int lzgpu_dev_download(lzgpu_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+int lzgpu_dev_sync(lzgpu_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LZGPU_H */

@@ -1,0 +1,81 @@
+// device_math.cuh — device-side GF(2^8) and CRC-32 primitives shared by every kernel.
+//
+// GF(2^8) bytes are processed four at a time, packed in a 32-bit register ("packed word").
+// CRC-32 is handled as its GF(2)-LINEAR part only:  lin(M) = M(x) * x^32 mod P  (reflected
+// representation, P = 0xEDB88320, no initial complement, no final complement).  For a message
+// of n bytes  mycrc32(0, M, n) = lin(M) xor mycrc32(0, 0^n, n);  the second term is a host
+// constant (lz::crc_of_zeros) — e.g. 0xD7978EEB for a 64 KiB block
+// (reference: src/common/crc.cc:54-56, crc.h:27-29 `mycrc32_xorblocks` is this very identity).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace lzd {
+
+constexpr uint32_t kCrcPoly = 0xEDB88320u;
+constexpr uint32_t kCrcZeroBlock64K = 0xD7978EEBu;  // mycrc32(0, 65536 zero bytes); checked at ctx creation
+
+// ---- GF(2^8) on packed words -----------------------------------------------------------------
+// multiply each of the 4 bytes by 2 (x^8 = x^4+x^3+x^2+1, reference galois_coeff.h:30-32)
+__device__ __forceinline__ uint32_t gf_x2(uint32_t v) {
+	const uint32_t hi = v & 0x80808080u;
+	return ((v ^ hi) << 1) ^ ((hi >> 7) * 0x1du);
+}
+
+// One coefficient prepared for the bit-plane product: plane[b] = c * 2^b in GF(2^8), each stored
+// in a 32-bit word so that  c*v = XOR_b ((v >> b) & 0x01010101) * plane[b]  — every partial
+// product stays inside its byte lane (a 0/1 byte times an 8-bit constant), hence no carries.
+struct CoefPlanes {
+	uint32_t plane[8];
+};
+
+// acc ^= c * v for one packed word
+__device__ __forceinline__ uint32_t gf_mac(uint32_t acc, uint32_t v, const CoefPlanes &c) {
+#pragma unroll
+	for (int b = 0; b < 8; b += 2) {
+		const uint32_t p0 = ((v >> b) & 0x01010101u) * c.plane[b];
+		const uint32_t p1 = ((v >> (b + 1)) & 0x01010101u) * c.plane[b + 1];
+		acc = acc ^ p0 ^ p1;
+	}
+	return acc;
+}
+
+// ---- CRC-32 linear part ------------------------------------------------------------------------
+// a * b mod P in the reflected domain (bit 31 = x^0).  32 steps; used only O(1) times per block.
+__device__ __forceinline__ uint32_t crc_mulmod(uint32_t a, uint32_t b) {
+	uint32_t prod = 0;
+#pragma unroll 8
+	for (int i = 0; i < 32; ++i) {
+		prod ^= (a & 0x80000000u) ? b : 0u;
+		a <<= 1;
+		b = (b >> 1) ^ ((b & 1u) ? kCrcPoly : 0u);
+	}
+	return prod;
+}
+
+// state <- (state + w) * x^32 : absorb one little-endian 32-bit word with the 4 slicing tables
+// (tab[t][v] = v * x^(32+8t) style tables built by lz::crc_make_tables; tab points to 4*256 words)
+__device__ __forceinline__ uint32_t crc_step_word(uint32_t state, uint32_t w, const uint32_t *tab) {
+	const uint32_t v = state ^ w;
+	return tab[768 + (v & 0xff)] ^ tab[512 + ((v >> 8) & 0xff)] ^ tab[256 + ((v >> 16) & 0xff)] ^ tab[v >> 24];
+}
+
+__device__ __forceinline__ uint32_t crc_step_byte(uint32_t state, uint32_t byte, const uint32_t *tab) {
+	return tab[(state ^ byte) & 0xff] ^ (state >> 8);
+}
+
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p) {  // streaming 16-byte load, no L1 allocation
+	uint4 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+	             : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+	             : "l"(p));
+	return r;
+}
+
+__device__ __forceinline__ void st_stream(uint4 *p, const uint4 &v) {
+	asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+	             "r"(v.w)
+	             : "memory");
+}
+
+}  // namespace lzd

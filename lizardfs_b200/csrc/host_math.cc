@@ -1,0 +1,301 @@
+// host_math.cc — see host_math.h.  Written from the mathematical definitions; results are
+// checked against the oracle and the compiled reference in tests/test_host_math.py.
+#include "host_math.h"
+
+#include <cctype>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace lz {
+
+// ---------------------------------------------------------------- GF(2^8)
+// Shift-and-add multiply; any correct GF(2^8)/0x11d product equals the reference's
+// log/antilog result (galois_field_isal.cc:37-44).
+uint8_t gf_mul_host(uint8_t a, uint8_t b) {
+	unsigned acc = 0, aa = a;
+	for (int bit = 0; bit < 8; ++bit) {
+		if (b & (1u << bit)) acc ^= aa;
+		aa = (aa << 1) ^ ((aa & 0x80) ? 0x11d : 0);
+	}
+	return static_cast<uint8_t>(acc);
+}
+
+// a^254 = a^-1 in GF(2^8)* (galois_field_isal.cc:46-51 uses exp[255 - log a]); inv(0) = 0 there.
+uint8_t gf_inv_host(uint8_t a) {
+	if (a == 0) return 0;
+	uint8_t result = 1, base = a;
+	for (unsigned e = 254; e; e >>= 1) {
+		if (e & 1) result = gf_mul_host(result, base);
+		base = gf_mul_host(base, base);
+	}
+	return result;
+}
+
+bool uses_cauchy(int k, int m) { return m >= 5 || (m == 4 && k > 20); }
+
+static bool km_ok(int k, int m) { return k >= 1 && k <= LZGPU_MAX_DATA && m >= 1 && m <= LZGPU_MAX_PARITY; }
+
+int rs_generator(int k, int m, uint8_t *g) {
+	if (!km_ok(k, m)) return LZGPU_ERR_ARG;
+	if (uses_cauchy(k, m)) gf_gen_cauchy1_matrix(g, k + m, k);
+	else gf_gen_rs_matrix(g, k + m, k);
+	return LZGPU_OK;
+}
+
+int rs_recovery_matrix(int k, int m, const uint8_t *erased, const uint8_t *wanted, uint8_t *out, bool *singular) {
+	if (singular) *singular = false;
+	if (!km_ok(k, m)) return LZGPU_ERR_ARG;
+	const int n = k + m;
+	uint8_t gen[LZGPU_MAX_PARTS * LZGPU_MAX_DATA];
+	rs_generator(k, m, gen);
+	int n_erased = 0, data_present = 0, n_rows = 0;
+	bool parity_wanted = false;
+	for (int i = 0; i < n; ++i) {
+		if (erased[i]) {
+			++n_erased;
+			if (wanted[i]) { ++n_rows; parity_wanted |= i >= k; }
+		} else if (i < k) {
+			++data_present;
+		}
+	}
+	if (n_erased != m) return LZGPU_ERR_ARG;  // reed_solomon.h:95
+	if (n_rows == 0) return 0;
+	int r = 0;
+	if (data_present == k) {  // every data part is an input: plain generator rows
+		for (int i = k; i < n; ++i)
+			if (erased[i] && wanted[i]) std::memcpy(out + (r++) * k, gen + i * k, k);
+		return n_rows;
+	}
+	uint8_t sub[LZGPU_MAX_DATA * LZGPU_MAX_DATA], inv[LZGPU_MAX_DATA * LZGPU_MAX_DATA];
+	for (int i = 0; i < n; ++i)
+		if (!erased[i]) std::memcpy(sub + (r++) * k, gen + i * k, k);
+	if (gf_invert_matrix(sub, inv, k) != 0) {
+		if (singular) *singular = true;
+		return LZGPU_ERR_ARG;
+	}
+	r = 0;
+	if (!parity_wanted) {
+		for (int i = 0; i < k; ++i)
+			if (erased[i] && wanted[i]) std::memcpy(out + (r++) * k, inv + i * k, k);
+		return n_rows;
+	}
+	for (int i = 0; i < n; ++i) {
+		if (!(erased[i] && wanted[i])) continue;
+		for (int c = 0; c < k; ++c) {  // row_i(gen) * inv
+			uint8_t s = 0;
+			for (int t = 0; t < k; ++t) s ^= gf_mul_host(gen[i * k + t], inv[t * k + c]);
+			out[r * k + c] = s;
+		}
+		++r;
+	}
+	return n_rows;
+}
+
+// ---------------------------------------------------------------- CRC-32 algebra
+uint32_t crc_mulmod(uint32_t a, uint32_t b) {
+	uint32_t prod = 0;
+	for (int i = 0; i < 32; ++i) {
+		prod ^= (a & 0x80000000u) ? b : 0u;
+		a <<= 1;
+		b = (b >> 1) ^ ((b & 1u) ? kCrcPolyReflected : 0u);
+	}
+	return prod;
+}
+
+uint32_t crc_xpow_bytes(uint64_t nbytes) {
+	uint32_t acc = 0x80000000u;  // the polynomial 1
+	uint32_t sq = 0x00800000u;   // x^8
+	for (; nbytes; nbytes >>= 1) {
+		if (nbytes & 1) acc = crc_mulmod(acc, sq);
+		sq = crc_mulmod(sq, sq);
+	}
+	return acc;
+}
+
+// CRC(A||B) = CRC(A)*x^(8|B|) xor CRC(B)  (crcutil gf_util.h:92-105 "Concatenate")
+uint32_t crc_combine(uint32_t crc1, uint32_t crc2, uint64_t len2) {
+	return crc_mulmod(crc1, crc_xpow_bytes(len2)) ^ crc2;
+}
+
+// mycrc32(0, n zero bytes): the affine constant of the CRC for length n.
+// = mycrc32_zeroblock(0, n) = combine(0xFFFFFFFF, 0xFFFFFFFF, n)  (crc.h:27)
+uint32_t crc_of_zeros(uint64_t nbytes) { return crc_combine(0xFFFFFFFFu, 0xFFFFFFFFu, nbytes); }
+
+void crc_make_tables(uint32_t tab[4][256]) {
+	for (uint32_t v = 0; v < 256; ++v) {
+		uint32_t c = v;
+		for (int b = 0; b < 8; ++b) c = (c >> 1) ^ ((c & 1u) ? kCrcPolyReflected : 0u);
+		tab[0][v] = c;
+	}
+	for (int t = 1; t < 4; ++t)
+		for (uint32_t v = 0; v < 256; ++v) tab[t][v] = (tab[t - 1][v] >> 8) ^ tab[0][tab[t - 1][v] & 0xff];
+}
+
+}  // namespace lz
+
+// =============================================================== C ABI: scalar / matrix entry points
+extern "C" {
+
+unsigned char gf_mul(unsigned char a, unsigned char b) { return lz::gf_mul_host(a, b); }
+unsigned char gf_inv(unsigned char a) { return lz::gf_inv_host(a); }
+
+// src/common/galois_field_isal.cc:53-69 semantics: `m` is the TOTAL row count (k identity rows +
+// parity rows); parity row r is the geometric progression of ratio 2^r.
+void gf_gen_rs_matrix(unsigned char *a, int m, int k) {
+	std::memset(a, 0, static_cast<size_t>(m) * k);
+	for (int d = 0; d < k && d < m; ++d) a[d * k + d] = 1;
+	uint8_t ratio = 1;
+	for (int row = k; row < m; ++row) {
+		uint8_t term = 1;
+		for (int col = 0; col < k; ++col) {
+			a[row * k + col] = term;
+			term = lz::gf_mul_host(term, ratio);
+		}
+		ratio = lz::gf_mul_host(ratio, 2);
+	}
+}
+
+// src/common/galois_field_isal.cc:71-85 semantics: parity entries are 1/(row xor col).
+void gf_gen_cauchy1_matrix(unsigned char *a, int m, int k) {
+	std::memset(a, 0, static_cast<size_t>(m) * k);
+	for (int d = 0; d < k && d < m; ++d) a[d * k + d] = 1;
+	for (int row = k; row < m; ++row)
+		for (int col = 0; col < k; ++col) a[row * k + col] = lz::gf_inv_host(static_cast<uint8_t>(row ^ col));
+}
+
+// Gauss-Jordan inverse over GF(2^8); 0 on success, -1 when singular; `in` is clobbered like the
+// reference's (galois_field_isal.cc:87-139).  The inverse of a non-singular matrix is unique, so the
+// elimination order does not influence the result.
+int gf_invert_matrix(unsigned char *in, unsigned char *out, const int n) {
+	for (int i = 0; i < n * n; ++i) out[i] = 0;
+	for (int i = 0; i < n; ++i) out[i * n + i] = 1;
+	for (int col = 0; col < n; ++col) {
+		int piv = col;
+		while (piv < n && in[piv * n + col] == 0) ++piv;
+		if (piv == n) return -1;
+		if (piv != col) {
+			for (int c = 0; c < n; ++c) {
+				unsigned char t = in[col * n + c]; in[col * n + c] = in[piv * n + c]; in[piv * n + c] = t;
+				t = out[col * n + c]; out[col * n + c] = out[piv * n + c]; out[piv * n + c] = t;
+			}
+		}
+		const uint8_t scale = lz::gf_inv_host(in[col * n + col]);
+		for (int c = 0; c < n; ++c) {
+			in[col * n + c] = lz::gf_mul_host(in[col * n + c], scale);
+			out[col * n + c] = lz::gf_mul_host(out[col * n + c], scale);
+		}
+		for (int row = 0; row < n; ++row) {
+			const uint8_t f = in[row * n + col];
+			if (row == col || f == 0) continue;
+			for (int c = 0; c < n; ++c) {
+				in[row * n + c] ^= lz::gf_mul_host(f, in[col * n + c]);
+				out[row * n + c] ^= lz::gf_mul_host(f, out[col * n + c]);
+			}
+		}
+	}
+	return 0;
+}
+
+// 32-byte ISA-L table of coefficient c: products with the 16 low-nibble values, then with the 16
+// high-nibble values (galois_field_isal.cc:143-244 layout).
+void gf_vect_mul_init(unsigned char c, unsigned char *tbl) {
+	for (int nib = 0; nib < 16; ++nib) {
+		tbl[nib] = lz::gf_mul_host(c, static_cast<uint8_t>(nib));
+		tbl[16 + nib] = lz::gf_mul_host(c, static_cast<uint8_t>(nib << 4));
+	}
+}
+
+void ec_init_tables(int k, int rows, unsigned char *a, unsigned char *gftbls) {
+	const int total = k * rows;
+	for (int i = 0; i < total; ++i) gf_vect_mul_init(a[i], gftbls + 32 * static_cast<size_t>(i));
+}
+
+int lzgpu_rs_generator(int k, int m, uint8_t *matrix) { return lz::rs_generator(k, m, matrix); }
+
+int lzgpu_rs_recovery_matrix(int k, int m, const uint8_t *erased, const uint8_t *wanted, uint8_t *matrix) {
+	return lz::rs_recovery_matrix(k, m, erased, wanted, matrix, nullptr);
+}
+
+uint32_t lzgpu_mycrc32_combine(uint32_t crc1, uint32_t crc2, uint32_t leng2) {
+	return lz::crc_combine(crc1, crc2, leng2);
+}
+uint32_t lzgpu_mycrc32_zeroblock(uint32_t crc, uint32_t zeros) {
+	return lz::crc_combine(crc ^ 0xFFFFFFFFu, 0xFFFFFFFFu, zeros);
+}
+uint32_t lzgpu_mycrc32_xorblocks(uint32_t crc, uint32_t c1, uint32_t c2, uint32_t leng) {
+	return c1 ^ c2 ^ lzgpu_mycrc32_zeroblock(crc, leng);
+}
+
+// ---------------------------------------------------------------- goals & geometry
+int lzgpu_goal_valid(const lzgpu_goal *g) {
+	if (!g) return 0;
+	if (g->kind == 0) return g->k >= 2 && g->k <= 9 && g->m == 1;                 // slice_traits.h:99-100
+	if (g->kind == 1) return g->k >= 2 && g->k <= 32 && g->m >= 1 && g->m <= 32;  // slice_traits.h:143-146
+	return 0;
+}
+
+int lzgpu_goal_parse(const char *text, lzgpu_goal *out) {
+	if (!text || !out) return LZGPU_ERR_ARG;
+	while (*text && std::isspace(static_cast<unsigned char>(*text))) ++text;
+	if (*text == '$') ++text;
+	lzgpu_goal g{};
+	int consumed = 0;
+	if (std::sscanf(text, "xor%d%n", &g.k, &consumed) == 1 && consumed > 0) {
+		g.kind = 0;
+		g.m = 1;
+	} else if (std::sscanf(text, "ec ( %d , %d )%n", &g.k, &g.m, &consumed) == 2 && consumed > 0) {
+		g.kind = 1;
+	} else {
+		return LZGPU_ERR_ARG;
+	}
+	for (const char *p = text + consumed; *p; ++p)
+		if (!std::isspace(static_cast<unsigned char>(*p))) return LZGPU_ERR_ARG;
+	if (!lzgpu_goal_valid(&g)) return LZGPU_ERR_ARG;
+	*out = g;
+	return LZGPU_OK;
+}
+
+int lzgpu_goal_slice_type(const lzgpu_goal *g) {
+	if (!lzgpu_goal_valid(g)) return LZGPU_ERR_ARG;
+	return g->kind == 0 ? 2 + (g->k - 2) : 10 + 32 * (g->k - 2) + (g->m - 1);
+}
+
+int lzgpu_goal_from_slice_type(int t, lzgpu_goal *out) {
+	if (!out) return LZGPU_ERR_ARG;
+	if (t >= 2 && t <= 9) { *out = lzgpu_goal{0, t, 1}; return LZGPU_OK; }
+	if (t >= 10 && t < 10 + 31 * 32) { *out = lzgpu_goal{1, 2 + (t - 10) / 32, 1 + (t - 10) % 32}; return LZGPU_OK; }
+	return LZGPU_ERR_ARG;
+}
+
+int lzgpu_ref_part_index(const lzgpu_goal *g, int part) {
+	if (!lzgpu_goal_valid(g) || part < 0 || part >= g->k + g->m) return LZGPU_ERR_ARG;
+	if (g->kind == 0) return part < g->k ? part + 1 : 0;  // xor: parity is part 0, data 1..N
+	return part;
+}
+
+int lzgpu_chunk_part_id(const lzgpu_goal *g, int part) {
+	const int ref_part = lzgpu_ref_part_index(g, part);
+	if (ref_part < 0) return ref_part;
+	return lzgpu_goal_slice_type(g) * 64 + ref_part;
+}
+
+uint32_t lzgpu_part_blocks(const lzgpu_goal *g, int part, uint32_t nb) {
+	const uint32_t k = static_cast<uint32_t>(g->k);
+	const uint32_t idx = part < g->k ? static_cast<uint32_t>(part) : 0u;  // parity counts like data part 0
+	return (nb + (k - idx - 1)) / k;
+}
+
+uint32_t lzgpu_part_length(const lzgpu_goal *g, int part, uint32_t chunk_length) {
+	const uint32_t k = static_cast<uint32_t>(g->k), B = LZGPU_BLOCK_SIZE;
+	const uint32_t idx = part < g->k ? static_cast<uint32_t>(part) : 0u;
+	const uint32_t whole = chunk_length / (k * B);
+	const uint32_t tail = chunk_length - whole * k * B;
+	uint32_t mine = tail > idx * B ? tail - idx * B : 0;
+	if (mine > B) mine = B;
+	return whole * B + mine;
+}
+
+const char *lzgpu_version(void) { return "lizardfs_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

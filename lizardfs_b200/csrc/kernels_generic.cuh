@@ -1,0 +1,203 @@
+// kernels_generic.cuh — shape-generic kernels behind the reference-shaped entry points
+// (ec_encode_data, ReedSolomon::recover on arbitrary fragments, blockXor, mycrc32 of any length)
+// and the fall-back route of the batched API for goals the fused kernels do not specialise.
+// HBM-bound byte/integer work: 16-byte coalesced accesses, grid sized from the SM count, no tensor cores.
+#pragma once
+#include "device_math.cuh"
+
+namespace lzd {
+
+constexpr int kMaxSrc = 32;
+constexpr int kDotDests = 4;  // dests produced per pass (accumulators live in registers)
+
+// Addressing of one GF dot-product pass.  A "unit" is 16 bytes.  Unit u decomposes into
+// (chunk c, block s, offset o) with units_per_block units per block and blocks_per_chunk blocks;
+//   src_j = src[j] + c*src_chunk_stride + s*src_block_stride + 16*o      (valid iff s*valid_k + j < valid_nb or valid_nb == 0)
+//   dst_r = dst[r] + c*dst_chunk_stride + s*dst_block_stride + 16*o
+// Chunk-order encode: src[j] = data + j*64K, src_block_stride = k*64K, valid_k = k, valid_nb = nb
+// (absent blocks of the last stripe are zero: reference chunk_writer.cc:97-108,377, reed_solomon.h:104-107).
+// Part-major recover / plain fragments: src_block_stride = 64K (or the fragment length), valid_nb = 0.
+struct DotArgs {
+	const uint8_t *src[kMaxSrc];
+	uint8_t *dst[kDotDests];
+	const CoefPlanes *coef;  // [n_dst][n_src]
+	unsigned long long total_units;
+	unsigned long long src_chunk_stride, src_block_stride;
+	unsigned long long dst_chunk_stride, dst_block_stride;
+	unsigned int units_per_block, blocks_per_chunk;
+	unsigned int n_src, n_dst;
+	unsigned int valid_k, valid_nb;
+	unsigned int pure_xor;  // every coefficient is 1 (xorN goals / parity row 0): skip the multiply
+};
+
+template <int ND>
+__global__ void __launch_bounds__(256) gf_dot_kernel(const DotArgs a) {
+	extern __shared__ CoefPlanes s_coef[];  // [ND][n_src]
+	for (unsigned i = threadIdx.x; i < ND * a.n_src * 8; i += blockDim.x)
+		reinterpret_cast<uint32_t *>(s_coef)[i] = reinterpret_cast<const uint32_t *>(a.coef)[i];
+	__syncthreads();
+
+	const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+	for (unsigned long long u = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	     u < a.total_units; u += stride) {
+		const unsigned o = static_cast<unsigned>(u % a.units_per_block);
+		const unsigned long long blk = u / a.units_per_block;
+		const unsigned s = static_cast<unsigned>(blk % a.blocks_per_chunk);
+		const unsigned long long c = blk / a.blocks_per_chunk;
+		const unsigned long long src_off = c * a.src_chunk_stride + s * a.src_block_stride + 16ull * o;
+		unsigned n_valid = a.n_src;
+		if (a.valid_nb) {
+			const unsigned first = s * a.valid_k;
+			n_valid = first >= a.valid_nb ? 0u : min(a.n_src, a.valid_nb - first);
+		}
+		uint32_t acc[ND][4];
+#pragma unroll
+		for (int d = 0; d < ND; ++d) acc[d][0] = acc[d][1] = acc[d][2] = acc[d][3] = 0;
+		for (unsigned j = 0; j < n_valid; ++j) {
+			const uint4 v = ld_stream(reinterpret_cast<const uint4 *>(a.src[j] + src_off));
+			if (a.pure_xor) {
+#pragma unroll
+				for (int d = 0; d < ND; ++d) { acc[d][0] ^= v.x; acc[d][1] ^= v.y; acc[d][2] ^= v.z; acc[d][3] ^= v.w; }
+			} else {
+#pragma unroll
+				for (int d = 0; d < ND; ++d) {
+					const CoefPlanes &cp = s_coef[d * a.n_src + j];
+					acc[d][0] = gf_mac(acc[d][0], v.x, cp);
+					acc[d][1] = gf_mac(acc[d][1], v.y, cp);
+					acc[d][2] = gf_mac(acc[d][2], v.z, cp);
+					acc[d][3] = gf_mac(acc[d][3], v.w, cp);
+				}
+			}
+		}
+		const unsigned long long dst_off = c * a.dst_chunk_stride + s * a.dst_block_stride + 16ull * o;
+#pragma unroll
+		for (int d = 0; d < ND; ++d)
+			st_stream(reinterpret_cast<uint4 *>(a.dst[d] + dst_off), make_uint4(acc[d][0], acc[d][1], acc[d][2], acc[d][3]));
+	}
+}
+
+// dest ^= source (reference block_xor.cc:47-63), n16 16-byte units; tail bytes by the last threads
+__global__ void __launch_bounds__(256) xor_inplace_kernel(uint8_t *dest, const uint8_t *src, unsigned long long n16,
+                                                           unsigned tail_bytes) {
+	const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+	const unsigned long long t0 = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	for (unsigned long long u = t0; u < n16; u += stride) {
+		uint4 d = reinterpret_cast<const uint4 *>(dest)[u];
+		const uint4 s = ld_stream(reinterpret_cast<const uint4 *>(src) + u);
+		d.x ^= s.x; d.y ^= s.y; d.z ^= s.z; d.w ^= s.w;
+		reinterpret_cast<uint4 *>(dest)[u] = d;
+	}
+	if (t0 < tail_bytes) dest[16 * n16 + t0] ^= src[16 * n16 + t0];
+}
+
+// Block-interleave copy between part-major and chunk order (reference chunk_read_planner.h:41-58:
+// chunk block b <-> part b % k, index b / k).  One thread per 16-byte unit of the chunk image.
+struct GatherArgs {
+	const uint8_t *part[kMaxSrc];  // k data parts (already holding recovered data where needed)
+	uint8_t *chunk_out;
+	unsigned long long part_stride, chunk_out_stride, total_units;
+	unsigned int k, nb;
+};
+
+__global__ void __launch_bounds__(256) parts_to_chunk_kernel(const GatherArgs a) {
+	const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+	for (unsigned long long u = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	     u < a.total_units; u += stride) {
+		const unsigned o = static_cast<unsigned>(u & 4095u);
+		const unsigned long long blk = u >> 12;
+		const unsigned b = static_cast<unsigned>(blk % a.nb);
+		const unsigned long long c = blk / a.nb;
+		const uint4 v = ld_stream(reinterpret_cast<const uint4 *>(a.part[b % a.k] + c * a.part_stride +
+		                                                           static_cast<unsigned long long>(b / a.k) * 65536ull + 16ull * o));
+		st_stream(reinterpret_cast<uint4 *>(a.chunk_out + c * a.chunk_out_stride + static_cast<unsigned long long>(b) * 65536ull + 16ull * o), v);
+	}
+}
+
+// Linear CRC of many equally sized blocks, one warp per block, table driven (slicing by 4).
+// The message is virtually left-padded with zero words to 32*wpl words (leading zeros do not change
+// the linear CRC), lane L owns virtual words [L*wpl, (L+1)*wpl); lane partials are merged with the
+// concatenation identity crc(A||B) = crc(A)*x^(8|B|) + crc(B) (reference crc.cc:58-60,
+// crcutil gf_util.h:92-105) as a 5-level tree whose multipliers x^(32*wpl*2^i) come from the host.
+// out[b] = lin(block b) xor affine  (affine = mycrc32(0, zeros, len)).
+struct CrcArgs {
+	const uint8_t *base;
+	uint32_t *out;
+	const uint32_t *tables;  // 4*256 slicing tables in global memory
+	unsigned long long n_blocks, blocks_per_chunk, chunk_stride, block_stride;
+	unsigned long long out_chunk_stride;  // in uint32 elements; out index = c*out_chunk_stride + (b % blocks_per_chunk)
+	unsigned int len;             // bytes per block
+	unsigned int wpl;             // virtual words per lane
+	unsigned int pad_words;       // 32*wpl - len/4
+	uint32_t tree_mult[5];        // x^(32*wpl*2^i) mod P
+	uint32_t affine;
+};
+
+__global__ void __launch_bounds__(256) crc_blocks_kernel(const CrcArgs a) {
+	__shared__ uint32_t s_tab[1024];
+	for (unsigned i = threadIdx.x; i < 1024; i += blockDim.x) s_tab[i] = a.tables[i];
+	__syncthreads();
+	const unsigned lane = threadIdx.x & 31;
+	const unsigned long long warp0 = (static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+	const unsigned long long n_warps = (static_cast<unsigned long long>(gridDim.x) * blockDim.x) >> 5;
+	const unsigned n_words = a.len >> 2;
+	for (unsigned long long b = warp0; b < a.n_blocks; b += n_warps) {
+		const unsigned long long c = b / a.blocks_per_chunk, bi = b % a.blocks_per_chunk;
+		const uint8_t *blk = a.base + c * a.chunk_stride + bi * a.block_stride;
+		const uint32_t *w = reinterpret_cast<const uint32_t *>(blk);
+		uint32_t st = 0;
+		const long long first = static_cast<long long>(lane) * a.wpl - a.pad_words;
+		for (unsigned i = 0; i < a.wpl; ++i) {
+			const long long idx = first + i;
+			const uint32_t v = idx >= 0 ? __ldg(w + idx) : 0u;
+			st = crc_step_word(st, v, s_tab);
+		}
+		// tree merge: after level i, lanes that are multiples of 2^(i+1) hold the CRC of 2^(i+1) segments
+#pragma unroll
+		for (int i = 0; i < 5; ++i) {
+			const uint32_t right = __shfl_down_sync(0xffffffffu, st, 1u << i);
+			st = crc_mulmod(st, a.tree_mult[i]) ^ right;
+		}
+		if (lane == 0) {
+			for (unsigned t = n_words * 4; t < a.len; ++t) st = crc_step_byte(st, blk[t], s_tab);
+			a.out[c * a.out_chunk_stride + bi] = st ^ a.affine;
+		}
+	}
+	(void)n_words;
+}
+
+// Compare computed CRCs with stored ones; records the smallest mismatching index.
+// sparse_rule: a stored value of 0 is accepted when the computed CRC is that of an all-zero block
+// (reference crc.cc:235-243: stored crc 0 + empty block => mycrc32_zeroblock(0, 64 KiB)).
+__global__ void __launch_bounds__(256) crc_compare_kernel(const uint32_t *computed, const uint32_t *stored,
+                                                          unsigned long long n, uint32_t zero_block_crc,
+                                                          int sparse_rule, int big_endian_stored,
+                                                          unsigned long long *first_bad) {
+	const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+	for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+		uint32_t s = stored[i];
+		if (big_endian_stored) s = __byte_perm(s, 0, 0x0123);
+		const uint32_t c = computed[i];
+		const bool ok = (s == c) || (sparse_rule && s == 0 && c == zero_block_crc);
+		if (!ok) atomicMin(first_bad, i);
+	}
+}
+
+// splitmix64 counter stream: 8-byte word w of chunk c = mix(seed + ((c<<23) + w + 1) * golden)
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256) fill_chunks_kernel(uint8_t *base, unsigned long long chunk_stride,
+                                                          unsigned long long words_per_chunk, unsigned long long total_words,
+                                                          unsigned long long seed, unsigned long long first_chunk) {
+	const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+	for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_words; i += stride) {
+		const unsigned long long c = i / words_per_chunk, w = i % words_per_chunk;
+		const unsigned long long z = seed + (((first_chunk + c) << 23) + w + 1ull) * 0x9E3779B97F4A7C15ull;
+		reinterpret_cast<unsigned long long *>(base + c * chunk_stride)[w] = splitmix64(z);
+	}
+}
+
+}  // namespace lzd

@@ -1,0 +1,231 @@
+"""GPU parity tests of the batched chunk API (encode + per-block CRC, degraded-read recover with CRC
+verification, scrub) against the oracle, the golden vectors of the compiled reference, and
+size-independent properties at full chunk size."""
+import hashlib
+import itertools
+import json
+import os
+
+import numpy as np
+import pytest
+
+import lizardfs_b200 as L
+from tests import _oracle as O
+
+pytestmark = pytest.mark.gpu
+BLOCK = 65536
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "vectors.json")))
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = L.Engine(0)
+    yield e
+    e.close()
+
+
+def rnd(shape, seed):
+    return np.random.default_rng(seed).integers(0, 256, size=shape, dtype=np.uint8)
+
+
+def all_parts(data, parity, k):
+    """[n, chunk] data + [n, m, pb*64K] parity -> list of k+m arrays [n, pb*64K]"""
+    n = data.shape[0]
+    per = [O.split_parts(data[c], k)[0] for c in range(n)]
+    parts = [np.stack([per[c][j] for c in range(n)]) for j in range(k)]
+    return parts + [np.ascontiguousarray(parity[:, r]) for r in range(parity.shape[1])]
+
+
+@pytest.mark.parametrize("case", GOLD["cases"], ids=lambda c: c["goal"])
+def test_encode_matches_reference_golden(eng, oracle, case):
+    goal = L.SliceType(case["goal"])
+    chunk = O.fill_chunk(oracle, case["chunk_len"], case["seed"], 0)
+    stride = case["nb"] * BLOCK
+    buf = np.zeros((1, stride), dtype=np.uint8)
+    buf[0, : case["chunk_len"]] = chunk
+    parity, crc = eng.encode_chunks(goal, buf, chunk_len=case["chunk_len"])
+    assert crc[0].tolist() == case["crc"]
+    assert [hashlib.sha256(parity[0, r].tobytes()).hexdigest() for r in range(goal.m)] == case["parity_sha256"]
+
+
+@pytest.mark.parametrize("text,nblocks,n_chunks", [("xor2", 5, 3), ("xor3", 8, 2), ("ec(3,2)", 10, 3), ("ec(5,3)", 11, 2),
+                                                   ("ec(8,2)", 17, 3), ("ec(8,2)", 128, 2), ("ec(8,4)", 24, 2), ("ec(4,5)", 9, 1), ("ec(16,3)", 33, 1)])
+def test_encode_batch_vs_oracle(eng, oracle, text, nblocks, n_chunks):
+    goal = L.SliceType(text)
+    data = rnd((n_chunks, nblocks * BLOCK), hash(text) & 0xffff)
+    data[0, :BLOCK] = 0            # an all-zero block: CRC 0xD7978EEB
+    data[-1, -BLOCK:] = 0xFF       # an all-ones block
+    parity, crc = eng.encode_chunks(goal, data)
+    for c in range(n_chunks):
+        p_ref, c_ref = oracle.encode_chunk(goal.kind, goal.k, goal.m, data[c])
+        assert (parity[c] == p_ref).all()
+        assert (crc[c] == c_ref).all()
+    assert crc[0, 0] == 0xD7978EEB
+
+
+def test_encode_partial_last_block(eng, oracle):
+    goal = L.SliceType("ec(3,2)")
+    clen = 7 * BLOCK + 12345
+    nb = 8
+    buf = rnd((2, nb * BLOCK), 4)     # garbage beyond chunk_len must be ignored (treated as zeros)
+    parity, crc = eng.encode_chunks(goal, buf, chunk_len=clen)
+    for c in range(2):
+        p_ref, c_ref = oracle.encode_chunk(1, 3, 2, buf[c, :clen])
+        assert (parity[c] == p_ref).all() and (crc[c] == c_ref).all()
+
+
+def test_encode_full_size_chunk_ec82(eng, oracle, ref):
+    """BASELINE config 3 shape: ec(8,2) on a full 64 MiB chunk, bit-exact vs the (compiled) reference."""
+    goal = L.SliceType("ec(8,2)")
+    data = O.fill_chunk(oracle, 64 << 20, 1, 0).reshape(1, -1)
+    parity, crc = eng.encode_chunks(goal, data)
+    checker = ref if ref is not None else oracle
+    p_ref, c_ref = checker.encode_chunk(1, 8, 2, data[0])
+    assert (parity[0] == p_ref).all() and (crc[0] == c_ref).all()
+    assert crc[0, 0] == 0x7173879a and crc[0, 1023] == 0xfa2e261f          # SURVEY §8c known answers
+    assert parity[0, 0, :8].tobytes().hex() == "183a4cd28cd5bfa7" and parity[0, 1, :8].tobytes().hex() == "a1a590174c2d64f0"
+    assert crc[0, 1024] == 0x8c7def0b and crc[0, 1024 + 128] == 0x577d57e4
+
+
+def test_encode_full_size_ec32_tail_stripe(eng, oracle):
+    """BASELINE config 2 shape: ec(3,2), 1024 blocks -> 342/341/341-block parts, last stripe has 1 real block."""
+    goal = L.SliceType("ec(3,2)")
+    data = O.fill_chunk(oracle, 64 << 20, 2, 5).reshape(1, -1)
+    parity, crc = eng.encode_chunks(goal, data)
+    p_ref, c_ref = oracle.encode_chunk(1, 3, 2, data[0])
+    assert parity.shape[2] == 342 * BLOCK
+    assert (parity[0] == p_ref).all() and (crc[0] == c_ref).all()
+
+
+def test_linearity_properties_full_batch(eng):
+    """Size-independent properties on a larger batch (no oracle pass needed):
+    CRC(P) = xor of the data CRCs (+ the zero-block constant for an even count), and parity of the
+    xor of two inputs = xor of the parities."""
+    goal = L.SliceType("ec(8,2)")
+    a, b = rnd((4, 256 * BLOCK), 21), rnd((4, 256 * BLOCK), 22)
+    pa, ca = eng.encode_chunks(goal, a)
+    pb_, cb = eng.encode_chunks(goal, b)
+    px, cx = eng.encode_chunks(goal, a ^ b)
+    assert (px == (pa ^ pb_)).all()
+    nb = 256
+    stripes = ca[:, :nb].reshape(4, 32, 8)
+    crc_p = np.bitwise_xor.reduce(stripes, axis=2)  # 8 blocks: the affine constants cancel pairwise ... plus one
+    assert (ca[:, nb:nb + 32] == (crc_p ^ 0xD7978EEB)).all()
+    z = np.uint32(0xD7978EEB)
+    assert (cx[:, :nb] == (ca[:, :nb] ^ cb[:, :nb] ^ z)).all()  # mycrc32_xorblocks identity, crc.h:29
+
+
+@pytest.mark.parametrize("text,nblocks", [("ec(8,2)", 19), ("ec(3,2)", 10), ("ec(5,3)", 11), ("ec(8,4)", 16), ("xor2", 5), ("xor3", 7)])
+def test_recover_all_patterns(eng, oracle, text, nblocks):
+    goal = L.SliceType(text)
+    k, m = goal.k, goal.m
+    data = rnd((2, nblocks * BLOCK), 31)
+    parity, crc = eng.encode_chunks(goal, data)
+    parts = all_parts(data, parity, k)
+    pb = parts[0].shape[1] // BLOCK
+    patterns = [p for r in range(1, m + 1) for p in itertools.combinations(range(k + m), r)]
+    if len(patterns) > 40:
+        rng = np.random.default_rng(1)
+        patterns = [patterns[i] for i in rng.choice(len(patterns), size=40, replace=False)]
+    if text == "ec(8,2)":
+        patterns = [p for p in itertools.combinations(range(8), 2)]  # all 28 data pairs (BASELINE config 4)
+    for lost in patterns:
+        avail = [None if i in lost else parts[i] for i in range(k + m)]
+        want = [1 if i in lost else 0 for i in range(k + m)]
+        out, img = eng.recover_chunks(goal, nblocks, avail, want=want, chunk_image=True)
+        for i in lost:
+            assert (out[i] == parts[i]).all(), (text, lost, i)
+        assert (img == data).all()
+        rc, o_ref, _ = oracle.recover_chunk(goal.kind, k, m, [None if a is None else a[0] for a in avail], None, want, pb)
+        for i in lost:
+            assert (out[i][0] == o_ref[i]).all()
+
+
+def test_recover_verifies_crc(eng):
+    goal = L.SliceType("ec(8,2)")
+    nblocks = 24
+    data = rnd((3, nblocks * BLOCK), 41)
+    parity, crc = eng.encode_chunks(goal, data)
+    parts = all_parts(data, parity, 8)
+    pb = 3
+    # per-part stored CRCs from the encode output: data block b -> part b%8 index b//8
+    pcrc = [np.ascontiguousarray(crc[:, :nblocks].reshape(3, pb, 8)[:, :, j]) for j in range(8)]
+    pcrc += [np.ascontiguousarray(crc[:, nblocks + r * pb: nblocks + (r + 1) * pb]) for r in range(2)]
+    avail = [None if i in (1, 4) else parts[i] for i in range(10)]
+    acrc = [None if i in (1, 4) else pcrc[i] for i in range(10)]
+    out, _ = eng.recover_chunks(goal, nblocks, avail, part_crc=acrc)
+    assert (out[1] == parts[1]).all() and (out[4] == parts[4]).all()
+    bad = [None if a is None else a.copy() for a in avail]
+    bad[6][2, BLOCK + 99] ^= 1     # chunk 2, part 6, block 1
+    with pytest.raises(L.ChunkCrcError) as ei:
+        eng.recover_chunks(goal, nblocks, bad, part_crc=acrc)
+    assert ei.value.where == (2, 6, 1)
+    with pytest.raises(L.LzGpuError):  # fewer than k parts
+        eng.recover_chunks(goal, nblocks, [None, None, None] + parts[3:], want=[1, 1, 1] + [0] * 7)
+
+
+def test_recover_parity_rebuild(eng):
+    """Chunkserver replication rebuilds parity parts too (ECReadPlan::RecoverParity, ec_read_plan.h:38-76)."""
+    goal = L.SliceType("ec(5,3)")
+    data = rnd((2, 15 * BLOCK), 51)
+    parity, _ = eng.encode_chunks(goal, data)
+    parts = all_parts(data, parity, 5)
+    avail = [parts[0], None, parts[2], parts[3], parts[4], None, parts[6], None]
+    out, _ = eng.recover_chunks(goal, 15, avail, want=[0, 1, 0, 0, 0, 1, 0, 1])
+    assert (out[1] == parts[1]).all() and (out[5] == parts[5]).all() and (out[7] == parts[7]).all()
+
+
+@pytest.mark.parametrize("block_len", [1, 4, 5, 4096, 65535, 65536])
+def test_crc_blocks_and_scrub(eng, oracle, block_len):
+    n = 37
+    data = rnd(n * block_len, block_len)
+    got = eng.crc_blocks(data, block_len)
+    want = [oracle.crc32(0, data[i * block_len:(i + 1) * block_len]) for i in range(n)]
+    assert got.tolist() == want
+    eng.verify_blocks(data, got, block_len)
+    stored = got.copy()
+    stored[20] ^= 0x10
+    with pytest.raises(L.ChunkCrcError) as ei:
+        eng.verify_blocks(data, stored, block_len)
+    assert ei.value.where == (20,)
+
+
+def test_scrub_interleaved_disk_format(eng, oracle):
+    """hdd_int_test (hddspacemgr.cc:2148-2210) over 4-byte big-endian CRC + 64 KiB records, incl. the sparse rule."""
+    n = 9
+    blocks = rnd((n, BLOCK), 61)
+    blocks[3] = 0
+    rec = np.zeros((n, 4 + BLOCK), dtype=np.uint8)
+    for i in range(n):
+        c = oracle.crc32(0, blocks[i])
+        rec[i, :4] = np.frombuffer(int(c).to_bytes(4, "big"), dtype=np.uint8)
+        rec[i, 4:] = blocks[i]
+    eng.verify_interleaved(rec)
+    rec[3, :4] = 0                 # sparse block: stored CRC 0 + all-zero data is accepted (crc.cc:235-243)
+    eng.verify_interleaved(rec)
+    rec[5, 1000] ^= 0x80
+    with pytest.raises(L.ChunkCrcError) as ei:
+        eng.verify_interleaved(rec)
+    assert ei.value.where == (5,)
+
+
+def test_device_resident_api_and_generator(eng, oracle):
+    goal = L.SliceType("ec(8,2)")
+    n, clen = 3, 32 * BLOCK
+    nb, pb = 32, 4
+    d_data = eng.dev_alloc(n * clen)
+    d_par = eng.dev_alloc(n * 2 * pb * BLOCK)
+    d_crc = eng.dev_alloc(n * (nb + 2 * pb) * 4)
+    eng.fill_chunks_dev(d_data, n, clen, clen, seed=12345, first_chunk=7)
+    eng.encode_chunks_dev(goal, n, clen, d_data, clen, d_par, 2 * pb * BLOCK, d_crc, nb + 2 * pb)
+    eng.sync()
+    data = eng.download(d_data, n * clen).reshape(n, clen)
+    for c in range(n):
+        assert (data[c] == O.fill_chunk(oracle, clen, 12345, 7 + c)).all()
+    parity = eng.download(d_par, n * 2 * pb * BLOCK).reshape(n, 2, pb * BLOCK)
+    crc = eng.download(d_crc, n * (nb + 2 * pb) * 4, dtype=np.uint32).reshape(n, -1)
+    for c in range(n):
+        p_ref, c_ref = oracle.encode_chunk(1, 8, 2, data[c])
+        assert (parity[c] == p_ref).all() and (crc[c] == c_ref).all()
+    for p in (d_data, d_par, d_crc):
+        eng.dev_free(p)

@@ -1,0 +1,143 @@
+"""Host-side logic of the product library (no GPU needed): GF matrices, ISA-L tables, recovery
+matrices, CRC algebra and goal geometry of liblzgpu.so, checked against the oracle (and through it
+the reference).  Mirrors src/common/reed_solomon_unittest.cc:252-319 (TestMatrix),
+goal_unittest.cc / chunk_part_type_unittest.cc for the id arithmetic."""
+import ctypes as C
+import itertools
+import json
+import os
+
+import numpy as np
+import pytest
+
+import lizardfs_b200 as L
+
+BLOCK = 65536
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "vectors.json")))
+
+
+def test_gf_mul_inv_all_pairs(oracle):
+    for a in range(256):
+        assert L.gf_inv(a) == oracle.gf_inv(a)
+        for b in range(0, 256, 7):
+            assert L.gf_mul(a, b) == oracle.gf_mul(a, b)
+
+
+@pytest.mark.parametrize("k,m", [(2, 1), (3, 2), (5, 3), (8, 2), (8, 4), (4, 5), (21, 4), (20, 4), (32, 3), (32, 32)])
+def test_generator_matrices(oracle, k, m):
+    assert (L.gf_gen_rs_matrix(k + m, k) == oracle.gen_rs_matrix(k + m, k)).all()
+    assert (L.gf_gen_cauchy1_matrix(k + m, k) == oracle.gen_cauchy1_matrix(k + m, k)).all()
+    cauchy = m >= 5 or (m == 4 and k > 20)
+    want = oracle.gen_cauchy1_matrix(k + m, k) if cauchy else oracle.gen_rs_matrix(k + m, k)
+    assert (L.ReedSolomon(k, m).generator() == want).all()
+    key = f"{k},{m}"
+    if key in GOLD["generator_parity_rows"]:
+        assert L.ReedSolomon(k, m).generator()[k:].tolist() == GOLD["generator_parity_rows"][key]
+
+
+def test_invert_and_tables(oracle):
+    rng = np.random.default_rng(3)
+    for n in [1, 2, 5, 8, 17, 32]:
+        for _ in range(5):
+            mat = rng.integers(0, 256, size=(n, n), dtype=np.uint8)
+            rc1, inv1 = L.gf_invert_matrix(mat)
+            rc2, inv2 = oracle.invert_matrix(mat)
+            assert rc1 == rc2
+            if rc1 == 0:
+                assert (inv1 == inv2).all()
+    singular = np.array([[1, 2], [1, 2]], dtype=np.uint8)
+    assert L.gf_invert_matrix(singular)[0] == -1 == oracle.invert_matrix(singular)[0]
+    # a zero pivot that needs the row swap (galois_field_isal.cc:103-124)
+    swap = np.array([[0, 1, 0], [1, 0, 0], [0, 0, 1]], dtype=np.uint8)
+    assert L.gf_invert_matrix(swap)[0] == 0 and (L.gf_invert_matrix(swap)[1] == oracle.invert_matrix(swap)[1]).all()
+    coeffs = rng.integers(0, 256, size=(4, 8), dtype=np.uint8)
+    assert (L.ec_init_tables(8, 4, coeffs) == oracle.init_tables(coeffs)).all()
+
+
+@pytest.mark.parametrize("k,m", [(4, 2), (8, 2), (3, 2), (5, 3), (8, 4), (4, 5)])
+def test_recovery_matrix_all_patterns(oracle, k, m):
+    """Every erasure pattern (TestMatrix, reed_solomon_unittest.cc:252-319) gives the oracle's rows."""
+    f = oracle.dll.lzo_rs_recovery_matrix
+    f.restype = C.c_int
+    rs = L.ReedSolomon(k, m)
+    for erased_idx in itertools.combinations(range(k + m), m):
+        erased = np.zeros(k + m, dtype=np.uint8)
+        erased[list(erased_idx)] = 1
+        for wanted in (erased, np.where(np.arange(k + m) < k, erased, 0).astype(np.uint8)):
+            if wanted.sum() == 0:
+                continue
+            want_rows = np.zeros((m, k), dtype=np.uint8)
+            rows = f(k, m, erased.ctypes.data_as(C.c_void_p), wanted.ctypes.data_as(C.c_void_p), want_rows.ctypes.data_as(C.c_void_p))
+            got = rs.recovery_matrix(erased, wanted)
+            assert got.shape[0] == rows and (got == want_rows[:rows]).all()
+
+
+def test_recovery_matrix_wide(oracle):
+    # k <= 32, m <= 3 and k <= 20, m = 4 are all invertible in the reference's sweep; sample the big ones
+    f = oracle.dll.lzo_rs_recovery_matrix
+    f.restype = C.c_int
+    rng = np.random.default_rng(9)
+    for k, m in [(32, 3), (20, 4), (21, 4), (32, 32), (17, 9)]:
+        rs = L.ReedSolomon(k, m)
+        for _ in range(20):
+            erased = np.zeros(k + m, dtype=np.uint8)
+            erased[rng.choice(k + m, size=m, replace=False)] = 1
+            want_rows = np.zeros((m, k), dtype=np.uint8)
+            rows = f(k, m, erased.ctypes.data_as(C.c_void_p), erased.ctypes.data_as(C.c_void_p), want_rows.ctypes.data_as(C.c_void_p))
+            got = rs.recovery_matrix(erased, erased)
+            assert got.shape[0] == rows == m and (got == want_rows).all()
+    with pytest.raises(L.LzGpuError):
+        L.ReedSolomon(4, 2).recovery_matrix([1, 0, 0, 0, 0, 0], [1, 0, 0, 0, 0, 0])  # only 1 erased, m = 2
+
+
+def test_crc_algebra(oracle):
+    assert L.mycrc32_zeroblock(0, BLOCK) == 0xD7978EEB
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        a, b = (int(x) for x in rng.integers(0, 2**32, size=2))
+        n = int(rng.integers(1, 1 << 27))
+        assert L.mycrc32_combine(a, b, n) == oracle.crc32_combine(a, b, n)
+        assert L.mycrc32_zeroblock(a, n) == oracle.crc32_zeroblock(a, n)
+        assert L.mycrc32_xorblocks(a, b, 77, n & 0xffff) == oracle.crc32_xorblocks(a, b, 77, n & 0xffff)
+    for a, b, n, want in GOLD["crc_combine"]:
+        assert L.mycrc32_combine(a, b, n) == want
+    z = np.zeros(BLOCK, dtype=np.uint8)
+    assert L.recompute_crc_if_block_empty(z, 0) == 0xD7978EEB
+    assert L.recompute_crc_if_block_empty(z, 5) == 5
+    z[100] = 1
+    assert L.recompute_crc_if_block_empty(z, 0) == 0
+
+
+def test_goal_parsing_and_ids():
+    g = L.SliceType("ec(8,2)")
+    assert (g.kind, g.k, g.m) == (1, 8, 2) and g.type_id() == 10 + 32 * 6 + 1
+    assert g.chunk_part_id(9) == 13001  # "ec(8,2):9" 
+    assert L.SliceType("$ec(3,2)").type_id() == 10 + 32 * 1 + 1
+    x = L.SliceType("$xor3")
+    assert (x.kind, x.k, x.m) == (0, 3, 1) and x.type_id() == 3
+    assert x.ref_part_index(3) == 0 and x.ref_part_index(0) == 1  # xor: parity is part 0 (slice_traits.h:98)
+    assert str(L.SliceType.from_id(203)) == "ec(8,2)" and str(L.SliceType.from_id(9)) == "xor9"
+    for bad in ["xor1", "xor10", "ec(1,1)", "ec(33,1)", "ec(2,0)", "ec(2,33)", "std", "ec(8,2)x", ""]:
+        with pytest.raises(ValueError):
+            L.SliceType(bad)
+    for k in range(2, 33):
+        for m in range(1, 33):
+            assert L.SliceType.from_id(L.SliceType(1, k, m).type_id()).k == k
+
+
+def test_geometry_matches_slice_traits(oracle):
+    fb, fl = oracle.dll.lzo_part_blocks, oracle.dll.lzo_part_length
+    fb.restype = fl.restype = C.c_int
+    for text in ["xor2", "xor3", "xor9", "ec(3,2)", "ec(5,3)", "ec(8,2)", "ec(8,4)", "ec(32,32)"]:
+        g = L.SliceType(text)
+        for nb in [1, 2, 3, 7, 100, 1023, 1024]:
+            for part in range(g.k + g.m):
+                j = part if part < g.k else -1
+                assert g.part_blocks(part, nb) == fb(g.k, j, nb)
+        for clen in [1, 65535, 65536, 65537, 3 * BLOCK + 17, 1 << 26, (1 << 26) - 1, 37 * (1 << 20) + BLOCK]:
+            for part in range(g.k + g.m):
+                j = part if part < g.k else -1
+                assert g.part_length(part, clen) == fl(g.k, j, clen)
+    # the numbers quoted in SURVEY.md §7: ec(3,2) parts hold 342/341/341 blocks, parity 342
+    g = L.SliceType("ec(3,2)")
+    assert [g.part_blocks(p) for p in range(5)] == [342, 341, 341, 342, 342]
