@@ -222,8 +222,12 @@ def main():
     d_data = torch.empty(T * CHUNK, dtype=torch.uint8, device=dev)
     d_par = torch.empty(T * par_stride, dtype=torch.uint8, device=dev)
     d_crc = torch.empty(T * crc_stride, dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream(dev)
+    # a dedicated non-default stream: handle 0 (torch's legacy default stream) would make the library
+    # pick its own stream and the CUDA events below would not bracket the kernels
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
+    assert sptr != 0
     eng.fill_chunks_dev(d_data.data_ptr(), T, CHUNK, CHUNK, seed=12345, first_chunk=rank * T, stream=sptr)
 
     def step():

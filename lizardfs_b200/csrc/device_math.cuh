@@ -19,7 +19,9 @@ constexpr uint32_t kCrcZeroBlock64K = 0xD7978EEBu;  // mycrc32(0, 65536 zero byt
 // multiply each of the 4 bytes by 2 (x^8 = x^4+x^3+x^2+1, reference galois_coeff.h:30-32)
 __device__ __forceinline__ uint32_t gf_x2(uint32_t v) {
 	const uint32_t hi = v & 0x80808080u;
-	return ((v ^ hi) << 1) ^ ((hi >> 7) * 0x1du);
+	// (hi >> 7) * 0x1d without the shift: hi * 0x1d is a multiple of 128, so the high half of
+	// hi * (0x1d << 25) is exactly (hi * 0x1d) >> 7  (one IMAD.HI on the otherwise idle FMA pipe)
+	return ((v ^ hi) << 1) ^ __umulhi(hi, 0x3A000000u);
 }
 
 // One coefficient prepared for the bit-plane product: plane[b] = c * 2^b in GF(2^8), each stored

@@ -1,10 +1,205 @@
-// fused.cu — placeholder hooks (the TMA-streamed fused kernels land here)
+// fused.cu — host side of the TMA-streamed fused kernels (fused_kernel.cuh): tensor-map creation,
+// work-unit geometry, launch.  Returns LZGPU_NOT_HANDLED for shapes the fused path does not cover
+// (engine.cu then uses the generic kernels).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
 #include "engine_internal.h"
-int lz_fused_init(lzgpu_ctx *) { return LZGPU_OK; }
-void lz_fused_destroy(lzgpu_ctx *) {}
-int lz_fused_encode(lzgpu_ctx *, const lzgpu_goal *, uint32_t, uint32_t, const void *, size_t, void *, size_t, void *, size_t, cudaStream_t) {
+#include "fused_kernel.cuh"
+#include "host_math.h"
+
+using namespace lzd;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct FusedState {
+	EncodeTiledFn encode_tiled = nullptr;
+	uint32_t qmult[4];
+	int max_smem = 0;
+	bool disabled = false;
+};
+
+// x^n mod P for a possibly negative n (x has multiplicative order dividing 2^32 - 1)
+static uint32_t crc_xpow_bits_signed(long long n) {
+	const long long ord = 0xFFFFFFFFll;
+	n %= ord;
+	if (n < 0) n += ord;
+	uint32_t acc = 0x80000000u, sq = 0x40000000u;  // 1, x
+	for (; n; n >>= 1) {
+		if (n & 1) acc = lz::crc_mulmod(acc, sq);
+		sq = lz::crc_mulmod(sq, sq);
+	}
+	return acc;
+}
+
+template <int M, bool GENERIC, int KT = 0>
+static int set_smem_attr(int bytes) {
+	CUDA_TRY(cudaFuncSetAttribute(fused_stream_kernel<M, GENERIC, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+	return LZGPU_OK;
+}
+
+int lz_fused_init(lzgpu_ctx *ctx) {
+	auto *fs = new FusedState();
+	ctx->fused = fs;
+	if (const char *e = std::getenv("LZGPU_DISABLE_FUSED")) fs->disabled = std::atoi(e) != 0;
+	void *fn = nullptr;
+	cudaDriverEntryPointQueryResult qres;
+	cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+	if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+		cudaGetLastError();
+		lz_set_error("cuTensorMapEncodeTiled is not available from the driver");
+		return LZGPU_ERR_CUDA;
+	}
+	fs->encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+	for (int q = 0; q < 4; ++q) fs->qmult[q] = crc_xpow_bits_signed(32ll * (4096ll * (3 - q) - kFoldDeg));
+	CUDA_TRY(cudaDeviceGetAttribute(&fs->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+	const int smem = std::min(fs->max_smem, 112 * 1024);
+	int rc;
+	if ((rc = set_smem_attr<0, false>(smem))) return rc;
+	if ((rc = set_smem_attr<1, false>(smem))) return rc;
+	if ((rc = set_smem_attr<2, false>(smem))) return rc;
+	if ((rc = set_smem_attr<3, false>(smem))) return rc;
+	if ((rc = set_smem_attr<4, false>(smem))) return rc;
+	if ((rc = set_smem_attr<4, true>(smem))) return rc;
+	if ((rc = set_smem_attr<2, false, 8>(smem))) return rc;
+	return LZGPU_OK;
+}
+
+void lz_fused_destroy(lzgpu_ctx *ctx) {
+	delete ctx->fused;
+	ctx->fused = nullptr;
+}
+
+static size_t fused_smem_bytes(uint32_t rows, uint32_t prows) {
+	const size_t pstage = (static_cast<size_t>(prows) * kStepBytes + 1023) & ~size_t(1023);
+	return static_cast<size_t>(kNST) * rows * kStepBytes + static_cast<size_t>(kNPST) * pstage + 4096 + 512 + 128;
+}
+
+// Largest stripe group G such that data + parity-CRC rows fit the consumer threads, the data rows fit
+// one TMA box (<= 256 rows, a multiple of 8 for the 1024-byte stage alignment) and the stages fit shared memory.
+static uint32_t pick_group(uint32_t K, uint32_t PC, int max_smem_per_cta) {
+	uint32_t best = 0;
+	for (uint32_t g = 1; g <= 64; ++g) {
+		const uint32_t rows = g * K * 4, prows = g * PC * 4;
+		if (rows > kMaxRows || rows + prows > kConsumers || prows > kMaxParityRows || g * K > 64) break;
+		if (rows % 8) continue;
+		if (fused_smem_bytes(rows, prows) > static_cast<size_t>(max_smem_per_cta)) break;
+		best = g;
+	}
+	return best;
+}
+
+static int make_tensor_map(FusedState *fs, CUtensorMap *map, const void *base, uint64_t rows_per_chunk, uint64_t n_chunks,
+                           uint64_t chunk_stride, uint32_t box_rows) {
+	const cuuint64_t dims[3] = {static_cast<cuuint64_t>(kRowBytes), rows_per_chunk, n_chunks};
+	const cuuint64_t strides[2] = {static_cast<cuuint64_t>(kRowBytes), chunk_stride ? chunk_stride : rows_per_chunk * kRowBytes};
+	const cuuint32_t box[3] = {kStepBytes, box_rows, 1};
+	const cuuint32_t estr[3] = {1, 1, 1};
+	CUresult r = fs->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), dims, strides, box, estr,
+	                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+	                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) {
+		lz_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows/chunk %llu, chunks %llu, stride %llu, box rows %u)",
+		             static_cast<int>(r), static_cast<unsigned long long>(rows_per_chunk), static_cast<unsigned long long>(n_chunks),
+		             static_cast<unsigned long long>(chunk_stride), box_rows);
+		return LZGPU_ERR_CUDA;
+	}
+	return LZGPU_OK;
+}
+
+template <int M, bool GENERIC, int KT = 0>
+static int launch(lzgpu_ctx *ctx, const CUtensorMap &map, const FusedParams &p, size_t smem, cudaStream_t st) {
+	const int grid = static_cast<int>(std::min<uint64_t>(p.total_units, static_cast<uint64_t>(ctx->sm_count) * 2));
+	fused_stream_kernel<M, GENERIC, KT><<<grid, kFusedThreads, smem, st>>>(map, p);
+	CUDA_TRY(cudaGetLastError());
+	ctx->stats.kernel_launches++;
+	return LZGPU_OK;
+}
+
+static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_rows, uint32_t K, uint32_t n_chunks, uint32_t nb,
+                     const void *d_data, size_t chunk_stride, void *d_parity, size_t parity_stride, void *d_crc, size_t crc_stride,
+                     cudaStream_t st) {
+	FusedState *fs = ctx->fused;
+	const uint32_t PC = M == 0 ? 0 : (generic ? M : M - 1);
+	const int smem_cap = std::min(fs->max_smem, 112 * 1024);
+	const uint32_t G = pick_group(K, PC, smem_cap);
+	if (G == 0) return LZGPU_NOT_HANDLED;
+	if ((chunk_stride % 16) || (reinterpret_cast<uintptr_t>(d_data) % 16)) return LZGPU_NOT_HANDLED;
+	FusedParams p{};
+	p.parity = static_cast<uint8_t *>(d_parity);
+	p.crc = static_cast<uint32_t *>(d_crc);
+	p.tables = ctx->d_crc_tables;
+	p.parity_stride = parity_stride;
+	p.crc_stride = crc_stride;
+	p.n_chunks = n_chunks;
+	p.nb = nb;
+	p.pb = (nb + K - 1) / K;
+	p.K = K;
+	p.G = G;
+	p.units_per_chunk = (p.pb + G - 1) / G;
+	const uint64_t total = static_cast<uint64_t>(p.units_per_chunk) * n_chunks;
+	if (total > 0x7fffffffull) return LZGPU_NOT_HANDLED;
+	p.total_units = static_cast<uint32_t>(total);
+	std::memcpy(p.qmult, fs->qmult, sizeof(p.qmult));
+	p.zconst = lz::crc_of_zeros(LZGPU_BLOCK_SIZE);
+	if (generic) {
+		for (int r = 0; r < M; ++r)
+			for (uint32_t j = 0; j < K; ++j) {
+				uint8_t v = coef_rows[r * K + j];
+				for (int b = 0; b < 8; ++b) {
+					p.coef[r * 32 + j].plane[b] = v;
+					v = lz::gf_mul_host(v, 2);
+				}
+			}
+	}
+	CUtensorMap map;
+	const uint32_t rows = G * K * 4;
+	int rc = make_tensor_map(fs, &map, d_data, static_cast<uint64_t>(nb) * 4, n_chunks, chunk_stride, rows);
+	if (rc) return rc;
+	const size_t smem = fused_smem_bytes(rows, G * PC * 4);
+	if (generic) return launch<4, true>(ctx, map, p, smem, st);
+	switch (M) {
+		case 0: return launch<0, false>(ctx, map, p, smem, st);
+		case 1: return launch<1, false>(ctx, map, p, smem, st);
+		case 2: return K == 8 ? launch<2, false, 8>(ctx, map, p, smem, st) : launch<2, false>(ctx, map, p, smem, st);
+		case 3: return launch<3, false>(ctx, map, p, smem, st);
+		case 4: return launch<4, false>(ctx, map, p, smem, st);
+	}
 	return LZGPU_NOT_HANDLED;
 }
-int lz_fused_crc(lzgpu_ctx *, const void *, unsigned long long, unsigned long long, unsigned long long, void *, unsigned long long, cudaStream_t) {
-	return LZGPU_NOT_HANDLED;
+
+int lz_fused_encode(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb, const void *d_data, size_t chunk_stride,
+                    void *d_parity, size_t parity_stride, void *d_crc, size_t crc_stride, cudaStream_t st) {
+	FusedState *fs = ctx->fused;
+	if (!fs || fs->disabled) return LZGPU_NOT_HANDLED;
+	const int K = goal->k, M = goal->m;
+	if (M > 4) return LZGPU_NOT_HANDLED;
+	if (lz::uses_cauchy(K, M)) {
+		// Cauchy generator (m == 4 and k > 20): arbitrary coefficients, bit-plane multiply inside the fused kernel
+		uint8_t gen[LZGPU_MAX_PARTS * LZGPU_MAX_DATA];
+		lz::rs_generator(K, M, gen);
+		return fused_run(ctx, 4, true, gen + K * K, K, n_chunks, nb, d_data, chunk_stride, d_parity, parity_stride, d_crc, crc_stride, st);
+	}
+	// xorN is ec(N,1): parity row 0 of the Vandermonde generator is all ones (chunk_writer.cc:373-381)
+	return fused_run(ctx, M, false, nullptr, K, n_chunks, nb, d_data, chunk_stride, d_parity, parity_stride, d_crc, crc_stride, st);
+}
+
+int lz_fused_crc(lzgpu_ctx *ctx, const void *base, unsigned long long n_blocks, unsigned long long blocks_per_chunk,
+                 unsigned long long chunk_stride, void *out, unsigned long long out_chunk_stride, cudaStream_t st) {
+	FusedState *fs = ctx->fused;
+	if (!fs || fs->disabled || n_blocks == 0) return LZGPU_NOT_HANDLED;
+	if (blocks_per_chunk == 0) blocks_per_chunk = n_blocks;
+	if (n_blocks % blocks_per_chunk) return LZGPU_NOT_HANDLED;
+	const unsigned long long n_chunks = n_blocks / blocks_per_chunk;
+	if (blocks_per_chunk > 0x3fffffffull || n_chunks > 0x7fffffffull) return LZGPU_NOT_HANDLED;
+	if (n_chunks == 1) chunk_stride = blocks_per_chunk * LZGPU_BLOCK_SIZE;
+	// CRC only: "K" = 64 blocks per unit, one stripe group per unit, no parity
+	return fused_run(ctx, 0, false, nullptr, 64, static_cast<uint32_t>(n_chunks), static_cast<uint32_t>(blocks_per_chunk), base, chunk_stride,
+	                 nullptr, 0, out, out_chunk_stride, st);
 }

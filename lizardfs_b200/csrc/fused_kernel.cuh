@@ -1,0 +1,341 @@
+// fused_kernel.cuh — the TMA-streamed fused kernel: GF(2^8) parity + CRC32 of every 64 KiB block in
+// ONE pass over HBM (reference work it replaces: ChunkWriter::computeParityBlock per stripe per parity
+// + mycrc32 per block, src/mount/chunk_writer.cc:365-401,531-541, src/common/write_executor.cc:97;
+// with M = 0 it is the scrub / verify CRC pass of hdd_int_test, src/chunkserver/hddspacemgr.cc:2174-2190).
+//
+// Data movement
+//   The input is viewed as a 3-D tensor [chunk][row][16384 B] where a ROW is a quarter of a 64 KiB block
+//   (4 rows per block, blocks in chunk order).  A work UNIT is G consecutive stripes of one chunk =
+//   ROWS = G*K*4 consecutive rows.  Each pipeline step moves one box [ROWS x 128 B] with a single
+//   cp.async.bulk.tensor (TMA, 128-byte swizzle, out-of-range rows zero-filled = the absent blocks of a
+//   short last stripe, reference chunk_writer.cc:97-108,377) into one of NST shared-memory stages,
+//   tracked by full/empty mbarriers; 128 steps stream the unit.  One producer warp issues TMA, the
+//   other warps consume.  Parity leaves through 16-byte coalesced global stores (full 128 B lines).
+//
+// Work mapping (consumer threads)
+//   CRC role   thread t owns row t: a contiguous 16 KiB stream, 128 B per step, read conflict-free
+//              (swizzled LDS.128).  Streams of parity rows are read from a small shared staging ring the
+//              GF role fills.  Four adjacent threads hold the four quarters of one block.
+//   GF role    item (stripe g, quarter q, 16-byte column i): reads the K data blocks of the stripe at
+//              that column, Horner-evaluates the Vandermonde parity rows (row r: acc = acc*2^r + d_j,
+//              reference generator galois_field_isal.cc:53-69) on packed words, stores 16 B per parity.
+//
+// CRC without tables or carry-less multiply
+//   CRC is GF(2)-linear, so the kernel computes lin(M) = M(x)*x^32 mod P and the host constant
+//   mycrc32(0, zeros) is xored at the end.  A stream is reduced with a SPARSE MULTIPLE of P:
+//   g(x) = x^53+x^38+x^36+x^33+x^30+x^27+x^25+x^7+x^3+1 is divisible by the CRC-32 polynomial, and
+//   g(x^32) = g(x)^32 is too, so with y = x^32 (one 32-bit word)  y^53 = y^38+...+1 (mod P):
+//   word u is xored into words u+15, u+17, u+20, u+23, u+26, u+28, u+46, u+50, u+53.  In pull form
+//   W'[u] = W[u] ^ W'[u-15] ^ ... ^ W'[u-53]: nine XORs (5 LOP3) per word on a 64-word register
+//   window, no shifts, no lookups.  After 4096 words the stream is flushed into 53 words that are
+//   reduced once with the byte tables; quarter streams are merged with x^(8*len) multipliers
+//   (the mycrc32_combine identity, reference crc.cc:58-60).  CRC(parity row 0) of a Vandermonde code
+//   needs no work at all: P = xor of the data blocks, hence lin(P) = xor of their lin CRCs
+//   (reference crc.h:29 mycrc32_xorblocks).
+#pragma once
+#include <cuda.h>
+
+#include "device_math.cuh"
+
+namespace lzd {
+
+constexpr int kFoldDeg = 53;
+constexpr int kStepBytes = 128;
+constexpr int kRowBytes = 16384;
+constexpr int kStepsPerUnit = kRowBytes / kStepBytes;  // 128
+constexpr int kConsumers = 288;                        // 9 warps
+constexpr int kFusedThreads = kConsumers + 32;         // + producer warp
+constexpr int kMaxRows = 256;                          // TMA box limit per dimension
+constexpr int kNST = 3;                                // data stages
+constexpr int kNPST = 2;                               // parity staging ring
+constexpr int kMaxParityRows = 128;
+
+struct FusedParams {
+	uint8_t *parity;         // part-major parity output (chunk c at + c*parity_stride)
+	uint32_t *crc;           // crc output (chunk c at + c*crc_stride elements)
+	const uint32_t *tables;  // 4*256 slicing tables
+	unsigned long long parity_stride, crc_stride;
+	uint32_t n_chunks, nb, pb;       // blocks per chunk, blocks per parity part
+	uint32_t K, G;                   // data parts, stripes per unit
+	uint32_t units_per_chunk, total_units;
+	uint32_t qmult[4];               // x^(32*(4096*(3-q) - 53)) mod P : stream -> block merge incl. the flush offset
+	uint32_t zconst;                 // mycrc32(0, 64 KiB of zeros)
+	CoefPlanes coef[4 * 32];         // only read by the GENERIC instantiation: [M][K]
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+	const uint32_t addr = smem_u32(bar);
+	uint32_t done;
+	do {
+		asm volatile(
+		    "{\n\t.reg .pred p;\n\t"
+		    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+		    "selp.u32 %0, 1, 0, p;\n\t}"
+		    : "=r"(done)
+		    : "r"(addr), "r"(parity)
+		    : "memory");
+	} while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
+	asm volatile(
+	    "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+	        smem_u32(smem_dst)),
+	    "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+	    : "memory");
+}
+
+// ---- sparse-fold CRC stream ------------------------------------------------------------------------
+// window slot of word u is u & 63; the nine pulled words of slot S are the static slots (S - lag) & 63
+#define LZ_FOLD(win, S, w)                                                                                     \
+	win[(S)&63] = (w) ^ win[((S)-15) & 63] ^ win[((S)-17) & 63] ^ win[((S)-20) & 63] ^ win[((S)-23) & 63] ^ \
+	              win[((S)-26) & 63] ^ win[((S)-28) & 63] ^ win[((S)-46) & 63] ^ win[((S)-50) & 63] ^ win[((S)-53) & 63]
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v) {
+	asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int BASE>
+__device__ __forceinline__ void fold_step(uint32_t (&win)[64], uint32_t row_addr_swz) {
+	// 8 x 16 bytes of this row.  Rows are 128-byte aligned, so the TMA 128-byte swizzle
+	// (chunk c of row r stored at chunk c ^ (r & 7)) is a pure XOR on the shared address:
+	// row_addr_swz = row_addr ^ ((r & 7) << 4), chunk c at row_addr_swz ^ (c << 4).
+#pragma unroll
+	for (int c = 0; c < 8; ++c) {
+		const uint4 v = lds128(row_addr_swz ^ (c << 4));
+		LZ_FOLD(win, BASE + 4 * c + 0, v.x);
+		LZ_FOLD(win, BASE + 4 * c + 1, v.y);
+		LZ_FOLD(win, BASE + 4 * c + 2, v.z);
+		LZ_FOLD(win, BASE + 4 * c + 3, v.w);
+	}
+}
+
+// After the last word of a stream (word count a multiple of 64): run the recurrence 53 more steps with
+// zero input, pulling ONLY from real stream words (lag > j), which leaves R_j = win[j], j < 53, with
+// stream(x) * y^53 = R(x) (mod P); then reduce R with the byte tables.
+__device__ __forceinline__ uint32_t fold_finish(uint32_t (&win)[64], const uint32_t *tab) {
+	constexpr int lags[9] = {15, 17, 20, 23, 26, 28, 46, 50, 53};
+#pragma unroll
+	for (int j = 0; j < kFoldDeg; ++j) {
+		uint32_t acc = 0;
+#pragma unroll
+		for (int t = 0; t < 9; ++t)
+			if (lags[t] > j) acc ^= win[(j - lags[t]) & 63];
+		win[j] = acc;
+	}
+	uint32_t st = 0;
+#pragma unroll
+	for (int j = 0; j < kFoldDeg; ++j) st = crc_step_word(st, win[j], tab);
+	return st;
+}
+
+// ---- the kernel -------------------------------------------------------------------------------------
+// M        parity parts produced (0 = CRC only)
+// GENERIC  false: Vandermonde rows 1, 2^j, 4^j, 8^j by Horner (row 0 = XOR; its CRC comes from linearity)
+//          true : arbitrary coefficient rows from p.coef (Cauchy generators); every parity CRC is computed
+template <int M, bool GENERIC, int KT>
+__global__ void __launch_bounds__(kFusedThreads, 2)
+fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
+	constexpr int PC = (M == 0) ? 0 : (GENERIC ? M : M - 1);  // parity parts whose CRC is computed from bytes
+	constexpr int P0 = GENERIC ? 0 : 1;                       // first such parity part
+
+	extern __shared__ __align__(1024) uint8_t smem[];
+	const uint32_t K = KT ? KT : p.K, G = p.G;
+	const uint32_t ROWS = G * K * 4;
+	const uint32_t PROWS = G * PC * 4;
+	const uint32_t stage_bytes = ROWS * kStepBytes;  // multiple of 1024 because ROWS is a multiple of 8 (host guarantees)
+	uint8_t *stage0 = smem;
+	const uint32_t pstage_bytes = (PROWS * kStepBytes + 1023u) & ~1023u;
+	uint8_t *pstage0 = smem + kNST * stage_bytes;    // 1024-aligned
+	uint32_t *s_tab = reinterpret_cast<uint32_t *>(pstage0 + kNPST * pstage_bytes);
+	uint32_t *s_blk = s_tab + 1024;                  // [2][64] block lin-CRCs for the row-0 parity CRC
+	uint64_t *bars = reinterpret_cast<uint64_t *>(s_blk + 128);
+	uint64_t *full = bars, *empty = bars + kNST, *pfull = bars + 2 * kNST, *pempty = bars + 2 * kNST + kNPST;
+
+	const uint32_t tid = threadIdx.x;
+	const uint32_t warp = tid >> 5, lane = tid & 31;
+	const uint32_t n_items = 32 * G * (M > 0 ? 1 : 0);
+	const uint32_t n_cons_warps = kConsumers / 32;
+	const uint32_t n_gf_warps = (min(n_items, (uint32_t)kConsumers) + 31) / 32;
+	const uint32_t first_pwarp = ROWS / 32, last_pwarp = PROWS ? (ROWS + PROWS - 1) / 32 : 0;
+
+	for (uint32_t i = tid; i < 1024; i += blockDim.x) s_tab[i] = p.tables[i];
+	if (tid == 0) {
+		for (int s = 0; s < kNST; ++s) {
+			mbar_init(&full[s], 1);
+			mbar_init(&empty[s], n_cons_warps);
+		}
+		for (int s = 0; s < kNPST; ++s) {
+			mbar_init(&pfull[s], n_gf_warps ? n_gf_warps : 1);
+			mbar_init(&pempty[s], PROWS ? (last_pwarp - first_pwarp + 1) : 1);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+
+	if (warp == kConsumers / 32) {
+		// ===================== producer warp: one lane drives TMA =====================
+		if (lane == 0) {
+			uint32_t it = 0;
+			for (uint32_t unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
+				const uint32_t c = unit / p.units_per_chunk, gi = unit % p.units_per_chunk;
+				const int row0 = static_cast<int>(gi * ROWS);
+				for (int step = 0; step < kStepsPerUnit; ++step, ++it) {
+					const uint32_t st = it % kNST, ph = (it / kNST) & 1;
+					mbar_wait(&empty[st], ph ^ 1);
+					mbar_expect_tx(&full[st], stage_bytes);
+					tma_load_3d(stage0 + st * stage_bytes, &tmap, step * kStepBytes, row0, static_cast<int>(c), &full[st]);
+				}
+			}
+		}
+		return;
+	}
+
+	// ===================== consumer warps =====================
+	const bool is_data_row = tid < ROWS;
+	const bool is_parity_row = tid >= ROWS && tid < ROWS + PROWS;
+	const bool has_stream = is_data_row || is_parity_row;
+	const uint32_t prow = tid - ROWS;                       // parity row id (g*PC + r')*4 + q
+	const uint32_t my_row = is_data_row ? tid : prow;
+	const uint32_t row_off = my_row * kStepBytes, row_swz = my_row & 7;
+	const bool warp_has_items = warp < n_gf_warps;
+	const bool warp_has_prow = PROWS && warp >= first_pwarp && warp <= last_pwarp;
+
+	uint32_t win[64];
+	uint32_t it = 0, pit = 0;
+	uint32_t unit_parity = 0;
+
+	for (uint32_t unit = blockIdx.x; unit < p.total_units; unit += gridDim.x, unit_parity ^= 1) {
+		const uint32_t c = unit / p.units_per_chunk, gi = unit % p.units_per_chunk;
+		const uint32_t stripe0 = gi * G;
+#pragma unroll
+		for (int i = 0; i < 64; ++i) win[i] = 0;
+
+		for (int step2 = 0; step2 < kStepsPerUnit; step2 += 2) {
+#pragma unroll
+			for (int half = 0; half < 2; ++half, ++it, ++pit) {
+				const int step = step2 + half;
+				const uint32_t st = it % kNST, ph = (it / kNST) & 1;
+				const uint32_t pst = pit % kNPST, pph = (pit / kNPST) & 1;
+				const uint32_t stage = smem_u32(stage0) + st * stage_bytes;
+				const uint32_t pstage = smem_u32(pstage0) + pst * pstage_bytes;
+				mbar_wait(&full[st], ph);
+
+				// ---------------- GF role ----------------
+				if (M > 0 && warp_has_items) {
+					if (PC > 0) mbar_wait(&pempty[pst], pph ^ 1);
+					for (uint32_t item = tid; item < n_items; item += kConsumers) {
+						const uint32_t col = item & 7, q = (item >> 3) & 3, g = item >> 5;
+						uint32_t acc[M > 0 ? M : 1][4];
+#pragma unroll
+						for (int r = 0; r < M; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0;
+						const uint32_t rbase = g * K * 4 + q;
+#pragma unroll
+						for (int j = static_cast<int>(K) - 1; j >= 0; --j) {
+							const uint32_t row = rbase + 4u * j;
+							const uint4 v = lds128(stage + row * kStepBytes + ((col ^ (row & 7)) << 4));
+							if (GENERIC) {
+#pragma unroll
+								for (int r = 0; r < M; ++r) {
+									const CoefPlanes &cp = p.coef[r * 32 + j];
+									acc[r][0] = gf_mac(acc[r][0], v.x, cp);
+									acc[r][1] = gf_mac(acc[r][1], v.y, cp);
+									acc[r][2] = gf_mac(acc[r][2], v.z, cp);
+									acc[r][3] = gf_mac(acc[r][3], v.w, cp);
+								}
+							} else {
+#pragma unroll
+								for (int r = 0; r < M; ++r) {
+#pragma unroll
+									for (int w = 0; w < 4; ++w) {
+										uint32_t a = acc[r][w];
+#pragma unroll
+										for (int t = 0; t < r; ++t) a = gf_x2(a);  // times 2^r
+										acc[r][w] = a ^ (w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w);
+									}
+								}
+							}
+						}
+						const uint32_t stripe = stripe0 + g;
+						if (stripe < p.pb) {
+							uint8_t *dst = p.parity + c * p.parity_stride + (static_cast<unsigned long long>(stripe) << 16) +
+							               (q << 14) + step * kStepBytes + (col << 4);
+#pragma unroll
+							for (int r = 0; r < M; ++r)
+								st_stream(reinterpret_cast<uint4 *>(dst + static_cast<unsigned long long>(r) * p.pb * 65536ull),
+								          make_uint4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
+						}
+#pragma unroll
+						for (int r = P0; r < M; ++r) {
+							const uint32_t pr = (g * PC + (r - P0)) * 4 + q;
+							sts128(pstage + pr * kStepBytes + ((col ^ (pr & 7)) << 4), make_uint4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
+						}
+					}
+					if (PC > 0) {
+						__syncwarp();
+						if (lane == 0) mbar_arrive(&pfull[pst]);
+					}
+				}
+
+				// ---------------- CRC role ----------------
+				if (PC > 0 && warp_has_prow) mbar_wait(&pfull[pst], pph);
+				if (has_stream) {
+					const uint32_t rowp = ((is_data_row ? stage : pstage) + row_off) ^ (row_swz << 4);
+					if (half == 0) fold_step<0>(win, rowp);
+					else fold_step<32>(win, rowp);
+				}
+				__syncwarp();
+				if (lane == 0) {
+					mbar_arrive(&empty[st]);
+					if (PC > 0 && warp_has_prow) mbar_arrive(&pempty[pst]);
+				}
+			}
+		}
+
+		// ---------------- unit epilogue: streams -> block CRCs ----------------
+		uint32_t lin = 0;
+		if (has_stream) lin = crc_mulmod(fold_finish(win, s_tab), p.qmult[my_row & 3]);
+		lin ^= __shfl_xor_sync(0xffffffffu, lin, 1);
+		lin ^= __shfl_xor_sync(0xffffffffu, lin, 2);
+		uint32_t *blk = s_blk + unit_parity * 64;
+		if (is_data_row && (tid & 3) == 0) {
+			const uint32_t b = stripe0 * K + (tid >> 2);  // block index in the chunk
+			if (M > 0 && !GENERIC) blk[tid >> 2] = lin;
+			if (b < p.nb) p.crc[c * p.crc_stride + b] = lin ^ p.zconst;
+		}
+		if (is_parity_row && (prow & 3) == 0) {
+			constexpr uint32_t PCD = PC ? PC : 1;
+			const uint32_t g = (prow >> 2) / PCD, r = P0 + (prow >> 2) % PCD;
+			const uint32_t stripe = stripe0 + g;
+			if (stripe < p.pb) p.crc[c * p.crc_stride + p.nb + r * p.pb + stripe] = lin ^ p.zconst;
+		}
+		if (M > 0 && !GENERIC) {
+			// CRC of parity row 0 (plain XOR of the stripe): xor of the data blocks' linear CRCs
+			asm volatile("bar.sync 1, %0;" ::"r"(kConsumers) : "memory");
+			if (tid < G) {
+				uint32_t x = 0;
+				for (uint32_t j = 0; j < K; ++j) x ^= blk[tid * K + j];
+				const uint32_t stripe = stripe0 + tid;
+				if (stripe < p.pb) p.crc[c * p.crc_stride + p.nb + stripe] = x ^ p.zconst;
+			}
+		}
+	}
+}
+
+}  // namespace lzd
