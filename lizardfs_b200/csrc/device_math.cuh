@@ -24,6 +24,15 @@ __device__ __forceinline__ uint32_t gf_x2(uint32_t v) {
 	return ((v ^ hi) << 1) ^ __umulhi(hi, 0x3A000000u);
 }
 
+// acc*2 + d with the byte-lane doubling done on the FMA pipe: (v - hi)*2 = v*2 + hi*(-2) (two IMADs),
+// leaving two LOP3 (mask, final 3-input XOR) on the ALU pipe, which is the busy one in the fused kernel
+__device__ __forceinline__ uint32_t gf_x2_add(uint32_t v, uint32_t d) {
+	const uint32_t hi = v & 0x80808080u;
+	uint32_t dbl;
+	asm("{\n\t.reg .u32 t;\n\tmul.lo.u32 t, %1, 2;\n\tmad.lo.u32 %0, %2, 0xFFFFFFFE, t;\n\t}" : "=r"(dbl) : "r"(v), "r"(hi));
+	return dbl ^ __umulhi(hi, 0x3A000000u) ^ d;
+}
+
 // One coefficient prepared for the bit-plane product: plane[b] = c * 2^b in GF(2^8), each stored
 // in a 32-bit word so that  c*v = XOR_b ((v >> b) & 0x01010101) * plane[b]  — every partial
 // product stays inside its byte lane (a 0/1 byte times an 8-bit constant), hence no carries.
@@ -60,6 +69,12 @@ __device__ __forceinline__ uint32_t crc_mulmod(uint32_t a, uint32_t b) {
 __device__ __forceinline__ uint32_t crc_step_word(uint32_t state, uint32_t w, const uint32_t *tab) {
 	const uint32_t v = state ^ w;
 	return tab[768 + (v & 0xff)] ^ tab[512 + ((v >> 8) & 0xff)] ^ tab[256 + ((v >> 16) & 0xff)] ^ tab[v >> 24];
+}
+
+// same, tables in global memory (read-only path; used once per 16 KiB stream by the fused kernels)
+__device__ __forceinline__ uint32_t crc_step_word_ldg(uint32_t state, uint32_t w, const uint32_t *tab) {
+	const uint32_t v = state ^ w;
+	return __ldg(tab + 768 + (v & 0xff)) ^ __ldg(tab + 512 + ((v >> 8) & 0xff)) ^ __ldg(tab + 256 + ((v >> 16) & 0xff)) ^ __ldg(tab + (v >> 24));
 }
 
 __device__ __forceinline__ uint32_t crc_step_byte(uint32_t state, uint32_t byte, const uint32_t *tab) {

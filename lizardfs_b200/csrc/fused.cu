@@ -18,11 +18,17 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// two CTAs per SM: 228 KiB per SM minus 1 KiB reserved per CTA
+constexpr int kSmemCap = 113 * 1024;
+
 struct FusedState {
 	EncodeTiledFn encode_tiled = nullptr;
 	uint32_t qmult[4];
 	int max_smem = 0;
 	bool disabled = false;
+	uint32_t probe = 0;
+	uint32_t *d_sm_ctr = nullptr;
+	int promo = 3;  // CU_TENSOR_MAP_L2_PROMOTION_L2_256B: +12% streaming bandwidth over 128B/none (profiles/probe_r1.md)
 };
 
 // x^n mod P for a possibly negative n (x has multiplicative order dividing 2^32 - 1)
@@ -38,9 +44,9 @@ static uint32_t crc_xpow_bits_signed(long long n) {
 	return acc;
 }
 
-template <int M, bool GENERIC, int KT = 0>
+template <int M, bool GENERIC, int KT = 0, int GT = 0>
 static int set_smem_attr(int bytes) {
-	CUDA_TRY(cudaFuncSetAttribute(fused_stream_kernel<M, GENERIC, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+	CUDA_TRY(cudaFuncSetAttribute(fused_stream_kernel<M, GENERIC, KT, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
 	return LZGPU_OK;
 }
 
@@ -48,6 +54,8 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	auto *fs = new FusedState();
 	ctx->fused = fs;
 	if (const char *e = std::getenv("LZGPU_DISABLE_FUSED")) fs->disabled = std::atoi(e) != 0;
+	if (const char *e = std::getenv("LZGPU_PROBE")) fs->probe = static_cast<uint32_t>(std::atoi(e));
+	if (const char *e = std::getenv("LZGPU_L2_PROMO")) fs->promo = std::atoi(e);
 	void *fn = nullptr;
 	cudaDriverEntryPointQueryResult qres;
 	cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -59,7 +67,8 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	fs->encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
 	for (int q = 0; q < 4; ++q) fs->qmult[q] = crc_xpow_bits_signed(32ll * (4096ll * (3 - q) - kFoldDeg));
 	CUDA_TRY(cudaDeviceGetAttribute(&fs->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-	const int smem = std::min(fs->max_smem, 112 * 1024);
+	CUDA_TRY(cudaMalloc(&fs->d_sm_ctr, 256 * sizeof(uint32_t)));
+	const int smem = std::min(fs->max_smem, kSmemCap);
 	int rc;
 	if ((rc = set_smem_attr<0, false>(smem))) return rc;
 	if ((rc = set_smem_attr<1, false>(smem))) return rc;
@@ -67,18 +76,19 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if ((rc = set_smem_attr<3, false>(smem))) return rc;
 	if ((rc = set_smem_attr<4, false>(smem))) return rc;
 	if ((rc = set_smem_attr<4, true>(smem))) return rc;
-	if ((rc = set_smem_attr<2, false, 8>(smem))) return rc;
+	if ((rc = set_smem_attr<2, false, 8, 8>(smem))) return rc;
 	return LZGPU_OK;
 }
 
 void lz_fused_destroy(lzgpu_ctx *ctx) {
+	if (ctx->fused && ctx->fused->d_sm_ctr) cudaFree(ctx->fused->d_sm_ctr);
 	delete ctx->fused;
 	ctx->fused = nullptr;
 }
 
 static size_t fused_smem_bytes(uint32_t rows, uint32_t prows) {
 	const size_t pstage = (static_cast<size_t>(prows) * kStepBytes + 1023) & ~size_t(1023);
-	return static_cast<size_t>(kNST) * rows * kStepBytes + static_cast<size_t>(kNPST) * pstage + 4096 + 512 + 128;
+	return static_cast<size_t>(kNST) * rows * kStepBytes + static_cast<size_t>(kNPST) * pstage + 520 + 8 * (2 * kNST + 2 * kNPST);
 }
 
 // Largest stripe group G such that data + parity-CRC rows fit the consumer threads, the data rows fit
@@ -102,7 +112,7 @@ static int make_tensor_map(FusedState *fs, CUtensorMap *map, const void *base, u
 	const cuuint32_t box[3] = {kStepBytes, box_rows, 1};
 	const cuuint32_t estr[3] = {1, 1, 1};
 	CUresult r = fs->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), dims, strides, box, estr,
-	                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+	                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, static_cast<CUtensorMapL2promotion>(fs->promo),
 	                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) {
 		lz_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows/chunk %llu, chunks %llu, stride %llu, box rows %u)",
@@ -113,10 +123,10 @@ static int make_tensor_map(FusedState *fs, CUtensorMap *map, const void *base, u
 	return LZGPU_OK;
 }
 
-template <int M, bool GENERIC, int KT = 0>
+template <int M, bool GENERIC, int KT = 0, int GT = 0>
 static int launch(lzgpu_ctx *ctx, const CUtensorMap &map, const FusedParams &p, size_t smem, cudaStream_t st) {
 	const int grid = static_cast<int>(std::min<uint64_t>(p.total_units, static_cast<uint64_t>(ctx->sm_count) * 2));
-	fused_stream_kernel<M, GENERIC, KT><<<grid, kFusedThreads, smem, st>>>(map, p);
+	fused_stream_kernel<M, GENERIC, KT, GT><<<grid, kFusedThreads, smem, st>>>(map, p);
 	CUDA_TRY(cudaGetLastError());
 	ctx->stats.kernel_launches++;
 	return LZGPU_OK;
@@ -127,7 +137,7 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
                      cudaStream_t st) {
 	FusedState *fs = ctx->fused;
 	const uint32_t PC = M == 0 ? 0 : (generic ? M : M - 1);
-	const int smem_cap = std::min(fs->max_smem, 112 * 1024);
+	const int smem_cap = std::min(fs->max_smem, kSmemCap);
 	const uint32_t G = pick_group(K, PC, smem_cap);
 	if (G == 0) return LZGPU_NOT_HANDLED;
 	if ((chunk_stride % 16) || (reinterpret_cast<uintptr_t>(d_data) % 16)) return LZGPU_NOT_HANDLED;
@@ -148,6 +158,7 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	p.total_units = static_cast<uint32_t>(total);
 	std::memcpy(p.qmult, fs->qmult, sizeof(p.qmult));
 	p.zconst = lz::crc_of_zeros(LZGPU_BLOCK_SIZE);
+	p.probe = fs->probe;
 	if (generic) {
 		for (int r = 0; r < M; ++r)
 			for (uint32_t j = 0; j < K; ++j) {
@@ -167,7 +178,7 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	switch (M) {
 		case 0: return launch<0, false>(ctx, map, p, smem, st);
 		case 1: return launch<1, false>(ctx, map, p, smem, st);
-		case 2: return K == 8 ? launch<2, false, 8>(ctx, map, p, smem, st) : launch<2, false>(ctx, map, p, smem, st);
+		case 2: return (K == 8 && G == 8) ? launch<2, false, 8, 8>(ctx, map, p, smem, st) : launch<2, false>(ctx, map, p, smem, st);
 		case 3: return launch<3, false>(ctx, map, p, smem, st);
 		case 4: return launch<4, false>(ctx, map, p, smem, st);
 	}

@@ -39,15 +39,21 @@
 
 namespace lzd {
 
+#ifdef LZ_ENABLE_PROBE
+#define LZ_PROBE(bit) (p.probe & (bit))
+#else
+#define LZ_PROBE(bit) 0
+#endif
+
 constexpr int kFoldDeg = 53;
 constexpr int kStepBytes = 128;
 constexpr int kRowBytes = 16384;
 constexpr int kStepsPerUnit = kRowBytes / kStepBytes;  // 128
-constexpr int kConsumers = 288;                        // 9 warps
-constexpr int kFusedThreads = kConsumers + 32;         // + producer warp
+constexpr int kConsumers = 288;                        // 9 warps, all consumers (2 CTAs/SM -> 112 registers per thread)
+constexpr int kFusedThreads = kConsumers;
 constexpr int kMaxRows = 256;                          // TMA box limit per dimension
 constexpr int kNST = 3;                                // data stages
-constexpr int kNPST = 2;                               // parity staging ring
+constexpr int kNPST = 4;                               // parity staging ring (decouples GF warps from the parity-CRC warp)
 constexpr int kMaxParityRows = 128;
 
 struct FusedParams {
@@ -60,39 +66,49 @@ struct FusedParams {
 	uint32_t units_per_chunk, total_units;
 	uint32_t qmult[4];               // x^(32*(4096*(3-q) - 53)) mod P : stream -> block merge incl. the flush offset
 	uint32_t zconst;                 // mycrc32(0, 64 KiB of zeros)
+	uint32_t probe;                  // diagnostics only (LZGPU_PROBE): bit1 skip GF role, bit2 skip CRC folds (results then invalid)
 	CoefPlanes coef[4 * 32];         // only read by the GENERIC instantiation: [M][K]
 };
 
-// ---- PTX wrappers --------------------------------------------------------------------------------
+// ---- PTX wrappers (all shared-memory operands are 32-bit shared-window addresses) ------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+// arrive and report whether this arrival completed the phase (pending count captured by the returned
+// state is the count BEFORE this arrival, so exactly one arriver sees 1)
+__device__ __forceinline__ bool mbar_arrive_is_last(uint32_t bar) {
+	uint64_t state;
+	uint32_t pending;
+	asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(state) : "r"(bar) : "memory");
+	asm volatile("mbarrier.pending_count.b64 %0, %1;" : "=r"(pending) : "l"(state));
+	return pending == 1;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-	const uint32_t addr = smem_u32(bar);
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
 	uint32_t done;
 	do {
+		// the suspend-time hint lets the warp sleep in hardware until the phase completes instead of spinning
 		asm volatile(
 		    "{\n\t.reg .pred p;\n\t"
-		    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+		    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
 		    "selp.u32 %0, 1, 0, p;\n\t}"
 		    : "=r"(done)
-		    : "r"(addr), "r"(parity)
+		    : "r"(addr), "r"(parity), "r"(0x989680u)
 		    : "memory");
 	} while (!done);
 }
-__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar) {
 	asm volatile(
 	    "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-	        smem_u32(smem_dst)),
-	    "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+	        smem_dst),
+	    "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
 	    : "memory");
 }
 
@@ -141,7 +157,7 @@ __device__ __forceinline__ uint32_t fold_finish(uint32_t (&win)[64], const uint3
 	}
 	uint32_t st = 0;
 #pragma unroll
-	for (int j = 0; j < kFoldDeg; ++j) st = crc_step_word(st, win[j], tab);
+	for (int j = 0; j < kFoldDeg; ++j) st = crc_step_word_ldg(st, win[j], tab);
 	return st;
 }
 
@@ -149,107 +165,120 @@ __device__ __forceinline__ uint32_t fold_finish(uint32_t (&win)[64], const uint3
 // M        parity parts produced (0 = CRC only)
 // GENERIC  false: Vandermonde rows 1, 2^j, 4^j, 8^j by Horner (row 0 = XOR; its CRC comes from linearity)
 //          true : arbitrary coefficient rows from p.coef (Cauchy generators); every parity CRC is computed
-template <int M, bool GENERIC, int KT>
+// KT, GT   compile-time K and G (0 = runtime p.K / p.G); the hot configurations are fully constant-folded
+//
+// Pipeline control: there is no producer warp.  Every consumer warp, after its last read of a stage,
+// arrives on the stage's `empty` mbarrier; the arrival that completes the phase re-arms `full` and issues
+// the TMA load of the step NST ahead ("last releaser refills") — no spinning producer, minimal refill latency.
+//
+// shared memory map (offsets from the 1024-aligned dynamic base):
+//   [0, NST*stage)            data stages          stage = ROWS*128
+//   [.., + NPST*pstage)       parity staging ring  pstage = roundup(PROWS*128, 1024)
+//   + 0    s_blk[2][64]       block linear CRCs of the current / previous unit (row-0 parity CRC)
+//   + 520  full[NST], empty[NST], pfull[NPST], pempty[NPST]   (8 bytes each)
+template <int M, bool GENERIC, int KT, int GT>
 __global__ void __launch_bounds__(kFusedThreads, 2)
 fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
 	constexpr int PC = (M == 0) ? 0 : (GENERIC ? M : M - 1);  // parity parts whose CRC is computed from bytes
 	constexpr int P0 = GENERIC ? 0 : 1;                       // first such parity part
 
 	extern __shared__ __align__(1024) uint8_t smem[];
-	const uint32_t K = KT ? KT : p.K, G = p.G;
+	const uint32_t sbase = smem_u32(smem);
+	const uint32_t K = KT ? KT : p.K, G = GT ? GT : p.G;
 	const uint32_t ROWS = G * K * 4;
 	const uint32_t PROWS = G * PC * 4;
 	const uint32_t stage_bytes = ROWS * kStepBytes;  // multiple of 1024 because ROWS is a multiple of 8 (host guarantees)
-	uint8_t *stage0 = smem;
 	const uint32_t pstage_bytes = (PROWS * kStepBytes + 1023u) & ~1023u;
-	uint8_t *pstage0 = smem + kNST * stage_bytes;    // 1024-aligned
-	uint32_t *s_tab = reinterpret_cast<uint32_t *>(pstage0 + kNPST * pstage_bytes);
-	uint32_t *s_blk = s_tab + 1024;                  // [2][64] block lin-CRCs for the row-0 parity CRC
-	uint64_t *bars = reinterpret_cast<uint64_t *>(s_blk + 128);
-	uint64_t *full = bars, *empty = bars + kNST, *pfull = bars + 2 * kNST, *pempty = bars + 2 * kNST + kNPST;
+	const uint32_t pstage0 = sbase + kNST * stage_bytes;
+	const uint32_t misc = pstage0 + kNPST * pstage_bytes;
+	const uint32_t a_blk = misc;
+	const uint32_t a_full = misc + 520, a_empty = a_full + 8 * kNST, a_pfull = a_empty + 8 * kNST, a_pempty = a_pfull + 8 * kNPST;
 
 	const uint32_t tid = threadIdx.x;
 	const uint32_t warp = tid >> 5, lane = tid & 31;
 	const uint32_t n_items = 32 * G * (M > 0 ? 1 : 0);
-	const uint32_t n_cons_warps = kConsumers / 32;
 	const uint32_t n_gf_warps = (min(n_items, (uint32_t)kConsumers) + 31) / 32;
 	const uint32_t first_pwarp = ROWS / 32, last_pwarp = PROWS ? (ROWS + PROWS - 1) / 32 : 0;
+	// warps that read the TMA data stages (data streams or GF items); pure parity-CRC warps do not gate the refill
+	const uint32_t n_stage_warps = max((ROWS + 31) / 32, n_gf_warps);
 
-	for (uint32_t i = tid; i < 1024; i += blockDim.x) s_tab[i] = p.tables[i];
+	const uint32_t my_units = blockIdx.x < p.total_units ? (p.total_units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+	const uint32_t total_steps = my_units * kStepsPerUnit;
+
+	// load of step `step` of unit (chunk c, stripe group gi) into stage `st` (caller guarantees the stage is free)
+	auto issue_load = [&](uint32_t c, uint32_t gi, uint32_t step, uint32_t st) {
+		mbar_expect_tx(a_full + 8 * st, stage_bytes);
+		tma_load_3d(sbase + st * stage_bytes, &tmap, static_cast<int>(step * kStepBytes), static_cast<int>(gi * ROWS), static_cast<int>(c),
+		            a_full + 8 * st);
+	};
+
 	if (tid == 0) {
 		for (int s = 0; s < kNST; ++s) {
-			mbar_init(&full[s], 1);
-			mbar_init(&empty[s], n_cons_warps);
+			mbar_init(a_full + 8 * s, 1);
+			mbar_init(a_empty + 8 * s, n_stage_warps);
 		}
 		for (int s = 0; s < kNPST; ++s) {
-			mbar_init(&pfull[s], n_gf_warps ? n_gf_warps : 1);
-			mbar_init(&pempty[s], PROWS ? (last_pwarp - first_pwarp + 1) : 1);
+			mbar_init(a_pfull + 8 * s, n_gf_warps ? n_gf_warps : 1);
+			mbar_init(a_pempty + 8 * s, PROWS ? (last_pwarp - first_pwarp + 1) : 1);
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		if (total_steps)
+			for (uint32_t g0 = 0; g0 < kNST; ++g0) issue_load(blockIdx.x / p.units_per_chunk, blockIdx.x % p.units_per_chunk, g0, g0);
 	}
 	__syncthreads();
 
-	if (warp == kConsumers / 32) {
-		// ===================== producer warp: one lane drives TMA =====================
-		if (lane == 0) {
-			uint32_t it = 0;
-			for (uint32_t unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
-				const uint32_t c = unit / p.units_per_chunk, gi = unit % p.units_per_chunk;
-				const int row0 = static_cast<int>(gi * ROWS);
-				for (int step = 0; step < kStepsPerUnit; ++step, ++it) {
-					const uint32_t st = it % kNST, ph = (it / kNST) & 1;
-					mbar_wait(&empty[st], ph ^ 1);
-					mbar_expect_tx(&full[st], stage_bytes);
-					tma_load_3d(stage0 + st * stage_bytes, &tmap, step * kStepBytes, row0, static_cast<int>(c), &full[st]);
-				}
-			}
-		}
-		return;
-	}
-
-	// ===================== consumer warps =====================
-	const bool is_data_row = tid < ROWS;
-	const bool is_parity_row = tid >= ROWS && tid < ROWS + PROWS;
+	// ===================== role assignment =====================
+	const uint32_t cw = warp;                                 // consumer warp index 0..8
+	const uint32_t vt = tid;                                  // consumer thread index 0..287
+	const bool is_data_row = vt < ROWS;
+	const bool is_parity_row = vt >= ROWS && vt < ROWS + PROWS;
 	const bool has_stream = is_data_row || is_parity_row;
-	const uint32_t prow = tid - ROWS;                       // parity row id (g*PC + r')*4 + q
-	const uint32_t my_row = is_data_row ? tid : prow;
-	const uint32_t row_off = my_row * kStepBytes, row_swz = my_row & 7;
-	const bool warp_has_items = warp < n_gf_warps;
-	const bool warp_has_prow = PROWS && warp >= first_pwarp && warp <= last_pwarp;
+	const uint32_t prow = vt - ROWS;                          // parity row id (g*PC + r')*4 + q
+	const uint32_t my_row = is_data_row ? vt : prow;
+	// address of this thread's stream row inside stage 0 / parity stage 0, swizzle pre-applied
+	const uint32_t row_addr0 = ((is_data_row ? sbase : pstage0) + my_row * kStepBytes) ^ ((my_row & 7) << 4);
+	const uint32_t row_stride = is_data_row ? stage_bytes : pstage_bytes;
+	const bool warp_has_items = cw < n_gf_warps;
+	const bool warp_has_prow = PROWS && cw >= first_pwarp && cw <= last_pwarp;
+	const bool warp_reads_stage = cw < n_stage_warps;
 
 	uint32_t win[64];
-	uint32_t it = 0, pit = 0;
+	uint32_t it = 0;               // this CTA's global step counter
+	uint32_t st = 0, ph = 0;       // data stage index / phase parity of `it`
+	uint32_t pst = 0, pph = 0;     // parity ring index / phase parity of `it`
 	uint32_t unit_parity = 0;
 
 	for (uint32_t unit = blockIdx.x; unit < p.total_units; unit += gridDim.x, unit_parity ^= 1) {
 		const uint32_t c = unit / p.units_per_chunk, gi = unit % p.units_per_chunk;
 		const uint32_t stripe0 = gi * G;
+		const uint32_t next_unit = unit + gridDim.x;   // only read when it exists (it + NST < total_steps)
+		const uint32_t next_c = next_unit / p.units_per_chunk, next_gi = next_unit % p.units_per_chunk;
 #pragma unroll
 		for (int i = 0; i < 64; ++i) win[i] = 0;
 
 		for (int step2 = 0; step2 < kStepsPerUnit; step2 += 2) {
 #pragma unroll
-			for (int half = 0; half < 2; ++half, ++it, ++pit) {
+			for (int half = 0; half < 2; ++half) {
 				const int step = step2 + half;
-				const uint32_t st = it % kNST, ph = (it / kNST) & 1;
-				const uint32_t pst = pit % kNPST, pph = (pit / kNPST) & 1;
-				const uint32_t stage = smem_u32(stage0) + st * stage_bytes;
-				const uint32_t pstage = smem_u32(pstage0) + pst * pstage_bytes;
-				mbar_wait(&full[st], ph);
+				const uint32_t stage = sbase + st * stage_bytes;
+				const uint32_t pstage = pstage0 + pst * pstage_bytes;
+				if (warp_reads_stage) mbar_wait(a_full + 8 * st, ph);
 
 				// ---------------- GF role ----------------
-				if (M > 0 && warp_has_items) {
-					if (PC > 0) mbar_wait(&pempty[pst], pph ^ 1);
-					for (uint32_t item = tid; item < n_items; item += kConsumers) {
+				if (M > 0 && warp_has_items && !LZ_PROBE(2)) {
+					if (PC > 0) mbar_wait(a_pempty + 8 * pst, pph ^ 1);
+					for (uint32_t item = vt; item < n_items; item += kConsumers) {
 						const uint32_t col = item & 7, q = (item >> 3) & 3, g = item >> 5;
 						uint32_t acc[M > 0 ? M : 1][4];
 #pragma unroll
 						for (int r = 0; r < M; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0;
+						// row (g*K + j)*4 + q: its swizzle (row & 7) = (4*((g*K + j) & 1) + q) alternates with j
 						const uint32_t rbase = g * K * 4 + q;
+						const uint32_t a_even = (stage + rbase * kStepBytes) ^ ((col ^ (rbase & 7)) << 4);
+						const uint32_t a_odd = (stage + rbase * kStepBytes) ^ ((col ^ ((rbase & 7) ^ 4)) << 4);
 #pragma unroll
 						for (int j = static_cast<int>(K) - 1; j >= 0; --j) {
-							const uint32_t row = rbase + 4u * j;
-							const uint4 v = lds128(stage + row * kStepBytes + ((col ^ (row & 7)) << 4));
+							const uint4 v = lds128(((j & 1) ? a_odd : a_even) + 4u * j * kStepBytes);
 							if (GENERIC) {
 #pragma unroll
 								for (int r = 0; r < M; ++r) {
@@ -265,15 +294,16 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 #pragma unroll
 									for (int w = 0; w < 4; ++w) {
 										uint32_t a = acc[r][w];
+										const uint32_t d = (w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w);
 #pragma unroll
-										for (int t = 0; t < r; ++t) a = gf_x2(a);  // times 2^r
-										acc[r][w] = a ^ (w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w);
+										for (int t = 0; t + 1 < r; ++t) a = gf_x2(a);  // times 2^r ...
+										acc[r][w] = r == 0 ? (a ^ d) : gf_x2_add(a, d);   // ... the last doubling fused with + d_j
 									}
 								}
 							}
 						}
 						const uint32_t stripe = stripe0 + g;
-						if (stripe < p.pb) {
+						if (stripe < p.pb && !LZ_PROBE(8)) {
 							uint8_t *dst = p.parity + c * p.parity_stride + (static_cast<unsigned long long>(stripe) << 16) +
 							               (q << 14) + step * kStepBytes + (col << 4);
 #pragma unroll
@@ -284,39 +314,47 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 #pragma unroll
 						for (int r = P0; r < M; ++r) {
 							const uint32_t pr = (g * PC + (r - P0)) * 4 + q;
-							sts128(pstage + pr * kStepBytes + ((col ^ (pr & 7)) << 4), make_uint4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
+							sts128((pstage + pr * kStepBytes) ^ ((col ^ (pr & 7)) << 4), make_uint4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
 						}
 					}
 					if (PC > 0) {
 						__syncwarp();
-						if (lane == 0) mbar_arrive(&pfull[pst]);
+						if (lane == 0) mbar_arrive(a_pfull + 8 * pst);
 					}
 				}
 
 				// ---------------- CRC role ----------------
-				if (PC > 0 && warp_has_prow) mbar_wait(&pfull[pst], pph);
-				if (has_stream) {
-					const uint32_t rowp = ((is_data_row ? stage : pstage) + row_off) ^ (row_swz << 4);
+				if (PC > 0 && warp_has_prow && !LZ_PROBE(2)) mbar_wait(a_pfull + 8 * pst, pph);
+				if (has_stream && !LZ_PROBE(4)) {
+					const uint32_t rowp = row_addr0 + (is_data_row ? st : pst) * row_stride;
 					if (half == 0) fold_step<0>(win, rowp);
 					else fold_step<32>(win, rowp);
 				}
 				__syncwarp();
 				if (lane == 0) {
-					mbar_arrive(&empty[st]);
-					if (PC > 0 && warp_has_prow) mbar_arrive(&pempty[pst]);
+					// release the data stage; the arrival that completes the phase refills it with the step NST ahead
+					if (warp_reads_stage && mbar_arrive_is_last(a_empty + 8 * st) && it + kNST < total_steps) {
+						asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+						if (step + kNST < kStepsPerUnit) issue_load(c, gi, step + kNST, st);
+						else issue_load(next_c, next_gi, step + kNST - kStepsPerUnit, st);
+					}
+					if (PC > 0 && warp_has_prow && !LZ_PROBE(2)) mbar_arrive(a_pempty + 8 * pst);
 				}
+				++it;
+				if (++st == kNST) { st = 0; ph ^= 1; }
+				if (++pst == kNPST) { pst = 0; pph ^= 1; }
 			}
 		}
 
 		// ---------------- unit epilogue: streams -> block CRCs ----------------
 		uint32_t lin = 0;
-		if (has_stream) lin = crc_mulmod(fold_finish(win, s_tab), p.qmult[my_row & 3]);
+		if (has_stream) lin = crc_mulmod(fold_finish(win, p.tables), p.qmult[my_row & 3]);
 		lin ^= __shfl_xor_sync(0xffffffffu, lin, 1);
 		lin ^= __shfl_xor_sync(0xffffffffu, lin, 2);
-		uint32_t *blk = s_blk + unit_parity * 64;
-		if (is_data_row && (tid & 3) == 0) {
-			const uint32_t b = stripe0 * K + (tid >> 2);  // block index in the chunk
-			if (M > 0 && !GENERIC) blk[tid >> 2] = lin;
+		const uint32_t blk = a_blk + unit_parity * 256;
+		if (is_data_row && (vt & 3) == 0) {
+			const uint32_t b = stripe0 * K + (vt >> 2);  // block index in the chunk
+			if (M > 0 && !GENERIC) asm volatile("st.shared.u32 [%0], %1;" ::"r"(blk + (vt & ~3u)), "r"(lin) : "memory");
 			if (b < p.nb) p.crc[c * p.crc_stride + b] = lin ^ p.zconst;
 		}
 		if (is_parity_row && (prow & 3) == 0) {
@@ -328,10 +366,14 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 		if (M > 0 && !GENERIC) {
 			// CRC of parity row 0 (plain XOR of the stripe): xor of the data blocks' linear CRCs
 			asm volatile("bar.sync 1, %0;" ::"r"(kConsumers) : "memory");
-			if (tid < G) {
+			if (vt < G) {
 				uint32_t x = 0;
-				for (uint32_t j = 0; j < K; ++j) x ^= blk[tid * K + j];
-				const uint32_t stripe = stripe0 + tid;
+				for (uint32_t j = 0; j < K; ++j) {
+					uint32_t t;
+					asm volatile("ld.shared.u32 %0, [%1];" : "=r"(t) : "r"(blk + 4 * (vt * K + j)));
+					x ^= t;
+				}
+				const uint32_t stripe = stripe0 + vt;
 				if (stripe < p.pb) p.crc[c * p.crc_stride + p.nb + stripe] = x ^ p.zconst;
 			}
 		}
