@@ -374,20 +374,20 @@ extern "C" int lzgpu_encode_chunks(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint3
 	}
 	std::lock_guard<std::mutex> lk(ctx->mu);
 	DeviceGuard g(ctx->device);
-	// two-slot pipeline: tile t uses slot t&1 with its own stream, so the H2D of one tile overlaps the
-	// kernels / D2H of the other.
+	// slot pipeline: tile t uses slot t % kHostSlots with its own stream, so the H2D of one tile overlaps the
+	// kernel of the previous and the D2H of the one before (both copy engines + compute busy).
 	const size_t d_chunk_stride = static_cast<size_t>(nb) * B;
 	const size_t d_crc_stride = (n_crc + 3) & ~size_t(3);
 	const uint32_t tile = std::max<uint32_t>(1, std::min<uint32_t>(n_chunks, kHostTileBytes / LZGPU_CHUNK_SIZE));
-	void *d_in[2], *d_par[2], *d_c[2];
-	for (int s = 0; s < 2; ++s) {
+	void *d_in[kHostSlots], *d_par[kHostSlots], *d_c[kHostSlots];
+	for (int s = 0; s < kHostSlots; ++s) {
 		if ((rc = lz_scratch(ctx, kScratchIn0 + s, tile * d_chunk_stride, &d_in[s]))) return rc;
 		if ((rc = lz_scratch(ctx, kScratchPar0 + s, tile * par_bytes, &d_par[s]))) return rc;
 		if ((rc = lz_scratch(ctx, kScratchCrc0 + s, tile * d_crc_stride * 4, &d_c[s]))) return rc;
 	}
 	for (uint32_t c0 = 0, t = 0; c0 < n_chunks; c0 += tile, ++t) {
 		const uint32_t n = std::min(tile, n_chunks - c0);
-		const int s = t & 1;
+		const int s = t % kHostSlots;
 		cudaStream_t st = ctx->slot_stream[s];
 		CUDA_TRY(cudaMemcpy2DAsync(d_in[s], d_chunk_stride, data + static_cast<size_t>(c0) * chunk_stride, chunk_stride, chunk_len, n,
 		                           cudaMemcpyHostToDevice, st));
@@ -400,8 +400,7 @@ extern "C" int lzgpu_encode_chunks(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint3
 		ctx->stats.bytes_h2d += static_cast<uint64_t>(n) * chunk_len;
 		ctx->stats.bytes_d2h += static_cast<uint64_t>(n) * (par_bytes + n_crc * 4);
 	}
-	CUDA_TRY(cudaStreamSynchronize(ctx->slot_stream[0]));
-	CUDA_TRY(cudaStreamSynchronize(ctx->slot_stream[1]));
+	for (auto &ss : ctx->slot_stream) CUDA_TRY(cudaStreamSynchronize(ss));
 	return LZGPU_OK;
 }
 

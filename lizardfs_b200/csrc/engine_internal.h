@@ -23,10 +23,11 @@ void lz_set_error(const char *fmt, ...);
 		}                                                                                      \
 	} while (0)
 
-constexpr size_t kHostTileBytes = size_t(512) << 20;  // staging tile of the host-pointer entry points
+constexpr size_t kHostTileBytes = size_t(128) << 20;  // staging tile of the host-pointer entry points
+constexpr int kHostSlots = 3;                          // tiles in flight: H2D(t+1) | kernel(t) | D2H(t-1)
 constexpr int kCoefSlots = 8;
 enum ScratchSlot {
-	kScratchIn0 = 0, kScratchIn1, kScratchPar0, kScratchPar1, kScratchCrc0, kScratchCrc1, kScratchTmpCrc,
+	kScratchIn0 = 0, kScratchIn1, kScratchIn2, kScratchPar0, kScratchPar1, kScratchPar2, kScratchCrc0, kScratchCrc1, kScratchCrc2, kScratchTmpCrc,
 	kScratchCoef0, kScratchCoefLast = kScratchCoef0 + kCoefSlots - 1,
 	kScratchFused0, kScratchFused1,
 	kScratchTmpPart0, kScratchTmpPartLast = kScratchTmpPart0 + LZGPU_MAX_PARTS - 1,
@@ -44,7 +45,7 @@ struct lzgpu_ctx {
 	int device = 0;
 	int sm_count = 0;
 	cudaStream_t stream = nullptr;
-	cudaStream_t slot_stream[2] = {nullptr, nullptr};
+	cudaStream_t slot_stream[kHostSlots] = {nullptr, nullptr, nullptr};
 	cudaEvent_t ev_a = nullptr, ev_b = nullptr;
 	uint32_t *d_crc_tables = nullptr;
 	unsigned long long *d_first_bad = nullptr, *h_first_bad = nullptr;

@@ -1,0 +1,26 @@
+"""Runs the C++ restatement of the reference's unit tests (tests/cpp/test_reference_api.cc) — the host side
+above the C ABI written in the reference's own language, through the reference-named interfaces."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "cpp", "build", "test_reference_api")
+
+
+def test_cpp_binary_is_built():
+    """CPU-side check: the binary exists (built by __graft_entry__.build()) and links against liblzgpu.so."""
+    if not os.path.exists(BIN):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")], check=True)
+    out = subprocess.run(["ldd", BIN], capture_output=True, text=True).stdout
+    assert "liblzgpu.so" in out and "not found" not in out.split("liblzgpu.so")[1].split("\n")[0]
+
+
+@pytest.mark.gpu
+def test_reference_api_cpp():
+    if not os.path.exists(BIN):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")], check=True)
+    r = subprocess.run([BIN], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "passed" in r.stdout
