@@ -434,6 +434,30 @@ extern "C" int lzgpu_recover_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, 
 	}
 	if (used < k) { lz_set_error("recover: only %d of %d required parts available", used, k); return LZGPU_ERR_TOO_FEW_PARTS; }
 
+	// 0. fused route: verify + rebuild the erased data parts + chunk-order image in one pass over the inputs
+	{
+		bool fused_verifying = false;
+		rc = lz_fused_recover(ctx, goal, n_chunks, nb, d_parts, part_stride, d_part_crc, want, d_out, d_chunk_out, chunk_out_stride, st,
+		                      &fused_verifying);
+		if (rc != LZGPU_NOT_HANDLED) {
+			if (rc) return rc;
+			ctx->stats.chunks_recovered += n_chunks;
+			if (fused_verifying && bad) {
+				CUDA_TRY(cudaMemcpyAsync(ctx->h_first_bad, ctx->d_first_bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+				CUDA_TRY(cudaStreamSynchronize(st));
+				const unsigned long long v = ctx->h_first_bad[0];
+				if (v != ~0ull) {
+					bad[0] = static_cast<int64_t>(v / (64ull * 1024ull));
+					bad[1] = static_cast<int64_t>((v / 1024ull) % 64ull);
+					bad[2] = static_cast<int64_t>(v % 1024ull);
+					lz_set_error("CRC mismatch: chunk %lld part %lld block %lld", (long long)bad[0], (long long)bad[1], (long long)bad[2]);
+					return LZGPU_ERR_CRC;
+				}
+			}
+			return LZGPU_OK;
+		}
+	}
+
 	// 1. verify the stored CRC of every block of every supplied part (read_operation_executor.cc:257-269)
 	bool verifying = false;
 	if (d_part_crc) {

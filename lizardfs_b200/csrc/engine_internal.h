@@ -78,6 +78,11 @@ int lz_fused_init(lzgpu_ctx *ctx);
 void lz_fused_destroy(lzgpu_ctx *ctx);
 int lz_fused_encode(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb, const void *d_data, size_t chunk_stride,
                     void *d_parity, size_t parity_stride, void *d_crc, size_t crc_stride, cudaStream_t st);
+// Fused degraded read (verify + rebuild erased data parts + chunk-order image).  On success *handled = true and, when
+// any part was verified, first-bad information sits in ctx->d_first_bad[0] encoded as (chunk*64 + part)*1024 + block.
+int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb, const void *const *d_parts, size_t part_stride,
+                     const void *const *d_part_crc, const uint8_t *want, void *const *d_out, void *d_chunk_out, size_t chunk_out_stride,
+                     cudaStream_t st, bool *verifying);
 // CRC of 64 KiB blocks: block (c, b) at base + c*chunk_stride + b*65536, out[c*out_chunk_stride + b]
 int lz_fused_crc(lzgpu_ctx *ctx, const void *base, unsigned long long n_blocks, unsigned long long blocks_per_chunk,
                  unsigned long long chunk_stride, void *out, unsigned long long out_chunk_stride, cudaStream_t st);

@@ -20,6 +20,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 
 // two CTAs per SM: 228 KiB per SM minus 1 KiB reserved per CTA
 constexpr int kSmemCap = 113 * 1024;
+constexpr int kRecoverSmemCap = 200 * 1024;  // recover kernel: one CTA per SM, 6 stages
 
 struct FusedState {
 	EncodeTiledFn encode_tiled = nullptr;
@@ -213,4 +214,144 @@ int lz_fused_crc(lzgpu_ctx *ctx, const void *base, unsigned long long n_blocks, 
 	// CRC only: "K" = 64 blocks per unit, one stripe group per unit, no parity
 	return fused_run(ctx, 0, false, nullptr, 64, static_cast<uint32_t>(n_chunks), static_cast<uint32_t>(blocks_per_chunk), base, chunk_stride,
 	                 nullptr, 0, out, out_chunk_stride, st);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fused degraded read
+// ---------------------------------------------------------------------------------------------------
+template <int E, int KT, int R0 = -1, int R1 = -1>
+static int launch_recover(lzgpu_ctx *ctx, const TmapArray &maps, const RecoverParams &p, size_t smem, cudaStream_t st) {
+	static bool attr_set = false;  // per instantiation; contexts share the device function attribute
+	if (!attr_set) {
+		CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<E, KT, R0, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCap));
+		attr_set = true;
+	}
+	const int grid = static_cast<int>(std::min<uint64_t>(p.total_units, static_cast<uint64_t>(ctx->sm_count)));
+	fused_recover_kernel<E, KT, R0, R1><<<grid, kFusedThreads, smem, st>>>(maps, p);
+	CUDA_TRY(cudaGetLastError());
+	ctx->stats.kernel_launches++;
+	return LZGPU_OK;
+}
+
+int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb, const void *const *d_parts, size_t part_stride,
+                     const void *const *d_part_crc, const uint8_t *want, void *const *d_out, void *d_chunk_out, size_t chunk_out_stride,
+                     cudaStream_t st, bool *verifying) {
+	FusedState *fs = ctx->fused;
+	*verifying = false;
+	if (!fs || fs->disabled) return LZGPU_NOT_HANDLED;
+	const int K = goal->k, M = goal->m, N = K + M;
+	if (lz::uses_cauchy(K, M)) return LZGPU_NOT_HANDLED;
+	if ((part_stride % 16) || (chunk_out_stride % 16)) return LZGPU_NOT_HANDLED;
+	// inputs: the first k available parts (ec_read_plan.h:126-133)
+	int used[LZGPU_MAX_DATA], n_used = 0;
+	for (int i = 0; i < N && n_used < K; ++i)
+		if (d_parts[i]) used[n_used++] = i;
+	if (n_used < K) return LZGPU_NOT_HANDLED;
+	RecoverParams p{};
+	std::memset(p.slot_of_data, 0xff, sizeof(p.slot_of_data));
+	uint32_t e = 0, n_par = 0;
+	for (int a = 0; a < K; ++a) {
+		const int idx = used[a];
+		p.part_id[a] = static_cast<uint8_t>(idx);
+		if (idx < K) p.slot_of_data[idx] = static_cast<uint8_t>(a);
+		else if (n_par < 4) { p.par_slot[n_par] = static_cast<uint8_t>(a); p.par_row[n_par] = static_cast<uint8_t>(idx - K); ++n_par; }
+		else return LZGPU_NOT_HANDLED;
+	}
+	for (int j = 0; j < K; ++j)
+		if (p.slot_of_data[j] == 0xff) {
+			if (e >= 4) return LZGPU_NOT_HANDLED;
+			p.erased_idx[e++] = static_cast<uint8_t>(j);
+		}
+	if (e == 0 || e != n_par) return LZGPU_NOT_HANDLED;
+	// every requested missing part must be a data part
+	for (int i = K; i < N; ++i)
+		if (want[i] && !d_parts[i] && d_out && d_out[i]) return LZGPU_NOT_HANDLED;
+	// geometry: even G (1024-byte aligned slot regions), K*G*4 rows <= 256
+	uint32_t G = 0;
+	for (uint32_t g = 2; g <= 64; g += 2) {
+		const uint32_t rows = K * g * 4;
+		if (rows > kMaxRows || static_cast<size_t>(kRecoverStages) * rows * kStepBytes + 256 > static_cast<size_t>(kRecoverSmemCap)) break;
+		G = g;
+	}
+	if (G == 0) return LZGPU_NOT_HANDLED;
+	const uint32_t pb = (nb + K - 1) / K;
+	for (uint32_t x = 0; x < e; ++x) {
+		const int j = p.erased_idx[x];
+		void *o = d_out ? d_out[j] : nullptr;
+		p.out[x] = (want[j] || d_chunk_out) ? static_cast<uint8_t *>(o) : nullptr;
+		if (!p.out[x] && !d_chunk_out) {}  // nothing requested for this part: still solved (cheap), not stored
+	}
+	p.image = static_cast<uint8_t *>(d_chunk_out);
+	p.out_stride = part_stride;
+	p.image_stride = chunk_out_stride;
+	p.tables = ctx->d_crc_tables;
+	p.first_bad = ctx->d_first_bad;
+	p.n_chunks = n_chunks;
+	p.nb = nb;
+	p.pb = pb;
+	p.K = K;
+	p.G = G;
+	p.units_per_chunk = (pb + G - 1) / G;
+	const uint64_t total = static_cast<uint64_t>(p.units_per_chunk) * n_chunks;
+	if (total > 0x7fffffffull) return LZGPU_NOT_HANDLED;
+	p.total_units = static_cast<uint32_t>(total);
+	p.e = e;
+	std::memcpy(p.qmult, fs->qmult, sizeof(p.qmult));
+	p.zconst = lz::crc_of_zeros(LZGPU_BLOCK_SIZE);
+	for (int a = 0; a < K; ++a) {
+		p.stored[a] = d_part_crc ? static_cast<const uint32_t *>(d_part_crc[used[a]]) : nullptr;
+		if (p.stored[a]) *verifying = true;
+	}
+	// V[r][x] = (2^row_r)^(erased_x); W = V^-1
+	uint8_t V[16], W[16];
+	for (uint32_t r = 0; r < e; ++r) {
+		uint8_t gen = 1;
+		for (int t = 0; t < p.par_row[r]; ++t) gen = lz::gf_mul_host(gen, 2);
+		for (uint32_t x = 0; x < e; ++x) {
+			uint8_t v = 1;
+			for (int t = 0; t < p.erased_idx[x]; ++t) v = lz::gf_mul_host(v, gen);
+			V[r * e + x] = v;
+		}
+	}
+	if (gf_invert_matrix(V, W, static_cast<int>(e)) != 0) return LZGPU_NOT_HANDLED;  // generic path reports the singular case
+	for (uint32_t x = 0; x < e; ++x)
+		for (uint32_t r = 0; r < e; ++r) {
+			uint8_t v = W[x * e + r];
+			for (int b = 0; b < 8; ++b) {
+				p.w[x * 4 + r].plane[b] = v;
+				v = lz::gf_mul_host(v, 2);
+			}
+		}
+	TmapArray maps;
+	for (int a = 0; a < K; ++a) {
+		const cuuint64_t dims[3] = {static_cast<cuuint64_t>(kRowBytes), static_cast<cuuint64_t>(pb) * 4, n_chunks};
+		const cuuint64_t strides[2] = {static_cast<cuuint64_t>(kRowBytes), part_stride};
+		const cuuint32_t box[3] = {kStepBytes, G * 4, 1};
+		const cuuint32_t estr[3] = {1, 1, 1};
+		CUresult r = fs->encode_tiled(&maps.m[a], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(d_parts[used[a]]), dims, strides, box, estr,
+		                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, static_cast<CUtensorMapL2promotion>(fs->promo),
+		                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+		if (r != CUDA_SUCCESS) return LZGPU_NOT_HANDLED;
+	}
+	if (*verifying) {
+		static const unsigned long long kNone = ~0ull;
+		CUDA_TRY(cudaMemcpyAsync(ctx->d_first_bad, &kNone, sizeof(kNone), cudaMemcpyHostToDevice, st));
+	}
+	const size_t smem = static_cast<size_t>(kRecoverStages) * K * G * 4 * kStepBytes + 16 * kRecoverStages + 64;
+	const bool k8 = K == 8 && G == 8;
+	const bool row0 = p.par_row[0] == 0, row01 = row0 && e >= 2 && p.par_row[1] == 1;
+	switch (e) {
+		case 1:
+			if (row0) return k8 ? launch_recover<1, 8, 0>(ctx, maps, p, smem, st) : launch_recover<1, 0, 0>(ctx, maps, p, smem, st);
+			return launch_recover<1, 0>(ctx, maps, p, smem, st);
+		case 2:
+			if (row01) return k8 ? launch_recover<2, 8, 0, 1>(ctx, maps, p, smem, st) : launch_recover<2, 0, 0, 1>(ctx, maps, p, smem, st);
+			return launch_recover<2, 0>(ctx, maps, p, smem, st);
+		case 3:
+			if (row01) return launch_recover<3, 0, 0, 1>(ctx, maps, p, smem, st);
+			return launch_recover<3, 0>(ctx, maps, p, smem, st);
+		default:
+			if (row01) return launch_recover<4, 0, 0, 1>(ctx, maps, p, smem, st);
+			return launch_recover<4, 0>(ctx, maps, p, smem, st);
+	}
 }

@@ -380,4 +380,215 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 	}
 }
 
+// =====================================================================================================
+// fused_recover_kernel — degraded read in ONE pass: verify the stored CRC of every input block, rebuild the
+// erased data parts, and scatter everything into the chunk-order image.
+// Replaces, per chunk: mycrc32 per received block (reference src/common/read_operation_executor.cc:257-269),
+// ECReadPlan::recoverParts / XorReadPlan::postProcessRead (src/common/ec_read_plan.h:113-146,
+// xor_read_plan.h:77-126) and the BlockConverter memcpy pass (src/common/chunk_read_planner.h:36-70).
+//
+// Inputs are the k parts the reference would use (first k available, ec_read_plan.h:126-133), part-major.
+// For a Vandermonde generator (rows g_r^j, g_r = 2^r) with e erased data parts X and e parity rows R in use:
+//   S_r = p_r ^ sum_{j not in X} g_r^j d_j  =  sum_{x in X} g_r^x d_x        (Horner, one pass over the columns)
+//   d_X = V^-1 S,  V[r][x] = g_r^x                                           (e x e general multiplies per column)
+// which is the unique solution the reference's inverted k x k matrix produces (reed_solomon.h:229-281), so
+// the bytes are identical, at RAID-6-like cost instead of an e x k general product per byte.
+//
+// Shared-memory stage: [slot a][stripe g][quarter q] rows of 128 B (one TMA box per used part per step).
+struct TmapArray {
+	CUtensorMap m[32];
+};
+
+struct RecoverParams {
+	uint8_t *out[4];               // rebuilt data part x (part-major) or nullptr
+	uint8_t *image;                // chunk-order image or nullptr
+	const uint32_t *stored[32];    // stored CRCs of used slot a (chunk c at + c*pb) or nullptr = not verified
+	const uint32_t *tables;
+	unsigned long long *first_bad; // atomicMin target: (c * 64 + part) * 1024 + block
+	unsigned long long out_stride, image_stride;
+	uint32_t n_chunks, nb, pb, K, G, units_per_chunk, total_units;
+	uint32_t e;                    // erased data parts (1..4)
+	uint8_t slot_of_data[32];      // data index j -> slot, 0xff = erased
+	uint8_t erased_idx[4];         // data index of erased part x
+	uint8_t par_slot[4], par_row[4];  // parity rows in use: slot and generator row r
+	uint8_t part_id[32];           // slot -> part index (error reporting)
+	uint32_t qmult[4];
+	uint32_t zconst;
+	CoefPlanes w[16];              // W = V^-1, w[x*4 + r]
+};
+
+// E = erased data parts; KT = compile-time K (0 = runtime); R0, R1 = generator rows of the first two parity
+// parts in use when known at compile time (-1 = read p.par_row): the RAID-6 shapes (row 0 = XOR, row 1 = powers of 2)
+// get constant doubling counts and the "last unknown = S0 ^ others" shortcut.
+// One CTA per SM (the solve needs registers: no spills at <= 224 per thread) with a deeper stage ring instead.
+constexpr int kRecoverStages = 6;
+
+template <int E, int KT, int R0, int R1>
+__global__ void __launch_bounds__(kFusedThreads, 1)
+fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_constant__ RecoverParams p) {
+	extern __shared__ __align__(1024) uint8_t smem[];
+	const uint32_t sbase = smem_u32(smem);
+	const uint32_t K = KT ? KT : p.K, G = p.G;
+	const uint32_t RG = G * 4;                       // rows per slot region
+	const uint32_t ROWS = K * RG;
+	const uint32_t region_bytes = RG * kStepBytes;   // multiple of 1024 (G even)
+	const uint32_t stage_bytes = ROWS * kStepBytes;
+	const uint32_t misc = sbase + kRecoverStages * stage_bytes;
+	const uint32_t a_full = misc, a_empty = a_full + 8 * kRecoverStages;
+
+	const uint32_t tid = threadIdx.x, lane = tid & 31, cw = tid >> 5;
+	const uint32_t n_items = 32 * G;
+	const uint32_t n_gf_warps = (min(n_items, (uint32_t)kConsumers) + 31) / 32;
+	const uint32_t n_stage_warps = max((ROWS + 31) / 32, n_gf_warps);
+	const uint32_t my_units = blockIdx.x < p.total_units ? (p.total_units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+	const uint32_t total_steps = my_units * kStepsPerUnit;
+
+	auto issue_load = [&](uint32_t c, uint32_t gi, uint32_t step, uint32_t st) {
+		mbar_expect_tx(a_full + 8 * st, stage_bytes);
+		for (uint32_t a = 0; a < K; ++a)
+			tma_load_3d(sbase + st * stage_bytes + a * region_bytes, &tmaps.m[a], static_cast<int>(step * kStepBytes),
+			            static_cast<int>(gi * RG), static_cast<int>(c), a_full + 8 * st);
+	};
+
+	if (tid == 0) {
+		for (int s = 0; s < kRecoverStages; ++s) {
+			mbar_init(a_full + 8 * s, 1);
+			mbar_init(a_empty + 8 * s, n_stage_warps);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		if (total_steps)
+			for (uint32_t g0 = 0; g0 < kRecoverStages; ++g0) issue_load(blockIdx.x / p.units_per_chunk, blockIdx.x % p.units_per_chunk, g0, g0);
+	}
+	__syncthreads();
+	if (cw >= n_stage_warps) return;
+
+	const bool has_stream = tid < ROWS;
+	const uint32_t slot = tid / RG, rr = tid % RG;           // this thread's stream: slot `slot`, block rr/4, quarter rr%4
+	const bool verify = has_stream && p.stored[has_stream ? slot : 0] != nullptr;
+	const uint32_t row_addr0 = (sbase + tid * kStepBytes) ^ ((tid & 7) << 4);
+	const bool warp_has_items = cw < n_gf_warps;
+
+	uint32_t win[64];
+	uint32_t it = 0, st = 0, ph = 0;
+	for (uint32_t unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
+		const uint32_t c = unit / p.units_per_chunk, gi = unit % p.units_per_chunk;
+		const uint32_t stripe0 = gi * G;
+		const uint32_t next_unit = unit + gridDim.x;
+		const uint32_t next_c = next_unit / p.units_per_chunk, next_gi = next_unit % p.units_per_chunk;
+#pragma unroll
+		for (int i = 0; i < 64; ++i) win[i] = 0;
+
+		for (int step2 = 0; step2 < kStepsPerUnit; step2 += 2) {
+#pragma unroll
+			for (int half = 0; half < 2; ++half) {
+				const int step = step2 + half;
+				const uint32_t stage = sbase + st * stage_bytes;
+				mbar_wait(a_full + 8 * st, ph);
+
+				// ---------------- GF role: syndromes, solve, scatter ----------------
+				if (warp_has_items) {
+					for (uint32_t item = tid; item < n_items; item += kConsumers) {
+						const uint32_t col = item & 7, q = (item >> 3) & 3, g = item >> 5;
+						const uint32_t r0 = g * 4 + q;   // row inside every slot region; region bases are multiples of 8 rows
+						const uint32_t a_item = (stage + r0 * kStepBytes) ^ ((col ^ (r0 & 7)) << 4);
+						const uint32_t stripe = stripe0 + g;
+						const unsigned long long in_block = (static_cast<unsigned long long>(q) << 14) + step * kStepBytes + (col << 4);
+						uint8_t *img = p.image ? p.image + c * p.image_stride + in_block : nullptr;
+						uint32_t acc[E][4];
+#pragma unroll
+						for (int r = 0; r < E; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0;
+#pragma unroll
+						for (int j = static_cast<int>(K) - 1; j >= 0; --j) {
+							const uint32_t sl = p.slot_of_data[j];
+							uint4 v = make_uint4(0, 0, 0, 0);
+							if (sl != 0xff) {
+								v = lds128(a_item + sl * region_bytes);
+								const uint32_t b = stripe * K + j;
+								if (img && b < p.nb) st_stream(reinterpret_cast<uint4 *>(img + (static_cast<unsigned long long>(b) << 16)), v);
+							}
+#pragma unroll
+							for (int r = 0; r < E; ++r) {
+								const int fixed = r == 0 ? R0 : (r == 1 ? R1 : -1);
+								const uint32_t dbl = fixed >= 0 ? static_cast<uint32_t>(fixed) : p.par_row[r];
+#pragma unroll
+								for (int w = 0; w < 4; ++w) {
+									uint32_t a = acc[r][w];
+									const uint32_t d = (w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w);
+									if (fixed == 0) a ^= d;
+									else if (fixed == 1) a = gf_x2_add(a, d);
+									else {
+										for (uint32_t t = 0; t < dbl; ++t) a = gf_x2(a);
+										a ^= d;
+									}
+									acc[r][w] = a;
+								}
+							}
+						}
+						// S_r = acc_r ^ p_r
+#pragma unroll
+						for (int r = 0; r < E; ++r) {
+							const uint4 pv = lds128(a_item + p.par_slot[r] * region_bytes);
+							acc[r][0] ^= pv.x; acc[r][1] ^= pv.y; acc[r][2] ^= pv.z; acc[r][3] ^= pv.w;
+						}
+						// d_x = sum_r W[x][r] * S_r.  When parity row 0 (all ones) is in use, S_0 = xor of all unknowns,
+						// so the last unknown is S_0 ^ (the others) and needs no multiply.
+						uint32_t others[4] = {0, 0, 0, 0};
+#pragma unroll
+						for (int x = 0; x < E; ++x) {
+							uint32_t d[4] = {0, 0, 0, 0};
+							if (R0 == 0 && x == E - 1) {
+#pragma unroll
+								for (int w = 0; w < 4; ++w) d[w] = acc[0][w] ^ others[w];
+							} else {
+#pragma unroll
+								for (int r = 0; r < E; ++r) {
+									const CoefPlanes &cp = p.w[x * 4 + r];
+#pragma unroll
+									for (int w = 0; w < 4; ++w) d[w] = gf_mac(d[w], acc[r][w], cp);
+								}
+#pragma unroll
+								for (int w = 0; w < 4; ++w) others[w] ^= d[w];
+							}
+							const uint4 dv = make_uint4(d[0], d[1], d[2], d[3]);
+							if (p.out[x] && stripe < p.pb)
+								st_stream(reinterpret_cast<uint4 *>(p.out[x] + c * p.out_stride + (static_cast<unsigned long long>(stripe) << 16) + in_block), dv);
+							const uint32_t b = stripe * K + p.erased_idx[x];
+							if (img && b < p.nb) st_stream(reinterpret_cast<uint4 *>(img + (static_cast<unsigned long long>(b) << 16)), dv);
+						}
+					}
+				}
+
+				// ---------------- CRC role: linear CRC of every input row ----------------
+				if (verify) {
+					const uint32_t rowp = row_addr0 + st * stage_bytes;
+					if (half == 0) fold_step<0>(win, rowp);
+					else fold_step<32>(win, rowp);
+				}
+				__syncwarp();
+				if (lane == 0 && mbar_arrive_is_last(a_empty + 8 * st) && it + kRecoverStages < total_steps) {
+					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+					if (step + kRecoverStages < kStepsPerUnit) issue_load(c, gi, step + kRecoverStages, st);
+					else issue_load(next_c, next_gi, step + kRecoverStages - kStepsPerUnit, st);
+				}
+				++it;
+				if (++st == kRecoverStages) { st = 0; ph ^= 1; }
+			}
+		}
+
+		// ---------------- unit epilogue: compare with the stored CRCs ----------------
+		uint32_t lin = 0;
+		if (verify) lin = crc_mulmod(fold_finish(win, p.tables), p.qmult[rr & 3]);
+		lin ^= __shfl_xor_sync(0xffffffffu, lin, 1);
+		lin ^= __shfl_xor_sync(0xffffffffu, lin, 2);
+		if (verify && (rr & 3) == 0) {
+			const uint32_t s = stripe0 + (rr >> 2);
+			if (s < p.pb) {
+				const uint32_t have = lin ^ p.zconst;
+				const uint32_t want = __ldg(p.stored[slot] + static_cast<unsigned long long>(c) * p.pb + s);
+				if (have != want) atomicMin(p.first_bad, (static_cast<unsigned long long>(c) * 64ull + p.part_id[slot]) * 1024ull + s);
+			}
+		}
+	}
+}
+
 }  // namespace lzd

@@ -1,0 +1,143 @@
+#!/usr/bin/env python
+"""Mixed-goal sweep (BASELINE.json configs[1], [3], [4]): GiB/s of chunk data and fraction of the measured HBM
+peak for encode+CRC over goals x chunk sizes, and for degraded-read recover, inputs resident in HBM, one GPU.
+Writes a markdown table (default gpurun_out/sweep.md).  Not the headline bench — that is bench.py."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import lizardfs_b200 as L  # noqa: E402
+
+BLOCK = 65536
+GIB = float(1 << 30)
+
+
+def alg_bytes_encode(k, m, chunk_len):
+    nb = (chunk_len + BLOCK - 1) // BLOCK
+    pb = (nb + k - 1) // k
+    return chunk_len + m * pb * BLOCK + 4 * (nb + m * pb)
+
+
+def time_steps(fn, steps, warmup, stream):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record(stream)
+    for _ in range(steps):
+        fn()
+    ev[1].record(stream)
+    torch.cuda.synchronize()
+    return ev[0].elapsed_time(ev[1]) / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.md"))
+    ap.add_argument("--bytes", type=int, default=8 << 30, help="chunk data per launch")
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    eng = L.Engine(0)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    sp = stream.cuda_stream
+    peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks))["hbm_gbs"]) if os.path.exists(peaks) else 6650.0
+    lines = ["# Mixed-goal sweep, 1 x B200, inputs resident in HBM", "",
+             f"`python tools/sweep.py` — {args.bytes / GIB:.0f} GiB of chunk data per launch, {args.steps} timed launches, CUDA events; "
+             f"frac = algorithmic bytes / time / {peak:.1f} GB/s (measured HBM copy peak).", "",
+             "## encode + per-block CRC32", "", "| goal | chunk | chunks/launch | ms | GiB/s data | GB/s algorithmic | frac of measured HBM |", "|---|---|---|---|---|---|---|"]
+    goals = ["xor2", "xor3", "ec(3,2)", "ec(5,3)", "ec(8,2)", "ec(8,4)"]
+    sizes = [1 << 20, 4 << 20, 16 << 20, 64 << 20, (37 << 20) + 5 * BLOCK]
+    if args.quick:
+        goals, sizes = ["ec(3,2)", "ec(8,2)"], [64 << 20]
+    d_data = torch.empty(args.bytes, dtype=torch.uint8, device=dev)
+    eng.fill_chunks_dev(d_data.data_ptr(), args.bytes // (64 << 20), 64 << 20, 64 << 20, seed=12345, stream=sp)
+    for text in goals:
+        g = L.SliceType(text)
+        for clen in sizes:
+            nb = (clen + BLOCK - 1) // BLOCK
+            pb = (nb + g.k - 1) // g.k
+            stride = nb * BLOCK
+            n = args.bytes // stride
+            par_stride, crc_stride = g.m * pb * BLOCK, nb + g.m * pb
+            d_par = torch.empty(n * par_stride, dtype=torch.uint8, device=dev)
+            d_crc = torch.empty(n * crc_stride, dtype=torch.int32, device=dev)
+            ms = time_steps(lambda: eng.encode_chunks_dev(g, n, clen, d_data.data_ptr(), stride, d_par.data_ptr(), par_stride,
+                                                          d_crc.data_ptr(), crc_stride, stream=sp), args.steps, args.warmup, stream)
+            gibs = n * clen / GIB / (ms / 1e3)
+            gbs = n * alg_bytes_encode(g.k, g.m, clen) / (ms / 1e3) / 1e9
+            label = f"{clen / (1 << 20):.2f} MiB"
+            lines.append(f"| {text} | {label} | {n} | {ms:.3f} | {gibs:.0f} | {gbs:.0f} | {gbs / peak:.3f} |")
+            del d_par, d_crc
+    # degraded read: ec(8,2), data parts 1 and 4 lost (BASELINE configs[3]); also ec(3,2) / ec(5,3) / xor3
+    lines += ["", "## degraded-read recover (stored CRCs verified, chunk-order image written)", "",
+              "| goal | lost parts | chunks/launch | variant | ms | GiB/s chunk data | GB/s algorithmic | frac |", "|---|---|---|---|---|---|---|---|"]
+    cases = [("ec(8,2)", (1, 4)), ("ec(8,2)", (0,)), ("ec(3,2)", (0, 2)), ("ec(5,3)", (0, 1, 4)), ("xor3", (1,))]
+    if args.quick:
+        cases = cases[:1]
+    clen = 64 << 20
+    nb = clen // BLOCK
+    for text, lost in cases:
+        g = L.SliceType(text)
+        k, m = g.k, g.m
+        pb = (nb + k - 1) // k
+        n = min(args.bytes // clen, 64)
+        part_stride = pb * BLOCK
+        # build part-major parts from an encode of the resident data (parity) + a gather of the data parts on the host side of torch
+        d_par = torch.empty(n * m * part_stride, dtype=torch.uint8, device=dev)
+        d_crc = torch.empty(n * (nb + m * pb), dtype=torch.int32, device=dev)
+        eng.encode_chunks_dev(g, n, clen, d_data.data_ptr(), clen, d_par.data_ptr(), m * part_stride, d_crc.data_ptr(), nb + m * pb, stream=sp)
+        torch.cuda.synchronize()
+        chunks = d_data[: n * clen].view(n, nb, BLOCK)
+        parts, pcrc = [], []
+        crc_all = d_crc.view(n, nb + m * pb)
+        for j in range(k):
+            pj = torch.zeros((n, pb, BLOCK), dtype=torch.uint8, device=dev)
+            blk = chunks[:, j::k]
+            pj[:, : blk.shape[1]] = blk
+            parts.append(pj.contiguous())
+            cj = torch.full((n, pb), -0x28687115, dtype=torch.int32, device=dev)  # 0xD7978EEB as int32 (zero padding blocks)
+            cj[:, : blk.shape[1]] = crc_all[:, j:nb:k]
+            pcrc.append(cj.contiguous())
+        for r in range(m):
+            parts.append(d_par.view(n, m, part_stride)[:, r].contiguous())
+            pcrc.append(crc_all[:, nb + r * pb: nb + (r + 1) * pb].contiguous())
+        outs = [torch.empty((n, part_stride), dtype=torch.uint8, device=dev) if i in lost else None for i in range(k + m)]
+        img = torch.empty((n, nb * BLOCK), dtype=torch.uint8, device=dev)
+        dp = [0 if i in lost else parts[i].data_ptr() for i in range(k + m)]
+        dc = [0 if i in lost else pcrc[i].data_ptr() for i in range(k + m)]
+        do = [outs[i].data_ptr() if i in lost else 0 for i in range(k + m)]
+        want = [1 if i in lost else 0 for i in range(k + m)]
+        e = len([i for i in lost if i < k])
+        for variant, crcs, image in [("recover only", None, None), ("verify + recover + image", dc, img)]:
+            ms = time_steps(lambda: eng.recover_chunks_dev(g, n, nb, dp, part_stride, crcs, want, do, image.data_ptr() if image is not None else None,
+                                                           nb * BLOCK, stream=sp), args.steps, args.warmup, stream)
+            alg = k * pb * BLOCK + e * pb * BLOCK + (4 * k * pb + nb * BLOCK if crcs is not None else 0)
+            gibs = n * clen / GIB / (ms / 1e3)
+            gbs = n * alg / (ms / 1e3) / 1e9
+            lines.append(f"| {text} | {list(lost)} | {n} | {variant} | {ms:.3f} | {gibs:.0f} | {gbs:.0f} | {gbs / peak:.3f} |")
+        # correctness spot check of the timed outputs
+        torch.cuda.synchronize()
+        for i in lost:
+            if i < k:
+                assert torch.equal(outs[i].view(n, pb, BLOCK), parts[i]), (text, i)
+        assert torch.equal(img.view(n, nb, BLOCK), chunks)
+        del parts, pcrc, outs, img, d_par, d_crc
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    open(args.out, "w").write("\n".join(lines) + "\n")
+    print("\n".join(lines))
+
+
+if __name__ == "__main__":
+    main()
