@@ -34,6 +34,21 @@ GIB = float(1 << 30)
 METRIC = "GiB/s encoded+CRC (ec(8,2), 64 MiB chunks)"
 
 
+class stdout_to_stderr:
+    """NCCL prints its version banner on fd 1 when the first communicator is created; the contract is ONE JSON line
+    on stdout, so fd 1 is pointed at fd 2 while torch.distributed initialises."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -208,7 +223,10 @@ def main():
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
     dev = torch.device("cuda", local)
     eng = L.Engine(local)
     goal = L.SliceType(args.goal)

@@ -78,6 +78,14 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if ((rc = set_smem_attr<4, false>(smem))) return rc;
 	if ((rc = set_smem_attr<4, true>(smem))) return rc;
 	if ((rc = set_smem_attr<2, false, 8, 8>(smem))) return rc;
+	if ((rc = set_smem_attr<1, false, 2, 32>(smem))) return rc;
+	if ((rc = set_smem_attr<1, false, 3, 20>(smem))) return rc;
+	if ((rc = set_smem_attr<2, false, 3, 16>(smem))) return rc;
+	if ((rc = set_smem_attr<2, false, 4, 14>(smem))) return rc;
+	if ((rc = set_smem_attr<2, false, 6, 10>(smem))) return rc;
+	if ((rc = set_smem_attr<3, false, 5, 8>(smem))) return rc;
+	if ((rc = set_smem_attr<3, false, 6, 8>(smem))) return rc;
+	if ((rc = set_smem_attr<4, false, 8, 6>(smem))) return rc;
 	return LZGPU_OK;
 }
 
@@ -153,8 +161,20 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	p.pb = (nb + K - 1) / K;
 	p.K = K;
 	p.G = G;
-	p.units_per_chunk = (p.pb + G - 1) / G;
-	const uint64_t total = static_cast<uint64_t>(p.units_per_chunk) * n_chunks;
+	// flat mode: contiguous chunks made of whole stripes are one run of n_chunks*pb stripes (small chunks then fill the
+	// G-stripe units instead of leaving most TMA rows out of range)
+	const bool flat = M > 0 && n_chunks > 1 && chunk_stride == static_cast<size_t>(nb) * LZGPU_BLOCK_SIZE && nb % K == 0 &&
+	                  static_cast<uint64_t>(n_chunks) * p.pb < (1ull << 31) && static_cast<uint64_t>(n_chunks) * nb * 4 < (1ull << 32);
+	p.flat = flat ? 1u : 0u;
+	p.flat_magic = (1ull << 40) / p.pb + 1;
+	uint64_t total;
+	if (flat) {
+		p.units_per_chunk = static_cast<uint32_t>((static_cast<uint64_t>(n_chunks) * p.pb + G - 1) / G);
+		total = p.units_per_chunk;
+	} else {
+		p.units_per_chunk = (p.pb + G - 1) / G;
+		total = static_cast<uint64_t>(p.units_per_chunk) * n_chunks;
+	}
 	if (total > 0x7fffffffull) return LZGPU_NOT_HANDLED;
 	p.total_units = static_cast<uint32_t>(total);
 	std::memcpy(p.qmult, fs->qmult, sizeof(p.qmult));
@@ -172,14 +192,28 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	}
 	CUtensorMap map;
 	const uint32_t rows = G * K * 4;
-	int rc = make_tensor_map(fs, &map, d_data, static_cast<uint64_t>(nb) * 4, n_chunks, chunk_stride, rows);
+	int rc = flat ? make_tensor_map(fs, &map, d_data, static_cast<uint64_t>(n_chunks) * nb * 4, 1, 0, rows)
+	              : make_tensor_map(fs, &map, d_data, static_cast<uint64_t>(nb) * 4, n_chunks, chunk_stride, rows);
 	if (rc) return rc;
 	const size_t smem = fused_smem_bytes(rows, G * PC * 4);
 	if (generic) return launch<4, true>(ctx, map, p, smem, st);
+	// constant-folded instantiations for the common goals (k, G from pick_group), runtime k/G otherwise
+#define LZ_FOLDED(MM, KK, GG) \
+	if (M == MM && K == KK && G == GG) return launch<MM, false, KK, GG>(ctx, map, p, smem, st);
+	LZ_FOLDED(2, 8, 8)    // ec(8,2)
+	LZ_FOLDED(1, 2, 32)   // xor2
+	LZ_FOLDED(1, 3, 20)   // xor3
+	LZ_FOLDED(2, 3, 16)   // ec(3,2)
+	LZ_FOLDED(2, 4, 14)   // ec(4,2)
+	LZ_FOLDED(2, 6, 10)   // ec(6,2)
+	LZ_FOLDED(3, 5, 8)    // ec(5,3)
+	LZ_FOLDED(3, 6, 8)    // ec(6,3)
+	LZ_FOLDED(4, 8, 6)    // ec(8,4)
+#undef LZ_FOLDED
 	switch (M) {
 		case 0: return launch<0, false>(ctx, map, p, smem, st);
 		case 1: return launch<1, false>(ctx, map, p, smem, st);
-		case 2: return (K == 8 && G == 8) ? launch<2, false, 8, 8>(ctx, map, p, smem, st) : launch<2, false>(ctx, map, p, smem, st);
+		case 2: return launch<2, false>(ctx, map, p, smem, st);
 		case 3: return launch<3, false>(ctx, map, p, smem, st);
 		case 4: return launch<4, false>(ctx, map, p, smem, st);
 	}

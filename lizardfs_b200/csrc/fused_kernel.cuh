@@ -64,6 +64,10 @@ struct FusedParams {
 	uint32_t n_chunks, nb, pb;       // blocks per chunk, blocks per parity part
 	uint32_t K, G;                   // data parts, stripes per unit
 	uint32_t units_per_chunk, total_units;
+	// flat mode (chunks contiguous and nb % K == 0): the batch is one run of n_chunks*pb stripes, units may straddle
+	// chunks; flat_magic = floor(2^40 / pb) + 1 turns a global stripe index into (chunk, stripe) without a division
+	uint32_t flat;
+	unsigned long long flat_magic;
 	uint32_t qmult[4];               // x^(32*(4096*(3-q) - 53)) mod P : stream -> block merge incl. the flush offset
 	uint32_t zconst;                 // mycrc32(0, 64 KiB of zeros)
 	uint32_t probe;                  // diagnostics only (LZGPU_PROBE): bit1 skip GF role, bit2 skip CRC folds (results then invalid)
@@ -212,6 +216,19 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 		            a_full + 8 * st);
 	};
 
+	// global stripe index -> (chunk, stripe in chunk); in per-chunk mode the unit's chunk is passed through
+	auto locate = [&](uint32_t sg, uint32_t unit_c, uint32_t &c_out, uint32_t &s_out) {
+		if (p.flat) {
+			const uint32_t cc = static_cast<uint32_t>((static_cast<unsigned long long>(sg) * p.flat_magic) >> 40);
+			c_out = cc;
+			s_out = sg - cc * p.pb;
+		} else {
+			c_out = unit_c;
+			s_out = sg;
+		}
+	};
+	const uint32_t stripes_total = p.flat ? p.n_chunks * p.pb : p.pb;  // bound on the (global) stripe index
+
 	if (tid == 0) {
 		for (int s = 0; s < kNST; ++s) {
 			mbar_init(a_full + 8 * s, 1);
@@ -302,9 +319,11 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 								}
 							}
 						}
-						const uint32_t stripe = stripe0 + g;
-						if (stripe < p.pb && !LZ_PROBE(8)) {
-							uint8_t *dst = p.parity + c * p.parity_stride + (static_cast<unsigned long long>(stripe) << 16) +
+						const uint32_t sg = stripe0 + g;
+						if (sg < stripes_total && !LZ_PROBE(8)) {
+							uint32_t pc, stripe;
+							locate(sg, c, pc, stripe);
+							uint8_t *dst = p.parity + pc * p.parity_stride + (static_cast<unsigned long long>(stripe) << 16) +
 							               (q << 14) + step * kStepBytes + (col << 4);
 #pragma unroll
 							for (int r = 0; r < M; ++r)
@@ -353,15 +372,21 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 		lin ^= __shfl_xor_sync(0xffffffffu, lin, 2);
 		const uint32_t blk = a_blk + unit_parity * 256;
 		if (is_data_row && (vt & 3) == 0) {
-			const uint32_t b = stripe0 * K + (vt >> 2);  // block index in the chunk
+			const uint32_t bl = vt >> 2;                  // block inside the unit: stripe bl / K, data part bl % K
 			if (M > 0 && !GENERIC) asm volatile("st.shared.u32 [%0], %1;" ::"r"(blk + (vt & ~3u)), "r"(lin) : "memory");
-			if (b < p.nb) p.crc[c * p.crc_stride + b] = lin ^ p.zconst;
+			const uint32_t sg = stripe0 + bl / K;
+			uint32_t bc, bs;
+			locate(sg, c, bc, bs);
+			const uint32_t b = bs * K + bl % K;           // block index in its chunk
+			if (sg < stripes_total && b < p.nb) p.crc[bc * p.crc_stride + b] = lin ^ p.zconst;
 		}
 		if (is_parity_row && (prow & 3) == 0) {
 			constexpr uint32_t PCD = PC ? PC : 1;
 			const uint32_t g = (prow >> 2) / PCD, r = P0 + (prow >> 2) % PCD;
-			const uint32_t stripe = stripe0 + g;
-			if (stripe < p.pb) p.crc[c * p.crc_stride + p.nb + r * p.pb + stripe] = lin ^ p.zconst;
+			const uint32_t sg = stripe0 + g;
+			uint32_t pc, stripe;
+			locate(sg, c, pc, stripe);
+			if (sg < stripes_total) p.crc[pc * p.crc_stride + p.nb + r * p.pb + stripe] = lin ^ p.zconst;
 		}
 		if (M > 0 && !GENERIC) {
 			// CRC of parity row 0 (plain XOR of the stripe): xor of the data blocks' linear CRCs
@@ -373,8 +398,10 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 					asm volatile("ld.shared.u32 %0, [%1];" : "=r"(t) : "r"(blk + 4 * (vt * K + j)));
 					x ^= t;
 				}
-				const uint32_t stripe = stripe0 + vt;
-				if (stripe < p.pb) p.crc[c * p.crc_stride + p.nb + stripe] = x ^ p.zconst;
+				const uint32_t sg = stripe0 + vt;
+				uint32_t pc, stripe;
+				locate(sg, c, pc, stripe);
+				if (sg < stripes_total) p.crc[pc * p.crc_stride + p.nb + stripe] = x ^ p.zconst;
 			}
 		}
 	}

@@ -63,6 +63,19 @@ def test_encode_batch_vs_oracle(eng, oracle, text, nblocks, n_chunks):
     assert crc[0, 0] == 0xD7978EEB
 
 
+@pytest.mark.parametrize("text,nblocks,n_chunks", [("ec(8,2)", 16, 37), ("ec(8,2)", 8, 5), ("ec(3,2)", 12, 11), ("xor2", 4, 50), ("ec(8,4)", 16, 9), ("ec(5,3)", 10, 13)])
+def test_encode_many_small_chunks_flat_units(eng, oracle, text, nblocks, n_chunks):
+    """Contiguous chunks made of whole stripes are processed as one run of stripes (units straddle chunk
+    boundaries); every chunk must still get exactly its own parity and CRCs."""
+    goal = L.SliceType(text)
+    data = rnd((n_chunks, nblocks * BLOCK), (hash(text) ^ nblocks) & 0xffff)
+    parity, crc = eng.encode_chunks(goal, data)
+    for c in range(n_chunks):
+        p_ref, c_ref = oracle.encode_chunk(goal.kind, goal.k, goal.m, data[c])
+        assert (parity[c] == p_ref).all(), (text, c)
+        assert (crc[c] == c_ref).all(), (text, c)
+
+
 def test_encode_partial_last_block(eng, oracle):
     goal = L.SliceType("ec(3,2)")
     clen = 7 * BLOCK + 12345
