@@ -88,7 +88,7 @@ lzgpu_ctx *lzgpu_default_ctx(void);
 const char *lzgpu_last_error(void); /* thread-local text of the last failure */
 const char *lzgpu_version(void);
 
-/* per-context counters (SURVEY.md §5 "metrics"): kernels launched, bytes, device ms of the last call */
+/* per-context counters (SURVEY.md §5 "metrics") */
 typedef struct lzgpu_stats {
 	uint64_t kernel_launches;
 	uint64_t bytes_h2d;
@@ -96,7 +96,6 @@ typedef struct lzgpu_stats {
 	uint64_t chunks_encoded;
 	uint64_t chunks_recovered;
 	uint64_t blocks_crc;
-	double last_kernel_ms;
 } lzgpu_stats;
 void lzgpu_get_stats(lzgpu_ctx *ctx, lzgpu_stats *out);
 void lzgpu_reset_stats(lzgpu_ctx *ctx);

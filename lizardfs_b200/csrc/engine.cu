@@ -87,8 +87,6 @@ extern "C" int lzgpu_ctx_create(int device, lzgpu_ctx **out) {
 	ctx->sm_count = prop.multiProcessorCount;
 	CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 	for (auto &s : ctx->slot_stream) CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-	CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDefault));
-	CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDefault));
 	uint32_t tabs[4][256];
 	lz::crc_make_tables(tabs);
 	CUDA_TRY(cudaMalloc(&ctx->d_crc_tables, sizeof(tabs)));
@@ -111,12 +109,9 @@ extern "C" void lzgpu_ctx_destroy(lzgpu_ctx *ctx) {
 	cudaDeviceSynchronize();
 	lz_fused_destroy(ctx);
 	for (auto &b : ctx->scratch) if (b.ptr) cudaFree(b.ptr);
-	if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
 	cudaFree(ctx->d_crc_tables);
 	cudaFree(ctx->d_first_bad);
 	cudaFreeHost(ctx->h_first_bad);
-	cudaEventDestroy(ctx->ev_a);
-	cudaEventDestroy(ctx->ev_b);
 	for (auto &s : ctx->slot_stream) cudaStreamDestroy(s);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
@@ -874,14 +869,11 @@ extern "C" uint32_t lzgpu_mycrc32_zeroexpanded(uint32_t crc, const uint8_t *bloc
 	return lzgpu_mycrc32_zeroblock(lzgpu_mycrc32(crc, block, leng), zeros);
 }
 
-// crc.cc:235-243: a stored CRC of 0 on an all-zero block becomes the CRC of 64 KiB of zeros.
-// "all zero" is decided on the GPU: the block is all zero iff ... its CRC equals the zero-block CRC
-// is NOT sufficient in general, so the kernel result is cross-checked with a zero scan of the linear
-// part: lin(block) == 0 for an all-zero block, and a non-zero block with lin == 0 would be a CRC
-// collision with the zero block — the reference's memcmp cannot be fooled by that, so we scan.
+// crc.cc:235-243: a stored CRC of 0 on an all-zero block becomes the CRC of 64 KiB of zeros.  The block lives in
+// host memory and the test is a plain zero scan (the reference uses memcmp), so it stays on the host; the batched
+// equivalent on the GPU is the sparse_rule of lzgpu_verify_blocks / lzgpu_verify_interleaved.
 extern "C" void lzgpu_recompute_crc_if_block_empty(const uint8_t *block, uint32_t *crc) {
 	if (!block || !crc || *crc != 0) return;
-	// cheap early exit on the host keeps semantics exact (memcmp in the reference)
 	for (uint32_t i = 0; i < LZGPU_BLOCK_SIZE; ++i)
 		if (block[i]) return;
 	*crc = lz::crc_of_zeros(LZGPU_BLOCK_SIZE);

@@ -46,10 +46,8 @@ struct lzgpu_ctx {
 	int sm_count = 0;
 	cudaStream_t stream = nullptr;
 	cudaStream_t slot_stream[kHostSlots] = {nullptr, nullptr, nullptr};
-	cudaEvent_t ev_a = nullptr, ev_b = nullptr;
 	uint32_t *d_crc_tables = nullptr;
 	unsigned long long *d_first_bad = nullptr, *h_first_bad = nullptr;
-	void *h_stage = nullptr;
 	ScratchBuf scratch[kScratchCount];
 	unsigned coef_rr = 0;
 	FusedState *fused = nullptr;

@@ -29,6 +29,7 @@ struct FusedState {
 	bool disabled = false;
 	uint32_t probe = 0;
 	uint32_t *d_sm_ctr = nullptr;
+	int evict_first = 0;
 	int promo = 3;  // CU_TENSOR_MAP_L2_PROMOTION_L2_256B: +12% streaming bandwidth over 128B/none (profiles/probe_r1.md)
 };
 
@@ -51,12 +52,35 @@ static int set_smem_attr(int bytes) {
 	return LZGPU_OK;
 }
 
+template <int E, int KT, int R0 = -1, int R1 = -1>
+static int set_recover_attr() {
+	CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<E, KT, R0, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCap));
+	return LZGPU_OK;
+}
+
+// function attributes are per device: done once per context
+static int set_all_recover_attrs() {
+	int rc;
+	if ((rc = set_recover_attr<1, 8, 0>())) return rc;
+	if ((rc = set_recover_attr<1, 0, 0>())) return rc;
+	if ((rc = set_recover_attr<1, 0>())) return rc;
+	if ((rc = set_recover_attr<2, 8, 0, 1>())) return rc;
+	if ((rc = set_recover_attr<2, 0, 0, 1>())) return rc;
+	if ((rc = set_recover_attr<2, 0>())) return rc;
+	if ((rc = set_recover_attr<3, 0, 0, 1>())) return rc;
+	if ((rc = set_recover_attr<3, 0>())) return rc;
+	if ((rc = set_recover_attr<4, 0, 0, 1>())) return rc;
+	if ((rc = set_recover_attr<4, 0>())) return rc;
+	return LZGPU_OK;
+}
+
 int lz_fused_init(lzgpu_ctx *ctx) {
 	auto *fs = new FusedState();
 	ctx->fused = fs;
 	if (const char *e = std::getenv("LZGPU_DISABLE_FUSED")) fs->disabled = std::atoi(e) != 0;
 	if (const char *e = std::getenv("LZGPU_PROBE")) fs->probe = static_cast<uint32_t>(std::atoi(e));
 	if (const char *e = std::getenv("LZGPU_L2_PROMO")) fs->promo = std::atoi(e);
+	if (const char *e = std::getenv("LZGPU_EVICT_FIRST")) fs->evict_first = std::atoi(e);
 	void *fn = nullptr;
 	cudaDriverEntryPointQueryResult qres;
 	cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -86,6 +110,7 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if ((rc = set_smem_attr<3, false, 5, 8>(smem))) return rc;
 	if ((rc = set_smem_attr<3, false, 6, 8>(smem))) return rc;
 	if ((rc = set_smem_attr<4, false, 8, 6>(smem))) return rc;
+	if ((rc = set_all_recover_attrs())) return rc;
 	return LZGPU_OK;
 }
 
@@ -180,6 +205,7 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	std::memcpy(p.qmult, fs->qmult, sizeof(p.qmult));
 	p.zconst = lz::crc_of_zeros(LZGPU_BLOCK_SIZE);
 	p.probe = fs->probe;
+	p.evict_first = static_cast<uint32_t>(fs->evict_first);
 	if (generic) {
 		for (int r = 0; r < M; ++r)
 			for (uint32_t j = 0; j < K; ++j) {
@@ -255,11 +281,6 @@ int lz_fused_crc(lzgpu_ctx *ctx, const void *base, unsigned long long n_blocks, 
 // ---------------------------------------------------------------------------------------------------
 template <int E, int KT, int R0 = -1, int R1 = -1>
 static int launch_recover(lzgpu_ctx *ctx, const TmapArray &maps, const RecoverParams &p, size_t smem, cudaStream_t st) {
-	static bool attr_set = false;  // per instantiation; contexts share the device function attribute
-	if (!attr_set) {
-		CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<E, KT, R0, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCap));
-		attr_set = true;
-	}
 	const int grid = static_cast<int>(std::min<uint64_t>(p.total_units, static_cast<uint64_t>(ctx->sm_count)));
 	fused_recover_kernel<E, KT, R0, R1><<<grid, kFusedThreads, smem, st>>>(maps, p);
 	CUDA_TRY(cudaGetLastError());

@@ -45,6 +45,18 @@ namespace lzd {
 #define LZ_PROBE(bit) 0
 #endif
 
+// Diagnostics build (-DLZ_ALL_LANES_ARRIVE): every lane arrives on the parity-ring mbarriers instead of one elected
+// lane after __syncwarp().  compute-sanitizer racecheck does not model the cumulativity of __syncwarp + elected arrive
+// and reports the ring's STS/LDS pairs as hazards; with all lanes arriving the same protocol is reported clean
+// (profiles/sanitizer_r1.md).  The production build elects one lane (fewer barrier operations).
+#ifdef LZ_ALL_LANES_ARRIVE
+#define LZ_RING_ARRIVERS 32u
+#define LZ_RING_LANE(lane) true
+#else
+#define LZ_RING_ARRIVERS 1u
+#define LZ_RING_LANE(lane) ((lane) == 0)
+#endif
+
 constexpr int kFoldDeg = 53;
 constexpr int kStepBytes = 128;
 constexpr int kRowBytes = 16384;
@@ -67,6 +79,7 @@ struct FusedParams {
 	// flat mode (chunks contiguous and nb % K == 0): the batch is one run of n_chunks*pb stripes, units may straddle
 	// chunks; flat_magic = floor(2^40 / pb) + 1 turns a global stripe index into (chunk, stripe) without a division
 	uint32_t flat;
+	uint32_t evict_first;            // TMA loads carry an L2 evict_first hint
 	unsigned long long flat_magic;
 	uint32_t qmult[4];               // x^(32*(4096*(3-q) - 53)) mod P : stream -> block merge incl. the flush offset
 	uint32_t zconst;                 // mycrc32(0, 64 KiB of zeros)
@@ -90,7 +103,20 @@ __device__ __forceinline__ bool mbar_arrive_is_last(uint32_t bar) {
 	uint32_t pending;
 	asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(state) : "r"(bar) : "memory");
 	asm volatile("mbarrier.pending_count.b64 %0, %1;" : "=r"(pending) : "l"(state));
-	return pending == 1;
+	if (pending == 1) {
+		// the completing arriver observes the phase it completed (acquire side of the release sequence of all
+		// arrivals; also keeps compute-sanitizer synccheck from flagging a barrier that nobody ever waits on)
+		uint32_t done;
+		asm volatile(
+		    "{\n\t.reg .pred p;\n\t"
+		    "mbarrier.test_wait.shared::cta.b64 p, [%1], %2;\n\t"
+		    "selp.u32 %0, 1, 0, p;\n\t}"
+		    : "=r"(done)
+		    : "r"(bar), "l"(state)
+		    : "memory");
+		return done != 0;
+	}
+	return false;
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -107,6 +133,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
 		    : "r"(addr), "r"(parity), "r"(0x989680u)
 		    : "memory");
 	} while (!done);
+}
+// same with an L2 eviction-priority hint: the input is read exactly once, so its lines should be the first to go
+__device__ __forceinline__ void tma_load_3d_evict_first(uint32_t smem_dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar) {
+	uint64_t policy;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+	asm volatile(
+	    "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
+	        smem_dst),
+	    "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(policy)
+	    : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar) {
 	asm volatile(
@@ -212,8 +248,12 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 	// load of step `step` of unit (chunk c, stripe group gi) into stage `st` (caller guarantees the stage is free)
 	auto issue_load = [&](uint32_t c, uint32_t gi, uint32_t step, uint32_t st) {
 		mbar_expect_tx(a_full + 8 * st, stage_bytes);
-		tma_load_3d(sbase + st * stage_bytes, &tmap, static_cast<int>(step * kStepBytes), static_cast<int>(gi * ROWS), static_cast<int>(c),
-		            a_full + 8 * st);
+		if (p.evict_first)
+			tma_load_3d_evict_first(sbase + st * stage_bytes, &tmap, static_cast<int>(step * kStepBytes), static_cast<int>(gi * ROWS),
+			                        static_cast<int>(c), a_full + 8 * st);
+		else
+			tma_load_3d(sbase + st * stage_bytes, &tmap, static_cast<int>(step * kStepBytes), static_cast<int>(gi * ROWS), static_cast<int>(c),
+			            a_full + 8 * st);
 	};
 
 	// global stripe index -> (chunk, stripe in chunk); in per-chunk mode the unit's chunk is passed through
@@ -235,8 +275,8 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 			mbar_init(a_empty + 8 * s, n_stage_warps);
 		}
 		for (int s = 0; s < kNPST; ++s) {
-			mbar_init(a_pfull + 8 * s, n_gf_warps ? n_gf_warps : 1);
-			mbar_init(a_pempty + 8 * s, PROWS ? (last_pwarp - first_pwarp + 1) : 1);
+			mbar_init(a_pfull + 8 * s, (n_gf_warps ? n_gf_warps : 1) * LZ_RING_ARRIVERS);
+			mbar_init(a_pempty + 8 * s, (PROWS ? (last_pwarp - first_pwarp + 1) : 1) * LZ_RING_ARRIVERS);
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		if (total_steps)
@@ -338,7 +378,7 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 					}
 					if (PC > 0) {
 						__syncwarp();
-						if (lane == 0) mbar_arrive(a_pfull + 8 * pst);
+						if (LZ_RING_LANE(lane)) mbar_arrive(a_pfull + 8 * pst);
 					}
 				}
 
@@ -357,8 +397,8 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 						if (step + kNST < kStepsPerUnit) issue_load(c, gi, step + kNST, st);
 						else issue_load(next_c, next_gi, step + kNST - kStepsPerUnit, st);
 					}
-					if (PC > 0 && warp_has_prow && !LZ_PROBE(2)) mbar_arrive(a_pempty + 8 * pst);
 				}
+				if (PC > 0 && warp_has_prow && !LZ_PROBE(2) && LZ_RING_LANE(lane)) mbar_arrive(a_pempty + 8 * pst);
 				++it;
 				if (++st == kNST) { st = 0; ph ^= 1; }
 				if (++pst == kNPST) { pst = 0; pph ^= 1; }

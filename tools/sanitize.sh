@@ -1,4 +1,5 @@
-# compute-sanitizer passes over a small encode + recover + scrub through the C ABI (run under gpurun)
+# compute-sanitizer passes over a small encode + recover + scrub through the C ABI (run under gpurun).
+# Full reports land in gpurun_out/sanitize_<tool>.log.
 mkdir -p gpurun_out
 cat > /tmp/san_case.py <<'PY'
 import numpy as np, sys
@@ -21,6 +22,7 @@ for text, nblk in [("ec(8,2)", 24), ("ec(3,2)", 7), ("xor3", 9)]:
 eng.verify_blocks(data.reshape(-1), eng.crc_blocks(data.reshape(-1)))
 print("sanitizer case OK")
 PY
-for tool in memcheck racecheck synccheck; do
-  echo "== $tool"; timeout 900 compute-sanitizer --tool $tool --print-limit 5 python /tmp/san_case.py 2>&1 | tail -6
+for tool in ${TOOLS:-memcheck racecheck synccheck}; do
+  echo "== $tool"; timeout 900 compute-sanitizer --tool $tool --print-limit 8 python /tmp/san_case.py > gpurun_out/sanitize_$tool.log 2>&1
+  grep -E "SUMMARY|sanitizer case OK|Error|error" gpurun_out/sanitize_$tool.log | head -5
 done
