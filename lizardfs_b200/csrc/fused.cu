@@ -20,12 +20,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 
 // two CTAs per SM: 228 KiB per SM minus 1 KiB reserved per CTA
 constexpr int kSmemCap = 113 * 1024;
+constexpr int kSmemCap128 = 226 * 1024;       // FW = 128 variant: one CTA per SM
 constexpr int kRecoverSmemCap = 200 * 1024;  // recover kernel: one CTA per SM, 6 stages
 
 struct FusedState {
 	EncodeTiledFn encode_tiled = nullptr;
-	uint32_t qmult[4];
+	uint32_t qmult64[4], qmult128[4];
 	int max_smem = 0;
+	int fold = 0;  // LZGPU_FOLD: 0 = per-goal default, 64 / 128 = force
 	bool disabled = false;
 	uint32_t probe = 0;
 	uint32_t *d_sm_ctr = nullptr;
@@ -46,15 +48,18 @@ static uint32_t crc_xpow_bits_signed(long long n) {
 	return acc;
 }
 
-template <int M, bool GENERIC, int KT = 0, int GT = 0>
+template <int M, bool GENERIC, int KT = 0, int GT = 0, int FW = 64>
 static int set_smem_attr(int bytes) {
-	CUDA_TRY(cudaFuncSetAttribute(fused_stream_kernel<M, GENERIC, KT, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+	CUDA_TRY(cudaFuncSetAttribute(fused_stream_kernel<M, GENERIC, KT, GT, FW>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
 	return LZGPU_OK;
 }
 
 template <int E, int KT, int R0 = -1, int R1 = -1>
 static int set_recover_attr() {
-	CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<E, KT, R0, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCap));
+	CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<E, KT, R0, R1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCap));
+#ifdef LZ_ENABLE_FOLD128
+	CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<E, KT, R0, R1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCap));
+#endif
 	return LZGPU_OK;
 }
 
@@ -90,7 +95,11 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 		return LZGPU_ERR_CUDA;
 	}
 	fs->encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
-	for (int q = 0; q < 4; ++q) fs->qmult[q] = crc_xpow_bits_signed(32ll * (4096ll * (3 - q) - kFoldDeg));
+	for (int q = 0; q < 4; ++q) {
+		fs->qmult64[q] = crc_xpow_bits_signed(32ll * (4096ll * (3 - q) - FoldSpec<64>::deg));
+		fs->qmult128[q] = crc_xpow_bits_signed(32ll * (4096ll * (3 - q) - FoldSpec<128>::deg));
+	}
+	if (const char *e = std::getenv("LZGPU_FOLD")) fs->fold = std::atoi(e);
 	CUDA_TRY(cudaDeviceGetAttribute(&fs->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
 	CUDA_TRY(cudaMalloc(&fs->d_sm_ctr, 256 * sizeof(uint32_t)));
 	const int smem = std::min(fs->max_smem, kSmemCap);
@@ -110,6 +119,17 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if ((rc = set_smem_attr<3, false, 5, 8>(smem))) return rc;
 	if ((rc = set_smem_attr<3, false, 6, 8>(smem))) return rc;
 	if ((rc = set_smem_attr<4, false, 8, 6>(smem))) return rc;
+#ifdef LZ_ENABLE_FOLD128
+	const int smem128 = std::min(fs->max_smem, kSmemCap128);
+	if ((rc = set_smem_attr<0, false, 0, 0, 128>(smem128))) return rc;
+	if ((rc = set_smem_attr<1, false, 0, 0, 128>(smem128))) return rc;
+	if ((rc = set_smem_attr<2, false, 0, 0, 128>(smem128))) return rc;
+	if ((rc = set_smem_attr<3, false, 0, 0, 128>(smem128))) return rc;
+	if ((rc = set_smem_attr<4, false, 0, 0, 128>(smem128))) return rc;
+	if ((rc = set_smem_attr<2, false, 8, 8, 128>(smem128))) return rc;
+	if ((rc = set_smem_attr<4, false, 8, 6, 128>(smem128))) return rc;
+	if ((rc = set_smem_attr<3, false, 5, 8, 128>(smem128))) return rc;
+#endif
 	if ((rc = set_all_recover_attrs())) return rc;
 	return LZGPU_OK;
 }
@@ -120,20 +140,21 @@ void lz_fused_destroy(lzgpu_ctx *ctx) {
 	ctx->fused = nullptr;
 }
 
-static size_t fused_smem_bytes(uint32_t rows, uint32_t prows) {
+static size_t fused_smem_bytes(uint32_t rows, uint32_t prows, int fw) {
 	const size_t pstage = (static_cast<size_t>(prows) * kStepBytes + 1023) & ~size_t(1023);
-	return static_cast<size_t>(kNST) * rows * kStepBytes + static_cast<size_t>(kNPST) * pstage + 520 + 8 * (2 * kNST + 2 * kNPST);
+	const size_t nst = fused_nst(fw), npst = fused_npst(fw);
+	return nst * rows * kStepBytes + npst * pstage + 520 + 8 * (2 * nst + 2 * npst);
 }
 
 // Largest stripe group G such that data + parity-CRC rows fit the consumer threads, the data rows fit
 // one TMA box (<= 256 rows, a multiple of 8 for the 1024-byte stage alignment) and the stages fit shared memory.
-static uint32_t pick_group(uint32_t K, uint32_t PC, int max_smem_per_cta) {
+static uint32_t pick_group(uint32_t K, uint32_t PC, int max_smem_per_cta, int fw) {
 	uint32_t best = 0;
 	for (uint32_t g = 1; g <= 64; ++g) {
 		const uint32_t rows = g * K * 4, prows = g * PC * 4;
 		if (rows > kMaxRows || rows + prows > kConsumers || prows > kMaxParityRows || g * K > 64) break;
 		if (rows % 8) continue;
-		if (fused_smem_bytes(rows, prows) > static_cast<size_t>(max_smem_per_cta)) break;
+		if (fused_smem_bytes(rows, prows, fw) > static_cast<size_t>(max_smem_per_cta)) break;
 		best = g;
 	}
 	return best;
@@ -157,13 +178,30 @@ static int make_tensor_map(FusedState *fs, CUtensorMap *map, const void *base, u
 	return LZGPU_OK;
 }
 
-template <int M, bool GENERIC, int KT = 0, int GT = 0>
+template <int M, bool GENERIC, int KT = 0, int GT = 0, int FW = 64>
 static int launch(lzgpu_ctx *ctx, const CUtensorMap &map, const FusedParams &p, size_t smem, cudaStream_t st) {
-	const int grid = static_cast<int>(std::min<uint64_t>(p.total_units, static_cast<uint64_t>(ctx->sm_count) * 2));
-	fused_stream_kernel<M, GENERIC, KT, GT><<<grid, kFusedThreads, smem, st>>>(map, p);
+	const int per_sm = FW == 64 ? 2 : 1;
+	const int grid = static_cast<int>(std::min<uint64_t>(p.total_units, static_cast<uint64_t>(ctx->sm_count) * per_sm));
+	fused_stream_kernel<M, GENERIC, KT, GT, FW><<<grid, kFusedThreads, smem, st>>>(map, p);
 	CUDA_TRY(cudaGetLastError());
 	ctx->stats.kernel_launches++;
 	return LZGPU_OK;
+}
+
+// Fold window per shape: the 128-word window (3 LOP3 per word, one CTA per SM) pays off where the kernel is ALU bound
+// (many parity rows); the 64-word window (two CTAs per SM) is the default.  LZGPU_FOLD=64|128 forces one.
+// (measured in round 1, profiles/probe_r1.md: the 128-word window is slower for every goal — the kernels are bound by
+// per-warp latency, not ALU throughput, and halving the resident warps costs more than the saved LOP3s — so it is only
+// compiled with -DLZ_ENABLE_FOLD128 for experiments)
+static int choose_fold(const FusedState *fs, int M, bool generic) {
+	(void)M;
+#ifdef LZ_ENABLE_FOLD128
+	if (fs->fold == 128 && !generic) return 128;
+#else
+	(void)fs;
+	(void)generic;
+#endif
+	return 64;
 }
 
 static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_rows, uint32_t K, uint32_t n_chunks, uint32_t nb,
@@ -171,8 +209,9 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
                      cudaStream_t st) {
 	FusedState *fs = ctx->fused;
 	const uint32_t PC = M == 0 ? 0 : (generic ? M : M - 1);
-	const int smem_cap = std::min(fs->max_smem, kSmemCap);
-	const uint32_t G = pick_group(K, PC, smem_cap);
+	const int fw = choose_fold(fs, M, generic);
+	const int smem_cap = std::min(fs->max_smem, fw == 64 ? kSmemCap : kSmemCap128);
+	const uint32_t G = pick_group(K, PC, smem_cap, fw);
 	if (G == 0) return LZGPU_NOT_HANDLED;
 	if ((chunk_stride % 16) || (reinterpret_cast<uintptr_t>(d_data) % 16)) return LZGPU_NOT_HANDLED;
 	FusedParams p{};
@@ -202,7 +241,7 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	}
 	if (total > 0x7fffffffull) return LZGPU_NOT_HANDLED;
 	p.total_units = static_cast<uint32_t>(total);
-	std::memcpy(p.qmult, fs->qmult, sizeof(p.qmult));
+	std::memcpy(p.qmult, fw == 64 ? fs->qmult64 : fs->qmult128, sizeof(p.qmult));
 	p.zconst = lz::crc_of_zeros(LZGPU_BLOCK_SIZE);
 	p.probe = fs->probe;
 	p.evict_first = static_cast<uint32_t>(fs->evict_first);
@@ -221,8 +260,23 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	int rc = flat ? make_tensor_map(fs, &map, d_data, static_cast<uint64_t>(n_chunks) * nb * 4, 1, 0, rows)
 	              : make_tensor_map(fs, &map, d_data, static_cast<uint64_t>(nb) * 4, n_chunks, chunk_stride, rows);
 	if (rc) return rc;
-	const size_t smem = fused_smem_bytes(rows, G * PC * 4);
+	const size_t smem = fused_smem_bytes(rows, G * PC * 4, fw);
 	if (generic) return launch<4, true>(ctx, map, p, smem, st);
+#ifdef LZ_ENABLE_FOLD128
+	if (fw == 128) {
+		if (M == 2 && K == 8 && G == 8) return launch<2, false, 8, 8, 128>(ctx, map, p, smem, st);
+		if (M == 4 && K == 8 && G == 6) return launch<4, false, 8, 6, 128>(ctx, map, p, smem, st);
+		if (M == 3 && K == 5 && G == 8) return launch<3, false, 5, 8, 128>(ctx, map, p, smem, st);
+		switch (M) {
+			case 0: return launch<0, false, 0, 0, 128>(ctx, map, p, smem, st);
+			case 1: return launch<1, false, 0, 0, 128>(ctx, map, p, smem, st);
+			case 2: return launch<2, false, 0, 0, 128>(ctx, map, p, smem, st);
+			case 3: return launch<3, false, 0, 0, 128>(ctx, map, p, smem, st);
+			case 4: return launch<4, false, 0, 0, 128>(ctx, map, p, smem, st);
+		}
+		return LZGPU_NOT_HANDLED;
+	}
+#endif
 	// constant-folded instantiations for the common goals (k, G from pick_group), runtime k/G otherwise
 #define LZ_FOLDED(MM, KK, GG) \
 	if (M == MM && K == KK && G == GG) return launch<MM, false, KK, GG>(ctx, map, p, smem, st);
@@ -282,7 +336,11 @@ int lz_fused_crc(lzgpu_ctx *ctx, const void *base, unsigned long long n_blocks, 
 template <int E, int KT, int R0 = -1, int R1 = -1>
 static int launch_recover(lzgpu_ctx *ctx, const TmapArray &maps, const RecoverParams &p, size_t smem, cudaStream_t st) {
 	const int grid = static_cast<int>(std::min<uint64_t>(p.total_units, static_cast<uint64_t>(ctx->sm_count)));
-	fused_recover_kernel<E, KT, R0, R1><<<grid, kFusedThreads, smem, st>>>(maps, p);
+#ifdef LZ_ENABLE_FOLD128
+	if (ctx->fused->fold == 128) fused_recover_kernel<E, KT, R0, R1, 128><<<grid, kFusedThreads, smem, st>>>(maps, p);
+	else
+#endif
+		fused_recover_kernel<E, KT, R0, R1, 64><<<grid, kFusedThreads, smem, st>>>(maps, p);
 	CUDA_TRY(cudaGetLastError());
 	ctx->stats.kernel_launches++;
 	return LZGPU_OK;
@@ -351,7 +409,11 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 	if (total > 0x7fffffffull) return LZGPU_NOT_HANDLED;
 	p.total_units = static_cast<uint32_t>(total);
 	p.e = e;
-	std::memcpy(p.qmult, fs->qmult, sizeof(p.qmult));
+#ifdef LZ_ENABLE_FOLD128
+	std::memcpy(p.qmult, fs->fold == 128 ? fs->qmult128 : fs->qmult64, sizeof(p.qmult));
+#else
+	std::memcpy(p.qmult, fs->qmult64, sizeof(p.qmult));
+#endif
 	p.zconst = lz::crc_of_zeros(LZGPU_BLOCK_SIZE);
 	for (int a = 0; a < K; ++a) {
 		p.stored[a] = d_part_crc ? static_cast<const uint32_t *>(d_part_crc[used[a]]) : nullptr;

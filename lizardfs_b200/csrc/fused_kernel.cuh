@@ -57,15 +57,16 @@ namespace lzd {
 #define LZ_RING_LANE(lane) ((lane) == 0)
 #endif
 
-constexpr int kFoldDeg = 53;
 constexpr int kStepBytes = 128;
 constexpr int kRowBytes = 16384;
 constexpr int kStepsPerUnit = kRowBytes / kStepBytes;  // 128
 constexpr int kConsumers = 288;                        // 9 warps, all consumers (2 CTAs/SM -> 112 registers per thread)
 constexpr int kFusedThreads = kConsumers;
 constexpr int kMaxRows = 256;                          // TMA box limit per dimension
-constexpr int kNST = 3;                                // data stages
-constexpr int kNPST = 4;                               // parity staging ring (decouples GF warps from the parity-CRC warp)
+// pipeline depth by fold window: FW = 64 -> 2 CTAs/SM (96 registers), 3 data stages + 4-deep parity ring;
+// FW = 128 -> 1 CTA/SM (the 128-word window needs ~170 registers), 6 data stages + 6-deep parity ring
+__host__ __device__ constexpr int fused_nst(int fw) { return fw == 64 ? 3 : 6; }
+__host__ __device__ constexpr int fused_npst(int fw) { return fw == 64 ? 4 : 6; }
 constexpr int kMaxParityRows = 128;
 
 struct FusedParams {
@@ -81,7 +82,7 @@ struct FusedParams {
 	uint32_t flat;
 	uint32_t evict_first;            // TMA loads carry an L2 evict_first hint
 	unsigned long long flat_magic;
-	uint32_t qmult[4];               // x^(32*(4096*(3-q) - 53)) mod P : stream -> block merge incl. the flush offset
+	uint32_t qmult[4];               // x^(32*(4096*(3-q) - deg)) mod P : stream -> block merge incl. the flush offset (deg of the fold in use)
 	uint32_t zconst;                 // mycrc32(0, 64 KiB of zeros)
 	uint32_t probe;                  // diagnostics only (LZGPU_PROBE): bit1 skip GF role, bit2 skip CRC folds (results then invalid)
 	CoefPlanes coef[4 * 32];         // only read by the GENERIC instantiation: [M][K]
@@ -153,10 +154,23 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap
 }
 
 // ---- sparse-fold CRC stream ------------------------------------------------------------------------
-// window slot of word u is u & 63; the nine pulled words of slot S are the static slots (S - lag) & 63
-#define LZ_FOLD(win, S, w)                                                                                     \
-	win[(S)&63] = (w) ^ win[((S)-15) & 63] ^ win[((S)-17) & 63] ^ win[((S)-20) & 63] ^ win[((S)-23) & 63] ^ \
-	              win[((S)-26) & 63] ^ win[((S)-28) & 63] ^ win[((S)-46) & 63] ^ win[((S)-50) & 63] ^ win[((S)-53) & 63]
+// Two sparse multiples of the CRC-32 polynomial P (found by meet-in-the-middle search, lowest weight for the window):
+//   FW = 64 : g(x) = x^53+x^38+x^36+x^33+x^30+x^27+x^25+x^7+x^3+1      9 pulls (5 LOP3) per word, 64-word window
+//   FW = 128: g(x) = x^123+x^120+x^80+x^74+x^53+x^45+1                 6 pulls (3 LOP3) per word, 128-word window
+// g(x^32) = g(x)^32 is a multiple of P too, so with y = one 32-bit word:  W'[u] = W[u] ^ XOR_lag W'[u - lag],
+// lag = deg - exponent.  The window lives in registers; slot of word u is u & (FW-1), all indices are static.
+template <int FW>
+struct FoldSpec;
+template <>
+struct FoldSpec<64> {
+	static constexpr int deg = 53, nlag = 9;
+	__host__ __device__ static constexpr int lag(int t) { return t == 0 ? 15 : t == 1 ? 17 : t == 2 ? 20 : t == 3 ? 23 : t == 4 ? 26 : t == 5 ? 28 : t == 6 ? 46 : t == 7 ? 50 : 53; }
+};
+template <>
+struct FoldSpec<128> {
+	static constexpr int deg = 123, nlag = 6;
+	__host__ __device__ static constexpr int lag(int t) { return t == 0 ? 3 : t == 1 ? 43 : t == 2 ? 49 : t == 3 ? 70 : t == 4 ? 78 : 123; }
+};
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 	uint4 v;
@@ -167,37 +181,46 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v) {
 	asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <int BASE>
-__device__ __forceinline__ void fold_step(uint32_t (&win)[64], uint32_t row_addr_swz) {
-	// 8 x 16 bytes of this row.  Rows are 128-byte aligned, so the TMA 128-byte swizzle
-	// (chunk c of row r stored at chunk c ^ (r & 7)) is a pure XOR on the shared address:
-	// row_addr_swz = row_addr ^ ((r & 7) << 4), chunk c at row_addr_swz ^ (c << 4).
+template <int FW>
+__device__ __forceinline__ void fold_word(uint32_t (&win)[FW], int S, uint32_t w) {
+	uint32_t acc = w;
+#pragma unroll
+	for (int t = 0; t < FoldSpec<FW>::nlag; ++t) acc ^= win[(S - FoldSpec<FW>::lag(t)) & (FW - 1)];
+	win[S & (FW - 1)] = acc;
+}
+
+// one pipeline step of a stream: 8 x 16 bytes of this row, window slots base .. base+31 (base is a multiple of 32).
+// Rows are 128-byte aligned, so the TMA 128-byte swizzle (chunk c of row r stored at chunk c ^ (r & 7)) is a pure
+// XOR on the shared address: row_addr_swz = row_addr ^ ((r & 7) << 4), chunk c at row_addr_swz ^ (c << 4).
+template <int FW>
+__device__ __forceinline__ void fold_step(uint32_t (&win)[FW], int base, uint32_t row_addr_swz) {
 #pragma unroll
 	for (int c = 0; c < 8; ++c) {
 		const uint4 v = lds128(row_addr_swz ^ (c << 4));
-		LZ_FOLD(win, BASE + 4 * c + 0, v.x);
-		LZ_FOLD(win, BASE + 4 * c + 1, v.y);
-		LZ_FOLD(win, BASE + 4 * c + 2, v.z);
-		LZ_FOLD(win, BASE + 4 * c + 3, v.w);
+		fold_word<FW>(win, base + 4 * c + 0, v.x);
+		fold_word<FW>(win, base + 4 * c + 1, v.y);
+		fold_word<FW>(win, base + 4 * c + 2, v.z);
+		fold_word<FW>(win, base + 4 * c + 3, v.w);
 	}
 }
 
-// After the last word of a stream (word count a multiple of 64): run the recurrence 53 more steps with
-// zero input, pulling ONLY from real stream words (lag > j), which leaves R_j = win[j], j < 53, with
-// stream(x) * y^53 = R(x) (mod P); then reduce R with the byte tables.
-__device__ __forceinline__ uint32_t fold_finish(uint32_t (&win)[64], const uint32_t *tab) {
-	constexpr int lags[9] = {15, 17, 20, 23, 26, 28, 46, 50, 53};
+// After the last word of a stream (word count a multiple of FW): run the recurrence deg more steps with zero input,
+// pulling ONLY from real stream words (lag > j), which leaves R_j = win[j], j < deg, with
+// stream(x) * y^deg = R(x) (mod P); then reduce R with the byte tables.
+template <int FW>
+__device__ __forceinline__ uint32_t fold_finish(uint32_t (&win)[FW], const uint32_t *tab) {
+	constexpr int deg = FoldSpec<FW>::deg;
 #pragma unroll
-	for (int j = 0; j < kFoldDeg; ++j) {
+	for (int j = 0; j < deg; ++j) {
 		uint32_t acc = 0;
 #pragma unroll
-		for (int t = 0; t < 9; ++t)
-			if (lags[t] > j) acc ^= win[(j - lags[t]) & 63];
+		for (int t = 0; t < FoldSpec<FW>::nlag; ++t)
+			if (FoldSpec<FW>::lag(t) > j) acc ^= win[(j - FoldSpec<FW>::lag(t)) & (FW - 1)];
 		win[j] = acc;
 	}
 	uint32_t st = 0;
 #pragma unroll
-	for (int j = 0; j < kFoldDeg; ++j) st = crc_step_word_ldg(st, win[j], tab);
+	for (int j = 0; j < deg; ++j) st = crc_step_word_ldg(st, win[j], tab);
 	return st;
 }
 
@@ -216,9 +239,14 @@ __device__ __forceinline__ uint32_t fold_finish(uint32_t (&win)[64], const uint3
 //   [.., + NPST*pstage)       parity staging ring  pstage = roundup(PROWS*128, 1024)
 //   + 0    s_blk[2][64]       block linear CRCs of the current / previous unit (row-0 parity CRC)
 //   + 520  full[NST], empty[NST], pfull[NPST], pempty[NPST]   (8 bytes each)
-template <int M, bool GENERIC, int KT, int GT>
-__global__ void __launch_bounds__(kFusedThreads, 2)
+// register budget: the register file is handed out per CTA in 4-warp granules, so a 9-warp CTA is charged for 12:
+// 2 CTAs/SM -> 65536 / (2 * 384) = 85 -> 96 still fits by measurement (ncu: 2 blocks/SM at 96); 1 CTA/SM -> 65536 / 384 = 170
+#define LZ_FUSED_MAXNREG(fw) __maxnreg__((fw) == 64 ? 96 : 168)
+
+template <int M, bool GENERIC, int KT, int GT, int FW>
+__global__ void LZ_FUSED_MAXNREG(FW)
 fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
+	constexpr int kNST = fused_nst(FW), kNPST = fused_npst(FW);
 	constexpr int PC = (M == 0) ? 0 : (GENERIC ? M : M - 1);  // parity parts whose CRC is computed from bytes
 	constexpr int P0 = GENERIC ? 0 : 1;                       // first such parity part
 
@@ -299,7 +327,7 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 	const bool warp_has_prow = PROWS && cw >= first_pwarp && cw <= last_pwarp;
 	const bool warp_reads_stage = cw < n_stage_warps;
 
-	uint32_t win[64];
+	uint32_t win[FW];
 	uint32_t it = 0;               // this CTA's global step counter
 	uint32_t st = 0, ph = 0;       // data stage index / phase parity of `it`
 	uint32_t pst = 0, pph = 0;     // parity ring index / phase parity of `it`
@@ -311,12 +339,12 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 		const uint32_t next_unit = unit + gridDim.x;   // only read when it exists (it + NST < total_steps)
 		const uint32_t next_c = next_unit / p.units_per_chunk, next_gi = next_unit % p.units_per_chunk;
 #pragma unroll
-		for (int i = 0; i < 64; ++i) win[i] = 0;
+		for (int i = 0; i < FW; ++i) win[i] = 0;
 
-		for (int step2 = 0; step2 < kStepsPerUnit; step2 += 2) {
+		for (int step0 = 0; step0 < kStepsPerUnit; step0 += FW / 32) {
 #pragma unroll
-			for (int half = 0; half < 2; ++half) {
-				const int step = step2 + half;
+			for (int sub = 0; sub < FW / 32; ++sub) {
+				const int step = step0 + sub;
 				const uint32_t stage = sbase + st * stage_bytes;
 				const uint32_t pstage = pstage0 + pst * pstage_bytes;
 				if (warp_reads_stage) mbar_wait(a_full + 8 * st, ph);
@@ -386,8 +414,7 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 				if (PC > 0 && warp_has_prow && !LZ_PROBE(2)) mbar_wait(a_pfull + 8 * pst, pph);
 				if (has_stream && !LZ_PROBE(4)) {
 					const uint32_t rowp = row_addr0 + (is_data_row ? st : pst) * row_stride;
-					if (half == 0) fold_step<0>(win, rowp);
-					else fold_step<32>(win, rowp);
+					fold_step<FW>(win, sub * 32, rowp);
 				}
 				__syncwarp();
 				if (lane == 0) {
@@ -407,7 +434,7 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 
 		// ---------------- unit epilogue: streams -> block CRCs ----------------
 		uint32_t lin = 0;
-		if (has_stream) lin = crc_mulmod(fold_finish(win, p.tables), p.qmult[my_row & 3]);
+		if (has_stream) lin = crc_mulmod(fold_finish<FW>(win, p.tables), p.qmult[my_row & 3]);
 		lin ^= __shfl_xor_sync(0xffffffffu, lin, 1);
 		lin ^= __shfl_xor_sync(0xffffffffu, lin, 2);
 		const uint32_t blk = a_blk + unit_parity * 256;
@@ -487,11 +514,12 @@ struct RecoverParams {
 // E = erased data parts; KT = compile-time K (0 = runtime); R0, R1 = generator rows of the first two parity
 // parts in use when known at compile time (-1 = read p.par_row): the RAID-6 shapes (row 0 = XOR, row 1 = powers of 2)
 // get constant doubling counts and the "last unknown = S0 ^ others" shortcut.
-// One CTA per SM (the solve needs registers: no spills at <= 224 per thread) with a deeper stage ring instead.
+// One CTA per SM (the solve needs registers: no spills at <= 224 per thread) with a deeper stage ring instead;
+// that also leaves room for the 128-word fold window (3 LOP3 per word).
 constexpr int kRecoverStages = 6;
 
-template <int E, int KT, int R0, int R1>
-__global__ void __launch_bounds__(kFusedThreads, 1)
+template <int E, int KT, int R0, int R1, int kRecoverFW>
+__global__ void __maxnreg__(168)
 fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_constant__ RecoverParams p) {
 	extern __shared__ __align__(1024) uint8_t smem[];
 	const uint32_t sbase = smem_u32(smem);
@@ -535,7 +563,7 @@ fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 	const uint32_t row_addr0 = (sbase + tid * kStepBytes) ^ ((tid & 7) << 4);
 	const bool warp_has_items = cw < n_gf_warps;
 
-	uint32_t win[64];
+	uint32_t win[kRecoverFW];
 	uint32_t it = 0, st = 0, ph = 0;
 	for (uint32_t unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
 		const uint32_t c = unit / p.units_per_chunk, gi = unit % p.units_per_chunk;
@@ -543,12 +571,12 @@ fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 		const uint32_t next_unit = unit + gridDim.x;
 		const uint32_t next_c = next_unit / p.units_per_chunk, next_gi = next_unit % p.units_per_chunk;
 #pragma unroll
-		for (int i = 0; i < 64; ++i) win[i] = 0;
+		for (int i = 0; i < kRecoverFW; ++i) win[i] = 0;
 
-		for (int step2 = 0; step2 < kStepsPerUnit; step2 += 2) {
+		for (int step0 = 0; step0 < kStepsPerUnit; step0 += kRecoverFW / 32) {
 #pragma unroll
-			for (int half = 0; half < 2; ++half) {
-				const int step = step2 + half;
+			for (int sub = 0; sub < kRecoverFW / 32; ++sub) {
+				const int step = step0 + sub;
 				const uint32_t stage = sbase + st * stage_bytes;
 				mbar_wait(a_full + 8 * st, ph);
 
@@ -628,8 +656,7 @@ fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 				// ---------------- CRC role: linear CRC of every input row ----------------
 				if (verify) {
 					const uint32_t rowp = row_addr0 + st * stage_bytes;
-					if (half == 0) fold_step<0>(win, rowp);
-					else fold_step<32>(win, rowp);
+					fold_step<kRecoverFW>(win, sub * 32, rowp);
 				}
 				__syncwarp();
 				if (lane == 0 && mbar_arrive_is_last(a_empty + 8 * st) && it + kRecoverStages < total_steps) {
@@ -644,7 +671,7 @@ fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 
 		// ---------------- unit epilogue: compare with the stored CRCs ----------------
 		uint32_t lin = 0;
-		if (verify) lin = crc_mulmod(fold_finish(win, p.tables), p.qmult[rr & 3]);
+		if (verify) lin = crc_mulmod(fold_finish<kRecoverFW>(win, p.tables), p.qmult[rr & 3]);
 		lin ^= __shfl_xor_sync(0xffffffffu, lin, 1);
 		lin ^= __shfl_xor_sync(0xffffffffu, lin, 2);
 		if (verify && (rr & 3) == 0) {

@@ -44,6 +44,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--full-size-only", action="store_true", help="all goals, 64 MiB chunks only")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
@@ -61,6 +62,8 @@ def main():
     sizes = [1 << 20, 4 << 20, 16 << 20, 64 << 20, (37 << 20) + 5 * BLOCK]
     if args.quick:
         goals, sizes = ["ec(3,2)", "ec(8,2)"], [64 << 20]
+    if args.full_size_only:
+        sizes = [64 << 20]
     d_data = torch.empty(args.bytes, dtype=torch.uint8, device=dev)
     eng.fill_chunks_dev(d_data.data_ptr(), args.bytes // (64 << 20), 64 << 20, 64 << 20, seed=12345, stream=sp)
     for text in goals:
