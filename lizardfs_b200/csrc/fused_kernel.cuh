@@ -239,12 +239,11 @@ __device__ __forceinline__ uint32_t fold_finish(uint32_t (&win)[FW], const uint3
 //   [.., + NPST*pstage)       parity staging ring  pstage = roundup(PROWS*128, 1024)
 //   + 0    s_blk[2][64]       block linear CRCs of the current / previous unit (row-0 parity CRC)
 //   + 520  full[NST], empty[NST], pfull[NPST], pempty[NPST]   (8 bytes each)
-// register budget: the register file is handed out per CTA in 4-warp granules, so a 9-warp CTA is charged for 12:
-// 2 CTAs/SM -> 65536 / (2 * 384) = 85 -> 96 still fits by measurement (ncu: 2 blocks/SM at 96); 1 CTA/SM -> 65536 / 384 = 170
-#define LZ_FUSED_MAXNREG(fw) __maxnreg__((fw) == 64 ? 96 : 168)
-
+// Register budget: __launch_bounds__(288, 2) makes ptxas target 96 registers (2 CTAs/SM), (288, 1) -> 168.
+// (An explicit __maxnreg__(96) instead of the launch bounds produced a 5 % slower kernel on the same box: ptxas
+// schedules differently when it does not know the block size.)
 template <int M, bool GENERIC, int KT, int GT, int FW>
-__global__ void LZ_FUSED_MAXNREG(FW)
+__global__ void __launch_bounds__(kFusedThreads, FW == 64 ? 2 : 1)
 fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
 	constexpr int kNST = fused_nst(FW), kNPST = fused_npst(FW);
 	constexpr int PC = (M == 0) ? 0 : (GENERIC ? M : M - 1);  // parity parts whose CRC is computed from bytes
@@ -519,7 +518,7 @@ struct RecoverParams {
 constexpr int kRecoverStages = 6;
 
 template <int E, int KT, int R0, int R1, int kRecoverFW>
-__global__ void __maxnreg__(168)
+__global__ void __launch_bounds__(kFusedThreads, 1)
 fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_constant__ RecoverParams p) {
 	extern __shared__ __align__(1024) uint8_t smem[];
 	const uint32_t sbase = smem_u32(smem);
