@@ -110,6 +110,33 @@ def test_encode_full_size_ec32_tail_stripe(eng, oracle):
     assert (parity[0] == p_ref).all() and (crc[0] == c_ref).all()
 
 
+def test_full_size_batch_roundtrip_with_verification(eng):
+    """BASELINE configs[2]/[3] at full chunk size: encode a batch of 64 MiB chunks, lose two data parts, recover with the
+    stored CRCs verified and the chunk-order image rebuilt; the round trip must reproduce every byte."""
+    goal = L.SliceType("ec(8,2)")
+    n, nb, pb = 4, 1024, 128
+    data = rnd((n, nb * BLOCK), 77)
+    parity, crc = eng.encode_chunks(goal, data)
+    blocks = data.reshape(n, pb, 8, BLOCK)
+    parts = [np.ascontiguousarray(blocks[:, :, j]).reshape(n, pb * BLOCK) for j in range(8)]
+    parts += [np.ascontiguousarray(parity[:, r]) for r in range(2)]
+    pcrc = [np.ascontiguousarray(crc[:, :nb].reshape(n, pb, 8)[:, :, j]) for j in range(8)]
+    pcrc += [np.ascontiguousarray(crc[:, nb + r * pb: nb + (r + 1) * pb]) for r in range(2)]
+    lost = (2, 7)
+    avail = [None if i in lost else parts[i] for i in range(10)]
+    acrc = [None if i in lost else pcrc[i] for i in range(10)]
+    out, img = eng.recover_chunks(goal, nb, avail, part_crc=acrc, chunk_image=True)
+    for i in lost:
+        assert (out[i] == parts[i]).all()
+    assert (img == data).all()
+    # and a corrupted stored CRC deep inside the batch is located exactly
+    acrc[9] = acrc[9].copy()
+    acrc[9][3, 100] ^= 0x8000
+    with pytest.raises(L.ChunkCrcError) as ei:
+        eng.recover_chunks(goal, nb, avail, part_crc=acrc)
+    assert ei.value.where == (3, 9, 100)
+
+
 def test_linearity_properties_full_batch(eng):
     """Size-independent properties on a larger batch (no oracle pass needed):
     CRC(P) = xor of the data CRCs (+ the zero-block constant for an even count), and parity of the

@@ -83,6 +83,14 @@ def main():
             label = f"{clen / (1 << 20):.2f} MiB"
             lines.append(f"| {text} | {label} | {n} | {ms:.3f} | {gibs:.0f} | {gbs:.0f} | {gbs / peak:.3f} |")
             del d_par, d_crc
+    # scrub: CRC32 of every 64 KiB block of the resident buffer (hdd_int_test, hddspacemgr.cc:2174-2190)
+    nblk = args.bytes // BLOCK
+    d_c = torch.empty(nblk, dtype=torch.int32, device=dev)
+    ms = time_steps(lambda: eng.crc_blocks_dev(d_data.data_ptr(), nblk, d_c.data_ptr(), stream=sp), args.steps, args.warmup, stream)
+    gbs = (args.bytes + 4 * nblk) / (ms / 1e3) / 1e9
+    lines += ["", "## scrub (CRC32 of 64 KiB blocks, fused kernel with M = 0)", "", "| blocks | ms | GiB/s | GB/s algorithmic | frac |", "|---|---|---|---|---|",
+              f"| {nblk} | {ms:.3f} | {args.bytes / GIB / (ms / 1e3):.0f} | {gbs:.0f} | {gbs / peak:.3f} |"]
+    del d_c
     # degraded read: ec(8,2), data parts 1 and 4 lost (BASELINE configs[3]); also ec(3,2) / ec(5,3) / xor3
     lines += ["", "## degraded-read recover (stored CRCs verified, chunk-order image written)", "",
               "| goal | lost parts | chunks/launch | variant | ms | GiB/s chunk data | GB/s algorithmic | frac |", "|---|---|---|---|---|---|---|---|"]
