@@ -152,6 +152,14 @@ int lzgpu_recover_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_
                              int64_t *bad /* host; written after an internal sync only if non-NULL */,
                              void *stream);
 
+/* Slice-type conversion helper (replication, SliceRecoveryPlanner::BlockConverter, src/chunkserver/slice_recovery_planner.h:41-57):
+ * chunk order -> part-major data parts (part j block s = chunk block s*k + j, short parts zero-padded to pb blocks).
+ * parts[j] == NULL skips part j.  Parity parts come from lzgpu_encode_chunks. */
+int lzgpu_split_chunks(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb,
+                       const uint8_t *data, size_t chunk_stride, uint8_t *const *parts, size_t part_stride);
+int lzgpu_split_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb,
+                           const void *d_data, size_t chunk_stride, void *const *d_parts, size_t part_stride, void *stream);
+
 /* CRC of n_blocks consecutive blocks of block_len bytes (block_len <= 65536, any value >= 1).
  * crc_out[i] = mycrc32(0, data + i*block_stride, block_len). */
 int lzgpu_crc_blocks(lzgpu_ctx *ctx, const uint8_t *data, size_t n_blocks, uint32_t block_len,

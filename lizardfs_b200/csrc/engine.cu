@@ -626,6 +626,66 @@ extern "C" int lzgpu_recover_chunks(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint
 }
 
 // ------------------------------------------------------------------------------------------------
+// chunk order -> part-major data parts
+// ------------------------------------------------------------------------------------------------
+extern "C" int lzgpu_split_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb, const void *d_data,
+                                       size_t chunk_stride, void *const *d_parts, size_t part_stride, void *stream) {
+	if (!ctx || !d_data || !d_parts) return LZGPU_ERR_ARG;
+	int rc = check_goal(goal);
+	if (rc) return rc;
+	if (nb == 0 || nb > LZGPU_BLOCKS_IN_CHUNK) { lz_set_error("nb out of range"); return LZGPU_ERR_ARG; }
+	const uint32_t B = LZGPU_BLOCK_SIZE, k = goal->k, pb = (nb + k - 1) / k;
+	if (chunk_stride < static_cast<size_t>(nb) * B || part_stride < static_cast<size_t>(pb) * B || (chunk_stride & 15) || (part_stride & 15)) {
+		lz_set_error("split: bad strides");
+		return LZGPU_ERR_ARG;
+	}
+	if (n_chunks == 0) return LZGPU_OK;
+	DeviceGuard g(ctx->device);
+	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+	SplitArgs a{};
+	a.chunk = static_cast<const uint8_t *>(d_data);
+	for (uint32_t j = 0; j < k; ++j) a.part[j] = static_cast<uint8_t *>(d_parts[j]);
+	a.chunk_stride = chunk_stride;
+	a.part_stride = part_stride;
+	a.k = k;
+	a.nb = nb;
+	a.pb = pb;
+	a.total_units = static_cast<unsigned long long>(n_chunks) * k * pb * (B / 16);
+	chunk_to_parts_kernel<<<grid_for(ctx, a.total_units, 256, 8), 256, 0, st>>>(a);
+	CUDA_TRY(cudaGetLastError());
+	ctx->stats.kernel_launches++;
+	return LZGPU_OK;
+}
+
+extern "C" int lzgpu_split_chunks(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb, const uint8_t *data,
+                                   size_t chunk_stride, uint8_t *const *parts, size_t part_stride) {
+	if (!ctx || !data || !parts) return LZGPU_ERR_ARG;
+	int rc = check_goal(goal);
+	if (rc) return rc;
+	if (nb == 0 || nb > LZGPU_BLOCKS_IN_CHUNK) { lz_set_error("nb out of range"); return LZGPU_ERR_ARG; }
+	if (n_chunks == 0) return LZGPU_OK;
+	const uint32_t B = LZGPU_BLOCK_SIZE, k = goal->k, pb = (nb + k - 1) / k;
+	const size_t chunk_bytes = static_cast<size_t>(nb) * B, part_bytes = static_cast<size_t>(pb) * B;
+	if (chunk_stride < chunk_bytes || part_stride < part_bytes) { lz_set_error("split: strides smaller than the payload"); return LZGPU_ERR_ARG; }
+	std::lock_guard<std::mutex> lk(ctx->mu);
+	DeviceGuard g(ctx->device);
+	cudaStream_t st = ctx->stream;
+	void *d_in = nullptr, *d_out = nullptr;
+	if ((rc = lz_scratch(ctx, kScratchIn0, static_cast<size_t>(n_chunks) * chunk_bytes, &d_in))) return rc;
+	if ((rc = lz_scratch(ctx, kScratchPar0, static_cast<size_t>(n_chunks) * part_bytes * k, &d_out))) return rc;
+	CUDA_TRY(cudaMemcpy2DAsync(d_in, chunk_bytes, data, chunk_stride, chunk_bytes, n_chunks, cudaMemcpyHostToDevice, st));
+	std::vector<void *> dp(k, nullptr);
+	for (uint32_t j = 0; j < k; ++j)
+		if (parts[j]) dp[j] = static_cast<uint8_t *>(d_out) + static_cast<size_t>(j) * n_chunks * part_bytes;
+	if ((rc = lzgpu_split_chunks_dev(ctx, goal, n_chunks, nb, d_in, chunk_bytes, dp.data(), part_bytes, st))) return rc;
+	for (uint32_t j = 0; j < k; ++j)
+		if (parts[j]) CUDA_TRY(cudaMemcpy2DAsync(parts[j], part_stride, dp[j], part_bytes, part_bytes, n_chunks, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	ctx->stats.bytes_h2d += static_cast<uint64_t>(n_chunks) * chunk_bytes;
+	return LZGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // CRC of block arrays / scrub
 // ------------------------------------------------------------------------------------------------
 extern "C" int lzgpu_crc_blocks_dev(lzgpu_ctx *ctx, const void *d_data, size_t n_blocks, uint32_t block_len, size_t block_stride,

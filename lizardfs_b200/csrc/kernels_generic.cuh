@@ -113,6 +113,32 @@ __global__ void __launch_bounds__(256) parts_to_chunk_kernel(const GatherArgs a)
 	}
 }
 
+// The inverse pick (reference src/chunkserver/slice_recovery_planner.h:41-57 BlockConverter: part block i <- chunk block
+// i*k + j): chunk order -> part-major data parts, short parts zero-padded to pb blocks.
+struct SplitArgs {
+	const uint8_t *chunk;
+	uint8_t *part[kMaxSrc];  // nullptr = part not wanted
+	unsigned long long chunk_stride, part_stride, total_units;  // units = n_chunks * k * pb * 4096
+	unsigned int k, nb, pb;
+};
+
+__global__ void __launch_bounds__(256) chunk_to_parts_kernel(const SplitArgs a) {
+	const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+	for (unsigned long long u = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+	     u < a.total_units; u += stride) {
+		const unsigned o = static_cast<unsigned>(u & 4095u);
+		const unsigned long long blk = u >> 12;                       // (c, s, j) with j fastest: reads stay contiguous
+		const unsigned j = static_cast<unsigned>(blk % a.k);
+		const unsigned s = static_cast<unsigned>((blk / a.k) % a.pb);
+		const unsigned long long c = blk / (static_cast<unsigned long long>(a.k) * a.pb);
+		if (!a.part[j]) continue;
+		const unsigned b = s * a.k + j;
+		uint4 v = make_uint4(0, 0, 0, 0);
+		if (b < a.nb) v = ld_stream(reinterpret_cast<const uint4 *>(a.chunk + c * a.chunk_stride + static_cast<unsigned long long>(b) * 65536ull + 16ull * o));
+		st_stream(reinterpret_cast<uint4 *>(a.part[j] + c * a.part_stride + static_cast<unsigned long long>(s) * 65536ull + 16ull * o), v);
+	}
+}
+
 // Linear CRC of many equally sized blocks, one warp per block, table driven (slicing by 4).
 // The message is virtually left-padded with zero words to 32*wpl words (leading zeros do not change
 // the linear CRC), lane L owns virtual words [L*wpl, (L+1)*wpl); lane partials are merged with the

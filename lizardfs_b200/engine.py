@@ -356,6 +356,25 @@ class Engine:
             raise ChunkCrcError(rc, "recover_chunks_dev", (bad[0], bad[1], bad[2]))
         _check(rc, "recover_chunks_dev")
 
+    # ---- slice conversion ---------------------------------------------------------------------
+    def split_chunks(self, goal, data, nb=None):
+        """chunk order [n, nb*64K] -> list of k part-major data parts [n, pb*64K] (BlockConverter,
+        src/chunkserver/slice_recovery_planner.h:41-57)."""
+        data = _u8(data)
+        if data.ndim == 1:
+            data = data.reshape(1, -1)
+        n, stride = data.shape
+        if nb is None:
+            nb = stride // BLOCK_SIZE
+        pb = (nb + goal.k - 1) // goal.k
+        parts = [np.empty((n, pb * BLOCK_SIZE), dtype=np.uint8) for _ in range(goal.k)]
+        _check(self.lib.lzgpu_split_chunks(self.h, C.byref(goal.c), n, nb, _p(data), stride, _ptr_array(parts), pb * BLOCK_SIZE), "split_chunks")
+        return parts
+
+    def split_chunks_dev(self, goal, n_chunks, nb, d_data, chunk_stride, d_parts, part_stride, stream=None):
+        dp = (C.c_void_p * goal.k)(*[p if p else None for p in d_parts])
+        _check(self.lib.lzgpu_split_chunks_dev(self.h, C.byref(goal.c), n_chunks, nb, d_data, chunk_stride, dp, part_stride, stream), "split_chunks_dev")
+
     # ---- CRC ---------------------------------------------------------------------------------
     def crc_blocks(self, data, block_len=BLOCK_SIZE, block_stride=None):
         data = _u8(data).reshape(-1)

@@ -204,6 +204,17 @@ def test_recover_verifies_crc(eng):
         eng.recover_chunks(goal, nblocks, [None, None, None] + parts[3:], want=[1, 1, 1] + [0] * 7)
 
 
+@pytest.mark.parametrize("text,nblocks", [("ec(8,2)", 19), ("ec(3,2)", 10), ("xor2", 5), ("ec(5,3)", 25)])
+def test_split_chunks_is_the_block_converter(eng, text, nblocks):
+    goal = L.SliceType(text)
+    data = rnd((3, nblocks * BLOCK), 91)
+    parts = eng.split_chunks(goal, data)
+    for c in range(3):
+        want, pb = O.split_parts(data[c], goal.k)
+        for j in range(goal.k):
+            assert (parts[j][c] == want[j]).all()
+
+
 def test_recover_parity_rebuild(eng):
     """Chunkserver replication rebuilds parity parts too (ECReadPlan::RecoverParity, ec_read_plan.h:38-76)."""
     goal = L.SliceType("ec(5,3)")
