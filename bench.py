@@ -219,6 +219,19 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    # Host buffers of the e2e leg should live on the NUMA node next to this rank's GPU: bind the process to the GPU's
+    # ideal CPUs before anything is allocated (restored before the CPU baseline, which must see every core).
+    all_cpus = os.sched_getaffinity(0)
+    numa_note = "not bound"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else local
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+        numa_note = f"bound to {len(os.sched_getaffinity(0))} CPUs local to GPU {phys}"
+    except Exception as exc:  # no NVML / not permitted: keep the default placement
+        numa_note = f"not bound ({type(exc).__name__})"
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -322,7 +335,7 @@ def main():
         assert (np_crc[:crc_stride] == crc_host).all(), "e2e result differs from the resident run"
         e2e = {"value": world * E * args.steps * CHUNK / GIB / dt, "unit": "GiB/s", "h2d_bytes_per_step": E * CHUNK,
                "d2h_bytes_per_step": E * (par_stride + 4 * crc_stride), "chunks_per_step": E,
-               "timing": "host wall clock around the synchronous C-ABI call, max over ranks"}
+               "timing": "host wall clock around the synchronous C-ABI call, max over ranks", "host_placement": numa_note}
 
     if rank != 0:
         if dist:
@@ -355,6 +368,7 @@ def main():
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)
         cores = host_threads()
         n = args.cpu_chunks or max(cores, 8)
         v, kind, secs = cpu_reference_run(args.goal, n, cores)
