@@ -63,6 +63,24 @@ extern "C" int lzgpu_device_count(void) {
 	return n;
 }
 
+extern "C" void lzgpu_ctx_destroy(lzgpu_ctx *ctx);
+
+static int ctx_init_resources(lzgpu_ctx *ctx) {
+	CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+	for (auto &s : ctx->slot_stream) CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+	uint32_t tabs[4][256];
+	lz::crc_make_tables(tabs);
+	CUDA_TRY(cudaMalloc(&ctx->d_crc_tables, sizeof(tabs)));
+	CUDA_TRY(cudaMemcpy(ctx->d_crc_tables, tabs, sizeof(tabs), cudaMemcpyHostToDevice));
+	CUDA_TRY(cudaMalloc(&ctx->d_first_bad, sizeof(unsigned long long) * LZGPU_MAX_PARTS));
+	CUDA_TRY(cudaMallocHost(&ctx->h_first_bad, sizeof(unsigned long long) * LZGPU_MAX_PARTS));
+	if (lz::crc_of_zeros(LZGPU_BLOCK_SIZE) != kCrcZeroBlock64K) {
+		lz_set_error("internal: CRC constant self-check failed");
+		return LZGPU_ERR_ARG;
+	}
+	return lz_fused_init(ctx);
+}
+
 extern "C" int lzgpu_ctx_create(int device, lzgpu_ctx **out) {
 	if (!out) return LZGPU_ERR_ARG;
 	*out = nullptr;
@@ -85,20 +103,11 @@ extern "C" int lzgpu_ctx_create(int device, lzgpu_ctx **out) {
 	auto *ctx = new lzgpu_ctx();
 	ctx->device = device;
 	ctx->sm_count = prop.multiProcessorCount;
-	CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-	for (auto &s : ctx->slot_stream) CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-	uint32_t tabs[4][256];
-	lz::crc_make_tables(tabs);
-	CUDA_TRY(cudaMalloc(&ctx->d_crc_tables, sizeof(tabs)));
-	CUDA_TRY(cudaMemcpy(ctx->d_crc_tables, tabs, sizeof(tabs), cudaMemcpyHostToDevice));
-	CUDA_TRY(cudaMalloc(&ctx->d_first_bad, sizeof(unsigned long long) * LZGPU_MAX_PARTS));
-	CUDA_TRY(cudaMallocHost(&ctx->h_first_bad, sizeof(unsigned long long) * LZGPU_MAX_PARTS));
-	if (lz::crc_of_zeros(LZGPU_BLOCK_SIZE) != kCrcZeroBlock64K) {
-		lz_set_error("internal: CRC constant self-check failed");
-		return LZGPU_ERR_ARG;
+	int rc = ctx_init_resources(ctx);
+	if (rc != LZGPU_OK) {
+		lzgpu_ctx_destroy(ctx);  // releases whatever was created before the failure
+		return rc;
 	}
-	int rc = lz_fused_init(ctx);
-	if (rc != LZGPU_OK) return rc;
 	*out = ctx;
 	return LZGPU_OK;
 }
@@ -109,11 +118,12 @@ extern "C" void lzgpu_ctx_destroy(lzgpu_ctx *ctx) {
 	cudaDeviceSynchronize();
 	lz_fused_destroy(ctx);
 	for (auto &b : ctx->scratch) if (b.ptr) cudaFree(b.ptr);
-	cudaFree(ctx->d_crc_tables);
-	cudaFree(ctx->d_first_bad);
-	cudaFreeHost(ctx->h_first_bad);
-	for (auto &s : ctx->slot_stream) cudaStreamDestroy(s);
-	cudaStreamDestroy(ctx->stream);
+	if (ctx->d_crc_tables) cudaFree(ctx->d_crc_tables);
+	if (ctx->d_first_bad) cudaFree(ctx->d_first_bad);
+	if (ctx->h_first_bad) cudaFreeHost(ctx->h_first_bad);
+	for (auto &s : ctx->slot_stream) if (s) cudaStreamDestroy(s);
+	if (ctx->stream) cudaStreamDestroy(ctx->stream);
+	cudaGetLastError();
 	delete ctx;
 }
 

@@ -9,8 +9,9 @@
 //   ROWS = G*K*4 consecutive rows.  Each pipeline step moves one box [ROWS x 128 B] with a single
 //   cp.async.bulk.tensor (TMA, 128-byte swizzle, out-of-range rows zero-filled = the absent blocks of a
 //   short last stripe, reference chunk_writer.cc:97-108,377) into one of NST shared-memory stages,
-//   tracked by full/empty mbarriers; 128 steps stream the unit.  One producer warp issues TMA, the
-//   other warps consume.  Parity leaves through 16-byte coalesced global stores (full 128 B lines).
+//   tracked by full/empty mbarriers; 128 steps stream the unit.  There is no producer warp: the consumer
+//   warp whose arrival completes a stage's `empty` barrier re-arms it and issues the TMA load NST steps
+//   ahead.  Parity leaves through 16-byte coalesced global stores (full 128 B lines).
 //
 // Work mapping (consumer threads)
 //   CRC role   thread t owns row t: a contiguous 16 KiB stream, 128 B per step, read conflict-free
@@ -27,7 +28,7 @@
 //   g(x^32) = g(x)^32 is too, so with y = x^32 (one 32-bit word)  y^53 = y^38+...+1 (mod P):
 //   word u is xored into words u+15, u+17, u+20, u+23, u+26, u+28, u+46, u+50, u+53.  In pull form
 //   W'[u] = W[u] ^ W'[u-15] ^ ... ^ W'[u-53]: nine XORs (5 LOP3) per word on a 64-word register
-//   window, no shifts, no lookups.  After 4096 words the stream is flushed into 53 words that are
+//   window, no shifts, no lookups (FoldSpec below).  After 4096 words the stream is flushed into 53 words that are
 //   reduced once with the byte tables; quarter streams are merged with x^(8*len) multipliers
 //   (the mycrc32_combine identity, reference crc.cc:58-60).  CRC(parity row 0) of a Vandermonde code
 //   needs no work at all: P = xor of the data blocks, hence lin(P) = xor of their lin CRCs

@@ -76,6 +76,31 @@ def test_encode_many_small_chunks_flat_units(eng, oracle, text, nblocks, n_chunk
         assert (crc[c] == c_ref).all(), (text, c)
 
 
+def test_encode_and_recover_every_goal_shape(eng, oracle):
+    """Every ec(k, m <= 4) for k = 2..32, a few m >= 5 (generic route) and xor2..9: stripe-group geometry, mixed
+    data/parity warps, the Cauchy switch (m = 4, k > 20) and ragged last stripes all go through here."""
+    rng = np.random.default_rng(2024)
+    goals = [L.SliceType(1, k, m) for k in range(2, 33) for m in range(1, 5)]
+    goals += [L.SliceType(1, k, m) for k, m in [(4, 5), (10, 6), (32, 8)]] + [L.SliceType(0, k, 1) for k in range(2, 10)]
+    for goal in goals:
+        k, m = goal.k, goal.m
+        nb = int(rng.integers(k, 2 * k + 2))           # 1..2 full stripes + a ragged one
+        data = rng.integers(0, 256, size=(2, nb * BLOCK), dtype=np.uint8)
+        parity, crc = eng.encode_chunks(goal, data)
+        for c in range(2):
+            p_ref, c_ref = oracle.encode_chunk(goal.kind, k, m, data[c])
+            assert (parity[c] == p_ref).all(), str(goal)
+            assert (crc[c] == c_ref).all(), str(goal)
+        # lose min(m, 2) random data parts and rebuild them (fused recover where the generator is Vandermonde)
+        lost = sorted(rng.choice(k, size=min(m, 2), replace=False).tolist())
+        parts = all_parts(data, parity, k)
+        avail = [None if i in lost else parts[i] for i in range(k + m)]
+        out, img = eng.recover_chunks(goal, nb, avail, chunk_image=True)
+        for i in lost:
+            assert (out[i] == parts[i]).all(), (str(goal), lost)
+        assert (img == data).all(), str(goal)
+
+
 def test_encode_partial_last_block(eng, oracle):
     goal = L.SliceType("ec(3,2)")
     clen = 7 * BLOCK + 12345
