@@ -152,6 +152,21 @@ int lzgpu_recover_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_
                              int64_t *bad /* host; written after an internal sync only if non-NULL */,
                              void *stream);
 
+/* Wire-format producer: LIZ_CLTOCS_WRITE_DATA packet prefixes (src/protocol/cltocs.h:116-137) for
+ * every block of every part of the encoded chunks, built on the GPU straight from the CRC array of
+ * lzgpu_encode_chunks, so that WriteExecutor::addDataPacket (src/common/write_executor.cc:91-107) becomes a pointer
+ * hand-off.  Prefix = type:u32(1212) length:u32(30+65536) version:u32(0) chunkId:u64 writeId:u32 block:u16 offset:u32(0)
+ * size:u32(65536) crc:u32, big-endian, 38 bytes.  Output layout: out[((c*(k+m) + part)*pb + s)*38], part numbering of
+ * this API, block = s; blocks a short data part does not have are left as 38 zero bytes.
+ * writeId = write_id_base + (c*(k+m) + part)*pb + s. */
+#define LZGPU_WRITE_PREFIX_SIZE 38
+int lzgpu_write_data_prefixes(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb,
+                              const uint32_t *crc, size_t crc_stride, const uint64_t *chunk_ids,
+                              uint32_t write_id_base, uint8_t *out);
+int lzgpu_write_data_prefixes_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb,
+                                  const void *d_crc, size_t crc_stride, const void *d_chunk_ids,
+                                  uint32_t write_id_base, void *d_out, void *stream);
+
 /* Slice-type conversion helper (replication, SliceRecoveryPlanner::BlockConverter, src/chunkserver/slice_recovery_planner.h:41-57):
  * chunk order -> part-major data parts (part j block s = chunk block s*k + j, short parts zero-padded to pb blocks).
  * parts[j] == NULL skips part j.  Parity parts come from lzgpu_encode_chunks. */

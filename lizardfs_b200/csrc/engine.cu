@@ -636,6 +636,60 @@ extern "C" int lzgpu_recover_chunks(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint
 }
 
 // ------------------------------------------------------------------------------------------------
+// wire-format producer: LIZ_CLTOCS_WRITE_DATA prefixes from the CRC array
+// ------------------------------------------------------------------------------------------------
+extern "C" int lzgpu_write_data_prefixes_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb, const void *d_crc,
+                                              size_t crc_stride, const void *d_chunk_ids, uint32_t write_id_base, void *d_out, void *stream) {
+	if (!ctx || !d_crc || !d_chunk_ids || !d_out) return LZGPU_ERR_ARG;
+	int rc = check_goal(goal);
+	if (rc) return rc;
+	if (nb == 0 || nb > LZGPU_BLOCKS_IN_CHUNK) { lz_set_error("nb out of range"); return LZGPU_ERR_ARG; }
+	const uint32_t k = goal->k, m = goal->m, pb = (nb + k - 1) / k;
+	if (crc_stride < nb + static_cast<size_t>(m) * pb) { lz_set_error("prefixes: crc_stride too small"); return LZGPU_ERR_ARG; }
+	if (n_chunks == 0) return LZGPU_OK;
+	DeviceGuard g(ctx->device);
+	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+	PrefixArgs a{};
+	a.crc = static_cast<const uint32_t *>(d_crc);
+	a.chunk_ids = static_cast<const unsigned long long *>(d_chunk_ids);
+	a.out = static_cast<uint8_t *>(d_out);
+	a.crc_stride = crc_stride;
+	a.k = k; a.m = m; a.nb = nb; a.pb = pb;
+	a.write_id_base = write_id_base;
+	a.total = static_cast<unsigned long long>(n_chunks) * (k + m) * pb;
+	write_prefix_kernel<<<grid_for(ctx, a.total, 256, 4), 256, 0, st>>>(a);
+	CUDA_TRY(cudaGetLastError());
+	ctx->stats.kernel_launches++;
+	return LZGPU_OK;
+}
+
+extern "C" int lzgpu_write_data_prefixes(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb, const uint32_t *crc,
+                                          size_t crc_stride, const uint64_t *chunk_ids, uint32_t write_id_base, uint8_t *out) {
+	if (!ctx || !crc || !chunk_ids || !out) return LZGPU_ERR_ARG;
+	int rc = check_goal(goal);
+	if (rc) return rc;
+	if (nb == 0 || nb > LZGPU_BLOCKS_IN_CHUNK) { lz_set_error("nb out of range"); return LZGPU_ERR_ARG; }
+	if (n_chunks == 0) return LZGPU_OK;
+	const uint32_t k = goal->k, m = goal->m, pb = (nb + k - 1) / k;
+	const size_t n_crc = nb + static_cast<size_t>(m) * pb;
+	if (crc_stride < n_crc) { lz_set_error("prefixes: crc_stride too small"); return LZGPU_ERR_ARG; }
+	const size_t out_bytes = static_cast<size_t>(n_chunks) * (k + m) * pb * LZGPU_WRITE_PREFIX_SIZE;
+	std::lock_guard<std::mutex> lk(ctx->mu);
+	DeviceGuard g(ctx->device);
+	cudaStream_t st = ctx->stream;
+	void *d_crc = nullptr, *d_ids = nullptr, *d_out = nullptr;
+	if ((rc = lz_scratch(ctx, kScratchCrc0, static_cast<size_t>(n_chunks) * n_crc * 4, &d_crc))) return rc;
+	if ((rc = lz_scratch(ctx, kScratchCrc1, static_cast<size_t>(n_chunks) * 8, &d_ids))) return rc;
+	if ((rc = lz_scratch(ctx, kScratchPar0, out_bytes, &d_out))) return rc;
+	CUDA_TRY(cudaMemcpy2DAsync(d_crc, n_crc * 4, crc, crc_stride * 4, n_crc * 4, n_chunks, cudaMemcpyHostToDevice, st));
+	CUDA_TRY(cudaMemcpyAsync(d_ids, chunk_ids, static_cast<size_t>(n_chunks) * 8, cudaMemcpyHostToDevice, st));
+	if ((rc = lzgpu_write_data_prefixes_dev(ctx, goal, n_chunks, nb, d_crc, n_crc, d_ids, write_id_base, d_out, st))) return rc;
+	CUDA_TRY(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	return LZGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // chunk order -> part-major data parts
 // ------------------------------------------------------------------------------------------------
 extern "C" int lzgpu_split_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb, const void *d_data,

@@ -139,6 +139,56 @@ __global__ void __launch_bounds__(256) chunk_to_parts_kernel(const SplitArgs a) 
 	}
 }
 
+// LIZ_CLTOCS_WRITE_DATA prefixes (reference src/protocol/cltocs.h:116-137), one thread per (chunk, part, part block).
+struct PrefixArgs {
+	const uint32_t *crc;               // encode output layout: nb data CRCs (chunk order), then m*pb parity CRCs
+	const unsigned long long *chunk_ids;
+	uint8_t *out;                      // [(c*(k+m) + part)*pb + s][38]
+	unsigned long long crc_stride, total;
+	unsigned int k, m, nb, pb, write_id_base;
+};
+
+__device__ __forceinline__ uint8_t *put_be32(uint8_t *p, uint32_t v) {
+	p[0] = static_cast<uint8_t>(v >> 24); p[1] = static_cast<uint8_t>(v >> 16); p[2] = static_cast<uint8_t>(v >> 8); p[3] = static_cast<uint8_t>(v);
+	return p + 4;
+}
+
+__global__ void __launch_bounds__(256) write_prefix_kernel(const PrefixArgs a) {
+	const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+	const unsigned parts = a.k + a.m;
+	for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.total; i += stride) {
+		const unsigned s = static_cast<unsigned>(i % a.pb);
+		const unsigned part = static_cast<unsigned>((i / a.pb) % parts);
+		const unsigned long long c = i / (static_cast<unsigned long long>(a.pb) * parts);
+		uint8_t *p = a.out + i * 38ull;
+		const uint32_t *crc = a.crc + c * a.crc_stride;
+		uint32_t v;
+		bool present = true;
+		if (part < a.k) {
+			const unsigned b = s * a.k + part;  // chunk block of data part `part`, part block s (chunk_writer.cc:505)
+			present = b < a.nb;
+			v = present ? crc[b] : 0u;
+		} else {
+			v = crc[a.nb + (part - a.k) * a.pb + s];
+		}
+		if (!present) {
+			for (int t = 0; t < 38; ++t) p[t] = 0;
+			continue;
+		}
+		const unsigned long long id = a.chunk_ids[c];
+		p = put_be32(p, 1212u);              // LIZ_CLTOCS_WRITE_DATA
+		p = put_be32(p, 30u + 65536u);       // kPrefixSize + payload
+		p = put_be32(p, 0u);                 // version
+		p = put_be32(p, static_cast<uint32_t>(id >> 32));
+		p = put_be32(p, static_cast<uint32_t>(id));
+		p = put_be32(p, a.write_id_base + static_cast<uint32_t>(i));
+		p[0] = static_cast<uint8_t>(s >> 8); p[1] = static_cast<uint8_t>(s); p += 2;
+		p = put_be32(p, 0u);                 // offset inside the block
+		p = put_be32(p, 65536u);             // size
+		put_be32(p, v);
+	}
+}
+
 // Linear CRC of many equally sized blocks, one warp per block, table driven (slicing by 4).
 // The message is virtually left-padded with zero words to 32*wpl words (leading zeros do not change
 // the linear CRC), lane L owns virtual words [L*wpl, (L+1)*wpl); lane partials are merged with the

@@ -356,6 +356,20 @@ class Engine:
             raise ChunkCrcError(rc, "recover_chunks_dev", (bad[0], bad[1], bad[2]))
         _check(rc, "recover_chunks_dev")
 
+    # ---- wire format --------------------------------------------------------------------------
+    def write_data_prefixes(self, goal, nb, crc, chunk_ids, write_id_base=0):
+        """LIZ_CLTOCS_WRITE_DATA prefixes (cltocs.h:116-137) for every block of every part: uint8 [n, k+m, pb, 38]
+        from the CRC array returned by encode_chunks."""
+        crc = np.ascontiguousarray(crc, dtype=np.uint32)
+        n, stride = crc.shape
+        ids = np.ascontiguousarray(chunk_ids, dtype=np.uint64)
+        assert ids.size == n
+        pb = (nb + goal.k - 1) // goal.k
+        out = np.zeros((n, goal.k + goal.m, pb, _lib.WRITE_PREFIX_SIZE), dtype=np.uint8)
+        _check(self.lib.lzgpu_write_data_prefixes(self.h, C.byref(goal.c), n, nb, _p(crc), stride, _p(ids), write_id_base, _p(out)),
+               "write_data_prefixes")
+        return out
+
     # ---- slice conversion ---------------------------------------------------------------------
     def split_chunks(self, goal, data, nb=None):
         """chunk order [n, nb*64K] -> list of k part-major data parts [n, pb*64K] (BlockConverter,

@@ -517,6 +517,27 @@ void lzo_parts_to_chunk(int k, const uint8_t *const *data_parts, uint32_t nb, ui
 		       data_parts[b % (uint32_t)k] + (size_t)(b / (uint32_t)k) * LZO_BLOCK_SIZE, LZO_BLOCK_SIZE);
 }
 
+/* cltocs.h:116-137: serializePacketPrefix(destination, size, LIZ_CLTOCS_WRITE_DATA, 0, chunkId, writeId, block,
+ * offset, size, crc) — PacketHeader(type, length = serialized size of version + fields (30) + size), big-endian. */
+static uint8_t *put_be(uint8_t *p, uint64_t v, int bytes) {
+	for (int i = bytes - 1; i >= 0; --i) *p++ = (uint8_t)(v >> (8 * i));
+	return p;
+}
+
+void lzo_write_data_prefix(uint8_t *out, uint64_t chunk_id, uint32_t write_id, uint16_t block, uint32_t offset,
+                           uint32_t size, uint32_t crc) {
+	uint8_t *p = out;
+	p = put_be(p, 1212u, 4);           /* LIZ_CLTOCS_WRITE_DATA = 1000 + 212 */
+	p = put_be(p, 30u + size, 4);      /* 4 + 8 + 4 + 2 + 4 + 4 + 4 = kPrefixSize, plus the payload */
+	p = put_be(p, 0u, 4);              /* packet version */
+	p = put_be(p, chunk_id, 8);
+	p = put_be(p, write_id, 4);
+	p = put_be(p, block, 2);
+	p = put_be(p, offset, 4);
+	p = put_be(p, size, 4);
+	p = put_be(p, crc, 4);
+}
+
 /* splitmix64 counter stream (not from the reference: SURVEY.md §8d asks for a generator
  * reproducible on CPU and GPU; seed 1, chunk 0 reproduces the survey's known answers). */
 static uint64_t splitmix(uint64_t z) {

@@ -109,6 +109,13 @@ int lzo_recover_chunk(int kind, int k, int m, const uint8_t *const *parts,
 /* part-major -> chunk order gather (chunk_read_planner.h:36-70) */
 void lzo_parts_to_chunk(int k, const uint8_t *const *data_parts, uint32_t nb, uint8_t *chunk);
 
+/* LIZ_CLTOCS_WRITE_DATA packet prefix (src/protocol/cltocs.h:116-137, packet.h:130-136, MFSCommunication.h:630):
+ * header type:u32 = 1212, length:u32 = 30 + size; then version:u32 = 0, chunkId:u64, writeId:u32, block:u16,
+ * offset:u32, size:u32, crc:u32 — all big-endian, 38 bytes; `size` data bytes follow on the wire. */
+#define LZO_WRITE_PREFIX_SIZE 38
+void lzo_write_data_prefix(uint8_t *out38, uint64_t chunk_id, uint32_t write_id, uint16_t block, uint32_t offset,
+                           uint32_t size, uint32_t crc);
+
 /* deterministic synthetic data shared by oracle, tests and the GPU generator:
  * splitmix64 counter stream, word w of chunk c = mix(seed + (c<<40) + w) little-endian. */
 void lzo_fill_chunk(uint8_t *dst, size_t len, uint64_t seed, uint64_t chunk_index);

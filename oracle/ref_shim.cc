@@ -20,6 +20,7 @@
 #include "common/crc.h"
 #include "common/galois_coeff.h"
 #include "common/reed_solomon.h"
+#include "protocol/cltocs.h"
 
 // not declared in galois_field.h but defined in galois_field_isal.cc:37,46
 uint8_t gf_mul(uint8_t a, uint8_t b);
@@ -84,6 +85,16 @@ void ref_recompute_crc_if_block_empty(uint8_t *block, uint32_t *crc) {
 	uint32_t c = *crc;
 	recompute_crc_if_block_empty(block, c);
 	*crc = c;
+}
+
+/* cltocs::writeData::serializePrefix (src/protocol/cltocs.h:118-123): the bytes WriteExecutor::addDataPacket puts
+ * in front of every block it sends (src/common/write_executor.cc:99-103).  Returns the prefix length (38). */
+int ref_write_data_prefix(uint8_t *out, uint64_t chunk_id, uint32_t write_id, uint16_t block, uint32_t offset,
+                          uint32_t size, uint32_t crc) {
+	std::vector<uint8_t> buf;
+	cltocs::writeData::serializePrefix(buf, chunk_id, write_id, block, offset, size, crc);
+	std::memcpy(out, buf.data(), buf.size());
+	return static_cast<int>(buf.size());
 }
 
 /* The reference CALL PATTERN of the write path for one chunk held in chunk order:

@@ -147,6 +147,14 @@ class Lib:
         return rc, out, (bad[0], bad[1])
 
 
+def write_data_prefix(lib, chunk_id, write_id, block, offset, size, crc):
+    """38-byte LIZ_CLTOCS_WRITE_DATA prefix from the oracle restatement or the compiled reference."""
+    out = np.zeros(38, dtype=np.uint8)
+    f = lib.fn("write_data_prefix", None if not lib.is_ref else C.c_int)
+    f(_ptr(out), C.c_uint64(chunk_id), C.c_uint32(write_id), C.c_uint16(block), C.c_uint32(offset), C.c_uint32(size), C.c_uint32(crc))
+    return out
+
+
 def load_oracle():
     path = os.path.join(ORACLE_DIR, "liboracle.so")
     if not os.path.exists(path):

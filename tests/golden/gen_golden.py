@@ -59,6 +59,8 @@ def main():
     out["crc_zero_block"] = int(ref.crc32_zeroblock(0, BLOCK))
     out["crc_combine"] = [[a, b, n, int(ref.crc32_combine(a, b, n))] for a, b, n in
                           [(0x12345678, 0x9ABCDEF0, 1), (0xDEADBEEF, 0x01020304, 65535), (0xFFFFFFFF, 0, 65536), (1, 2, 65537), (0xCAFEBABE, 0x0BADF00D, 1 << 26)]]
+    out["write_data_prefix"] = [[list(a), O.write_data_prefix(ref, *a).tobytes().hex()] for a in
+                                [(0x1122334455667788, 7, 3, 0, 65536, 0xAABBCCDD), (1, 0xFFFFFFFF, 1023, 4096, 61440, 0), (2**63 + 5, 12, 0, 0, 1, 0xD7978EEB)]]
     with open(os.path.join(os.path.dirname(__file__), "vectors.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("wrote vectors.json with", len(out["cases"]), "cases")

@@ -240,6 +240,32 @@ def test_split_chunks_is_the_block_converter(eng, text, nblocks):
             assert (parts[j][c] == want[j]).all()
 
 
+@pytest.mark.parametrize("text,nblocks", [("ec(8,2)", 24), ("ec(3,2)", 10), ("xor3", 7)])
+def test_write_data_prefixes(eng, oracle, text, nblocks):
+    """Wire-format producer: every prefix equals the oracle's restatement of cltocs::writeData::serializePrefix."""
+    goal = L.SliceType(text)
+    k, m = goal.k, goal.m
+    data = rnd((2, nblocks * BLOCK), 93)
+    parity, crc = eng.encode_chunks(goal, data)
+    ids = np.array([0x0102030405060708, 0xFFEEDDCCBBAA9988], dtype=np.uint64)
+    pre = eng.write_data_prefixes(goal, nblocks, crc, ids, write_id_base=1000)
+    pb = (nblocks + k - 1) // k
+    for c in range(2):
+        for part in range(k + m):
+            for s in range(pb):
+                if part < k:
+                    b = s * k + part
+                    if b >= nblocks:
+                        assert not pre[c, part, s].any()
+                        continue
+                    want_crc = int(crc[c, b])
+                else:
+                    want_crc = int(crc[c, nblocks + (part - k) * pb + s])
+                wid = 1000 + (c * (k + m) + part) * pb + s
+                want = O.write_data_prefix(oracle, int(ids[c]), wid, s, 0, BLOCK, want_crc)
+                assert (pre[c, part, s] == want).all(), (c, part, s)
+
+
 def test_recover_parity_rebuild(eng):
     """Chunkserver replication rebuilds parity parts too (ECReadPlan::RecoverParity, ec_read_plan.h:38-76)."""
     goal = L.SliceType("ec(5,3)")

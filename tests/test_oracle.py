@@ -204,3 +204,17 @@ def test_recover_detects_crc_mismatch(oracle):
     assert rc == -3 and where == (2, 1)
     rc, out, _ = oracle.recover_chunk(1, k, m, avail, [None, crcs[1], crcs[2], crcs[3], None], [1, 0, 0, 0, 0], pb)
     assert rc == 0 and (out[0] == allp[0]).all()
+
+
+def test_write_data_prefix_matches_reference(oracle, ref):
+    # the bytes printed by the reference's serializePrefix (cltocs.h:118-123) for a known packet
+    got = O.write_data_prefix(oracle, 0x1122334455667788, 7, 3, 0, 65536, 0xAABBCCDD)
+    assert got.tobytes().hex() == "000004bc0001001e0000000011223344556677880000000700030000000000010000aabbccdd"
+    for args, want in GOLD["write_data_prefix"]:
+        assert O.write_data_prefix(oracle, *args).tobytes().hex() == want
+    if ref is not None:
+        rng = np.random.default_rng(8)
+        for _ in range(20):
+            args = (int(rng.integers(0, 2**63)), int(rng.integers(0, 2**32)), int(rng.integers(0, 1024)), int(rng.integers(0, 65536)),
+                    int(rng.integers(1, 65537)), int(rng.integers(0, 2**32)))
+            assert (O.write_data_prefix(oracle, *args) == O.write_data_prefix(ref, *args)).all()
