@@ -162,6 +162,42 @@ def cpu_reference_run(goal_text, n_chunks, threads, reps=1):
     return n_chunks * CHUNK / GIB / best, kind, best
 
 
+def cpu_reference_best_case(goal_text, n_chunks, threads):
+    """SURVEY.md §8d(ii) "best-case reference kernel": ONE rs.encode over whole part-major parts
+    (reed_solomon.h:134-155) + mycrc32 per block, parts prepared outside the timed region.  Only with oracle/_ref."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    import ctypes as C
+
+    from tests import _oracle as O
+    import lizardfs_b200 as L
+
+    ref = O.load_ref()
+    if ref is None:
+        return None
+    g = L.SliceType(goal_text)
+    oracle = O.load_oracle()
+    nb = CHUNK // BLOCK
+    pb = (nb + g.k - 1) // g.k
+    n_buf = min(n_chunks, max(threads, 1))
+    bufs = []
+    for c in range(n_buf):
+        parts, _ = O.split_parts(O.fill_chunk(oracle, CHUNK, 12345, c), g.k)
+        parts = [np.ascontiguousarray(p) for p in parts]
+        bufs.append((parts, O.ptr_array(parts), np.zeros(g.m * pb * BLOCK, dtype=np.uint8), np.zeros((g.k + g.m) * pb, dtype=np.uint32)))
+    fn = ref.fn("encode_parts")
+
+    def one(i):
+        parts, ptrs, par, crc = bufs[i % n_buf]
+        assert fn(g.kind, g.k, g.m, ptrs, C.c_uint32(pb), par.ctypes.data_as(C.c_void_p), crc.ctypes.data_as(C.c_void_p)) == 0
+    one(0)
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        t0 = time.perf_counter()
+        list(ex.map(one, range(n_chunks)))
+        dt = time.perf_counter() - t0
+    return n_chunks * CHUNK / GIB / dt
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -372,8 +408,11 @@ def main():
         cores = host_threads()
         n = args.cpu_chunks or max(cores, 8)
         v, kind, secs = cpu_reference_run(args.goal, n, cores)
+        best = cpu_reference_best_case(args.goal, n, cores)
         cpu_baseline = {"value": v, "unit": "GiB/s", "cores": cores, "kind": kind,
-                        "sample": f"{n} x 64 MiB chunks ({secs:.1f} s), reference call pattern, {cores} threads"}
+                        "sample": f"{n} x 64 MiB chunks ({secs:.1f} s), reference call pattern, {cores} threads",
+                        "whole_part_kernel_value": best,
+                        "whole_part_kernel_note": "one rs.encode over whole parts + mycrc32 per block (SURVEY 8d(ii)), parts pre-split outside the timed region"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "GiB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
