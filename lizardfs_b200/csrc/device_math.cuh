@@ -28,9 +28,15 @@ __device__ __forceinline__ uint32_t gf_x2(uint32_t v) {
 // leaving two LOP3 (mask, final 3-input XOR) on the ALU pipe, which is the busy one in the fused kernel
 __device__ __forceinline__ uint32_t gf_x2_add(uint32_t v, uint32_t d) {
 	const uint32_t hi = v & 0x80808080u;
+#ifdef LZ_XTIME_SHALLOW
+	// dependency depth 3 (two parallel masks -> shift | mulhi -> xor3) at the price of one more ALU op
+	const uint32_t lo = v & 0x7F7F7F7Fu;
+	return (lo << 1) ^ __umulhi(hi, 0x3A000000u) ^ d;
+#else
 	uint32_t dbl;
 	asm("{\n\t.reg .u32 t;\n\tmul.lo.u32 t, %1, 2;\n\tmad.lo.u32 %0, %2, 0xFFFFFFFE, t;\n\t}" : "=r"(dbl) : "r"(v), "r"(hi));
 	return dbl ^ __umulhi(hi, 0x3A000000u) ^ d;
+#endif
 }
 
 // One coefficient prepared for the bit-plane product: plane[b] = c * 2^b in GF(2^8), each stored
