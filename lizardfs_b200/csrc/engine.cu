@@ -4,6 +4,7 @@
 // CPU implementation of encode / recover / CRC in this library.  If CUDA is unusable the calls
 // return LZGPU_ERR_NO_DEVICE / LZGPU_ERR_CUDA (or abort() for the void reference signatures).
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cstdarg>
@@ -38,6 +39,14 @@ extern "C" const char *lzgpu_last_error(void) { return t_err; }
 	std::fprintf(stderr, "liblzgpu: FATAL: %s failed (status %d): %s\n", what, rc, t_err);
 	std::abort();
 }
+
+// NVTX range around every batched entry point: the counterpart of the reference's TRACETHIS / LOG_AVG_TILL_END_OF_SCOPE
+// scoped timers on this path (src/devtools/TracePrinter.h:132-146, request_log.h:401-415, e.g. write_executor.cc:96);
+// visible in Nsight Systems / Compute, free when no tool is attached.
+struct NvtxScope {
+	explicit NvtxScope(const char *name) { nvtxRangePushA(name); }
+	~NvtxScope() { nvtxRangePop(); }
+};
 
 // ------------------------------------------------------------------------------------------------
 // context
@@ -304,6 +313,7 @@ static void goal_parity_rows(const lzgpu_goal *g, uint8_t *rows /* m*k */) {
 extern "C" int lzgpu_encode_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t chunk_len,
                                         const void *d_data, size_t chunk_stride, void *d_parity, size_t parity_stride,
                                         void *d_crc, size_t crc_stride, void *stream) {
+	NvtxScope nvtx_scope("lzgpu::encode_chunks_dev");
 	if (!ctx || !d_data || !d_parity || !d_crc) return LZGPU_ERR_ARG;
 	int rc = check_goal(goal);
 	if (rc) return rc;
@@ -363,6 +373,7 @@ extern "C" int lzgpu_encode_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, u
 extern "C" int lzgpu_encode_chunks(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t chunk_len,
                                     const uint8_t *data, size_t chunk_stride, uint8_t *parity, size_t parity_stride,
                                     uint32_t *crc, size_t crc_stride) {
+	NvtxScope nvtx_scope("lzgpu::encode_chunks");
 	if (!ctx || !data || !parity || !crc) return LZGPU_ERR_ARG;
 	int rc = check_goal(goal);
 	if (rc) return rc;
@@ -416,6 +427,7 @@ extern "C" int lzgpu_recover_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, 
                                          const void *const *d_parts, size_t part_stride, const void *const *d_part_crc,
                                          const uint8_t *want, void *const *d_out, void *d_chunk_out, size_t chunk_out_stride,
                                          int64_t *bad, void *stream) {
+	NvtxScope nvtx_scope("lzgpu::recover_chunks_dev");
 	if (!ctx || !d_parts || !want) return LZGPU_ERR_ARG;
 	int rc = check_goal(goal);
 	if (rc) return rc;
@@ -570,6 +582,7 @@ extern "C" int lzgpu_recover_chunks(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint
                                      const uint8_t *const *parts, size_t part_stride, const uint32_t *const *part_crc,
                                      const uint8_t *want, uint8_t *const *out, uint8_t *chunk_out, size_t chunk_out_stride,
                                      int64_t *bad) {
+	NvtxScope nvtx_scope("lzgpu::recover_chunks");
 	if (!ctx || !parts || !want) return LZGPU_ERR_ARG;
 	int rc = check_goal(goal);
 	if (rc) return rc;
@@ -754,6 +767,7 @@ extern "C" int lzgpu_split_chunks(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32
 // ------------------------------------------------------------------------------------------------
 extern "C" int lzgpu_crc_blocks_dev(lzgpu_ctx *ctx, const void *d_data, size_t n_blocks, uint32_t block_len, size_t block_stride,
                                      void *d_crc_out, void *stream) {
+	NvtxScope nvtx_scope("lzgpu::crc_blocks_dev");
 	if (!ctx || !d_data || !d_crc_out) return LZGPU_ERR_ARG;
 	if (block_len == 0 || block_len > LZGPU_BLOCK_SIZE || block_stride < block_len) { lz_set_error("crc_blocks: bad block_len/stride"); return LZGPU_ERR_ARG; }
 	DeviceGuard g(ctx->device);
@@ -767,6 +781,7 @@ extern "C" int lzgpu_crc_blocks_dev(lzgpu_ctx *ctx, const void *d_data, size_t n
 
 extern "C" int lzgpu_crc_blocks(lzgpu_ctx *ctx, const uint8_t *data, size_t n_blocks, uint32_t block_len, size_t block_stride,
                                  uint32_t *crc_out) {
+	NvtxScope nvtx_scope("lzgpu::crc_blocks");
 	if (!ctx || !data || !crc_out) return LZGPU_ERR_ARG;
 	if (block_len == 0 || block_len > LZGPU_BLOCK_SIZE || block_stride < block_len) { lz_set_error("crc_blocks: bad block_len/stride"); return LZGPU_ERR_ARG; }
 	if (n_blocks == 0) return LZGPU_OK;
