@@ -228,7 +228,7 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	// flat mode: contiguous chunks made of whole stripes are one run of n_chunks*pb stripes (small chunks then fill the
 	// G-stripe units instead of leaving most TMA rows out of range)
 	const bool flat = M > 0 && n_chunks > 1 && chunk_stride == static_cast<size_t>(nb) * LZGPU_BLOCK_SIZE && nb % K == 0 &&
-	                  static_cast<uint64_t>(n_chunks) * p.pb < (1ull << 31) && static_cast<uint64_t>(n_chunks) * nb * 4 < (1ull << 32);
+	                  static_cast<uint64_t>(n_chunks) * p.pb < (1ull << 31) && static_cast<uint64_t>(n_chunks) * nb * 4 < (1ull << 31);  // TMA coordinates are int32
 	p.flat = flat ? 1u : 0u;
 	p.flat_magic = (1ull << 40) / p.pb + 1;
 	uint64_t total;
