@@ -101,6 +101,54 @@ def test_encode_and_recover_every_goal_shape(eng, oracle):
         assert (img == data).all(), str(goal)
 
 
+def test_fuzz_encode_recover_against_oracle(eng, oracle):
+    """Seeded fuzz over goal, chunk length (incl. partial last blocks and nb < k), batch size and erasure pattern;
+    exercises flat / per-chunk units, fused and generic routes, CRC verification on and off."""
+    rng = np.random.default_rng(777)
+    for it in range(60):
+        if rng.random() < 0.25:
+            goal = L.SliceType(0, int(rng.integers(2, 10)), 1)
+        else:
+            goal = L.SliceType(1, int(rng.integers(2, 17)), int(rng.integers(1, 6)))
+        k, m = goal.k, goal.m
+        nb = int(rng.integers(1, 4 * k + 3))
+        partial = int(rng.integers(1, BLOCK)) if rng.random() < 0.3 else 0
+        clen = (nb - 1) * BLOCK + (partial if partial else BLOCK)
+        n = int(rng.integers(1, 6))
+        buf = rng.integers(0, 256, size=(n, nb * BLOCK), dtype=np.uint8)
+        parity, crc = eng.encode_chunks(goal, buf, chunk_len=clen)
+        for c in range(n):
+            p_ref, c_ref = oracle.encode_chunk(goal.kind, k, m, buf[c, :clen])
+            assert (parity[c] == p_ref).all(), (it, str(goal), nb, clen, n)
+            assert (crc[c] == c_ref).all(), (it, str(goal), nb, clen, n)
+        # degraded read of the zero-extended chunks with a random erasure pattern (any parts, up to m)
+        padded = buf.copy()
+        padded[:, clen:] = 0
+        parts = all_parts(padded, parity, k)
+        pb = parts[0].shape[1] // BLOCK
+        lost = sorted(rng.choice(k + m, size=int(rng.integers(1, m + 1)), replace=False).tolist())
+        avail = [None if i in lost else parts[i] for i in range(k + m)]
+        want = [1 if i in lost else 0 for i in range(k + m)]
+        pcrc = None
+        if rng.random() < 0.5:
+            pcrc = []
+            for i in range(k + m):
+                if i in lost:
+                    pcrc.append(None)
+                elif i < k:
+                    col = np.full((n, pb), 0xD7978EEB, dtype=np.uint32)
+                    have = crc[:, i:nb:k]
+                    col[:, : have.shape[1]] = have
+                    pcrc.append(col)
+                else:
+                    pcrc.append(np.ascontiguousarray(crc[:, nb + (i - k) * pb: nb + (i - k + 1) * pb]))
+        out, img = eng.recover_chunks(goal, nb, avail, part_crc=pcrc, want=want, chunk_image=bool(rng.random() < 0.5))
+        for i in lost:
+            assert (out[i] == parts[i]).all(), (it, str(goal), lost, i)
+        if img is not None:
+            assert (img == padded).all(), (it, str(goal), lost)
+
+
 def test_encode_partial_last_block(eng, oracle):
     goal = L.SliceType("ec(3,2)")
     clen = 7 * BLOCK + 12345
