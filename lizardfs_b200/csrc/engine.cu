@@ -819,28 +819,35 @@ static int verify_common(lzgpu_ctx *ctx, const uint8_t *h_data, size_t n_blocks,
 	DeviceGuard g(ctx->device);
 	cudaStream_t st = ctx->stream;
 	const size_t dstride = (static_cast<size_t>(block_len) + 15) & ~size_t(15);
+	// bounded staging: tiles of at most 1 GiB of block data, processed in order so the FIRST mismatch is reported
+	const size_t per_tile = std::max<size_t>(1, (size_t(1) << 30) / dstride);
+	const size_t tile_blocks = std::min(per_tile, n_blocks);
 	void *d_in, *d_c, *d_s;
 	int rc;
-	if ((rc = lz_scratch(ctx, kScratchIn0, n_blocks * dstride, &d_in))) return rc;
-	if ((rc = lz_scratch(ctx, kScratchCrc0, n_blocks * 4, &d_c))) return rc;
-	if ((rc = lz_scratch(ctx, kScratchCrc0 + 1, n_blocks * 4, &d_s))) return rc;
-	CUDA_TRY(cudaMemcpy2DAsync(d_in, dstride, h_data + h_offset, h_stride, block_len, n_blocks, cudaMemcpyHostToDevice, st));
-	CUDA_TRY(cudaMemcpy2DAsync(d_s, 4, h_stored, stored_stride_bytes, 4, n_blocks, cudaMemcpyHostToDevice, st));
+	if ((rc = lz_scratch(ctx, kScratchIn0, tile_blocks * dstride, &d_in))) return rc;
+	if ((rc = lz_scratch(ctx, kScratchCrc0, tile_blocks * 4, &d_c))) return rc;
+	if ((rc = lz_scratch(ctx, kScratchCrc0 + 1, tile_blocks * 4, &d_s))) return rc;
 	const unsigned long long init = ~0ull;
-	CUDA_TRY(cudaMemcpyAsync(ctx->d_first_bad, &init, sizeof(init), cudaMemcpyHostToDevice, st));
-	if ((rc = lzgpu_crc_blocks_dev(ctx, d_in, n_blocks, block_len, dstride, d_c, st))) return rc;
-	crc_compare_kernel<<<grid_for(ctx, n_blocks, 256, 4), 256, 0, st>>>(static_cast<const uint32_t *>(d_c), static_cast<const uint32_t *>(d_s),
-	                                                                   n_blocks, lz::crc_of_zeros(block_len), sparse_rule, big_endian,
-	                                                                   ctx->d_first_bad);
-	CUDA_TRY(cudaGetLastError());
-	ctx->stats.kernel_launches++;
-	CUDA_TRY(cudaMemcpyAsync(ctx->h_first_bad, ctx->d_first_bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-	CUDA_TRY(cudaStreamSynchronize(st));
-	ctx->stats.bytes_h2d += n_blocks * (block_len + 4ull);
-	if (ctx->h_first_bad[0] != ~0ull) {
-		if (first_bad) *first_bad = static_cast<int64_t>(ctx->h_first_bad[0]);
-		lz_set_error("CRC mismatch in block %llu", ctx->h_first_bad[0]);
-		return LZGPU_ERR_CRC;
+	for (size_t b0 = 0; b0 < n_blocks; b0 += tile_blocks) {
+		const size_t n = std::min(tile_blocks, n_blocks - b0);
+		CUDA_TRY(cudaMemcpy2DAsync(d_in, dstride, h_data + h_offset + b0 * h_stride, h_stride, block_len, n, cudaMemcpyHostToDevice, st));
+		CUDA_TRY(cudaMemcpy2DAsync(d_s, 4, reinterpret_cast<const uint8_t *>(h_stored) + b0 * stored_stride_bytes, stored_stride_bytes, 4, n,
+		                           cudaMemcpyHostToDevice, st));
+		CUDA_TRY(cudaMemcpyAsync(ctx->d_first_bad, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+		if ((rc = lzgpu_crc_blocks_dev(ctx, d_in, n, block_len, dstride, d_c, st))) return rc;
+		crc_compare_kernel<<<grid_for(ctx, n, 256, 4), 256, 0, st>>>(static_cast<const uint32_t *>(d_c), static_cast<const uint32_t *>(d_s), n,
+		                                                            lz::crc_of_zeros(block_len), sparse_rule, big_endian, ctx->d_first_bad);
+		CUDA_TRY(cudaGetLastError());
+		ctx->stats.kernel_launches++;
+		CUDA_TRY(cudaMemcpyAsync(ctx->h_first_bad, ctx->d_first_bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+		ctx->stats.bytes_h2d += n * (block_len + 4ull);
+		if (ctx->h_first_bad[0] != ~0ull) {
+			const unsigned long long bad = b0 + ctx->h_first_bad[0];
+			if (first_bad) *first_bad = static_cast<int64_t>(bad);
+			lz_set_error("CRC mismatch in block %llu", bad);
+			return LZGPU_ERR_CRC;
+		}
 	}
 	return LZGPU_OK;
 }
