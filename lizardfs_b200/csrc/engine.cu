@@ -593,58 +593,63 @@ extern "C" int lzgpu_recover_chunks(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint
 	const uint32_t pb = (nb + k - 1) / k;
 	const size_t part_bytes = static_cast<size_t>(pb) * B;
 	if (part_stride < part_bytes) { lz_set_error("recover: part_stride too small"); return LZGPU_ERR_ARG; }
+	if (chunk_out && chunk_out_stride < static_cast<size_t>(nb) * B) { lz_set_error("recover: chunk_out_stride too small"); return LZGPU_ERR_ARG; }
 	std::lock_guard<std::mutex> lk(ctx->mu);
 	DeviceGuard g(ctx->device);
 	cudaStream_t st = ctx->stream;
-	// stage every supplied part (device layout: dense, stride = part_bytes)
-	const size_t dev_part = static_cast<size_t>(n_chunks) * part_bytes;
-	const size_t dev_crc = static_cast<size_t>(n_chunks) * pb * 4;
+	// Chunks are staged in tiles of about 1 GiB of part data (device layout: dense, stride = part_bytes); tiles run in order,
+	// so the first CRC mismatch of the whole batch is the one reported.
+	const uint32_t tile = static_cast<uint32_t>(std::max<size_t>(1, std::min<size_t>(n_chunks, (size_t(1) << 30) / (part_bytes * n))));
+	const size_t dev_part = static_cast<size_t>(tile) * part_bytes;
+	const size_t dev_crc = static_cast<size_t>(tile) * pb * 4;
 	void *d_all = nullptr, *d_crc_all = nullptr, *d_img = nullptr;
 	if ((rc = lz_scratch(ctx, kScratchIn0, dev_part * n, &d_all))) return rc;
 	if ((rc = lz_scratch(ctx, kScratchCrc0, dev_crc * n, &d_crc_all))) return rc;
-	std::vector<const void *> dp(n, nullptr), dc(n, nullptr);
-	std::vector<void *> dout(n, nullptr);
-	bool any_crc = false;
-	for (int i = 0; i < n; ++i) {
-		uint8_t *slot = static_cast<uint8_t *>(d_all) + dev_part * i;
-		if (parts[i]) {
-			CUDA_TRY(cudaMemcpy2DAsync(slot, part_bytes, parts[i], part_stride, part_bytes, n_chunks, cudaMemcpyHostToDevice, st));
-			ctx->stats.bytes_h2d += dev_part;
-			dp[i] = slot;
-			if (part_crc && part_crc[i]) {
-				uint8_t *cs = static_cast<uint8_t *>(d_crc_all) + dev_crc * i;
-				CUDA_TRY(cudaMemcpyAsync(cs, part_crc[i], dev_crc, cudaMemcpyHostToDevice, st));
-				dc[i] = cs;
-				any_crc = true;
+	if (chunk_out && (rc = lz_scratch(ctx, kScratchPar0, static_cast<size_t>(tile) * nb * B, &d_img))) return rc;
+	for (uint32_t c0 = 0; c0 < n_chunks; c0 += tile) {
+		const uint32_t nc = std::min(tile, n_chunks - c0);
+		std::vector<const void *> dp(n, nullptr), dc(n, nullptr);
+		std::vector<void *> dout(n, nullptr);
+		bool any_crc = false;
+		for (int i = 0; i < n; ++i) {
+			uint8_t *slot = static_cast<uint8_t *>(d_all) + dev_part * i;
+			if (parts[i]) {
+				CUDA_TRY(cudaMemcpy2DAsync(slot, part_bytes, parts[i] + static_cast<size_t>(c0) * part_stride, part_stride, part_bytes, nc,
+				                           cudaMemcpyHostToDevice, st));
+				ctx->stats.bytes_h2d += static_cast<uint64_t>(nc) * part_bytes;
+				dp[i] = slot;
+				if (part_crc && part_crc[i]) {
+					uint8_t *cs = static_cast<uint8_t *>(d_crc_all) + dev_crc * i;
+					CUDA_TRY(cudaMemcpyAsync(cs, part_crc[i] + static_cast<size_t>(c0) * pb, static_cast<size_t>(nc) * pb * 4, cudaMemcpyHostToDevice, st));
+					dc[i] = cs;
+					any_crc = true;
+				}
+			} else if ((want[i] && out && out[i]) || (chunk_out && i < k)) {
+				dout[i] = slot;
 			}
-		} else if ((want[i] && out && out[i]) || (chunk_out && i < k)) {
-			dout[i] = slot;
 		}
-	}
-	if (chunk_out) {
-		if (chunk_out_stride < static_cast<size_t>(nb) * B) { lz_set_error("recover: chunk_out_stride too small"); return LZGPU_ERR_ARG; }
-		if ((rc = lz_scratch(ctx, kScratchPar0, static_cast<size_t>(n_chunks) * nb * B, &d_img))) return rc;
-	}
-	int64_t bad_local[3] = {-1, -1, -1};
-	rc = lzgpu_recover_chunks_dev(ctx, goal, n_chunks, nb, dp.data(), part_bytes, any_crc ? dc.data() : nullptr, want, dout.data(), d_img,
-	                              static_cast<size_t>(nb) * B, bad_local, st);
-	if (rc) {
-		if (bad) { bad[0] = bad_local[0]; bad[1] = bad_local[1]; bad[2] = bad_local[2]; }
-		cudaStreamSynchronize(st);
-		return rc;
-	}
-	for (int i = 0; i < n; ++i) {
-		if (dout[i] && out && out[i] && want[i] && !parts[i]) {
-			CUDA_TRY(cudaMemcpy2DAsync(out[i], part_stride, dout[i], part_bytes, part_bytes, n_chunks, cudaMemcpyDeviceToHost, st));
-			ctx->stats.bytes_d2h += dev_part;
+		int64_t bad_local[3] = {-1, -1, -1};
+		rc = lzgpu_recover_chunks_dev(ctx, goal, nc, nb, dp.data(), part_bytes, any_crc ? dc.data() : nullptr, want, dout.data(), d_img,
+		                              static_cast<size_t>(nb) * B, bad_local, st);
+		if (rc) {
+			if (bad) { bad[0] = bad_local[0] < 0 ? bad_local[0] : bad_local[0] + c0; bad[1] = bad_local[1]; bad[2] = bad_local[2]; }
+			cudaStreamSynchronize(st);
+			return rc;
 		}
+		for (int i = 0; i < n; ++i) {
+			if (dout[i] && out && out[i] && want[i] && !parts[i]) {
+				CUDA_TRY(cudaMemcpy2DAsync(out[i] + static_cast<size_t>(c0) * part_stride, part_stride, dout[i], part_bytes, part_bytes, nc,
+				                           cudaMemcpyDeviceToHost, st));
+				ctx->stats.bytes_d2h += static_cast<uint64_t>(nc) * part_bytes;
+			}
+		}
+		if (chunk_out) {
+			CUDA_TRY(cudaMemcpy2DAsync(chunk_out + static_cast<size_t>(c0) * chunk_out_stride, chunk_out_stride, d_img, static_cast<size_t>(nb) * B,
+			                           static_cast<size_t>(nb) * B, nc, cudaMemcpyDeviceToHost, st));
+			ctx->stats.bytes_d2h += static_cast<uint64_t>(nc) * nb * B;
+		}
+		CUDA_TRY(cudaStreamSynchronize(st));
 	}
-	if (chunk_out) {
-		CUDA_TRY(cudaMemcpy2DAsync(chunk_out, chunk_out_stride, d_img, static_cast<size_t>(nb) * B, static_cast<size_t>(nb) * B, n_chunks,
-		                           cudaMemcpyDeviceToHost, st));
-		ctx->stats.bytes_d2h += static_cast<uint64_t>(n_chunks) * nb * B;
-	}
-	CUDA_TRY(cudaStreamSynchronize(st));
 	return LZGPU_OK;
 }
 

@@ -187,7 +187,7 @@ def test_full_size_batch_roundtrip_with_verification(eng):
     """BASELINE configs[2]/[3] at full chunk size: encode a batch of 64 MiB chunks, lose two data parts, recover with the
     stored CRCs verified and the chunk-order image rebuilt; the round trip must reproduce every byte."""
     goal = L.SliceType("ec(8,2)")
-    n, nb, pb = 4, 1024, 128
+    n, nb, pb = 14, 1024, 128          # 14 chunks = two staging tiles of the host recover path (12 + 2)
     data = rnd((n, nb * BLOCK), 77)
     parity, crc = eng.encode_chunks(goal, data)
     blocks = data.reshape(n, pb, 8, BLOCK)
@@ -204,10 +204,10 @@ def test_full_size_batch_roundtrip_with_verification(eng):
     assert (img == data).all()
     # and a corrupted stored CRC deep inside the batch is located exactly
     acrc[9] = acrc[9].copy()
-    acrc[9][3, 100] ^= 0x8000
+    acrc[9][13, 100] ^= 0x8000
     with pytest.raises(L.ChunkCrcError) as ei:
         eng.recover_chunks(goal, nb, avail, part_crc=acrc)
-    assert ei.value.where == (3, 9, 100)
+    assert ei.value.where == (13, 9, 100)
 
 
 def test_linearity_properties_full_batch(eng):
