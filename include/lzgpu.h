@@ -52,6 +52,7 @@ extern "C" {
 #define LZGPU_ERR_CRC (-4)
 #define LZGPU_ERR_TOO_FEW_PARTS (-5)
 #define LZGPU_ERR_NO_DEVICE (-6)
+#define LZGPU_ERR_DAMAGED (-7) /* a stored block fails its CRC during a read-modify-write (hddspacemgr.cc:1962-1971) */
 
 /* ---------------------------------------------------------------------------------------------
  * Goals (src/common/goal.h:108-120, slice_traits.h:96-211).
@@ -59,14 +60,17 @@ extern "C" {
  * Part numbering in THIS API is uniform for both kinds: data 0..k-1, then parity k..k+m-1.
  * (The reference numbers xor parts parity = 0, data = 1..N; lzgpu_ref_part_index converts.)
  * ------------------------------------------------------------------------------------------- */
+#define LZGPU_KIND_XOR 0
+#define LZGPU_KIND_EC 1
+#define LZGPU_KIND_STD 2 /* standard (one full copy; k = 1, m = 0): accepted by lzgpu_convert_chunks* only */
 typedef struct lzgpu_goal {
-	int kind; /* 0 xor, 1 ec */
+	int kind; /* LZGPU_KIND_* */
 	int k;    /* data parts: xor 2..9, ec 2..32 */
 	int m;    /* parity parts: xor 1, ec 1..32 */
 } lzgpu_goal;
 
-int lzgpu_goal_parse(const char *text, lzgpu_goal *out); /* "xor3", "$xor3", "ec(8,2)", "$ec(8,2)" (goal_config_loader.cc:228-245) */
-int lzgpu_goal_valid(const lzgpu_goal *g);                /* 1 / 0 */
+int lzgpu_goal_parse(const char *text, lzgpu_goal *out); /* "xor3", "$xor3", "ec(8,2)", "$ec(8,2)", "std" / "_" (goal_config_loader.cc:228-245) */
+int lzgpu_goal_valid(const lzgpu_goal *g);                /* 1 for an xor/ec goal this engine encodes, else 0 (standard included) */
 int lzgpu_goal_slice_type(const lzgpu_goal *g);           /* Goal::Slice::Type value: xorN -> 2+(N-2), ec -> 10+32(k-2)+(m-1) */
 int lzgpu_goal_from_slice_type(int slice_type, lzgpu_goal *out);
 int lzgpu_ref_part_index(const lzgpu_goal *g, int part);  /* this API's part index -> reference slice part number */
@@ -175,6 +179,29 @@ int lzgpu_split_chunks(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks
 int lzgpu_split_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb,
                            const void *d_data, size_t chunk_stride, void *const *d_parts, size_t part_stride, void *stream);
 
+/* Replication / slice-type conversion: rebuild parts of slice type `dst` from the available parts of
+ * slice type `src`, one call for a batch of chunks.  Replaces, per part, SliceRecoveryPlanner's three methods
+ * (src/chunkserver/slice_recovery_planner.h:87-204) together with the post-processing they schedule — read or
+ * ReedSolomon/xor rebuild inside one slice type (slice_read_planner.cc, ec_read_plan.h:113-146, xor_read_plan.h:77-126);
+ * chunk data via ChunkReadPlanner then BlockConverter (:41-57) for a data part, or XorReadPlan::RecoverParity
+ * (xor_read_plan.h:39-62) / ECReadPlan::RecoverParity (ec_read_plan.h:38-76) for a parity part — and the per-block
+ * mycrc32 loop of ChunkReplicator::replicate (src/chunkserver/chunk_replicator.cc:186-192).
+ *   src, parts, part_stride, part_crc   as in lzgpu_recover_chunks (verification included); a standard source
+ *                                       ({LZGPU_KIND_STD,1,0}) has the single part 0 = the chunk itself.
+ *   want[i], out[i]  (i < dst.k+dst.m)  requested parts of the destination slice: pb' = ceil(nb/dst.k) blocks per chunk,
+ *                                       chunk c at out[i] + c*out_stride, short data parts zero-padded.  A standard
+ *                                       destination has the single part 0 = the chunk-order image (nb blocks).
+ *   out_crc[i]       optional           mycrc32 of every block of out[i]: chunk c at out_crc[i] + c*pb'.
+ * src == dst rebuilds/copies inside the slice (out_stride must equal part_stride for the _dev variant). */
+int lzgpu_convert_chunks(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_goal *dst, uint32_t n_chunks, uint32_t nb,
+                         const uint8_t *const *parts, size_t part_stride, const uint32_t *const *part_crc,
+                         const uint8_t *want, uint8_t *const *out, size_t out_stride, uint32_t *const *out_crc,
+                         int64_t *bad);
+int lzgpu_convert_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_goal *dst, uint32_t n_chunks, uint32_t nb,
+                             const void *const *d_parts, size_t part_stride, const void *const *d_part_crc,
+                             const uint8_t *want, void *const *d_out, size_t out_stride, void *const *d_out_crc,
+                             int64_t *bad /* host; as in lzgpu_recover_chunks_dev */, void *stream);
+
 /* CRC of n_blocks consecutive blocks of block_len bytes (block_len <= 65536, any value >= 1).
  * crc_out[i] = mycrc32(0, data + i*block_stride, block_len). */
 int lzgpu_crc_blocks(lzgpu_ctx *ctx, const uint8_t *data, size_t n_blocks, uint32_t block_len,
@@ -183,12 +210,39 @@ int lzgpu_crc_blocks_dev(lzgpu_ctx *ctx, const void *d_data, size_t n_blocks, ui
                          size_t block_stride, void *d_crc_out, void *stream);
 /* Scrub (hdd_int_test, hddspacemgr.cc:2174-2190): compare against stored CRCs; returns LZGPU_OK or
  * LZGPU_ERR_CRC with *first_bad = index of the first mismatching block.  A stored CRC of 0 on an
- * all-zero block is accepted when sparse_rule != 0 (recompute_crc_if_block_empty, crc.cc:235-243). */
+ * all-zero block is accepted when sparse_rule != 0 (recompute_crc_if_block_empty, crc.cc:235-243): the block bytes
+ * are checked, a non-zero block whose CRC merely equals that of zeros is still a mismatch, as in the reference. */
 int lzgpu_verify_blocks(lzgpu_ctx *ctx, const uint8_t *data, size_t n_blocks, uint32_t block_len,
                         size_t block_stride, const uint32_t *stored_crc, int sparse_rule, int64_t *first_bad);
 /* On-disk chunk-file scrub: records of 4-byte big-endian CRC + 65536 data bytes
  * (src/chunkserver/chunk.h:40, chunk.cc:195-209). */
 int lzgpu_verify_interleaved(lzgpu_ctx *ctx, const uint8_t *records, size_t n_blocks, int64_t *first_bad);
+/* MooseFS-format chunk file (src/chunkserver/chunk.cc:126-190): 1 KiB signature, big-endian CRC table, data blocks from
+ * lzgpu_moosefs_header_size(data_parts) (5120 for a standard chunk, 4096 for xor/ec parts; data_parts = 1 / N / k).
+ * No sparse rule on this format (hddspacemgr.cc:1746-1764). */
+size_t lzgpu_moosefs_header_size(int data_parts);
+int lzgpu_verify_moosefs(lzgpu_ctx *ctx, int data_parts, const uint8_t *file_image, size_t n_blocks, int64_t *first_bad);
+
+/* Chunkserver block writes, batched (hdd_write, src/chunkserver/hddspacemgr.cc:1898-2008).
+ * Per request, exactly the reference's checks and CRC arithmetic: the payload must match the CRC of its packet
+ * (:1916-1918, LZGPU_ERR_CRC); a whole-block write stores the packet CRC (:1920-1940); a partial write verifies the stored
+ * block through mycrc32_combine(pre, under, post) == stored (:1948-1971, LZGPU_ERR_DAMAGED; with sparse_rule != 0 a stored
+ * CRC of 0 on an all-zero block counts as valid, the interleaved-format reader's rule, :1779) and stores
+ * mycrc32_combine(pre, crc, post); a block beyond the end of the file (exists = 0) is created as zeros (:1976-1993).
+ * blocks[b] (64 KiB each) and stored_crc[b] are updated in place for the requests that succeed; every request gets its
+ * status.  At most one request per block and call.  Returns LZGPU_OK or the status of the first failed request. */
+typedef struct lzgpu_block_write {
+	uint32_t block;       /* index into blocks / stored_crc */
+	uint32_t offset, size;/* byte range inside the block */
+	uint32_t crc;         /* CRC of the payload as carried by LIZ_CLTOCS_WRITE_DATA (cltocs.h:116-137) */
+	uint64_t payload_off; /* where this request's `size` bytes start inside `payload` */
+	uint32_t exists;      /* 0: blocknum >= chunk->blocks */
+	int32_t status;       /* out */
+} lzgpu_block_write;
+int lzgpu_write_blocks(lzgpu_ctx *ctx, uint8_t *blocks, uint32_t *stored_crc, size_t n_blocks, const uint8_t *payload,
+                       size_t payload_bytes, lzgpu_block_write *writes, uint32_t n_writes, int sparse_rule);
+int lzgpu_write_blocks_dev(lzgpu_ctx *ctx, void *d_blocks, void *d_stored_crc, const void *d_payload, void *d_writes,
+                           uint32_t n_writes, int sparse_rule, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Reference-shaped single-call API (runs on the default context; every call is H2D + kernel + D2H).

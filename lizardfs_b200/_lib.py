@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblzgpu.so")
 
 OK = 0
-ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_CRC, ERR_TOO_FEW_PARTS, ERR_NO_DEVICE = -1, -2, -3, -4, -5, -6
+ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_CRC, ERR_TOO_FEW_PARTS, ERR_NO_DEVICE, ERR_DAMAGED = -1, -2, -3, -4, -5, -6, -7
 BLOCK_SIZE = 65536
 BLOCKS_IN_CHUNK = 1024
 CHUNK_SIZE = BLOCK_SIZE * BLOCKS_IN_CHUNK
@@ -24,6 +24,11 @@ class LzGoal(C.Structure):
 class LzStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("bytes_h2d", C.c_uint64), ("bytes_d2h", C.c_uint64),
                 ("chunks_encoded", C.c_uint64), ("chunks_recovered", C.c_uint64), ("blocks_crc", C.c_uint64)]
+
+
+class LzBlockWrite(C.Structure):
+    _fields_ = [("block", C.c_uint32), ("offset", C.c_uint32), ("size", C.c_uint32), ("crc", C.c_uint32),
+                ("payload_off", C.c_uint64), ("exists", C.c_uint32), ("status", C.c_int32)]
 
 
 _vp, _u32, _u64, _sz, _int = C.c_void_p, C.c_uint32, C.c_uint64, C.c_size_t, C.c_int
@@ -60,6 +65,12 @@ SIGNATURES = {
     "lzgpu_crc_blocks_dev": (_int, [_vp, _vp, _sz, _u32, _sz, _vp, _vp]),
     "lzgpu_verify_blocks": (_int, [_vp, _vp, _sz, _u32, _sz, _vp, _int, _vp]),
     "lzgpu_verify_interleaved": (_int, [_vp, _vp, _sz, _vp]),
+    "lzgpu_write_blocks": (_int, [_vp, _vp, _vp, _sz, _vp, _sz, _vp, _u32, _int]),
+    "lzgpu_write_blocks_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _u32, _int, _vp]),
+    "lzgpu_convert_chunks": (_int, [_vp, _goalp, _goalp, _u32, _u32, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "lzgpu_convert_chunks_dev": (_int, [_vp, _goalp, _goalp, _u32, _u32, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "lzgpu_moosefs_header_size": (_sz, [_int]),
+    "lzgpu_verify_moosefs": (_int, [_vp, _int, _vp, _sz, _vp]),
     "lzgpu_rs_encode": (_int, [_int, _int, _vp, _vp, _sz]),
     "lzgpu_rs_recover": (_int, [_int, _int, _vp, _vp, _vp, _sz]),
     "lzgpu_rs_generator": (_int, [_int, _int, _vp]),

@@ -654,6 +654,214 @@ extern "C" int lzgpu_recover_chunks(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint
 }
 
 // ------------------------------------------------------------------------------------------------
+// replication / slice-type conversion (SliceRecoveryPlanner, src/chunkserver/slice_recovery_planner.h:87-204)
+// ------------------------------------------------------------------------------------------------
+static bool goal_is_std(const lzgpu_goal *g) { return g && g->kind == LZGPU_KIND_STD && g->k == 1 && g->m == 0; }
+static int check_goal_or_std(const lzgpu_goal *g) { return goal_is_std(g) ? LZGPU_OK : check_goal(g); }
+static bool same_goal(const lzgpu_goal *a, const lzgpu_goal *b) { return a->kind == b->kind && a->k == b->k && a->m == b->m; }
+
+static int crc_of_parts(lzgpu_ctx *ctx, const void *d_part, uint32_t n_chunks, uint32_t pb, size_t stride, void *d_out, cudaStream_t st) {
+	const unsigned long long nblk = static_cast<unsigned long long>(n_chunks) * pb;
+	int rc = lz_fused_crc(ctx, d_part, nblk, pb, stride, d_out, pb, st);
+	if (rc == LZGPU_NOT_HANDLED) rc = lz_crc_blocks(ctx, d_part, nblk, pb, stride, LZGPU_BLOCK_SIZE, LZGPU_BLOCK_SIZE, d_out, pb, st);
+	return rc;
+}
+
+extern "C" int lzgpu_convert_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_goal *dst, uint32_t n_chunks, uint32_t nb,
+                                         const void *const *d_parts, size_t part_stride, const void *const *d_part_crc,
+                                         const uint8_t *want, void *const *d_out, size_t out_stride, void *const *d_out_crc,
+                                         int64_t *bad, void *stream) {
+	NvtxScope nvtx_scope("lzgpu::convert_chunks_dev");
+	if (!ctx || !src || !dst || !d_parts || !want || !d_out) return LZGPU_ERR_ARG;
+	int rc;
+	if ((rc = check_goal_or_std(src)) || (rc = check_goal_or_std(dst))) return rc;
+	if (nb == 0 || nb > LZGPU_BLOCKS_IN_CHUNK) { lz_set_error("nb out of range"); return LZGPU_ERR_ARG; }
+	if (n_chunks == 0) return LZGPU_OK;
+	const uint32_t B = LZGPU_BLOCK_SIZE;
+	const int ks = src->k, kd = dst->k, nd = dst->k + dst->m;
+	const uint32_t pbs = (nb + ks - 1) / ks, pbd = (nb + kd - 1) / kd;
+	if (part_stride < static_cast<size_t>(pbs) * B || (part_stride & 15) || out_stride < static_cast<size_t>(pbd) * B || (out_stride & 15)) {
+		lz_set_error("convert: strides too small or not multiples of 16");
+		return LZGPU_ERR_ARG;
+	}
+	for (int i = 0; i < nd; ++i)
+		if (want[i] && !d_out[i]) { lz_set_error("convert: wanted part %d has no output buffer", i); return LZGPU_ERR_ARG; }
+	DeviceGuard g(ctx->device);
+	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+	if (bad) bad[0] = bad[1] = bad[2] = -1;
+
+	if (same_goal(src, dst) && !goal_is_std(src)) {
+		// kReadDataPart (slice_recovery_planner.h:98-101): the part is read, or rebuilt from k parts of the same slice
+		uint8_t need[LZGPU_MAX_PARTS] = {0};
+		bool any = false;
+		for (int i = 0; i < nd; ++i) {
+			if (!want[i]) continue;
+			if (d_parts[i]) {
+				if (d_parts[i] != d_out[i])
+					CUDA_TRY(cudaMemcpy2DAsync(d_out[i], out_stride, d_parts[i], part_stride, static_cast<size_t>(pbd) * B, n_chunks, cudaMemcpyDeviceToDevice, st));
+			} else {
+				need[i] = 1;
+				any = true;
+			}
+		}
+		if (any || d_part_crc) {
+			if (out_stride != part_stride) { lz_set_error("convert: same-slice rebuild needs out_stride == part_stride"); return LZGPU_ERR_ARG; }
+			if ((rc = lzgpu_recover_chunks_dev(ctx, src, n_chunks, nb, d_parts, part_stride, d_part_crc, need, d_out, nullptr, 0, bad, st))) return rc;
+		}
+	} else {
+		// kRecoverDataPart / kRecoverParityPart (:102-119): chunk data first (ChunkReadPlanner), then BlockConverter or RecoverParity
+		const uint8_t *image;
+		size_t image_stride;
+		void *direct_image = (goal_is_std(dst) && want[0]) ? d_out[0] : nullptr;  // a standard destination IS the chunk image
+		if (goal_is_std(src)) {
+			if (!d_parts[0]) { lz_set_error("convert: the standard chunk is not available"); return LZGPU_ERR_TOO_FEW_PARTS; }
+			image = static_cast<const uint8_t *>(d_parts[0]);
+			image_stride = part_stride;
+			if (d_part_crc && d_part_crc[0]) {
+				void *d_tmp;
+				const unsigned long long nblk = static_cast<unsigned long long>(n_chunks) * nb;
+				const unsigned long long none = ~0ull;
+				if ((rc = lz_scratch(ctx, kScratchTmpCrc, nblk * 4, &d_tmp))) return rc;
+				CUDA_TRY(cudaMemcpyAsync(ctx->d_first_bad, &none, sizeof(none), cudaMemcpyHostToDevice, st));
+				if ((rc = crc_of_parts(ctx, image, n_chunks, nb, image_stride, d_tmp, st))) return rc;
+				crc_compare_kernel<<<grid_for(ctx, nblk, 256, 4), 256, 0, st>>>(static_cast<const uint32_t *>(d_tmp), static_cast<const uint32_t *>(d_part_crc[0]),
+				                                                              nblk, kCrcZeroBlock64K, 0, 0, ctx->d_first_bad);
+				CUDA_TRY(cudaGetLastError());
+				ctx->stats.kernel_launches++;
+				if (bad) {
+					CUDA_TRY(cudaMemcpyAsync(ctx->h_first_bad, ctx->d_first_bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+					CUDA_TRY(cudaStreamSynchronize(st));
+					if (ctx->h_first_bad[0] != ~0ull) {
+						bad[0] = static_cast<int64_t>(ctx->h_first_bad[0] / nb); bad[1] = 0; bad[2] = static_cast<int64_t>(ctx->h_first_bad[0] % nb);
+						lz_set_error("CRC mismatch: chunk %lld part 0 block %lld", (long long)bad[0], (long long)bad[2]);
+						return LZGPU_ERR_CRC;
+					}
+				}
+			}
+			if (direct_image && direct_image != image)
+				CUDA_TRY(cudaMemcpy2DAsync(direct_image, out_stride, image, image_stride, static_cast<size_t>(nb) * B, n_chunks, cudaMemcpyDeviceToDevice, st));
+		} else {
+			void *d_img = direct_image;
+			image_stride = direct_image ? out_stride : static_cast<size_t>(nb) * B;
+			if (!d_img && (rc = lz_scratch(ctx, kScratchConvImage, static_cast<size_t>(n_chunks) * image_stride, &d_img))) return rc;
+			const uint8_t none_wanted[LZGPU_MAX_PARTS] = {0};
+			if ((rc = lzgpu_recover_chunks_dev(ctx, src, n_chunks, nb, d_parts, part_stride, d_part_crc, none_wanted, nullptr, d_img, image_stride, bad, st)))
+				return rc;
+			image = static_cast<const uint8_t *>(d_img);
+		}
+		if (!goal_is_std(dst)) {
+			bool data_wanted = false, parity_wanted = false;
+			void *dp[LZGPU_MAX_DATA] = {nullptr};
+			for (int i = 0; i < nd; ++i) {
+				if (!want[i]) continue;
+				if (i < kd) { dp[i] = d_out[i]; data_wanted = true; }
+				else parity_wanted = true;
+			}
+			// data part j, block s = chunk block s*k + j (SliceRecoveryPlanner::BlockConverter, :41-57)
+			if (data_wanted && (rc = lzgpu_split_chunks_dev(ctx, dst, n_chunks, nb, image, image_stride, dp, out_stride, st))) return rc;
+			// parity parts = XorReadPlan::RecoverParity / ECReadPlan::RecoverParity over the chunk data (xor_read_plan.h:39-62, ec_read_plan.h:38-76)
+			if (parity_wanted) {
+				void *d_par, *d_crc;
+				const size_t par_stride = static_cast<size_t>(dst->m) * pbd * B, crc_stride = (nb + static_cast<size_t>(dst->m) * pbd + 3) & ~size_t(3);
+				if ((rc = lz_scratch(ctx, kScratchConvPar, n_chunks * par_stride, &d_par))) return rc;
+				if ((rc = lz_scratch(ctx, kScratchConvCrc, n_chunks * crc_stride * 4, &d_crc))) return rc;
+				if ((rc = lzgpu_encode_chunks_dev(ctx, dst, n_chunks, nb * B, image, image_stride, d_par, par_stride, d_crc, crc_stride, st))) return rc;
+				for (int r = 0; r < dst->m; ++r)
+					if (want[kd + r])
+						CUDA_TRY(cudaMemcpy2DAsync(d_out[kd + r], out_stride, static_cast<uint8_t *>(d_par) + static_cast<size_t>(r) * pbd * B, par_stride,
+						                           static_cast<size_t>(pbd) * B, n_chunks, cudaMemcpyDeviceToDevice, st));
+			}
+		}
+	}
+	// ChunkReplicator::replicate computes mycrc32 of every rebuilt block (chunk_replicator.cc:186-192)
+	if (d_out_crc)
+		for (int i = 0; i < nd; ++i)
+			if (want[i] && d_out_crc[i] && (rc = crc_of_parts(ctx, d_out[i], n_chunks, pbd, out_stride, d_out_crc[i], st))) return rc;
+	return LZGPU_OK;
+}
+
+extern "C" int lzgpu_convert_chunks(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_goal *dst, uint32_t n_chunks, uint32_t nb,
+                                     const uint8_t *const *parts, size_t part_stride, const uint32_t *const *part_crc, const uint8_t *want,
+                                     uint8_t *const *out, size_t out_stride, uint32_t *const *out_crc, int64_t *bad) {
+	NvtxScope nvtx_scope("lzgpu::convert_chunks");
+	if (!ctx || !src || !dst || !parts || !want || !out) return LZGPU_ERR_ARG;
+	int rc;
+	if ((rc = check_goal_or_std(src)) || (rc = check_goal_or_std(dst))) return rc;
+	if (nb == 0 || nb > LZGPU_BLOCKS_IN_CHUNK) { lz_set_error("nb out of range"); return LZGPU_ERR_ARG; }
+	if (n_chunks == 0) return LZGPU_OK;
+	const uint32_t B = LZGPU_BLOCK_SIZE;
+	const int ns = src->k + src->m, nd = dst->k + dst->m;
+	const uint32_t pbs = (nb + src->k - 1) / src->k, pbd = (nb + dst->k - 1) / dst->k;
+	const size_t sbytes = static_cast<size_t>(pbs) * B, dbytes = static_cast<size_t>(pbd) * B;
+	if (part_stride < sbytes || out_stride < dbytes) { lz_set_error("convert: strides too small"); return LZGPU_ERR_ARG; }
+	int n_in = 0, n_out = 0;
+	for (int i = 0; i < ns; ++i) n_in += parts[i] != nullptr;
+	for (int i = 0; i < nd; ++i) {
+		if (want[i] && !out[i]) { lz_set_error("convert: wanted part %d has no output buffer", i); return LZGPU_ERR_ARG; }
+		n_out += want[i] != 0;
+	}
+	if (n_out == 0) return LZGPU_OK;
+	std::lock_guard<std::mutex> lk(ctx->mu);
+	DeviceGuard g(ctx->device);
+	cudaStream_t st = ctx->stream;
+	// tiles of about 1 GiB of staged part data; a same-slice rebuild writes into buffers shaped like the inputs
+	const bool same = same_goal(src, dst) && !goal_is_std(src);
+	const size_t per_chunk = sbytes * std::max(n_in, 1) + dbytes * n_out;
+	const uint32_t tile = static_cast<uint32_t>(std::max<size_t>(1, std::min<size_t>(n_chunks, (size_t(1) << 30) / per_chunk)));
+	void *d_in, *d_cin, *d_o, *d_co;
+	if ((rc = lz_scratch(ctx, kScratchIn0, tile * sbytes * std::max(n_in, 1), &d_in))) return rc;
+	if ((rc = lz_scratch(ctx, kScratchCrc0, static_cast<size_t>(tile) * pbs * 4 * std::max(n_in, 1), &d_cin))) return rc;
+	if ((rc = lz_scratch(ctx, kScratchPar0, tile * dbytes * n_out, &d_o))) return rc;
+	if ((rc = lz_scratch(ctx, kScratchCrc1, static_cast<size_t>(tile) * pbd * 4 * n_out, &d_co))) return rc;
+	for (uint32_t c0 = 0; c0 < n_chunks; c0 += tile) {
+		const uint32_t nc = std::min(tile, n_chunks - c0);
+		std::vector<const void *> dp(ns, nullptr), dc(ns, nullptr);
+		std::vector<void *> dout(nd, nullptr), dcrc(nd, nullptr);
+		bool any_crc = false;
+		int a = 0;
+		for (int i = 0; i < ns; ++i) {
+			if (!parts[i]) continue;
+			uint8_t *slot = static_cast<uint8_t *>(d_in) + static_cast<size_t>(a) * tile * sbytes;
+			CUDA_TRY(cudaMemcpy2DAsync(slot, sbytes, parts[i] + static_cast<size_t>(c0) * part_stride, part_stride, sbytes, nc, cudaMemcpyHostToDevice, st));
+			ctx->stats.bytes_h2d += static_cast<uint64_t>(nc) * sbytes;
+			dp[i] = slot;
+			if (part_crc && part_crc[i]) {
+				uint8_t *cs = static_cast<uint8_t *>(d_cin) + static_cast<size_t>(a) * tile * pbs * 4;
+				CUDA_TRY(cudaMemcpyAsync(cs, part_crc[i] + static_cast<size_t>(c0) * pbs, static_cast<size_t>(nc) * pbs * 4, cudaMemcpyHostToDevice, st));
+				dc[i] = cs;
+				any_crc = true;
+			}
+			++a;
+		}
+		a = 0;
+		for (int i = 0; i < nd; ++i) {
+			if (!want[i]) continue;
+			dout[i] = static_cast<uint8_t *>(d_o) + static_cast<size_t>(a) * tile * dbytes;
+			if (out_crc && out_crc[i]) dcrc[i] = static_cast<uint8_t *>(d_co) + static_cast<size_t>(a) * tile * pbd * 4;
+			++a;
+		}
+		int64_t bad_local[3] = {-1, -1, -1};
+		(void)same;
+		rc = lzgpu_convert_chunks_dev(ctx, src, dst, nc, nb, dp.data(), sbytes, any_crc ? dc.data() : nullptr, want, dout.data(), dbytes,
+		                              out_crc ? dcrc.data() : nullptr, bad_local, st);
+		if (rc) {
+			if (bad) { bad[0] = bad_local[0] < 0 ? bad_local[0] : bad_local[0] + c0; bad[1] = bad_local[1]; bad[2] = bad_local[2]; }
+			cudaStreamSynchronize(st);
+			return rc;
+		}
+		for (int i = 0; i < nd; ++i) {
+			if (!want[i]) continue;
+			CUDA_TRY(cudaMemcpy2DAsync(out[i] + static_cast<size_t>(c0) * out_stride, out_stride, dout[i], dbytes, dbytes, nc, cudaMemcpyDeviceToHost, st));
+			ctx->stats.bytes_d2h += static_cast<uint64_t>(nc) * dbytes;
+			if (dcrc[i])
+				CUDA_TRY(cudaMemcpyAsync(out_crc[i] + static_cast<size_t>(c0) * pbd, dcrc[i], static_cast<size_t>(nc) * pbd * 4, cudaMemcpyDeviceToHost, st));
+		}
+		CUDA_TRY(cudaStreamSynchronize(st));
+	}
+	return LZGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // wire-format producer: LIZ_CLTOCS_WRITE_DATA prefixes from the CRC array
 // ------------------------------------------------------------------------------------------------
 extern "C" int lzgpu_write_data_prefixes_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb, const void *d_crc,
@@ -844,6 +1052,14 @@ static int verify_common(lzgpu_ctx *ctx, const uint8_t *h_data, size_t n_blocks,
 		                                                            lz::crc_of_zeros(block_len), sparse_rule, big_endian, ctx->d_first_bad);
 		CUDA_TRY(cudaGetLastError());
 		ctx->stats.kernel_launches++;
+		if (sparse_rule) {
+			// holes accepted on their CRC are re-read and must really be all zero (crc.cc:235-243)
+			const unsigned grid = static_cast<unsigned>(std::min<size_t>(n, static_cast<size_t>(ctx->sm_count) * 8));
+			sparse_confirm_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t *>(d_in), dstride, block_len, static_cast<const uint32_t *>(d_c),
+			                                            static_cast<const uint32_t *>(d_s), n, lz::crc_of_zeros(block_len), ctx->d_first_bad);
+			CUDA_TRY(cudaGetLastError());
+			ctx->stats.kernel_launches++;
+		}
 		CUDA_TRY(cudaMemcpyAsync(ctx->h_first_bad, ctx->d_first_bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 		CUDA_TRY(cudaStreamSynchronize(st));
 		ctx->stats.bytes_h2d += n * (block_len + 4ull);
@@ -868,6 +1084,133 @@ extern "C" int lzgpu_verify_interleaved(lzgpu_ctx *ctx, const uint8_t *records, 
 	if (!ctx || !records) return LZGPU_ERR_ARG;
 	const size_t rec = 4 + LZGPU_BLOCK_SIZE;  // chunk.h:40 kDiskBlockSize
 	return verify_common(ctx, records, n_blocks, LZGPU_BLOCK_SIZE, rec, 4, reinterpret_cast<const uint32_t *>(records), rec, 1, 1, first_bad);
+}
+
+// MooseFS chunk-file format (chunk.cc:126-190): 1 KiB signature block, then the table of big-endian block CRCs, then
+// (for xor/ec parts: after padding to a 4 KiB disk block) the data blocks.  The reader of this format does not apply the
+// sparse-block rule (hddspacemgr.cc:1746-1764).
+extern "C" size_t lzgpu_moosefs_header_size(int data_parts) {
+	if (data_parts < 1 || data_parts > LZGPU_MAX_DATA) return 0;
+	const size_t max_blocks = (LZGPU_BLOCKS_IN_CHUNK + data_parts - 1) / data_parts;  // Chunk::maxBlocksInFile, chunk.cc:74-77
+	const size_t required = 1024 + 4 * max_blocks;                                       // kMaxSignatureBlockSize + crc table
+	return data_parts == 1 ? required : (required + 4095) / 4096 * 4096;                 // chunk.cc:169-181
+}
+
+extern "C" int lzgpu_verify_moosefs(lzgpu_ctx *ctx, int data_parts, const uint8_t *file_image, size_t n_blocks, int64_t *first_bad) {
+	if (!ctx || !file_image) return LZGPU_ERR_ARG;
+	const size_t hdr = lzgpu_moosefs_header_size(data_parts);
+	if (!hdr || n_blocks > (LZGPU_BLOCKS_IN_CHUNK + data_parts - 1) / data_parts) return LZGPU_ERR_ARG;
+	return verify_common(ctx, file_image, n_blocks, LZGPU_BLOCK_SIZE, LZGPU_BLOCK_SIZE, hdr, reinterpret_cast<const uint32_t *>(file_image + 1024), 4, 1, 0,
+	                     first_bad);
+}
+
+// ------------------------------------------------------------------------------------------------
+// chunkserver block writes (hdd_write, hddspacemgr.cc:1898-2008), batched
+// ------------------------------------------------------------------------------------------------
+static_assert(sizeof(BlockWrite) == sizeof(lzgpu_block_write) && offsetof(BlockWrite, status) == offsetof(lzgpu_block_write, status) &&
+                  offsetof(BlockWrite, payload_off) == offsetof(lzgpu_block_write, payload_off),
+              "device and ABI write descriptors must match");
+
+extern "C" int lzgpu_write_blocks_dev(lzgpu_ctx *ctx, void *d_blocks, void *d_stored_crc, const void *d_payload, void *d_writes, uint32_t n_writes,
+                                       int sparse_rule, void *stream) {
+	NvtxScope nvtx_scope("lzgpu::write_blocks_dev");
+	if (!ctx || !d_blocks || !d_stored_crc || !d_writes || (reinterpret_cast<uintptr_t>(d_blocks) & 15)) return LZGPU_ERR_ARG;
+	if (n_writes == 0) return LZGPU_OK;
+	DeviceGuard g(ctx->device);
+	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+	BlockWriteArgs a{};
+	a.blocks = static_cast<uint8_t *>(d_blocks);
+	a.stored_crc = static_cast<uint32_t *>(d_stored_crc);
+	a.payload = static_cast<const uint8_t *>(d_payload);
+	a.writes = static_cast<BlockWrite *>(d_writes);
+	a.tables = ctx->d_crc_tables;
+	uint32_t p = 0x00800000u;  // x^8
+	for (int i = 0; i < 32; ++i) {
+		a.pow2[i] = p;
+		p = lz::crc_mulmod(p, p);
+	}
+	a.n_writes = n_writes;
+	a.sparse_rule = sparse_rule;
+	const unsigned grid = std::min<unsigned>(n_writes, static_cast<unsigned>(ctx->sm_count) * 8);
+	block_write_kernel<<<grid, 256, 0, st>>>(a);
+	CUDA_TRY(cudaGetLastError());
+	ctx->stats.kernel_launches++;
+	return LZGPU_OK;
+}
+
+extern "C" int lzgpu_write_blocks(lzgpu_ctx *ctx, uint8_t *blocks, uint32_t *stored_crc, size_t n_blocks, const uint8_t *payload, size_t payload_bytes,
+                                   lzgpu_block_write *writes, uint32_t n_writes, int sparse_rule) {
+	NvtxScope nvtx_scope("lzgpu::write_blocks");
+	if (!ctx || !blocks || !stored_crc || !writes || (!payload && payload_bytes)) return LZGPU_ERR_ARG;
+	if (n_writes == 0) return LZGPU_OK;
+	const size_t B = LZGPU_BLOCK_SIZE;
+	{
+		// one write per block and call: the requests of a batch are independent, like the jobs of different chunks
+		std::vector<uint32_t> seen(n_writes);
+		for (uint32_t i = 0; i < n_writes; ++i) {
+			if (writes[i].block >= n_blocks) { lz_set_error("write %u: block %u out of range", i, writes[i].block); return LZGPU_ERR_ARG; }
+			if (writes[i].size <= B && writes[i].payload_off + writes[i].size > payload_bytes) { lz_set_error("write %u: payload out of range", i); return LZGPU_ERR_ARG; }
+			seen[i] = writes[i].block;
+		}
+		std::sort(seen.begin(), seen.end());
+		if (std::adjacent_find(seen.begin(), seen.end()) != seen.end()) { lz_set_error("write_blocks: two writes to the same block in one call"); return LZGPU_ERR_ARG; }
+	}
+	std::lock_guard<std::mutex> lk(ctx->mu);
+	DeviceGuard g(ctx->device);
+	cudaStream_t st = ctx->stream;
+	const uint32_t tile = std::min<uint32_t>(n_writes, 8192);
+	void *d_blk, *d_crc, *d_pay, *d_wr;
+	int rc;
+	if ((rc = lz_scratch(ctx, kScratchIn0, tile * B, &d_blk))) return rc;
+	if ((rc = lz_scratch(ctx, kScratchCrc0, tile * 4, &d_crc))) return rc;
+	if ((rc = lz_scratch(ctx, kScratchPar0, std::max<size_t>(payload_bytes, 16), &d_pay))) return rc;
+	if ((rc = lz_scratch(ctx, kScratchCrc1, tile * sizeof(lzgpu_block_write), &d_wr))) return rc;
+	if (payload_bytes) CUDA_TRY(cudaMemcpyAsync(d_pay, payload, payload_bytes, cudaMemcpyHostToDevice, st));
+	ctx->stats.bytes_h2d += payload_bytes;
+	int first_error = LZGPU_OK;
+	std::vector<lzgpu_block_write> local(tile);
+	std::vector<uint32_t> crcs(tile);
+	for (uint32_t w0 = 0; w0 < n_writes; w0 += tile) {
+		const uint32_t n = std::min(tile, n_writes - w0);
+		for (uint32_t i = 0; i < n; ++i) {
+			const lzgpu_block_write &w = writes[w0 + i];
+			local[i] = w;
+			local[i].block = i;  // staged densely: slot i holds the block this write touches
+			local[i].status = 0;
+			crcs[i] = stored_crc[w.block];
+			const bool partial = !(w.offset == 0 && w.size == B);
+			if (w.exists && partial) {
+				CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(d_blk) + i * B, blocks + w.block * B, B, cudaMemcpyHostToDevice, st));
+				ctx->stats.bytes_h2d += B;
+			} else {
+				local[i].exists = 0;  // a whole-block write never reads the stored block (hddspacemgr.cc:1920-1940)
+			}
+		}
+		CUDA_TRY(cudaMemcpyAsync(d_crc, crcs.data(), n * 4, cudaMemcpyHostToDevice, st));
+		CUDA_TRY(cudaMemcpyAsync(d_wr, local.data(), n * sizeof(lzgpu_block_write), cudaMemcpyHostToDevice, st));
+		if ((rc = lzgpu_write_blocks_dev(ctx, d_blk, d_crc, d_pay, d_wr, n, sparse_rule, st))) return rc;
+		CUDA_TRY(cudaMemcpyAsync(local.data(), d_wr, n * sizeof(lzgpu_block_write), cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaMemcpyAsync(crcs.data(), d_crc, n * 4, cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+		ctx->stats.bytes_d2h += n * (4 + sizeof(lzgpu_block_write));
+		for (uint32_t i = 0; i < n; ++i) {
+			lzgpu_block_write &w = writes[w0 + i];
+			w.status = local[i].status;
+			if (w.status != LZGPU_OK) {
+				if (first_error == LZGPU_OK) {
+					first_error = w.status;
+					lz_set_error(w.status == LZGPU_ERR_CRC ? "write %u: payload CRC mismatch" : w.status == LZGPU_ERR_DAMAGED ? "write %u: stored block fails its CRC" : "write %u: bad offset/size", w0 + i);
+				}
+				continue;
+			}
+			// the caller's copy of the block is patched on the host: the bytes are the payload it already holds
+			uint8_t *blk = blocks + w.block * B;
+			if (!w.exists) std::memset(blk, 0, B);
+			std::memcpy(blk + w.offset, payload + w.payload_off, w.size);
+			stored_crc[w.block] = crcs[i];
+		}
+	}
+	return first_error;
 }
 
 // ------------------------------------------------------------------------------------------------

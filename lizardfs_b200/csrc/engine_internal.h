@@ -31,6 +31,7 @@ enum ScratchSlot {
 	kScratchCoef0, kScratchCoefLast = kScratchCoef0 + kCoefSlots - 1,
 	kScratchFused0, kScratchFused1,
 	kScratchTmpPart0, kScratchTmpPartLast = kScratchTmpPart0 + LZGPU_MAX_PARTS - 1,
+	kScratchConvImage, kScratchConvPar, kScratchConvCrc,
 	kScratchCount
 };
 

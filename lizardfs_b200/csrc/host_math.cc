@@ -241,6 +241,13 @@ int lzgpu_goal_parse(const char *text, lzgpu_goal *out) {
 	if (*text == '$') ++text;
 	lzgpu_goal g{};
 	int consumed = 0;
+	if (std::strncmp(text, "std", 3) == 0 || *text == '_') {  // the standard slice ("_" in goal definitions, goal_config_loader.cc:228-245)
+		const char *p = text + (*text == '_' ? 1 : 3);
+		for (; *p; ++p)
+			if (!std::isspace(static_cast<unsigned char>(*p))) return LZGPU_ERR_ARG;
+		*out = lzgpu_goal{LZGPU_KIND_STD, 1, 0};
+		return LZGPU_OK;
+	}
 	if (std::sscanf(text, "xor%d%n", &g.k, &consumed) == 1 && consumed > 0) {
 		g.kind = 0;
 		g.m = 1;

@@ -258,6 +258,160 @@ __global__ void __launch_bounds__(256) crc_compare_kernel(const uint32_t *comput
 	}
 }
 
+// Exact form of the sparse-block rule.  The reference accepts a stored CRC of 0 only when the block IS all zero
+// (crc.cc:235-243 compares the bytes), not merely when its CRC equals that of 64 KiB of zeros; crc_compare_kernel
+// accepts on the CRC, this pass re-reads only those accepted blocks (sparse chunk files: the holes) and rejects the
+// ones that hold a non-zero byte.  One CTA per block, grid-stride.
+__global__ void __launch_bounds__(256) sparse_confirm_kernel(const uint8_t *base, unsigned long long block_stride, unsigned int len,
+                                                             const uint32_t *computed, const uint32_t *stored,
+                                                             unsigned long long n, uint32_t zero_block_crc,
+                                                             unsigned long long *first_bad) {
+	for (unsigned long long i = blockIdx.x; i < n; i += gridDim.x) {
+		if (stored[i] != 0 || computed[i] != zero_block_crc) continue;  // uniform per CTA
+		const uint8_t *blk = base + i * block_stride;
+		const unsigned int n16 = len >> 4;
+		uint32_t any = 0;
+		for (unsigned int t = threadIdx.x; t < n16; t += blockDim.x) {
+			const uint4 v = ld_stream(reinterpret_cast<const uint4 *>(blk) + t);
+			any |= v.x | v.y | v.z | v.w;
+		}
+		for (unsigned int t = (n16 << 4) + threadIdx.x; t < len; t += blockDim.x) any |= blk[t];
+		if (__syncthreads_or(any != 0) && threadIdx.x == 0) atomicMin(first_bad, i);
+	}
+}
+
+// ---- chunkserver block writes (hdd_write, src/chunkserver/hddspacemgr.cc:1898-2008) ---------------------------
+// One CTA per write request.  The reference reads the stored block, CRCs the three ranges before / under / after the
+// write, checks  combine(pre, under, post) == stored  and stores  combine(pre, crc_of_payload, post).  With lin() the
+// linear part of the CRC that is:   stored check  <=>  lin(old block) ^ Z(64K) == stored
+//                                   new CRC        =   CRC(old block) ^ lin(old_under ^ payload) * x^(8*bytes after the write)
+// so the old block is read once (aligned, 16 B per thread per step) and the payload once (two CRC states share the
+// pass: the payload itself for the packet check, payload ^ old bytes for the update).
+struct BlockWrite {          // mirrors lzgpu_block_write (include/lzgpu.h)
+	uint32_t block, offset, size, crc;
+	unsigned long long payload_off;
+	uint32_t exists;
+	int32_t status;
+};
+
+struct BlockWriteArgs {
+	uint8_t *blocks;             // 64 KiB blocks, patched in place
+	uint32_t *stored_crc;        // per block, updated in place
+	const uint8_t *payload;
+	BlockWrite *writes;
+	const uint32_t *tables;      // 4*256 slicing tables
+	uint32_t pow2[32];           // x^(8 * 2^i) mod P
+	uint32_t n_writes;
+	int sparse_rule;             // interleaved chunk format: a stored CRC of 0 on an all-zero block counts as Z(64K)
+};
+
+__device__ __forceinline__ uint32_t crc_xpow_bytes_dev(uint32_t nbytes, const uint32_t *pow2) {
+	uint32_t acc = 0x80000000u;  // x^0 in the reflected representation
+	for (int i = 0; i < 32 && (nbytes >> i); ++i)
+		if ((nbytes >> i) & 1u) acc = crc_mulmod(acc, pow2[i]);
+	return acc;
+}
+
+// tree merge of 256 per-thread partial CRCs of equally long consecutive segments (seg_bytes each); result in thread 0
+__device__ __forceinline__ uint32_t cta_crc_tree(uint32_t st, uint32_t seg_bytes, const uint32_t *pow2, uint32_t *s_red) {
+	uint32_t mult = crc_xpow_bytes_dev(seg_bytes, pow2);
+	const unsigned t = threadIdx.x;
+	for (unsigned step = 1; step < 256; step <<= 1) {
+		s_red[t] = st;
+		__syncthreads();
+		if ((t & (2 * step - 1)) == 0) st = crc_mulmod(st, mult) ^ s_red[t + step];
+		__syncthreads();
+		mult = crc_mulmod(mult, mult);
+	}
+	return st;
+}
+
+__global__ void __launch_bounds__(256) block_write_kernel(const BlockWriteArgs a) {
+	__shared__ uint32_t s_tab[1024];
+	__shared__ uint32_t s_red[256];
+	__shared__ uint32_t s_bcast[4];
+	for (unsigned i = threadIdx.x; i < 1024; i += 256) s_tab[i] = a.tables[i];
+	__syncthreads();
+	const unsigned t = threadIdx.x;
+	const uint32_t B = 65536u;
+	for (uint32_t w = blockIdx.x; w < a.n_writes; w += gridDim.x) {
+		BlockWrite &wr = a.writes[w];
+		const uint32_t off = wr.offset, size = wr.size;
+		if (size > B || off >= B || off + size > B) {  // LIZARDFS_ERROR_WRONGSIZE / WRONGOFFSET (:1907-1915)
+			if (t == 0) wr.status = -1;
+			continue;
+		}
+		uint8_t *blk = a.blocks + static_cast<unsigned long long>(wr.block) * B;
+		const uint8_t *pay = a.payload + wr.payload_off;
+		const bool exists = wr.exists != 0;
+
+		// pass 1: the stored block — CRC and all-zero test (a block being created is all zero by definition)
+		uint32_t st = 0, any = 0;
+		if (exists) {
+			const uint4 *p = reinterpret_cast<const uint4 *>(blk) + t * 16;  // 256 bytes per thread
+#pragma unroll 4
+			for (int i = 0; i < 16; ++i) {
+				const uint4 v = p[i];
+				any |= v.x | v.y | v.z | v.w;
+				st = crc_step_word(st, v.x, s_tab);
+				st = crc_step_word(st, v.y, s_tab);
+				st = crc_step_word(st, v.z, s_tab);
+				st = crc_step_word(st, v.w, s_tab);
+			}
+		}
+		const uint32_t lin_old = cta_crc_tree(st, 256, a.pow2, s_red);
+		const int nonzero = __syncthreads_or(any != 0);
+
+		// pass 2: the payload — packet CRC and the update term, front-padded to 256 equal segments
+		const uint32_t seg = (size + 255) / 256, pad = seg * 256 - size;
+		uint32_t sp = 0, sd = 0;
+		for (uint32_t i = 0; i < seg; ++i) {
+			const long long idx = static_cast<long long>(t) * seg + i - pad;
+			uint32_t b = 0, o = 0;
+			if (idx >= 0) {
+				b = pay[idx];
+				o = exists ? blk[off + idx] : 0u;
+			}
+			sp = crc_step_byte(sp, b, s_tab);
+			sd = crc_step_byte(sd, b ^ o, s_tab);
+		}
+		const uint32_t lin_pay = cta_crc_tree(sp, seg, a.pow2, s_red);
+		const uint32_t lin_delta = cta_crc_tree(sd, seg, a.pow2, s_red);
+
+		if (t == 0) {
+			const uint32_t z_size = crc_mulmod(0xFFFFFFFFu, crc_xpow_bytes_dev(size, a.pow2)) ^ 0xFFFFFFFFu;  // mycrc32_zeroblock(0, size)
+			int status = 0;
+			uint32_t new_crc = 0;
+			if ((lin_pay ^ z_size) != wr.crc) status = -4;  // LZGPU_ERR_CRC: the packet is corrupt (:1916-1918)
+			else if (off == 0 && size == B) new_crc = wr.crc;  // whole-block write: no read-modify-write (:1920-1940)
+			else {
+				uint32_t crc_old = lin_old ^ kCrcZeroBlock64K;
+				if (exists) {
+					uint32_t stored = a.stored_crc[wr.block];
+					if (a.sparse_rule && stored == 0 && !nonzero) stored = kCrcZeroBlock64K;  // crc.cc:235-243 via hddspacemgr.cc:1779
+					if (stored != crc_old) status = -7;  // LZGPU_ERR_DAMAGED: the stored block fails its CRC (:1962-1971)
+				}
+				new_crc = crc_old ^ crc_mulmod(lin_delta, crc_xpow_bytes_dev(B - off - size, a.pow2));
+			}
+			s_bcast[0] = static_cast<uint32_t>(status);
+			s_bcast[1] = new_crc;
+		}
+		__syncthreads();
+		const int status = static_cast<int>(s_bcast[0]);
+		if (status == 0) {
+			if (!exists) {  // create the block as zeros (ftruncate, :1977-1985)
+				uint4 *p = reinterpret_cast<uint4 *>(blk);
+				for (unsigned i = t; i < B / 16; i += 256) p[i] = make_uint4(0, 0, 0, 0);
+				__syncthreads();
+			}
+			for (uint32_t i = t; i < size; i += 256) blk[off + i] = pay[i];
+			if (t == 0) a.stored_crc[wr.block] = s_bcast[1];
+		}
+		if (t == 0) wr.status = status;
+		__syncthreads();
+	}
+}
+
 // splitmix64 counter stream: 8-byte word w of chunk c = mix(seed + ((c<<23) + w + 1) * golden)
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
 	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;

@@ -71,7 +71,9 @@ class SliceType:
     def __init__(self, text_or_kind, k=None, m=None):
         lib = _lib.load()
         g = LzGoal()
-        if isinstance(text_or_kind, str):
+        if text_or_kind == 2 and (k, m) == (1, 0):
+            g.kind, g.k, g.m = 2, 1, 0      # standard slice: only Engine.convert_chunks accepts it
+        elif isinstance(text_or_kind, str):
             if lib.lzgpu_goal_parse(text_or_kind.encode(), C.byref(g)) != 0:
                 raise ValueError(f"bad goal {text_or_kind!r} (expected xorN with N in 2..9 or ec(K,M) with K in 2..32, M in 1..32)")
         else:
@@ -84,6 +86,7 @@ class SliceType:
     k = property(lambda s: s.c.k)
     m = property(lambda s: s.c.m)
     is_xor = property(lambda s: s.c.kind == 0)
+    is_std = property(lambda s: s.c.kind == 2)
 
     @classmethod
     def from_id(cls, type_id):
@@ -93,6 +96,8 @@ class SliceType:
         return cls(g.kind, g.k, g.m)
 
     def type_id(self):
+        if self.is_std:
+            return 0                        # Goal::Slice::Type::kStandard (goal.h:108-120)
         return _lib.load().lzgpu_goal_slice_type(C.byref(self.c))
 
     def chunk_part_id(self, part):
@@ -108,7 +113,7 @@ class SliceType:
         return _lib.load().lzgpu_part_length(C.byref(self.c), part, chunk_length)
 
     def __str__(self):
-        return f"xor{self.k}" if self.is_xor else f"ec({self.k},{self.m})"
+        return "std" if self.is_std else f"xor{self.k}" if self.is_xor else f"ec({self.k},{self.m})"
 
     __repr__ = __str__
 
@@ -389,6 +394,41 @@ class Engine:
         dp = (C.c_void_p * goal.k)(*[p if p else None for p in d_parts])
         _check(self.lib.lzgpu_split_chunks_dev(self.h, C.byref(goal.c), n_chunks, nb, d_data, chunk_stride, dp, part_stride, stream), "split_chunks_dev")
 
+    # ---- replication / slice-type conversion ----------------------------------------------------
+    def convert_chunks(self, src, dst, nb, parts, want, part_crc=None, with_crc=True):
+        """Rebuild the `want`ed parts of slice type `dst` from the available `parts` of slice type `src`
+        (SliceRecoveryPlanner, slice_recovery_planner.h:87-204).  parts[i]: (n_chunks, pb_src*65536) uint8 or None.
+        Returns (out, out_crc): lists indexed by destination part (None where not wanted)."""
+        ns, nd = src.k + src.m, dst.k + dst.m
+        pbs, pbd = -(-nb // src.k), -(-nb // dst.k)
+        arrs = [None if p is None else _u8(p).reshape(-1, pbs * BLOCK_SIZE) for p in parts]
+        n = next(a.shape[0] for a in arrs if a is not None)
+        crcs = None
+        if part_crc is not None:
+            crcs = [None if c is None else np.ascontiguousarray(c, dtype=np.uint32).reshape(n, pbs) for c in part_crc]
+        w = np.asarray(want, dtype=np.uint8)
+        assert len(arrs) == ns and w.size == nd
+        out = [np.zeros((n, pbd * BLOCK_SIZE), dtype=np.uint8) if w[i] else None for i in range(nd)]
+        ocrc = [np.zeros((n, pbd), dtype=np.uint32) if (w[i] and with_crc) else None for i in range(nd)]
+        bad = (C.c_int64 * 3)(-1, -1, -1)
+        rc = self.lib.lzgpu_convert_chunks(self.h, C.byref(src.c), C.byref(dst.c), n, nb, _ptr_array(arrs), pbs * BLOCK_SIZE,
+                                           _ptr_array(crcs) if crcs is not None else None, _p(w), _ptr_array(out), pbd * BLOCK_SIZE,
+                                           _ptr_array(ocrc) if with_crc else None, bad)
+        if rc == _lib.ERR_CRC:
+            raise ChunkCrcError(rc, "convert_chunks", tuple(bad))
+        _check(rc, "convert_chunks")
+        return out, ocrc
+
+    def convert_chunks_dev(self, src, dst, n_chunks, nb, d_parts, part_stride, want, d_out, out_stride, d_part_crc=None, d_out_crc=None, stream=None):
+        ns, nd = src.k + src.m, dst.k + dst.m
+        dp = (C.c_void_p * ns)(*[p if p else None for p in d_parts])
+        dc = (C.c_void_p * ns)(*[p if p else None for p in d_part_crc]) if d_part_crc is not None else None
+        do = (C.c_void_p * nd)(*[p if p else None for p in d_out])
+        doc = (C.c_void_p * nd)(*[p if p else None for p in d_out_crc]) if d_out_crc is not None else None
+        w = np.asarray(want, dtype=np.uint8)
+        _check(self.lib.lzgpu_convert_chunks_dev(self.h, C.byref(src.c), C.byref(dst.c), n_chunks, nb, dp, part_stride, dc, _p(w), do, out_stride,
+                                                 doc, None, stream), "convert_chunks_dev")
+
     # ---- CRC ---------------------------------------------------------------------------------
     def crc_blocks(self, data, block_len=BLOCK_SIZE, block_stride=None):
         data = _u8(data).reshape(-1)
@@ -420,6 +460,40 @@ class Engine:
         if rc == _lib.ERR_CRC:
             raise ChunkCrcError(rc, "verify_interleaved", (bad.value,))
         _check(rc, "verify_interleaved")
+
+    def moosefs_header_size(self, data_parts=1):
+        return int(self.lib.lzgpu_moosefs_header_size(data_parts))
+
+    def verify_moosefs(self, file_image, n_blocks, data_parts=1):
+        """file_image: MooseFS-format chunk file (chunk.cc:126-190): signature, big-endian CRC table at 1024, data after the header."""
+        img = _u8(file_image).reshape(-1)
+        bad = C.c_int64(-1)
+        rc = self.lib.lzgpu_verify_moosefs(self.h, data_parts, _p(img), n_blocks, C.byref(bad))
+        if rc == _lib.ERR_CRC:
+            raise ChunkCrcError(rc, "verify_moosefs", (bad.value,))
+        _check(rc, "verify_moosefs")
+
+    # ---- chunkserver block writes ----------------------------------------------------------------
+    def write_blocks(self, blocks, stored_crc, writes, sparse_rule=True):
+        """Batched hdd_write (hddspacemgr.cc:1898-2008).  blocks: uint8 [n, 65536], stored_crc: uint32 [n], both updated in place.
+        writes: list of dicts {block, offset, data (uint8 array), crc, exists (default True)}.  Returns the list of per-request
+        status codes (0, ERR_CRC = corrupt packet, ERR_DAMAGED = the stored block fails its CRC, ERR_ARG = bad range)."""
+        assert blocks.dtype == np.uint8 and blocks.flags.c_contiguous and stored_crc.dtype == np.uint32 and stored_crc.flags.c_contiguous
+        n = len(writes)
+        arr = (_lib.LzBlockWrite * max(n, 1))()
+        payload = np.concatenate([_u8(w["data"]).reshape(-1) for w in writes]) if n else np.zeros(0, dtype=np.uint8)
+        pos = 0
+        for i, w in enumerate(writes):
+            size = int(np.asarray(w["data"]).size)
+            arr[i].block, arr[i].offset, arr[i].size, arr[i].crc = int(w["block"]), int(w["offset"]), size, int(w["crc"])
+            arr[i].payload_off, arr[i].exists, arr[i].status = pos, int(w.get("exists", True)), 0
+            pos += size
+        payload = np.ascontiguousarray(payload)
+        rc = self.lib.lzgpu_write_blocks(self.h, _p(blocks), _p(stored_crc), blocks.size // BLOCK_SIZE, _p(payload) if payload.size else None,
+                                         payload.size, arr, n, int(sparse_rule))
+        if rc not in (_lib.OK, _lib.ERR_CRC, _lib.ERR_DAMAGED, _lib.ERR_ARG) or (rc == _lib.ERR_ARG and all(arr[i].status == 0 for i in range(n))):
+            _check(rc, "write_blocks")
+        return [arr[i].status for i in range(n)]
 
     # ---- device helpers ----------------------------------------------------------------------
     def fill_chunks_dev(self, d_data, n_chunks, chunk_len, chunk_stride, seed, first_chunk=0, stream=None):

@@ -517,6 +517,185 @@ void lzo_parts_to_chunk(int k, const uint8_t *const *data_parts, uint32_t nb, ui
 		       data_parts[b % (uint32_t)k] + (size_t)(b / (uint32_t)k) * LZO_BLOCK_SIZE, LZO_BLOCK_SIZE);
 }
 
+/* ------------------------------------------------------------------------------------
+ * Replication: rebuild parts of slice type (dkind,dk,dm) from parts of slice type (skind,sk,sm).
+ * Restates SliceRecoveryPlanner::prepare/buildPlan (src/chunkserver/slice_recovery_planner.h:87-204):
+ *   same slice type            -> kReadDataPart: read the part, or rebuild it inside the slice
+ *   data part of another type  -> kRecoverDataPart: chunk data, then BlockConverter (:41-57)
+ *   parity part                -> kRecoverParityPart: chunk data, then XorReadPlan::RecoverParity
+ *                                 (xor_read_plan.h:39-62) / ECReadPlan::RecoverParity (ec_read_plan.h:38-76)
+ * and the per-block mycrc32 of ChunkReplicator::replicate (chunk_replicator.cc:186-192).
+ * kind 2 = standard slice (k = 1, m = 0; part 0 is the chunk).  Output parts are pbd = ceil(nb/dk) blocks,
+ * short data parts zero-padded.
+ * ---------------------------------------------------------------------------------- */
+int lzo_convert_chunk(int skind, int sk, int sm, const uint8_t *const *parts, const uint32_t *const *part_crc,
+                      int dkind, int dk, int dm, const uint8_t *want, uint8_t *const *out, uint32_t *const *out_crc,
+                      uint32_t nb, int *bad) {
+	const size_t B = LZO_BLOCK_SIZE;
+	const uint32_t pbs = (nb + (uint32_t)sk - 1) / (uint32_t)sk, pbd = (nb + (uint32_t)dk - 1) / (uint32_t)dk;
+	int rc = 0;
+	if (skind == dkind && sk == dk && sm == dm && skind != 2) {
+		rc = lzo_recover_chunk(skind, sk, sm, parts, part_crc, want, out, (int)pbs, bad);
+		if (rc) return rc;
+		for (int i = 0; i < dk + dm; ++i)
+			if (want[i] && parts[i] && out[i]) memcpy(out[i], parts[i], pbs * B);
+	} else {
+		/* chunk data in chunk order (ChunkReadPlanner + its BlockConverter, chunk_read_planner.h:36-70) */
+		uint8_t *chunk = (uint8_t *)calloc((size_t)pbd * (size_t)dk + 1, B); /* zero tail = absent blocks of the last stripe */
+		uint8_t *tmp[LZO_MAX_PARTS] = {0};
+		if (!chunk) return -1;
+		if (skind == 2) {
+			if (!parts[0]) { free(chunk); return -2; }
+			if (part_crc && part_crc[0])
+				for (uint32_t b = 0; b < nb; ++b)
+					if (lzo_crc32(0, parts[0] + b * B, LZO_BLOCK_SIZE) != part_crc[0][b]) {
+						if (bad) { bad[0] = 0; bad[1] = (int)b; }
+						free(chunk);
+						return -3;
+					}
+			memcpy(chunk, parts[0], nb * B);
+		} else {
+			uint8_t all_data[LZO_MAX_PARTS] = {0};
+			const uint8_t *data_parts[LZO_MAX_PARTS] = {0};
+			for (int j = 0; j < sk; ++j) {
+				all_data[j] = 1;
+				if (!parts[j]) tmp[j] = (uint8_t *)calloc(pbs, B);
+			}
+			rc = lzo_recover_chunk(skind, sk, sm, parts, part_crc, all_data, tmp, (int)pbs, bad);
+			if (rc == 0) {
+				for (int j = 0; j < sk; ++j) data_parts[j] = parts[j] ? parts[j] : tmp[j];
+				lzo_parts_to_chunk(sk, data_parts, nb, chunk);
+			}
+			for (int j = 0; j < sk; ++j) free(tmp[j]);
+			if (rc) { free(chunk); return rc; }
+		}
+		if (dkind == 2) {
+			if (want[0] && out[0]) memcpy(out[0], chunk, nb * B);
+		} else {
+			for (int j = 0; j < dk; ++j) {
+				if (!want[j] || !out[j]) continue;
+				/* SliceRecoveryPlanner::BlockConverter: dst block s <- chunk block s*dk + j */
+				const uint32_t mine = (uint32_t)lzo_part_blocks(dk, j, nb);
+				memset(out[j], 0, pbd * B);
+				for (uint32_t s2 = 0; s2 < mine; ++s2) memcpy(out[j] + s2 * B, chunk + ((size_t)s2 * dk + j) * B, B);
+			}
+			for (int r = 0; r < dm; ++r) {
+				uint8_t *dst = out[dk + r];
+				if (!want[dk + r] || !dst) continue;
+				for (uint32_t s2 = 0; s2 < pbd; ++s2) {
+					const uint8_t *src = chunk + (size_t)s2 * dk * B;
+					if (dkind == 0) { /* XorReadPlan::RecoverParity: memcpy the first block, blockXor the rest */
+						memcpy(dst + s2 * B, src, B);
+						for (int i = 1; i < dk; ++i) lzo_block_xor(dst + s2 * B, src + i * B, B);
+					} else { /* ECReadPlan::RecoverParity: rs.recover with every parity part erased, one output */
+						const uint8_t *in[LZO_MAX_PARTS] = {0};
+						uint8_t erased[LZO_MAX_PARTS] = {0};
+						uint8_t *res[LZO_MAX_PARTS] = {0};
+						for (int i = 0; i < dk; ++i) in[i] = src + i * B;
+						for (int i = 0; i < dm; ++i) erased[dk + i] = 1;
+						res[dk + r] = dst + s2 * B;
+						lzo_rs_recover(dk, dm, in, erased, res, B);
+					}
+				}
+			}
+		}
+		free(chunk);
+	}
+	if (out_crc)
+		for (int i = 0; i < dk + dm; ++i)
+			if (want[i] && out[i] && out_crc[i])
+				for (uint32_t b = 0; b < (dkind == 2 ? nb : pbd); ++b) out_crc[i][b] = lzo_crc32(0, out[i] + b * B, LZO_BLOCK_SIZE);
+	return 0;
+}
+
+/* ------------------------------------------------------------------------------------
+ * Chunkserver scrub, hdd_int_test (src/chunkserver/hddspacemgr.cc:2148-2210) over an in-memory chunk file.
+ * Interleaved format (chunk.h:40, chunk.cc:195-209): records of 4-byte big-endian CRC + 64 KiB; the reader applies
+ * the sparse-block rule (hddspacemgr.cc:1766-1780).  MooseFS format (chunk.cc:126-190): 1 KiB signature, CRC table,
+ * data from the header size on; no sparse rule (hddspacemgr.cc:1748-1764).  Returns 0 or -3 with *first_bad.
+ * ---------------------------------------------------------------------------------- */
+static uint32_t get_be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+
+int lzo_scrub_interleaved(const uint8_t *records, size_t n_blocks, int64_t *first_bad) {
+	for (size_t b = 0; b < n_blocks; ++b) {
+		const uint8_t *rec = records + b * (4 + (size_t)LZO_BLOCK_SIZE);
+		uint32_t stored = get_be32(rec);
+		lzo_recompute_crc_if_block_empty(rec + 4, &stored);
+		if (stored != lzo_crc32(0, rec + 4, LZO_BLOCK_SIZE)) {
+			if (first_bad) *first_bad = (int64_t)b;
+			return -3;
+		}
+	}
+	return 0;
+}
+
+size_t lzo_moosefs_header_size(int data_parts) {
+	size_t max_blocks = (LZO_BLOCKS_IN_CHUNK + (size_t)data_parts - 1) / (size_t)data_parts; /* chunk.cc:74-77 */
+	size_t required = 1024 + 4 * max_blocks;                                                   /* chunk.cc:171,175 */
+	return data_parts == 1 ? required : (required + 4095) / 4096 * 4096;                       /* chunk.cc:176-180 */
+}
+
+int lzo_scrub_moosefs(const uint8_t *image, int data_parts, size_t n_blocks, int64_t *first_bad) {
+	const uint8_t *crc_table = image + 1024; /* getCrcOffset, chunk.cc:183-185 */
+	const uint8_t *data = image + lzo_moosefs_header_size(data_parts);
+	for (size_t b = 0; b < n_blocks; ++b)
+		if (get_be32(crc_table + 4 * b) != lzo_crc32(0, data + b * (size_t)LZO_BLOCK_SIZE, LZO_BLOCK_SIZE)) {
+			if (first_bad) *first_bad = (int64_t)b;
+			return -3;
+		}
+	return 0;
+}
+
+/* ------------------------------------------------------------------------------------
+ * hdd_write of one block (src/chunkserver/hddspacemgr.cc:1898-2008), the CRC arithmetic only.
+ *   block      the 64 KiB block as stored (modified in place), or NULL when the block does not exist yet
+ *              (blocknum >= chunk->blocks: it is created as zeros, :1976-1993)
+ *   stored_crc in: CRC stored for the block (ignored when block == NULL); out: the CRC to store
+ *   offset,size,crc,buffer  the write request (LIZ_CLTOCS_WRITE_DATA fields)
+ *   new_block  when block == NULL, receives the created block (64 KiB)
+ * Returns 0, -3 when the packet CRC is wrong (LIZARDFS_ERROR_CRC, :1916-1918), -4 when the stored block fails its CRC
+ * check (:1962-1971), -1 on bad offset/size (:1910-1915).
+ * ---------------------------------------------------------------------------------- */
+int lzo_hdd_write_block(uint8_t *block, uint32_t *stored_crc, uint32_t offset, uint32_t size, uint32_t crc,
+                        const uint8_t *buffer, uint8_t *new_block) {
+	const uint32_t B = LZO_BLOCK_SIZE;
+	uint32_t precrc, postcrc, combined;
+	if (size > B || offset >= B || offset + size > B) return -1;
+	if (crc != lzo_crc32(0, buffer, size)) return -3;
+	if (offset == 0 && size == B) {
+		uint8_t *dst = block ? block : new_block;
+		memcpy(dst, buffer, B);
+		*stored_crc = crc;
+		return 0;
+	}
+	if (block) {
+		uint32_t have = *stored_crc;
+		lzo_recompute_crc_if_block_empty(block, &have); /* hdd_int_read_block_and_crc, interleaved format, :1779 */
+		precrc = lzo_crc32(0, block, offset);
+		uint32_t chcrc = lzo_crc32(0, block + offset, size);
+		postcrc = lzo_crc32(0, block + offset + size, B - (offset + size));
+		if (offset == 0) combined = lzo_crc32_combine(chcrc, postcrc, B - (offset + size));
+		else {
+			combined = lzo_crc32_combine(precrc, chcrc, size);
+			if (offset + size < B) combined = lzo_crc32_combine(combined, postcrc, B - (offset + size));
+		}
+		if (have != combined) return -4;
+	} else {
+		block = new_block;
+		memset(block, 0, B);
+		precrc = lzo_crc32_zeroblock(0, offset);
+		postcrc = lzo_crc32_zeroblock(0, B - (offset + size));
+	}
+	if (offset == 0) combined = lzo_crc32_combine(crc, postcrc, B - (offset + size));
+	else {
+		combined = lzo_crc32_combine(precrc, crc, size);
+		if (offset + size < B) combined = lzo_crc32_combine(combined, postcrc, B - (offset + size));
+	}
+	memcpy(block + offset, buffer, size);
+	*stored_crc = combined;
+	return 0;
+}
+
 /* cltocs.h:116-137: serializePacketPrefix(destination, size, LIZ_CLTOCS_WRITE_DATA, 0, chunkId, writeId, block,
  * offset, size, crc) — PacketHeader(type, length = serialized size of version + fields (30) + size), big-endian. */
 static uint8_t *put_be(uint8_t *p, uint64_t v, int bytes) {

@@ -109,6 +109,22 @@ int lzo_recover_chunk(int kind, int k, int m, const uint8_t *const *parts,
 /* part-major -> chunk order gather (chunk_read_planner.h:36-70) */
 void lzo_parts_to_chunk(int k, const uint8_t *const *data_parts, uint32_t nb, uint8_t *chunk);
 
+/* Replication / slice-type conversion (SliceRecoveryPlanner, src/chunkserver/slice_recovery_planner.h:87-204 + the CRC loop
+ * of chunk_replicator.cc:186-192).  kinds: 0 xor, 1 ec, 2 standard (k = 1, m = 0).  Parts indexed data 0..k-1, parity k...
+ * out[i] holds pbd = ceil(nb/dk) blocks (nb for a standard destination), out_crc[i] as many CRCs.  Returns as lzo_recover_chunk. */
+int lzo_convert_chunk(int skind, int sk, int sm, const uint8_t *const *parts, const uint32_t *const *part_crc,
+                      int dkind, int dk, int dm, const uint8_t *want, uint8_t *const *out, uint32_t *const *out_crc,
+                      uint32_t nb, int *bad);
+
+/* hdd_int_test (hddspacemgr.cc:2148-2210) over in-memory chunk files of both on-disk formats (chunk.cc:126-209). */
+int lzo_scrub_interleaved(const uint8_t *records, size_t n_blocks, int64_t *first_bad);
+size_t lzo_moosefs_header_size(int data_parts);
+int lzo_scrub_moosefs(const uint8_t *image, int data_parts, size_t n_blocks, int64_t *first_bad);
+
+/* hdd_write of one block (hddspacemgr.cc:1898-2008): packet CRC check, stored-block check via mycrc32_combine, new CRC. */
+int lzo_hdd_write_block(uint8_t *block, uint32_t *stored_crc, uint32_t offset, uint32_t size, uint32_t crc,
+                        const uint8_t *buffer, uint8_t *new_block);
+
 /* LIZ_CLTOCS_WRITE_DATA packet prefix (src/protocol/cltocs.h:116-137, packet.h:130-136, MFSCommunication.h:630):
  * header type:u32 = 1212, length:u32 = 30 + size; then version:u32 = 0, chunkId:u64, writeId:u32, block:u16,
  * offset:u32, size:u32, crc:u32 — all big-endian, 38 bytes; `size` data bytes follow on the wire. */
@@ -117,7 +133,7 @@ void lzo_write_data_prefix(uint8_t *out38, uint64_t chunk_id, uint32_t write_id,
                            uint32_t size, uint32_t crc);
 
 /* deterministic synthetic data shared by oracle, tests and the GPU generator:
- * splitmix64 counter stream, word w of chunk c = mix(seed + (c<<40) + w) little-endian. */
+ * splitmix64 counter stream, 8-byte word w of chunk c = mix(seed + ((c<<23) + w + 1) * 0x9E3779B97F4A7C15), little-endian. */
 void lzo_fill_chunk(uint8_t *dst, size_t len, uint64_t seed, uint64_t chunk_index);
 
 #ifdef __cplusplus

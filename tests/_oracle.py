@@ -191,3 +191,129 @@ def split_parts(chunk, k):
     for b in range(nb):
         parts[b % k][b // k] = blocks[b]
     return [p.reshape(-1) for p in parts], pb
+
+
+# ---- the reference's planners, executed in memory (oracle/ref_plans.cc) ----------------------
+def slice_type(kind, k, m):
+    """Goal::Slice::Type value (slice_traits.h:96-151): standard 0, xorN 2+(N-2), ec 10+32(k-2)+(m-1)."""
+    if kind == 2:
+        return 0
+    return 2 + (k - 2) if kind == 0 else 10 + 32 * (k - 2) + (m - 1)
+
+
+def ref_part_number(kind, k, part):
+    """this repo's part index (data 0..k-1, parity k..) -> the reference's slice part number."""
+    if kind == 0:
+        return part + 1 if part < k else 0
+    return part
+
+
+def _sources(sources):
+    """sources: list of (slice_type, ref_part_number, uint8 array)."""
+    n = len(sources)
+    types = (C.c_int * n)(*[s[0] for s in sources])
+    parts = (C.c_int * n)(*[s[1] for s in sources])
+    arrs = [np.ascontiguousarray(s[2], dtype=np.uint8) for s in sources]
+    data = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    sizes = (C.c_size_t * n)(*[a.size for a in arrs])
+    return n, types, parts, data, sizes, arrs
+
+
+def plan_read_chunk(ref, sources, first_block, block_count):
+    """ChunkReadPlanner + ReadPlan::postProcessData of the compiled reference; None when reading is impossible."""
+    n, types, parts, data, sizes, keep = _sources(sources)
+    out = np.zeros(block_count * BLOCK, dtype=np.uint8)
+    f = ref.dll.ref_plan_read_chunk
+    f.restype = C.c_long
+    got = f(n, types, parts, data, sizes, first_block, block_count, _ptr(out))
+    return None if got < 0 else out[:got]
+
+
+def plan_recover_part(ref, sources, dst_type, dst_part, first_block, block_count):
+    """SliceRecoveryPlanner + the replicator's CRC loop of the compiled reference -> (bytes, crcs) or None."""
+    n, types, parts, data, sizes, keep = _sources(sources)
+    out = np.zeros(block_count * BLOCK, dtype=np.uint8)
+    crc = np.zeros(block_count, dtype=np.uint32)
+    f = ref.dll.ref_plan_recover_part
+    f.restype = C.c_long
+    got = f(n, types, parts, data, sizes, dst_type, dst_part, first_block, block_count, _ptr(out), _ptr(crc))
+    return None if got < 0 else (out[:got], crc)
+
+
+# ---- chunkserver-side restatements (oracle only) -------------------------------------------------
+def convert_chunk(oracle, src, parts, part_crc, dst, want, nb):
+    """lzo_convert_chunk.  src/dst = (kind, k, m); parts/part_crc indexed data 0..k-1 then parity.
+    Returns (rc, out, out_crc, bad)."""
+    (skind, sk, sm), (dkind, dk, dm) = src, dst
+    pbd = nb if dkind == 2 else -(-nb // dk)
+    nd = dk + dm
+    out = [np.zeros(pbd * BLOCK, dtype=np.uint8) if want[i] else None for i in range(nd)]
+    ocrc = [np.zeros(pbd, dtype=np.uint32) if want[i] else None for i in range(nd)]
+    bad = (C.c_int * 2)(-1, -1)
+    w = np.asarray(want, dtype=np.uint8)
+    f = oracle.dll.lzo_convert_chunk
+    f.restype = C.c_int
+    rc = f(skind, sk, sm, ptr_array(parts), ptr_array(part_crc) if part_crc is not None else None, dkind, dk, dm, _ptr(w),
+           ptr_array(out), ptr_array(ocrc), C.c_uint32(nb), bad)
+    return rc, out, ocrc, (bad[0], bad[1])
+
+
+def scrub_interleaved(oracle, records, n_blocks):
+    bad = C.c_int64(-1)
+    f = oracle.dll.lzo_scrub_interleaved
+    f.restype = C.c_int
+    rc = f(_ptr(np.ascontiguousarray(records, dtype=np.uint8)), C.c_size_t(n_blocks), C.byref(bad))
+    return rc, bad.value
+
+
+def moosefs_header_size(oracle, data_parts):
+    f = oracle.dll.lzo_moosefs_header_size
+    f.restype = C.c_size_t
+    return f(data_parts)
+
+
+def scrub_moosefs(oracle, image, data_parts, n_blocks):
+    bad = C.c_int64(-1)
+    f = oracle.dll.lzo_scrub_moosefs
+    f.restype = C.c_int
+    rc = f(_ptr(np.ascontiguousarray(image, dtype=np.uint8)), data_parts, C.c_size_t(n_blocks), C.byref(bad))
+    return rc, bad.value
+
+
+def hdd_write_block(oracle, block, stored_crc, offset, size, crc, buffer):
+    """lzo_hdd_write_block: returns (rc, new_block, new_crc).  block None = the block does not exist yet."""
+    new_block = np.zeros(BLOCK, dtype=np.uint8)
+    work = None if block is None else np.array(block, dtype=np.uint8, copy=True)
+    c = C.c_uint32(stored_crc)
+    buf = np.ascontiguousarray(buffer, dtype=np.uint8)
+    f = oracle.dll.lzo_hdd_write_block
+    f.restype = C.c_int
+    rc = f(_ptr(work) if work is not None else None, C.byref(c), C.c_uint32(offset), C.c_uint32(size), C.c_uint32(crc), _ptr(buf), _ptr(new_block))
+    return rc, (work if work is not None else new_block), c.value
+
+
+def forge_block_with_crc(target_crc, seed=0):
+    """A NON-zero 64 KiB block whose CRC-32 equals target_crc (the last four bytes are solved for: CRC is affine in them)."""
+    import zlib
+    rng = np.random.default_rng(seed)
+    blk = rng.integers(0, 256, BLOCK, dtype=np.uint8)
+    body = blk[:-4].tobytes()
+    base = zlib.crc32(body + b"\0\0\0\0")
+    cols = [zlib.crc32(body + (1 << i).to_bytes(4, "little")) ^ base for i in range(32)]
+    # solve sum_i x_i * cols[i] = target ^ base over GF(2)
+    rows = [(cols[i], 1 << i) for i in range(32)]
+    want, x = target_crc ^ base, 0
+    basis = {}
+    for v, tag in rows:
+        for bit in sorted(basis, reverse=True):
+            if v >> bit & 1:
+                v ^= basis[bit][0]; tag ^= basis[bit][1]
+        if v:
+            basis[v.bit_length() - 1] = (v, tag)
+    for bit in sorted(basis, reverse=True):
+        if want >> bit & 1:
+            want ^= basis[bit][0]; x ^= basis[bit][1]
+    assert want == 0
+    blk[-4:] = np.frombuffer(x.to_bytes(4, "little"), dtype=np.uint8)
+    assert zlib.crc32(blk.tobytes()) == target_crc and blk.any()
+    return blk

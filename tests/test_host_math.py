@@ -117,12 +117,16 @@ def test_goal_parsing_and_ids():
     assert (x.kind, x.k, x.m) == (0, 3, 1) and x.type_id() == 3
     assert x.ref_part_index(3) == 0 and x.ref_part_index(0) == 1  # xor: parity is part 0 (slice_traits.h:98)
     assert str(L.SliceType.from_id(203)) == "ec(8,2)" and str(L.SliceType.from_id(9)) == "xor9"
-    for bad in ["xor1", "xor10", "ec(1,1)", "ec(33,1)", "ec(2,0)", "ec(2,33)", "std", "ec(8,2)x", ""]:
+    for bad in ["xor1", "xor10", "ec(1,1)", "ec(33,1)", "ec(2,0)", "ec(2,33)", "stdx", "ec(8,2)x", ""]:
         with pytest.raises(ValueError):
             L.SliceType(bad)
     for k in range(2, 33):
         for m in range(1, 33):
             assert L.SliceType.from_id(L.SliceType(1, k, m).type_id()).k == k
+    # the standard slice exists only as the source/destination of a conversion (Goal::Slice::Type 0)
+    for text in ("std", "$std", "_"):
+        s = L.SliceType(text)
+        assert (s.kind, s.k, s.m) == (2, 1, 0) and s.type_id() == 0 and s.is_std and str(s) == "std"
 
 
 def test_geometry_matches_slice_traits(oracle):
