@@ -291,6 +291,9 @@ int lzgpu_dev_free(lzgpu_ctx *ctx, void *d_ptr);
 int lzgpu_dev_upload(lzgpu_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
 int lzgpu_dev_download(lzgpu_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
 int lzgpu_dev_sync(lzgpu_ctx *ctx);
+/* page-locked host memory for staging buffers that feed the host-pointer entry points (H2D/D2H at full PCIe rate) */
+int lzgpu_host_alloc(lzgpu_ctx *ctx, size_t bytes, void **h_ptr);
+int lzgpu_host_free(lzgpu_ctx *ctx, void *h_ptr);
 
 #ifdef __cplusplus
 }

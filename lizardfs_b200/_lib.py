@@ -96,6 +96,8 @@ SIGNATURES = {
     "lzgpu_dev_free": (_int, [_vp, _vp]),
     "lzgpu_dev_upload": (_int, [_vp, _vp, _vp, _sz]),
     "lzgpu_dev_download": (_int, [_vp, _vp, _vp, _sz]),
+    "lzgpu_host_alloc": (_int, [_vp, _sz, _vp]),
+    "lzgpu_host_free": (_int, [_vp, _vp]),
     "lzgpu_dev_sync": (_int, [_vp]),
 }
 

@@ -1401,6 +1401,19 @@ extern "C" int lzgpu_dev_free(lzgpu_ctx *ctx, void *d_ptr) {
 	CUDA_TRY(cudaFree(d_ptr));
 	return LZGPU_OK;
 }
+extern "C" int lzgpu_host_alloc(lzgpu_ctx *ctx, size_t bytes, void **h_ptr) {
+	if (!ctx || !h_ptr) return LZGPU_ERR_ARG;
+	DeviceGuard g(ctx->device);
+	cudaError_t e = cudaHostAlloc(h_ptr, bytes, cudaHostAllocPortable);
+	if (e != cudaSuccess) { cudaGetLastError(); lz_set_error("cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e)); return LZGPU_ERR_NOMEM; }
+	return LZGPU_OK;
+}
+extern "C" int lzgpu_host_free(lzgpu_ctx *ctx, void *h_ptr) {
+	if (!ctx) return LZGPU_ERR_ARG;
+	DeviceGuard g(ctx->device);
+	CUDA_TRY(cudaFreeHost(h_ptr));
+	return LZGPU_OK;
+}
 extern "C" int lzgpu_dev_upload(lzgpu_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
 	if (!ctx) return LZGPU_ERR_ARG;
 	DeviceGuard g(ctx->device);

@@ -7,6 +7,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "tests", "cpp", "build", "test_reference_api")
+BATCHER = os.path.join(ROOT, "tests", "cpp", "build", "test_stripe_batcher")
 
 
 def test_cpp_binary_is_built():
@@ -24,3 +25,21 @@ def test_reference_api_cpp():
     r = subprocess.run([BIN], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "passed" in r.stdout
+
+
+def test_batcher_binary_is_built():
+    if not os.path.exists(BATCHER):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")], check=True)
+    out = subprocess.run(["ldd", BATCHER], capture_output=True, text=True).stdout
+    assert "liblzgpu.so" in out and "liboracle.so" in out and "not found" not in out
+
+
+@pytest.mark.gpu
+def test_stripe_batcher_cpp():
+    """lzgpu::StripeBatcher (include/lzgpu_stripe_batcher.hpp): the mount write path batched by stripe, checked block by
+    block against the CPU oracle inside the C++ test (tests/cpp/test_stripe_batcher.cc)."""
+    if not os.path.exists(BATCHER):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")], check=True)
+    r = subprocess.run([BATCHER], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all tests passed" in r.stdout
