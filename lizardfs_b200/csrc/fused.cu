@@ -32,6 +32,7 @@ struct FusedState {
 	uint32_t probe = 0;
 	uint32_t *d_sm_ctr = nullptr;
 	int evict_first = 0;
+	int striped = -1;  // LZGPU_STRIPED: -1 automatic, 0 never, 1 whenever the shape allows
 	int promo = 3;  // CU_TENSOR_MAP_L2_PROMOTION_L2_256B: +12% streaming bandwidth over 128B/none (profiles/probe_r1.md)
 };
 
@@ -48,9 +49,9 @@ static uint32_t crc_xpow_bits_signed(long long n) {
 	return acc;
 }
 
-template <int M, bool GENERIC, int KT = 0, int GT = 0, int FW = 64>
+template <int M, bool GENERIC, int KT = 0, int GT = 0, int FW = 64, bool STRIPED = false>
 static int set_smem_attr(int bytes) {
-	CUDA_TRY(cudaFuncSetAttribute(fused_stream_kernel<M, GENERIC, KT, GT, FW>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+	CUDA_TRY(cudaFuncSetAttribute(fused_stream_kernel<M, GENERIC, KT, GT, FW, STRIPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
 	return LZGPU_OK;
 }
 
@@ -86,6 +87,7 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if (const char *e = std::getenv("LZGPU_PROBE")) fs->probe = static_cast<uint32_t>(std::atoi(e));
 	if (const char *e = std::getenv("LZGPU_L2_PROMO")) fs->promo = std::atoi(e);
 	if (const char *e = std::getenv("LZGPU_EVICT_FIRST")) fs->evict_first = std::atoi(e);
+	if (const char *e = std::getenv("LZGPU_STRIPED")) fs->striped = std::atoi(e);  // 0 never, 1 whenever possible, unset = automatic
 	void *fn = nullptr;
 	cudaDriverEntryPointQueryResult qres;
 	cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -110,6 +112,17 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if ((rc = set_smem_attr<3, false>(smem))) return rc;
 	if ((rc = set_smem_attr<4, false>(smem))) return rc;
 	if ((rc = set_smem_attr<4, true>(smem))) return rc;
+	if ((rc = set_smem_attr<1, false, 0, 0, 64, true>(smem))) return rc;
+	if ((rc = set_smem_attr<2, false, 0, 0, 64, true>(smem))) return rc;
+	if ((rc = set_smem_attr<3, false, 0, 0, 64, true>(smem))) return rc;
+	if ((rc = set_smem_attr<4, false, 0, 0, 64, true>(smem))) return rc;
+	if ((rc = set_smem_attr<4, true, 0, 0, 64, true>(smem))) return rc;
+	if ((rc = set_smem_attr<2, false, 8, 8, 64, true>(smem))) return rc;
+	if ((rc = set_smem_attr<1, false, 2, 32, 64, true>(smem))) return rc;
+	if ((rc = set_smem_attr<1, false, 3, 20, 64, true>(smem))) return rc;
+	if ((rc = set_smem_attr<2, false, 3, 16, 64, true>(smem))) return rc;
+	if ((rc = set_smem_attr<3, false, 5, 8, 64, true>(smem))) return rc;
+	if ((rc = set_smem_attr<4, false, 8, 6, 64, true>(smem))) return rc;
 	if ((rc = set_smem_attr<2, false, 8, 8>(smem))) return rc;
 	if ((rc = set_smem_attr<1, false, 2, 32>(smem))) return rc;
 	if ((rc = set_smem_attr<1, false, 3, 20>(smem))) return rc;
@@ -178,11 +191,11 @@ static int make_tensor_map(FusedState *fs, CUtensorMap *map, const void *base, u
 	return LZGPU_OK;
 }
 
-template <int M, bool GENERIC, int KT = 0, int GT = 0, int FW = 64>
+template <int M, bool GENERIC, int KT = 0, int GT = 0, int FW = 64, bool STRIPED = false>
 static int launch(lzgpu_ctx *ctx, const CUtensorMap &map, const FusedParams &p, size_t smem, cudaStream_t st) {
 	const int per_sm = FW == 64 ? 2 : 1;
 	const int grid = static_cast<int>(std::min<uint64_t>(p.total_units, static_cast<uint64_t>(ctx->sm_count) * per_sm));
-	fused_stream_kernel<M, GENERIC, KT, GT, FW><<<grid, kFusedThreads, smem, st>>>(map, p);
+	fused_stream_kernel<M, GENERIC, KT, GT, FW, STRIPED><<<grid, kFusedThreads, smem, st>>>(map, p);
 	CUDA_TRY(cudaGetLastError());
 	ctx->stats.kernel_launches++;
 	return LZGPU_OK;
@@ -231,8 +244,18 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	                  static_cast<uint64_t>(n_chunks) * p.pb < (1ull << 31) && static_cast<uint64_t>(n_chunks) * nb * 4 < (1ull << 31);  // TMA coordinates are int32
 	p.flat = flat ? 1u : 0u;
 	p.flat_magic = (1ull << 40) / p.pb + 1;
+	// striped mode: the same run of global stripes for ANY nb / chunk stride, loaded one stripe box at a time; chosen when
+	// per-chunk units would leave more than 12 % of their stripe slots empty (small or ragged chunks).  Measured
+	// (profiles/sweep_r1.md): G boxes per step instead of one cost 2-10 % at 64 MiB, and win up to 2.4x at 1-4 MiB.
+	if (!flat && M > 0 && static_cast<uint64_t>(n_chunks) * p.pb < (1ull << 31) && static_cast<uint64_t>(nb) * 4 < (1ull << 31)) {
+		const uint64_t per_chunk_slots = static_cast<uint64_t>((p.pb + G - 1) / G) * G * n_chunks;
+		const uint64_t stripes = static_cast<uint64_t>(n_chunks) * p.pb;
+		const bool wasteful = per_chunk_slots * 100 > stripes * 112;
+		if (fs->striped == 1 || (fs->striped < 0 && wasteful)) p.flat = 2u;
+	}
+	const bool striped = p.flat == 2u;
 	uint64_t total;
-	if (flat) {
+	if (flat || striped) {
 		p.units_per_chunk = static_cast<uint32_t>((static_cast<uint64_t>(n_chunks) * p.pb + G - 1) / G);
 		total = p.units_per_chunk;
 	} else {
@@ -258,9 +281,28 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	CUtensorMap map;
 	const uint32_t rows = G * K * 4;
 	int rc = flat ? make_tensor_map(fs, &map, d_data, static_cast<uint64_t>(n_chunks) * nb * 4, 1, 0, rows)
-	              : make_tensor_map(fs, &map, d_data, static_cast<uint64_t>(nb) * 4, n_chunks, chunk_stride, rows);
+	              : make_tensor_map(fs, &map, d_data, static_cast<uint64_t>(nb) * 4, n_chunks, chunk_stride, striped ? K * 4 : rows);
 	if (rc) return rc;
 	const size_t smem = fused_smem_bytes(rows, G * PC * 4, fw);
+	if (striped) {
+		if (generic) return launch<4, true, 0, 0, 64, true>(ctx, map, p, smem, st);
+#define LZ_FOLDED_STRIPED(MM, KK, GG) \
+	if (M == MM && K == KK && G == GG) return launch<MM, false, KK, GG, 64, true>(ctx, map, p, smem, st);
+		LZ_FOLDED_STRIPED(2, 8, 8)
+		LZ_FOLDED_STRIPED(1, 2, 32)
+		LZ_FOLDED_STRIPED(1, 3, 20)
+		LZ_FOLDED_STRIPED(2, 3, 16)
+		LZ_FOLDED_STRIPED(3, 5, 8)
+		LZ_FOLDED_STRIPED(4, 8, 6)
+#undef LZ_FOLDED_STRIPED
+		switch (M) {
+			case 1: return launch<1, false, 0, 0, 64, true>(ctx, map, p, smem, st);
+			case 2: return launch<2, false, 0, 0, 64, true>(ctx, map, p, smem, st);
+			case 3: return launch<3, false, 0, 0, 64, true>(ctx, map, p, smem, st);
+			case 4: return launch<4, false, 0, 0, 64, true>(ctx, map, p, smem, st);
+		}
+		return LZGPU_NOT_HANDLED;
+	}
 	if (generic) return launch<4, true>(ctx, map, p, smem, st);
 #ifdef LZ_ENABLE_FOLD128
 	if (fw == 128) {

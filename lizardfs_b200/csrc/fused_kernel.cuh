@@ -230,6 +230,7 @@ __device__ __forceinline__ uint32_t fold_finish(uint32_t (&win)[FW], const uint3
 // GENERIC  false: Vandermonde rows 1, 2^j, 4^j, 8^j by Horner (row 0 = XOR; its CRC comes from linearity)
 //          true : arbitrary coefficient rows from p.coef (Cauchy generators); every parity CRC is computed
 // KT, GT   compile-time K and G (0 = runtime p.K / p.G); the hot configurations are fully constant-folded
+// STRIPED  units are runs of G global stripes loaded one stripe box at a time (ragged / small chunks, any stride)
 //
 // Pipeline control: there is no producer warp.  Every consumer warp, after its last read of a stage,
 // arrives on the stage's `empty` mbarrier; the arrival that completes the phase re-arms `full` and issues
@@ -243,7 +244,7 @@ __device__ __forceinline__ uint32_t fold_finish(uint32_t (&win)[FW], const uint3
 // Register budget: __launch_bounds__(288, 2) makes ptxas target 96 registers (2 CTAs/SM), (288, 1) -> 168.
 // (An explicit __maxnreg__(96) instead of the launch bounds produced a 5 % slower kernel on the same box: ptxas
 // schedules differently when it does not know the block size.)
-template <int M, bool GENERIC, int KT, int GT, int FW>
+template <int M, bool GENERIC, int KT, int GT, int FW, bool STRIPED = false>
 __global__ void __launch_bounds__(kFusedThreads, FW == 64 ? 2 : 1)
 fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
 	constexpr int kNST = fused_nst(FW), kNPST = fused_npst(FW);
@@ -284,6 +285,23 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 			            a_full + 8 * st);
 	};
 
+	// striped units: G consecutive GLOBAL stripes, one box per stripe (the tensor map's box is K*4 rows), so units run
+	// across chunk boundaries whatever nb and the chunk stride are; rows of blocks a tail stripe does not have lie
+	// outside the chunk's row extent and arrive as zeros.  Stripes past the end of the batch are not loaded.
+	// Called by one thread (prologue: first_g 0, g_step 1) or by a whole warp (refill: lane L issues stripes L, L+32, ...).
+	auto issue_striped = [&](uint32_t unit, uint32_t step, uint32_t st, uint32_t first_g, uint32_t g_step) {
+		const uint32_t s0 = unit * G;
+		const uint32_t n_valid = min(G, p.n_chunks * p.pb - s0);
+		const uint32_t stripe_bytes = K * 4 * kStepBytes;
+		if (first_g == 0) mbar_expect_tx(a_full + 8 * st, n_valid * stripe_bytes);
+		for (uint32_t g = first_g; g < n_valid; g += g_step) {
+			const uint32_t sg = s0 + g;
+			const uint32_t cc = static_cast<uint32_t>((static_cast<unsigned long long>(sg) * p.flat_magic) >> 40);
+			tma_load_3d(sbase + st * stage_bytes + g * stripe_bytes, &tmap, static_cast<int>(step * kStepBytes),
+			            static_cast<int>((sg - cc * p.pb) * K * 4), static_cast<int>(cc), a_full + 8 * st);
+		}
+	};
+
 	// global stripe index -> (chunk, stripe in chunk); in per-chunk mode the unit's chunk is passed through
 	auto locate = [&](uint32_t sg, uint32_t unit_c, uint32_t &c_out, uint32_t &s_out) {
 		if (p.flat) {
@@ -308,7 +326,10 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		if (total_steps)
-			for (uint32_t g0 = 0; g0 < kNST; ++g0) issue_load(blockIdx.x / p.units_per_chunk, blockIdx.x % p.units_per_chunk, g0, g0);
+			for (uint32_t g0 = 0; g0 < kNST; ++g0) {
+				if (STRIPED) issue_striped(blockIdx.x, g0, g0, 0, 1);
+				else issue_load(blockIdx.x / p.units_per_chunk, blockIdx.x % p.units_per_chunk, g0, g0);
+			}
 	}
 	__syncthreads();
 
@@ -417,7 +438,16 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 					fold_step<FW>(win, sub * 32, rowp);
 				}
 				__syncwarp();
-				if (lane == 0) {
+				if (STRIPED) {
+					// striped units: the warp whose arrival completes the phase issues the per-stripe boxes with all its lanes
+					uint32_t refill = 0;
+					if (lane == 0) refill = warp_reads_stage && mbar_arrive_is_last(a_empty + 8 * st) && it + kNST < total_steps;
+					if (__shfl_sync(0xffffffffu, refill, 0)) {
+						asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+						if (step + kNST < kStepsPerUnit) issue_striped(unit, step + kNST, st, lane, 32);
+						else issue_striped(next_unit, step + kNST - kStepsPerUnit, st, lane, 32);
+					}
+				} else if (lane == 0) {
 					// release the data stage; the arrival that completes the phase refills it with the step NST ahead
 					if (warp_reads_stage && mbar_arrive_is_last(a_empty + 8 * st) && it + kNST < total_steps) {
 						asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -76,6 +76,43 @@ def test_encode_many_small_chunks_flat_units(eng, oracle, text, nblocks, n_chunk
         assert (crc[c] == c_ref).all(), (text, c)
 
 
+@pytest.mark.parametrize("mode", ["0", "1"])
+@pytest.mark.parametrize("text,nblocks,n_chunks,stride_blocks", [
+    ("ec(8,2)", 13, 21, 13), ("ec(3,2)", 16, 40, 16), ("xor3", 7, 33, 9), ("ec(5,3)", 11, 17, 11), ("xor2", 5, 9, 5), ("ec(8,4)", 19, 7, 24),
+    ("ec(22,4)", 30, 5, 30), ("ec(4,2)", 9, 12, 9), ("xor9", 10, 10, 10), ("ec(3,2)", 1, 50, 1)])
+def test_encode_ragged_chunks_striped_and_per_chunk_units(oracle, mode, text, nblocks, n_chunks, stride_blocks):
+    """Ragged small chunks (nb not a multiple of k, padded strides): 'striped' units — runs of global stripes loaded one
+    stripe box at a time, crossing chunk boundaries — and per-chunk units must both give every chunk exactly its own parity
+    and CRCs (tail stripes see absent blocks as zeros; units that end past the batch load nothing for the missing stripes)."""
+    os.environ["LZGPU_STRIPED"] = mode
+    try:
+        e = L.Engine()
+    finally:
+        del os.environ["LZGPU_STRIPED"]
+    goal = L.SliceType(text)
+    data = rnd((n_chunks, stride_blocks * BLOCK), (hash(text) ^ nblocks) & 0xffff)
+    parity, crc = e.encode_chunks(goal, data, chunk_len=nblocks * BLOCK)
+    refs = [oracle.encode_chunk(goal.kind, goal.k, goal.m, data[c, : nblocks * BLOCK]) for c in range(n_chunks)]
+    for c in range(n_chunks):
+        assert (parity[c] == refs[c][0]).all(), (text, c)
+        assert (crc[c] == refs[c][1]).all(), (text, c)
+    if stride_blocks != nblocks:
+        # device-resident chunks with a padded stride (the host entry point stages chunks densely, this one does not)
+        pb = -(-nblocks // goal.k)
+        n_crc = nblocks + goal.m * pb
+        d_data = e.dev_alloc(data.size)
+        d_par = e.dev_alloc(n_chunks * goal.m * pb * BLOCK)
+        d_crc = e.dev_alloc(n_chunks * n_crc * 4)
+        e.upload(d_data, data)
+        e.encode_chunks_dev(goal, n_chunks, nblocks * BLOCK, d_data, stride_blocks * BLOCK, d_par, goal.m * pb * BLOCK, d_crc, n_crc)
+        e.sync()
+        par2 = e.download(d_par, n_chunks * goal.m * pb * BLOCK).reshape(n_chunks, goal.m, pb * BLOCK)
+        crc2 = e.download(d_crc, n_chunks * n_crc * 4, dtype=np.uint32).reshape(n_chunks, n_crc)
+        assert (par2 == parity).all() and (crc2 == crc).all()
+        for ptr in (d_data, d_par, d_crc):
+            e.dev_free(ptr)
+
+
 def test_encode_and_recover_every_goal_shape(eng, oracle):
     """Every ec(k, m <= 4) for k = 2..32, a few m >= 5 (generic route) and xor2..9: stripe-group geometry, mixed
     data/parity warps, the Cauchy switch (m = 4, k > 20) and ragged last stripes all go through here."""

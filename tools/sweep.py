@@ -144,7 +144,61 @@ def main():
             if i < k:
                 assert torch.equal(outs[i].view(n, pb, BLOCK), parts[i]), (text, i)
         assert torch.equal(img.view(n, nb, BLOCK), chunks)
+        if text == "ec(8,2)" and lost == (1, 4) or args.quick:
+            conv_src = (g, n, nb, pb, dp, dc)
+            conv_keep = (parts, pcrc)
         del parts, pcrc, outs, img, d_par, d_crc
+
+    # ---- replication: slice-type conversion (SliceRecoveryPlanner) --------------------------------------------------
+    lines += ["", "## slice-type conversion for replication (source CRCs verified, destination block CRCs produced)", "",
+              "| source | destination parts | chunks/launch | ms | GiB/s chunk data |", "|---|---|---|---|---|"]
+    g, n, nb, pb, dp, dc = conv_src
+    for dst_text, want_parts in [("ec(3,2)", "all"), ("ec(3,2)", "one parity"), ("std", "all"), ("xor3", "all")]:
+        d = L.SliceType(dst_text)
+        nd = d.k + d.m
+        pbd = (nb + d.k - 1) // d.k
+        want = [1] * nd if want_parts == "all" else [0] * (nd - 1) + [1]
+        outs = [torch.empty((n, pbd * BLOCK), dtype=torch.uint8, device=dev) if want[i] else None for i in range(nd)]
+        ocrc = [torch.empty((n, pbd), dtype=torch.int32, device=dev) if want[i] else None for i in range(nd)]
+        ms = time_steps(lambda: eng.convert_chunks_dev(g, d, n, nb, dp, pb * BLOCK, want, [o.data_ptr() if o is not None else 0 for o in outs], pbd * BLOCK,
+                                                       d_part_crc=dc, d_out_crc=[o.data_ptr() if o is not None else 0 for o in ocrc], stream=sp),
+                        args.steps, args.warmup, stream)
+        lines.append(f"| ec(8,2), data parts 1 and 4 lost | {dst_text}: {want_parts} | {n} | {ms:.3f} | {n * clen / GIB / (ms / 1e3):.0f} |")
+        torch.cuda.synchronize()
+        if dst_text == "std":
+            assert torch.equal(outs[0].view(n, nb, BLOCK), chunks)
+        del outs, ocrc
+    del conv_keep
+
+    # ---- chunkserver block writes (hdd_write) -------------------------------------------------------------------------
+    lines += ["", "## batched chunkserver block writes (packet CRC check + stored-block check + new CRC)", "",
+              "| requests | bytes per request | ms | requests/s | GB/s of stored blocks read |", "|---|---|---|---|---|"]
+    import ctypes as C
+    import zlib
+    import numpy as np
+    from lizardfs_b200 import _lib
+    nreq = 16384
+    for size in (4096, 65535):
+        blocks = d_data[: nreq * BLOCK]
+        crc_t = torch.empty(nreq, dtype=torch.int32, device=dev)
+        eng.crc_blocks_dev(blocks.data_ptr(), nreq, crc_t.data_ptr(), stream=sp)
+        payload_h = np.random.default_rng(1).integers(0, 256, size, dtype=np.uint8)
+        pcrc = zlib.crc32(payload_h.tobytes())
+        payload = torch.from_numpy(payload_h).to(dev)
+        arr = (_lib.LzBlockWrite * nreq)()
+        for i in range(nreq):
+            arr[i].block, arr[i].offset, arr[i].size, arr[i].crc, arr[i].payload_off, arr[i].exists = i, (i * 37) % (BLOCK - size + 1), size, pcrc, 0, 1
+        d_wr = torch.empty(C.sizeof(arr), dtype=torch.uint8, device=dev)
+        d_wr.copy_(torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8))
+        torch.cuda.synchronize()
+        # every launch re-applies the same payload: the first one changes the blocks, later ones find them already patched (the stored
+        # CRC was updated by the first), so each timed launch does the full read-check-update work
+        ms = time_steps(lambda: _lib.load().lzgpu_write_blocks_dev(eng.h, blocks.data_ptr(), crc_t.data_ptr(), payload.data_ptr(), d_wr.data_ptr(), nreq, 1,
+                                                                  sp), args.steps, args.warmup, stream)
+        st = np.frombuffer(d_wr.cpu().numpy().tobytes(), dtype=np.int32).reshape(nreq, 8)[:, 7]
+        assert (st == 0).all(), st[:8]
+        lines.append(f"| {nreq} | {size} | {ms:.3f} | {nreq / (ms / 1e3):.3g} | {nreq * BLOCK / (ms / 1e3) / 1e9:.0f} |")
+    eng.fill_chunks_dev(d_data.data_ptr(), args.bytes // (64 << 20), 64 << 20, 64 << 20, seed=12345, stream=sp)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     open(args.out, "w").write("\n".join(lines) + "\n")
     print("\n".join(lines))
