@@ -22,6 +22,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 constexpr int kSmemCap = 113 * 1024;
 constexpr int kSmemCap128 = 226 * 1024;       // FW = 128 variant: one CTA per SM
 constexpr int kRecoverSmemCap = 200 * 1024;  // recover kernel: one CTA per SM, 6 stages
+constexpr int kRecoverSmemCap2 = 100 * 1024; // two CTAs per SM, 3 stages (E <= 2)
 
 struct FusedState {
 	EncodeTiledFn encode_tiled = nullptr;
@@ -32,7 +33,8 @@ struct FusedState {
 	uint32_t probe = 0;
 	uint32_t *d_sm_ctr = nullptr;
 	int evict_first = 0;
-	int striped = -1;  // LZGPU_STRIPED: -1 automatic, 0 never, 1 whenever the shape allows
+	int striped = -1;
+	int recover_two = -1;  // LZGPU_RECOVER_TWO: -1 automatic, 0 one CTA per SM (6 stages), 1 two CTAs (3 stages) for e <= 2  // LZGPU_STRIPED: -1 automatic, 0 never, 1 whenever the shape allows
 	int promo = 3;  // CU_TENSOR_MAP_L2_PROMOTION_L2_256B: +12% streaming bandwidth over 128B/none (profiles/probe_r1.md)
 };
 
@@ -58,6 +60,7 @@ static int set_smem_attr(int bytes) {
 template <int E, int KT, int R0 = -1, int R1 = -1>
 static int set_recover_attr() {
 	CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<E, KT, R0, R1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCap));
+	if constexpr (E <= 2) CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<E, KT, R0, R1, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCap2));
 #ifdef LZ_ENABLE_FOLD128
 	CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<E, KT, R0, R1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCap));
 #endif
@@ -87,6 +90,7 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if (const char *e = std::getenv("LZGPU_PROBE")) fs->probe = static_cast<uint32_t>(std::atoi(e));
 	if (const char *e = std::getenv("LZGPU_L2_PROMO")) fs->promo = std::atoi(e);
 	if (const char *e = std::getenv("LZGPU_EVICT_FIRST")) fs->evict_first = std::atoi(e);
+	if (const char *e = std::getenv("LZGPU_RECOVER_TWO")) fs->recover_two = std::atoi(e);
 	if (const char *e = std::getenv("LZGPU_STRIPED")) fs->striped = std::atoi(e);  // 0 never, 1 whenever possible, unset = automatic
 	void *fn = nullptr;
 	cudaDriverEntryPointQueryResult qres;
@@ -376,7 +380,14 @@ int lz_fused_crc(lzgpu_ctx *ctx, const void *base, unsigned long long n_blocks, 
 // fused degraded read
 // ---------------------------------------------------------------------------------------------------
 template <int E, int KT, int R0 = -1, int R1 = -1>
-static int launch_recover(lzgpu_ctx *ctx, const TmapArray &maps, const RecoverParams &p, size_t smem, cudaStream_t st) {
+static int launch_recover(lzgpu_ctx *ctx, const TmapArray &maps, const RecoverParams &p, size_t smem, cudaStream_t st, bool two) {
+	if (two && E <= 2) {
+		const int grid2 = static_cast<int>(std::min<uint64_t>(p.total_units, static_cast<uint64_t>(ctx->sm_count) * 2));
+		fused_recover_kernel<(E <= 2 ? E : 1), KT, R0, R1, 64, true><<<grid2, kFusedThreads, smem, st>>>(maps, p);
+		CUDA_TRY(cudaGetLastError());
+		ctx->stats.kernel_launches++;
+		return LZGPU_OK;
+	}
 	const int grid = static_cast<int>(std::min<uint64_t>(p.total_units, static_cast<uint64_t>(ctx->sm_count)));
 #ifdef LZ_ENABLE_FOLD128
 	if (ctx->fused->fold == 128) fused_recover_kernel<E, KT, R0, R1, 128><<<grid, kFusedThreads, smem, st>>>(maps, p);
@@ -422,10 +433,18 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 	for (int i = K; i < N; ++i)
 		if (want[i] && !d_parts[i] && d_out && d_out[i]) return LZGPU_NOT_HANDLED;
 	// geometry: even G (1024-byte aligned slot regions), K*G*4 rows <= 256
+	// Two CTAs per SM with a 3-stage ring, or one CTA with 6 stages?  Measured on the same box (64 MiB chunks, fraction of
+	// the HBM copy peak, two / one):  ec(3,2) 2 lost 0.48 / 0.42 (+image 0.64 / 0.58),  xor3 1 lost 0.93 / 0.70 (+image
+	// 0.73 / 0.77),  ec(8,2) 2 lost 0.66 / 0.70 (+image 0.72 / 0.78),  ec(8,2) 1 lost 0.94 / 0.99.  So: the runtime-k
+	// shapes, except the single-erasure case that also writes the image.  LZGPU_RECOVER_TWO=0|1 forces either.
+	const bool two_auto = K != 8 && (e == 2 || (e == 1 && !d_chunk_out));
+	const bool two = e <= 2 && (fs->recover_two < 0 ? two_auto : fs->recover_two != 0);
+	const int n_stages = recover_stages(two);
+	const size_t smem_cap = two ? kRecoverSmemCap2 : kRecoverSmemCap;
 	uint32_t G = 0;
 	for (uint32_t g = 2; g <= 64; g += 2) {
 		const uint32_t rows = K * g * 4;
-		if (rows > kMaxRows || static_cast<size_t>(kRecoverStages) * rows * kStepBytes + 256 > static_cast<size_t>(kRecoverSmemCap)) break;
+		if (rows > kMaxRows || static_cast<size_t>(n_stages) * rows * kStepBytes + 256 > smem_cap) break;
 		G = g;
 	}
 	if (G == 0) return LZGPU_NOT_HANDLED;
@@ -496,21 +515,21 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 		static const unsigned long long kNone = ~0ull;
 		CUDA_TRY(cudaMemcpyAsync(ctx->d_first_bad, &kNone, sizeof(kNone), cudaMemcpyHostToDevice, st));
 	}
-	const size_t smem = static_cast<size_t>(kRecoverStages) * K * G * 4 * kStepBytes + 16 * kRecoverStages + 64;
+	const size_t smem = static_cast<size_t>(n_stages) * K * G * 4 * kStepBytes + 16 * n_stages + 64;
 	const bool k8 = K == 8 && G == 8;
 	const bool row0 = p.par_row[0] == 0, row01 = row0 && e >= 2 && p.par_row[1] == 1;
 	switch (e) {
 		case 1:
-			if (row0) return k8 ? launch_recover<1, 8, 0>(ctx, maps, p, smem, st) : launch_recover<1, 0, 0>(ctx, maps, p, smem, st);
-			return launch_recover<1, 0>(ctx, maps, p, smem, st);
+			if (row0) return k8 ? launch_recover<1, 8, 0>(ctx, maps, p, smem, st, two) : launch_recover<1, 0, 0>(ctx, maps, p, smem, st, two);
+			return launch_recover<1, 0>(ctx, maps, p, smem, st, two);
 		case 2:
-			if (row01) return k8 ? launch_recover<2, 8, 0, 1>(ctx, maps, p, smem, st) : launch_recover<2, 0, 0, 1>(ctx, maps, p, smem, st);
-			return launch_recover<2, 0>(ctx, maps, p, smem, st);
+			if (row01) return k8 ? launch_recover<2, 8, 0, 1>(ctx, maps, p, smem, st, two) : launch_recover<2, 0, 0, 1>(ctx, maps, p, smem, st, two);
+			return launch_recover<2, 0>(ctx, maps, p, smem, st, two);
 		case 3:
-			if (row01) return launch_recover<3, 0, 0, 1>(ctx, maps, p, smem, st);
-			return launch_recover<3, 0>(ctx, maps, p, smem, st);
+			if (row01) return launch_recover<3, 0, 0, 1>(ctx, maps, p, smem, st, two);
+			return launch_recover<3, 0>(ctx, maps, p, smem, st, two);
 		default:
-			if (row01) return launch_recover<4, 0, 0, 1>(ctx, maps, p, smem, st);
-			return launch_recover<4, 0>(ctx, maps, p, smem, st);
+			if (row01) return launch_recover<4, 0, 0, 1>(ctx, maps, p, smem, st, two);
+			return launch_recover<4, 0>(ctx, maps, p, smem, st, two);
 	}
 }

@@ -546,11 +546,14 @@ struct RecoverParams {
 // get constant doubling counts and the "last unknown = S0 ^ others" shortcut.
 // One CTA per SM (the solve needs registers: no spills at <= 224 per thread) with a deeper stage ring instead;
 // that also leaves room for the 128-word fold window (3 LOP3 per word).
-constexpr int kRecoverStages = 6;
+// TWO = two CTAs per SM with a 3-stage ring (96 registers) instead of one CTA with 6 stages: the cheap solves (E <= 2) are
+// latency bound at 9 warps per SM, the second CTA hides it.
+__host__ __device__ constexpr int recover_stages(bool two) { return two ? 3 : 6; }
 
-template <int E, int KT, int R0, int R1, int kRecoverFW>
-__global__ void __launch_bounds__(kFusedThreads, 1)
+template <int E, int KT, int R0, int R1, int kRecoverFW, bool TWO = false>
+__global__ void __launch_bounds__(kFusedThreads, TWO ? 2 : 1)
 fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_constant__ RecoverParams p) {
+	constexpr int kRecoverStages = recover_stages(TWO);
 	extern __shared__ __align__(1024) uint8_t smem[];
 	const uint32_t sbase = smem_u32(smem);
 	const uint32_t K = KT ? KT : p.K, G = p.G;

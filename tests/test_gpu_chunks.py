@@ -291,6 +291,44 @@ def test_recover_all_patterns(eng, oracle, text, nblocks):
             assert (out[i][0] == o_ref[i]).all()
 
 
+@pytest.mark.parametrize("two", ["0", "1"])
+@pytest.mark.parametrize("text,nblocks,lost", [("ec(8,2)", 40, (1, 4)), ("ec(8,2)", 40, (6,)), ("ec(3,2)", 31, (0, 2)), ("xor3", 22, (1,)), ("ec(5,3)", 23, (3,)), ("ec(6,2)", 30, (0, 5))])
+def test_recover_one_and_two_ctas_per_sm(oracle, two, text, nblocks, lost):
+    """both geometries of the degraded-read kernel (one CTA per SM with 6 stages, two with 3) give the reference's bytes,
+    with and without CRC verification and the chunk-order image"""
+    os.environ["LZGPU_RECOVER_TWO"] = two
+    try:
+        e = L.Engine()
+    finally:
+        del os.environ["LZGPU_RECOVER_TWO"]
+    goal = L.SliceType(text)
+    k, m = goal.k, goal.m
+    data = rnd((5, nblocks * BLOCK), 77)
+    parity, crc = e.encode_chunks(goal, data)
+    parts = all_parts(data, parity, k)
+    pb = parts[0].shape[1] // BLOCK
+    part_crc = []
+    for j in range(k):
+        c = np.full((5, pb), 0xD7978EEB, dtype=np.uint32)
+        mine = crc[:, j:nblocks:k]
+        c[:, : mine.shape[1]] = mine
+        part_crc.append(c)
+    for r in range(m):
+        part_crc.append(np.ascontiguousarray(crc[:, nblocks + r * pb: nblocks + (r + 1) * pb]))
+    avail = [None if i in lost else parts[i] for i in range(k + m)]
+    acrc = [None if i in lost else part_crc[i] for i in range(k + m)]
+    want = [1 if i in lost else 0 for i in range(k + m)]
+    for crcs, image in [(None, False), (acrc, True), (acrc, False), (None, True)]:
+        out, img = e.recover_chunks(goal, nblocks, avail, part_crc=crcs, want=want, chunk_image=image)
+        for i in lost:
+            assert (out[i] == parts[i]).all(), (text, lost, i)
+        if image:
+            assert (img == data).all()
+    rc, o_ref, _ = oracle.recover_chunk(goal.kind, k, m, [None if a is None else a[2] for a in avail], None, want, pb)
+    for i in lost:
+        assert (out[i][2] == o_ref[i]).all()
+
+
 def test_recover_verifies_crc(eng):
     goal = L.SliceType("ec(8,2)")
     nblocks = 24
