@@ -21,7 +21,15 @@ __device__ __forceinline__ uint32_t gf_x2(uint32_t v) {
 	const uint32_t hi = v & 0x80808080u;
 	// (hi >> 7) * 0x1d without the shift: hi * 0x1d is a multiple of 128, so the high half of
 	// hi * (0x1d << 25) is exactly (hi * 0x1d) >> 7  (one IMAD.HI on the otherwise idle FMA pipe)
+#ifndef LZ_X2_ON_FMA
 	return ((v ^ hi) << 1) ^ __umulhi(hi, 0x3A000000u);
+#else
+	// diagnostics: (v - hi) * 2 = v*2 + hi*(-2), the byte-lane shift as two IMADs too.  Measured slower where gf_x2 is used
+	// (rows 2, 3): ec(8,4) 0.386 -> 0.355 of peak — the IMAD count then matches the LOP3 count and the FMA pipe binds.
+	uint32_t dbl;
+	asm("{\n\t.reg .u32 t;\n\tmul.lo.u32 t, %1, 2;\n\tmad.lo.u32 %0, %2, 0xFFFFFFFE, t;\n\t}" : "=r"(dbl) : "r"(v), "r"(hi));
+	return dbl ^ __umulhi(hi, 0x3A000000u);
+#endif
 }
 
 // acc*2 + d with the byte-lane doubling done on the FMA pipe: (v - hi)*2 = v*2 + hi*(-2) (two IMADs),
