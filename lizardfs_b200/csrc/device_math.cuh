@@ -47,6 +47,33 @@ __device__ __forceinline__ uint32_t gf_x2_add(uint32_t v, uint32_t d) {
 #endif
 }
 
+// acc*4 + d and acc*8 + d in one step (generator rows 2 and 3: Horner with 4^j, 8^j).  The bits shifted out are reduced with
+// x^8 = 0x1d, x^9 = 0x3a, x^10 = 0x74: one mask + one IMAD.HI each ((hi7 >> 7) * 0x3a = umulhi(hi7, 0x3a << 25), and so on —
+// the constants come out as 0x74000000 for x4 and 0xE8000000 for x8); the lane shift is (v - hi) * 4 = v*4 + hi*(-4) on the FMA pipe.
+// ALU ops per word: 5 (x4) and 6 (x8) instead of 6 and 10 for chained doublings, same number of FMA-pipe ops.
+#ifndef LZ_CHAINED_DOUBLINGS
+__device__ __forceinline__ uint32_t gf_x4_add(uint32_t v, uint32_t d) {
+	const uint32_t hi = v & 0xC0C0C0C0u;
+	uint32_t lo;
+	asm("{\n\t.reg .u32 t;\n\tmul.lo.u32 t, %1, 4;\n\tmad.lo.u32 %0, %2, 0xFFFFFFFC, t;\n\t}" : "=r"(lo) : "r"(v), "r"(hi));
+	const uint32_t r7 = __umulhi(v & 0x80808080u, 0x74000000u);  // bit 7 -> x^9  = 0x3a
+	const uint32_t r6 = __umulhi(v & 0x40404040u, 0x74000000u);  // bit 6 -> x^8  = 0x1d
+	return (lo ^ r7) ^ (r6 ^ d);
+}
+__device__ __forceinline__ uint32_t gf_x8_add(uint32_t v, uint32_t d) {
+	const uint32_t hi = v & 0xE0E0E0E0u;
+	uint32_t lo;
+	asm("{\n\t.reg .u32 t;\n\tmul.lo.u32 t, %1, 8;\n\tmad.lo.u32 %0, %2, 0xFFFFFFF8, t;\n\t}" : "=r"(lo) : "r"(v), "r"(hi));
+	const uint32_t r7 = __umulhi(v & 0x80808080u, 0xE8000000u);  // bit 7 -> x^10 = 0x74
+	const uint32_t r6 = __umulhi(v & 0x40404040u, 0xE8000000u);  // bit 6 -> x^9  = 0x3a
+	const uint32_t r5 = __umulhi(v & 0x20202020u, 0xE8000000u);  // bit 5 -> x^8  = 0x1d
+	return (lo ^ r7 ^ r6) ^ (r5 ^ d);
+}
+#else
+__device__ __forceinline__ uint32_t gf_x4_add(uint32_t v, uint32_t d) { return gf_x2_add(gf_x2(v), d); }
+__device__ __forceinline__ uint32_t gf_x8_add(uint32_t v, uint32_t d) { return gf_x2_add(gf_x2(gf_x2(v)), d); }
+#endif
+
 // One coefficient prepared for the bit-plane product: plane[b] = c * 2^b in GF(2^8), each stored
 // in a 32-bit word so that  c*v = XOR_b ((v >> b) & 0x01010101) * plane[b]  — every partial
 // product stays inside its byte lane (a 0/1 byte times an 8-bit constant), hence no carries.

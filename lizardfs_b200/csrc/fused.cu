@@ -126,7 +126,7 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if ((rc = set_smem_attr<1, false, 3, 20, 64, true>(smem))) return rc;
 	if ((rc = set_smem_attr<2, false, 3, 16, 64, true>(smem))) return rc;
 	if ((rc = set_smem_attr<3, false, 5, 8, 64, true>(smem))) return rc;
-	if ((rc = set_smem_attr<4, false, 8, 6, 64, true>(smem))) return rc;
+	if ((rc = set_smem_attr<4, false, 8, 5, 64, true>(smem))) return rc;
 	if ((rc = set_smem_attr<2, false, 8, 8>(smem))) return rc;
 	if ((rc = set_smem_attr<1, false, 2, 32>(smem))) return rc;
 	if ((rc = set_smem_attr<1, false, 3, 20>(smem))) return rc;
@@ -135,7 +135,7 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if ((rc = set_smem_attr<2, false, 6, 10>(smem))) return rc;
 	if ((rc = set_smem_attr<3, false, 5, 8>(smem))) return rc;
 	if ((rc = set_smem_attr<3, false, 6, 8>(smem))) return rc;
-	if ((rc = set_smem_attr<4, false, 8, 6>(smem))) return rc;
+	if ((rc = set_smem_attr<4, false, 8, 5>(smem))) return rc;
 #ifdef LZ_ENABLE_FOLD128
 	const int smem128 = std::min(fs->max_smem, kSmemCap128);
 	if ((rc = set_smem_attr<0, false, 0, 0, 128>(smem128))) return rc;
@@ -144,7 +144,7 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if ((rc = set_smem_attr<3, false, 0, 0, 128>(smem128))) return rc;
 	if ((rc = set_smem_attr<4, false, 0, 0, 128>(smem128))) return rc;
 	if ((rc = set_smem_attr<2, false, 8, 8, 128>(smem128))) return rc;
-	if ((rc = set_smem_attr<4, false, 8, 6, 128>(smem128))) return rc;
+	if ((rc = set_smem_attr<4, false, 8, 5, 128>(smem128))) return rc;
 	if ((rc = set_smem_attr<3, false, 5, 8, 128>(smem128))) return rc;
 #endif
 	if ((rc = set_all_recover_attrs())) return rc;
@@ -165,11 +165,11 @@ static size_t fused_smem_bytes(uint32_t rows, uint32_t prows, int fw) {
 
 // Largest stripe group G such that data + parity-CRC rows fit the consumer threads, the data rows fit
 // one TMA box (<= 256 rows, a multiple of 8 for the 1024-byte stage alignment) and the stages fit shared memory.
-static uint32_t pick_group(uint32_t K, uint32_t PC, int max_smem_per_cta, int fw) {
+static uint32_t pick_group(uint32_t K, uint32_t PC, int max_smem_per_cta, int fw, uint32_t threads) {
 	uint32_t best = 0;
 	for (uint32_t g = 1; g <= 64; ++g) {
 		const uint32_t rows = g * K * 4, prows = g * PC * 4;
-		if (rows > kMaxRows || rows + prows > kConsumers || prows > kMaxParityRows || g * K > 64) break;
+		if (rows > kMaxRows || rows + prows > threads || prows > kMaxParityRows || g * K > 64) break;
 		if (rows % 8) continue;
 		if (fused_smem_bytes(rows, prows, fw) > static_cast<size_t>(max_smem_per_cta)) break;
 		best = g;
@@ -199,7 +199,7 @@ template <int M, bool GENERIC, int KT = 0, int GT = 0, int FW = 64, bool STRIPED
 static int launch(lzgpu_ctx *ctx, const CUtensorMap &map, const FusedParams &p, size_t smem, cudaStream_t st) {
 	const int per_sm = FW == 64 ? 2 : 1;
 	const int grid = static_cast<int>(std::min<uint64_t>(p.total_units, static_cast<uint64_t>(ctx->sm_count) * per_sm));
-	fused_stream_kernel<M, GENERIC, KT, GT, FW, STRIPED><<<grid, kFusedThreads, smem, st>>>(map, p);
+	fused_stream_kernel<M, GENERIC, KT, GT, FW, STRIPED><<<grid, fused_threads(M), smem, st>>>(map, p);
 	CUDA_TRY(cudaGetLastError());
 	ctx->stats.kernel_launches++;
 	return LZGPU_OK;
@@ -228,7 +228,7 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	const uint32_t PC = M == 0 ? 0 : (generic ? M : M - 1);
 	const int fw = choose_fold(fs, M, generic);
 	const int smem_cap = std::min(fs->max_smem, fw == 64 ? kSmemCap : kSmemCap128);
-	const uint32_t G = pick_group(K, PC, smem_cap, fw);
+	const uint32_t G = pick_group(K, PC, smem_cap, fw, static_cast<uint32_t>(fused_threads(generic ? 4 : M)));
 	if (G == 0) return LZGPU_NOT_HANDLED;
 	if ((chunk_stride % 16) || (reinterpret_cast<uintptr_t>(d_data) % 16)) return LZGPU_NOT_HANDLED;
 	FusedParams p{};
@@ -297,7 +297,7 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 		LZ_FOLDED_STRIPED(1, 3, 20)
 		LZ_FOLDED_STRIPED(2, 3, 16)
 		LZ_FOLDED_STRIPED(3, 5, 8)
-		LZ_FOLDED_STRIPED(4, 8, 6)
+		LZ_FOLDED_STRIPED(4, 8, 5)
 #undef LZ_FOLDED_STRIPED
 		switch (M) {
 			case 1: return launch<1, false, 0, 0, 64, true>(ctx, map, p, smem, st);
@@ -311,7 +311,7 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 #ifdef LZ_ENABLE_FOLD128
 	if (fw == 128) {
 		if (M == 2 && K == 8 && G == 8) return launch<2, false, 8, 8, 128>(ctx, map, p, smem, st);
-		if (M == 4 && K == 8 && G == 6) return launch<4, false, 8, 6, 128>(ctx, map, p, smem, st);
+		if (M == 4 && K == 8 && G == 5) return launch<4, false, 8, 5, 128>(ctx, map, p, smem, st);
 		if (M == 3 && K == 5 && G == 8) return launch<3, false, 5, 8, 128>(ctx, map, p, smem, st);
 		switch (M) {
 			case 0: return launch<0, false, 0, 0, 128>(ctx, map, p, smem, st);
@@ -334,7 +334,7 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	LZ_FOLDED(2, 6, 10)   // ec(6,2)
 	LZ_FOLDED(3, 5, 8)    // ec(5,3)
 	LZ_FOLDED(3, 6, 8)    // ec(6,3)
-	LZ_FOLDED(4, 8, 6)    // ec(8,4)
+	LZ_FOLDED(4, 8, 5)    // ec(8,4)
 #undef LZ_FOLDED
 	switch (M) {
 		case 0: return launch<0, false>(ctx, map, p, smem, st);

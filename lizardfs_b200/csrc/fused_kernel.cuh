@@ -63,6 +63,10 @@ constexpr int kRowBytes = 16384;
 constexpr int kStepsPerUnit = kRowBytes / kStepBytes;  // 128
 constexpr int kConsumers = 288;                        // 9 warps, all consumers (2 CTAs/SM -> 112 registers per thread)
 constexpr int kFusedThreads = kConsumers;
+// Three or four parity rows keep 12-16 Horner accumulators live next to the 64-word CRC window: at 96 registers the kernel
+// spills into its inner loop (ncu: long-scoreboard stalls on the local loads, profiles/ec84_r1_ncu_summary.md).  Those
+// shapes run with 8 warps instead of 9, which lets two CTAs per SM have 128 registers per thread.
+__host__ __device__ constexpr int fused_threads(int m) { return m >= 3 ? 256 : kConsumers; }
 constexpr int kMaxRows = 256;                          // TMA box limit per dimension
 // pipeline depth by fold window: FW = 64 -> 2 CTAs/SM (96 registers), 3 data stages + 4-deep parity ring;
 // FW = 128 -> 1 CTA/SM (the 128-word window needs ~170 registers), 6 data stages + 6-deep parity ring
@@ -245,9 +249,10 @@ __device__ __forceinline__ uint32_t fold_finish(uint32_t (&win)[FW], const uint3
 // (An explicit __maxnreg__(96) instead of the launch bounds produced a 5 % slower kernel on the same box: ptxas
 // schedules differently when it does not know the block size.)
 template <int M, bool GENERIC, int KT, int GT, int FW, bool STRIPED = false>
-__global__ void __launch_bounds__(kFusedThreads, FW == 64 ? 2 : 1)
+__global__ void __launch_bounds__(fused_threads(M), FW == 64 ? 2 : 1)
 fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
 	constexpr int kNST = fused_nst(FW), kNPST = fused_npst(FW);
+	constexpr int NT = fused_threads(M);
 	constexpr int PC = (M == 0) ? 0 : (GENERIC ? M : M - 1);  // parity parts whose CRC is computed from bytes
 	constexpr int P0 = GENERIC ? 0 : 1;                       // first such parity part
 
@@ -266,7 +271,7 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 	const uint32_t tid = threadIdx.x;
 	const uint32_t warp = tid >> 5, lane = tid & 31;
 	const uint32_t n_items = 32 * G * (M > 0 ? 1 : 0);
-	const uint32_t n_gf_warps = (min(n_items, (uint32_t)kConsumers) + 31) / 32;
+	const uint32_t n_gf_warps = (min(n_items, (uint32_t)NT) + 31) / 32;
 	const uint32_t first_pwarp = ROWS / 32, last_pwarp = PROWS ? (ROWS + PROWS - 1) / 32 : 0;
 	// warps that read the TMA data stages (data streams or GF items); pure parity-CRC warps do not gate the refill
 	const uint32_t n_stage_warps = max((ROWS + 31) / 32, n_gf_warps);
@@ -373,7 +378,7 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 				// ---------------- GF role ----------------
 				if (M > 0 && warp_has_items && !LZ_PROBE(2)) {
 					if (PC > 0) mbar_wait(a_pempty + 8 * pst, pph ^ 1);
-					for (uint32_t item = vt; item < n_items; item += kConsumers) {
+					for (uint32_t item = vt; item < n_items; item += NT) {
 						const uint32_t col = item & 7, q = (item >> 3) & 3, g = item >> 5;
 						uint32_t acc[M > 0 ? M : 1][4];
 #pragma unroll
@@ -401,9 +406,8 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 									for (int w = 0; w < 4; ++w) {
 										uint32_t a = acc[r][w];
 										const uint32_t d = (w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w);
-#pragma unroll
-										for (int t = 0; t + 1 < r; ++t) a = gf_x2(a);  // times 2^r ...
-										acc[r][w] = r == 0 ? (a ^ d) : gf_x2_add(a, d);   // ... the last doubling fused with + d_j
+										// Horner step acc*2^r + d_j, the multiplication by 2, 4 or 8 done in one go
+										acc[r][w] = r == 0 ? (a ^ d) : r == 1 ? gf_x2_add(a, d) : r == 2 ? gf_x4_add(a, d) : gf_x8_add(a, d);
 									}
 								}
 							}
@@ -487,7 +491,7 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 		}
 		if (M > 0 && !GENERIC) {
 			// CRC of parity row 0 (plain XOR of the stripe): xor of the data blocks' linear CRCs
-			asm volatile("bar.sync 1, %0;" ::"r"(kConsumers) : "memory");
+			asm volatile("bar.sync 1, %0;" ::"r"(NT) : "memory");
 			if (vt < G) {
 				uint32_t x = 0;
 				for (uint32_t j = 0; j < K; ++j) {
