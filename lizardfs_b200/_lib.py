@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblzgpu.so")
+# LZGPU_LIB=<path> loads an experiment build of the same ABI instead (A/B runs on one box; see csrc/Makefile)
+LIB_PATH = os.environ.get("LZGPU_LIB") or os.path.join(_HERE, "liblzgpu.so")
 
 OK = 0
 ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_CRC, ERR_TOO_FEW_PARTS, ERR_NO_DEVICE, ERR_DAMAGED = -1, -2, -3, -4, -5, -6, -7
