@@ -33,7 +33,6 @@ struct FusedState {
 	uint32_t probe = 0;
 	uint32_t *d_sm_ctr = nullptr;
 	int evict_first = 0;
-	int rot_warps = 0;  // LZGPU_ROTATE (experiment build only)
 	int striped = -1;
 	int recover_two = -1;  // LZGPU_RECOVER_TWO: -1 automatic, 0 one CTA per SM (6 stages), 1 two CTAs (3 stages) for e <= 2  // LZGPU_STRIPED: -1 automatic, 0 never, 1 whenever the shape allows
 	int promo = 3;  // CU_TENSOR_MAP_L2_PROMOTION_L2_256B: +12% streaming bandwidth over 128B/none (profiles/probe_r1.md)
@@ -92,7 +91,6 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if (const char *e = std::getenv("LZGPU_L2_PROMO")) fs->promo = std::atoi(e);
 	if (const char *e = std::getenv("LZGPU_EVICT_FIRST")) fs->evict_first = std::atoi(e);
 	if (const char *e = std::getenv("LZGPU_RECOVER_TWO")) fs->recover_two = std::atoi(e);
-	if (const char *e = std::getenv("LZGPU_ROTATE")) fs->rot_warps = std::atoi(e);
 	if (const char *e = std::getenv("LZGPU_STRIPED")) fs->striped = std::atoi(e);  // 0 never, 1 whenever possible, unset = automatic
 	void *fn = nullptr;
 	cudaDriverEntryPointQueryResult qres;
@@ -129,7 +127,7 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if ((rc = set_smem_attr<1, false, 3, 20, 64, true>(smem))) return rc;
 	if ((rc = set_smem_attr<2, false, 3, 16, 64, true>(smem))) return rc;
 	if ((rc = set_smem_attr<3, false, 5, 8, 64, true>(smem))) return rc;
-	if ((rc = set_smem_attr<4, false, 8, 4, 64, true>(smem))) return rc;
+	if ((rc = set_smem_attr<4, false, 8, 5, 64, true>(smem))) return rc;
 	if ((rc = set_smem_attr<2, false, 8, 8>(smem))) return rc;
 	if ((rc = set_smem_attr<1, false, 2, 32>(smem))) return rc;
 	if ((rc = set_smem_attr<1, false, 3, 20>(smem))) return rc;
@@ -138,7 +136,7 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if ((rc = set_smem_attr<2, false, 6, 10>(smem))) return rc;
 	if ((rc = set_smem_attr<3, false, 5, 8>(smem))) return rc;
 	if ((rc = set_smem_attr<3, false, 6, 8>(smem))) return rc;
-	if ((rc = set_smem_attr<4, false, 8, 4>(smem))) return rc;
+	if ((rc = set_smem_attr<4, false, 8, 5>(smem))) return rc;
 #ifdef LZ_ENABLE_FOLD128
 	const int smem128 = std::min(fs->max_smem, kSmemCap128);
 	if ((rc = set_smem_attr<0, false, 0, 0, 128>(smem128))) return rc;
@@ -147,7 +145,7 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if ((rc = set_smem_attr<3, false, 0, 0, 128>(smem128))) return rc;
 	if ((rc = set_smem_attr<4, false, 0, 0, 128>(smem128))) return rc;
 	if ((rc = set_smem_attr<2, false, 8, 8, 128>(smem128))) return rc;
-	if ((rc = set_smem_attr<4, false, 8, 4, 128>(smem128))) return rc;
+	if ((rc = set_smem_attr<4, false, 8, 5, 128>(smem128))) return rc;
 	if ((rc = set_smem_attr<3, false, 5, 8, 128>(smem128))) return rc;
 #endif
 	if ((rc = set_all_recover_attrs())) return rc;
@@ -177,10 +175,6 @@ static uint32_t pick_group(uint32_t K, uint32_t PC, int max_smem_per_cta, int fw
 		if (fused_smem_bytes(rows, prows, fw) > static_cast<size_t>(max_smem_per_cta)) break;
 		best = g;
 	}
-	// GF-heavy shapes (3-4 parity rows): warp w runs on scheduler w % 4 and every step waits for the slowest warp, so the
-	// number of item-carrying warps (= G while 32*G <= threads) should be a multiple of 4; G = 5 put two of them on
-	// scheduler 0 of each CTA and cost ~1.5x (profiles/probe_r1.md)
-	if (PC >= 2 && best > 4 && 32 * best <= threads && best % 4) best -= best % 4;
 	return best;
 }
 
@@ -279,8 +273,6 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	p.zconst = lz::crc_of_zeros(LZGPU_BLOCK_SIZE);
 	p.probe = fs->probe;
 	p.evict_first = static_cast<uint32_t>(fs->evict_first);
-	p.sm_ctr = fs->rot_warps > 0 ? fs->d_sm_ctr : nullptr;
-	p.rot_warps = static_cast<uint32_t>(fs->rot_warps > 0 ? fs->rot_warps : 0);
 	if (generic) {
 		for (int r = 0; r < M; ++r)
 			for (uint32_t j = 0; j < K; ++j) {
@@ -306,7 +298,7 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 		LZ_FOLDED_STRIPED(1, 3, 20)
 		LZ_FOLDED_STRIPED(2, 3, 16)
 		LZ_FOLDED_STRIPED(3, 5, 8)
-		LZ_FOLDED_STRIPED(4, 8, 4)
+		LZ_FOLDED_STRIPED(4, 8, 5)
 #undef LZ_FOLDED_STRIPED
 		switch (M) {
 			case 1: return launch<1, false, 0, 0, 64, true>(ctx, map, p, smem, st);
@@ -320,7 +312,7 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 #ifdef LZ_ENABLE_FOLD128
 	if (fw == 128) {
 		if (M == 2 && K == 8 && G == 8) return launch<2, false, 8, 8, 128>(ctx, map, p, smem, st);
-		if (M == 4 && K == 8 && G == 4) return launch<4, false, 8, 4, 128>(ctx, map, p, smem, st);
+		if (M == 4 && K == 8 && G == 5) return launch<4, false, 8, 5, 128>(ctx, map, p, smem, st);
 		if (M == 3 && K == 5 && G == 8) return launch<3, false, 5, 8, 128>(ctx, map, p, smem, st);
 		switch (M) {
 			case 0: return launch<0, false, 0, 0, 128>(ctx, map, p, smem, st);
@@ -343,7 +335,7 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	LZ_FOLDED(2, 6, 10)   // ec(6,2)
 	LZ_FOLDED(3, 5, 8)    // ec(5,3)
 	LZ_FOLDED(3, 6, 8)    // ec(6,3)
-	LZ_FOLDED(4, 8, 4)    // ec(8,4)
+	LZ_FOLDED(4, 8, 5)    // ec(8,4)
 #undef LZ_FOLDED
 	switch (M) {
 		case 0: return launch<0, false>(ctx, map, p, smem, st);

@@ -90,8 +90,6 @@ struct FusedParams {
 	uint32_t qmult[4];               // x^(32*(4096*(3-q) - deg)) mod P : stream -> block merge incl. the flush offset (deg of the fold in use)
 	uint32_t zconst;                 // mycrc32(0, 64 KiB of zeros)
 	uint32_t probe;                  // diagnostics only (LZGPU_PROBE): bit1 skip GF role, bit2 skip CRC folds (results then invalid)
-	uint32_t *sm_ctr;                // experiment build LZ_ENABLE_ROTATE: per-SM CTA counter (role rotation of co-resident CTAs)
-	uint32_t rot_warps;              // ... warps to rotate the roles of every second CTA of an SM by
 	CoefPlanes coef[4 * 32];         // only read by the GENERIC instantiation: [M][K]
 };
 
@@ -341,24 +339,8 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 	__syncthreads();
 
 	// ===================== role assignment =====================
-#ifdef LZ_ENABLE_ROTATE
-	// experiment: the second CTA of an SM shifts its roles by rot_warps warps, so that the item-carrying warps of the two
-	// co-resident CTAs land on different schedulers (warp w issues on scheduler w % 4)
-	__shared__ uint32_t s_rot;
-	if (tid == 0) {
-		uint32_t smid;
-		asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-		s_rot = (p.sm_ctr && (atomicAdd(p.sm_ctr + smid, 1u) & 1u)) ? p.rot_warps : 0u;
-	}
-	__syncthreads();
-	uint32_t cw_rot = warp + s_rot;
-	if (cw_rot >= NT / 32) cw_rot -= NT / 32;
-	const uint32_t cw = cw_rot;
-	const uint32_t vt = cw * 32 + lane;
-#else
 	const uint32_t cw = warp;                                 // consumer warp index 0..8
 	const uint32_t vt = tid;                                  // consumer thread index 0..287
-#endif
 	const bool is_data_row = vt < ROWS;
 	const bool is_parity_row = vt >= ROWS && vt < ROWS + PROWS;
 	const bool has_stream = is_data_row || is_parity_row;
