@@ -120,3 +120,88 @@ long ref_plan_recover_part(int n_avail, const int *types, const int *parts, cons
 }
 
 }  // extern "C"
+
+/* ------------------------------------------------------------------------------------------------
+ * The same chunk read, stopped between the network part and the post-processing: exports the plan the reference built
+ * (the public fields of SliceReadPlan + the parameters ChunkReadPlanner::buildPlan gives its BlockConverter), the full
+ * buffer as the executor leaves it, and the reference's own post-processed result.  Used to test
+ * include/lzgpu_read_plan.hpp (the GPU-backed mirror of ReadPlan::postProcessData) on plans made by the reference.
+ * desc layout (ints): slice_type, buffer_part_size, read_buffer_size, read_offset, n_requested, {part, size}*,
+ *   n_ops, {slice_part, request_offset, request_size, buffer_offset, wave}*, has_converter, chunk_first_block,
+ *   chunk_block_count, part_first_block, part_block_count, first_required_part, data_part_count, n_available, {slice_part}*
+ * Returns the full buffer size, -1 when reading is impossible, -2 when a capacity is too small.
+ * ---------------------------------------------------------------------------------------------- */
+namespace {
+struct PlannerProbe : ChunkReadPlanner {  // read access to what buildPlan() hands to the BlockConverter
+	using ChunkReadPlanner::chunk_block_count_;
+	using ChunkReadPlanner::chunk_first_block_;
+	using ChunkReadPlanner::part_block_count_;
+	using ChunkReadPlanner::part_first_block_;
+	using ChunkReadPlanner::read_from_type_;
+	using ChunkReadPlanner::read_parts_;
+};
+}  // namespace
+
+extern "C" long ref_plan_chunk_read_staged(int n_avail, const int *types, const int *parts, const uint8_t *const *data, const size_t *bytes,
+                                           int first_block, int block_count, int *desc, int desc_cap, uint8_t *staged, uint8_t *expected,
+                                           size_t buffer_cap) {
+	std::vector<PartSource> sources = gather(n_avail, types, parts, data, bytes);
+	PlannerProbe planner;
+	planner.prepare(first_block, block_count, parts_of(sources));
+	if (!planner.isReadingPossible()) return -1;
+	std::unique_ptr<ReadPlan> plan = planner.buildPlan();
+	SliceReadPlan *sp = dynamic_cast<SliceReadPlan *>(plan.get());
+	if (!sp) return -1;
+	const size_t full = plan->fullBufferSize();
+	if (full > buffer_cap) return -2;
+	std::vector<int> d;
+	d.push_back((int)sp->slice_type);
+	d.push_back(sp->buffer_part_size);
+	d.push_back(plan->read_buffer_size);
+	d.push_back(plan->readOffset());
+	d.push_back((int)sp->requested_parts.size());
+	for (const auto &r : sp->requested_parts) { d.push_back(r.part); d.push_back(r.size); }
+	d.push_back((int)plan->read_operations.size());
+	for (const auto &op : plan->read_operations) {
+		d.push_back(op.first.getSlicePart()); d.push_back(op.second.request_offset); d.push_back(op.second.request_size);
+		d.push_back(op.second.buffer_offset); d.push_back(op.second.wave);
+	}
+	const bool conv = !plan->postprocess_operations.empty();
+	d.push_back(conv ? 1 : 0);
+	d.push_back(planner.chunk_first_block_); d.push_back(planner.chunk_block_count_);
+	d.push_back(planner.part_first_block_); d.push_back(planner.part_block_count_);
+	d.push_back(slice_traits::isXor(planner.read_from_type_) ? planner.read_parts_[0] - 1 : planner.read_parts_[0]);
+	d.push_back(slice_traits::requiredPartsToRecover(planner.read_from_type_));
+
+	// the executor part (plan_tester.cc:155-184), stopped before postProcessData
+	std::vector<uint8_t> buffer(full, 0);
+	PartsContainer available;
+	for (int wave = 0; wave < 10; ++wave) {
+		for (const auto &op : plan->read_operations) {
+			if (op.second.wave != wave) continue;
+			const PartSource *src = nullptr;
+			for (const auto &s : sources)
+				if (s.slice_type == (int)op.first.getSliceType() && s.slice_part == op.first.getSlicePart()) src = &s;
+			if (!src) continue;
+			uint8_t *dst = buffer.data() + plan->readOffset() + op.second.buffer_offset;
+			const size_t off = op.second.request_offset, size = op.second.request_size;
+			if (off < src->bytes) std::memcpy(dst, src->data + off, std::min(size, src->bytes - off));
+			available.push_back(op.first);
+		}
+		if (plan->isReadingFinished(available)) break;
+	}
+	if (!plan->isReadingFinished(available)) return -1;
+	d.push_back((int)available.size());
+	for (const auto &a : available) d.push_back(a.getSlicePart());
+	if ((int)d.size() > desc_cap) return -2;
+	std::memcpy(desc, d.data(), d.size() * sizeof(int));
+	std::memcpy(staged, buffer.data(), full);
+#ifndef NDEBUG
+	plan->buffer_start = buffer.data();
+	plan->buffer_read = buffer.data() + plan->readOffset();
+	plan->buffer_end = buffer.data() + full;
+#endif
+	const int size = plan->postProcessData(buffer.data(), available);
+	std::memcpy(expected, buffer.data(), size);
+	return (long)full;
+}

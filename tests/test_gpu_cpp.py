@@ -43,3 +43,18 @@ def test_stripe_batcher_cpp():
     r = subprocess.run([BATCHER], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "all tests passed" in r.stdout
+
+
+READ_PLAN = os.path.join(ROOT, "tests", "cpp", "build", "test_read_plan")
+
+
+@pytest.mark.gpu
+def test_read_plan_mirror_cpp():
+    """lzgpu::SliceReadPlan (include/lzgpu_read_plan.hpp), the GPU-backed mirror of ReadPlan::postProcessData, on plans
+    built and pre-executed by the reference's own ChunkReadPlanner (oracle/_ref) — must reproduce the reference's
+    post-processed buffer byte for byte (tests/cpp/test_read_plan.cc)."""
+    if not os.path.exists(READ_PLAN):
+        pytest.skip("oracle/_ref/liblzref.so was not built (no /root/reference), so the reference planners are unavailable")
+    r = subprocess.run([READ_PLAN], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all tests passed" in r.stdout
