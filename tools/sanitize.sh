@@ -20,6 +20,47 @@ for text, nblk in [("ec(8,2)", 24), ("ec(3,2)", 7), ("xor3", 9)]:
     out, img = eng.recover_chunks(g, nblk, avail, chunk_image=True)
     assert (out[1] == parts[1]).all() and (img == data).all()
 eng.verify_blocks(data.reshape(-1), eng.crc_blocks(data.reshape(-1)))
+# round-1 additions: striped units (ragged small chunks), the two-CTA recover geometry, slice conversion, both scrub formats
+# with the exact sparse rule, batched block writes
+import os, zlib
+for mode in ("1", "0"):
+    os.environ["LZGPU_STRIPED"] = mode; os.environ["LZGPU_RECOVER_TWO"] = mode
+    e2 = L.Engine(0)
+    for text, nblk, n in [("ec(5,3)", 11, 7), ("xor3", 7, 9), ("ec(8,2)", 13, 5)]:
+        g = L.SliceType(text)
+        data = np.stack([O.fill_chunk(o, nblk * 65536, 5, c) for c in range(n)])
+        par, crc = e2.encode_chunks(g, data)
+        for c in range(n):
+            p_ref, c_ref = o.encode_chunk(g.kind, g.k, g.m, data[c])
+            assert (par[c] == p_ref).all() and (crc[c] == c_ref).all()
+        parts = [np.stack([O.split_parts(data[c], g.k)[0][j] for c in range(n)]) for j in range(g.k)] + [np.ascontiguousarray(par[:, r]) for r in range(g.m)]
+        avail = [None if i == 0 else parts[i] for i in range(g.k + g.m)]
+        out, img = e2.recover_chunks(g, nblk, avail, chunk_image=True)
+        assert (out[0] == parts[0]).all() and (img == data).all()
+        out2, ocrc = e2.convert_chunks(g, L.SliceType("ec(3,2)"), nblk, avail, [1] * 5)
+        p32, c32 = e2.encode_chunks(L.SliceType("ec(3,2)"), data)
+        assert (out2[3] == p32[:, 0]).all() and (out2[4] == p32[:, 1]).all()
+rec = np.zeros((5, 4 + 65536), dtype=np.uint8)
+for i in range(5):
+    rec[i, 4:] = O.fill_chunk(o, 65536, 9, i)
+    rec[i, :4] = np.frombuffer(zlib.crc32(rec[i, 4:].tobytes()).to_bytes(4, "big"), dtype=np.uint8)
+rec[2] = 0
+eng.verify_interleaved(rec)
+hdr = eng.moosefs_header_size(3)
+img = np.zeros(hdr + 3 * 65536, dtype=np.uint8)
+for b in range(3):
+    img[hdr + b * 65536: hdr + (b + 1) * 65536] = rec[b, 4:]
+    img[1024 + 4 * b: 1028 + 4 * b] = rec[b, :4]
+img[1024 + 8: 1024 + 12] = np.frombuffer((0xD7978EEB).to_bytes(4, "big"), dtype=np.uint8)
+eng.verify_moosefs(img, 3, 3)
+blocks = np.stack([O.fill_chunk(o, 65536, 11, i) for i in range(6)])
+stored = np.array([zlib.crc32(b.tobytes()) for b in blocks], dtype=np.uint32)
+ws = []
+for i, (off, size) in enumerate([(0, 65536), (1, 1), (100, 4097), (65535, 1), (0, 3), (32768, 32768)]):
+    d = O.fill_chunk(o, max(size, 8), 13, i)[:size]
+    ws.append(dict(block=i, offset=off, data=d, crc=zlib.crc32(d.tobytes()), exists=i != 4))
+st = eng.write_blocks(blocks, stored, ws)
+assert st == [0] * 6 and all(stored[i] == zlib.crc32(blocks[i].tobytes()) for i in range(6))
 print("sanitizer case OK")
 PY
 for tool in ${TOOLS:-memcheck racecheck synccheck}; do
