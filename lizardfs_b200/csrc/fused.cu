@@ -132,6 +132,7 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if ((rc = set_smem_attr<1, false, 2, 32>(smem))) return rc;
 	if ((rc = set_smem_attr<1, false, 3, 20>(smem))) return rc;
 	if ((rc = set_smem_attr<2, false, 3, 16>(smem))) return rc;
+	if ((rc = set_smem_attr<2, false, 3, 18>(smem))) return rc;
 	if ((rc = set_smem_attr<2, false, 4, 14>(smem))) return rc;
 	if ((rc = set_smem_attr<2, false, 6, 10>(smem))) return rc;
 	if ((rc = set_smem_attr<3, false, 5, 8>(smem))) return rc;
@@ -331,6 +332,7 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	LZ_FOLDED(1, 2, 32)   // xor2
 	LZ_FOLDED(1, 3, 20)   // xor3
 	LZ_FOLDED(2, 3, 16)   // ec(3,2)
+	LZ_FOLDED(2, 3, 18)   // ec(3,2) with a 3-deep parity ring (-DLZ_NPST=3)
 	LZ_FOLDED(2, 4, 14)   // ec(4,2)
 	LZ_FOLDED(2, 6, 10)   // ec(6,2)
 	LZ_FOLDED(3, 5, 8)    // ec(5,3)

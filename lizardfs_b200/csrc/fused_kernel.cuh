@@ -71,7 +71,10 @@ constexpr int kMaxRows = 256;                          // TMA box limit per dime
 // pipeline depth by fold window: FW = 64 -> 2 CTAs/SM (96 registers), 3 data stages + 4-deep parity ring;
 // FW = 128 -> 1 CTA/SM (the 128-word window needs ~170 registers), 6 data stages + 6-deep parity ring
 __host__ __device__ constexpr int fused_nst(int fw) { return fw == 64 ? 3 : 6; }
-__host__ __device__ constexpr int fused_npst(int fw) { return fw == 64 ? 4 : 6; }
+#ifndef LZ_NPST
+#define LZ_NPST 4
+#endif
+__host__ __device__ constexpr int fused_npst(int fw) { return fw == 64 ? LZ_NPST : 6; }
 constexpr int kMaxParityRows = 128;
 
 struct FusedParams {
