@@ -42,6 +42,21 @@ struct PartBlock {
 	const uint8_t *prefix;     // LZGPU_WRITE_PREFIX_SIZE bytes, ready to send in front of `data`
 };
 
+// ChunkWriter::computeParityBlock (src/mount/chunk_writer.cc:365-401) with the reference's arguments — the per-call path for
+// what the batcher does not take (sub-block ranges: `size` < 64 KiB at the same offset in every block).  data_blocks[offset + i]
+// is block i of the stripe, nullptr = a block that does not exist (zeros, :377,:396).  xorN: memcpy + blockXor == the all-ones row.
+inline void computeParityBlock(const lzgpu_goal &goal, int parity_index, uint8_t *parity_block, const std::vector<uint8_t *> &data_blocks,
+                               int offset, int size) {
+	const uint8_t *in[LZGPU_MAX_PARTS] = {nullptr};
+	uint8_t erased[LZGPU_MAX_PARTS] = {0};
+	uint8_t *out[LZGPU_MAX_PARTS] = {nullptr};
+	for (int i = 0; i < goal.k; ++i) in[i] = data_blocks[offset + i];
+	for (int i = 0; i < goal.m; ++i) erased[goal.k + i] = 1;  // rs.recover with every parity part erased, one output (:386-400)
+	out[goal.k + parity_index] = parity_block;
+	if (lzgpu_rs_recover(goal.k, goal.m, in, erased, out, static_cast<size_t>(size)) != LZGPU_OK)
+		throw std::runtime_error(std::string("computeParityBlock: ") + lzgpu_last_error());
+}
+
 class StripeBatcher {
 public:
 	typedef std::function<void(const PartBlock &)> Sink;

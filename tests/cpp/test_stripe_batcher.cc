@@ -151,6 +151,34 @@ static void run(const char *text, unsigned seed) {
 	std::printf("%s: ok\n", text);
 }
 
+// the per-call mirror of ChunkWriter::computeParityBlock: sub-block sizes, absent (NULL) blocks, every parity part
+static void test_compute_parity_block(const char *text) {
+	lzgpu_goal goal;
+	EXPECT(lzgpu_goal_parse(text, &goal) == LZGPU_OK);
+	std::mt19937_64 rng(99);
+	for (int size : {65536, 4096, 1, 12345}) {
+		std::vector<std::vector<uint8_t>> blocks(2 + goal.k, std::vector<uint8_t>(size));
+		std::vector<uint8_t *> ptrs(2 + goal.k, nullptr);
+		for (int i = 0; i < goal.k; ++i) {
+			for (auto &x : blocks[2 + i]) x = static_cast<uint8_t>(rng());
+			ptrs[2 + i] = (i == goal.k - 1 && size != 65536) ? nullptr : blocks[2 + i].data();  // a block past the end of the file
+		}
+		for (int r = 0; r < goal.m; ++r) {
+			std::vector<uint8_t> got(size, 0xEE), want(size);
+			lzgpu::computeParityBlock(goal, r, got.data(), ptrs, 2, size);
+			const uint8_t *in[LZO_MAX_PARTS] = {nullptr};
+			uint8_t erased[LZO_MAX_PARTS] = {0};
+			uint8_t *out[LZO_MAX_PARTS] = {nullptr};
+			for (int i = 0; i < goal.k; ++i) in[i] = ptrs[2 + i];
+			for (int i = 0; i < goal.m; ++i) erased[goal.k + i] = 1;
+			out[goal.k + r] = want.data();
+			EXPECT(lzo_rs_recover(goal.k, goal.m, in, erased, out, size) == 0);
+			EXPECT(got == want);
+		}
+	}
+	std::printf("computeParityBlock %s: ok\n", text);
+}
+
 int main() {
 	if (!lzgpu_default_ctx()) {
 		std::fprintf(stderr, "no GPU context: %s\n", lzgpu_last_error());
@@ -160,6 +188,9 @@ int main() {
 	run("ec(3,2)", 2);
 	run("xor3", 3);
 	run("ec(5,3)", 4);
+	test_compute_parity_block("ec(8,2)");
+	test_compute_parity_block("xor3");
+	test_compute_parity_block("ec(3,2)");
 	if (failures) {
 		std::fprintf(stderr, "%d failure(s)\n", failures);
 		return 1;
