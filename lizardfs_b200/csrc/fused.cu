@@ -503,6 +503,21 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 				v = lz::gf_mul_host(v, 2);
 			}
 		}
+	p.raid6_dbl = 0xffu;
+	if (e == 2 && p.par_row[0] == 0 && p.par_row[1] == 1 && !(K == 8 && G == 8)) {
+		// RAID-6 shape on a runtime-k instantiation: w[0] = planes of 2^x0, w[1] = planes of (2^x0 ^ 2^x1)^-1 (see the kernel)
+		uint8_t gx0 = 1, gx1 = 1;
+		for (int t = 0; t < p.erased_idx[0]; ++t) gx0 = lz::gf_mul_host(gx0, 2);
+		for (int t = 0; t < p.erased_idx[1]; ++t) gx1 = lz::gf_mul_host(gx1, 2);
+		uint8_t v0 = gx0, v1 = lz::gf_inv_host(gx0 ^ gx1);
+		for (int b = 0; b < 8; ++b) {
+			p.w[0].plane[b] = v0;
+			p.w[1].plane[b] = v1;
+			v0 = lz::gf_mul_host(v0, 2);
+			v1 = lz::gf_mul_host(v1, 2);
+		}
+		if (p.erased_idx[0] <= 4) p.raid6_dbl = p.erased_idx[0];
+	}
 	TmapArray maps;
 	for (int a = 0; a < K; ++a) {
 		const cuuint64_t dims[3] = {static_cast<cuuint64_t>(kRowBytes), static_cast<cuuint64_t>(pb) * 4, n_chunks};

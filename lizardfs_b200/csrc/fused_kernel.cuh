@@ -539,6 +539,7 @@ struct RecoverParams {
 	unsigned long long out_stride, image_stride;
 	uint32_t n_chunks, nb, pb, K, G, units_per_chunk, total_units;
 	uint32_t e;                    // erased data parts (1..4)
+	uint32_t raid6_dbl;            // E = 2 with parity rows 0 and 1 (the RAID-6 shape): doublings for 2^x0 * S0, 0xff = use w[0]
 	uint8_t slot_of_data[32];      // data index j -> slot, 0xff = erased
 	uint8_t erased_idx[4];         // data index of erased part x
 	uint8_t par_slot[4], par_row[4];  // parity rows in use: slot and generator row r
@@ -664,6 +665,33 @@ fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 						for (int r = 0; r < E; ++r) {
 							const uint4 pv = lds128(a_item + p.par_slot[r] * region_bytes);
 							acc[r][0] ^= pv.x; acc[r][1] ^= pv.y; acc[r][2] ^= pv.z; acc[r][3] ^= pv.w;
+						}
+						if (E == 2 && R0 == 0 && R1 == 1 && KT == 0) {
+							// (runtime-k shapes only: for the k = 8 instantiation the two bit-plane multiplies measured 5 % faster)
+							// RAID-6 elimination: S0 = d0 ^ d1, S1 = 2^x0 d0 ^ 2^x1 d1  =>  (2^x0 ^ 2^x1) d1 = S1 ^ 2^x0 S0, d0 = S0 ^ d1:
+							// ONE general multiply per word (w[1] = planes of (2^x0 ^ 2^x1)^-1) and x0 doublings (x0 is the smaller
+							// index; more than four doublings cost more than the bit-plane multiply by 2^x0, w[0]).
+							uint32_t d0[4], d1[4];
+#pragma unroll
+							for (int w = 0; w < 4; ++w) {
+								uint32_t t = acc[0][w];
+								if (p.raid6_dbl != 0xffu) {
+									for (uint32_t i = 0; i < p.raid6_dbl; ++i) t = gf_x2(t);
+								} else {
+									t = gf_mac(0u, t, p.w[0]);
+								}
+								d1[w] = gf_mac(0u, acc[1][w] ^ t, p.w[1]);
+								d0[w] = acc[0][w] ^ d1[w];
+							}
+#pragma unroll
+							for (int x = 0; x < 2; ++x) {
+								const uint4 dv = x == 0 ? make_uint4(d0[0], d0[1], d0[2], d0[3]) : make_uint4(d1[0], d1[1], d1[2], d1[3]);
+								if (p.out[x] && stripe < p.pb)
+									st_stream(reinterpret_cast<uint4 *>(p.out[x] + c * p.out_stride + (static_cast<unsigned long long>(stripe) << 16) + in_block), dv);
+								const uint32_t b = stripe * K + p.erased_idx[x];
+								if (img && b < p.nb) st_stream(reinterpret_cast<uint4 *>(img + (static_cast<unsigned long long>(b) << 16)), dv);
+							}
+							continue;
 						}
 						// d_x = sum_r W[x][r] * S_r.  When parity row 0 (all ones) is in use, S_0 = xor of all unknowns,
 						// so the last unknown is S_0 ^ (the others) and needs no multiply.
