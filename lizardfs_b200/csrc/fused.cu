@@ -246,7 +246,7 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	p.G = G;
 	// flat mode: contiguous chunks made of whole stripes are one run of n_chunks*pb stripes (small chunks then fill the
 	// G-stripe units instead of leaving most TMA rows out of range)
-	const bool flat = M > 0 && n_chunks > 1 && chunk_stride == static_cast<size_t>(nb) * LZGPU_BLOCK_SIZE && nb % K == 0 &&
+	const bool flat = n_chunks > 1 && chunk_stride == static_cast<size_t>(nb) * LZGPU_BLOCK_SIZE && nb % K == 0 &&
 	                  static_cast<uint64_t>(n_chunks) * p.pb < (1ull << 31) && static_cast<uint64_t>(n_chunks) * nb * 4 < (1ull << 31);  // TMA coordinates are int32
 	p.flat = flat ? 1u : 0u;
 	p.flat_magic = (1ull << 40) / p.pb + 1;
@@ -374,8 +374,12 @@ int lz_fused_crc(lzgpu_ctx *ctx, const void *base, unsigned long long n_blocks, 
 	const unsigned long long n_chunks = n_blocks / blocks_per_chunk;
 	if (blocks_per_chunk > 0x3fffffffull || n_chunks > 0x7fffffffull) return LZGPU_NOT_HANDLED;
 	if (n_chunks == 1) chunk_stride = blocks_per_chunk * LZGPU_BLOCK_SIZE;
-	// CRC only: "K" = 64 blocks per unit, one stripe group per unit, no parity
-	return fused_run(ctx, 0, false, nullptr, 64, static_cast<uint32_t>(n_chunks), static_cast<uint32_t>(blocks_per_chunk), base, chunk_stride,
+	// CRC only, no parity: a unit is 64 blocks.  Contiguous "chunks" (parts) whose block count is not a multiple of 64 are
+	// taken as one run of single-block stripes (K = 1, G = 64, flat units crossing the part boundaries) instead of
+	// K = 64 blocks per unit inside each part, which would leave the last unit of every part partly empty.
+	const bool contiguous = n_chunks > 1 && chunk_stride == blocks_per_chunk * LZGPU_BLOCK_SIZE;
+	const uint32_t K = (contiguous && blocks_per_chunk % 64) ? 1 : 64;
+	return fused_run(ctx, 0, false, nullptr, K, static_cast<uint32_t>(n_chunks), static_cast<uint32_t>(blocks_per_chunk), base, chunk_stride,
 	                 nullptr, 0, out, out_chunk_stride, st);
 }
 
