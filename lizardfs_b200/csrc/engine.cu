@@ -689,6 +689,8 @@ extern "C" int lzgpu_convert_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *src, c
 	DeviceGuard g(ctx->device);
 	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
 	if (bad) bad[0] = bad[1] = bad[2] = -1;
+	void *d_encode_crc = nullptr;  // CRC array of the destination-slice encode, when that ran
+	size_t encode_crc_stride = 0;
 
 	if (same_goal(src, dst) && !goal_is_std(src)) {
 		// kReadDataPart (slice_recovery_planner.h:98-101): the part is read, or rebuilt from k parts of the same slice
@@ -766,6 +768,8 @@ extern "C" int lzgpu_convert_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *src, c
 				if ((rc = lz_scratch(ctx, kScratchConvPar, n_chunks * par_stride, &d_par))) return rc;
 				if ((rc = lz_scratch(ctx, kScratchConvCrc, n_chunks * crc_stride * 4, &d_crc))) return rc;
 				if ((rc = lzgpu_encode_chunks_dev(ctx, dst, n_chunks, nb * B, image, image_stride, d_par, par_stride, d_crc, crc_stride, st))) return rc;
+				d_encode_crc = d_crc;
+				encode_crc_stride = crc_stride;
 				for (int r = 0; r < dst->m; ++r)
 					if (want[kd + r])
 						CUDA_TRY(cudaMemcpy2DAsync(d_out[kd + r], out_stride, static_cast<uint8_t *>(d_par) + static_cast<size_t>(r) * pbd * B, par_stride,
@@ -774,9 +778,27 @@ extern "C" int lzgpu_convert_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *src, c
 		}
 	}
 	// ChunkReplicator::replicate computes mycrc32 of every rebuilt block (chunk_replicator.cc:186-192)
-	if (d_out_crc)
-		for (int i = 0; i < nd; ++i)
-			if (want[i] && d_out_crc[i] && (rc = crc_of_parts(ctx, d_out[i], n_chunks, pbd, out_stride, d_out_crc[i], st))) return rc;
+	if (d_out_crc) {
+		if (d_encode_crc) {
+			// the encode pass that produced the parity already checksummed every data and parity block of the destination slice
+			CrcPartsArgs a{};
+			bool any = false;
+			for (int i = 0; i < nd; ++i)
+				if (want[i] && d_out_crc[i]) { a.out[i] = static_cast<uint32_t *>(d_out_crc[i]); any = true; }
+			if (any) {
+				a.crc = static_cast<const uint32_t *>(d_encode_crc);
+				a.crc_stride = encode_crc_stride;
+				a.k = kd; a.m = dst->m; a.nb = nb; a.pb = pbd; a.zero_crc = kCrcZeroBlock64K;
+				a.total = static_cast<unsigned long long>(n_chunks) * nd * pbd;
+				crc_to_parts_kernel<<<grid_for(ctx, a.total, 256, 4), 256, 0, st>>>(a);
+				CUDA_TRY(cudaGetLastError());
+				ctx->stats.kernel_launches++;
+			}
+		} else {
+			for (int i = 0; i < nd; ++i)
+				if (want[i] && d_out_crc[i] && (rc = crc_of_parts(ctx, d_out[i], n_chunks, pbd, out_stride, d_out_crc[i], st))) return rc;
+		}
+	}
 	return LZGPU_OK;
 }
 

@@ -280,6 +280,36 @@ __global__ void __launch_bounds__(256) sparse_confirm_kernel(const uint8_t *base
 	}
 }
 
+// CRC array of lzgpu_encode_chunks (per chunk: nb data-block CRCs in chunk order, then m x pb parity CRCs) -> per-part arrays
+// (part i, chunk c at out[i] + c*pb): data part j block s is chunk block s*k + j, zero padding blocks carry the CRC of zeros.
+struct CrcPartsArgs {
+	const uint32_t *crc;
+	uint32_t *out[64];            // nullptr = part not wanted
+	unsigned long long crc_stride, total;  // total = n_chunks * (k + m) * pb
+	uint32_t k, m, nb, pb, zero_crc;
+};
+
+__global__ void __launch_bounds__(256) crc_to_parts_kernel(const CrcPartsArgs a) {
+	const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+	const unsigned parts = a.k + a.m;
+	for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.total; i += stride) {
+		const unsigned s = static_cast<unsigned>(i % a.pb);
+		const unsigned part = static_cast<unsigned>((i / a.pb) % parts);
+		const unsigned long long c = i / (static_cast<unsigned long long>(a.pb) * parts);
+		uint32_t *dst = a.out[part];
+		if (!dst) continue;
+		const uint32_t *src = a.crc + c * a.crc_stride;
+		uint32_t v;
+		if (part < a.k) {
+			const unsigned b = s * a.k + part;
+			v = b < a.nb ? src[b] : a.zero_crc;
+		} else {
+			v = src[a.nb + (part - a.k) * a.pb + s];
+		}
+		dst[c * a.pb + s] = v;
+	}
+}
+
 // ---- chunkserver block writes (hdd_write, src/chunkserver/hddspacemgr.cc:1898-2008) ---------------------------
 // One CTA per write request.  The reference reads the stored block, CRCs the three ranges before / under / after the
 // write, checks  combine(pre, under, post) == stored  and stores  combine(pre, crc_of_payload, post).  With lin() the
