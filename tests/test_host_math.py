@@ -145,3 +145,14 @@ def test_geometry_matches_slice_traits(oracle):
     # the numbers quoted in SURVEY.md §7: ec(3,2) parts hold 342/341/341 blocks, parity 342
     g = L.SliceType("ec(3,2)")
     assert [g.part_blocks(p) for p in range(5)] == [342, 341, 341, 342, 342]
+
+
+def test_moosefs_header_size_matches_chunk_cc(oracle):
+    """Chunk-file header of the MooseFS format (src/chunkserver/chunk.cc:169-181): 1 KiB signature + 4 B per block, padded to
+    4 KiB for xor/ec parts — a host-side constant the scrub entry point depends on (no GPU needed)."""
+    from tests import _oracle as O
+    lib = L._lib.load()
+    assert lib.lzgpu_moosefs_header_size(1) == 5120
+    for parts in range(1, 33):
+        assert lib.lzgpu_moosefs_header_size(parts) == O.moosefs_header_size(oracle, parts)
+    assert lib.lzgpu_moosefs_header_size(0) == 0 and lib.lzgpu_moosefs_header_size(33) == 0
