@@ -117,6 +117,8 @@ void lzgpu_reset_stats(lzgpu_ctx *ctx);
  *           then for r < m the pb CRCs of parity part r.  Host byte order (callers put32bit them).
  * The *_dev variants take device pointers of the context's device, enqueue on `stream`
  * (a cudaStream_t passed as void*, NULL = the context's stream) and do not synchronise.
+ * lzgpu_encode_chunks_dev zero-fills the rest of a trailing partial block IN the caller's data buffer (the chunk
+ * stride must cover whole blocks, and buffers must be 16-byte aligned); nothing else of the inputs is written.
  * The host variants stage through pinned memory (H2D, kernel, D2H) and return when results are
  * in the caller's buffers.
  * ------------------------------------------------------------------------------------------- */
