@@ -210,7 +210,9 @@ int lzgpu_crc_blocks(lzgpu_ctx *ctx, const uint8_t *data, size_t n_blocks, uint3
                      size_t block_stride, uint32_t *crc_out);
 int lzgpu_crc_blocks_dev(lzgpu_ctx *ctx, const void *d_data, size_t n_blocks, uint32_t block_len,
                          size_t block_stride, void *d_crc_out, void *stream);
-/* Scrub (hdd_int_test, hddspacemgr.cc:2174-2190): compare against stored CRCs; returns LZGPU_OK or
+/* The three scrub entry points below accept host pointers or device pointers of the context's device for `data` / `records` /
+ * `file_image` and `stored_crc` (unified addressing; a chunk file read straight into device memory needs no host round trip).
+ * Scrub (hdd_int_test, hddspacemgr.cc:2174-2190): compare against stored CRCs; returns LZGPU_OK or
  * LZGPU_ERR_CRC with *first_bad = index of the first mismatching block.  A stored CRC of 0 on an
  * all-zero block is accepted when sparse_rule != 0 (recompute_crc_if_block_empty, crc.cc:235-243): the block bytes
  * are checked, a non-zero block whose CRC merely equals that of zeros is still a mismatch, as in the reference. */

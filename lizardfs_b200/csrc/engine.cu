@@ -1065,9 +1065,11 @@ static int verify_common(lzgpu_ctx *ctx, const uint8_t *h_data, size_t n_blocks,
 	const unsigned long long init = ~0ull;
 	for (size_t b0 = 0; b0 < n_blocks; b0 += tile_blocks) {
 		const size_t n = std::min(tile_blocks, n_blocks - b0);
-		CUDA_TRY(cudaMemcpy2DAsync(d_in, dstride, h_data + h_offset + b0 * h_stride, h_stride, block_len, n, cudaMemcpyHostToDevice, st));
+		// cudaMemcpyDefault: the source may be host memory or (unified addressing) a device buffer, e.g. chunk files read straight
+		// into device memory; either way the blocks land densely and 16-byte aligned in the staging tile the fused CRC kernel reads
+		CUDA_TRY(cudaMemcpy2DAsync(d_in, dstride, h_data + h_offset + b0 * h_stride, h_stride, block_len, n, cudaMemcpyDefault, st));
 		CUDA_TRY(cudaMemcpy2DAsync(d_s, 4, reinterpret_cast<const uint8_t *>(h_stored) + b0 * stored_stride_bytes, stored_stride_bytes, 4, n,
-		                           cudaMemcpyHostToDevice, st));
+		                           cudaMemcpyDefault, st));
 		CUDA_TRY(cudaMemcpyAsync(ctx->d_first_bad, &init, sizeof(init), cudaMemcpyHostToDevice, st));
 		if ((rc = lzgpu_crc_blocks_dev(ctx, d_in, n, block_len, dstride, d_c, st))) return rc;
 		crc_compare_kernel<<<grid_for(ctx, n, 256, 4), 256, 0, st>>>(static_cast<const uint32_t *>(d_c), static_cast<const uint32_t *>(d_s), n,

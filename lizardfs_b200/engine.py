@@ -461,6 +461,14 @@ class Engine:
             raise ChunkCrcError(rc, "verify_interleaved", (bad.value,))
         _check(rc, "verify_interleaved")
 
+    def verify_interleaved_ptr(self, ptr, n_blocks):
+        """same, `ptr` = raw address of the records: host memory or a device buffer of this engine's device"""
+        bad = C.c_int64(-1)
+        rc = self.lib.lzgpu_verify_interleaved(self.h, ptr, n_blocks, C.byref(bad))
+        if rc == _lib.ERR_CRC:
+            raise ChunkCrcError(rc, "verify_interleaved", (bad.value,))
+        _check(rc, "verify_interleaved")
+
     def moosefs_header_size(self, data_parts=1):
         return int(self.lib.lzgpu_moosefs_header_size(data_parts))
 

@@ -61,6 +61,28 @@ def main():
                           [(0x12345678, 0x9ABCDEF0, 1), (0xDEADBEEF, 0x01020304, 65535), (0xFFFFFFFF, 0, 65536), (1, 2, 65537), (0xCAFEBABE, 0x0BADF00D, 1 << 26)]]
     out["write_data_prefix"] = [[list(a), O.write_data_prefix(ref, *a).tobytes().hex()] for a in
                                 [(0x1122334455667788, 7, 3, 0, 65536, 0xAABBCCDD), (1, 0xFFFFFFFF, 1023, 4096, 61440, 0), (2**63 + 5, 12, 0, 0, 1, 0xD7978EEB)]]
+    # planner-level rows: the reference's own ChunkReadPlanner / SliceRecoveryPlanner executed in memory (oracle/ref_plans.cc)
+    from tests.test_oracle_plans import GOALS, make_slice, ref_sources, true_blocks
+    plans = []
+    for src_name, lost, nb, dst_name, seed in [("ec(3,2)", (0, 2), 10, "ec(8,2)", 31), ("ec(8,2)", (1, 4), 19, "ec(3,2)", 32), ("xor3", (1,), 10, "ec(5,3)", 33),
+                                               ("std", (), 9, "xor2", 34), ("ec(5,3)", (0, 1, 4), 11, "std", 35), ("ec(8,2)", (8,), 16, "ec(8,2)", 36)]:
+        src, dst = GOALS[src_name], GOALS[dst_name]
+        chunk = O.fill_chunk(oracle, nb * BLOCK, seed, 0)
+        parts, _ = make_slice(oracle, src, chunk)
+        sources = ref_sources(src, parts, nb, lost)
+        case = {"src": src_name, "lost": list(lost), "nb": nb, "dst": dst_name, "seed": seed, "parts": []}
+        if src[0] != 2:
+            image = O.plan_read_chunk(ref, sources, 0, nb)
+            case["image_sha256"] = hashlib.sha256(image.tobytes()).hexdigest()
+        for part in range(dst[1] + dst[2]):
+            nblk = true_blocks(dst, part, nb)
+            if nblk == 0:
+                case["parts"].append(None)
+                continue
+            data, crc = O.plan_recover_part(ref, sources, O.slice_type(*dst), O.ref_part_number(dst[0], dst[1], part), 0, nblk)
+            case["parts"].append({"blocks": nblk, "sha256": hashlib.sha256(data.tobytes()).hexdigest(), "crc": [int(x) for x in crc]})
+        plans.append(case)
+    out["planner_cases"] = plans
     with open(os.path.join(os.path.dirname(__file__), "vectors.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("wrote vectors.json with", len(out["cases"]), "cases")

@@ -136,6 +136,26 @@ def test_scrub_exact_sparse_rule(eng, oracle):
     eng.verify_interleaved(rec)
 
 
+def test_scrub_of_device_resident_records(eng):
+    """a chunk file that already sits in device memory is scrubbed in place (no host round trip)"""
+    rng = np.random.default_rng(5)
+    n = 33
+    rec = np.zeros((n, 4 + BLOCK), dtype=np.uint8)
+    for i in range(n):
+        rec[i, 4:] = rng.integers(0, 256, BLOCK, dtype=np.uint8)
+        rec[i, :4] = np.frombuffer(zlib.crc32(rec[i, 4:].tobytes()).to_bytes(4, "big"), dtype=np.uint8)
+    rec[9] = 0                                          # a hole
+    d = eng.dev_alloc(rec.size)
+    eng.upload(d, rec)
+    eng.verify_interleaved_ptr(d, n)
+    rec[20, 777] ^= 1
+    eng.upload(d, rec)
+    with pytest.raises(L.ChunkCrcError) as ei:
+        eng.verify_interleaved_ptr(d, n)
+    assert ei.value.where == (20,)
+    eng.dev_free(d)
+
+
 @pytest.mark.parametrize("data_parts", [1, 3, 8])
 def test_scrub_moosefs_format(eng, oracle, data_parts):
     header = eng.moosefs_header_size(data_parts)
@@ -201,3 +221,21 @@ def test_write_blocks_matches_hdd_write(eng, oracle):
     assert st == [L._lib.ERR_ARG]
     with pytest.raises(L.LzGpuError):
         eng.write_blocks(blocks, stored, [dict(block=1, offset=0, data=np.zeros(4, np.uint8), crc=0), dict(block=1, offset=8, data=np.zeros(4, np.uint8), crc=0)])
+
+
+@pytest.mark.parametrize("idx", range(6))
+def test_convert_and_degraded_read_match_committed_reference_vectors(eng, oracle, idx):
+    """the GPU engine against tests/golden/vectors.json "planner_cases" (outputs of the reference's own planners)"""
+    from tests.test_oracle_plans import check_against_golden_case, golden_planner_cases
+    case = golden_planner_cases()[idx]
+    src, dst = GOALS[case["src"]], GOALS[case["dst"]]
+    nb = case["nb"]
+    chunk = O.fill_chunk(oracle, nb * BLOCK, case["seed"], 0)
+    sparts, _ = make_slice(oracle, src, chunk)
+    parts = [None if i in case["lost"] else sparts[i][None, :] for i in range(len(sparts))]
+    out, ocrc = eng.convert_chunks(slice_of(case["src"]), slice_of(case["dst"]), nb, parts, [1] * (dst[1] + dst[2]))
+    image = None
+    if src[0] != 2:
+        _, img = eng.recover_chunks(slice_of(case["src"]), nb, parts, want=[0] * (src[1] + src[2]), chunk_image=True)
+        image = img[0]
+    check_against_golden_case(case, [o[0] for o in out], [c[0] for c in ocrc], image)
