@@ -279,6 +279,14 @@ def test_recover_all_patterns(eng, oracle, text, nblocks):
         patterns = [patterns[i] for i in rng.choice(len(patterns), size=40, replace=False)]
     if text == "ec(8,2)":
         patterns = [p for p in itertools.combinations(range(8), 2)]  # all 28 data pairs (BASELINE config 4)
+    if text == "ec(5,3)":
+        # every way of losing up to 3 of the 8 parts, as tests/test_suites/ShortSystemTests/test_ec_read_combinations.sh does by
+        # stopping every 3-of-8 combination of chunkservers; data = the reference fixture pattern (every int32 equals its own
+        # byte offset in the chunk, src/unittests/plan_tester.cc:186-305)
+        patterns = [p for r in range(1, 4) for p in itertools.combinations(range(8), r)]
+        data = np.stack([(np.arange(nblocks * BLOCK // 4, dtype=np.uint32) * 4 + c * (1 << 26)).view(np.uint8) for c in range(2)])
+        parity, crc = eng.encode_chunks(goal, data)
+        parts = all_parts(data, parity, k)
     for lost in patterns:
         avail = [None if i in lost else parts[i] for i in range(k + m)]
         want = [1 if i in lost else 0 for i in range(k + m)]
