@@ -78,6 +78,16 @@ int lzgpu_chunk_part_id(const lzgpu_goal *g, int part);   /* ChunkPartType id = 
 uint32_t lzgpu_part_blocks(const lzgpu_goal *g, int part, uint32_t blocks_in_chunk); /* slice_traits.h:311-316 */
 uint32_t lzgpu_part_length(const lzgpu_goal *g, int part, uint32_t chunk_length);    /* slice_traits.h:332-349 */
 
+/* Diagnostics: how lzgpu_encode_chunks_dev would lay a batch out on the GPU (pure host logic, works without a device).
+ * mode 0: a unit is `stripes_per_unit` stripes of one chunk; 1 ("flat"): contiguous whole-stripe chunks are one run of stripes;
+ * 2 ("striped"): a run of global stripes for any chunk length / stride, one TMA box per stripe.  striped_policy: -1 automatic
+ * (what the library does unless LZGPU_STRIPED is set), 0 never, 1 always.  fused = 0: the generic kernels take the shape. */
+typedef struct lzgpu_encode_plan {
+	int fused, mode;
+	uint32_t stripes_per_unit, threads_per_cta, units, stage_rows, smem_bytes;
+} lzgpu_encode_plan;
+int lzgpu_plan_encode(const lzgpu_goal *g, uint32_t n_chunks, uint32_t nb, size_t chunk_stride, int striped_policy, lzgpu_encode_plan *out);
+
 /* ---------------------------------------------------------------------------------------------
  * Engine context: one per (process, device).  Owns streams, pinned staging and device scratch.
  * lzgpu_default_ctx() lazily creates a context on the current device (LZGPU_DEVICE env or 0) for

@@ -27,6 +27,11 @@ class LzStats(C.Structure):
                 ("chunks_encoded", C.c_uint64), ("chunks_recovered", C.c_uint64), ("blocks_crc", C.c_uint64)]
 
 
+class LzEncodePlan(C.Structure):
+    _fields_ = [("fused", C.c_int), ("mode", C.c_int), ("stripes_per_unit", C.c_uint32), ("threads_per_cta", C.c_uint32),
+                ("units", C.c_uint32), ("stage_rows", C.c_uint32), ("smem_bytes", C.c_uint32)]
+
+
 class LzBlockWrite(C.Structure):
     _fields_ = [("block", C.c_uint32), ("offset", C.c_uint32), ("size", C.c_uint32), ("crc", C.c_uint32),
                 ("payload_off", C.c_uint64), ("exists", C.c_uint32), ("status", C.c_int32)]
@@ -40,6 +45,7 @@ _goalp = C.POINTER(LzGoal)
 SIGNATURES = {
     "lzgpu_goal_parse": (_int, [C.c_char_p, _goalp]),
     "lzgpu_goal_valid": (_int, [_goalp]),
+    "lzgpu_plan_encode": (_int, [_goalp, _u32, _u32, _sz, _int, _vp]),
     "lzgpu_goal_slice_type": (_int, [_goalp]),
     "lzgpu_goal_from_slice_type": (_int, [_int, _goalp]),
     "lzgpu_ref_part_index": (_int, [_goalp, _int]),

@@ -19,7 +19,6 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // two CTAs per SM: 228 KiB per SM minus 1 KiB reserved per CTA
-constexpr int kSmemCap = 113 * 1024;
 constexpr int kSmemCap128 = 226 * 1024;       // FW = 128 variant: one CTA per SM
 constexpr int kRecoverSmemCap = 200 * 1024;  // recover kernel: one CTA per SM, 6 stages
 constexpr int kRecoverSmemCap2 = 100 * 1024; // two CTAs per SM, 3 stages (E <= 2)
@@ -159,26 +158,6 @@ void lz_fused_destroy(lzgpu_ctx *ctx) {
 	ctx->fused = nullptr;
 }
 
-static size_t fused_smem_bytes(uint32_t rows, uint32_t prows, int fw) {
-	const size_t pstage = (static_cast<size_t>(prows) * kStepBytes + 1023) & ~size_t(1023);
-	const size_t nst = fused_nst(fw), npst = fused_npst(fw);
-	return nst * rows * kStepBytes + npst * pstage + 520 + 8 * (2 * nst + 2 * npst);
-}
-
-// Largest stripe group G such that data + parity-CRC rows fit the consumer threads, the data rows fit
-// one TMA box (<= 256 rows, a multiple of 8 for the 1024-byte stage alignment) and the stages fit shared memory.
-static uint32_t pick_group(uint32_t K, uint32_t PC, int max_smem_per_cta, int fw, uint32_t threads) {
-	uint32_t best = 0;
-	for (uint32_t g = 1; g <= 64; ++g) {
-		const uint32_t rows = g * K * 4, prows = g * PC * 4;
-		if (rows > kMaxRows || rows + prows > threads || prows > kMaxParityRows || g * K > 64) break;
-		if (rows % 8) continue;
-		if (fused_smem_bytes(rows, prows, fw) > static_cast<size_t>(max_smem_per_cta)) break;
-		best = g;
-	}
-	return best;
-}
-
 static int make_tensor_map(FusedState *fs, CUtensorMap *map, const void *base, uint64_t rows_per_chunk, uint64_t n_chunks,
                            uint64_t chunk_stride, uint32_t box_rows) {
 	const cuuint64_t dims[3] = {static_cast<cuuint64_t>(kRowBytes), rows_per_chunk, n_chunks};
@@ -230,9 +209,11 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	const uint32_t PC = M == 0 ? 0 : (generic ? M : M - 1);
 	const int fw = choose_fold(fs, M, generic);
 	const int smem_cap = std::min(fs->max_smem, fw == 64 ? kSmemCap : kSmemCap128);
-	const uint32_t G = pick_group(K, PC, smem_cap, fw, static_cast<uint32_t>(fused_threads(generic ? 4 : M)));
-	if (G == 0) return LZGPU_NOT_HANDLED;
-	if ((chunk_stride % 16) || (reinterpret_cast<uintptr_t>(d_data) % 16)) return LZGPU_NOT_HANDLED;
+	// unit geometry: per-chunk, flat or striped units, stripes per unit (fused_plan.h; unit-tested without a GPU)
+	const FusedPlan pl = fused_plan(M, generic, K, n_chunks, nb, chunk_stride, smem_cap, fw, fs->striped);
+	if (!pl.ok || (reinterpret_cast<uintptr_t>(d_data) % 16)) return LZGPU_NOT_HANDLED;
+	const uint32_t G = pl.G;
+	const bool flat = pl.mode == 1u, striped = pl.mode == 2u;
 	FusedParams p{};
 	p.parity = static_cast<uint8_t *>(d_parity);
 	p.crc = static_cast<uint32_t *>(d_crc);
@@ -241,35 +222,13 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	p.crc_stride = crc_stride;
 	p.n_chunks = n_chunks;
 	p.nb = nb;
-	p.pb = (nb + K - 1) / K;
+	p.pb = pl.pb;
 	p.K = K;
 	p.G = G;
-	// flat mode: contiguous chunks made of whole stripes are one run of n_chunks*pb stripes (small chunks then fill the
-	// G-stripe units instead of leaving most TMA rows out of range)
-	const bool flat = n_chunks > 1 && chunk_stride == static_cast<size_t>(nb) * LZGPU_BLOCK_SIZE && nb % K == 0 &&
-	                  static_cast<uint64_t>(n_chunks) * p.pb < (1ull << 31) && static_cast<uint64_t>(n_chunks) * nb * 4 < (1ull << 31);  // TMA coordinates are int32
-	p.flat = flat ? 1u : 0u;
+	p.flat = pl.mode;
 	p.flat_magic = (1ull << 40) / p.pb + 1;
-	// striped mode: the same run of global stripes for ANY nb / chunk stride, loaded one stripe box at a time; chosen when
-	// per-chunk units would leave more than 12 % of their stripe slots empty (small or ragged chunks).  Measured
-	// (profiles/sweep_r1.md): G boxes per step instead of one cost 2-10 % at 64 MiB, and win up to 2.4x at 1-4 MiB.
-	if (!flat && M > 0 && static_cast<uint64_t>(n_chunks) * p.pb < (1ull << 31) && static_cast<uint64_t>(nb) * 4 < (1ull << 31)) {
-		const uint64_t per_chunk_slots = static_cast<uint64_t>((p.pb + G - 1) / G) * G * n_chunks;
-		const uint64_t stripes = static_cast<uint64_t>(n_chunks) * p.pb;
-		const bool wasteful = per_chunk_slots * 100 > stripes * 112;
-		if (fs->striped == 1 || (fs->striped < 0 && wasteful)) p.flat = 2u;
-	}
-	const bool striped = p.flat == 2u;
-	uint64_t total;
-	if (flat || striped) {
-		p.units_per_chunk = static_cast<uint32_t>((static_cast<uint64_t>(n_chunks) * p.pb + G - 1) / G);
-		total = p.units_per_chunk;
-	} else {
-		p.units_per_chunk = (p.pb + G - 1) / G;
-		total = static_cast<uint64_t>(p.units_per_chunk) * n_chunks;
-	}
-	if (total > 0x7fffffffull) return LZGPU_NOT_HANDLED;
-	p.total_units = static_cast<uint32_t>(total);
+	p.units_per_chunk = pl.units_per_chunk;
+	p.total_units = pl.total_units;
 	std::memcpy(p.qmult, fw == 64 ? fs->qmult64 : fs->qmult128, sizeof(p.qmult));
 	p.zconst = lz::crc_of_zeros(LZGPU_BLOCK_SIZE);
 	p.probe = fs->probe;
@@ -289,7 +248,8 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	int rc = flat ? make_tensor_map(fs, &map, d_data, static_cast<uint64_t>(n_chunks) * nb * 4, 1, 0, rows)
 	              : make_tensor_map(fs, &map, d_data, static_cast<uint64_t>(nb) * 4, n_chunks, chunk_stride, striped ? K * 4 : rows);
 	if (rc) return rc;
-	const size_t smem = fused_smem_bytes(rows, G * PC * 4, fw);
+	const size_t smem = pl.smem;
+	(void)PC;
 	if (striped) {
 		if (generic) return launch<4, true, 0, 0, 64, true>(ctx, map, p, smem, st);
 #define LZ_FOLDED_STRIPED(MM, KK, GG) \

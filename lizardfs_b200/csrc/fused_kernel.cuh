@@ -37,6 +37,7 @@
 #include <cuda.h>
 
 #include "device_math.cuh"
+#include "fused_plan.h"
 
 namespace lzd {
 
@@ -57,25 +58,6 @@ namespace lzd {
 #define LZ_RING_ARRIVERS 1u
 #define LZ_RING_LANE(lane) ((lane) == 0)
 #endif
-
-constexpr int kStepBytes = 128;
-constexpr int kRowBytes = 16384;
-constexpr int kStepsPerUnit = kRowBytes / kStepBytes;  // 128
-constexpr int kConsumers = 288;                        // 9 warps, all consumers (2 CTAs/SM -> 112 registers per thread)
-constexpr int kFusedThreads = kConsumers;
-// Three or four parity rows keep 12-16 Horner accumulators live next to the 64-word CRC window: at 96 registers the kernel
-// spills into its inner loop (ncu: long-scoreboard stalls on the local loads, profiles/ec84_r1_ncu_summary.md).  Those
-// shapes run with 8 warps instead of 9, which lets two CTAs per SM have 128 registers per thread.
-__host__ __device__ constexpr int fused_threads(int m) { return m >= 3 ? 256 : kConsumers; }
-constexpr int kMaxRows = 256;                          // TMA box limit per dimension
-// pipeline depth by fold window: FW = 64 -> 2 CTAs/SM (96 registers), 3 data stages + 4-deep parity ring;
-// FW = 128 -> 1 CTA/SM (the 128-word window needs ~170 registers), 6 data stages + 6-deep parity ring
-__host__ __device__ constexpr int fused_nst(int fw) { return fw == 64 ? 3 : 6; }
-#ifndef LZ_NPST
-#define LZ_NPST 4
-#endif
-__host__ __device__ constexpr int fused_npst(int fw) { return fw == 64 ? LZ_NPST : 6; }
-constexpr int kMaxParityRows = 128;
 
 struct FusedParams {
 	uint8_t *parity;         // part-major parity output (chunk c at + c*parity_stride)

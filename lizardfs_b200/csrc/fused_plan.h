@@ -1,0 +1,104 @@
+// fused_plan.h — geometry of the fused encode kernel as pure functions (no CUDA calls): which unit mode a batch gets, how many
+// stripes a unit holds, how many units there are.  Shared by the launcher (fused.cu) and the diagnostics entry point
+// lzgpu_plan_encode (engine side), so the decisions are unit-tested on a machine without a GPU (tests/test_host_math.py).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+#ifndef __CUDACC__
+#define LZ_HD
+#else
+#define LZ_HD __host__ __device__
+#endif
+
+namespace lzd {
+
+constexpr int kStepBytes = 128;
+constexpr int kRowBytes = 16384;
+constexpr int kStepsPerUnit = kRowBytes / kStepBytes;  // 128
+constexpr int kConsumers = 288;                        // 9 warps, all consumers (2 CTAs/SM -> 112 registers per thread)
+constexpr int kFusedThreads = kConsumers;
+constexpr int kMaxRows = 256;                          // TMA box limit per dimension
+constexpr int kMaxParityRows = 128;
+constexpr int kSmemCap = 113 * 1024;                   // dynamic shared memory per CTA with two CTAs per SM
+
+// Three or four parity rows keep 12-16 Horner accumulators live next to the 64-word CRC window: at 96 registers the kernel
+// spills into its inner loop (ncu: long-scoreboard stalls on the local loads, profiles/ec84_r1_ncu_summary.md).  Those
+// shapes run with 8 warps instead of 9, which lets two CTAs per SM have 128 registers per thread.
+LZ_HD constexpr int fused_threads(int m) { return m >= 3 ? 256 : kConsumers; }
+
+// pipeline depth by fold window: FW = 64 -> 2 CTAs/SM (96 registers), 3 data stages + 4-deep parity ring;
+// FW = 128 -> 1 CTA/SM (the 128-word window needs ~170 registers), 6 data stages + 6-deep parity ring
+#ifndef LZ_NPST
+#define LZ_NPST 4
+#endif
+LZ_HD constexpr int fused_nst(int fw) { return fw == 64 ? 3 : 6; }
+LZ_HD constexpr int fused_npst(int fw) { return fw == 64 ? LZ_NPST : 6; }
+
+inline size_t fused_smem_bytes(uint32_t rows, uint32_t prows, int fw) {
+	const size_t pstage = (static_cast<size_t>(prows) * kStepBytes + 1023) & ~size_t(1023);
+	const size_t nst = fused_nst(fw), npst = fused_npst(fw);
+	return nst * rows * kStepBytes + npst * pstage + 520 + 8 * (2 * nst + 2 * npst);
+}
+
+// Largest stripe group G such that data + parity-CRC rows fit the consumer threads, the data rows fit
+// one TMA box (<= 256 rows, a multiple of 8 for the 1024-byte stage alignment) and the stages fit shared memory.
+inline uint32_t pick_group(uint32_t K, uint32_t PC, int max_smem_per_cta, int fw, uint32_t threads) {
+	uint32_t best = 0;
+	for (uint32_t g = 1; g <= 64; ++g) {
+		const uint32_t rows = g * K * 4, prows = g * PC * 4;
+		if (rows > kMaxRows || rows + prows > threads || prows > kMaxParityRows || g * K > 64) break;
+		if (rows % 8) continue;
+		if (fused_smem_bytes(rows, prows, fw) > static_cast<size_t>(max_smem_per_cta)) break;
+		best = g;
+	}
+	return best;
+}
+
+// Unit geometry of one launch.  mode 0: a unit is G stripes of ONE chunk (out-of-range rows zero-filled by TMA);
+// mode 1 ("flat"): chunks are contiguous and made of whole stripes, the batch is one run of n_chunks*pb stripes in one
+// 2-D tensor; mode 2 ("striped"): the same run of global stripes for any nb / stride, one TMA box per stripe.
+struct FusedPlan {
+	uint32_t G = 0, pb = 0, mode = 0, units_per_chunk = 0, total_units = 0, threads = 0, rows = 0, prows = 0;
+	size_t smem = 0;
+	bool ok = false;  // false: the fused kernel does not take this shape (generic kernels do)
+};
+
+// striped_policy: -1 automatic (striped when per-chunk units would leave more than 12 % of their stripe slots empty — measured,
+// profiles/sweep_r1.md: G boxes per step instead of one cost 2-10 % at 64 MiB and win up to 2.4x at 1-4 MiB), 0 never, 1 always
+inline FusedPlan fused_plan(int M, bool generic, uint32_t K, uint32_t n_chunks, uint32_t nb, size_t chunk_stride, int smem_cap, int fw,
+                            int striped_policy) {
+	FusedPlan pl;
+	const uint32_t PC = M == 0 ? 0 : (generic ? M : M - 1);
+	pl.threads = static_cast<uint32_t>(fused_threads(generic ? 4 : M));
+	pl.G = pick_group(K, PC, smem_cap, fw, pl.threads);
+	if (pl.G == 0 || (chunk_stride % 16)) return pl;
+	const uint32_t G = pl.G;
+	pl.pb = (nb + K - 1) / K;
+	const bool flat = n_chunks > 1 && chunk_stride == static_cast<size_t>(nb) * 65536u && nb % K == 0 &&
+	                  static_cast<uint64_t>(n_chunks) * pl.pb < (1ull << 31) && static_cast<uint64_t>(n_chunks) * nb * 4 < (1ull << 31);  // TMA coordinates are int32
+	pl.mode = flat ? 1u : 0u;
+	if (!flat && M > 0 && static_cast<uint64_t>(n_chunks) * pl.pb < (1ull << 31) && static_cast<uint64_t>(nb) * 4 < (1ull << 31)) {
+		const uint64_t per_chunk_slots = static_cast<uint64_t>((pl.pb + G - 1) / G) * G * n_chunks;
+		const uint64_t stripes = static_cast<uint64_t>(n_chunks) * pl.pb;
+		const bool wasteful = per_chunk_slots * 100 > stripes * 112;
+		if (striped_policy == 1 || (striped_policy < 0 && wasteful)) pl.mode = 2u;
+	}
+	uint64_t total;
+	if (pl.mode != 0) {
+		pl.units_per_chunk = static_cast<uint32_t>((static_cast<uint64_t>(n_chunks) * pl.pb + G - 1) / G);
+		total = pl.units_per_chunk;
+	} else {
+		pl.units_per_chunk = (pl.pb + G - 1) / G;
+		total = static_cast<uint64_t>(pl.units_per_chunk) * n_chunks;
+	}
+	if (total > 0x7fffffffull) return pl;
+	pl.total_units = static_cast<uint32_t>(total);
+	pl.rows = G * K * 4;
+	pl.prows = G * PC * 4;
+	pl.smem = fused_smem_bytes(pl.rows, pl.prows, fw);
+	pl.ok = true;
+	return pl;
+}
+
+}  // namespace lzd

@@ -1,6 +1,7 @@
 // host_math.cc — see host_math.h.  Written from the mathematical definitions; results are
 // checked against the oracle and the compiled reference in tests/test_host_math.py.
 #include "host_math.h"
+#include "fused_plan.h"
 
 #include <cctype>
 #include <cstdio>
@@ -301,6 +302,24 @@ uint32_t lzgpu_part_length(const lzgpu_goal *g, int part, uint32_t chunk_length)
 	uint32_t mine = tail > idx * B ? tail - idx * B : 0;
 	if (mine > B) mine = B;
 	return whole * B + mine;
+}
+
+// Diagnostics: the unit geometry lzgpu_encode_chunks_dev would use for a batch (pure host logic, no device needed).
+int lzgpu_plan_encode(const lzgpu_goal *g, uint32_t n_chunks, uint32_t nb, size_t chunk_stride, int striped_policy, lzgpu_encode_plan *out) {
+	if (!out || !lzgpu_goal_valid(g) || nb == 0 || nb > LZGPU_BLOCKS_IN_CHUNK) return LZGPU_ERR_ARG;
+	*out = lzgpu_encode_plan{};
+	if (g->m > 4) return LZGPU_OK;  // five or more parity parts: generic kernels (fused = 0)
+	const bool cauchy = lz::uses_cauchy(g->k, g->m);
+	const lzd::FusedPlan pl = lzd::fused_plan(cauchy ? 4 : g->m, cauchy, static_cast<uint32_t>(g->k), n_chunks, nb, chunk_stride, lzd::kSmemCap, 64, striped_policy);
+	if (!pl.ok) return LZGPU_OK;
+	out->fused = 1;
+	out->mode = static_cast<int>(pl.mode);
+	out->stripes_per_unit = pl.G;
+	out->threads_per_cta = pl.threads;
+	out->units = pl.total_units;
+	out->stage_rows = pl.rows;
+	out->smem_bytes = static_cast<uint32_t>(pl.smem);
+	return LZGPU_OK;
 }
 
 const char *lzgpu_version(void) { return "lizardfs_b200 0.1 (sm_100a)"; }

@@ -156,3 +156,42 @@ def test_moosefs_header_size_matches_chunk_cc(oracle):
     for parts in range(1, 33):
         assert lib.lzgpu_moosefs_header_size(parts) == O.moosefs_header_size(oracle, parts)
     assert lib.lzgpu_moosefs_header_size(0) == 0 and lib.lzgpu_moosefs_header_size(33) == 0
+
+
+def _plan(text, n_chunks, nb, stride_blocks=None, policy=-1):
+    g = L.SliceType(text)
+    out = L._lib.LzEncodePlan()
+    stride = (stride_blocks if stride_blocks is not None else nb) * BLOCK
+    assert L._lib.load().lzgpu_plan_encode(C.byref(g.c), n_chunks, nb, stride, policy, C.byref(out)) == 0
+    return out
+
+
+def test_encode_unit_geometry_decisions():
+    """The launcher's host logic (csrc/fused_plan.h) without a GPU: stripes per unit, CTA size, and which unit mode a batch gets
+    (per-chunk / flat / striped) for the BASELINE.json configurations and the ragged cases the sweep measures."""
+    # stripes per unit: rows = G*k*4 <= 256 (one TMA box), data + parity-CRC rows <= threads, stages fit 113 KB
+    for text, G, threads in [("ec(8,2)", 8, 288), ("xor2", 32, 288), ("xor3", 20, 288), ("ec(3,2)", 16, 288), ("ec(4,2)", 14, 288),
+                             ("ec(6,2)", 10, 288), ("ec(5,3)", 8, 256), ("ec(6,3)", 8, 256), ("ec(8,4)", 5, 256)]:
+        p = _plan(text, 128, 1024)
+        assert (p.fused, p.stripes_per_unit, p.threads_per_cta) == (1, G, threads), text
+        k = L.SliceType(text).k
+        assert p.stage_rows == G * k * 4 and p.stage_rows % 8 == 0 and p.smem_bytes <= 113 * 1024
+    # configs[2]: 512 contiguous 64 MiB chunks of ec(8,2) are whole stripes -> one flat run of 512*128 stripes
+    p = _plan("ec(8,2)", 512, 1024)
+    assert (p.mode, p.units) == (1, 512 * 128 // 8)
+    # configs[1]: ec(3,2), 342 stripes per chunk (the last one ragged): per-chunk units waste 352/342 - 1 = 2.9 % -> stay per chunk
+    p = _plan("ec(3,2)", 1024, 1024)
+    assert (p.mode, p.units) == (0, 1024 * 22)
+    # 1 MiB chunks of ec(3,2): 6 stripes in 16-stripe units would be 62 % empty -> striped units across chunk boundaries
+    p = _plan("ec(3,2)", 8192, 16)
+    assert (p.mode, p.units) == (2, (8192 * 6 + 15) // 16)
+    assert _plan("ec(3,2)", 8192, 16, policy=0).mode == 0 and _plan("ec(3,2)", 1024, 1024, policy=1).mode == 2
+    # padded strides cannot be flat; whole-stripe small chunks with a dense stride are
+    assert _plan("ec(8,2)", 100, 16).mode == 1 and _plan("ec(8,2)", 100, 16, stride_blocks=20).mode == 2
+    assert _plan("ec(8,2)", 1, 1024).mode == 0                      # a single chunk needs neither
+    # 37 MiB + 5 blocks of ec(8,2): 75 stripes, 80 slots = 6.7 % waste -> per chunk; xor3 4 MiB: 22 stripes in 20-stripe units -> striped
+    assert _plan("ec(8,2)", 219, 597).mode == 0 and _plan("xor3", 2048, 64).mode == 2
+    # Cauchy goal (m = 4, k > 20) runs the bit-plane instantiation with 8 warps; five parity parts leave the fused kernel
+    p = _plan("ec(21,4)", 10, 63)
+    assert p.fused == 1 and p.threads_per_cta == 256
+    assert _plan("ec(4,5)", 10, 64).fused == 0
