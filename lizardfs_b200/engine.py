@@ -394,6 +394,14 @@ class Engine:
         dp = (C.c_void_p * goal.k)(*[p if p else None for p in d_parts])
         _check(self.lib.lzgpu_split_chunks_dev(self.h, C.byref(goal.c), n_chunks, nb, d_data, chunk_stride, dp, part_stride, stream), "split_chunks_dev")
 
+    def plan_encode(self, goal, n_chunks, nb, chunk_stride=None, striped_policy=-1):
+        """how encode_chunks_dev would lay the batch out (pure host logic, csrc/fused_plan.h): dict with fused, mode
+        (0 per-chunk / 1 flat / 2 striped units), stripes_per_unit, threads_per_cta, units, stage_rows, smem_bytes"""
+        out = _lib.LzEncodePlan()
+        stride = nb * BLOCK_SIZE if chunk_stride is None else chunk_stride
+        _check(self.lib.lzgpu_plan_encode(C.byref(goal.c), n_chunks, nb, stride, striped_policy, C.byref(out)), "plan_encode")
+        return {f: getattr(out, f) for f, _ in _lib.LzEncodePlan._fields_}
+
     # ---- replication / slice-type conversion ----------------------------------------------------
     def convert_chunks(self, src, dst, nb, parts, want, part_crc=None, with_crc=True):
         """Rebuild the `want`ed parts of slice type `dst` from the available `parts` of slice type `src`
