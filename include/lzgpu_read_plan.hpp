@@ -40,7 +40,7 @@ struct RequestedPartInfo {  // SliceReadPlan::RequestedPartInfo, slice_read_plan
 
 class ChunkCrcException : public std::runtime_error {  // what the mount throws on a bad block (read_operation_executor.cc:262-264)
 public:
-	ChunkCrcException(const std::string &what, int part, int block) : std::runtime_error(what), part(part), block(block) {}
+	ChunkCrcException(const std::string &what, int bad_part, int bad_block) : std::runtime_error(what), part(bad_part), block(bad_block) {}
 	int part, block;
 };
 
