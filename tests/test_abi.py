@@ -57,3 +57,30 @@ def test_fails_loudly_without_gpu():
     import lizardfs_b200 as L
     with pytest.raises(L.LzGpuError):
         L.Engine(0)
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """ctypes mirrors of the ABI structs (lizardfs_b200/_lib.py) against sizeof / offsetof taken from include/lzgpu.h by the C compiler"""
+    import ctypes as C
+    import subprocess
+    from lizardfs_b200 import _lib
+    structs = {"lzgpu_goal": _lib.LzGoal, "lzgpu_stats": _lib.LzStats, "lzgpu_block_write": _lib.LzBlockWrite, "lzgpu_encode_plan": _lib.LzEncodePlan}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "lzgpu.h"', 'int main(void) {']
+    for name, cls in structs.items():
+        lines.append(f'printf("{name} %zu", sizeof({name}));')
+        for field, _ in cls._fields_:
+            lines.append(f'printf(" %zu", offsetof({name}, {field}));')
+        lines.append('printf("\\n");')
+    lines += ['return 0; }']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    for line in out:
+        if not line:
+            continue
+        name, size, *offsets = line.split()
+        cls = structs[name]
+        assert int(size) == C.sizeof(cls), name
+        assert [int(o) for o in offsets] == [getattr(cls, f).offset for f, _ in cls._fields_], name
