@@ -58,3 +58,27 @@ def test_read_plan_mirror_cpp():
     r = subprocess.run([READ_PLAN], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "all tests passed" in r.stdout
+
+
+def _run_cpu_build(name, needs_ref=False):
+    """The same C++ test source linked against tests/cpp/oracle_backend.cc (a test-only stand-in for the GPU entry points backed
+    by the CPU oracle) instead of liblzgpu.so: covers the HOST logic of the header on a machine without a GPU."""
+    exe = os.path.join(ROOT, "tests", "cpp", "build", name)
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")], check=True)
+    if not os.path.exists(exe):
+        assert needs_ref, f"{name} was not built"
+        pytest.skip("oracle/_ref/liblzref.so was not built (no /root/reference), so the reference planners are unavailable")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all tests passed" in r.stdout
+
+
+def test_stripe_batcher_host_logic_on_cpu():
+    """slot bookkeeping, completeness, read-back blocks, write ids, packet prefixes of lzgpu::StripeBatcher"""
+    _run_cpu_build("test_stripe_batcher_cpu")
+
+
+def test_read_plan_mirror_host_logic_on_cpu():
+    """part numbering, buffer layout, BlockConverter of lzgpu::SliceReadPlan on plans built by the reference's ChunkReadPlanner"""
+    _run_cpu_build("test_read_plan_cpu", needs_ref=True)
