@@ -195,3 +195,35 @@ def test_encode_unit_geometry_decisions():
     p = _plan("ec(21,4)", 10, 63)
     assert p.fused == 1 and p.threads_per_cta == 256
     assert _plan("ec(4,5)", 10, 64).fused == 0
+
+
+def test_encode_unit_geometry_invariants_for_every_goal():
+    """every xor / ec(k, m <= 4) goal, several chunk lengths and batch sizes: the planned geometry always satisfies what the
+    kernel assumes (one TMA box <= 256 rows and a multiple of 8, data + parity-CRC rows fit the CTA, stages fit 113 KB, the units
+    cover every stripe exactly once)"""
+    goals = [f"xor{n}" for n in range(2, 10)] + [f"ec({k},{m})" for k in range(2, 33) for m in range(1, 5)]
+    for text in goals:
+        g = L.SliceType(text)
+        cauchy = g.m == 4 and g.k > 20
+        for n_chunks, nb, stride in [(1, 1024, None), (64, 1024, None), (500, 16, None), (33, 597, None), (7, 13, 16), (1000, 1, None), (3, g.k, None)]:
+            p = _plan(text, n_chunks, nb, stride)
+            threads = 256 if (g.m >= 3 or cauchy) else 288
+            pc0 = g.m if cauchy else g.m - 1
+            if p.fused == 0:
+                # only when no unit fits: an odd k needs TWO stripes per unit for the 8-row alignment of the stage, and
+                # 2*k*4 data rows + 2*pc*4 parity-CRC rows exceed the CTA (ec(31,3), ec(29,4), ec(31,4)): generic kernels
+                assert g.k % 2 == 1 and 2 * g.k * 4 + 2 * pc0 * 4 > threads, text
+                continue
+            G, rows = p.stripes_per_unit, p.stage_rows
+            pc = g.m if cauchy else g.m - 1
+            assert G >= 1 and rows == G * g.k * 4 and rows <= 256 and rows % 8 == 0 and G * g.k <= 64
+            assert rows + G * pc * 4 <= p.threads_per_cta and p.threads_per_cta == (256 if (g.m >= 3 or cauchy) else 288)
+            assert p.smem_bytes <= 113 * 1024
+            pb = -(-nb // g.k)
+            if p.mode == 0:
+                assert p.units == n_chunks * -(-pb // G)
+            else:
+                assert p.units == -(-(n_chunks * pb) // G)
+                if p.mode == 1:
+                    assert nb % g.k == 0 and (stride is None or stride == nb) and n_chunks > 1
+            assert p.units * G >= n_chunks * pb
