@@ -102,7 +102,12 @@ lzgpu_ctx *lzgpu_default_ctx(void);
 const char *lzgpu_last_error(void); /* thread-local text of the last failure */
 const char *lzgpu_version(void);
 
-/* per-context counters (SURVEY.md §5 "metrics") */
+/* per-context counters (SURVEY.md §5 "metrics").  The batch_* fields time the batched entry points on the device: CUDA events
+ * bracket the kernels of every lzgpu_{encode,recover,convert,crc,write}_* call on the stream it runs on (the analogue of the
+ * reference's LOG_AVG_TILL_END_OF_SCOPE timers on this path, src/devtools/request_log.h:401-404 used at
+ * src/common/write_executor.cc:96); finished batches are folded in when the statistics are read, so an asynchronous *_dev
+ * call shows up once its stream has passed it.  GB/s = algorithmic bytes of the batch / device time.
+ * LZGPU_TIMING=0 in the environment switches the events off. */
 typedef struct lzgpu_stats {
 	uint64_t kernel_launches;
 	uint64_t bytes_h2d;
@@ -110,6 +115,12 @@ typedef struct lzgpu_stats {
 	uint64_t chunks_encoded;
 	uint64_t chunks_recovered;
 	uint64_t blocks_crc;
+	uint64_t batches_timed;     /* batched calls whose device time has been collected */
+	uint64_t batch_bytes_last;  /* algorithmic bytes of the most recently finished batch */
+	double batch_ms_total;      /* sum of their device times, milliseconds */
+	double batch_ms_last;
+	double batch_gbps_last;     /* batch_bytes_last / batch_ms_last, GB/s */
+	double batch_gbps_mean;     /* all collected bytes / batch_ms_total */
 } lzgpu_stats;
 void lzgpu_get_stats(lzgpu_ctx *ctx, lzgpu_stats *out);
 void lzgpu_reset_stats(lzgpu_ctx *ctx);
@@ -126,7 +137,12 @@ void lzgpu_reset_stats(lzgpu_ctx *ctx);
  *   crc     chunk c at crc + c*crc_stride (in uint32 elements): nb data-block CRCs in chunk order,
  *           then for r < m the pb CRCs of parity part r.  Host byte order (callers put32bit them).
  * The *_dev variants take device pointers of the context's device, enqueue on `stream`
- * (a cudaStream_t passed as void*, NULL = the context's stream) and do not synchronise.
+ * (a cudaStream_t passed as void*, NULL = the context's stream) and do not synchronise — with one exception: a call that
+ * is given stored CRCs to verify (d_part_crc) waits for its stream and returns LZGPU_ERR_CRC on a mismatch, whether or not
+ * `bad` is supplied, so corrupt input can never pass unnoticed.
+ * Threading: any number of threads may call *_dev functions on one context concurrently (temporaries come from a
+ * stream-ordered pool, results from per-call slots); use a different stream per thread for overlap.  The host-pointer
+ * variants share the context's staging buffers and serialise on an internal lock.
  * lzgpu_encode_chunks_dev zero-fills the rest of a trailing partial block IN the caller's data buffer (the chunk
  * stride must cover whole blocks, and buffers must be 16-byte aligned); nothing else of the inputs is written.
  * The host variants stage through pinned memory (H2D, kernel, D2H) and return when results are
@@ -165,7 +181,7 @@ int lzgpu_recover_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_
                              const void *const *d_part_crc,
                              const uint8_t *want, void *const *d_out,
                              void *d_chunk_out, size_t chunk_out_stride,
-                             int64_t *bad /* host; written after an internal sync only if non-NULL */,
+                             int64_t *bad /* host, optional: chunk, part, block of the first mismatch */,
                              void *stream);
 
 /* Wire-format producer: LIZ_CLTOCS_WRITE_DATA packet prefixes (src/protocol/cltocs.h:116-137) for
@@ -308,6 +324,13 @@ int lzgpu_dev_sync(lzgpu_ctx *ctx);
 /* page-locked host memory for staging buffers that feed the host-pointer entry points (H2D/D2H at full PCIe rate) */
 int lzgpu_host_alloc(lzgpu_ctx *ctx, size_t bytes, void **h_ptr);
 int lzgpu_host_free(lzgpu_ctx *ctx, void *h_ptr);
+/* Page-lock a buffer the caller already owns (a chunkserver's block pool, the mount's write cache) so that the host-pointer
+ * entry points copy at the pinned rate; a buffer that is neither allocated by lzgpu_host_alloc nor registered here takes the
+ * driver's pageable path (staged through bounce buffers, several times slower; bench.py reports both).  Registration costs
+ * about 0.1-0.3 ms per MiB, so it pays for long-lived buffers only.  LZGPU_AUTO_REGISTER=1 in the environment makes the
+ * host-pointer entry points register pageable arguments for the duration of each call (and say so once on stderr). */
+int lzgpu_host_register(lzgpu_ctx *ctx, void *h_ptr, size_t bytes);
+int lzgpu_host_unregister(lzgpu_ctx *ctx, void *h_ptr);
 
 #ifdef __cplusplus
 }

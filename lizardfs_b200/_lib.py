@@ -24,7 +24,9 @@ class LzGoal(C.Structure):
 
 class LzStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("bytes_h2d", C.c_uint64), ("bytes_d2h", C.c_uint64),
-                ("chunks_encoded", C.c_uint64), ("chunks_recovered", C.c_uint64), ("blocks_crc", C.c_uint64)]
+                ("chunks_encoded", C.c_uint64), ("chunks_recovered", C.c_uint64), ("blocks_crc", C.c_uint64),
+                ("batches_timed", C.c_uint64), ("batch_bytes_last", C.c_uint64), ("batch_ms_total", C.c_double),
+                ("batch_ms_last", C.c_double), ("batch_gbps_last", C.c_double), ("batch_gbps_mean", C.c_double)]
 
 
 class LzEncodePlan(C.Structure):
@@ -105,6 +107,8 @@ SIGNATURES = {
     "lzgpu_dev_download": (_int, [_vp, _vp, _vp, _sz]),
     "lzgpu_host_alloc": (_int, [_vp, _sz, _vp]),
     "lzgpu_host_free": (_int, [_vp, _vp]),
+    "lzgpu_host_register": (_int, [_vp, _vp, _sz]),
+    "lzgpu_host_unregister": (_int, [_vp, _vp]),
     "lzgpu_dev_sync": (_int, [_vp]),
 }
 

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -63,6 +64,21 @@ struct DeviceGuard {
 	}
 };
 
+// Pageable caller buffers: optional page-locking for the duration of one host-pointer call (LZGPU_AUTO_REGISTER=1).  Without
+// it such buffers take the driver's pageable copy path; long-lived buffers are better registered once (lzgpu_host_register).
+struct AutoPin {
+	lzgpu_ctx *ctx;
+	std::vector<void *> regs;
+	explicit AutoPin(lzgpu_ctx *c) : ctx(c) {}
+	AutoPin(const AutoPin &) = delete;
+	AutoPin &operator=(const AutoPin &) = delete;
+	void add(const void *p, size_t bytes);
+	~AutoPin() {
+		for (void *p : regs) cudaHostUnregister(p);
+		if (!regs.empty()) cudaGetLastError();
+	}
+};
+
 extern "C" int lzgpu_device_count(void) {
 	int n = 0;
 	if (cudaGetDeviceCount(&n) != cudaSuccess) {
@@ -81,8 +97,32 @@ static int ctx_init_resources(lzgpu_ctx *ctx) {
 	lz::crc_make_tables(tabs);
 	CUDA_TRY(cudaMalloc(&ctx->d_crc_tables, sizeof(tabs)));
 	CUDA_TRY(cudaMemcpy(ctx->d_crc_tables, tabs, sizeof(tabs), cudaMemcpyHostToDevice));
-	CUDA_TRY(cudaMalloc(&ctx->d_first_bad, sizeof(unsigned long long) * LZGPU_MAX_PARTS));
-	CUDA_TRY(cudaMallocHost(&ctx->h_first_bad, sizeof(unsigned long long) * LZGPU_MAX_PARTS));
+	{
+		// stream-ordered pool for the temporaries of the *_dev entry points: kept (no trimming at synchronisation points), so a
+		// steady stream of calls re-uses the same memory without touching the allocator
+		cudaMemPoolProps props{};
+		props.allocType = cudaMemAllocationTypePinned;
+		props.handleTypes = cudaMemHandleTypeNone;
+		props.location.type = cudaMemLocationTypeDevice;
+		props.location.id = ctx->device;
+		CUDA_TRY(cudaMemPoolCreate(&ctx->pool, &props));
+		uint64_t keep = ~0ull;
+		CUDA_TRY(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+	}
+	for (int i = 0; i < 8; ++i) {
+		StatusSlot sl;
+		CUDA_TRY(cudaMalloc(&sl.d, sizeof(unsigned long long) * LZGPU_MAX_PARTS));
+		CUDA_TRY(cudaMallocHost(&sl.h, sizeof(unsigned long long) * LZGPU_MAX_PARTS));
+		sl.index = i;
+		ctx->status_all.push_back(sl);
+		ctx->status_free.push_back(i);
+	}
+	for (auto &t : ctx->timing) {
+		CUDA_TRY(cudaEventCreate(&t.e0));
+		CUDA_TRY(cudaEventCreate(&t.e1));
+	}
+	if (const char *e = std::getenv("LZGPU_TIMING")) ctx->timing_enabled = std::atoi(e);
+	if (const char *e = std::getenv("LZGPU_AUTO_REGISTER")) ctx->auto_register = std::atoi(e);
 	if (lz::crc_of_zeros(LZGPU_BLOCK_SIZE) != kCrcZeroBlock64K) {
 		lz_set_error("internal: CRC constant self-check failed");
 		return LZGPU_ERR_ARG;
@@ -128,12 +168,33 @@ extern "C" void lzgpu_ctx_destroy(lzgpu_ctx *ctx) {
 	lz_fused_destroy(ctx);
 	for (auto &b : ctx->scratch) if (b.ptr) cudaFree(b.ptr);
 	if (ctx->d_crc_tables) cudaFree(ctx->d_crc_tables);
-	if (ctx->d_first_bad) cudaFree(ctx->d_first_bad);
-	if (ctx->h_first_bad) cudaFreeHost(ctx->h_first_bad);
+	for (auto &sl : ctx->status_all) {
+		if (sl.d) cudaFree(sl.d);
+		if (sl.h) cudaFreeHost(sl.h);
+	}
+	for (auto &t : ctx->timing) {
+		if (t.e0) cudaEventDestroy(t.e0);
+		if (t.e1) cudaEventDestroy(t.e1);
+	}
+	if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
 	for (auto &s : ctx->slot_stream) if (s) cudaStreamDestroy(s);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	cudaGetLastError();
 	delete ctx;
+}
+
+void AutoPin::add(const void *p, size_t bytes) {
+	if (!ctx->auto_register || !p || !bytes) return;
+	cudaPointerAttributes a{};
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return; }
+	if (a.type != cudaMemoryTypeUnregistered) return;
+	if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) {
+		regs.push_back(const_cast<void *>(p));
+		static std::atomic<bool> said{false};
+		if (!said.exchange(true)) std::fprintf(stderr, "liblzgpu: LZGPU_AUTO_REGISTER: page-locking pageable caller buffers per call\n");
+	} else {
+		cudaGetLastError();  // e.g. overlapping an existing registration: the copy falls back to the pageable path
+	}
 }
 
 static std::mutex g_default_mu;
@@ -156,14 +217,113 @@ static lzgpu_ctx *need_default(const char *who) {
 	return c;
 }
 
-extern "C" void lzgpu_get_stats(lzgpu_ctx *ctx, lzgpu_stats *out) {
-	if (ctx && out) *out = ctx->stats;
-}
-extern "C" void lzgpu_reset_stats(lzgpu_ctx *ctx) {
-	if (ctx) ctx->stats = lzgpu_stats{};
+// ---- per-batch device timing ------------------------------------------------------------------------------------
+// completed entries of the event ring are folded into the totals (called with timing_mu held)
+static void timing_collect(lzgpu_ctx *ctx, bool wait) {
+	for (auto &t : ctx->timing) {
+		if (!t.pending) continue;
+		cudaError_t q = wait ? cudaEventSynchronize(t.e1) : cudaEventQuery(t.e1);
+		if (q == cudaErrorNotReady) { cudaGetLastError(); continue; }
+		float ms = 0.f;
+		if (q == cudaSuccess && cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) {
+			ctx->batches_timed++;
+			ctx->batch_ms_total += ms;
+			ctx->batch_bytes_total += static_cast<double>(t.bytes);
+			ctx->batch_ms_last = ms;
+			ctx->batch_bytes_last = t.bytes;
+		} else {
+			cudaGetLastError();
+		}
+		t.pending = false;
+	}
 }
 
-// scratch device buffers, grown on demand and kept (slot = purpose)
+BatchTimer::BatchTimer(lzgpu_ctx *c, cudaStream_t s, uint64_t algorithmic_bytes) : ctx(c), st(s), bytes(algorithmic_bytes) {
+	if (!ctx->timing_enabled) return;
+	// events recorded into a stream that is being captured would become graph nodes of their own: a captured call is not timed
+	cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+	if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) { cudaGetLastError(); return; }
+	std::lock_guard<std::mutex> lk(ctx->timing_mu);
+	int i = static_cast<int>(ctx->timing_next % kTimingRing);
+	if (ctx->timing[i].pending) {
+		timing_collect(ctx, false);
+		if (ctx->timing[i].pending) return;  // ring full of unfinished batches: this one goes untimed
+	}
+	ctx->timing_next++;
+	if (cudaEventRecord(ctx->timing[i].e0, st) != cudaSuccess) { cudaGetLastError(); return; }
+	idx = i;
+}
+
+BatchTimer::~BatchTimer() {
+	if (idx < 0) return;
+	std::lock_guard<std::mutex> lk(ctx->timing_mu);
+	if (cudaEventRecord(ctx->timing[idx].e1, st) != cudaSuccess) { cudaGetLastError(); return; }
+	ctx->timing[idx].bytes = bytes;
+	ctx->timing[idx].pending = true;
+}
+
+extern "C" void lzgpu_get_stats(lzgpu_ctx *ctx, lzgpu_stats *out) {
+	if (!ctx || !out) return;
+	out->kernel_launches = ctx->stats.kernel_launches.load();
+	out->bytes_h2d = ctx->stats.bytes_h2d.load();
+	out->bytes_d2h = ctx->stats.bytes_d2h.load();
+	out->chunks_encoded = ctx->stats.chunks_encoded.load();
+	out->chunks_recovered = ctx->stats.chunks_recovered.load();
+	out->blocks_crc = ctx->stats.blocks_crc.load();
+	DeviceGuard g(ctx->device);
+	std::lock_guard<std::mutex> lk(ctx->timing_mu);
+	timing_collect(ctx, false);
+	out->batches_timed = ctx->batches_timed;
+	out->batch_ms_total = ctx->batch_ms_total;
+	out->batch_ms_last = ctx->batch_ms_last;
+	out->batch_bytes_last = ctx->batch_bytes_last;
+	out->batch_gbps_last = ctx->batch_ms_last > 0.0 ? static_cast<double>(ctx->batch_bytes_last) / (ctx->batch_ms_last * 1e6) : 0.0;
+	out->batch_gbps_mean = ctx->batch_ms_total > 0.0 ? ctx->batch_bytes_total / (ctx->batch_ms_total * 1e6) : 0.0;
+}
+extern "C" void lzgpu_reset_stats(lzgpu_ctx *ctx) {
+	if (!ctx) return;
+	ctx->stats.kernel_launches = 0; ctx->stats.bytes_h2d = 0; ctx->stats.bytes_d2h = 0;
+	ctx->stats.chunks_encoded = 0; ctx->stats.chunks_recovered = 0; ctx->stats.blocks_crc = 0;
+	DeviceGuard g(ctx->device);
+	std::lock_guard<std::mutex> lk(ctx->timing_mu);
+	timing_collect(ctx, true);
+	ctx->batches_timed = 0; ctx->batch_ms_total = 0.0; ctx->batch_ms_last = 0.0; ctx->batch_bytes_last = 0; ctx->batch_bytes_total = 0.0;
+}
+
+// ---- temporaries and result slots of the *_dev entry points --------------------------------------------------------
+int TmpBuf::alloc(size_t bytes) {
+	cudaError_t e = cudaMallocFromPoolAsync(&p, bytes ? bytes : 16, ctx->pool, st);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		p = nullptr;
+		lz_set_error("cudaMallocFromPoolAsync(%zu) failed: %s", bytes, cudaGetErrorString(e));
+		return LZGPU_ERR_NOMEM;
+	}
+	return LZGPU_OK;
+}
+
+int lz_status_acquire(lzgpu_ctx *ctx, StatusSlot *out) {
+	std::lock_guard<std::mutex> lk(ctx->slot_mu);
+	if (ctx->status_free.empty()) {
+		StatusSlot sl;
+		CUDA_TRY(cudaMalloc(&sl.d, sizeof(unsigned long long) * LZGPU_MAX_PARTS));
+		CUDA_TRY(cudaMallocHost(&sl.h, sizeof(unsigned long long) * LZGPU_MAX_PARTS));
+		sl.index = static_cast<int>(ctx->status_all.size());
+		ctx->status_all.push_back(sl);
+		ctx->status_free.push_back(sl.index);
+	}
+	*out = ctx->status_all[ctx->status_free.back()];
+	ctx->status_free.pop_back();
+	return LZGPU_OK;
+}
+
+void lz_status_release(lzgpu_ctx *ctx, const StatusSlot &s) {
+	if (s.index < 0) return;
+	std::lock_guard<std::mutex> lk(ctx->slot_mu);
+	ctx->status_free.push_back(s.index);
+}
+
+// staging buffers of the host-pointer entry points, grown on demand and kept (slot = purpose; callers hold ctx->mu)
 int lz_scratch(lzgpu_ctx *ctx, int slot, size_t bytes, void **out) {
 	auto &b = ctx->scratch[slot];
 	if (b.size < bytes) {
@@ -195,19 +355,10 @@ static int grid_for(const lzgpu_ctx *ctx, unsigned long long work_items, int thr
 // ------------------------------------------------------------------------------------------------
 // device-level building blocks (all asynchronous on `st`)
 // ------------------------------------------------------------------------------------------------
-static void make_planes(uint8_t c, CoefPlanes *out) {
-	uint8_t v = c;
-	for (int b = 0; b < 8; ++b) {
-		out->plane[b] = v;
-		v = lz::gf_mul_host(v, 2);
-	}
-}
-
 // dst[r] = XOR_j coef[r][j] * src[j]  over the addressing described in DotDesc
 int lz_gf_dot(lzgpu_ctx *ctx, const DotDesc &d, const uint8_t *coef /* n_dst x n_src */, cudaStream_t st) {
 	if (d.n_src < 1 || d.n_src > kMaxSrc || d.n_dst < 1) return LZGPU_ERR_ARG;
 	if (d.total_units == 0) return LZGPU_OK;
-	std::vector<CoefPlanes> planes(static_cast<size_t>(kDotDests) * d.n_src);
 	for (unsigned r0 = 0; r0 < d.n_dst; r0 += kDotDests) {
 		const unsigned nd = std::min<unsigned>(kDotDests, d.n_dst - r0);
 		DotArgs a{};
@@ -218,16 +369,9 @@ int lz_gf_dot(lzgpu_ctx *ctx, const DotDesc &d, const uint8_t *coef /* n_dst x n
 			for (unsigned j = 0; j < d.n_src; ++j) {
 				const uint8_t c = coef[(r0 + r) * d.n_src + j];
 				all_one &= c == 1;
-				make_planes(c, &planes[r * d.n_src + j]);
+				a.coef[r * d.n_src + j] = c;  // the coefficients travel in the kernel parameters; the kernel expands them to planes
 			}
 		}
-		// coefficient planes travel through a per-launch device buffer filled from the host;
-		// cudaMemcpyAsync from pageable memory snapshots the source before returning.
-		void *d_coef = nullptr;
-		int rc = lz_scratch(ctx, kScratchCoef0 + (ctx->coef_rr++ % kCoefSlots), sizeof(CoefPlanes) * kDotDests * kMaxSrc, &d_coef);
-		if (rc != LZGPU_OK) return rc;
-		CUDA_TRY(cudaMemcpyAsync(d_coef, planes.data(), sizeof(CoefPlanes) * nd * d.n_src, cudaMemcpyHostToDevice, st));
-		a.coef = static_cast<const CoefPlanes *>(d_coef);
 		a.total_units = d.total_units;
 		a.src_chunk_stride = d.src_chunk_stride;
 		a.src_block_stride = d.src_block_stride;
@@ -310,10 +454,30 @@ static void goal_parity_rows(const lzgpu_goal *g, uint8_t *rows /* m*k */) {
 // ------------------------------------------------------------------------------------------------
 // batched encode
 // ------------------------------------------------------------------------------------------------
+static int encode_enqueue(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t chunk_len, const void *d_data, size_t chunk_stride,
+                          void *d_parity, size_t parity_stride, void *d_crc, size_t crc_stride, cudaStream_t st);
+
+static uint64_t encode_alg_bytes(const lzgpu_goal *goal, uint32_t n_chunks, uint32_t chunk_len) {
+	// read S, write m*pb*B parity, write 4*(nb + m*pb) CRC bytes
+	const uint64_t B = LZGPU_BLOCK_SIZE, nb = (chunk_len + B - 1) / B, pb = (nb + goal->k - 1) / goal->k;
+	return n_chunks * (static_cast<uint64_t>(chunk_len) + goal->m * pb * B + 4 * (nb + goal->m * pb));
+}
+
 extern "C" int lzgpu_encode_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t chunk_len,
                                         const void *d_data, size_t chunk_stride, void *d_parity, size_t parity_stride,
                                         void *d_crc, size_t crc_stride, void *stream) {
 	NvtxScope nvtx_scope("lzgpu::encode_chunks_dev");
+	if (!ctx || !d_data || !d_parity || !d_crc) return LZGPU_ERR_ARG;
+	int rc = check_goal(goal);
+	if (rc) return rc;
+	DeviceGuard g(ctx->device);
+	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+	BatchTimer timer(ctx, st, n_chunks ? encode_alg_bytes(goal, n_chunks, chunk_len) : 0);
+	return encode_enqueue(ctx, goal, n_chunks, chunk_len, d_data, chunk_stride, d_parity, parity_stride, d_crc, crc_stride, st);
+}
+
+static int encode_enqueue(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t chunk_len, const void *d_data, size_t chunk_stride,
+                          void *d_parity, size_t parity_stride, void *d_crc, size_t crc_stride, cudaStream_t st) {
 	if (!ctx || !d_data || !d_parity || !d_crc) return LZGPU_ERR_ARG;
 	int rc = check_goal(goal);
 	if (rc) return rc;
@@ -328,8 +492,6 @@ extern "C" int lzgpu_encode_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, u
 		lz_set_error("encode: strides too small or buffers not 16-byte aligned");
 		return LZGPU_ERR_ARG;
 	}
-	DeviceGuard g(ctx->device);
-	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
 	// a trailing partial block is zero-extended to a whole block (the pad belongs to the stride)
 	if (chunk_len % B) {
 		CUDA_TRY(cudaMemset2DAsync(const_cast<uint8_t *>(static_cast<const uint8_t *>(d_data)) + chunk_len, chunk_stride, 0,
@@ -390,6 +552,10 @@ extern "C" int lzgpu_encode_chunks(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint3
 	}
 	std::lock_guard<std::mutex> lk(ctx->mu);
 	DeviceGuard g(ctx->device);
+	AutoPin pin(ctx);
+	pin.add(data, static_cast<size_t>(n_chunks - 1) * chunk_stride + chunk_len);
+	pin.add(parity, static_cast<size_t>(n_chunks - 1) * parity_stride + par_bytes);
+	pin.add(crc, (static_cast<size_t>(n_chunks - 1) * crc_stride + n_crc) * 4);
 	// slot pipeline: tile t uses slot t % kHostSlots with its own stream, so the H2D of one tile overlaps the
 	// kernel of the previous and the D2H of the one before (both copy engines + compute busy).
 	const size_t d_chunk_stride = static_cast<size_t>(nb) * B;
@@ -423,77 +589,114 @@ extern "C" int lzgpu_encode_chunks(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint3
 // ------------------------------------------------------------------------------------------------
 // batched recover
 // ------------------------------------------------------------------------------------------------
-extern "C" int lzgpu_recover_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb,
-                                         const void *const *d_parts, size_t part_stride, const void *const *d_part_crc,
-                                         const uint8_t *want, void *const *d_out, void *d_chunk_out, size_t chunk_out_stride,
-                                         int64_t *bad, void *stream) {
-	NvtxScope nvtx_scope("lzgpu::recover_chunks_dev");
-	if (!ctx || !d_parts || !want) return LZGPU_ERR_ARG;
-	int rc = check_goal(goal);
-	if (rc) return rc;
-	if (nb == 0 || nb > LZGPU_BLOCKS_IN_CHUNK) { lz_set_error("nb out of range"); return LZGPU_ERR_ARG; }
-	if (n_chunks == 0) return LZGPU_OK;
+// What a verifying call leaves behind: the result words are copied to the slot's pinned mirror on the call's stream and
+// decoded once that stream has been synchronised (by the public *_dev wrapper, or by the host pipelines when they retire a tile).
+struct VerifyTicket {
+	StatusSlot slot;       // index < 0: nothing was verified
+	bool fused = false;    // fused route: one word (chunk*64 + part)*1024 + block; otherwise one word per part: chunk*blocks + block
+	int n_words = 0;
+	uint32_t blocks = 0;   // blocks per chunk of a verified part (generic encoding)
+	bool active() const { return slot.index >= 0; }
+};
+
+// after the stream of the call has been synchronised: LZGPU_OK or LZGPU_ERR_CRC (+ first bad chunk / part / block); returns the slot
+static int ticket_result(lzgpu_ctx *ctx, VerifyTicket *tk, int64_t *bad) {
+	if (!tk->active()) return LZGPU_OK;
+	long long best_chunk = -1, best_part = -1, best_block = -1;
+	if (tk->fused) {
+		const unsigned long long v = tk->slot.h[0];
+		if (v != ~0ull) {
+			best_chunk = static_cast<long long>(v / (64ull * 1024ull));
+			best_part = static_cast<long long>((v / 1024ull) % 64ull);
+			best_block = static_cast<long long>(v % 1024ull);
+		}
+	} else {
+		for (int i = 0; i < tk->n_words; ++i) {
+			const unsigned long long v = tk->slot.h[i];
+			if (v == ~0ull) continue;
+			const long long c = static_cast<long long>(v / tk->blocks), b = static_cast<long long>(v % tk->blocks);
+			if (best_chunk < 0 || c < best_chunk || (c == best_chunk && i < best_part)) { best_chunk = c; best_part = i; best_block = b; }
+		}
+	}
+	lz_status_release(ctx, tk->slot);
+	tk->slot.index = -1;
+	if (best_chunk < 0) return LZGPU_OK;
+	if (bad) { bad[0] = best_chunk; bad[1] = best_part; bad[2] = best_block; }
+	lz_set_error("CRC mismatch: chunk %lld part %lld block %lld", best_chunk, best_part, best_block);
+	return LZGPU_ERR_CRC;
+}
+
+static void ticket_drop(lzgpu_ctx *ctx, VerifyTicket *tk) {
+	if (tk->active()) lz_status_release(ctx, tk->slot);
+	tk->slot.index = -1;
+}
+
+// enqueue the whole degraded read on `st` without synchronising; *tk describes the pending verification (if any)
+static int recover_enqueue(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb, const void *const *d_parts, size_t part_stride,
+                           const void *const *d_part_crc, const uint8_t *want, void *const *d_out, void *d_chunk_out, size_t chunk_out_stride,
+                           cudaStream_t st, VerifyTicket *tk) {
 	const int k = goal->k, m = goal->m, n = k + m;
 	const uint32_t B = LZGPU_BLOCK_SIZE;
 	const uint32_t pb = (nb + k - 1) / k;
 	if (part_stride < static_cast<size_t>(pb) * B || (part_stride & 15)) { lz_set_error("recover: bad part_stride"); return LZGPU_ERR_ARG; }
-	DeviceGuard g(ctx->device);
-	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+	// validated before anything is enqueued: the fused route scatters the image straight from its stores
+	if (d_chunk_out && (chunk_out_stride < static_cast<size_t>(nb) * B || (chunk_out_stride & 15))) {
+		lz_set_error("recover: chunk_out_stride must cover nb blocks and be a multiple of 16");
+		return LZGPU_ERR_ARG;
+	}
 
 	// ECReadPlan::recoverParts (ec_read_plan.h:126-133): the first k available parts are the inputs,
 	// everything else counts as erased.
 	uint8_t erased[LZGPU_MAX_PARTS] = {0}, wanted[LZGPU_MAX_PARTS] = {0};
 	const uint8_t *src[LZGPU_MAX_DATA];
 	int used = 0;
+	bool any_crc = false;
 	for (int i = 0; i < n; ++i) {
 		if (!d_parts[i] || used >= k) erased[i] = 1;
-		else src[used++] = static_cast<const uint8_t *>(d_parts[i]);
+		else {
+			src[used++] = static_cast<const uint8_t *>(d_parts[i]);
+			// only the parts that are actually read are verified (the reference checks each block it receives,
+			// read_operation_executor.cc:257-269; a surplus part is never requested) — same rule on both routes
+			any_crc |= d_part_crc && d_part_crc[i];
+		}
 	}
 	if (used < k) { lz_set_error("recover: only %d of %d required parts available", used, k); return LZGPU_ERR_TOO_FEW_PARTS; }
+	int rc;
+	if (any_crc) {
+		if ((rc = lz_status_acquire(ctx, &tk->slot))) return rc;
+		CUDA_TRY(cudaMemsetAsync(tk->slot.d, 0xff, sizeof(unsigned long long) * LZGPU_MAX_PARTS, st));
+	}
 
 	// 0. fused route: verify + rebuild the erased data parts + chunk-order image in one pass over the inputs
 	{
 		bool fused_verifying = false;
 		rc = lz_fused_recover(ctx, goal, n_chunks, nb, d_parts, part_stride, d_part_crc, want, d_out, d_chunk_out, chunk_out_stride, st,
-		                      &fused_verifying);
+		                      tk->slot.d, &fused_verifying);
 		if (rc != LZGPU_NOT_HANDLED) {
-			if (rc) return rc;
+			if (rc) { ticket_drop(ctx, tk); return rc; }
 			ctx->stats.chunks_recovered += n_chunks;
-			if (fused_verifying && bad) {
-				CUDA_TRY(cudaMemcpyAsync(ctx->h_first_bad, ctx->d_first_bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-				CUDA_TRY(cudaStreamSynchronize(st));
-				const unsigned long long v = ctx->h_first_bad[0];
-				if (v != ~0ull) {
-					bad[0] = static_cast<int64_t>(v / (64ull * 1024ull));
-					bad[1] = static_cast<int64_t>((v / 1024ull) % 64ull);
-					bad[2] = static_cast<int64_t>(v % 1024ull);
-					lz_set_error("CRC mismatch: chunk %lld part %lld block %lld", (long long)bad[0], (long long)bad[1], (long long)bad[2]);
-					return LZGPU_ERR_CRC;
-				}
+			if (any_crc) {
+				tk->fused = true;
+				tk->n_words = 1;
+				CUDA_TRY(cudaMemcpyAsync(tk->slot.h, tk->slot.d, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 			}
 			return LZGPU_OK;
 		}
 	}
 
-	// 1. verify the stored CRC of every block of every supplied part (read_operation_executor.cc:257-269)
-	bool verifying = false;
-	if (d_part_crc) {
-		void *d_tmp = nullptr;
+	// 1. verify the stored CRC of every block of every part that is read
+	TmpBuf tmp_crc(ctx, st);
+	if (any_crc) {
 		const unsigned long long nblk = static_cast<unsigned long long>(n_chunks) * pb;
-		std::vector<unsigned long long> init(n, ~0ull);
+		if ((rc = tmp_crc.alloc(nblk * 4))) { ticket_drop(ctx, tk); return rc; }
 		for (int i = 0; i < n; ++i) {
-			if (!d_parts[i] || !d_part_crc[i]) continue;
-			if (!verifying) {
-				if ((rc = lz_scratch(ctx, kScratchTmpCrc, nblk * 4, &d_tmp))) return rc;
-				CUDA_TRY(cudaMemcpyAsync(ctx->d_first_bad, init.data(), sizeof(unsigned long long) * n, cudaMemcpyHostToDevice, st));
-				verifying = true;
-			}
-			rc = lz_fused_crc(ctx, d_parts[i], nblk, pb, part_stride, d_tmp, pb, st);
-			if (rc == LZGPU_NOT_HANDLED) rc = lz_crc_blocks(ctx, d_parts[i], nblk, pb, part_stride, B, B, d_tmp, pb, st);
-			if (rc) return rc;
-			crc_compare_kernel<<<grid_for(ctx, nblk, 256, 4), 256, 0, st>>>(static_cast<const uint32_t *>(d_tmp),
+			if (erased[i] || !d_part_crc[i]) continue;
+			rc = lz_fused_crc(ctx, d_parts[i], nblk, pb, part_stride, tmp_crc.p, pb, st);
+			if (rc == LZGPU_NOT_HANDLED) rc = lz_crc_blocks(ctx, d_parts[i], nblk, pb, part_stride, B, B, tmp_crc.p, pb, st);
+			if (rc) { ticket_drop(ctx, tk); return rc; }
+			crc_compare_kernel<<<grid_for(ctx, nblk, 256, 4), 256, 0, st>>>(static_cast<const uint32_t *>(tmp_crc.p),
 			                                                              static_cast<const uint32_t *>(d_part_crc[i]), nblk,
-			                                                              kCrcZeroBlock64K, 0, 0, ctx->d_first_bad + i);
+			                                                              kCrcZeroBlock64K, 0, 0, tk->slot.d + i);
 			CUDA_TRY(cudaGetLastError());
 			ctx->stats.kernel_launches++;
 		}
@@ -502,13 +705,16 @@ extern "C" int lzgpu_recover_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, 
 	// 2. rebuild the wanted parts
 	std::vector<uint8_t *> dst;
 	std::vector<void *> tmp_parts(n, nullptr);
+	std::vector<std::unique_ptr<TmpBuf>> tmp_owned;
 	for (int i = 0; i < n; ++i) {
 		const bool need = (want[i] || (d_chunk_out && i < k)) && !d_parts[i];
 		if (!need) continue;
 		void *o = d_out ? d_out[i] : nullptr;
 		if (!o) {
 			if (!(d_chunk_out && i < k)) continue;  // not requested anywhere
-			if ((rc = lz_scratch(ctx, kScratchTmpPart0 + i, static_cast<size_t>(n_chunks) * part_stride, &o))) return rc;
+			tmp_owned.emplace_back(new TmpBuf(ctx, st));
+			if ((rc = tmp_owned.back()->alloc(static_cast<size_t>(n_chunks) * part_stride))) { ticket_drop(ctx, tk); return rc; }
+			o = tmp_owned.back()->p;
 			tmp_parts[i] = o;
 		}
 		wanted[i] = 1;
@@ -522,6 +728,7 @@ extern "C" int lzgpu_recover_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, 
 		int nrows = lz::rs_recovery_matrix(k, m, erased, wanted, rows, &singular);
 		if (nrows != static_cast<int>(dst.size())) {
 			lz_set_error(singular ? "recover: decode matrix is singular" : "recover: bad erasure pattern");
+			ticket_drop(ctx, tk);
 			return LZGPU_ERR_ARG;
 		}
 		DotDesc d{};
@@ -536,12 +743,11 @@ extern "C" int lzgpu_recover_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, 
 		d.dst_block_stride = B;
 		d.units_per_block = B / 16;
 		d.blocks_per_chunk = pb;
-		if ((rc = lz_gf_dot(ctx, d, rows, st))) return rc;
+		if ((rc = lz_gf_dot(ctx, d, rows, st))) { ticket_drop(ctx, tk); return rc; }
 	}
 
 	// 3. optional chunk-order image (BlockConverter, chunk_read_planner.h:36-70)
 	if (d_chunk_out) {
-		if (chunk_out_stride < static_cast<size_t>(nb) * B || (chunk_out_stride & 15)) { lz_set_error("recover: bad chunk_out_stride"); return LZGPU_ERR_ARG; }
 		GatherArgs ga{};
 		for (int j = 0; j < k; ++j) {
 			const void *p = d_parts[j] ? d_parts[j] : (d_out && d_out[j] ? d_out[j] : tmp_parts[j]);
@@ -558,24 +764,92 @@ extern "C" int lzgpu_recover_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, 
 		ctx->stats.kernel_launches++;
 	}
 	ctx->stats.chunks_recovered += n_chunks;
-
-	if (verifying && bad) {
-		CUDA_TRY(cudaMemcpyAsync(ctx->h_first_bad, ctx->d_first_bad, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, st));
-		CUDA_TRY(cudaStreamSynchronize(st));
-		long long best_chunk = -1, best_part = -1, best_block = -1;
-		for (int i = 0; i < n; ++i) {
-			const unsigned long long v = ctx->h_first_bad[i];
-			if (v == ~0ull) continue;
-			const long long c = static_cast<long long>(v / pb), b = static_cast<long long>(v % pb);
-			if (best_chunk < 0 || c < best_chunk || (c == best_chunk && i < best_part)) { best_chunk = c; best_part = i; best_block = b; }
-		}
-		if (best_chunk >= 0) {
-			bad[0] = best_chunk; bad[1] = best_part; bad[2] = best_block;
-			lz_set_error("CRC mismatch: chunk %lld part %lld block %lld", best_chunk, best_part, best_block);
-			return LZGPU_ERR_CRC;
-		}
+	if (any_crc) {
+		tk->fused = false;
+		tk->n_words = n;
+		tk->blocks = pb;
+		CUDA_TRY(cudaMemcpyAsync(tk->slot.h, tk->slot.d, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, st));
 	}
 	return LZGPU_OK;
+}
+
+static int recover_check_args(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t nb, const void *parts, const uint8_t *want) {
+	if (!ctx || !parts || !want) return LZGPU_ERR_ARG;
+	int rc = check_goal(goal);
+	if (rc) return rc;
+	if (nb == 0 || nb > LZGPU_BLOCKS_IN_CHUNK) { lz_set_error("nb out of range"); return LZGPU_ERR_ARG; }
+	return LZGPU_OK;
+}
+
+static uint64_t recover_alg_bytes(const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb, const void *const *parts, const uint8_t *want,
+                                  bool image, bool crcs) {
+	// read k parts (+ their stored CRCs), write the rebuilt parts (+ the image)
+	const uint64_t pb = (nb + goal->k - 1) / goal->k, B = LZGPU_BLOCK_SIZE;
+	uint64_t out_parts = 0;
+	for (int i = 0; i < goal->k + goal->m; ++i) out_parts += (!parts[i] && (want[i] || (image && i < goal->k))) ? 1 : 0;
+	return n_chunks * (goal->k * pb * B + (crcs ? 4ull * goal->k * pb : 0) + out_parts * pb * B + (image ? static_cast<uint64_t>(nb) * B : 0));
+}
+
+extern "C" int lzgpu_recover_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb,
+                                         const void *const *d_parts, size_t part_stride, const void *const *d_part_crc,
+                                         const uint8_t *want, void *const *d_out, void *d_chunk_out, size_t chunk_out_stride,
+                                         int64_t *bad, void *stream) {
+	NvtxScope nvtx_scope("lzgpu::recover_chunks_dev");
+	int rc = recover_check_args(ctx, goal, nb, d_parts, want);
+	if (rc) return rc;
+	if (n_chunks == 0) return LZGPU_OK;
+	DeviceGuard g(ctx->device);
+	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+	VerifyTicket tk;
+	{
+		BatchTimer timer(ctx, st, recover_alg_bytes(goal, n_chunks, nb, d_parts, want, d_chunk_out != nullptr, d_part_crc != nullptr));
+		if ((rc = recover_enqueue(ctx, goal, n_chunks, nb, d_parts, part_stride, d_part_crc, want, d_out, d_chunk_out, chunk_out_stride, st, &tk)))
+			return rc;
+	}
+	if (!tk.active()) return LZGPU_OK;
+	// stored CRCs were supplied: the call reports their verdict itself (with or without `bad`)
+	cudaError_t e = cudaStreamSynchronize(st);
+	if (e != cudaSuccess) {
+		ticket_drop(ctx, &tk);
+		cudaGetLastError();
+		lz_set_error("CUDA error %s while waiting for the verification result", cudaGetErrorName(e));
+		return LZGPU_ERR_CUDA;
+	}
+	return ticket_result(ctx, &tk, bad);
+}
+
+// Host-pointer pipelines: tile t runs on slot t % kHostSlots with its own stream and staging buffers, so the H2D copies of one
+// tile overlap the kernels of the previous and the D2H copies of the one before.  Tiles are retired in order (stream
+// synchronised, verification result read) before their slot is re-used, so the first CRC mismatch of the batch is the one reported.
+struct SlotState {
+	VerifyTicket tk;
+	uint32_t c0 = 0;
+	bool busy = false;
+};
+
+static int retire_slot(lzgpu_ctx *ctx, int s, SlotState *ss, int64_t *bad) {
+	if (!ss->busy) return LZGPU_OK;
+	ss->busy = false;
+	cudaError_t e = cudaStreamSynchronize(ctx->slot_stream[s]);
+	if (e != cudaSuccess) {
+		ticket_drop(ctx, &ss->tk);
+		cudaGetLastError();
+		lz_set_error("CUDA error %s in the host pipeline", cudaGetErrorName(e));
+		return LZGPU_ERR_CUDA;
+	}
+	int64_t local[3] = {-1, -1, -1};
+	int rc = ticket_result(ctx, &ss->tk, local);
+	if (rc == LZGPU_ERR_CRC && bad) { bad[0] = local[0] + ss->c0; bad[1] = local[1]; bad[2] = local[2]; }
+	return rc;
+}
+
+static void drain_slots(lzgpu_ctx *ctx, SlotState *ss) {
+	for (int s = 0; s < kHostSlots; ++s) {
+		cudaStreamSynchronize(ctx->slot_stream[s]);
+		ticket_drop(ctx, &ss[s].tk);
+		ss[s].busy = false;
+	}
+	cudaGetLastError();
 }
 
 extern "C" int lzgpu_recover_chunks(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb,
@@ -583,10 +857,8 @@ extern "C" int lzgpu_recover_chunks(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint
                                      const uint8_t *want, uint8_t *const *out, uint8_t *chunk_out, size_t chunk_out_stride,
                                      int64_t *bad) {
 	NvtxScope nvtx_scope("lzgpu::recover_chunks");
-	if (!ctx || !parts || !want) return LZGPU_ERR_ARG;
-	int rc = check_goal(goal);
+	int rc = recover_check_args(ctx, goal, nb, parts, want);
 	if (rc) return rc;
-	if (nb == 0 || nb > LZGPU_BLOCKS_IN_CHUNK) { lz_set_error("nb out of range"); return LZGPU_ERR_ARG; }
 	if (n_chunks == 0) return LZGPU_OK;
 	const int k = goal->k, n = goal->k + goal->m;
 	const uint32_t B = LZGPU_BLOCK_SIZE;
@@ -596,30 +868,42 @@ extern "C" int lzgpu_recover_chunks(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint
 	if (chunk_out && chunk_out_stride < static_cast<size_t>(nb) * B) { lz_set_error("recover: chunk_out_stride too small"); return LZGPU_ERR_ARG; }
 	std::lock_guard<std::mutex> lk(ctx->mu);
 	DeviceGuard g(ctx->device);
-	cudaStream_t st = ctx->stream;
-	// Chunks are staged in tiles of about 1 GiB of part data (device layout: dense, stride = part_bytes); tiles run in order,
-	// so the first CRC mismatch of the whole batch is the one reported.
-	const uint32_t tile = static_cast<uint32_t>(std::max<size_t>(1, std::min<size_t>(n_chunks, (size_t(1) << 30) / (part_bytes * n))));
+	AutoPin pin(ctx);
+	for (int i = 0; i < n; ++i) {
+		if (parts[i]) pin.add(parts[i], static_cast<size_t>(n_chunks - 1) * part_stride + part_bytes);
+		else if (out && out[i] && want[i]) pin.add(out[i], static_cast<size_t>(n_chunks - 1) * part_stride + part_bytes);
+	}
+	if (chunk_out) pin.add(chunk_out, static_cast<size_t>(n_chunks - 1) * chunk_out_stride + static_cast<size_t>(nb) * B);
+	// device layout of a tile: every part dense (stride = part_bytes), all parts of a slot in one buffer
+	const uint32_t tile = static_cast<uint32_t>(std::max<size_t>(1, std::min<size_t>(n_chunks, (2 * kHostTileBytes) / (part_bytes * k))));
 	const size_t dev_part = static_cast<size_t>(tile) * part_bytes;
 	const size_t dev_crc = static_cast<size_t>(tile) * pb * 4;
-	void *d_all = nullptr, *d_crc_all = nullptr, *d_img = nullptr;
-	if ((rc = lz_scratch(ctx, kScratchIn0, dev_part * n, &d_all))) return rc;
-	if ((rc = lz_scratch(ctx, kScratchCrc0, dev_crc * n, &d_crc_all))) return rc;
-	if (chunk_out && (rc = lz_scratch(ctx, kScratchPar0, static_cast<size_t>(tile) * nb * B, &d_img))) return rc;
-	for (uint32_t c0 = 0; c0 < n_chunks; c0 += tile) {
+	void *d_all[kHostSlots], *d_crc_all[kHostSlots], *d_img[kHostSlots] = {nullptr, nullptr, nullptr};
+	const int n_slots = n_chunks > tile ? kHostSlots : 1;
+	for (int s = 0; s < n_slots; ++s) {
+		if ((rc = lz_scratch(ctx, kScratchIn0 + s, dev_part * n, &d_all[s]))) return rc;
+		if ((rc = lz_scratch(ctx, kScratchCrc0 + s, dev_crc * n, &d_crc_all[s]))) return rc;
+		if (chunk_out && (rc = lz_scratch(ctx, kScratchPar0 + s, static_cast<size_t>(tile) * nb * B, &d_img[s]))) return rc;
+	}
+	SlotState ss[kHostSlots];
+	uint32_t t = 0;
+	for (uint32_t c0 = 0; c0 < n_chunks; c0 += tile, ++t) {
 		const uint32_t nc = std::min(tile, n_chunks - c0);
+		const int s = static_cast<int>(t % n_slots);
+		if ((rc = retire_slot(ctx, s, &ss[s], bad))) { drain_slots(ctx, ss); return rc; }
+		cudaStream_t st = ctx->slot_stream[s];
 		std::vector<const void *> dp(n, nullptr), dc(n, nullptr);
 		std::vector<void *> dout(n, nullptr);
 		bool any_crc = false;
 		for (int i = 0; i < n; ++i) {
-			uint8_t *slot = static_cast<uint8_t *>(d_all) + dev_part * i;
+			uint8_t *slot = static_cast<uint8_t *>(d_all[s]) + dev_part * i;
 			if (parts[i]) {
 				CUDA_TRY(cudaMemcpy2DAsync(slot, part_bytes, parts[i] + static_cast<size_t>(c0) * part_stride, part_stride, part_bytes, nc,
 				                           cudaMemcpyHostToDevice, st));
 				ctx->stats.bytes_h2d += static_cast<uint64_t>(nc) * part_bytes;
 				dp[i] = slot;
 				if (part_crc && part_crc[i]) {
-					uint8_t *cs = static_cast<uint8_t *>(d_crc_all) + dev_crc * i;
+					uint8_t *cs = static_cast<uint8_t *>(d_crc_all[s]) + dev_crc * i;
 					CUDA_TRY(cudaMemcpyAsync(cs, part_crc[i] + static_cast<size_t>(c0) * pb, static_cast<size_t>(nc) * pb * 4, cudaMemcpyHostToDevice, st));
 					dc[i] = cs;
 					any_crc = true;
@@ -628,14 +912,14 @@ extern "C" int lzgpu_recover_chunks(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint
 				dout[i] = slot;
 			}
 		}
-		int64_t bad_local[3] = {-1, -1, -1};
-		rc = lzgpu_recover_chunks_dev(ctx, goal, nc, nb, dp.data(), part_bytes, any_crc ? dc.data() : nullptr, want, dout.data(), d_img,
-		                              static_cast<size_t>(nb) * B, bad_local, st);
-		if (rc) {
-			if (bad) { bad[0] = bad_local[0] < 0 ? bad_local[0] : bad_local[0] + c0; bad[1] = bad_local[1]; bad[2] = bad_local[2]; }
-			cudaStreamSynchronize(st);
-			return rc;
+		ss[s].c0 = c0;
+		{
+			BatchTimer timer(ctx, st, recover_alg_bytes(goal, nc, nb, dp.data(), want, chunk_out != nullptr, any_crc));
+			rc = recover_enqueue(ctx, goal, nc, nb, dp.data(), part_bytes, any_crc ? dc.data() : nullptr, want, dout.data(), d_img[s],
+			                     static_cast<size_t>(nb) * B, st, &ss[s].tk);
 		}
+		if (rc) { drain_slots(ctx, ss); return rc; }
+		ss[s].busy = true;
 		for (int i = 0; i < n; ++i) {
 			if (dout[i] && out && out[i] && want[i] && !parts[i]) {
 				CUDA_TRY(cudaMemcpy2DAsync(out[i] + static_cast<size_t>(c0) * part_stride, part_stride, dout[i], part_bytes, part_bytes, nc,
@@ -644,11 +928,15 @@ extern "C" int lzgpu_recover_chunks(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint
 			}
 		}
 		if (chunk_out) {
-			CUDA_TRY(cudaMemcpy2DAsync(chunk_out + static_cast<size_t>(c0) * chunk_out_stride, chunk_out_stride, d_img, static_cast<size_t>(nb) * B,
+			CUDA_TRY(cudaMemcpy2DAsync(chunk_out + static_cast<size_t>(c0) * chunk_out_stride, chunk_out_stride, d_img[s], static_cast<size_t>(nb) * B,
 			                           static_cast<size_t>(nb) * B, nc, cudaMemcpyDeviceToHost, st));
 			ctx->stats.bytes_d2h += static_cast<uint64_t>(nc) * nb * B;
 		}
-		CUDA_TRY(cudaStreamSynchronize(st));
+	}
+	// retire what is still in flight, oldest tile first
+	for (uint32_t i = 0; i < static_cast<uint32_t>(n_slots); ++i) {
+		const int s = static_cast<int>((t + i) % n_slots);
+		if ((rc = retire_slot(ctx, s, &ss[s], bad))) { drain_slots(ctx, ss); return rc; }
 	}
 	return LZGPU_OK;
 }
@@ -667,16 +955,20 @@ static int crc_of_parts(lzgpu_ctx *ctx, const void *d_part, uint32_t n_chunks, u
 	return rc;
 }
 
-extern "C" int lzgpu_convert_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_goal *dst, uint32_t n_chunks, uint32_t nb,
-                                         const void *const *d_parts, size_t part_stride, const void *const *d_part_crc,
-                                         const uint8_t *want, void *const *d_out, size_t out_stride, void *const *d_out_crc,
-                                         int64_t *bad, void *stream) {
-	NvtxScope nvtx_scope("lzgpu::convert_chunks_dev");
-	if (!ctx || !src || !dst || !d_parts || !want || !d_out) return LZGPU_ERR_ARG;
+static int convert_check_args(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_goal *dst, uint32_t nb, const void *parts, const uint8_t *want,
+                              const void *out) {
+	if (!ctx || !src || !dst || !parts || !want || !out) return LZGPU_ERR_ARG;
 	int rc;
 	if ((rc = check_goal_or_std(src)) || (rc = check_goal_or_std(dst))) return rc;
 	if (nb == 0 || nb > LZGPU_BLOCKS_IN_CHUNK) { lz_set_error("nb out of range"); return LZGPU_ERR_ARG; }
-	if (n_chunks == 0) return LZGPU_OK;
+	return LZGPU_OK;
+}
+
+// everything enqueued on `st`, nothing synchronised; *tk = pending verification of the source parts (if any)
+static int convert_enqueue(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_goal *dst, uint32_t n_chunks, uint32_t nb,
+                           const void *const *d_parts, size_t part_stride, const void *const *d_part_crc, const uint8_t *want,
+                           void *const *d_out, size_t out_stride, void *const *d_out_crc, cudaStream_t st, VerifyTicket *tk) {
+	int rc;
 	const uint32_t B = LZGPU_BLOCK_SIZE;
 	const int ks = src->k, kd = dst->k, nd = dst->k + dst->m;
 	const uint32_t pbs = (nb + ks - 1) / ks, pbd = (nb + kd - 1) / kd;
@@ -686,9 +978,7 @@ extern "C" int lzgpu_convert_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *src, c
 	}
 	for (int i = 0; i < nd; ++i)
 		if (want[i] && !d_out[i]) { lz_set_error("convert: wanted part %d has no output buffer", i); return LZGPU_ERR_ARG; }
-	DeviceGuard g(ctx->device);
-	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
-	if (bad) bad[0] = bad[1] = bad[2] = -1;
+	TmpBuf t_image(ctx, st), t_par(ctx, st), t_crc(ctx, st), t_vcrc(ctx, st);
 	void *d_encode_crc = nullptr;  // CRC array of the destination-slice encode, when that ran
 	size_t encode_crc_stride = 0;
 
@@ -708,7 +998,7 @@ extern "C" int lzgpu_convert_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *src, c
 		}
 		if (any || d_part_crc) {
 			if (any && out_stride != part_stride) { lz_set_error("convert: same-slice rebuild needs out_stride == part_stride"); return LZGPU_ERR_ARG; }
-			if ((rc = lzgpu_recover_chunks_dev(ctx, src, n_chunks, nb, d_parts, part_stride, d_part_crc, need, d_out, nullptr, 0, bad, st))) return rc;
+			if ((rc = recover_enqueue(ctx, src, n_chunks, nb, d_parts, part_stride, d_part_crc, need, d_out, nullptr, 0, st, tk))) return rc;
 		}
 	} else {
 		// kRecoverDataPart / kRecoverParityPart (:102-119): chunk data first (ChunkReadPlanner), then BlockConverter or RecoverParity
@@ -720,34 +1010,31 @@ extern "C" int lzgpu_convert_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *src, c
 			image = static_cast<const uint8_t *>(d_parts[0]);
 			image_stride = part_stride;
 			if (d_part_crc && d_part_crc[0]) {
-				void *d_tmp;
 				const unsigned long long nblk = static_cast<unsigned long long>(n_chunks) * nb;
-				const unsigned long long none = ~0ull;
-				if ((rc = lz_scratch(ctx, kScratchTmpCrc, nblk * 4, &d_tmp))) return rc;
-				CUDA_TRY(cudaMemcpyAsync(ctx->d_first_bad, &none, sizeof(none), cudaMemcpyHostToDevice, st));
-				if ((rc = crc_of_parts(ctx, image, n_chunks, nb, image_stride, d_tmp, st))) return rc;
-				crc_compare_kernel<<<grid_for(ctx, nblk, 256, 4), 256, 0, st>>>(static_cast<const uint32_t *>(d_tmp), static_cast<const uint32_t *>(d_part_crc[0]),
-				                                                              nblk, kCrcZeroBlock64K, 0, 0, ctx->d_first_bad);
+				if ((rc = t_vcrc.alloc(nblk * 4))) return rc;
+				if ((rc = lz_status_acquire(ctx, &tk->slot))) return rc;
+				CUDA_TRY(cudaMemsetAsync(tk->slot.d, 0xff, sizeof(unsigned long long) * LZGPU_MAX_PARTS, st));
+				if ((rc = crc_of_parts(ctx, image, n_chunks, nb, image_stride, t_vcrc.p, st))) { ticket_drop(ctx, tk); return rc; }
+				crc_compare_kernel<<<grid_for(ctx, nblk, 256, 4), 256, 0, st>>>(static_cast<const uint32_t *>(t_vcrc.p), static_cast<const uint32_t *>(d_part_crc[0]),
+				                                                              nblk, kCrcZeroBlock64K, 0, 0, tk->slot.d);
 				CUDA_TRY(cudaGetLastError());
 				ctx->stats.kernel_launches++;
-				if (bad) {
-					CUDA_TRY(cudaMemcpyAsync(ctx->h_first_bad, ctx->d_first_bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-					CUDA_TRY(cudaStreamSynchronize(st));
-					if (ctx->h_first_bad[0] != ~0ull) {
-						bad[0] = static_cast<int64_t>(ctx->h_first_bad[0] / nb); bad[1] = 0; bad[2] = static_cast<int64_t>(ctx->h_first_bad[0] % nb);
-						lz_set_error("CRC mismatch: chunk %lld part 0 block %lld", (long long)bad[0], (long long)bad[2]);
-						return LZGPU_ERR_CRC;
-					}
-				}
+				tk->fused = false;
+				tk->n_words = 1;
+				tk->blocks = nb;
+				CUDA_TRY(cudaMemcpyAsync(tk->slot.h, tk->slot.d, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 			}
 			if (direct_image && direct_image != image)
 				CUDA_TRY(cudaMemcpy2DAsync(direct_image, out_stride, image, image_stride, static_cast<size_t>(nb) * B, n_chunks, cudaMemcpyDeviceToDevice, st));
 		} else {
 			void *d_img = direct_image;
 			image_stride = direct_image ? out_stride : static_cast<size_t>(nb) * B;
-			if (!d_img && (rc = lz_scratch(ctx, kScratchConvImage, static_cast<size_t>(n_chunks) * image_stride, &d_img))) return rc;
+			if (!d_img) {
+				if ((rc = t_image.alloc(static_cast<size_t>(n_chunks) * image_stride))) return rc;
+				d_img = t_image.p;
+			}
 			const uint8_t none_wanted[LZGPU_MAX_PARTS] = {0};
-			if ((rc = lzgpu_recover_chunks_dev(ctx, src, n_chunks, nb, d_parts, part_stride, d_part_crc, none_wanted, nullptr, d_img, image_stride, bad, st)))
+			if ((rc = recover_enqueue(ctx, src, n_chunks, nb, d_parts, part_stride, d_part_crc, none_wanted, nullptr, d_img, image_stride, st, tk)))
 				return rc;
 			image = static_cast<const uint8_t *>(d_img);
 		}
@@ -760,19 +1047,17 @@ extern "C" int lzgpu_convert_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *src, c
 				else parity_wanted = true;
 			}
 			// data part j, block s = chunk block s*k + j (SliceRecoveryPlanner::BlockConverter, :41-57)
-			if (data_wanted && (rc = lzgpu_split_chunks_dev(ctx, dst, n_chunks, nb, image, image_stride, dp, out_stride, st))) return rc;
+			if (data_wanted && (rc = lzgpu_split_chunks_dev(ctx, dst, n_chunks, nb, image, image_stride, dp, out_stride, st))) { ticket_drop(ctx, tk); return rc; }
 			// parity parts = XorReadPlan::RecoverParity / ECReadPlan::RecoverParity over the chunk data (xor_read_plan.h:39-62, ec_read_plan.h:38-76)
 			if (parity_wanted) {
-				void *d_par, *d_crc;
 				const size_t par_stride = static_cast<size_t>(dst->m) * pbd * B, crc_stride = (nb + static_cast<size_t>(dst->m) * pbd + 3) & ~size_t(3);
-				if ((rc = lz_scratch(ctx, kScratchConvPar, n_chunks * par_stride, &d_par))) return rc;
-				if ((rc = lz_scratch(ctx, kScratchConvCrc, n_chunks * crc_stride * 4, &d_crc))) return rc;
-				if ((rc = lzgpu_encode_chunks_dev(ctx, dst, n_chunks, nb * B, image, image_stride, d_par, par_stride, d_crc, crc_stride, st))) return rc;
-				d_encode_crc = d_crc;
+				if ((rc = t_par.alloc(n_chunks * par_stride)) || (rc = t_crc.alloc(n_chunks * crc_stride * 4))) { ticket_drop(ctx, tk); return rc; }
+				if ((rc = encode_enqueue(ctx, dst, n_chunks, nb * B, image, image_stride, t_par.p, par_stride, t_crc.p, crc_stride, st))) { ticket_drop(ctx, tk); return rc; }
+				d_encode_crc = t_crc.p;
 				encode_crc_stride = crc_stride;
 				for (int r = 0; r < dst->m; ++r)
 					if (want[kd + r])
-						CUDA_TRY(cudaMemcpy2DAsync(d_out[kd + r], out_stride, static_cast<uint8_t *>(d_par) + static_cast<size_t>(r) * pbd * B, par_stride,
+						CUDA_TRY(cudaMemcpy2DAsync(d_out[kd + r], out_stride, static_cast<uint8_t *>(t_par.p) + static_cast<size_t>(r) * pbd * B, par_stride,
 						                           static_cast<size_t>(pbd) * B, n_chunks, cudaMemcpyDeviceToDevice, st));
 			}
 		}
@@ -796,20 +1081,53 @@ extern "C" int lzgpu_convert_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *src, c
 			}
 		} else {
 			for (int i = 0; i < nd; ++i)
-				if (want[i] && d_out_crc[i] && (rc = crc_of_parts(ctx, d_out[i], n_chunks, pbd, out_stride, d_out_crc[i], st))) return rc;
+				if (want[i] && d_out_crc[i] && (rc = crc_of_parts(ctx, d_out[i], n_chunks, pbd, out_stride, d_out_crc[i], st))) { ticket_drop(ctx, tk); return rc; }
 		}
 	}
 	return LZGPU_OK;
+}
+
+static uint64_t convert_alg_bytes(const lzgpu_goal *src, const lzgpu_goal *dst, uint32_t n_chunks, uint32_t nb, const uint8_t *want, bool crcs) {
+	// read k source parts once (+ stored CRCs), write the wanted destination parts once (+ their CRCs)
+	const uint64_t B = LZGPU_BLOCK_SIZE, pbs = (nb + src->k - 1) / src->k, pbd = (nb + dst->k - 1) / dst->k;
+	uint64_t n_out = 0;
+	for (int i = 0; i < dst->k + dst->m; ++i) n_out += want[i] ? 1 : 0;
+	return n_chunks * (src->k * pbs * (B + (crcs ? 4 : 0)) + n_out * pbd * (B + 4));
+}
+
+extern "C" int lzgpu_convert_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_goal *dst, uint32_t n_chunks, uint32_t nb,
+                                         const void *const *d_parts, size_t part_stride, const void *const *d_part_crc,
+                                         const uint8_t *want, void *const *d_out, size_t out_stride, void *const *d_out_crc,
+                                         int64_t *bad, void *stream) {
+	NvtxScope nvtx_scope("lzgpu::convert_chunks_dev");
+	int rc = convert_check_args(ctx, src, dst, nb, d_parts, want, d_out);
+	if (rc) return rc;
+	if (n_chunks == 0) return LZGPU_OK;
+	DeviceGuard g(ctx->device);
+	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+	if (bad) bad[0] = bad[1] = bad[2] = -1;
+	VerifyTicket tk;
+	{
+		BatchTimer timer(ctx, st, convert_alg_bytes(src, dst, n_chunks, nb, want, d_part_crc != nullptr));
+		if ((rc = convert_enqueue(ctx, src, dst, n_chunks, nb, d_parts, part_stride, d_part_crc, want, d_out, out_stride, d_out_crc, st, &tk))) return rc;
+	}
+	if (!tk.active()) return LZGPU_OK;
+	cudaError_t e = cudaStreamSynchronize(st);
+	if (e != cudaSuccess) {
+		ticket_drop(ctx, &tk);
+		cudaGetLastError();
+		lz_set_error("CUDA error %s while waiting for the verification result", cudaGetErrorName(e));
+		return LZGPU_ERR_CUDA;
+	}
+	return ticket_result(ctx, &tk, bad);
 }
 
 extern "C" int lzgpu_convert_chunks(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_goal *dst, uint32_t n_chunks, uint32_t nb,
                                      const uint8_t *const *parts, size_t part_stride, const uint32_t *const *part_crc, const uint8_t *want,
                                      uint8_t *const *out, size_t out_stride, uint32_t *const *out_crc, int64_t *bad) {
 	NvtxScope nvtx_scope("lzgpu::convert_chunks");
-	if (!ctx || !src || !dst || !parts || !want || !out) return LZGPU_ERR_ARG;
-	int rc;
-	if ((rc = check_goal_or_std(src)) || (rc = check_goal_or_std(dst))) return rc;
-	if (nb == 0 || nb > LZGPU_BLOCKS_IN_CHUNK) { lz_set_error("nb out of range"); return LZGPU_ERR_ARG; }
+	int rc = convert_check_args(ctx, src, dst, nb, parts, want, out);
+	if (rc) return rc;
 	if (n_chunks == 0) return LZGPU_OK;
 	const uint32_t B = LZGPU_BLOCK_SIZE;
 	const int ns = src->k + src->m, nd = dst->k + dst->m;
@@ -823,32 +1141,44 @@ extern "C" int lzgpu_convert_chunks(lzgpu_ctx *ctx, const lzgpu_goal *src, const
 		n_out += want[i] != 0;
 	}
 	if (n_out == 0) return LZGPU_OK;
+	if (bad) bad[0] = bad[1] = bad[2] = -1;
 	std::lock_guard<std::mutex> lk(ctx->mu);
 	DeviceGuard g(ctx->device);
-	cudaStream_t st = ctx->stream;
-	// tiles of about 1 GiB of staged part data; a same-slice rebuild writes into buffers shaped like the inputs
-	const bool same = same_goal(src, dst) && !goal_is_std(src);
+	AutoPin pin(ctx);
+	for (int i = 0; i < ns; ++i)
+		if (parts[i]) pin.add(parts[i], static_cast<size_t>(n_chunks - 1) * part_stride + sbytes);
+	for (int i = 0; i < nd; ++i)
+		if (want[i]) pin.add(out[i], static_cast<size_t>(n_chunks - 1) * out_stride + dbytes);
+	// three pipeline slots (see lzgpu_recover_chunks); a same-slice rebuild writes into buffers shaped like the inputs
 	const size_t per_chunk = sbytes * std::max(n_in, 1) + dbytes * n_out;
-	const uint32_t tile = static_cast<uint32_t>(std::max<size_t>(1, std::min<size_t>(n_chunks, (size_t(1) << 30) / per_chunk)));
-	void *d_in, *d_cin, *d_o, *d_co;
-	if ((rc = lz_scratch(ctx, kScratchIn0, tile * sbytes * std::max(n_in, 1), &d_in))) return rc;
-	if ((rc = lz_scratch(ctx, kScratchCrc0, static_cast<size_t>(tile) * pbs * 4 * std::max(n_in, 1), &d_cin))) return rc;
-	if ((rc = lz_scratch(ctx, kScratchPar0, tile * dbytes * n_out, &d_o))) return rc;
-	if ((rc = lz_scratch(ctx, kScratchCrc1, static_cast<size_t>(tile) * pbd * 4 * n_out, &d_co))) return rc;
-	for (uint32_t c0 = 0; c0 < n_chunks; c0 += tile) {
+	const uint32_t tile = static_cast<uint32_t>(std::max<size_t>(1, std::min<size_t>(n_chunks, (2 * kHostTileBytes) / per_chunk)));
+	const int n_slots = n_chunks > tile ? kHostSlots : 1;
+	void *d_in[kHostSlots], *d_cin[kHostSlots], *d_o[kHostSlots], *d_co[kHostSlots];
+	for (int s = 0; s < n_slots; ++s) {
+		if ((rc = lz_scratch(ctx, kScratchIn0 + s, tile * sbytes * std::max(n_in, 1), &d_in[s]))) return rc;
+		if ((rc = lz_scratch(ctx, kScratchCrc0 + s, static_cast<size_t>(tile) * pbs * 4 * std::max(n_in, 1), &d_cin[s]))) return rc;
+		if ((rc = lz_scratch(ctx, kScratchPar0 + s, tile * dbytes * n_out, &d_o[s]))) return rc;
+		if ((rc = lz_scratch(ctx, kScratchOutCrc0 + s, static_cast<size_t>(tile) * pbd * 4 * n_out, &d_co[s]))) return rc;
+	}
+	SlotState ss[kHostSlots];
+	uint32_t t = 0;
+	for (uint32_t c0 = 0; c0 < n_chunks; c0 += tile, ++t) {
 		const uint32_t nc = std::min(tile, n_chunks - c0);
+		const int s = static_cast<int>(t % n_slots);
+		if ((rc = retire_slot(ctx, s, &ss[s], bad))) { drain_slots(ctx, ss); return rc; }
+		cudaStream_t st = ctx->slot_stream[s];
 		std::vector<const void *> dp(ns, nullptr), dc(ns, nullptr);
 		std::vector<void *> dout(nd, nullptr), dcrc(nd, nullptr);
 		bool any_crc = false;
 		int a = 0;
 		for (int i = 0; i < ns; ++i) {
 			if (!parts[i]) continue;
-			uint8_t *slot = static_cast<uint8_t *>(d_in) + static_cast<size_t>(a) * tile * sbytes;
+			uint8_t *slot = static_cast<uint8_t *>(d_in[s]) + static_cast<size_t>(a) * tile * sbytes;
 			CUDA_TRY(cudaMemcpy2DAsync(slot, sbytes, parts[i] + static_cast<size_t>(c0) * part_stride, part_stride, sbytes, nc, cudaMemcpyHostToDevice, st));
 			ctx->stats.bytes_h2d += static_cast<uint64_t>(nc) * sbytes;
 			dp[i] = slot;
 			if (part_crc && part_crc[i]) {
-				uint8_t *cs = static_cast<uint8_t *>(d_cin) + static_cast<size_t>(a) * tile * pbs * 4;
+				uint8_t *cs = static_cast<uint8_t *>(d_cin[s]) + static_cast<size_t>(a) * tile * pbs * 4;
 				CUDA_TRY(cudaMemcpyAsync(cs, part_crc[i] + static_cast<size_t>(c0) * pbs, static_cast<size_t>(nc) * pbs * 4, cudaMemcpyHostToDevice, st));
 				dc[i] = cs;
 				any_crc = true;
@@ -858,19 +1188,18 @@ extern "C" int lzgpu_convert_chunks(lzgpu_ctx *ctx, const lzgpu_goal *src, const
 		a = 0;
 		for (int i = 0; i < nd; ++i) {
 			if (!want[i]) continue;
-			dout[i] = static_cast<uint8_t *>(d_o) + static_cast<size_t>(a) * tile * dbytes;
-			if (out_crc && out_crc[i]) dcrc[i] = static_cast<uint8_t *>(d_co) + static_cast<size_t>(a) * tile * pbd * 4;
+			dout[i] = static_cast<uint8_t *>(d_o[s]) + static_cast<size_t>(a) * tile * dbytes;
+			if (out_crc && out_crc[i]) dcrc[i] = static_cast<uint8_t *>(d_co[s]) + static_cast<size_t>(a) * tile * pbd * 4;
 			++a;
 		}
-		int64_t bad_local[3] = {-1, -1, -1};
-		(void)same;
-		rc = lzgpu_convert_chunks_dev(ctx, src, dst, nc, nb, dp.data(), sbytes, any_crc ? dc.data() : nullptr, want, dout.data(), dbytes,
-		                              out_crc ? dcrc.data() : nullptr, bad_local, st);
-		if (rc) {
-			if (bad) { bad[0] = bad_local[0] < 0 ? bad_local[0] : bad_local[0] + c0; bad[1] = bad_local[1]; bad[2] = bad_local[2]; }
-			cudaStreamSynchronize(st);
-			return rc;
+		ss[s].c0 = c0;
+		{
+			BatchTimer timer(ctx, st, convert_alg_bytes(src, dst, nc, nb, want, any_crc));
+			rc = convert_enqueue(ctx, src, dst, nc, nb, dp.data(), sbytes, any_crc ? dc.data() : nullptr, want, dout.data(), dbytes,
+			                     out_crc ? dcrc.data() : nullptr, st, &ss[s].tk);
 		}
+		if (rc) { drain_slots(ctx, ss); return rc; }
+		ss[s].busy = true;
 		for (int i = 0; i < nd; ++i) {
 			if (!want[i]) continue;
 			CUDA_TRY(cudaMemcpy2DAsync(out[i] + static_cast<size_t>(c0) * out_stride, out_stride, dout[i], dbytes, dbytes, nc, cudaMemcpyDeviceToHost, st));
@@ -878,7 +1207,10 @@ extern "C" int lzgpu_convert_chunks(lzgpu_ctx *ctx, const lzgpu_goal *src, const
 			if (dcrc[i])
 				CUDA_TRY(cudaMemcpyAsync(out_crc[i] + static_cast<size_t>(c0) * pbd, dcrc[i], static_cast<size_t>(nc) * pbd * 4, cudaMemcpyDeviceToHost, st));
 		}
-		CUDA_TRY(cudaStreamSynchronize(st));
+	}
+	for (uint32_t i = 0; i < static_cast<uint32_t>(n_slots); ++i) {
+		const int s = static_cast<int>((t + i) % n_slots);
+		if ((rc = retire_slot(ctx, s, &ss[s], bad))) { drain_slots(ctx, ss); return rc; }
 	}
 	return LZGPU_OK;
 }
@@ -927,7 +1259,7 @@ extern "C" int lzgpu_write_data_prefixes(lzgpu_ctx *ctx, const lzgpu_goal *goal,
 	cudaStream_t st = ctx->stream;
 	void *d_crc = nullptr, *d_ids = nullptr, *d_out = nullptr;
 	if ((rc = lz_scratch(ctx, kScratchCrc0, static_cast<size_t>(n_chunks) * n_crc * 4, &d_crc))) return rc;
-	if ((rc = lz_scratch(ctx, kScratchCrc1, static_cast<size_t>(n_chunks) * 8, &d_ids))) return rc;
+	if ((rc = lz_scratch(ctx, kScratchCrc0 + 1, static_cast<size_t>(n_chunks) * 8, &d_ids))) return rc;
 	if ((rc = lz_scratch(ctx, kScratchPar0, out_bytes, &d_out))) return rc;
 	CUDA_TRY(cudaMemcpy2DAsync(d_crc, n_crc * 4, crc, crc_stride * 4, n_crc * 4, n_chunks, cudaMemcpyHostToDevice, st));
 	CUDA_TRY(cudaMemcpyAsync(d_ids, chunk_ids, static_cast<size_t>(n_chunks) * 8, cudaMemcpyHostToDevice, st));
@@ -1062,7 +1394,12 @@ static int verify_common(lzgpu_ctx *ctx, const uint8_t *h_data, size_t n_blocks,
 	if ((rc = lz_scratch(ctx, kScratchIn0, tile_blocks * dstride, &d_in))) return rc;
 	if ((rc = lz_scratch(ctx, kScratchCrc0, tile_blocks * 4, &d_c))) return rc;
 	if ((rc = lz_scratch(ctx, kScratchCrc0 + 1, tile_blocks * 4, &d_s))) return rc;
-	const unsigned long long init = ~0ull;
+	StatusSlot slot;
+	if ((rc = lz_status_acquire(ctx, &slot))) return rc;
+	struct SlotReturn {
+		lzgpu_ctx *c; StatusSlot s;
+		~SlotReturn() { lz_status_release(c, s); }
+	} slot_return{ctx, slot};
 	for (size_t b0 = 0; b0 < n_blocks; b0 += tile_blocks) {
 		const size_t n = std::min(tile_blocks, n_blocks - b0);
 		// cudaMemcpyDefault: the source may be host memory or (unified addressing) a device buffer, e.g. chunk files read straight
@@ -1070,25 +1407,25 @@ static int verify_common(lzgpu_ctx *ctx, const uint8_t *h_data, size_t n_blocks,
 		CUDA_TRY(cudaMemcpy2DAsync(d_in, dstride, h_data + h_offset + b0 * h_stride, h_stride, block_len, n, cudaMemcpyDefault, st));
 		CUDA_TRY(cudaMemcpy2DAsync(d_s, 4, reinterpret_cast<const uint8_t *>(h_stored) + b0 * stored_stride_bytes, stored_stride_bytes, 4, n,
 		                           cudaMemcpyDefault, st));
-		CUDA_TRY(cudaMemcpyAsync(ctx->d_first_bad, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+		CUDA_TRY(cudaMemsetAsync(slot.d, 0xff, sizeof(unsigned long long), st));
 		if ((rc = lzgpu_crc_blocks_dev(ctx, d_in, n, block_len, dstride, d_c, st))) return rc;
 		crc_compare_kernel<<<grid_for(ctx, n, 256, 4), 256, 0, st>>>(static_cast<const uint32_t *>(d_c), static_cast<const uint32_t *>(d_s), n,
-		                                                            lz::crc_of_zeros(block_len), sparse_rule, big_endian, ctx->d_first_bad);
+		                                                            lz::crc_of_zeros(block_len), sparse_rule, big_endian, slot.d);
 		CUDA_TRY(cudaGetLastError());
 		ctx->stats.kernel_launches++;
 		if (sparse_rule) {
 			// holes accepted on their CRC are re-read and must really be all zero (crc.cc:235-243)
 			const unsigned grid = static_cast<unsigned>(std::min<size_t>(n, static_cast<size_t>(ctx->sm_count) * 8));
 			sparse_confirm_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t *>(d_in), dstride, block_len, static_cast<const uint32_t *>(d_c),
-			                                            static_cast<const uint32_t *>(d_s), n, lz::crc_of_zeros(block_len), ctx->d_first_bad);
+			                                            static_cast<const uint32_t *>(d_s), n, lz::crc_of_zeros(block_len), slot.d);
 			CUDA_TRY(cudaGetLastError());
 			ctx->stats.kernel_launches++;
 		}
-		CUDA_TRY(cudaMemcpyAsync(ctx->h_first_bad, ctx->d_first_bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaMemcpyAsync(slot.h, slot.d, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 		CUDA_TRY(cudaStreamSynchronize(st));
 		ctx->stats.bytes_h2d += n * (block_len + 4ull);
-		if (ctx->h_first_bad[0] != ~0ull) {
-			const unsigned long long bad = b0 + ctx->h_first_bad[0];
+		if (slot.h[0] != ~0ull) {
+			const unsigned long long bad = b0 + slot.h[0];
 			if (first_bad) *first_bad = static_cast<int64_t>(bad);
 			lz_set_error("CRC mismatch in block %llu", bad);
 			return LZGPU_ERR_CRC;
@@ -1188,7 +1525,7 @@ extern "C" int lzgpu_write_blocks(lzgpu_ctx *ctx, uint8_t *blocks, uint32_t *sto
 	if ((rc = lz_scratch(ctx, kScratchIn0, tile * B, &d_blk))) return rc;
 	if ((rc = lz_scratch(ctx, kScratchCrc0, tile * 4, &d_crc))) return rc;
 	if ((rc = lz_scratch(ctx, kScratchPar0, std::max<size_t>(payload_bytes, 16), &d_pay))) return rc;
-	if ((rc = lz_scratch(ctx, kScratchCrc1, tile * sizeof(lzgpu_block_write), &d_wr))) return rc;
+	if ((rc = lz_scratch(ctx, kScratchCrc0 + 1, tile * sizeof(lzgpu_block_write), &d_wr))) return rc;
 	if (payload_bytes) CUDA_TRY(cudaMemcpyAsync(d_pay, payload, payload_bytes, cudaMemcpyHostToDevice, st));
 	ctx->stats.bytes_h2d += payload_bytes;
 	int first_error = LZGPU_OK;
@@ -1436,6 +1773,19 @@ extern "C" int lzgpu_host_free(lzgpu_ctx *ctx, void *h_ptr) {
 	if (!ctx) return LZGPU_ERR_ARG;
 	DeviceGuard g(ctx->device);
 	CUDA_TRY(cudaFreeHost(h_ptr));
+	return LZGPU_OK;
+}
+extern "C" int lzgpu_host_register(lzgpu_ctx *ctx, void *h_ptr, size_t bytes) {
+	if (!ctx || !h_ptr || !bytes) return LZGPU_ERR_ARG;
+	DeviceGuard g(ctx->device);
+	cudaError_t e = cudaHostRegister(h_ptr, bytes, cudaHostRegisterPortable);
+	if (e != cudaSuccess) { cudaGetLastError(); lz_set_error("cudaHostRegister(%zu): %s", bytes, cudaGetErrorString(e)); return LZGPU_ERR_CUDA; }
+	return LZGPU_OK;
+}
+extern "C" int lzgpu_host_unregister(lzgpu_ctx *ctx, void *h_ptr) {
+	if (!ctx || !h_ptr) return LZGPU_ERR_ARG;
+	DeviceGuard g(ctx->device);
+	CUDA_TRY(cudaHostUnregister(h_ptr));
 	return LZGPU_OK;
 }
 extern "C" int lzgpu_dev_upload(lzgpu_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {

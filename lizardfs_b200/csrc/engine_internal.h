@@ -2,9 +2,11 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstddef>
 #include <cstdint>
 #include <mutex>
+#include <vector>
 
 #include "lzgpu.h"
 
@@ -25,13 +27,12 @@ void lz_set_error(const char *fmt, ...);
 
 constexpr size_t kHostTileBytes = size_t(128) << 20;  // staging tile of the host-pointer entry points
 constexpr int kHostSlots = 3;                          // tiles in flight: H2D(t+1) | kernel(t) | D2H(t-1)
-constexpr int kCoefSlots = 8;
+// Staging buffers of the HOST-pointer entry points (one set per pipeline slot; those calls hold ctx->mu).  The *_dev entry
+// points never touch them: their temporaries come from the context's stream-ordered memory pool (TmpBuf below), so any
+// number of threads may call *_dev functions on one context concurrently.
 enum ScratchSlot {
-	kScratchIn0 = 0, kScratchIn1, kScratchIn2, kScratchPar0, kScratchPar1, kScratchPar2, kScratchCrc0, kScratchCrc1, kScratchCrc2, kScratchTmpCrc,
-	kScratchCoef0, kScratchCoefLast = kScratchCoef0 + kCoefSlots - 1,
-	kScratchFused0, kScratchFused1,
-	kScratchTmpPart0, kScratchTmpPartLast = kScratchTmpPart0 + LZGPU_MAX_PARTS - 1,
-	kScratchConvImage, kScratchConvPar, kScratchConvCrc,
+	kScratchIn0 = 0, kScratchIn1, kScratchIn2, kScratchPar0, kScratchPar1, kScratchPar2, kScratchCrc0, kScratchCrc1, kScratchCrc2,
+	kScratchOutCrc0, kScratchOutCrc1, kScratchOutCrc2,
 	kScratchCount
 };
 
@@ -42,21 +43,79 @@ struct ScratchBuf {
 
 struct FusedState;  // fused.cu
 
+// per-context counters; updated from any thread
+struct LzCounters {
+	std::atomic<uint64_t> kernel_launches{0}, bytes_h2d{0}, bytes_d2h{0}, chunks_encoded{0}, chunks_recovered{0}, blocks_crc{0};
+};
+
+// A verification result slot: LZGPU_MAX_PARTS "first bad" words on the device and their pinned host mirror.  One slot per
+// call that verifies stored CRCs (taken from a small pool, returned when the call has read its result), so concurrent calls
+// never share a result word.
+struct StatusSlot {
+	unsigned long long *d = nullptr, *h = nullptr;
+	int index = -1;
+};
+
+// per-batch device timing (lzgpu_stats.batch_*): CUDA events recorded around the kernels of a batched call on its stream,
+// resolved lazily (cudaEventQuery) when the statistics are read — the analogue of the reference's
+// LOG_AVG_TILL_END_OF_SCOPE timers on this path (src/devtools/request_log.h:401-404, write_executor.cc:96)
+struct TimingEntry {
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	uint64_t bytes = 0;
+	bool pending = false;
+};
+constexpr int kTimingRing = 64;
+
 struct lzgpu_ctx {
 	int device = 0;
 	int sm_count = 0;
 	cudaStream_t stream = nullptr;
 	cudaStream_t slot_stream[kHostSlots] = {nullptr, nullptr, nullptr};
 	uint32_t *d_crc_tables = nullptr;
-	unsigned long long *d_first_bad = nullptr, *h_first_bad = nullptr;
-	ScratchBuf scratch[kScratchCount];
-	unsigned coef_rr = 0;
+	cudaMemPool_t pool = nullptr;            // stream-ordered temporaries of the *_dev entry points
+	std::mutex slot_mu;                      // guards status_free / status_all
+	std::vector<StatusSlot> status_all;
+	std::vector<int> status_free;
+	ScratchBuf scratch[kScratchCount];       // host-pointer entry points only (under mu)
 	FusedState *fused = nullptr;
-	lzgpu_stats stats{};
-	std::mutex mu;
+	LzCounters stats;
+	std::mutex timing_mu;
+	TimingEntry timing[kTimingRing];
+	unsigned timing_next = 0;
+	int timing_enabled = 1;
+	int auto_register = 0;                   // LZGPU_AUTO_REGISTER: page-lock pageable caller buffers per host-pointer call
+	uint64_t batches_timed = 0, batch_bytes_last = 0;
+	double batch_ms_total = 0.0, batch_ms_last = 0.0, batch_bytes_total = 0.0;
+	std::mutex mu;                           // serialises the host-pointer entry points (they share the staging slots)
 };
 
 int lz_scratch(lzgpu_ctx *ctx, int slot, size_t bytes, void **out);
+
+// stream-ordered temporary: allocated from the context pool on `st`, released on `st` when the scope ends
+struct TmpBuf {
+	lzgpu_ctx *ctx;
+	cudaStream_t st;
+	void *p = nullptr;
+	TmpBuf(lzgpu_ctx *c, cudaStream_t s) : ctx(c), st(s) {}
+	TmpBuf(const TmpBuf &) = delete;
+	TmpBuf &operator=(const TmpBuf &) = delete;
+	~TmpBuf() {
+		if (p) cudaFreeAsync(p, st);
+	}
+	int alloc(size_t bytes);
+};
+
+int lz_status_acquire(lzgpu_ctx *ctx, StatusSlot *out);
+void lz_status_release(lzgpu_ctx *ctx, const StatusSlot &s);
+// scope guard for the batch timer: records the start event now and the end event + bytes at scope exit
+struct BatchTimer {
+	lzgpu_ctx *ctx;
+	cudaStream_t st;
+	int idx = -1;
+	uint64_t bytes;
+	BatchTimer(lzgpu_ctx *c, cudaStream_t s, uint64_t algorithmic_bytes);
+	~BatchTimer();
+};
 
 // generic GF dot product descriptor (see kernels_generic.cuh DotArgs)
 struct DotDesc {
@@ -77,11 +136,12 @@ int lz_fused_init(lzgpu_ctx *ctx);
 void lz_fused_destroy(lzgpu_ctx *ctx);
 int lz_fused_encode(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb, const void *d_data, size_t chunk_stride,
                     void *d_parity, size_t parity_stride, void *d_crc, size_t crc_stride, cudaStream_t st);
-// Fused degraded read (verify + rebuild erased data parts + chunk-order image).  On success *handled = true and, when
-// any part was verified, first-bad information sits in ctx->d_first_bad[0] encoded as (chunk*64 + part)*1024 + block.
+// Fused degraded read (verify + rebuild erased data parts + chunk-order image).  When any part is verified (*verifying),
+// first-bad information is written to d_first_bad[0] encoded as (chunk*64 + part)*1024 + block (~0 = all good); the caller
+// owns that word (a StatusSlot) and must pass it whenever d_part_crc is given.
 int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb, const void *const *d_parts, size_t part_stride,
                      const void *const *d_part_crc, const uint8_t *want, void *const *d_out, void *d_chunk_out, size_t chunk_out_stride,
-                     cudaStream_t st, bool *verifying);
+                     cudaStream_t st, unsigned long long *d_first_bad, bool *verifying);
 // CRC of 64 KiB blocks: block (c, b) at base + c*chunk_stride + b*65536, out[c*out_chunk_stride + b]
 int lz_fused_crc(lzgpu_ctx *ctx, const void *base, unsigned long long n_blocks, unsigned long long blocks_per_chunk,
                  unsigned long long chunk_stride, void *out, unsigned long long out_chunk_stride, cudaStream_t st);

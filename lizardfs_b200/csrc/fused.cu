@@ -128,6 +128,7 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if ((rc = set_smem_attr<3, false, 5, 8, 64, true>(smem))) return rc;
 	if ((rc = set_smem_attr<4, false, 8, 5, 64, true>(smem))) return rc;
 	if ((rc = set_smem_attr<2, false, 8, 8>(smem))) return rc;
+	if ((rc = set_smem_attr<2, false, 8, 7>(smem))) return rc;
 	if ((rc = set_smem_attr<1, false, 2, 32>(smem))) return rc;
 	if ((rc = set_smem_attr<1, false, 3, 20>(smem))) return rc;
 	if ((rc = set_smem_attr<2, false, 3, 16>(smem))) return rc;
@@ -289,6 +290,7 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 #define LZ_FOLDED(MM, KK, GG) \
 	if (M == MM && K == KK && G == GG) return launch<MM, false, KK, GG>(ctx, map, p, smem, st);
 	LZ_FOLDED(2, 8, 8)    // ec(8,2)
+	LZ_FOLDED(2, 8, 7)    // ec(8,2) on an 8-warp CTA (-DLZ_T2=256)
 	LZ_FOLDED(1, 2, 32)   // xor2
 	LZ_FOLDED(1, 3, 20)   // xor3
 	LZ_FOLDED(2, 3, 16)   // ec(3,2)
@@ -368,7 +370,7 @@ static int launch_recover(lzgpu_ctx *ctx, const TmapArray &maps, const RecoverPa
 
 int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb, const void *const *d_parts, size_t part_stride,
                      const void *const *d_part_crc, const uint8_t *want, void *const *d_out, void *d_chunk_out, size_t chunk_out_stride,
-                     cudaStream_t st, bool *verifying) {
+                     cudaStream_t st, unsigned long long *d_first_bad, bool *verifying) {
 	FusedState *fs = ctx->fused;
 	*verifying = false;
 	if (!fs || fs->disabled) return LZGPU_NOT_HANDLED;
@@ -426,7 +428,7 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 	p.out_stride = part_stride;
 	p.image_stride = chunk_out_stride;
 	p.tables = ctx->d_crc_tables;
-	p.first_bad = ctx->d_first_bad;
+	p.first_bad = d_first_bad;
 	p.n_chunks = n_chunks;
 	p.nb = nb;
 	p.pb = pb;
@@ -493,10 +495,7 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 		                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 		if (r != CUDA_SUCCESS) return LZGPU_NOT_HANDLED;
 	}
-	if (*verifying) {
-		static const unsigned long long kNone = ~0ull;
-		CUDA_TRY(cudaMemcpyAsync(ctx->d_first_bad, &kNone, sizeof(kNone), cudaMemcpyHostToDevice, st));
-	}
+	if (*verifying && !d_first_bad) return LZGPU_NOT_HANDLED;  // (callers that pass stored CRCs always pass the result word, initialised to ~0)
 	const size_t smem = static_cast<size_t>(n_stages) * K * G * 4 * kStepBytes + 16 * n_stages + 64;
 	const bool k8 = K == 8 && G == 8;
 	const bool row0 = p.par_row[0] == 0, row01 = row0 && e >= 2 && p.par_row[1] == 1;

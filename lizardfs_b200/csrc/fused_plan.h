@@ -25,7 +25,10 @@ constexpr int kSmemCap = 113 * 1024;                   // dynamic shared memory 
 // Three or four parity rows keep 12-16 Horner accumulators live next to the 64-word CRC window: at 96 registers the kernel
 // spills into its inner loop (ncu: long-scoreboard stalls on the local loads, profiles/ec84_r1_ncu_summary.md).  Those
 // shapes run with 8 warps instead of 9, which lets two CTAs per SM have 128 registers per thread.
-LZ_HD constexpr int fused_threads(int m) { return m >= 3 ? 256 : kConsumers; }
+#ifndef LZ_T2
+#define LZ_T2 kConsumers  // experiment builds: -DLZ_T2=256 (one or two parity rows on 8-warp CTAs)
+#endif
+LZ_HD constexpr int fused_threads(int m) { return m >= 3 ? 256 : LZ_T2; }
 
 // pipeline depth by fold window: FW = 64 -> 2 CTAs/SM (96 registers), 3 data stages + 4-deep parity ring;
 // FW = 128 -> 1 CTA/SM (the 128-word window needs ~170 registers), 6 data stages + 6-deep parity ring

@@ -20,7 +20,7 @@ constexpr int kDotDests = 4;  // dests produced per pass (accumulators live in r
 struct DotArgs {
 	const uint8_t *src[kMaxSrc];
 	uint8_t *dst[kDotDests];
-	const CoefPlanes *coef;  // [n_dst][n_src]
+	uint8_t coef[kDotDests * kMaxSrc];  // [n_dst][n_src] coefficient bytes (expanded to bit planes in shared memory)
 	unsigned long long total_units;
 	unsigned long long src_chunk_stride, src_block_stride;
 	unsigned long long dst_chunk_stride, dst_block_stride;
@@ -33,8 +33,14 @@ struct DotArgs {
 template <int ND>
 __global__ void __launch_bounds__(256) gf_dot_kernel(const DotArgs a) {
 	extern __shared__ CoefPlanes s_coef[];  // [ND][n_src]
-	for (unsigned i = threadIdx.x; i < ND * a.n_src * 8; i += blockDim.x)
-		reinterpret_cast<uint32_t *>(s_coef)[i] = reinterpret_cast<const uint32_t *>(a.coef)[i];
+	for (unsigned i = threadIdx.x; i < ND * a.n_src; i += blockDim.x) {
+		uint32_t v = a.coef[i];
+#pragma unroll
+		for (int b = 0; b < 8; ++b) {
+			s_coef[i].plane[b] = v;                                  // plane[b] = c * 2^b
+			v = ((v << 1) ^ ((v & 0x80u) ? 0x1du : 0u)) & 0xffu;     // x^8 = x^4+x^3+x^2+1 (galois_coeff.h:30-32)
+		}
+	}
 	__syncthreads();
 
 	const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;

@@ -348,15 +348,20 @@ class Engine:
         return out, img
 
     def recover_chunks_dev(self, goal, n_chunks, nb, d_parts, part_stride, d_part_crc, want, d_out, d_chunk_out=None,
-                           chunk_out_stride=0, stream=None, check=False):
+                           chunk_out_stride=None, stream=None):
+        """Device-pointer degraded read.  With d_part_crc the call waits for its stream and raises ChunkCrcError on a
+        mismatch (the library never lets a failed verification pass); without it the call only enqueues."""
         n_parts = goal.k + goal.m
+        if d_chunk_out and chunk_out_stride is None:
+            raise ValueError("recover_chunks_dev: chunk_out_stride is required with d_chunk_out")
+        chunk_out_stride = chunk_out_stride or 0
         dp = (C.c_void_p * n_parts)(*[p if p else None for p in d_parts])
         dc = (C.c_void_p * n_parts)(*[p if p else None for p in d_part_crc]) if d_part_crc is not None else None
         do = (C.c_void_p * n_parts)(*[p if p else None for p in d_out])
         w = np.asarray(want, dtype=np.uint8)
         bad = (C.c_int64 * 3)(-1, -1, -1)
         rc = self.lib.lzgpu_recover_chunks_dev(self.h, C.byref(goal.c), n_chunks, nb, dp, part_stride, dc, _p(w), do, d_chunk_out,
-                                               chunk_out_stride, bad if check else None, stream)
+                                               chunk_out_stride, bad, stream)
         if rc == _lib.ERR_CRC:
             raise ChunkCrcError(rc, "recover_chunks_dev", (bad[0], bad[1], bad[2]))
         _check(rc, "recover_chunks_dev")

@@ -45,7 +45,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--full-size-only", action="store_true", help="all goals, 64 MiB chunks only")
+    ap.add_argument("--sections", default="enc,scrub,rec,conv,bw", help="comma list of enc,scrub,rec,conv,bw")
+    ap.add_argument("--goals", default="", help="comma-free list separated by ';' of encode goals, e.g. 'ec(8,4);ec(5,3)'")
+    ap.add_argument("--rec", default="", help="recover cases 'goal:lost,lost;...' e.g. 'ec(5,3):0,1,4;ec(3,2):0,2'")
+    ap.add_argument("--rec-variants", default="both", choices=["both", "plain", "full"])
     args = ap.parse_args()
+    sections = set(args.sections.split(","))
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     eng = L.Engine(0)
@@ -64,6 +69,10 @@ def main():
         goals, sizes = ["ec(3,2)", "ec(8,2)"], [64 << 20]
     if args.full_size_only:
         sizes = [64 << 20]
+    if args.goals:
+        goals = [g for g in args.goals.split(";") if g]
+    if "enc" not in sections:
+        goals = []
     d_data = torch.empty(args.bytes, dtype=torch.uint8, device=dev)
     eng.fill_chunks_dev(d_data.data_ptr(), args.bytes // (64 << 20), 64 << 20, 64 << 20, seed=12345, stream=sp)
     for text in goals:
@@ -85,18 +94,27 @@ def main():
             del d_par, d_crc
     # scrub: CRC32 of every 64 KiB block of the resident buffer (hdd_int_test, hddspacemgr.cc:2174-2190)
     nblk = args.bytes // BLOCK
-    d_c = torch.empty(nblk, dtype=torch.int32, device=dev)
-    ms = time_steps(lambda: eng.crc_blocks_dev(d_data.data_ptr(), nblk, d_c.data_ptr(), stream=sp), args.steps, args.warmup, stream)
-    gbs = (args.bytes + 4 * nblk) / (ms / 1e3) / 1e9
-    lines += ["", "## scrub (CRC32 of 64 KiB blocks, fused kernel with M = 0)", "", "| blocks | ms | GiB/s | GB/s algorithmic | frac |", "|---|---|---|---|---|",
-              f"| {nblk} | {ms:.3f} | {args.bytes / GIB / (ms / 1e3):.0f} | {gbs:.0f} | {gbs / peak:.3f} |"]
-    del d_c
+    if "scrub" in sections:
+        d_c = torch.empty(nblk, dtype=torch.int32, device=dev)
+        ms = time_steps(lambda: eng.crc_blocks_dev(d_data.data_ptr(), nblk, d_c.data_ptr(), stream=sp), args.steps, args.warmup, stream)
+        gbs = (args.bytes + 4 * nblk) / (ms / 1e3) / 1e9
+        lines += ["", "## scrub (CRC32 of 64 KiB blocks, fused kernel with M = 0)", "", "| blocks | ms | GiB/s | GB/s algorithmic | frac |", "|---|---|---|---|---|",
+                  f"| {nblk} | {ms:.3f} | {args.bytes / GIB / (ms / 1e3):.0f} | {gbs:.0f} | {gbs / peak:.3f} |"]
+        del d_c
     # degraded read: ec(8,2), data parts 1 and 4 lost (BASELINE configs[3]); also ec(3,2) / ec(5,3) / xor3
     lines += ["", "## degraded-read recover (stored CRCs verified, chunk-order image written)", "",
               "| goal | lost parts | chunks/launch | variant | ms | GiB/s chunk data | GB/s algorithmic | frac |", "|---|---|---|---|---|---|---|---|"]
     cases = [("ec(8,2)", (1, 4)), ("ec(8,2)", (0,)), ("ec(3,2)", (0, 2)), ("ec(5,3)", (0, 1, 4)), ("xor3", (1,))]
     if args.quick:
         cases = cases[:1]
+    if args.rec:
+        cases = [(c.split(":")[0], tuple(int(x) for x in c.split(":")[1].split(","))) for c in args.rec.split(";") if c]
+    if "rec" not in sections and "conv" not in sections:
+        cases = []
+    elif "rec" not in sections:
+        cases = [("ec(8,2)", (1, 4))]
+    variants_sel = {"both": (0, 1), "plain": (0,), "full": (1,)}[args.rec_variants]
+    conv_src = None
     clen = 64 << 20
     nb = clen // BLOCK
     for text, lost in cases:
@@ -131,7 +149,9 @@ def main():
         do = [outs[i].data_ptr() if i in lost else 0 for i in range(k + m)]
         want = [1 if i in lost else 0 for i in range(k + m)]
         e = len([i for i in lost if i < k])
-        for variant, crcs, image in [("recover only", None, None), ("verify + recover + image", dc, img)]:
+        for vi, (variant, crcs, image) in enumerate([("recover only", None, None), ("verify + recover + image", dc, img)]):
+            if vi not in variants_sel:
+                continue
             ms = time_steps(lambda: eng.recover_chunks_dev(g, n, nb, dp, part_stride, crcs, want, do, image.data_ptr() if image is not None else None,
                                                            nb * BLOCK, stream=sp), args.steps, args.warmup, stream)
             alg = k * pb * BLOCK + e * pb * BLOCK + (4 * k * pb + nb * BLOCK if crcs is not None else 0)
@@ -143,7 +163,8 @@ def main():
         for i in lost:
             if i < k:
                 assert torch.equal(outs[i].view(n, pb, BLOCK), parts[i]), (text, i)
-        assert torch.equal(img.view(n, nb, BLOCK), chunks)
+        if 1 in variants_sel:
+            assert torch.equal(img.view(n, nb, BLOCK), chunks)
         if text == "ec(8,2)" and lost == (1, 4) or args.quick:
             conv_src = (g, n, nb, pb, dp, dc)
             conv_keep = (parts, pcrc)
@@ -152,8 +173,12 @@ def main():
     # ---- replication: slice-type conversion (SliceRecoveryPlanner) --------------------------------------------------
     lines += ["", "## slice-type conversion for replication (source CRCs verified, destination block CRCs produced)", "",
               "| source | destination parts | chunks/launch | ms | GiB/s chunk data |", "|---|---|---|---|---|"]
-    g, n, nb, pb, dp, dc = conv_src
-    for dst_text, want_parts in [("ec(3,2)", "all"), ("ec(3,2)", "one parity"), ("std", "all"), ("xor3", "all")]:
+    conv_cases = [("ec(3,2)", "all"), ("ec(3,2)", "one parity"), ("std", "all"), ("xor3", "all")]
+    if "conv" not in sections or conv_src is None:
+        conv_cases = []
+    else:
+        g, n, nb, pb, dp, dc = conv_src
+    for dst_text, want_parts in conv_cases:
         d = L.SliceType(dst_text)
         nd = d.k + d.m
         pbd = (nb + d.k - 1) // d.k
@@ -168,7 +193,7 @@ def main():
         if dst_text == "std":
             assert torch.equal(outs[0].view(n, nb, BLOCK), chunks)
         del outs, ocrc
-    del conv_keep
+    conv_keep = None
 
     # ---- chunkserver block writes (hdd_write) -------------------------------------------------------------------------
     lines += ["", "## batched chunkserver block writes (packet CRC check + stored-block check + new CRC)", "",
@@ -178,7 +203,7 @@ def main():
     import numpy as np
     from lizardfs_b200 import _lib
     nreq = 16384
-    for size in (4096, 65535):
+    for size in ((4096, 65535) if "bw" in sections else ()):
         blocks = d_data[: nreq * BLOCK]
         crc_t = torch.empty(nreq, dtype=torch.int32, device=dev)
         eng.crc_blocks_dev(blocks.data_ptr(), nreq, crc_t.data_ptr(), stream=sp)
