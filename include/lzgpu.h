@@ -126,6 +126,25 @@ void lzgpu_get_stats(lzgpu_ctx *ctx, lzgpu_stats *out);
 void lzgpu_reset_stats(lzgpu_ctx *ctx);
 
 /* ---------------------------------------------------------------------------------------------
+ * Device pool: several GPUs behind ONE process (the mount runs ten write workers in one process, src/mount/lizard_client.h:77,
+ * src/mount/writedata.cc:645; the chunkserver a pool of background jobs).  A pool owns one context and one worker thread per
+ * device; a pool call cuts the batch into one contiguous run of chunks per device (lzgpu_pool_share: device slot i takes
+ * chunks [i*ceil(n/G), ...), i.e. the static round-robin of chunk batches with no collective on the data path), runs every
+ * share through that device's own H2D | kernel | D2H pipeline concurrently and returns when all are done.  Pool calls may be
+ * issued from any number of threads; the shares of concurrent calls queue per device.  Arguments as in the per-context calls.
+ * device_mask: bit d = CUDA device d, 0 = every visible device.  lzgpu_pool_create_list takes explicit device numbers (a
+ * device may be listed twice: two contexts, two pipelines on one GPU).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct lzgpu_pool lzgpu_pool;
+int lzgpu_pool_create(uint64_t device_mask, lzgpu_pool **out);
+int lzgpu_pool_create_list(const int *devices, int n_devices, lzgpu_pool **out);
+void lzgpu_pool_destroy(lzgpu_pool *pool);
+int lzgpu_pool_size(const lzgpu_pool *pool);
+lzgpu_ctx *lzgpu_pool_ctx(lzgpu_pool *pool, int i); /* context of device slot i, for the *_dev calls and per-device statistics */
+void lzgpu_pool_share(uint32_t n_chunks, int n_devices, int i, uint32_t *first, uint32_t *count); /* pure host logic */
+void lzgpu_pool_get_stats(lzgpu_pool *pool, lzgpu_stats *out); /* counters summed over the devices */
+
+/* ---------------------------------------------------------------------------------------------
  * Batched chunk API (what the GPU wants; hook points: ChunkWriter::startOperation,
  * ReadPlan::postProcessData, hdd_int_test).  All chunks of a call share goal and chunk_len.
  *
@@ -157,6 +176,11 @@ int lzgpu_encode_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_c
                             void *d_parity, size_t parity_stride,
                             void *d_crc, size_t crc_stride, void *stream);
 
+int lzgpu_pool_encode_chunks(lzgpu_pool *pool, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t chunk_len,
+                             const uint8_t *data, size_t chunk_stride,
+                             uint8_t *parity, size_t parity_stride,
+                             uint32_t *crc, size_t crc_stride);
+
 /* Degraded read / rebuild of n_chunks chunks.
  *   parts[i]    (i < k+m) part-major buffer of part i for all chunks: chunk c at + c*part_stride,
  *               pb blocks each (short parts zero-padded, slice_read_plan.h:94-105); NULL = unavailable.
@@ -176,6 +200,11 @@ int lzgpu_recover_chunks(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chun
                          const uint32_t *const *part_crc,
                          const uint8_t *want, uint8_t *const *out,
                          uint8_t *chunk_out, size_t chunk_out_stride, int64_t *bad);
+int lzgpu_pool_recover_chunks(lzgpu_pool *pool, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb,
+                              const uint8_t *const *parts, size_t part_stride,
+                              const uint32_t *const *part_crc,
+                              const uint8_t *want, uint8_t *const *out,
+                              uint8_t *chunk_out, size_t chunk_out_stride, int64_t *bad);
 int lzgpu_recover_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb,
                              const void *const *d_parts, size_t part_stride,
                              const void *const *d_part_crc,
@@ -236,6 +265,8 @@ int lzgpu_crc_blocks(lzgpu_ctx *ctx, const uint8_t *data, size_t n_blocks, uint3
                      size_t block_stride, uint32_t *crc_out);
 int lzgpu_crc_blocks_dev(lzgpu_ctx *ctx, const void *d_data, size_t n_blocks, uint32_t block_len,
                          size_t block_stride, void *d_crc_out, void *stream);
+int lzgpu_pool_crc_blocks(lzgpu_pool *pool, const uint8_t *data, size_t n_blocks, uint32_t block_len,
+                          size_t block_stride, uint32_t *crc_out);
 /* The three scrub entry points below accept host pointers or device pointers of the context's device for `data` / `records` /
  * `file_image` and `stored_crc` (unified addressing; a chunk file read straight into device memory needs no host round trip).
  * Scrub (hdd_int_test, hddspacemgr.cc:2174-2190): compare against stored CRCs; returns LZGPU_OK or
@@ -309,6 +340,14 @@ int gf_invert_matrix(unsigned char *in, unsigned char *out, const int n);
 void gf_vect_mul_init(unsigned char c, unsigned char *gftbl);
 void ec_init_tables(int k, int rows, unsigned char *a, unsigned char *gftbls);
 void ec_encode_data(int len, int srcs, int dests, unsigned char *v, unsigned char **src, unsigned char **dest);
+/* The same five under lzgpu_-prefixed names, plus (C++ only, lizardfs_b200/csrc/compat_cxx_gf.cc) C++-LINKAGE definitions of
+ * gf_gen_rs_matrix, gf_gen_cauchy1_matrix, gf_invert_matrix, ec_init_tables, ec_encode_data: the reference's own
+ * src/common/galois_field.h:35-88 declares them without extern "C", so a reference build without ISA-L links as well. */
+void lzgpu_isal_gf_gen_rs_matrix(unsigned char *a, int m, int k);
+void lzgpu_isal_gf_gen_cauchy1_matrix(unsigned char *a, int m, int k);
+int lzgpu_isal_gf_invert_matrix(unsigned char *in, unsigned char *out, const int n);
+void lzgpu_isal_ec_init_tables(int k, int rows, unsigned char *a, unsigned char *gftbls);
+void lzgpu_isal_ec_encode_data(int len, int srcs, int dests, unsigned char *v, unsigned char **src, unsigned char **dest);
 
 /* Synthetic data generator used by bench / tests (device side): fills chunks with the splitmix64
  * counter stream documented in DESIGN.md §6 (same bytes as oracle lzo_fill_chunk). */

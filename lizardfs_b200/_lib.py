@@ -100,6 +100,11 @@ SIGNATURES = {
     "gf_vect_mul_init": (None, [C.c_ubyte, _vp]),
     "ec_init_tables": (None, [_int, _int, _vp, _vp]),
     "ec_encode_data": (None, [_int, _int, _int, _vp, _vp, _vp]),
+    "lzgpu_isal_gf_gen_rs_matrix": (None, [_vp, _int, _int]),
+    "lzgpu_isal_gf_gen_cauchy1_matrix": (None, [_vp, _int, _int]),
+    "lzgpu_isal_gf_invert_matrix": (_int, [_vp, _vp, _int]),
+    "lzgpu_isal_ec_init_tables": (None, [_int, _int, _vp, _vp]),
+    "lzgpu_isal_ec_encode_data": (None, [_int, _int, _int, _vp, _vp, _vp]),
     "lzgpu_fill_chunks_dev": (_int, [_vp, _vp, _u32, _sz, _sz, _u64, _u64, _vp]),
     "lzgpu_dev_alloc": (_int, [_vp, _sz, C.POINTER(_vp)]),
     "lzgpu_dev_free": (_int, [_vp, _vp]),
@@ -110,6 +115,16 @@ SIGNATURES = {
     "lzgpu_host_register": (_int, [_vp, _vp, _sz]),
     "lzgpu_host_unregister": (_int, [_vp, _vp]),
     "lzgpu_dev_sync": (_int, [_vp]),
+    "lzgpu_pool_create": (_int, [_u64, C.POINTER(_vp)]),
+    "lzgpu_pool_create_list": (_int, [C.POINTER(_int), _int, C.POINTER(_vp)]),
+    "lzgpu_pool_destroy": (None, [_vp]),
+    "lzgpu_pool_size": (_int, [_vp]),
+    "lzgpu_pool_ctx": (_vp, [_vp, _int]),
+    "lzgpu_pool_share": (None, [_u32, _int, _int, C.POINTER(_u32), C.POINTER(_u32)]),
+    "lzgpu_pool_get_stats": (None, [_vp, C.POINTER(LzStats)]),
+    "lzgpu_pool_encode_chunks": (_int, [_vp, _goalp, _u32, _u32, _vp, _sz, _vp, _sz, _vp, _sz]),
+    "lzgpu_pool_recover_chunks": (_int, [_vp, _goalp, _u32, _u32, _vp, _sz, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "lzgpu_pool_crc_blocks": (_int, [_vp, _vp, _sz, _u32, _sz, _vp]),
 }
 
 _lib = None

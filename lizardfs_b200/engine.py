@@ -206,6 +206,95 @@ def ec_encode_data(length, tables, src, n_dest):
     return dest
 
 
+
+class Pool:
+    """Several GPUs behind one process (lzgpu_pool in include/lzgpu.h): one context and one worker thread per device, a batch is
+    cut into one contiguous run of chunks per device and every run goes through that device's own host pipeline.  `devices`:
+    None = every visible device, an int mask, or a list of device numbers (a device may appear twice)."""
+
+    def __init__(self, devices=None):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        if devices is None or isinstance(devices, int):
+            rc = self.lib.lzgpu_pool_create(int(devices or 0), C.byref(h))
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.lib.lzgpu_pool_create_list(arr, len(devices), C.byref(h))
+        if rc != _lib.OK:
+            raise LzGpuError(rc, f"lzgpu_pool_create({devices})")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lzgpu_pool_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return self.lib.lzgpu_pool_size(self.h)
+
+    @staticmethod
+    def share(n_chunks, n_devices, i):
+        """(first chunk, count) of device slot i — pure host logic, usable without a GPU"""
+        first, count = C.c_uint32(), C.c_uint32()
+        _lib.load().lzgpu_pool_share(n_chunks, n_devices, i, C.byref(first), C.byref(count))
+        return first.value, count.value
+
+    def stats(self):
+        s = LzStats()
+        self.lib.lzgpu_pool_get_stats(self.h, C.byref(s))
+        return {f[0]: getattr(s, f[0]) for f in LzStats._fields_}
+
+    def encode_chunks(self, goal, data, chunk_len=None, parity=None, crc=None):
+        data = _u8(data)
+        if data.ndim == 1:
+            data = data.reshape(1, -1)
+        n, stride = data.shape
+        if chunk_len is None:
+            chunk_len = stride
+        nb, pb = Engine.geometry(goal, chunk_len)
+        if parity is None:
+            parity = np.empty((n, goal.m, pb * BLOCK_SIZE), dtype=np.uint8)
+        if crc is None:
+            crc = np.empty((n, nb + goal.m * pb), dtype=np.uint32)
+        _check(self.lib.lzgpu_pool_encode_chunks(self.h, C.byref(goal.c), n, chunk_len, _p(data), stride, _p(parity),
+                                                 goal.m * pb * BLOCK_SIZE, _p(crc), nb + goal.m * pb), "pool_encode_chunks")
+        return parity, crc
+
+    def recover_chunks(self, goal, nb, parts, part_crc=None, want=None, chunk_image=False):
+        n_parts = goal.k + goal.m
+        pb = (nb + goal.k - 1) // goal.k
+        parts = [None if p is None else _u8(p).reshape(-1, pb * BLOCK_SIZE) for p in parts]
+        n = next(p.shape[0] for p in parts if p is not None)
+        if want is None:
+            want = [1 if (parts[i] is None and i < goal.k) else 0 for i in range(n_parts)]
+        w = np.asarray(want, dtype=np.uint8)
+        out = [np.zeros((n, pb * BLOCK_SIZE), dtype=np.uint8) if (w[i] and parts[i] is None) else None for i in range(n_parts)]
+        crcs = None
+        if part_crc is not None:
+            crcs = [None if c is None else np.ascontiguousarray(c, dtype=np.uint32) for c in part_crc]
+        img = np.zeros((n, nb * BLOCK_SIZE), dtype=np.uint8) if chunk_image else None
+        bad = (C.c_int64 * 3)(-1, -1, -1)
+        rc = self.lib.lzgpu_pool_recover_chunks(self.h, C.byref(goal.c), n, nb, _ptr_array(parts), pb * BLOCK_SIZE,
+                                                _ptr_array(crcs) if crcs is not None else None, _p(w), _ptr_array(out),
+                                                _p(img), nb * BLOCK_SIZE, bad)
+        if rc == _lib.ERR_CRC:
+            raise ChunkCrcError(rc, "pool_recover_chunks", (bad[0], bad[1], bad[2]))
+        _check(rc, "pool_recover_chunks")
+        return out, img
+
+    def crc_blocks(self, data, block_len=BLOCK_SIZE):
+        data = _u8(data).reshape(-1, block_len)
+        out = np.empty(data.shape[0], dtype=np.uint32)
+        _check(self.lib.lzgpu_pool_crc_blocks(self.h, _p(data), data.shape[0], block_len, block_len, _p(out)), "pool_crc_blocks")
+        return out
+
+
 class ReedSolomon:
     """Mirror of ReedSolomon<32,32> (src/common/reed_solomon.h:41-155)."""
 

@@ -82,3 +82,43 @@ def test_stripe_batcher_host_logic_on_cpu():
 def test_read_plan_mirror_host_logic_on_cpu():
     """part numbering, buffer layout, BlockConverter of lzgpu::SliceReadPlan on plans built by the reference's ChunkReadPlanner"""
     _run_cpu_build("test_read_plan_cpu", needs_ref=True)
+
+
+LINK_SUB = os.path.join(ROOT, "tests", "cpp", "build", "test_link_substitution")
+LINK_SUB_CXX = os.path.join(ROOT, "tests", "cpp", "build", "test_link_substitution_cxx")
+
+
+def _need_link_sub(exe):
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")], check=False)
+    if not os.path.exists(exe):
+        pytest.skip("built only where /root/reference exists (the reference's unit-test sources are compiled in place)")
+
+
+@pytest.mark.parametrize("exe", [LINK_SUB, LINK_SUB_CXX], ids=["isal_names", "cxx_names"])
+def test_link_substitution_binaries_use_only_liblzgpu(exe):
+    """The reference's own unit-test sources, linked: every GF / CRC / xor symbol must come from liblzgpu.so — no oracle, no
+    reference objects for crc.cc / block_xor.cc / galois_field_*.cc in the link."""
+    _need_link_sub(exe)
+    ldd = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    assert "liblzgpu.so" in ldd and "liblzref" not in ldd and "liboracle" not in ldd and "not found" not in ldd
+    undefined = subprocess.run(["nm", "-C", "-u", exe], capture_output=True, text=True).stdout
+    for name in ("ec_encode_data", "ec_init_tables", "gf_gen_rs_matrix", "gf_invert_matrix"):
+        assert name in undefined, name  # resolved at load time by the shared library, not by an object of the reference
+    if exe == LINK_SUB:
+        for name in ("mycrc32(", "mycrc32_combine(", "blockXor("):
+            assert name in undefined, name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("exe", [LINK_SUB, LINK_SUB_CXX], ids=["isal_names", "cxx_names"])
+def test_reference_unit_tests_run_on_the_gpu_library(exe):
+    """reed_solomon_unittest.cc, crc_unittest.cc, block_xor_unittest.cc, ec_read_plan_unittest.cc, xor_read_plan_unittest.cc of the
+    reference (unmodified, compiled where they lie) with liblzgpu.so substituted at link time: all their expectations hold."""
+    _need_link_sub(exe)
+    r = subprocess.run([exe, "-Benchmark"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
+    assert "0 failed expectations" in r.stdout
+    assert "ReedSolomon.TestRecovery" in r.stdout
+    if exe == LINK_SUB:
+        assert "ECReadPlanTests.VerifyRead1" in r.stdout and "CrcTests.MyCrc32" in r.stdout and "BlockXorTests.BlockXor" in r.stdout

@@ -3,6 +3,7 @@
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/r1_gpu.txt
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r1_pytest.log 2>&1; tail -3 gpurun_out/r1_pytest.log
 ./tools/micro/warpmap > gpurun_out/r1_warpmap.txt 2>&1
 python tools/sweep.py --full-size-only --sections enc,rec --rec 'ec(8,2):1,4;ec(3,2):0,2;ec(5,3):0,1,4;xor3:1' --out gpurun_out/r1_sweep_base.md > /dev/null 2> gpurun_out/r1_sweep_base.err
 LZGPU_LIB=$PWD/lizardfs_b200/liblzgpu_t256.so python tools/sweep.py --full-size-only --sections enc --out gpurun_out/r1_sweep_t256.md > /dev/null 2> gpurun_out/r1_sweep_t256.err
