@@ -220,6 +220,58 @@ def test_encode_full_size_ec32_tail_stripe(eng, oracle):
     assert (parity[0] == p_ref).all() and (crc[0] == c_ref).all()
 
 
+@pytest.mark.parametrize("text", ["xor2", "xor3", "ec(5,3)", "ec(8,4)", "ec(3,2)", "ec(8,2)"])
+def test_encode_full_size_chunk_every_bench_goal_vs_reference(eng, oracle, ref, text):
+    """BASELINE configs[1], [2], [4] at the size the numbers are quoted on: one full 64 MiB chunk per goal of the mixed sweep,
+    parity parts and all block CRCs bit-exact against the compiled reference (oracle/_ref; the restatement where it is absent).
+    Two chunks are encoded so that the second one exercises the unit that straddles the chunk boundary."""
+    goal = L.SliceType(text)
+    data = np.stack([O.fill_chunk(oracle, 64 << 20, 12345, c) for c in (3, 4)])
+    parity, crc = eng.encode_chunks(goal, data)
+    checker = ref if ref is not None else oracle
+    for c in range(2):
+        p_ref, c_ref = checker.encode_chunk(goal.kind, goal.k, goal.m, data[c])
+        assert (parity[c] == p_ref).all(), (text, c)
+        assert (crc[c] == c_ref).all(), (text, c)
+
+
+@pytest.mark.parametrize("clen_blocks", [16, 64, 256, 597])
+@pytest.mark.parametrize("text", ["xor2", "xor3", "ec(5,3)", "ec(8,4)"])
+def test_encode_sweep_chunk_sizes_vs_reference(eng, oracle, ref, text, clen_blocks):
+    """the other chunk sizes of the mixed sweep (1, 4, 16 and 37.31 MiB), a batch of several chunks each, vs the reference"""
+    goal = L.SliceType(text)
+    n = 5
+    data = np.stack([O.fill_chunk(oracle, clen_blocks * BLOCK, 777, c) for c in range(n)])
+    parity, crc = eng.encode_chunks(goal, data)
+    checker = ref if ref is not None else oracle
+    for c in (0, n // 2, n - 1):
+        p_ref, c_ref = checker.encode_chunk(goal.kind, goal.k, goal.m, data[c])
+        assert (parity[c] == p_ref).all() and (crc[c] == c_ref).all(), (text, clen_blocks, c)
+
+
+def test_recover_full_size_every_pair_vs_reference(eng, oracle, ref):
+    """BASELINE configs[3] at full size: ec(8,2), one 64 MiB chunk, EVERY pair of lost parts (28 data pairs, 16 data+parity
+    pairs, the parity pair), rebuilt parts compared with the reference's own recover (ECReadPlan::recoverParts semantics,
+    oracle ref_recover_chunk) and with the withheld originals."""
+    goal = L.SliceType("ec(8,2)")
+    k, m, nb, pb = 8, 2, 1024, 128
+    data = O.fill_chunk(oracle, 64 << 20, 4242, 0).reshape(1, -1)
+    parity, crc = eng.encode_chunks(goal, data)
+    parts = all_parts(data, parity, k)
+    checker = ref if ref is not None else oracle
+    for lost in itertools.combinations(range(k + m), 2):
+        avail = [None if i in lost else parts[i] for i in range(k + m)]
+        want = [1 if i in lost else 0 for i in range(k + m)]
+        out, _ = eng.recover_chunks(goal, nb, avail, want=want)
+        for i in lost:
+            assert (out[i][0] == parts[i][0]).all(), (lost, i)
+        if lost[1] - lost[0] in (1, 5):   # a third of the patterns also against the reference's recover (it is slow at this size)
+            rc, ro, _ = checker.recover_chunk(goal.kind, k, m, [None if a is None else a[0] for a in avail], None, want, pb)
+            assert rc == 0
+            for i in lost:
+                assert (ro[i] == out[i][0]).all(), (lost, i)
+
+
 def test_full_size_batch_roundtrip_with_verification(eng):
     """BASELINE configs[2]/[3] at full chunk size: encode a batch of 64 MiB chunks, lose two data parts, recover with the
     stored CRCs verified and the chunk-order image rebuilt; the round trip must reproduce every byte."""
