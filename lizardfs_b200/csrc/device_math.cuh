@@ -74,21 +74,50 @@ __device__ __forceinline__ uint32_t gf_x4_add(uint32_t v, uint32_t d) { return g
 __device__ __forceinline__ uint32_t gf_x8_add(uint32_t v, uint32_t d) { return gf_x2_add(gf_x2(gf_x2(v)), d); }
 #endif
 
-// One coefficient prepared for the bit-plane product: plane[b] = c * 2^b in GF(2^8), each stored
-// in a 32-bit word so that  c*v = XOR_b ((v >> b) & 0x01010101) * plane[b]  — every partial
-// product stays inside its byte lane (a 0/1 byte times an 8-bit constant), hence no carries.
+// One coefficient c prepared for the bit-plane product  c*v = XOR_b ((v >> b) & 0x01010101) * (c * 2^b):  every partial product
+// is a 0/1 byte times an 8-bit constant P_b = c*2^b (in GF(2^8)), so it stays inside its byte lane (no carries).
+// The shift is folded into the multiplications so that the ALU pipe only sees the mask and the final XORs:
+//   x = v & (0x01010101 << b)                      bit b of every byte, in place                      (1 LOP3)
+//   (x >> b) * P_b = umulhi(x, lo[b]) + x * hi[b]  with  lo[b] = (P_b mod 2^b) << (32 - b),  hi[b] = P_b >> b
+// — the low b bits of P_b come down through the high half of a 64-bit product, the high 8-b bits go up in place; the two
+// results occupy disjoint bits of the lane, so the addend of IMAD.HI joins them (2 ops on the FMA pipe).
+// Per packed word and coefficient: 8 LOP3 (masks) + 4 LOP3 (3-input XORs) on the ALU pipe and 15 IMAD/IMAD.HI on the FMA pipe;
+// some bits may use a funnel shift instead (template parameter NS below) to level the two pipes.
 struct CoefPlanes {
-	uint32_t plane[8];
+	uint32_t lo[8];  // lo[0] = 0
+	uint32_t hi[8];  // hi[0] = c
 };
 
+// host or device: fill the planes of coefficient c (x^8 = x^4+x^3+x^2+1, reference galois_coeff.h:30-32)
+__host__ __device__ inline void coef_planes_set(CoefPlanes &out, uint32_t c) {
+	uint32_t v = c & 0xffu;
+	for (int b = 0; b < 8; ++b) {
+		out.lo[b] = b ? ((v & ((1u << b) - 1u)) << (32 - b)) : 0u;
+		out.hi[b] = v >> b;
+		v = ((v << 1) ^ ((v & 0x80u) ? 0x1du : 0u)) & 0xffu;
+	}
+}
+
+// NS = how many of the bits 7, 6, ... use the funnel-shift form  ((v >> b) & 0x01010101) * P_b  (2 ALU + 1 FMA op; mask and
+// shift are shared by every coefficient applied to the same word) instead of the in-place form (1 ALU + 2 FMA).  With R
+// coefficients per input word the ALU pipe sees 8 + NS + 4R ops and the FMA pipe R(15 - NS): callers pick NS so that the two
+// pipes (both one warp instruction per two cycles) are level, counting what else the kernel puts on the ALU pipe.
+template <int NS>
+__device__ __forceinline__ uint32_t gf_mac_term(uint32_t v, const CoefPlanes &c, int b) {
+	if (b == 0) return (v & 0x01010101u) * c.hi[0];
+	if (b >= 8 - NS) return ((v >> b) & 0x01010101u) * ((c.hi[b] << b) | (c.lo[b] >> (32 - b)));
+	const uint32_t x = v & (0x01010101u << b);
+	uint32_t up, r;
+	asm("mul.lo.u32 %0, %1, %2;" : "=r"(up) : "r"(x), "r"(c.hi[b]));
+	asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(c.lo[b]), "r"(up));
+	return r;
+}
+
 // acc ^= c * v for one packed word
+template <int NS = 2>
 __device__ __forceinline__ uint32_t gf_mac(uint32_t acc, uint32_t v, const CoefPlanes &c) {
 #pragma unroll
-	for (int b = 0; b < 8; b += 2) {
-		const uint32_t p0 = ((v >> b) & 0x01010101u) * c.plane[b];
-		const uint32_t p1 = ((v >> (b + 1)) & 0x01010101u) * c.plane[b + 1];
-		acc = acc ^ p0 ^ p1;
-	}
+	for (int b = 0; b < 8; b += 2) acc = acc ^ gf_mac_term<NS>(v, c, b) ^ gf_mac_term<NS>(v, c, b + 1);
 	return acc;
 }
 

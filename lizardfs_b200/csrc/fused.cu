@@ -237,11 +237,7 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	if (generic) {
 		for (int r = 0; r < M; ++r)
 			for (uint32_t j = 0; j < K; ++j) {
-				uint8_t v = coef_rows[r * K + j];
-				for (int b = 0; b < 8; ++b) {
-					p.coef[r * 32 + j].plane[b] = v;
-					v = lz::gf_mul_host(v, 2);
-				}
+				coef_planes_set(p.coef[r * 32 + j], coef_rows[r * K + j]);
 			}
 	}
 	CUtensorMap map;
@@ -463,11 +459,7 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 	if (gf_invert_matrix(V, W, static_cast<int>(e)) != 0) return LZGPU_NOT_HANDLED;  // generic path reports the singular case
 	for (uint32_t x = 0; x < e; ++x)
 		for (uint32_t r = 0; r < e; ++r) {
-			uint8_t v = W[x * e + r];
-			for (int b = 0; b < 8; ++b) {
-				p.w[x * 4 + r].plane[b] = v;
-				v = lz::gf_mul_host(v, 2);
-			}
+			coef_planes_set(p.w[x * 4 + r], W[x * e + r]);
 		}
 	p.raid6_dbl = 0xffu;
 	if (e == 2 && p.par_row[0] == 0 && p.par_row[1] == 1 && !(K == 8 && G == 8)) {
@@ -475,13 +467,8 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 		uint8_t gx0 = 1, gx1 = 1;
 		for (int t = 0; t < p.erased_idx[0]; ++t) gx0 = lz::gf_mul_host(gx0, 2);
 		for (int t = 0; t < p.erased_idx[1]; ++t) gx1 = lz::gf_mul_host(gx1, 2);
-		uint8_t v0 = gx0, v1 = lz::gf_inv_host(gx0 ^ gx1);
-		for (int b = 0; b < 8; ++b) {
-			p.w[0].plane[b] = v0;
-			p.w[1].plane[b] = v1;
-			v0 = lz::gf_mul_host(v0, 2);
-			v1 = lz::gf_mul_host(v1, 2);
-		}
+		coef_planes_set(p.w[0], gx0);
+		coef_planes_set(p.w[1], lz::gf_inv_host(gx0 ^ gx1));
 		if (p.erased_idx[0] <= 4) p.raid6_dbl = p.erased_idx[0];
 	}
 	TmapArray maps;

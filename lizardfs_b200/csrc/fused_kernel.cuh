@@ -379,10 +379,11 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 #pragma unroll
 								for (int r = 0; r < M; ++r) {
 									const CoefPlanes &cp = p.coef[r * 32 + j];
-									acc[r][0] = gf_mac(acc[r][0], v.x, cp);
-									acc[r][1] = gf_mac(acc[r][1], v.y, cp);
-									acc[r][2] = gf_mac(acc[r][2], v.z, cp);
-									acc[r][3] = gf_mac(acc[r][3], v.w, cp);
+									// M coefficients share the word: ALU 8 + NS + 4M next to the CRC folds, FMA M (15 - NS)
+									acc[r][0] = gf_mac<6>(acc[r][0], v.x, cp);
+									acc[r][1] = gf_mac<6>(acc[r][1], v.y, cp);
+									acc[r][2] = gf_mac<6>(acc[r][2], v.z, cp);
+									acc[r][3] = gf_mac<6>(acc[r][3], v.w, cp);
 								}
 							} else {
 #pragma unroll

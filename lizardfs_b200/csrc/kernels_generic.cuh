@@ -33,14 +33,7 @@ struct DotArgs {
 template <int ND>
 __global__ void __launch_bounds__(256) gf_dot_kernel(const DotArgs a) {
 	extern __shared__ CoefPlanes s_coef[];  // [ND][n_src]
-	for (unsigned i = threadIdx.x; i < ND * a.n_src; i += blockDim.x) {
-		uint32_t v = a.coef[i];
-#pragma unroll
-		for (int b = 0; b < 8; ++b) {
-			s_coef[i].plane[b] = v;                                  // plane[b] = c * 2^b
-			v = ((v << 1) ^ ((v & 0x80u) ? 0x1du : 0u)) & 0xffu;     // x^8 = x^4+x^3+x^2+1 (galois_coeff.h:30-32)
-		}
-	}
+	for (unsigned i = threadIdx.x; i < ND * a.n_src; i += blockDim.x) coef_planes_set(s_coef[i], a.coef[i]);
 	__syncthreads();
 
 	const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
@@ -68,10 +61,11 @@ __global__ void __launch_bounds__(256) gf_dot_kernel(const DotArgs a) {
 #pragma unroll
 				for (int d = 0; d < ND; ++d) {
 					const CoefPlanes &cp = s_coef[d * a.n_src + j];
-					acc[d][0] = gf_mac(acc[d][0], v.x, cp);
-					acc[d][1] = gf_mac(acc[d][1], v.y, cp);
-					acc[d][2] = gf_mac(acc[d][2], v.z, cp);
-					acc[d][3] = gf_mac(acc[d][3], v.w, cp);
+					constexpr int NS = ND == 1 ? 3 : ND == 2 ? 5 : 7;  // levels ALU (8 + NS + 4 ND) against FMA (ND (15 - NS)) per word
+					acc[d][0] = gf_mac<NS>(acc[d][0], v.x, cp);
+					acc[d][1] = gf_mac<NS>(acc[d][1], v.y, cp);
+					acc[d][2] = gf_mac<NS>(acc[d][2], v.z, cp);
+					acc[d][3] = gf_mac<NS>(acc[d][3], v.w, cp);
 				}
 			}
 		}
