@@ -328,6 +328,9 @@ uint32_t lzgpu_mycrc32_zeroblock(uint32_t crc, uint32_t zeros);                 
 uint32_t lzgpu_mycrc32_zeroexpanded(uint32_t crc, const uint8_t *block, uint32_t leng, uint32_t zeros);
 uint32_t lzgpu_mycrc32_xorblocks(uint32_t crc, uint32_t crcblock1, uint32_t crcblock2, uint32_t leng);
 void lzgpu_recompute_crc_if_block_empty(const uint8_t *block, uint32_t *crc);       /* crc.cc:235-243 */
+/* mycrc32(0, block + from, to - from) from mycrc32 of the whole 64 KiB block when every byte outside [from, to) is zero
+ * (host scalar, the combine identity run backwards): lets sub-block writes ride the whole-block batched kernels. */
+uint32_t lzgpu_mycrc32_subrange(uint32_t crc_of_padded_block, uint32_t from, uint32_t to);
 
 /* ISA-L / galois_field.h names.  Matrix helpers are host scalar code (k <= 32: microseconds);
  * ec_encode_data moves the fragments to the GPU, runs the GF(2^8) dot-product kernel and copies

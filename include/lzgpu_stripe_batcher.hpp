@@ -14,8 +14,15 @@
 // block, and the 38-byte packet prefixes come back together; the sink receives exactly what addDataPacket would
 // have been given, plus the CRC and the finished prefix, so sending is a pointer hand-off.
 //
-// Whole blocks only (from = 0, to = 64 KiB).  Sub-block operations (WriteCacheBlock::from/to, chunk_writer.cc:479-481)
-// stay on the per-call path: ReedSolomon<>::recover on `size` bytes through lzgpu_reed_solomon.hpp.
+// Sub-block operations (WriteCacheBlock::from / to, src/mount/write_cache_block.cc:64-68; startOperation takes block_from /
+// block_to / block_size from the first block of the stripe and gives the parity blocks the same range,
+// chunk_writer.cc:479-481,522-529) are batched as well: a stripe whose blocks cover [from, to) is staged as whole 64 KiB blocks
+// that are zero outside the range.  GF(2^8) parity is byte-wise, so the whole-block parity is the range's parity inside
+// [from, to) and zero outside; the CRC of the `to - from` bytes that travel comes from the whole-block CRC through the
+// concatenation identity run backwards (lzgpu_mycrc32_subrange, host scalar).  The sink then receives offset = from,
+// size = to - from, data = block + from and a prefix carrying that offset and size — what addDataPacket(writeId, block,
+// from, size, data) is given in the reference.  The per-call path (computeParityBlock below) remains for callers that want a
+// single stripe encoded at once.
 #pragma once
 #include <algorithm>
 #include <cstdint>
@@ -37,8 +44,9 @@ struct PartBlock {
 	int part;                  // this API's numbering: data 0..k-1, parity k..k+m-1 (lzgpu_ref_part_index converts)
 	uint32_t block;            // block index inside the part = stripe index (blockIndex / data_part_count, chunk_writer.cc:541)
 	uint32_t write_id;
-	const uint8_t *data;       // 64 KiB, valid until the next flush()/addBlock()
-	uint32_t crc;              // mycrc32(0, data, 65536)
+	uint32_t offset, size;     // byte range inside the block: 0 / 64 KiB for whole blocks, from / to - from for a sub-block stripe
+	const uint8_t *data;       // `size` bytes (the block's bytes from `offset` on), valid until the next flush()/addBlock()
+	uint32_t crc;              // mycrc32(0, data, size)
 	const uint8_t *prefix;     // LZGPU_WRITE_PREFIX_SIZE bytes, ready to send in front of `data`
 };
 
@@ -83,7 +91,15 @@ public:
 	// (WriteCacheBlock::kReadBlock): it takes part in the parity but is not handed to the sink (chunk_writer.cc:503-508).
 	// A second write of the same block replaces the first.  Returns false when no stripe slot is free (flush first).
 	bool addBlock(uint64_t chunk_id, uint32_t block_index, const uint8_t *data, bool read_back = false) {
-		if (block_index >= LZGPU_BLOCKS_IN_CHUNK || !data) throw std::invalid_argument("StripeBatcher::addBlock: bad block");
+		return addBlockRange(chunk_id, block_index, 0, LZGPU_BLOCK_SIZE, data, read_back);
+	}
+
+	// ChunkWriter::addOperation for bytes [from, to) of a block (`data` points at byte `from`).  Every block of a stripe must
+	// carry the same range (the reference builds an operation from journal positions of one range, Operation::isExpandPossible):
+	// a different range for a buffered stripe throws.
+	bool addBlockRange(uint64_t chunk_id, uint32_t block_index, uint32_t from, uint32_t to, const uint8_t *data, bool read_back = false) {
+		if (block_index >= LZGPU_BLOCKS_IN_CHUNK || !data || from >= to || to > LZGPU_BLOCK_SIZE)
+			throw std::invalid_argument("StripeBatcher::addBlock: bad block or range");
 		const Key key(chunk_id, block_index / k_);
 		auto it = index_.find(key);
 		if (it == index_.end()) {
@@ -94,14 +110,20 @@ public:
 			// blocks past the end of the chunk do not exist: the last stripe of a chunk is complete without them
 			// (range_end, chunk_writer.cc:449), and they enter the parity as zeros
 			s.expected = std::min<uint32_t>(k_, LZGPU_BLOCKS_IN_CHUNK - s.stripe * k_);
+			s.from = from;
+			s.to = to;
 			std::memset(slot_data(slots_.size()) + static_cast<size_t>(s.expected) * LZGPU_BLOCK_SIZE, 0,
 			            static_cast<size_t>(k_ - s.expected) * LZGPU_BLOCK_SIZE);
 			it = index_.emplace(key, static_cast<uint32_t>(slots_.size())).first;
 			slots_.push_back(s);
 		}
 		Slot &s = slots_[it->second];
+		if (s.from != from || s.to != to) throw std::invalid_argument("StripeBatcher::addBlock: the blocks of a stripe must cover the same byte range");
 		const uint32_t j = block_index % k_;
-		std::memcpy(slot_data(it->second) + static_cast<size_t>(j) * LZGPU_BLOCK_SIZE, data, LZGPU_BLOCK_SIZE);
+		uint8_t *dst = slot_data(it->second) + static_cast<size_t>(j) * LZGPU_BLOCK_SIZE;
+		if (from) std::memset(dst, 0, from);  // staged as a whole block that is zero outside the range
+		std::memcpy(dst + from, data, to - from);
+		if (to < LZGPU_BLOCK_SIZE) std::memset(dst + to, 0, LZGPU_BLOCK_SIZE - to);
 		s.present |= 1ull << j;
 		if (read_back) s.read_back |= 1ull << j;
 		else s.read_back &= ~(1ull << j);
@@ -131,6 +153,9 @@ public:
 			if (i != n) swap_slots(i, n);
 			++n;
 		}
+		// the slots moved: the (chunk, stripe) -> slot map is rebuilt BEFORE anything can throw, so a failed encode leaves the
+		// batcher consistent and a retry copies into the right stripe
+		rebuild_index();
 		if (n == 0) return 0;
 		const uint32_t chunk_len = static_cast<uint32_t>(k_ * B);
 		int rc = lzgpu_encode_chunks(ctx_, &goal_, static_cast<uint32_t>(n), chunk_len, data_, chunk_len, parity_, m_ * B, crc_, k_ + m_);
@@ -146,10 +171,13 @@ public:
 				pb.part = part;
 				pb.block = s.stripe;
 				pb.write_id = write_id++;
-				pb.data = part < k_ ? slot_data(i) + part * B : parity_ + (i * m_ + (part - k_)) * B;
-				pb.crc = crc[part];  // layout of lzgpu_encode_chunks: k data CRCs in chunk order, then one per parity part
+				pb.offset = s.from;
+				pb.size = s.to - s.from;
+				pb.data = (part < k_ ? slot_data(i) + part * B : parity_ + (i * m_ + (part - k_)) * B) + s.from;
+				// layout of lzgpu_encode_chunks: k data CRCs in chunk order, then one per parity part (whole-block CRCs)
+				pb.crc = (s.from == 0 && s.to == B) ? crc[part] : lzgpu_mycrc32_subrange(crc[part], s.from, s.to);
 				uint8_t *px = prefix_.data() + (i * (k_ + m_) + part) * LZGPU_WRITE_PREFIX_SIZE;
-				write_prefix(px, s.chunk_id, pb.write_id, static_cast<uint16_t>(s.stripe), pb.crc);
+				write_prefix(px, s.chunk_id, pb.write_id, static_cast<uint16_t>(s.stripe), pb.offset, pb.size, pb.crc);
 				pb.prefix = px;
 				sink(pb);
 			}
@@ -158,8 +186,7 @@ public:
 		std::vector<Slot> rest(slots_.begin() + n, slots_.end());
 		for (size_t i = 0; i < rest.size(); ++i) std::memmove(slot_data(i), slot_data(n + i), static_cast<size_t>(k_) * B);
 		slots_.swap(rest);
-		index_.clear();
-		for (size_t i = 0; i < slots_.size(); ++i) index_.emplace(Key(slots_[i].chunk_id, slots_[i].stripe), static_cast<uint32_t>(i));
+		rebuild_index();
 		return n;
 	}
 
@@ -168,8 +195,14 @@ private:
 	struct Slot {
 		uint64_t chunk_id = 0;
 		uint32_t stripe = 0, expected = 0;
+		uint32_t from = 0, to = LZGPU_BLOCK_SIZE;  // byte range every block of the stripe covers
 		uint64_t present = 0, read_back = 0;  // bit j = data part j (k <= 32)
 	};
+
+	void rebuild_index() {
+		index_.clear();
+		for (size_t i = 0; i < slots_.size(); ++i) index_.emplace(Key(slots_[i].chunk_id, slots_[i].stripe), static_cast<uint32_t>(i));
+	}
 
 	void alloc(void **p, size_t bytes) {
 		if (lzgpu_host_alloc(ctx_, bytes, p) != LZGPU_OK) throw std::runtime_error(std::string("StripeBatcher: ") + lzgpu_last_error());
@@ -186,12 +219,12 @@ private:
 	}
 	// cltocs::writeData::serializePrefix (src/protocol/cltocs.h:116-137): header (type 1212, length 30 + size), version 0,
 	// chunkId, writeId, block, offset, size, crc — big-endian
-	static void write_prefix(uint8_t *p, uint64_t chunk_id, uint32_t write_id, uint16_t block, uint32_t crc) {
+	static void write_prefix(uint8_t *p, uint64_t chunk_id, uint32_t write_id, uint16_t block, uint32_t offset, uint32_t size, uint32_t crc) {
 		auto be = [&p](uint64_t v, int bytes) {
 			for (int i = bytes - 1; i >= 0; --i) *p++ = static_cast<uint8_t>(v >> (8 * i));
 		};
-		be(1212, 4); be(30u + LZGPU_BLOCK_SIZE, 4); be(0, 4); be(chunk_id, 8); be(write_id, 4); be(block, 2); be(0, 4);
-		be(LZGPU_BLOCK_SIZE, 4); be(crc, 4);
+		be(1212, 4); be(30u + size, 4); be(0, 4); be(chunk_id, 8); be(write_id, 4); be(block, 2); be(offset, 4);
+		be(size, 4); be(crc, 4);
 	}
 
 	lzgpu_ctx *ctx_;

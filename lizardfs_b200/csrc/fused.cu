@@ -52,6 +52,7 @@ static uint32_t crc_xpow_bits_signed(long long n) {
 
 template <int M, bool GENERIC, int KT = 0, int GT = 0, int FW = 64, bool STRIPED = false>
 static int set_smem_attr(int bytes) {
+	if (FW == 64) bytes = std::max(bytes, fused_smem_cap(M, FW));  // one-CTA-per-SM shapes use a deeper ring
 	CUDA_TRY(cudaFuncSetAttribute(fused_stream_kernel<M, GENERIC, KT, GT, FW, STRIPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
 	return LZGPU_OK;
 }
@@ -138,6 +139,11 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if ((rc = set_smem_attr<3, false, 5, 8>(smem))) return rc;
 	if ((rc = set_smem_attr<3, false, 6, 8>(smem))) return rc;
 	if ((rc = set_smem_attr<4, false, 8, 5>(smem))) return rc;
+#if LZ_T34 == 512
+	if ((rc = set_smem_attr<3, false, 5, 12>(smem))) return rc;
+	if ((rc = set_smem_attr<3, false, 6, 10>(smem))) return rc;
+	if ((rc = set_smem_attr<4, false, 8, 8>(smem))) return rc;
+#endif
 #ifdef LZ_ENABLE_FOLD128
 	const int smem128 = std::min(fs->max_smem, kSmemCap128);
 	if ((rc = set_smem_attr<0, false, 0, 0, 128>(smem128))) return rc;
@@ -179,7 +185,7 @@ static int make_tensor_map(FusedState *fs, CUtensorMap *map, const void *base, u
 
 template <int M, bool GENERIC, int KT = 0, int GT = 0, int FW = 64, bool STRIPED = false>
 static int launch(lzgpu_ctx *ctx, const CUtensorMap &map, const FusedParams &p, size_t smem, cudaStream_t st) {
-	const int per_sm = FW == 64 ? 2 : 1;
+	const int per_sm = fused_ctas_per_sm(M, FW);
 	const int grid = static_cast<int>(std::min<uint64_t>(p.total_units, static_cast<uint64_t>(ctx->sm_count) * per_sm));
 	fused_stream_kernel<M, GENERIC, KT, GT, FW, STRIPED><<<grid, fused_threads(M), smem, st>>>(map, p);
 	CUDA_TRY(cudaGetLastError());
@@ -209,7 +215,7 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	FusedState *fs = ctx->fused;
 	const uint32_t PC = M == 0 ? 0 : (generic ? M : M - 1);
 	const int fw = choose_fold(fs, M, generic);
-	const int smem_cap = std::min(fs->max_smem, fw == 64 ? kSmemCap : kSmemCap128);
+	const int smem_cap = std::min(fs->max_smem, fw == 64 ? fused_smem_cap(generic ? 4 : M, fw) : kSmemCap128);
 	// unit geometry: per-chunk, flat or striped units, stripes per unit (fused_plan.h; unit-tested without a GPU)
 	const FusedPlan pl = fused_plan(M, generic, K, n_chunks, nb, chunk_stride, smem_cap, fw, fs->striped);
 	if (!pl.ok || (reinterpret_cast<uintptr_t>(d_data) % 16)) return LZGPU_NOT_HANDLED;
@@ -296,6 +302,11 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	LZ_FOLDED(3, 5, 8)    // ec(5,3)
 	LZ_FOLDED(3, 6, 8)    // ec(6,3)
 	LZ_FOLDED(4, 8, 5)    // ec(8,4)
+#if LZ_T34 == 512
+	LZ_FOLDED(3, 5, 12)   // one 16-warp CTA per SM
+	LZ_FOLDED(3, 6, 10)
+	LZ_FOLDED(4, 8, 8)
+#endif
 #undef LZ_FOLDED
 	switch (M) {
 		case 0: return launch<0, false>(ctx, map, p, smem, st);

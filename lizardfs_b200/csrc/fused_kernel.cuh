@@ -234,9 +234,9 @@ __device__ __forceinline__ uint32_t fold_finish(uint32_t (&win)[FW], const uint3
 // (An explicit __maxnreg__(96) instead of the launch bounds produced a 5 % slower kernel on the same box: ptxas
 // schedules differently when it does not know the block size.)
 template <int M, bool GENERIC, int KT, int GT, int FW, bool STRIPED = false>
-__global__ void __launch_bounds__(fused_threads(M), FW == 64 ? 2 : 1)
+__global__ void __launch_bounds__(fused_threads(M), fused_ctas_per_sm(M, FW))
 fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
-	constexpr int kNST = fused_nst(FW), kNPST = fused_npst(FW);
+	constexpr int kNST = fused_nst(FW, M), kNPST = fused_npst(FW, M);
 	constexpr int NT = fused_threads(M);
 	constexpr int PC = (M == 0) ? 0 : (GENERIC ? M : M - 1);  // parity parts whose CRC is computed from bytes
 	constexpr int P0 = GENERIC ? 0 : 1;                       // first such parity part

@@ -28,31 +28,41 @@ constexpr int kSmemCap = 113 * 1024;                   // dynamic shared memory 
 #ifndef LZ_T2
 #define LZ_T2 kConsumers  // experiment builds: -DLZ_T2=256 (one or two parity rows on 8-warp CTAs)
 #endif
-LZ_HD constexpr int fused_threads(int m) { return m >= 3 ? 256 : LZ_T2; }
+#ifndef LZ_T34
+#define LZ_T34 256        // experiment builds: -DLZ_T34=512 (three or four parity rows on ONE 16-warp CTA per SM)
+#endif
+LZ_HD constexpr int fused_threads(int m) { return m >= 3 ? LZ_T34 : LZ_T2; }
+// CTAs per SM: two, except for the 128-word fold window and for CTAs of more than nine warps (16 warps x 128 registers fill the
+// register file on their own; their stage ring is deeper instead)
+LZ_HD constexpr int fused_ctas_per_sm(int m, int fw) { return (fw != 64 || fused_threads(m) > 288) ? 1 : 2; }
 
 // pipeline depth by fold window: FW = 64 -> 2 CTAs/SM (96 registers), 3 data stages + 4-deep parity ring;
 // FW = 128 -> 1 CTA/SM (the 128-word window needs ~170 registers), 6 data stages + 6-deep parity ring
 #ifndef LZ_NPST
 #define LZ_NPST 4
 #endif
-LZ_HD constexpr int fused_nst(int fw) { return fw == 64 ? 3 : 6; }
-LZ_HD constexpr int fused_npst(int fw) { return fw == 64 ? LZ_NPST : 6; }
+#ifndef LZ_NST_BIG
+#define LZ_NST_BIG 4
+#endif
+LZ_HD constexpr int fused_nst(int fw, int m) { return fw != 64 ? 6 : (fused_ctas_per_sm(m, fw) == 1 ? LZ_NST_BIG : 3); }
+LZ_HD constexpr int fused_npst(int fw, int m) { return fw == 64 ? LZ_NPST : 6; }
+LZ_HD constexpr int fused_smem_cap(int m, int fw) { return fused_ctas_per_sm(m, fw) == 1 ? 200 * 1024 : kSmemCap; }
 
-inline size_t fused_smem_bytes(uint32_t rows, uint32_t prows, int fw) {
+inline size_t fused_smem_bytes(uint32_t rows, uint32_t prows, int fw, int m) {
 	const size_t pstage = (static_cast<size_t>(prows) * kStepBytes + 1023) & ~size_t(1023);
-	const size_t nst = fused_nst(fw), npst = fused_npst(fw);
+	const size_t nst = fused_nst(fw, m), npst = fused_npst(fw, m);
 	return nst * rows * kStepBytes + npst * pstage + 520 + 8 * (2 * nst + 2 * npst);
 }
 
 // Largest stripe group G such that data + parity-CRC rows fit the consumer threads, the data rows fit
 // one TMA box (<= 256 rows, a multiple of 8 for the 1024-byte stage alignment) and the stages fit shared memory.
-inline uint32_t pick_group(uint32_t K, uint32_t PC, int max_smem_per_cta, int fw, uint32_t threads) {
+inline uint32_t pick_group(uint32_t K, uint32_t PC, int max_smem_per_cta, int fw, uint32_t threads, int m) {
 	uint32_t best = 0;
 	for (uint32_t g = 1; g <= 64; ++g) {
 		const uint32_t rows = g * K * 4, prows = g * PC * 4;
 		if (rows > kMaxRows || rows + prows > threads || prows > kMaxParityRows || g * K > 64) break;
 		if (rows % 8) continue;
-		if (fused_smem_bytes(rows, prows, fw) > static_cast<size_t>(max_smem_per_cta)) break;
+		if (fused_smem_bytes(rows, prows, fw, m) > static_cast<size_t>(max_smem_per_cta)) break;
 		best = g;
 	}
 	return best;
@@ -73,8 +83,9 @@ inline FusedPlan fused_plan(int M, bool generic, uint32_t K, uint32_t n_chunks, 
                             int striped_policy) {
 	FusedPlan pl;
 	const uint32_t PC = M == 0 ? 0 : (generic ? M : M - 1);
-	pl.threads = static_cast<uint32_t>(fused_threads(generic ? 4 : M));
-	pl.G = pick_group(K, PC, smem_cap, fw, pl.threads);
+	const int mm = generic ? 4 : M;  // the instantiation's M (thread count, stage depth)
+	pl.threads = static_cast<uint32_t>(fused_threads(mm));
+	pl.G = pick_group(K, PC, smem_cap, fw, pl.threads, mm);
 	if (pl.G == 0 || (chunk_stride % 16)) return pl;
 	const uint32_t G = pl.G;
 	pl.pb = (nb + K - 1) / K;
@@ -99,7 +110,7 @@ inline FusedPlan fused_plan(int M, bool generic, uint32_t K, uint32_t n_chunks, 
 	pl.total_units = static_cast<uint32_t>(total);
 	pl.rows = G * K * 4;
 	pl.prows = G * PC * 4;
-	pl.smem = fused_smem_bytes(pl.rows, pl.prows, fw);
+	pl.smem = fused_smem_bytes(pl.rows, pl.prows, fw, mm);
 	pl.ok = true;
 	return pl;
 }

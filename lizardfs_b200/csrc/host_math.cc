@@ -138,6 +138,25 @@ void crc_make_tables(uint32_t tab[4][256]) {
 // =============================================================== C ABI: scalar / matrix entry points
 extern "C" {
 
+// CRC of bytes [from, to) of a 64 KiB block, given mycrc32 of the whole block when every byte outside that range is zero.
+// lin(0^a || M || 0^c) = lin(M) * x^(8c); x has order dividing 2^32 - 1, so x^(-8c) = x^(8 * ((2^32 - 1) - c mod ...)) — the
+// exponent arithmetic is done in bits modulo 2^32 - 1.  Host scalar (a few hundred byte operations); used by
+// lzgpu::StripeBatcher to batch sub-block stripe writes through the whole-block kernel.
+uint32_t lzgpu_mycrc32_subrange(uint32_t crc_of_padded_block, uint32_t from, uint32_t to) {
+	if (to > LZGPU_BLOCK_SIZE || from >= to) return 0;
+	const uint32_t lin_pad = crc_of_padded_block ^ lz::crc_of_zeros(LZGPU_BLOCK_SIZE);
+	const uint64_t ord = 0xFFFFFFFFull;
+	const uint64_t neg_bits = (ord - (8ull * (LZGPU_BLOCK_SIZE - to)) % ord) % ord;  // -8c mod (2^32 - 1), in bits
+	// x^(neg_bits): square-and-multiply on bits (crc_xpow_bytes works on bytes)
+	uint32_t acc = 0x80000000u, sq = 0x40000000u;  // 1, x
+	for (uint64_t n = neg_bits; n; n >>= 1) {
+		if (n & 1) acc = lz::crc_mulmod(acc, sq);
+		sq = lz::crc_mulmod(sq, sq);
+	}
+	return lz::crc_mulmod(lin_pad, acc) ^ lz::crc_of_zeros(to - from);
+}
+
+
 unsigned char gf_mul(unsigned char a, unsigned char b) { return lz::gf_mul_host(a, b); }
 unsigned char gf_inv(unsigned char a) { return lz::gf_inv_host(a); }
 
@@ -310,7 +329,7 @@ int lzgpu_plan_encode(const lzgpu_goal *g, uint32_t n_chunks, uint32_t nb, size_
 	*out = lzgpu_encode_plan{};
 	if (g->m > 4) return LZGPU_OK;  // five or more parity parts: generic kernels (fused = 0)
 	const bool cauchy = lz::uses_cauchy(g->k, g->m);
-	const lzd::FusedPlan pl = lzd::fused_plan(cauchy ? 4 : g->m, cauchy, static_cast<uint32_t>(g->k), n_chunks, nb, chunk_stride, lzd::kSmemCap, 64, striped_policy);
+	const lzd::FusedPlan pl = lzd::fused_plan(cauchy ? 4 : g->m, cauchy, static_cast<uint32_t>(g->k), n_chunks, nb, chunk_stride, lzd::fused_smem_cap(cauchy ? 4 : g->m, 64), 64, striped_policy);
 	if (!pl.ok) return LZGPU_OK;
 	out->fused = 1;
 	out->mode = static_cast<int>(pl.mode);

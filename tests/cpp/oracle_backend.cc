@@ -29,8 +29,14 @@ int lzgpu_host_free(lzgpu_ctx *, void *h_ptr) {
 	return LZGPU_OK;
 }
 
+int lzgpu_test_fail_next_encode = 0;  // failure injection for the host-logic tests
+
 int lzgpu_encode_chunks(lzgpu_ctx *, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t chunk_len, const uint8_t *data, size_t chunk_stride,
                         uint8_t *parity, size_t parity_stride, uint32_t *crc, size_t crc_stride) {
+	if (lzgpu_test_fail_next_encode) {
+		lzgpu_test_fail_next_encode = 0;
+		return LZGPU_ERR_CUDA;
+	}
 	for (uint32_t c = 0; c < n_chunks; ++c)
 		if (lzo_encode_chunk(goal->kind, goal->k, goal->m, data + c * chunk_stride, chunk_len, parity + c * parity_stride, crc + c * crc_stride))
 			return LZGPU_ERR_ARG;

@@ -179,6 +179,102 @@ static void test_compute_parity_block(const char *text) {
 	std::printf("computeParityBlock %s: ok\n", text);
 }
 
+// Sub-block stripes (WriteCacheBlock::from / to, chunk_writer.cc:479-481): every block of the stripe carries bytes [from, to);
+// the sink must get exactly what addDataPacket(writeId, block, from, size, data) gets in the reference — the range's bytes, the
+// parity of the range (ChunkWriter::computeParityBlock on `size` bytes), mycrc32 of those `size` bytes, a prefix with
+// offset = from and size = to - from — batched with whole-block stripes in the same flush.
+static void test_sub_block_stripes(const char *text) {
+	lzgpu_goal goal;
+	EXPECT(lzgpu_goal_parse(text, &goal) == LZGPU_OK);
+	std::mt19937_64 rng(4242);
+	lzgpu::StripeBatcher batcher(lzgpu_default_ctx(), goal, 16);
+	struct Range { uint32_t from, to; };
+	const Range ranges[] = {{0, 65536}, {0, 4096}, {4096, 65536}, {100, 101}, {12345, 54321}, {65535, 65536}};
+	std::map<uint32_t, std::vector<std::vector<uint8_t>>> payload;  // stripe -> k payloads of to - from bytes
+	uint32_t stripe = 0;
+	for (const Range &r : ranges) {
+		payload[stripe].resize(goal.k);
+		for (int j = 0; j < goal.k; ++j) {
+			payload[stripe][j].resize(r.to - r.from);
+			for (auto &x : payload[stripe][j]) x = static_cast<uint8_t>(rng());
+			EXPECT(batcher.addBlockRange(77, stripe * goal.k + j, r.from, r.to, payload[stripe][j].data()));
+		}
+		++stripe;
+	}
+	// a block with another range for a buffered stripe is refused
+	bool threw = false;
+	try {
+		std::vector<uint8_t> x(10);
+		batcher.addBlockRange(77, 1 * goal.k, 0, 10, x.data());
+	} catch (const std::invalid_argument &) { threw = true; }
+	EXPECT(threw);
+	std::map<std::pair<uint32_t, int>, Seen> got;
+	const size_t n = batcher.flush(9, [&](const lzgpu::PartBlock &pb) {
+		got[{pb.block, pb.part}] = Seen{pb, std::vector<uint8_t>(pb.data, pb.data + pb.size), std::vector<uint8_t>(pb.prefix, pb.prefix + LZGPU_WRITE_PREFIX_SIZE)};
+	});
+	EXPECT(n == sizeof(ranges) / sizeof(ranges[0]));
+	EXPECT(got.size() == n * (goal.k + goal.m));
+	for (uint32_t s = 0; s < n; ++s) {
+		const Range &r = ranges[s];
+		const uint32_t size = r.to - r.from;
+		// the reference's computeParityBlock on `size` bytes
+		const uint8_t *in[LZO_MAX_PARTS] = {nullptr};
+		uint8_t erased[LZO_MAX_PARTS] = {0};
+		uint8_t *out[LZO_MAX_PARTS] = {nullptr};
+		std::vector<std::vector<uint8_t>> par(goal.m, std::vector<uint8_t>(size));
+		for (int j = 0; j < goal.k; ++j) in[j] = payload[s][j].data();
+		for (int i = 0; i < goal.m; ++i) { erased[goal.k + i] = 1; out[goal.k + i] = par[i].data(); }
+		EXPECT(lzo_rs_recover(goal.k, goal.m, in, erased, out, size) == 0);
+		for (int part = 0; part < goal.k + goal.m; ++part) {
+			auto it = got.find({s, part});
+			EXPECT(it != got.end());
+			if (it == got.end()) continue;
+			const std::vector<uint8_t> &want = part < goal.k ? payload[s][part] : par[part - goal.k];
+			const lzgpu::PartBlock &pb = it->second.pb;
+			EXPECT(pb.offset == r.from && pb.size == size);
+			EXPECT(it->second.data == want);
+			EXPECT(pb.crc == lzo_crc32(0, want.data(), size));
+			uint8_t prefix[LZO_WRITE_PREFIX_SIZE];
+			lzo_write_data_prefix(prefix, 77, pb.write_id, static_cast<uint16_t>(s), r.from, size, pb.crc);
+			EXPECT(std::memcmp(it->second.prefix.data(), prefix, sizeof(prefix)) == 0);
+		}
+	}
+	std::printf("sub-block stripes %s: ok\n", text);
+}
+
+#ifdef LZ_TEST_CPU_BACKEND
+extern "C" int lzgpu_test_fail_next_encode;  // oracle_backend.cc: makes the next lzgpu_encode_chunks call fail
+// a failed flush must leave the batcher consistent: the slots were re-ordered (complete stripes first) before the encode, so the
+// (chunk, stripe) -> slot map has to follow; the retry must then deliver every stripe with its own data
+static void test_failed_flush_keeps_the_index() {
+	lzgpu_goal goal;
+	EXPECT(lzgpu_goal_parse("ec(3,2)", &goal) == LZGPU_OK);
+	lzgpu::StripeBatcher batcher(lzgpu_default_ctx(), goal, 8);
+	std::vector<std::vector<uint8_t>> blk(9, std::vector<uint8_t>(B));
+	for (size_t i = 0; i < blk.size(); ++i) std::fill(blk[i].begin(), blk[i].end(), static_cast<uint8_t>(0x10 + i));
+	// stripe 0 of chunk 1 incomplete (2 of 3), then two complete stripes: flush() moves the complete ones to the front
+	EXPECT(batcher.addBlock(1, 0, blk[0].data()) && batcher.addBlock(1, 1, blk[1].data()));
+	for (int j = 0; j < 3; ++j) EXPECT(batcher.addBlock(2, j, blk[3 + j].data()));
+	for (int j = 0; j < 3; ++j) EXPECT(batcher.addBlock(3, j, blk[6 + j].data()));
+	lzgpu_test_fail_next_encode = 1;
+	bool threw = false;
+	try {
+		batcher.flush(0, [](const lzgpu::PartBlock &) {});
+	} catch (const std::runtime_error &) { threw = true; }
+	EXPECT(threw);
+	// the missing block of chunk 1 arrives: it must land in chunk 1's stripe, not in the slot that stripe used to occupy
+	EXPECT(batcher.addBlock(1, 2, blk[2].data()));
+	std::map<std::pair<uint64_t, int>, uint8_t> first_byte;
+	EXPECT(batcher.flush(0, [&](const lzgpu::PartBlock &pb) { if (pb.part < 3) first_byte[{pb.chunk_id, pb.part}] = pb.data[0]; }) == 3);
+	for (int j = 0; j < 3; ++j) {
+		EXPECT((first_byte[{1, j}] == 0x10 + j));
+		EXPECT((first_byte[{2, j}] == 0x13 + j));
+		EXPECT((first_byte[{3, j}] == 0x16 + j));
+	}
+	std::printf("failed flush keeps the index: ok\n");
+}
+#endif
+
 int main() {
 	if (!lzgpu_default_ctx()) {
 		std::fprintf(stderr, "no GPU context: %s\n", lzgpu_last_error());
@@ -191,6 +287,12 @@ int main() {
 	test_compute_parity_block("ec(8,2)");
 	test_compute_parity_block("xor3");
 	test_compute_parity_block("ec(3,2)");
+	test_sub_block_stripes("ec(8,2)");
+	test_sub_block_stripes("xor3");
+	test_sub_block_stripes("ec(5,3)");
+#ifdef LZ_TEST_CPU_BACKEND
+	test_failed_flush_keeps_the_index();
+#endif
 	if (failures) {
 		std::fprintf(stderr, "%d failure(s)\n", failures);
 		return 1;

@@ -7,6 +7,8 @@ timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r1_pytest.log 2>&1;
 ./tools/micro/warpmap > gpurun_out/r1_warpmap.txt 2>&1
 python tools/sweep.py --full-size-only --sections enc,rec --rec 'ec(8,2):1,4;ec(3,2):0,2;ec(5,3):0,1,4;xor3:1' --out gpurun_out/r1_sweep_base.md > /dev/null 2> gpurun_out/r1_sweep_base.err
 LZGPU_LIB=$PWD/lizardfs_b200/liblzgpu_t256.so python tools/sweep.py --full-size-only --sections enc --out gpurun_out/r1_sweep_t256.md > /dev/null 2> gpurun_out/r1_sweep_t256.err
+LZGPU_LIB=$PWD/lizardfs_b200/liblzgpu_big34.so python tools/sweep.py --full-size-only --sections enc --goals 'ec(5,3);ec(8,4)' --out gpurun_out/r1_sweep_big34.md > /dev/null 2> gpurun_out/r1_sweep_big34.err
+for V in t256 big34; do LZGPU_LIB=$PWD/lizardfs_b200/liblzgpu_$V.so timeout 300 python -m pytest tests/test_gpu_chunks.py -m gpu -x -q -k "golden or batch_vs_oracle or flat_units or every_bench_goal" > gpurun_out/r1_pytest_$V.log 2>&1; tail -2 gpurun_out/r1_pytest_$V.log; done
 NCU="ncu --set full --clock-control none --import-source on"
 $NCU -k regex:fused_stream -s 2 -c 1 -o gpurun_out/r1_prof_ec84 python tools/sweep.py --full-size-only --sections enc --goals 'ec(8,4)' --steps 1 --warmup 2 --out gpurun_out/r1_tmp.md > gpurun_out/r1_ncu_ec84.log 2>&1
 $NCU -k regex:fused_stream -s 2 -c 1 -o gpurun_out/r1_prof_ec53 python tools/sweep.py --full-size-only --sections enc --goals 'ec(5,3)' --steps 1 --warmup 2 --out gpurun_out/r1_tmp.md > gpurun_out/r1_ncu_ec53.log 2>&1
