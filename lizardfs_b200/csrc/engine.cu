@@ -1046,19 +1046,40 @@ static int convert_enqueue(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_go
 				if (i < kd) { dp[i] = d_out[i]; data_wanted = true; }
 				else parity_wanted = true;
 			}
-			// data part j, block s = chunk block s*k + j (SliceRecoveryPlanner::BlockConverter, :41-57)
-			if (data_wanted && (rc = lzgpu_split_chunks_dev(ctx, dst, n_chunks, nb, image, image_stride, dp, out_stride, st))) { ticket_drop(ctx, tk); return rc; }
-			// parity parts = XorReadPlan::RecoverParity / ECReadPlan::RecoverParity over the chunk data (xor_read_plan.h:39-62, ec_read_plan.h:38-76)
-			if (parity_wanted) {
-				const size_t par_stride = static_cast<size_t>(dst->m) * pbd * B, crc_stride = (nb + static_cast<size_t>(dst->m) * pbd + 3) & ~size_t(3);
-				if ((rc = t_par.alloc(n_chunks * par_stride)) || (rc = t_crc.alloc(n_chunks * crc_stride * 4))) { ticket_drop(ctx, tk); return rc; }
-				if ((rc = encode_enqueue(ctx, dst, n_chunks, nb * B, image, image_stride, t_par.p, par_stride, t_crc.p, crc_stride, st))) { ticket_drop(ctx, tk); return rc; }
-				d_encode_crc = t_crc.p;
-				encode_crc_stride = crc_stride;
-				for (int r = 0; r < dst->m; ++r)
-					if (want[kd + r])
-						CUDA_TRY(cudaMemcpy2DAsync(d_out[kd + r], out_stride, static_cast<uint8_t *>(t_par.p) + static_cast<size_t>(r) * pbd * B, par_stride,
-						                           static_cast<size_t>(pbd) * B, n_chunks, cudaMemcpyDeviceToDevice, st));
+			// One pass over the image when a parity part is wanted: data part j, block s = chunk block s*k + j
+			// (SliceRecoveryPlanner::BlockConverter, :41-57) and XorReadPlan::RecoverParity / ECReadPlan::RecoverParity
+			// (xor_read_plan.h:39-62, ec_read_plan.h:38-76), every destination part stored straight into its buffer, block CRCs of
+			// the whole destination slice as a by-product.  Algorithmic bytes: read the image once, write each wanted part once.
+			bool fused_done = false;
+			if (parity_wanted && image_stride >= static_cast<size_t>(nb) * B) {
+				const size_t crc_stride = (nb + static_cast<size_t>(dst->m) * pbd + 3) & ~size_t(3);
+				if ((rc = t_crc.alloc(n_chunks * crc_stride * 4))) { ticket_drop(ctx, tk); return rc; }
+				void *outs[LZGPU_MAX_PARTS] = {nullptr};
+				for (int i = 0; i < nd; ++i) outs[i] = want[i] ? d_out[i] : nullptr;
+				rc = lz_fused_encode_split(ctx, dst, n_chunks, nb, image, image_stride, outs, out_stride, t_crc.p, crc_stride, st);
+				if (rc == LZGPU_OK) {
+					fused_done = true;
+					d_encode_crc = t_crc.p;
+					encode_crc_stride = crc_stride;
+					ctx->stats.chunks_encoded += n_chunks;
+				} else if (rc != LZGPU_NOT_HANDLED) {
+					ticket_drop(ctx, tk);
+					return rc;
+				}
+			}
+			if (!fused_done) {
+				if (data_wanted && (rc = lzgpu_split_chunks_dev(ctx, dst, n_chunks, nb, image, image_stride, dp, out_stride, st))) { ticket_drop(ctx, tk); return rc; }
+				if (parity_wanted) {
+					const size_t par_stride = static_cast<size_t>(dst->m) * pbd * B, crc_stride = (nb + static_cast<size_t>(dst->m) * pbd + 3) & ~size_t(3);
+					if ((rc = t_par.alloc(n_chunks * par_stride)) || (!t_crc.p && (rc = t_crc.alloc(n_chunks * crc_stride * 4)))) { ticket_drop(ctx, tk); return rc; }
+					if ((rc = encode_enqueue(ctx, dst, n_chunks, nb * B, image, image_stride, t_par.p, par_stride, t_crc.p, crc_stride, st))) { ticket_drop(ctx, tk); return rc; }
+					d_encode_crc = t_crc.p;
+					encode_crc_stride = crc_stride;
+					for (int r = 0; r < dst->m; ++r)
+						if (want[kd + r])
+							CUDA_TRY(cudaMemcpy2DAsync(d_out[kd + r], out_stride, static_cast<uint8_t *>(t_par.p) + static_cast<size_t>(r) * pbd * B, par_stride,
+							                           static_cast<size_t>(pbd) * B, n_chunks, cudaMemcpyDeviceToDevice, st));
+				}
 			}
 		}
 	}

@@ -136,6 +136,8 @@ int lz_fused_init(lzgpu_ctx *ctx);
 void lz_fused_destroy(lzgpu_ctx *ctx);
 int lz_fused_encode(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb, const void *d_data, size_t chunk_stride,
                     void *d_parity, size_t parity_stride, void *d_crc, size_t crc_stride, cudaStream_t st);
+int lz_fused_encode_split(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb, const void *d_data, size_t chunk_stride,
+                          void *const *d_out, size_t out_stride, void *d_crc, size_t crc_stride, cudaStream_t st);
 // Fused degraded read (verify + rebuild erased data parts + chunk-order image).  When any part is verified (*verifying),
 // first-bad information is written to d_first_bad[0] encoded as (chunk*64 + part)*1024 + block (~0 = all good); the caller
 // owns that word (a StatusSlot) and must pass it whenever d_part_crc is given.

@@ -50,10 +50,10 @@ static uint32_t crc_xpow_bits_signed(long long n) {
 	return acc;
 }
 
-template <int M, bool GENERIC, int KT = 0, int GT = 0, int FW = 64, bool STRIPED = false>
+template <int M, bool GENERIC, int KT = 0, int GT = 0, int FW = 64, bool STRIPED = false, bool SPLIT = false>
 static int set_smem_attr(int bytes) {
 	if (FW == 64) bytes = std::max(bytes, fused_smem_cap(M, FW));  // one-CTA-per-SM shapes use a deeper ring
-	CUDA_TRY(cudaFuncSetAttribute(fused_stream_kernel<M, GENERIC, KT, GT, FW, STRIPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+	CUDA_TRY(cudaFuncSetAttribute(fused_stream_kernel<M, GENERIC, KT, GT, FW, STRIPED, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
 	return LZGPU_OK;
 }
 
@@ -117,6 +117,11 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if ((rc = set_smem_attr<3, false>(smem))) return rc;
 	if ((rc = set_smem_attr<4, false>(smem))) return rc;
 	if ((rc = set_smem_attr<4, true>(smem))) return rc;
+	if ((rc = set_smem_attr<1, false, 0, 0, 64, false, true>(smem))) return rc;
+	if ((rc = set_smem_attr<2, false, 0, 0, 64, false, true>(smem))) return rc;
+	if ((rc = set_smem_attr<3, false, 0, 0, 64, false, true>(smem))) return rc;
+	if ((rc = set_smem_attr<4, false, 0, 0, 64, false, true>(smem))) return rc;
+	if ((rc = set_smem_attr<4, true, 0, 0, 64, false, true>(smem))) return rc;
 	if ((rc = set_smem_attr<1, false, 0, 0, 64, true>(smem))) return rc;
 	if ((rc = set_smem_attr<2, false, 0, 0, 64, true>(smem))) return rc;
 	if ((rc = set_smem_attr<3, false, 0, 0, 64, true>(smem))) return rc;
@@ -183,11 +188,11 @@ static int make_tensor_map(FusedState *fs, CUtensorMap *map, const void *base, u
 	return LZGPU_OK;
 }
 
-template <int M, bool GENERIC, int KT = 0, int GT = 0, int FW = 64, bool STRIPED = false>
+template <int M, bool GENERIC, int KT = 0, int GT = 0, int FW = 64, bool STRIPED = false, bool SPLIT = false>
 static int launch(lzgpu_ctx *ctx, const CUtensorMap &map, const FusedParams &p, size_t smem, cudaStream_t st) {
 	const int per_sm = fused_ctas_per_sm(M, FW);
 	const int grid = static_cast<int>(std::min<uint64_t>(p.total_units, static_cast<uint64_t>(ctx->sm_count) * per_sm));
-	fused_stream_kernel<M, GENERIC, KT, GT, FW, STRIPED><<<grid, fused_threads(M), smem, st>>>(map, p);
+	fused_stream_kernel<M, GENERIC, KT, GT, FW, STRIPED, SPLIT><<<grid, fused_threads(M), smem, st>>>(map, p);
 	CUDA_TRY(cudaGetLastError());
 	ctx->stats.kernel_launches++;
 	return LZGPU_OK;
@@ -209,15 +214,17 @@ static int choose_fold(const FusedState *fs, int M, bool generic) {
 	return 64;
 }
 
+// split_out != nullptr: the conversion form — K + M destination part buffers (nullptr = part not wanted), data parts stored by the
+// BlockConverter pick and parity parts stored separately, chunk c at + c*split_stride; d_parity is then unused
 static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_rows, uint32_t K, uint32_t n_chunks, uint32_t nb,
                      const void *d_data, size_t chunk_stride, void *d_parity, size_t parity_stride, void *d_crc, size_t crc_stride,
-                     cudaStream_t st) {
+                     cudaStream_t st, void *const *split_out = nullptr, size_t split_stride = 0) {
 	FusedState *fs = ctx->fused;
 	const uint32_t PC = M == 0 ? 0 : (generic ? M : M - 1);
 	const int fw = choose_fold(fs, M, generic);
 	const int smem_cap = std::min(fs->max_smem, fw == 64 ? fused_smem_cap(generic ? 4 : M, fw) : kSmemCap128);
 	// unit geometry: per-chunk, flat or striped units, stripes per unit (fused_plan.h; unit-tested without a GPU)
-	const FusedPlan pl = fused_plan(M, generic, K, n_chunks, nb, chunk_stride, smem_cap, fw, fs->striped);
+	const FusedPlan pl = fused_plan(M, generic, K, n_chunks, nb, chunk_stride, smem_cap, fw, split_out ? 0 : fs->striped);
 	if (!pl.ok || (reinterpret_cast<uintptr_t>(d_data) % 16)) return LZGPU_NOT_HANDLED;
 	const uint32_t G = pl.G;
 	const bool flat = pl.mode == 1u, striped = pl.mode == 2u;
@@ -253,6 +260,20 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	if (rc) return rc;
 	const size_t smem = pl.smem;
 	(void)PC;
+	if (split_out) {
+		if (striped || (split_stride % 16)) return LZGPU_NOT_HANDLED;
+		for (uint32_t j = 0; j < K; ++j) p.data_out[j] = static_cast<uint8_t *>(split_out[j]);
+		for (int r = 0; r < M; ++r) p.par_out[r] = static_cast<uint8_t *>(split_out[K + r]);
+		p.part_out_stride = split_stride;
+		if (generic) return launch<4, true, 0, 0, 64, false, true>(ctx, map, p, smem, st);
+		switch (M) {
+			case 1: return launch<1, false, 0, 0, 64, false, true>(ctx, map, p, smem, st);
+			case 2: return launch<2, false, 0, 0, 64, false, true>(ctx, map, p, smem, st);
+			case 3: return launch<3, false, 0, 0, 64, false, true>(ctx, map, p, smem, st);
+			case 4: return launch<4, false, 0, 0, 64, false, true>(ctx, map, p, smem, st);
+		}
+		return LZGPU_NOT_HANDLED;
+	}
 	if (striped) {
 		if (generic) return launch<4, true, 0, 0, 64, true>(ctx, map, p, smem, st);
 #define LZ_FOLDED_STRIPED(MM, KK, GG) \
@@ -332,6 +353,22 @@ int lz_fused_encode(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, u
 	}
 	// xorN is ec(N,1): parity row 0 of the Vandermonde generator is all ones (chunk_writer.cc:373-381)
 	return fused_run(ctx, M, false, nullptr, K, n_chunks, nb, d_data, chunk_stride, d_parity, parity_stride, d_crc, crc_stride, st);
+}
+
+// conversion form of the encode (SliceRecoveryPlanner: BlockConverter for the data parts + RecoverParity for the parity parts in
+// ONE pass over the chunk image): d_out[i], i < k+m, nullptr = part not wanted; CRC array as in lz_fused_encode
+int lz_fused_encode_split(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb, const void *d_data, size_t chunk_stride,
+                          void *const *d_out, size_t out_stride, void *d_crc, size_t crc_stride, cudaStream_t st) {
+	FusedState *fs = ctx->fused;
+	if (!fs || fs->disabled) return LZGPU_NOT_HANDLED;
+	const int K = goal->k, M = goal->m;
+	if (M > 4) return LZGPU_NOT_HANDLED;
+	if (lz::uses_cauchy(K, M)) {
+		uint8_t gen[LZGPU_MAX_PARTS * LZGPU_MAX_DATA];
+		lz::rs_generator(K, M, gen);
+		return fused_run(ctx, 4, true, gen + K * K, K, n_chunks, nb, d_data, chunk_stride, nullptr, 0, d_crc, crc_stride, st, d_out, out_stride);
+	}
+	return fused_run(ctx, M, false, nullptr, K, n_chunks, nb, d_data, chunk_stride, nullptr, 0, d_crc, crc_stride, st, d_out, out_stride);
 }
 
 int lz_fused_crc(lzgpu_ctx *ctx, const void *base, unsigned long long n_blocks, unsigned long long blocks_per_chunk,

@@ -75,6 +75,12 @@ struct FusedParams {
 	uint32_t qmult[4];               // x^(32*(4096*(3-q) - deg)) mod P : stream -> block merge incl. the flush offset (deg of the fold in use)
 	uint32_t zconst;                 // mycrc32(0, 64 KiB of zeros)
 	uint32_t probe;                  // diagnostics only (LZGPU_PROBE): bit1 skip GF role, bit2 skip CRC folds (results then invalid)
+	// SPLIT instantiations only (slice conversion, SliceRecoveryPlanner::BlockConverter fused into the encode pass): the data
+	// blocks are also stored part-major (data part j of chunk c at data_out[j] + c*part_out_stride, nullptr = not wanted), and
+	// the parity parts go to separate buffers par_out[r] + c*part_out_stride (nullptr = not wanted) instead of p.parity
+	uint8_t *data_out[32];
+	uint8_t *par_out[4];
+	unsigned long long part_out_stride;
 	CoefPlanes coef[4 * 32];         // only read by the GENERIC instantiation: [M][K]
 };
 
@@ -233,7 +239,7 @@ __device__ __forceinline__ uint32_t fold_finish(uint32_t (&win)[FW], const uint3
 // Register budget: __launch_bounds__(288, 2) makes ptxas target 96 registers (2 CTAs/SM), (288, 1) -> 168.
 // (An explicit __maxnreg__(96) instead of the launch bounds produced a 5 % slower kernel on the same box: ptxas
 // schedules differently when it does not know the block size.)
-template <int M, bool GENERIC, int KT, int GT, int FW, bool STRIPED = false>
+template <int M, bool GENERIC, int KT, int GT, int FW, bool STRIPED = false, bool SPLIT = false>
 __global__ void __launch_bounds__(fused_threads(M), fused_ctas_per_sm(M, FW))
 fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
 	constexpr int kNST = fused_nst(FW, M), kNPST = fused_npst(FW, M);
@@ -370,11 +376,20 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 						for (int r = 0; r < M; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0;
 						// row (g*K + j)*4 + q: its swizzle (row & 7) = (4*((g*K + j) & 1) + q) alternates with j
 						const uint32_t rbase = g * K * 4 + q;
+						const uint32_t sg = stripe0 + g;
+						uint32_t pc = 0, stripe = 0;
+						if (sg < stripes_total) locate(sg, c, pc, stripe);
+						const unsigned long long in_part = (static_cast<unsigned long long>(stripe) << 16) + (q << 14) + step * kStepBytes + (col << 4);
 						const uint32_t a_even = (stage + rbase * kStepBytes) ^ ((col ^ (rbase & 7)) << 4);
 						const uint32_t a_odd = (stage + rbase * kStepBytes) ^ ((col ^ ((rbase & 7) ^ 4)) << 4);
 #pragma unroll
 						for (int j = static_cast<int>(K) - 1; j >= 0; --j) {
 							const uint4 v = lds128(((j & 1) ? a_odd : a_even) + 4u * j * kStepBytes);
+							if (SPLIT) {
+								// BlockConverter: chunk block stripe*K + j is block `stripe` of data part j (blocks the chunk does not have are zeros)
+								uint8_t *dp = p.data_out[j];
+								if (dp && sg < stripes_total) st_stream(reinterpret_cast<uint4 *>(dp + pc * p.part_out_stride + in_part), v);
+							}
 							if (GENERIC) {
 #pragma unroll
 								for (int r = 0; r < M; ++r) {
@@ -398,16 +413,20 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 								}
 							}
 						}
-						const uint32_t sg = stripe0 + g;
 						if (sg < stripes_total && !LZ_PROBE(8)) {
-							uint32_t pc, stripe;
-							locate(sg, c, pc, stripe);
-							uint8_t *dst = p.parity + pc * p.parity_stride + (static_cast<unsigned long long>(stripe) << 16) +
-							               (q << 14) + step * kStepBytes + (col << 4);
+							if (SPLIT) {
 #pragma unroll
-							for (int r = 0; r < M; ++r)
-								st_stream(reinterpret_cast<uint4 *>(dst + static_cast<unsigned long long>(r) * p.pb * 65536ull),
-								          make_uint4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
+								for (int r = 0; r < M; ++r)
+									if (p.par_out[r])
+										st_stream(reinterpret_cast<uint4 *>(p.par_out[r] + pc * p.part_out_stride + in_part),
+										          make_uint4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
+							} else {
+								uint8_t *dst = p.parity + pc * p.parity_stride + in_part;
+#pragma unroll
+								for (int r = 0; r < M; ++r)
+									st_stream(reinterpret_cast<uint4 *>(dst + static_cast<unsigned long long>(r) * p.pb * 65536ull),
+									          make_uint4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
+							}
 						}
 #pragma unroll
 						for (int r = P0; r < M; ++r) {
