@@ -81,10 +81,12 @@ uint32_t lzgpu_part_length(const lzgpu_goal *g, int part, uint32_t chunk_length)
 /* Diagnostics: how lzgpu_encode_chunks_dev would lay a batch out on the GPU (pure host logic, works without a device).
  * mode 0: a unit is `stripes_per_unit` stripes of one chunk; 1 ("flat"): contiguous whole-stripe chunks are one run of stripes;
  * 2 ("striped"): a run of global stripes for any chunk length / stride, one TMA box per stripe.  striped_policy: -1 automatic
- * (what the library does unless LZGPU_STRIPED is set), 0 never, 1 always.  fused = 0: the generic kernels take the shape. */
+ * (what the library does unless LZGPU_STRIPED is set), 0 never, 1 always.  fused = 0: the generic kernels take the shape.
+ * The geometry of a multi-pass encode (passes > 1) is that of its first pass. */
 typedef struct lzgpu_encode_plan {
 	int fused, mode;
 	uint32_t stripes_per_unit, threads_per_cta, units, stage_rows, smem_bytes;
+	uint32_t passes; /* 1; ceil(m / 4) for a goal with more than four parity parts (Cauchy rows, four per pass over the data) */
 } lzgpu_encode_plan;
 int lzgpu_plan_encode(const lzgpu_goal *g, uint32_t n_chunks, uint32_t nb, size_t chunk_stride, int striped_policy, lzgpu_encode_plan *out);
 

@@ -31,7 +31,7 @@ class LzStats(C.Structure):
 
 class LzEncodePlan(C.Structure):
     _fields_ = [("fused", C.c_int), ("mode", C.c_int), ("stripes_per_unit", C.c_uint32), ("threads_per_cta", C.c_uint32),
-                ("units", C.c_uint32), ("stage_rows", C.c_uint32), ("smem_bytes", C.c_uint32)]
+                ("units", C.c_uint32), ("stage_rows", C.c_uint32), ("smem_bytes", C.c_uint32), ("passes", C.c_uint32)]
 
 
 class LzBlockWrite(C.Structure):

@@ -117,6 +117,9 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if ((rc = set_smem_attr<3, false>(smem))) return rc;
 	if ((rc = set_smem_attr<4, false>(smem))) return rc;
 	if ((rc = set_smem_attr<4, true>(smem))) return rc;
+	if ((rc = set_smem_attr<1, true>(smem))) return rc;
+	if ((rc = set_smem_attr<2, true>(smem))) return rc;
+	if ((rc = set_smem_attr<3, true>(smem))) return rc;
 	if ((rc = set_smem_attr<1, false, 0, 0, 64, false, true>(smem))) return rc;
 	if ((rc = set_smem_attr<2, false, 0, 0, 64, false, true>(smem))) return rc;
 	if ((rc = set_smem_attr<3, false, 0, 0, 64, false, true>(smem))) return rc;
@@ -218,13 +221,14 @@ static int choose_fold(const FusedState *fs, int M, bool generic) {
 // BlockConverter pick and parity parts stored separately, chunk c at + c*split_stride; d_parity is then unused
 static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_rows, uint32_t K, uint32_t n_chunks, uint32_t nb,
                      const void *d_data, size_t chunk_stride, void *d_parity, size_t parity_stride, void *d_crc, size_t crc_stride,
-                     cudaStream_t st, void *const *split_out = nullptr, size_t split_stride = 0) {
+                     cudaStream_t st, void *const *split_out = nullptr, size_t split_stride = 0, uint32_t crc_row_base = 0, bool skip_data_crc = false,
+                     int striped_policy = -2 /* -2: the context's setting */) {
 	FusedState *fs = ctx->fused;
 	const uint32_t PC = M == 0 ? 0 : (generic ? M : M - 1);
 	const int fw = choose_fold(fs, M, generic);
-	const int smem_cap = std::min(fs->max_smem, fw == 64 ? fused_smem_cap(generic ? 4 : M, fw) : kSmemCap128);
+	const int smem_cap = std::min(fs->max_smem, fw == 64 ? fused_smem_cap(M, fw) : kSmemCap128);
 	// unit geometry: per-chunk, flat or striped units, stripes per unit (fused_plan.h; unit-tested without a GPU)
-	const FusedPlan pl = fused_plan(M, generic, K, n_chunks, nb, chunk_stride, smem_cap, fw, split_out ? 0 : fs->striped);
+	const FusedPlan pl = fused_plan(M, generic, K, n_chunks, nb, chunk_stride, smem_cap, fw, split_out ? 0 : (striped_policy == -2 ? fs->striped : striped_policy));
 	if (!pl.ok || (reinterpret_cast<uintptr_t>(d_data) % 16)) return LZGPU_NOT_HANDLED;
 	const uint32_t G = pl.G;
 	const bool flat = pl.mode == 1u, striped = pl.mode == 2u;
@@ -247,6 +251,8 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	p.zconst = lz::crc_of_zeros(LZGPU_BLOCK_SIZE);
 	p.probe = fs->probe;
 	p.evict_first = static_cast<uint32_t>(fs->evict_first);
+	p.crc_row_base = crc_row_base;
+	p.skip_data_crc = skip_data_crc ? 1u : 0u;
 	if (generic) {
 		for (int r = 0; r < M; ++r)
 			for (uint32_t j = 0; j < K; ++j) {
@@ -265,7 +271,10 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 		for (uint32_t j = 0; j < K; ++j) p.data_out[j] = static_cast<uint8_t *>(split_out[j]);
 		for (int r = 0; r < M; ++r) p.par_out[r] = static_cast<uint8_t *>(split_out[K + r]);
 		p.part_out_stride = split_stride;
-		if (generic) return launch<4, true, 0, 0, 64, false, true>(ctx, map, p, smem, st);
+		if (generic) {
+			if (M != 4) return LZGPU_NOT_HANDLED;
+			return launch<4, true, 0, 0, 64, false, true>(ctx, map, p, smem, st);
+		}
 		switch (M) {
 			case 1: return launch<1, false, 0, 0, 64, false, true>(ctx, map, p, smem, st);
 			case 2: return launch<2, false, 0, 0, 64, false, true>(ctx, map, p, smem, st);
@@ -275,7 +284,10 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 		return LZGPU_NOT_HANDLED;
 	}
 	if (striped) {
-		if (generic) return launch<4, true, 0, 0, 64, true>(ctx, map, p, smem, st);
+		if (generic) {
+			if (M != 4) return LZGPU_NOT_HANDLED;
+			return launch<4, true, 0, 0, 64, true>(ctx, map, p, smem, st);
+		}
 #define LZ_FOLDED_STRIPED(MM, KK, GG) \
 	if (M == MM && K == KK && G == GG) return launch<MM, false, KK, GG, 64, true>(ctx, map, p, smem, st);
 		LZ_FOLDED_STRIPED(2, 8, 8)
@@ -293,7 +305,15 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 		}
 		return LZGPU_NOT_HANDLED;
 	}
-	if (generic) return launch<4, true>(ctx, map, p, smem, st);
+	if (generic) {
+		switch (M) {
+			case 1: return launch<1, true>(ctx, map, p, smem, st);
+			case 2: return launch<2, true>(ctx, map, p, smem, st);
+			case 3: return launch<3, true>(ctx, map, p, smem, st);
+			case 4: return launch<4, true>(ctx, map, p, smem, st);
+		}
+		return LZGPU_NOT_HANDLED;
+	}
 #ifdef LZ_ENABLE_FOLD128
 	if (fw == 128) {
 		if (M == 2 && K == 8 && G == 8) return launch<2, false, 8, 8, 128>(ctx, map, p, smem, st);
@@ -344,13 +364,28 @@ int lz_fused_encode(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, u
 	FusedState *fs = ctx->fused;
 	if (!fs || fs->disabled) return LZGPU_NOT_HANDLED;
 	const int K = goal->k, M = goal->m;
-	if (M > 4) return LZGPU_NOT_HANDLED;
 	if (lz::uses_cauchy(K, M)) {
-		// Cauchy generator (m == 4 and k > 20): arbitrary coefficients, bit-plane multiply inside the fused kernel
+		// Cauchy generator (m >= 5, or m == 4 and k > 20; reed_solomon.h:168-172): arbitrary coefficients, bit-plane multiply inside
+		// the fused kernel, in passes of up to four parity rows over the same data (the TMA stream, the fused parity CRCs and the
+		// part-major stores stay; the first pass also checksums the data blocks).  A shape one pass cannot take leaves the whole
+		// encode to the generic kernels — decided before anything is launched (the plan is pure host logic).
 		uint8_t gen[LZGPU_MAX_PARTS * LZGPU_MAX_DATA];
 		lz::rs_generator(K, M, gen);
-		return fused_run(ctx, 4, true, gen + K * K, K, n_chunks, nb, d_data, chunk_stride, d_parity, parity_stride, d_crc, crc_stride, st);
+		if (M == 4) return fused_run(ctx, 4, true, gen + K * K, K, n_chunks, nb, d_data, chunk_stride, d_parity, parity_stride, d_crc, crc_stride, st);
+		const uint32_t pb = (nb + K - 1) / K;
+		for (int rows : {4, M % 4})
+			if (rows && !fused_plan(rows, true, K, n_chunks, nb, chunk_stride, std::min(fs->max_smem, fused_smem_cap(rows, 64)), 64, 0).ok) return LZGPU_NOT_HANDLED;
+		if (reinterpret_cast<uintptr_t>(d_data) % 16) return LZGPU_NOT_HANDLED;
+		for (int r0 = 0; r0 < M; r0 += 4) {
+			// per-chunk / flat units only: the passes share one geometry rule (striped policy 0)
+			int rc = fused_run(ctx, std::min(4, M - r0), true, gen + (K + r0) * K, K, n_chunks, nb, d_data, chunk_stride,
+			                   static_cast<uint8_t *>(d_parity) + static_cast<size_t>(r0) * pb * LZGPU_BLOCK_SIZE, parity_stride, d_crc, crc_stride, st, nullptr, 0,
+			                   static_cast<uint32_t>(r0), r0 > 0, 0);
+			if (rc != LZGPU_OK) return rc == LZGPU_NOT_HANDLED ? LZGPU_ERR_CUDA : rc;  // (cannot happen: the plans were checked above)
+		}
+		return LZGPU_OK;
 	}
+	if (M > 4) return LZGPU_NOT_HANDLED;
 	// xorN is ec(N,1): parity row 0 of the Vandermonde generator is all ones (chunk_writer.cc:373-381)
 	return fused_run(ctx, M, false, nullptr, K, n_chunks, nb, d_data, chunk_stride, d_parity, parity_stride, d_crc, crc_stride, st);
 }

@@ -78,6 +78,8 @@ struct FusedParams {
 	// SPLIT instantiations only (slice conversion, SliceRecoveryPlanner::BlockConverter fused into the encode pass): the data
 	// blocks are also stored part-major (data part j of chunk c at data_out[j] + c*part_out_stride, nullptr = not wanted), and
 	// the parity parts go to separate buffers par_out[r] + c*part_out_stride (nullptr = not wanted) instead of p.parity
+	uint32_t skip_data_crc;          // later passes of a many-parity encode: the data-block CRCs were produced by the first pass
+	uint32_t crc_row_base;           // parity row r of this launch is parity part crc_row_base + r in the CRC array
 	uint8_t *data_out[32];
 	uint8_t *par_out[4];
 	unsigned long long part_out_stride;
@@ -442,7 +444,7 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 
 				// ---------------- CRC role ----------------
 				if (PC > 0 && warp_has_prow && !LZ_PROBE(2)) mbar_wait(a_pfull + 8 * pst, pph);
-				if (has_stream && !LZ_PROBE(4)) {
+				if (has_stream && !(GENERIC && is_data_row && p.skip_data_crc) && !LZ_PROBE(4)) {
 					const uint32_t rowp = row_addr0 + (is_data_row ? st : pst) * row_stride;
 					fold_step<FW>(win, sub * 32, rowp);
 				}
@@ -484,7 +486,7 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 			uint32_t bc, bs;
 			locate(sg, c, bc, bs);
 			const uint32_t b = bs * K + bl % K;           // block index in its chunk
-			if (sg < stripes_total && b < p.nb) p.crc[bc * p.crc_stride + b] = lin ^ p.zconst;
+			if (sg < stripes_total && b < p.nb && !(GENERIC && p.skip_data_crc)) p.crc[bc * p.crc_stride + b] = lin ^ p.zconst;
 		}
 		if (is_parity_row && (prow & 3) == 0) {
 			constexpr uint32_t PCD = PC ? PC : 1;
@@ -492,7 +494,7 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 			const uint32_t sg = stripe0 + g;
 			uint32_t pc, stripe;
 			locate(sg, c, pc, stripe);
-			if (sg < stripes_total) p.crc[pc * p.crc_stride + p.nb + r * p.pb + stripe] = lin ^ p.zconst;
+			if (sg < stripes_total) p.crc[pc * p.crc_stride + p.nb + (p.crc_row_base + r) * p.pb + stripe] = lin ^ p.zconst;
 		}
 		if (M > 0 && !GENERIC) {
 			// CRC of parity row 0 (plain XOR of the stripe): xor of the data blocks' linear CRCs

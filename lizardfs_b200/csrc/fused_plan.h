@@ -83,7 +83,7 @@ inline FusedPlan fused_plan(int M, bool generic, uint32_t K, uint32_t n_chunks, 
                             int striped_policy) {
 	FusedPlan pl;
 	const uint32_t PC = M == 0 ? 0 : (generic ? M : M - 1);
-	const int mm = generic ? 4 : M;  // the instantiation's M (thread count, stage depth)
+	const int mm = M;  // the instantiation's M (thread count, stage depth); a Cauchy generator is encoded in passes of <= 4 rows
 	pl.threads = static_cast<uint32_t>(fused_threads(mm));
 	pl.G = pick_group(K, PC, smem_cap, fw, pl.threads, mm);
 	if (pl.G == 0 || (chunk_stride % 16)) return pl;

@@ -1,6 +1,8 @@
 // host_math.cc — see host_math.h.  Written from the mathematical definitions; results are
 // checked against the oracle and the compiled reference in tests/test_host_math.py.
 #include "host_math.h"
+#include <algorithm>
+
 #include "fused_plan.h"
 
 #include <cctype>
@@ -327,9 +329,16 @@ uint32_t lzgpu_part_length(const lzgpu_goal *g, int part, uint32_t chunk_length)
 int lzgpu_plan_encode(const lzgpu_goal *g, uint32_t n_chunks, uint32_t nb, size_t chunk_stride, int striped_policy, lzgpu_encode_plan *out) {
 	if (!out || !lzgpu_goal_valid(g) || nb == 0 || nb > LZGPU_BLOCKS_IN_CHUNK) return LZGPU_ERR_ARG;
 	*out = lzgpu_encode_plan{};
-	if (g->m > 4) return LZGPU_OK;  // five or more parity parts: generic kernels (fused = 0)
 	const bool cauchy = lz::uses_cauchy(g->k, g->m);
-	const lzd::FusedPlan pl = lzd::fused_plan(cauchy ? 4 : g->m, cauchy, static_cast<uint32_t>(g->k), n_chunks, nb, chunk_stride, lzd::fused_smem_cap(cauchy ? 4 : g->m, 64), 64, striped_policy);
+	// a Cauchy generator with more than four parity parts is encoded in passes of up to four rows (fused.cu lz_fused_encode):
+	// every pass must fit, per-chunk / flat units only; the geometry reported is the first pass's
+	const int first = cauchy ? std::min(g->m, 4) : g->m;
+	if (g->m > 4) {
+		striped_policy = 0;
+		const int last = g->m % 4;
+		if (last && !lzd::fused_plan(last, true, static_cast<uint32_t>(g->k), n_chunks, nb, chunk_stride, lzd::fused_smem_cap(last, 64), 64, 0).ok) return LZGPU_OK;
+	}
+	const lzd::FusedPlan pl = lzd::fused_plan(first, cauchy, static_cast<uint32_t>(g->k), n_chunks, nb, chunk_stride, lzd::fused_smem_cap(first, 64), 64, striped_policy);
 	if (!pl.ok) return LZGPU_OK;
 	out->fused = 1;
 	out->mode = static_cast<int>(pl.mode);
@@ -338,6 +347,7 @@ int lzgpu_plan_encode(const lzgpu_goal *g, uint32_t n_chunks, uint32_t nb, size_
 	out->units = pl.total_units;
 	out->stage_rows = pl.rows;
 	out->smem_bytes = static_cast<uint32_t>(pl.smem);
+	out->passes = static_cast<uint32_t>((g->m + 3) / 4 > 1 && cauchy ? (g->m + 3) / 4 : 1);
 	return LZGPU_OK;
 }
 

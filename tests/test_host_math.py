@@ -191,10 +191,13 @@ def test_encode_unit_geometry_decisions():
     assert _plan("ec(8,2)", 1, 1024).mode == 0                      # a single chunk needs neither
     # 37 MiB + 5 blocks of ec(8,2): 75 stripes, 80 slots = 6.7 % waste -> per chunk; xor3 4 MiB: 22 stripes in 20-stripe units -> striped
     assert _plan("ec(8,2)", 219, 597).mode == 0 and _plan("xor3", 2048, 64).mode == 2
-    # Cauchy goal (m = 4, k > 20) runs the bit-plane instantiation with 8 warps; five parity parts leave the fused kernel
+    # Cauchy goal (m = 4, k > 20) runs the bit-plane instantiation with 8 warps; more than four parity parts are encoded in
+    # passes of four Cauchy rows over the same data (ec(4,5): 4 + 1 rows, ec(8,6): 4 + 2, ec(32,32): eight passes)
     p = _plan("ec(21,4)", 10, 63)
-    assert p.fused == 1 and p.threads_per_cta == 256
-    assert _plan("ec(4,5)", 10, 64).fused == 0
+    assert p.fused == 1 and p.threads_per_cta == 256 and p.passes == 1
+    assert (_plan("ec(4,5)", 10, 64).fused, _plan("ec(4,5)", 10, 64).passes) == (1, 2)
+    assert (_plan("ec(8,6)", 64, 1024).fused, _plan("ec(8,6)", 64, 1024).passes) == (1, 2)
+    assert (_plan("ec(32,32)", 4, 1024).fused, _plan("ec(32,32)", 4, 1024).passes) == (1, 8)
 
 
 def test_encode_unit_geometry_invariants_for_every_goal():

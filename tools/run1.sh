@@ -16,4 +16,7 @@ $NCU -k regex:fused_recover -s 2 -c 1 -o gpurun_out/r1_prof_rec53 python tools/s
 # per-sub-partition instance values for the headline kernel
 ncu --clock-control none --metrics smsp__inst_executed.sum,smsp__inst_executed_pipe_alu.sum,smsp__cycles_active.sum,smsp__warps_active.sum --print-metric-instances values -k regex:fused_stream -s 2 -c 1 python tools/sweep.py --full-size-only --sections enc --goals 'ec(8,2)' --steps 1 --warmup 2 --out gpurun_out/r1_tmp.md > gpurun_out/r1_smsp_ec82.log 2>&1
 ncu --clock-control none --metrics smsp__inst_executed.sum,smsp__inst_executed_pipe_alu.sum,smsp__cycles_active.sum --print-metric-instances values -k regex:fused_stream -s 2 -c 1 python tools/sweep.py --full-size-only --sections enc --goals 'ec(8,4)' --steps 1 --warmup 2 --out gpurun_out/r1_tmp.md > gpurun_out/r1_smsp_ec84.log 2>&1
-ls -la gpurun_out | head -40
+timeout 600 python bench.py --steps 4 --cpu-chunks 32 > gpurun_out/r1_bench.json 2> gpurun_out/r1_bench.err; tail -c 600 gpurun_out/r1_bench.err
+LZGPU_LIB=$PWD/lizardfs_b200/liblzgpu_t256.so timeout 300 python bench.py --steps 6 --no-extra --no-e2e --no-cpu-baseline > gpurun_out/r1_bench_t256.json 2> gpurun_out/r1_bench_t256.err
+python tools/sweep.py --sections conv --out gpurun_out/r1_sweep_conv.md > /dev/null 2> gpurun_out/r1_sweep_conv.err
+ls -la gpurun_out | head -60
