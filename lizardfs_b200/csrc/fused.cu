@@ -22,6 +22,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 constexpr int kSmemCap128 = 226 * 1024;       // FW = 128 variant: one CTA per SM
 constexpr int kRecoverSmemCap = 200 * 1024;  // recover kernel: one CTA per SM, 6 stages
 constexpr int kRecoverSmemCap2 = 100 * 1024; // two CTAs per SM, 3 stages (E <= 2)
+constexpr int kRecoverSmemCapBig = 208 * 1024; // one 16-warp CTA per SM (GEO 2)
 
 struct FusedState {
 	EncodeTiledFn encode_tiled = nullptr;
@@ -33,7 +34,8 @@ struct FusedState {
 	uint32_t *d_sm_ctr = nullptr;
 	int evict_first = 0;
 	int striped = -1;
-	int recover_two = -1;  // LZGPU_RECOVER_TWO: -1 automatic, 0 one CTA per SM (6 stages), 1 two CTAs (3 stages) for e <= 2  // LZGPU_STRIPED: -1 automatic, 0 never, 1 whenever the shape allows
+	int recover_two = -1;  // LZGPU_RECOVER_TWO: -1 automatic, 0 one CTA per SM (6 stages), 1 two CTAs (3 stages) for e <= 2
+	int recover_geo = -1;  // LZGPU_RECOVER_GEO: -1 automatic, 0 / 1 as above, 2 one 16-warp CTA per SM
 	int promo = 3;  // CU_TENSOR_MAP_L2_PROMOTION_L2_256B: +12% streaming bandwidth over 128B/none (profiles/probe_r1.md)
 };
 
@@ -52,7 +54,7 @@ static uint32_t crc_xpow_bits_signed(long long n) {
 
 template <int M, bool GENERIC, int KT = 0, int GT = 0, int FW = 64, bool STRIPED = false, bool SPLIT = false>
 static int set_smem_attr(int bytes) {
-	if (FW == 64) bytes = std::max(bytes, fused_smem_cap(M, FW));  // one-CTA-per-SM shapes use a deeper ring
+	if (FW == 64) bytes = std::max(bytes, fused_smem_cap(M, GENERIC, FW));  // one-CTA-per-SM shapes use a deeper ring
 	CUDA_TRY(cudaFuncSetAttribute(fused_stream_kernel<M, GENERIC, KT, GT, FW, STRIPED, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
 	return LZGPU_OK;
 }
@@ -60,7 +62,8 @@ static int set_smem_attr(int bytes) {
 template <int E, int KT, int R0 = -1, int R1 = -1>
 static int set_recover_attr() {
 	CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<E, KT, R0, R1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCap));
-	if constexpr (E <= 2) CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<E, KT, R0, R1, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCap2));
+	if constexpr (E <= 2) CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<E, KT, R0, R1, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCap2));
+	CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<E, KT, R0, R1, 64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCapBig));
 #ifdef LZ_ENABLE_FOLD128
 	CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<E, KT, R0, R1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCap));
 #endif
@@ -91,6 +94,7 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if (const char *e = std::getenv("LZGPU_L2_PROMO")) fs->promo = std::atoi(e);
 	if (const char *e = std::getenv("LZGPU_EVICT_FIRST")) fs->evict_first = std::atoi(e);
 	if (const char *e = std::getenv("LZGPU_RECOVER_TWO")) fs->recover_two = std::atoi(e);
+	if (const char *e = std::getenv("LZGPU_RECOVER_GEO")) fs->recover_geo = std::atoi(e);
 	if (const char *e = std::getenv("LZGPU_STRIPED")) fs->striped = std::atoi(e);  // 0 never, 1 whenever possible, unset = automatic
 	void *fn = nullptr;
 	cudaDriverEntryPointQueryResult qres;
@@ -130,27 +134,30 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if ((rc = set_smem_attr<3, false, 0, 0, 64, true>(smem))) return rc;
 	if ((rc = set_smem_attr<4, false, 0, 0, 64, true>(smem))) return rc;
 	if ((rc = set_smem_attr<4, true, 0, 0, 64, true>(smem))) return rc;
-	if ((rc = set_smem_attr<2, false, 8, 8, 64, true>(smem))) return rc;
+	if ((rc = set_smem_attr<2, false, 8, 7, 64, true>(smem))) return rc;
 	if ((rc = set_smem_attr<1, false, 2, 32, 64, true>(smem))) return rc;
 	if ((rc = set_smem_attr<1, false, 3, 20, 64, true>(smem))) return rc;
 	if ((rc = set_smem_attr<2, false, 3, 16, 64, true>(smem))) return rc;
 	if ((rc = set_smem_attr<3, false, 5, 8, 64, true>(smem))) return rc;
-	if ((rc = set_smem_attr<4, false, 8, 5, 64, true>(smem))) return rc;
-	if ((rc = set_smem_attr<2, false, 8, 8>(smem))) return rc;
+	if ((rc = set_smem_attr<4, false, 8, 8, 64, true>(smem))) return rc;
 	if ((rc = set_smem_attr<2, false, 8, 7>(smem))) return rc;
 	if ((rc = set_smem_attr<1, false, 2, 32>(smem))) return rc;
 	if ((rc = set_smem_attr<1, false, 3, 20>(smem))) return rc;
 	if ((rc = set_smem_attr<2, false, 3, 16>(smem))) return rc;
-	if ((rc = set_smem_attr<2, false, 3, 18>(smem))) return rc;
-	if ((rc = set_smem_attr<2, false, 4, 14>(smem))) return rc;
-	if ((rc = set_smem_attr<2, false, 6, 10>(smem))) return rc;
+	if ((rc = set_smem_attr<2, false, 4, 12>(smem))) return rc;
+	if ((rc = set_smem_attr<2, false, 6, 9>(smem))) return rc;
 	if ((rc = set_smem_attr<3, false, 5, 8>(smem))) return rc;
 	if ((rc = set_smem_attr<3, false, 6, 8>(smem))) return rc;
+	if ((rc = set_smem_attr<4, false, 8, 8>(smem))) return rc;
+#if LZ_T2 == 288
+	if ((rc = set_smem_attr<2, false, 8, 8>(smem))) return rc;
+#endif
+#if LZ_T4 == 256
 	if ((rc = set_smem_attr<4, false, 8, 5>(smem))) return rc;
-#if LZ_T34 == 512
+#endif
+#if LZ_T3 == 512
 	if ((rc = set_smem_attr<3, false, 5, 12>(smem))) return rc;
 	if ((rc = set_smem_attr<3, false, 6, 10>(smem))) return rc;
-	if ((rc = set_smem_attr<4, false, 8, 8>(smem))) return rc;
 #endif
 #ifdef LZ_ENABLE_FOLD128
 	const int smem128 = std::min(fs->max_smem, kSmemCap128);
@@ -193,9 +200,9 @@ static int make_tensor_map(FusedState *fs, CUtensorMap *map, const void *base, u
 
 template <int M, bool GENERIC, int KT = 0, int GT = 0, int FW = 64, bool STRIPED = false, bool SPLIT = false>
 static int launch(lzgpu_ctx *ctx, const CUtensorMap &map, const FusedParams &p, size_t smem, cudaStream_t st) {
-	const int per_sm = fused_ctas_per_sm(M, FW);
+	const int per_sm = fused_ctas_per_sm(M, GENERIC, FW);
 	const int grid = static_cast<int>(std::min<uint64_t>(p.total_units, static_cast<uint64_t>(ctx->sm_count) * per_sm));
-	fused_stream_kernel<M, GENERIC, KT, GT, FW, STRIPED, SPLIT><<<grid, fused_threads(M), smem, st>>>(map, p);
+	fused_stream_kernel<M, GENERIC, KT, GT, FW, STRIPED, SPLIT><<<grid, fused_threads(M, GENERIC), smem, st>>>(map, p);
 	CUDA_TRY(cudaGetLastError());
 	ctx->stats.kernel_launches++;
 	return LZGPU_OK;
@@ -226,7 +233,7 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	FusedState *fs = ctx->fused;
 	const uint32_t PC = M == 0 ? 0 : (generic ? M : M - 1);
 	const int fw = choose_fold(fs, M, generic);
-	const int smem_cap = std::min(fs->max_smem, fw == 64 ? fused_smem_cap(M, fw) : kSmemCap128);
+	const int smem_cap = std::min(fs->max_smem, fw == 64 ? fused_smem_cap(M, generic, fw) : kSmemCap128);
 	// unit geometry: per-chunk, flat or striped units, stripes per unit (fused_plan.h; unit-tested without a GPU)
 	const FusedPlan pl = fused_plan(M, generic, K, n_chunks, nb, chunk_stride, smem_cap, fw, split_out ? 0 : (striped_policy == -2 ? fs->striped : striped_policy));
 	if (!pl.ok || (reinterpret_cast<uintptr_t>(d_data) % 16)) return LZGPU_NOT_HANDLED;
@@ -290,12 +297,12 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 		}
 #define LZ_FOLDED_STRIPED(MM, KK, GG) \
 	if (M == MM && K == KK && G == GG) return launch<MM, false, KK, GG, 64, true>(ctx, map, p, smem, st);
-		LZ_FOLDED_STRIPED(2, 8, 8)
+		LZ_FOLDED_STRIPED(2, 8, 7)
 		LZ_FOLDED_STRIPED(1, 2, 32)
 		LZ_FOLDED_STRIPED(1, 3, 20)
 		LZ_FOLDED_STRIPED(2, 3, 16)
 		LZ_FOLDED_STRIPED(3, 5, 8)
-		LZ_FOLDED_STRIPED(4, 8, 5)
+		LZ_FOLDED_STRIPED(4, 8, 8)
 #undef LZ_FOLDED_STRIPED
 		switch (M) {
 			case 1: return launch<1, false, 0, 0, 64, true>(ctx, map, p, smem, st);
@@ -332,21 +339,24 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	// constant-folded instantiations for the common goals (k, G from pick_group), runtime k/G otherwise
 #define LZ_FOLDED(MM, KK, GG) \
 	if (M == MM && K == KK && G == GG) return launch<MM, false, KK, GG>(ctx, map, p, smem, st);
-	LZ_FOLDED(2, 8, 8)    // ec(8,2)
-	LZ_FOLDED(2, 8, 7)    // ec(8,2) on an 8-warp CTA (-DLZ_T2=256)
+	LZ_FOLDED(2, 8, 7)    // ec(8,2)
 	LZ_FOLDED(1, 2, 32)   // xor2
 	LZ_FOLDED(1, 3, 20)   // xor3
 	LZ_FOLDED(2, 3, 16)   // ec(3,2)
-	LZ_FOLDED(2, 3, 18)   // ec(3,2) with a 3-deep parity ring (-DLZ_NPST=3)
-	LZ_FOLDED(2, 4, 14)   // ec(4,2)
-	LZ_FOLDED(2, 6, 10)   // ec(6,2)
+	LZ_FOLDED(2, 4, 12)   // ec(4,2)
+	LZ_FOLDED(2, 6, 9)    // ec(6,2)
 	LZ_FOLDED(3, 5, 8)    // ec(5,3)
 	LZ_FOLDED(3, 6, 8)    // ec(6,3)
-	LZ_FOLDED(4, 8, 5)    // ec(8,4)
-#if LZ_T34 == 512
-	LZ_FOLDED(3, 5, 12)   // one 16-warp CTA per SM
+	LZ_FOLDED(4, 8, 8)    // ec(8,4) on one 16-warp CTA per SM
+#if LZ_T2 == 288
+	LZ_FOLDED(2, 8, 8)    // experiment builds with the nine-warp CTA of round 1
+#endif
+#if LZ_T4 == 256
+	LZ_FOLDED(4, 8, 5)
+#endif
+#if LZ_T3 == 512
+	LZ_FOLDED(3, 5, 12)
 	LZ_FOLDED(3, 6, 10)
-	LZ_FOLDED(4, 8, 8)
 #endif
 #undef LZ_FOLDED
 	switch (M) {
@@ -374,7 +384,7 @@ int lz_fused_encode(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, u
 		if (M == 4) return fused_run(ctx, 4, true, gen + K * K, K, n_chunks, nb, d_data, chunk_stride, d_parity, parity_stride, d_crc, crc_stride, st);
 		const uint32_t pb = (nb + K - 1) / K;
 		for (int rows : {4, M % 4})
-			if (rows && !fused_plan(rows, true, K, n_chunks, nb, chunk_stride, std::min(fs->max_smem, fused_smem_cap(rows, 64)), 64, 0).ok) return LZGPU_NOT_HANDLED;
+			if (rows && !fused_plan(rows, true, K, n_chunks, nb, chunk_stride, std::min(fs->max_smem, fused_smem_cap(rows, true, 64)), 64, 0).ok) return LZGPU_NOT_HANDLED;
 		if (reinterpret_cast<uintptr_t>(d_data) % 16) return LZGPU_NOT_HANDLED;
 		for (int r0 = 0; r0 < M; r0 += 4) {
 			// per-chunk / flat units only: the passes share one geometry rule (striped policy 0)
@@ -428,10 +438,17 @@ int lz_fused_crc(lzgpu_ctx *ctx, const void *base, unsigned long long n_blocks, 
 // fused degraded read
 // ---------------------------------------------------------------------------------------------------
 template <int E, int KT, int R0 = -1, int R1 = -1>
-static int launch_recover(lzgpu_ctx *ctx, const TmapArray &maps, const RecoverParams &p, size_t smem, cudaStream_t st, bool two) {
-	if (two && E <= 2) {
+static int launch_recover(lzgpu_ctx *ctx, const TmapArray &maps, const RecoverParams &p, size_t smem, cudaStream_t st, int geo) {
+	if (geo == 2) {
+		const int gridb = static_cast<int>(std::min<uint64_t>(p.total_units, static_cast<uint64_t>(ctx->sm_count)));
+		fused_recover_kernel<E, KT, R0, R1, 64, 2><<<gridb, recover_threads(2), smem, st>>>(maps, p);
+		CUDA_TRY(cudaGetLastError());
+		ctx->stats.kernel_launches++;
+		return LZGPU_OK;
+	}
+	if (geo == 1 && E <= 2) {
 		const int grid2 = static_cast<int>(std::min<uint64_t>(p.total_units, static_cast<uint64_t>(ctx->sm_count) * 2));
-		fused_recover_kernel<(E <= 2 ? E : 1), KT, R0, R1, 64, true><<<grid2, kFusedThreads, smem, st>>>(maps, p);
+		fused_recover_kernel<(E <= 2 ? E : 1), KT, R0, R1, 64, 1><<<grid2, kFusedThreads, smem, st>>>(maps, p);
 		CUDA_TRY(cudaGetLastError());
 		ctx->stats.kernel_launches++;
 		return LZGPU_OK;
@@ -487,13 +504,29 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 	// shapes, except the single-erasure case that also writes the image.  LZGPU_RECOVER_TWO=0|1 forces either.
 	const bool two_auto = K != 8 && (e == 2 || (e == 1 && !d_chunk_out));
 	const bool two = e <= 2 && (fs->recover_two < 0 ? two_auto : fs->recover_two != 0);
-	const int n_stages = recover_stages(two);
-	const size_t smem_cap = two ? kRecoverSmemCap2 : kRecoverSmemCap;
-	uint32_t G = 0;
-	for (uint32_t g = 2; g <= 64; g += 2) {
-		const uint32_t rows = K * g * 4;
-		if (rows > kMaxRows || static_cast<size_t>(n_stages) * rows * kStepBytes + 256 > smem_cap) break;
-		G = g;
+	int geo = fs->recover_geo >= 0 ? fs->recover_geo : (two ? 1 : 0);
+	if (geo == 1 && e > 2) geo = 0;
+	uint32_t G = 0, n_stages = 0;
+	if (geo == 2) {
+		// one 16-warp CTA: the largest G whose K*G*4 input rows fit 512 threads (one TMA box per part: G*4 <= 256 rows) and whose
+		// 32*G items fill whole rounds of the CTA (G a multiple of 16) where K allows, with at least three stages in 200 KiB
+		uint32_t best = 0, best16 = 0;
+		for (uint32_t g = 2; g <= 64; g += 2) {
+			const uint32_t rows = K * g * 4;
+			if (rows > 512 || 3 * static_cast<size_t>(rows) * kStepBytes + 256 > kRecoverSmemCapBig) break;
+			best = g;
+			if (g % 16 == 0) best16 = g;
+		}
+		G = best16 ? best16 : best;
+		if (G) n_stages = static_cast<uint32_t>(std::min<size_t>(6, (kRecoverSmemCapBig - 256) / (static_cast<size_t>(K) * G * 4 * kStepBytes)));
+	} else {
+		n_stages = static_cast<uint32_t>(recover_stages(geo));
+		const size_t smem_cap = geo == 1 ? kRecoverSmemCap2 : kRecoverSmemCap;
+		for (uint32_t g = 2; g <= 64; g += 2) {
+			const uint32_t rows = K * g * 4;
+			if (rows > kMaxRows || static_cast<size_t>(n_stages) * rows * kStepBytes + 256 > smem_cap) break;
+			G = g;
+		}
 	}
 	if (G == 0) return LZGPU_NOT_HANDLED;
 	const uint32_t pb = (nb + K - 1) / K;
@@ -518,6 +551,7 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 	if (total > 0x7fffffffull) return LZGPU_NOT_HANDLED;
 	p.total_units = static_cast<uint32_t>(total);
 	p.e = e;
+	p.n_stages = n_stages;
 #ifdef LZ_ENABLE_FOLD128
 	std::memcpy(p.qmult, fs->fold == 128 ? fs->qmult128 : fs->qmult64, sizeof(p.qmult));
 #else
@@ -545,7 +579,8 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 			coef_planes_set(p.w[x * 4 + r], W[x * e + r]);
 		}
 	p.raid6_dbl = 0xffu;
-	if (e == 2 && p.par_row[0] == 0 && p.par_row[1] == 1 && !(K == 8 && G == 8)) {
+	const bool k8 = K == 8 && (G == 8 || geo == 2);
+	if (e == 2 && p.par_row[0] == 0 && p.par_row[1] == 1 && !k8) {
 		// RAID-6 shape on a runtime-k instantiation: w[0] = planes of 2^x0, w[1] = planes of (2^x0 ^ 2^x1)^-1 (see the kernel)
 		uint8_t gx0 = 1, gx1 = 1;
 		for (int t = 0; t < p.erased_idx[0]; ++t) gx0 = lz::gf_mul_host(gx0, 2);
@@ -567,20 +602,19 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 	}
 	if (*verifying && !d_first_bad) return LZGPU_NOT_HANDLED;  // (callers that pass stored CRCs always pass the result word, initialised to ~0)
 	const size_t smem = static_cast<size_t>(n_stages) * K * G * 4 * kStepBytes + 16 * n_stages + 64;
-	const bool k8 = K == 8 && G == 8;
 	const bool row0 = p.par_row[0] == 0, row01 = row0 && e >= 2 && p.par_row[1] == 1;
 	switch (e) {
 		case 1:
-			if (row0) return k8 ? launch_recover<1, 8, 0>(ctx, maps, p, smem, st, two) : launch_recover<1, 0, 0>(ctx, maps, p, smem, st, two);
-			return launch_recover<1, 0>(ctx, maps, p, smem, st, two);
+			if (row0) return k8 ? launch_recover<1, 8, 0>(ctx, maps, p, smem, st, geo) : launch_recover<1, 0, 0>(ctx, maps, p, smem, st, geo);
+			return launch_recover<1, 0>(ctx, maps, p, smem, st, geo);
 		case 2:
-			if (row01) return k8 ? launch_recover<2, 8, 0, 1>(ctx, maps, p, smem, st, two) : launch_recover<2, 0, 0, 1>(ctx, maps, p, smem, st, two);
-			return launch_recover<2, 0>(ctx, maps, p, smem, st, two);
+			if (row01) return k8 ? launch_recover<2, 8, 0, 1>(ctx, maps, p, smem, st, geo) : launch_recover<2, 0, 0, 1>(ctx, maps, p, smem, st, geo);
+			return launch_recover<2, 0>(ctx, maps, p, smem, st, geo);
 		case 3:
-			if (row01) return launch_recover<3, 0, 0, 1>(ctx, maps, p, smem, st, two);
-			return launch_recover<3, 0>(ctx, maps, p, smem, st, two);
+			if (row01) return launch_recover<3, 0, 0, 1>(ctx, maps, p, smem, st, geo);
+			return launch_recover<3, 0>(ctx, maps, p, smem, st, geo);
 		default:
-			if (row01) return launch_recover<4, 0, 0, 1>(ctx, maps, p, smem, st, two);
-			return launch_recover<4, 0>(ctx, maps, p, smem, st, two);
+			if (row01) return launch_recover<4, 0, 0, 1>(ctx, maps, p, smem, st, geo);
+			return launch_recover<4, 0>(ctx, maps, p, smem, st, geo);
 	}
 }

@@ -179,6 +179,27 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v) {
 	asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// W packed words of one GF item (W = 4: 16 bytes, the default; 2 or 1: narrower items = more, lighter items per step, for shapes
+// whose 16-byte items would leave most warps without GF work)
+template <int W>
+__device__ __forceinline__ void lds_item(uint32_t addr, uint32_t (&v)[W]) {
+	if constexpr (W == 4) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
+	else if constexpr (W == 2) asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(addr));
+	else asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v[0]) : "r"(addr));
+}
+template <int W>
+__device__ __forceinline__ void sts_item(uint32_t addr, const uint32_t (&v)[W]) {
+	if constexpr (W == 4) asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+	else if constexpr (W == 2) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(v[0]), "r"(v[1]) : "memory");
+	else asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v[0]) : "memory");
+}
+template <int W>
+__device__ __forceinline__ void stg_item(void *p, const uint32_t (&v)[W]) {
+	if constexpr (W == 4) asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+	else if constexpr (W == 2) asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v[0]), "r"(v[1]) : "memory");
+	else asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v[0]) : "memory");
+}
+
 template <int FW>
 __device__ __forceinline__ void fold_word(uint32_t (&win)[FW], int S, uint32_t w) {
 	uint32_t acc = w;
@@ -241,11 +262,11 @@ __device__ __forceinline__ uint32_t fold_finish(uint32_t (&win)[FW], const uint3
 // Register budget: __launch_bounds__(288, 2) makes ptxas target 96 registers (2 CTAs/SM), (288, 1) -> 168.
 // (An explicit __maxnreg__(96) instead of the launch bounds produced a 5 % slower kernel on the same box: ptxas
 // schedules differently when it does not know the block size.)
-template <int M, bool GENERIC, int KT, int GT, int FW, bool STRIPED = false, bool SPLIT = false>
-__global__ void __launch_bounds__(fused_threads(M), fused_ctas_per_sm(M, FW))
+template <int M, bool GENERIC, int KT, int GT, int FW, bool STRIPED = false, bool SPLIT = false, int W = fused_item_words(M, GENERIC)>
+__global__ void __launch_bounds__(fused_threads(M, GENERIC), fused_ctas_per_sm(M, GENERIC, FW))
 fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
-	constexpr int kNST = fused_nst(FW, M), kNPST = fused_npst(FW, M);
-	constexpr int NT = fused_threads(M);
+	constexpr int kNST = fused_nst(FW, M, GENERIC), kNPST = fused_npst(FW, M, GENERIC);
+	constexpr int NT = fused_threads(M, GENERIC);
 	constexpr int PC = (M == 0) ? 0 : (GENERIC ? M : M - 1);  // parity parts whose CRC is computed from bytes
 	constexpr int P0 = GENERIC ? 0 : 1;                       // first such parity part
 
@@ -263,7 +284,8 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 
 	const uint32_t tid = threadIdx.x;
 	const uint32_t warp = tid >> 5, lane = tid & 31;
-	const uint32_t n_items = 32 * G * (M > 0 ? 1 : 0);
+	constexpr uint32_t CPI = 32 / W;                               // items per 128-byte row step (columns of 4*W bytes)
+	const uint32_t n_items = 4 * CPI * G * (M > 0 ? 1 : 0);
 	const uint32_t n_gf_warps = (min(n_items, (uint32_t)NT) + 31) / 32;
 	const uint32_t first_pwarp = ROWS / 32, last_pwarp = PROWS ? (ROWS + PROWS - 1) / 32 : 0;
 	// warps that read the TMA data stages (data streams or GF items); pure parity-CRC warps do not gate the refill
@@ -372,43 +394,44 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 				if (M > 0 && warp_has_items && !LZ_PROBE(2)) {
 					if (PC > 0) mbar_wait(a_pempty + 8 * pst, pph ^ 1);
 					for (uint32_t item = vt; item < n_items; item += NT) {
-						const uint32_t col = item & 7, q = (item >> 3) & 3, g = item >> 5;
-						uint32_t acc[M > 0 ? M : 1][4];
+						const uint32_t col = item % CPI, q = (item / CPI) & 3, g = item / (4 * CPI);
+						const uint32_t c16 = (col * W) >> 2, sub = ((col * W) & 3) << 2;   // 16-byte chunk of the row step, byte offset inside it
+						uint32_t acc[M > 0 ? M : 1][W];
 #pragma unroll
-						for (int r = 0; r < M; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0;
+						for (int r = 0; r < M; ++r)
+#pragma unroll
+							for (int w = 0; w < W; ++w) acc[r][w] = 0;
 						// row (g*K + j)*4 + q: its swizzle (row & 7) = (4*((g*K + j) & 1) + q) alternates with j
 						const uint32_t rbase = g * K * 4 + q;
 						const uint32_t sg = stripe0 + g;
 						uint32_t pc = 0, stripe = 0;
 						if (sg < stripes_total) locate(sg, c, pc, stripe);
-						const unsigned long long in_part = (static_cast<unsigned long long>(stripe) << 16) + (q << 14) + step * kStepBytes + (col << 4);
-						const uint32_t a_even = (stage + rbase * kStepBytes) ^ ((col ^ (rbase & 7)) << 4);
-						const uint32_t a_odd = (stage + rbase * kStepBytes) ^ ((col ^ ((rbase & 7) ^ 4)) << 4);
+						const unsigned long long in_part = (static_cast<unsigned long long>(stripe) << 16) + (q << 14) + step * kStepBytes + col * (4 * W);
+						const uint32_t a_even = ((stage + rbase * kStepBytes) ^ ((c16 ^ (rbase & 7)) << 4)) + sub;
+						const uint32_t a_odd = ((stage + rbase * kStepBytes) ^ ((c16 ^ ((rbase & 7) ^ 4)) << 4)) + sub;
 #pragma unroll
 						for (int j = static_cast<int>(K) - 1; j >= 0; --j) {
-							const uint4 v = lds128(((j & 1) ? a_odd : a_even) + 4u * j * kStepBytes);
+							uint32_t v[W];
+							lds_item<W>(((j & 1) ? a_odd : a_even) + 4u * j * kStepBytes, v);
 							if (SPLIT) {
 								// BlockConverter: chunk block stripe*K + j is block `stripe` of data part j (blocks the chunk does not have are zeros)
 								uint8_t *dp = p.data_out[j];
-								if (dp && sg < stripes_total) st_stream(reinterpret_cast<uint4 *>(dp + pc * p.part_out_stride + in_part), v);
+								if (dp && sg < stripes_total) stg_item<W>(dp + pc * p.part_out_stride + in_part, v);
 							}
 							if (GENERIC) {
 #pragma unroll
 								for (int r = 0; r < M; ++r) {
 									const CoefPlanes &cp = p.coef[r * 32 + j];
 									// M coefficients share the word: ALU 8 + NS + 4M next to the CRC folds, FMA M (15 - NS)
-									acc[r][0] = gf_mac<6>(acc[r][0], v.x, cp);
-									acc[r][1] = gf_mac<6>(acc[r][1], v.y, cp);
-									acc[r][2] = gf_mac<6>(acc[r][2], v.z, cp);
-									acc[r][3] = gf_mac<6>(acc[r][3], v.w, cp);
+#pragma unroll
+									for (int w = 0; w < W; ++w) acc[r][w] = gf_mac<6>(acc[r][w], v[w], cp);
 								}
 							} else {
 #pragma unroll
 								for (int r = 0; r < M; ++r) {
 #pragma unroll
-									for (int w = 0; w < 4; ++w) {
-										uint32_t a = acc[r][w];
-										const uint32_t d = (w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w);
+									for (int w = 0; w < W; ++w) {
+										const uint32_t a = acc[r][w], d = v[w];
 										// Horner step acc*2^r + d_j, the multiplication by 2, 4 or 8 done in one go
 										acc[r][w] = r == 0 ? (a ^ d) : r == 1 ? gf_x2_add(a, d) : r == 2 ? gf_x4_add(a, d) : gf_x8_add(a, d);
 									}
@@ -419,21 +442,17 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 							if (SPLIT) {
 #pragma unroll
 								for (int r = 0; r < M; ++r)
-									if (p.par_out[r])
-										st_stream(reinterpret_cast<uint4 *>(p.par_out[r] + pc * p.part_out_stride + in_part),
-										          make_uint4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
+									if (p.par_out[r]) stg_item<W>(p.par_out[r] + pc * p.part_out_stride + in_part, acc[r]);
 							} else {
 								uint8_t *dst = p.parity + pc * p.parity_stride + in_part;
 #pragma unroll
-								for (int r = 0; r < M; ++r)
-									st_stream(reinterpret_cast<uint4 *>(dst + static_cast<unsigned long long>(r) * p.pb * 65536ull),
-									          make_uint4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
+								for (int r = 0; r < M; ++r) stg_item<W>(dst + static_cast<unsigned long long>(r) * p.pb * 65536ull, acc[r]);
 							}
 						}
 #pragma unroll
 						for (int r = P0; r < M; ++r) {
 							const uint32_t pr = (g * PC + (r - P0)) * 4 + q;
-							sts128((pstage + pr * kStepBytes) ^ ((col ^ (pr & 7)) << 4), make_uint4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
+							sts_item<W>(((pstage + pr * kStepBytes) ^ ((c16 ^ (pr & 7)) << 4)) + sub, acc[r]);
 						}
 					}
 					if (PC > 0) {
@@ -543,6 +562,7 @@ struct RecoverParams {
 	unsigned long long out_stride, image_stride;
 	uint32_t n_chunks, nb, pb, K, G, units_per_chunk, total_units;
 	uint32_t e;                    // erased data parts (1..4)
+	uint32_t n_stages;             // BIG geometry only: depth of the stage ring (as many stages as fit 200 KiB)
 	uint32_t raid6_dbl;            // E = 2 with parity rows 0 and 1 (the RAID-6 shape): doublings for 2^x0 * S0, 0xff = use w[0]
 	uint8_t slot_of_data[32];      // data index j -> slot, 0xff = erased
 	uint8_t erased_idx[4];         // data index of erased part x
@@ -560,12 +580,17 @@ struct RecoverParams {
 // that also leaves room for the 128-word fold window (3 LOP3 per word).
 // TWO = two CTAs per SM with a 3-stage ring (96 registers) instead of one CTA with 6 stages: the cheap solves (E <= 2) are
 // latency bound at 9 warps per SM, the second CTA hides it.
-__host__ __device__ constexpr int recover_stages(bool two) { return two ? 3 : 6; }
+// GEO 2 ("big"): ONE 16-warp CTA per SM (512 threads x 128 registers fill the register file), G chosen so that the K*G*4 input rows
+// and the 32*G items both fill whole warps (ec(8,2): G = 16 -> every thread owns one row and one item), ring depth at run time.
+// Twice the resident warps of GEO 0 and, unlike GEO 1, room for the solve's registers.
+__host__ __device__ constexpr int recover_stages(int geo) { return geo == 1 ? 3 : 6; }
+__host__ __device__ constexpr int recover_threads(int geo) { return geo == 2 ? 512 : kFusedThreads; }
 
-template <int E, int KT, int R0, int R1, int kRecoverFW, bool TWO = false>
-__global__ void __launch_bounds__(kFusedThreads, TWO ? 2 : 1)
+template <int E, int KT, int R0, int R1, int kRecoverFW, int GEO = 0>
+__global__ void __launch_bounds__(recover_threads(GEO), GEO == 1 ? 2 : 1)
 fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_constant__ RecoverParams p) {
-	constexpr int kRecoverStages = recover_stages(TWO);
+	constexpr int kThreads = recover_threads(GEO);
+	const uint32_t kRecoverStages = GEO == 2 ? p.n_stages : static_cast<uint32_t>(recover_stages(GEO));
 	extern __shared__ __align__(1024) uint8_t smem[];
 	const uint32_t sbase = smem_u32(smem);
 	const uint32_t K = KT ? KT : p.K, G = p.G;
@@ -578,7 +603,7 @@ fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, cw = tid >> 5;
 	const uint32_t n_items = 32 * G;
-	const uint32_t n_gf_warps = (min(n_items, (uint32_t)kConsumers) + 31) / 32;
+	const uint32_t n_gf_warps = (min(n_items, (uint32_t)kThreads) + 31) / 32;
 	const uint32_t n_stage_warps = max((ROWS + 31) / 32, n_gf_warps);
 	const uint32_t my_units = blockIdx.x < p.total_units ? (p.total_units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 	const uint32_t total_steps = my_units * kStepsPerUnit;
@@ -591,7 +616,7 @@ fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 	};
 
 	if (tid == 0) {
-		for (int s = 0; s < kRecoverStages; ++s) {
+		for (uint32_t s = 0; s < kRecoverStages; ++s) {
 			mbar_init(a_full + 8 * s, 1);
 			mbar_init(a_empty + 8 * s, n_stage_warps);
 		}
@@ -627,7 +652,7 @@ fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 
 				// ---------------- GF role: syndromes, solve, scatter ----------------
 				if (warp_has_items) {
-					for (uint32_t item = tid; item < n_items; item += kConsumers) {
+					for (uint32_t item = tid; item < n_items; item += kThreads) {
 						const uint32_t col = item & 7, q = (item >> 3) & 3, g = item >> 5;
 						const uint32_t r0 = g * 4 + q;   // row inside every slot region; region bases are multiples of 8 rows
 						const uint32_t a_item = (stage + r0 * kStepBytes) ^ ((col ^ (r0 & 7)) << 4);

@@ -16,7 +16,7 @@ namespace lzd {
 constexpr int kStepBytes = 128;
 constexpr int kRowBytes = 16384;
 constexpr int kStepsPerUnit = kRowBytes / kStepBytes;  // 128
-constexpr int kConsumers = 288;                        // 9 warps, all consumers (2 CTAs/SM -> 112 registers per thread)
+constexpr int kConsumers = 288;                        // recover kernel: 9 warps, all consumers
 constexpr int kFusedThreads = kConsumers;
 constexpr int kMaxRows = 256;                          // TMA box limit per dimension
 constexpr int kMaxParityRows = 128;
@@ -25,44 +25,70 @@ constexpr int kSmemCap = 113 * 1024;                   // dynamic shared memory 
 // Three or four parity rows keep 12-16 Horner accumulators live next to the 64-word CRC window: at 96 registers the kernel
 // spills into its inner loop (ncu: long-scoreboard stalls on the local loads, profiles/ec84_r1_ncu_summary.md).  Those
 // shapes run with 8 warps instead of 9, which lets two CTAs per SM have 128 registers per thread.
+// CTA shape per instantiation (parity rows M, Vandermonde or generic coefficients) — measured, profiles/sweep_r2.md:
+//   M <= 2            two 8-warp CTAs per SM (ec(8,2): G = 7, 252 of 256 threads carry a stream; +3.5 % over the 9-warp CTA whose
+//                     ninth warp — parity CRC only — unbalances the four schedulers)
+//   M == 3            two 8-warp CTAs per SM, 128 registers (12 Horner accumulators next to the 64-word CRC window spill at 96)
+//   M == 4            ONE 16-warp CTA per SM (ec(8,4): G = 8, every scheduler gets two item warps and three row warps; +11 % over
+//                     two 8-warp CTAs whose five item warps load the schedulers 2:1:1:1), deeper stage ring instead
+//   generic (Cauchy)  two 8-warp CTAs, narrow items (LZ_WGEN words): k > 20 leaves G <= 3, so 16-byte items would put all the
+//                     coefficient multiplies on two or three warps
+// Every value can be overridden at build time (-DLZ_T2=..., experiment builds next to the production library).
 #ifndef LZ_T2
-#define LZ_T2 kConsumers  // experiment builds: -DLZ_T2=256 (one or two parity rows on 8-warp CTAs)
+#define LZ_T2 256
 #endif
-#ifndef LZ_T34
-#define LZ_T34 256        // experiment builds: -DLZ_T34=512 (three or four parity rows on ONE 16-warp CTA per SM)
+#ifndef LZ_T3
+#define LZ_T3 256
 #endif
-LZ_HD constexpr int fused_threads(int m) { return m >= 3 ? LZ_T34 : LZ_T2; }
+#ifndef LZ_T4
+#define LZ_T4 512
+#endif
+#ifndef LZ_TGEN
+#define LZ_TGEN 256
+#endif
+#ifndef LZ_W3
+#define LZ_W3 4
+#endif
+#ifndef LZ_W4
+#define LZ_W4 4
+#endif
+#ifndef LZ_WGEN
+#define LZ_WGEN 1
+#endif
+LZ_HD constexpr int fused_threads(int m, bool generic) { return generic ? LZ_TGEN : m <= 2 ? LZ_T2 : m == 3 ? LZ_T3 : LZ_T4; }
+// packed words per GF item (4 = 16 bytes); narrower items = more, lighter items per step
+LZ_HD constexpr int fused_item_words(int m, bool generic) { return generic ? LZ_WGEN : m == 3 ? LZ_W3 : m == 4 ? LZ_W4 : 4; }
 // CTAs per SM: two, except for the 128-word fold window and for CTAs of more than nine warps (16 warps x 128 registers fill the
 // register file on their own; their stage ring is deeper instead)
-LZ_HD constexpr int fused_ctas_per_sm(int m, int fw) { return (fw != 64 || fused_threads(m) > 288) ? 1 : 2; }
+LZ_HD constexpr int fused_ctas_per_sm(int m, bool generic, int fw) { return (fw != 64 || fused_threads(m, generic) > 288) ? 1 : 2; }
 
-// pipeline depth by fold window: FW = 64 -> 2 CTAs/SM (96 registers), 3 data stages + 4-deep parity ring;
-// FW = 128 -> 1 CTA/SM (the 128-word window needs ~170 registers), 6 data stages + 6-deep parity ring
+// pipeline depth by fold window: FW = 64 -> 2 CTAs/SM (96-128 registers), 3 data stages + 4-deep parity ring (4 stages for the
+// one-CTA shapes); FW = 128 -> 1 CTA/SM (the 128-word window needs ~170 registers), 6 data stages + 6-deep parity ring
 #ifndef LZ_NPST
 #define LZ_NPST 4
 #endif
 #ifndef LZ_NST_BIG
 #define LZ_NST_BIG 4
 #endif
-LZ_HD constexpr int fused_nst(int fw, int m) { return fw != 64 ? 6 : (fused_ctas_per_sm(m, fw) == 1 ? LZ_NST_BIG : 3); }
-LZ_HD constexpr int fused_npst(int fw, int m) { return fw == 64 ? LZ_NPST : 6; }
-LZ_HD constexpr int fused_smem_cap(int m, int fw) { return fused_ctas_per_sm(m, fw) == 1 ? 200 * 1024 : kSmemCap; }
+LZ_HD constexpr int fused_nst(int fw, int m, bool generic) { return fw != 64 ? 6 : (fused_ctas_per_sm(m, generic, fw) == 1 ? LZ_NST_BIG : 3); }
+LZ_HD constexpr int fused_npst(int fw, int m, bool generic) { return fw == 64 ? LZ_NPST : 6; }
+LZ_HD constexpr int fused_smem_cap(int m, bool generic, int fw) { return fused_ctas_per_sm(m, generic, fw) == 1 ? 200 * 1024 : kSmemCap; }
 
-inline size_t fused_smem_bytes(uint32_t rows, uint32_t prows, int fw, int m) {
+inline size_t fused_smem_bytes(uint32_t rows, uint32_t prows, int fw, int m, bool generic) {
 	const size_t pstage = (static_cast<size_t>(prows) * kStepBytes + 1023) & ~size_t(1023);
-	const size_t nst = fused_nst(fw, m), npst = fused_npst(fw, m);
+	const size_t nst = fused_nst(fw, m, generic), npst = fused_npst(fw, m, generic);
 	return nst * rows * kStepBytes + npst * pstage + 520 + 8 * (2 * nst + 2 * npst);
 }
 
 // Largest stripe group G such that data + parity-CRC rows fit the consumer threads, the data rows fit
 // one TMA box (<= 256 rows, a multiple of 8 for the 1024-byte stage alignment) and the stages fit shared memory.
-inline uint32_t pick_group(uint32_t K, uint32_t PC, int max_smem_per_cta, int fw, uint32_t threads, int m) {
+inline uint32_t pick_group(uint32_t K, uint32_t PC, int max_smem_per_cta, int fw, uint32_t threads, int m, bool generic) {
 	uint32_t best = 0;
 	for (uint32_t g = 1; g <= 64; ++g) {
 		const uint32_t rows = g * K * 4, prows = g * PC * 4;
 		if (rows > kMaxRows || rows + prows > threads || prows > kMaxParityRows || g * K > 64) break;
 		if (rows % 8) continue;
-		if (fused_smem_bytes(rows, prows, fw, m) > static_cast<size_t>(max_smem_per_cta)) break;
+		if (fused_smem_bytes(rows, prows, fw, m, generic) > static_cast<size_t>(max_smem_per_cta)) break;
 		best = g;
 	}
 	return best;
@@ -84,8 +110,8 @@ inline FusedPlan fused_plan(int M, bool generic, uint32_t K, uint32_t n_chunks, 
 	FusedPlan pl;
 	const uint32_t PC = M == 0 ? 0 : (generic ? M : M - 1);
 	const int mm = M;  // the instantiation's M (thread count, stage depth); a Cauchy generator is encoded in passes of <= 4 rows
-	pl.threads = static_cast<uint32_t>(fused_threads(mm));
-	pl.G = pick_group(K, PC, smem_cap, fw, pl.threads, mm);
+	pl.threads = static_cast<uint32_t>(fused_threads(mm, generic));
+	pl.G = pick_group(K, PC, smem_cap, fw, pl.threads, mm, generic);
 	if (pl.G == 0 || (chunk_stride % 16)) return pl;
 	const uint32_t G = pl.G;
 	pl.pb = (nb + K - 1) / K;
@@ -110,7 +136,7 @@ inline FusedPlan fused_plan(int M, bool generic, uint32_t K, uint32_t n_chunks, 
 	pl.total_units = static_cast<uint32_t>(total);
 	pl.rows = G * K * 4;
 	pl.prows = G * PC * 4;
-	pl.smem = fused_smem_bytes(pl.rows, pl.prows, fw, mm);
+	pl.smem = fused_smem_bytes(pl.rows, pl.prows, fw, mm, generic);
 	pl.ok = true;
 	return pl;
 }

@@ -336,9 +336,9 @@ int lzgpu_plan_encode(const lzgpu_goal *g, uint32_t n_chunks, uint32_t nb, size_
 	if (g->m > 4) {
 		striped_policy = 0;
 		const int last = g->m % 4;
-		if (last && !lzd::fused_plan(last, true, static_cast<uint32_t>(g->k), n_chunks, nb, chunk_stride, lzd::fused_smem_cap(last, 64), 64, 0).ok) return LZGPU_OK;
+		if (last && !lzd::fused_plan(last, true, static_cast<uint32_t>(g->k), n_chunks, nb, chunk_stride, lzd::fused_smem_cap(last, true, 64), 64, 0).ok) return LZGPU_OK;
 	}
-	const lzd::FusedPlan pl = lzd::fused_plan(first, cauchy, static_cast<uint32_t>(g->k), n_chunks, nb, chunk_stride, lzd::fused_smem_cap(first, 64), 64, striped_policy);
+	const lzd::FusedPlan pl = lzd::fused_plan(first, cauchy, static_cast<uint32_t>(g->k), n_chunks, nb, chunk_stride, lzd::fused_smem_cap(first, cauchy, 64), 64, striped_policy);
 	if (!pl.ok) return LZGPU_OK;
 	out->fused = 1;
 	out->mode = static_cast<int>(pl.mode);

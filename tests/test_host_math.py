@@ -169,16 +169,17 @@ def _plan(text, n_chunks, nb, stride_blocks=None, policy=-1):
 def test_encode_unit_geometry_decisions():
     """The launcher's host logic (csrc/fused_plan.h) without a GPU: stripes per unit, CTA size, and which unit mode a batch gets
     (per-chunk / flat / striped) for the BASELINE.json configurations and the ragged cases the sweep measures."""
-    # stripes per unit: rows = G*k*4 <= 256 (one TMA box), data + parity-CRC rows <= threads, stages fit 113 KB
-    for text, G, threads in [("ec(8,2)", 8, 288), ("xor2", 32, 288), ("xor3", 20, 288), ("ec(3,2)", 16, 288), ("ec(4,2)", 14, 288),
-                             ("ec(6,2)", 10, 288), ("ec(5,3)", 8, 256), ("ec(6,3)", 8, 256), ("ec(8,4)", 5, 256)]:
+    # stripes per unit: rows = G*k*4 <= 256 (one TMA box), data + parity-CRC rows <= threads, stages fit 113 KB (two CTAs per SM)
+    # or 200 KB (the one-CTA shape of four parity rows)
+    for text, G, threads in [("ec(8,2)", 7, 256), ("xor2", 32, 256), ("xor3", 20, 256), ("ec(3,2)", 16, 256), ("ec(4,2)", 12, 256),
+                             ("ec(6,2)", 9, 256), ("ec(5,3)", 8, 256), ("ec(6,3)", 8, 256), ("ec(8,4)", 8, 512)]:
         p = _plan(text, 128, 1024)
         assert (p.fused, p.stripes_per_unit, p.threads_per_cta) == (1, G, threads), text
         k = L.SliceType(text).k
-        assert p.stage_rows == G * k * 4 and p.stage_rows % 8 == 0 and p.smem_bytes <= 113 * 1024
+        assert p.stage_rows == G * k * 4 and p.stage_rows % 8 == 0 and p.smem_bytes <= (200 if threads == 512 else 113) * 1024
     # configs[2]: 512 contiguous 64 MiB chunks of ec(8,2) are whole stripes -> one flat run of 512*128 stripes
     p = _plan("ec(8,2)", 512, 1024)
-    assert (p.mode, p.units) == (1, 512 * 128 // 8)
+    assert (p.mode, p.units) == (1, -(-512 * 128 // 7))
     # configs[1]: ec(3,2), 342 stripes per chunk (the last one ragged): per-chunk units waste 352/342 - 1 = 2.9 % -> stay per chunk
     p = _plan("ec(3,2)", 1024, 1024)
     assert (p.mode, p.units) == (0, 1024 * 22)
@@ -189,7 +190,7 @@ def test_encode_unit_geometry_decisions():
     # padded strides cannot be flat; whole-stripe small chunks with a dense stride are
     assert _plan("ec(8,2)", 100, 16).mode == 1 and _plan("ec(8,2)", 100, 16, stride_blocks=20).mode == 2
     assert _plan("ec(8,2)", 1, 1024).mode == 0                      # a single chunk needs neither
-    # 37 MiB + 5 blocks of ec(8,2): 75 stripes, 80 slots = 6.7 % waste -> per chunk; xor3 4 MiB: 22 stripes in 20-stripe units -> striped
+    # 37 MiB + 5 blocks of ec(8,2): 75 stripes, 77 slots of 7 = 2.7 % waste -> per chunk; xor3 4 MiB: 22 stripes in 20-stripe units -> striped
     assert _plan("ec(8,2)", 219, 597).mode == 0 and _plan("xor3", 2048, 64).mode == 2
     # Cauchy goal (m = 4, k > 20) runs the bit-plane instantiation with 8 warps; more than four parity parts are encoded in
     # passes of four Cauchy rows over the same data (ec(4,5): 4 + 1 rows, ec(8,6): 4 + 2, ec(32,32): eight passes)
@@ -202,26 +203,27 @@ def test_encode_unit_geometry_decisions():
 
 def test_encode_unit_geometry_invariants_for_every_goal():
     """every xor / ec(k, m <= 4) goal, several chunk lengths and batch sizes: the planned geometry always satisfies what the
-    kernel assumes (one TMA box <= 256 rows and a multiple of 8, data + parity-CRC rows fit the CTA, stages fit 113 KB, the units
-    cover every stripe exactly once)"""
+    kernel assumes (one TMA box <= 256 rows and a multiple of 8, data + parity-CRC rows fit the CTA, stages fit 113 KB — 200 KB
+    for the one-CTA shape of four Vandermonde parity rows —, the units cover every stripe exactly once)"""
     goals = [f"xor{n}" for n in range(2, 10)] + [f"ec({k},{m})" for k in range(2, 33) for m in range(1, 5)]
     for text in goals:
         g = L.SliceType(text)
         cauchy = g.m == 4 and g.k > 20
         for n_chunks, nb, stride in [(1, 1024, None), (64, 1024, None), (500, 16, None), (33, 597, None), (7, 13, 16), (1000, 1, None), (3, g.k, None)]:
             p = _plan(text, n_chunks, nb, stride)
-            threads = 256 if (g.m >= 3 or cauchy) else 288
+            threads = 512 if (g.m == 4 and not cauchy) else 256
             pc0 = g.m if cauchy else g.m - 1
             if p.fused == 0:
                 # only when no unit fits: an odd k needs TWO stripes per unit for the 8-row alignment of the stage, and
-                # 2*k*4 data rows + 2*pc*4 parity-CRC rows exceed the CTA (ec(31,3), ec(29,4), ec(31,4)): generic kernels
+                # 2*k*4 data rows + 2*pc*4 parity-CRC rows exceed the CTA (ec(31,3): 264 > 256; the 16-warp CTA of four parity
+                # rows takes ec(29,4) and ec(31,4)): generic kernels
                 assert g.k % 2 == 1 and 2 * g.k * 4 + 2 * pc0 * 4 > threads, text
                 continue
             G, rows = p.stripes_per_unit, p.stage_rows
             pc = g.m if cauchy else g.m - 1
             assert G >= 1 and rows == G * g.k * 4 and rows <= 256 and rows % 8 == 0 and G * g.k <= 64
-            assert rows + G * pc * 4 <= p.threads_per_cta and p.threads_per_cta == (256 if (g.m >= 3 or cauchy) else 288)
-            assert p.smem_bytes <= 113 * 1024
+            assert rows + G * pc * 4 <= p.threads_per_cta and p.threads_per_cta == threads
+            assert p.smem_bytes <= (200 if threads == 512 else 113) * 1024
             pb = -(-nb // g.k)
             if p.mode == 0:
                 assert p.units == n_chunks * -(-pb // G)
