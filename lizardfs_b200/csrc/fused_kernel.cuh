@@ -200,26 +200,49 @@ __device__ __forceinline__ void stg_item(void *p, const uint32_t (&v)[W]) {
 	else asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v[0]) : "memory");
 }
 
+// The 64-word polynomial's lags 17, 20, 23, 26 form an arithmetic progression.  Their four pulls are replaced by ONE pull from an
+// auxiliary sequence  Y[v] = W'[v] ^ W'[v-3] ^ W'[v-6] ^ W'[v-9],  which itself costs one 3-input XOR per word through
+// Y[v] = Y[v-3] ^ W'[v] ^ W'[v-12]:   W'[u] = W[u] ^ W'[u-15] ^ Y[u-17] ^ W'[u-28] ^ W'[u-46] ^ W'[u-50] ^ W'[u-53]
+// is 7 operands = 3 LOP3, plus 1 for Y: 4 LOP3 per word instead of 5 (9 pulls + the word = 10 operands), at the price of the
+// ~18 live words of Y (static slots, v mod 32).  The window and the flush (fold_finish) are unchanged: Y is derived state.
+struct FoldAux {
+	uint32_t y[32];
+};
+#ifndef LZ_FOLD_AUX
+#define LZ_FOLD_AUX 1
+#endif
+
 template <int FW>
-__device__ __forceinline__ void fold_word(uint32_t (&win)[FW], int S, uint32_t w) {
-	uint32_t acc = w;
+__device__ __forceinline__ void fold_word(uint32_t (&win)[FW], FoldAux &aux, int S, uint32_t w) {
+	if constexpr (FW == 64 && LZ_FOLD_AUX) {
+		uint32_t acc, y;
+		// three 3-input XORs for the word, one for Y (written as LOP3 so that the operand grouping is the intended one)
+		asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(acc) : "r"(w), "r"(win[(S - 15) & 63]), "r"(aux.y[(S - 17) & 31]));
+		asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(acc) : "r"(acc), "r"(win[(S - 28) & 63]), "r"(win[(S - 46) & 63]));
+		asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(acc) : "r"(acc), "r"(win[(S - 50) & 63]), "r"(win[(S - 53) & 63]));
+		asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(y) : "r"(aux.y[(S - 3) & 31]), "r"(acc), "r"(win[(S - 12) & 63]));
+		aux.y[S & 31] = y;
+		win[S & 63] = acc;
+	} else {
+		uint32_t acc = w;
 #pragma unroll
-	for (int t = 0; t < FoldSpec<FW>::nlag; ++t) acc ^= win[(S - FoldSpec<FW>::lag(t)) & (FW - 1)];
-	win[S & (FW - 1)] = acc;
+		for (int t = 0; t < FoldSpec<FW>::nlag; ++t) acc ^= win[(S - FoldSpec<FW>::lag(t)) & (FW - 1)];
+		win[S & (FW - 1)] = acc;
+	}
 }
 
 // one pipeline step of a stream: 8 x 16 bytes of this row, window slots base .. base+31 (base is a multiple of 32).
 // Rows are 128-byte aligned, so the TMA 128-byte swizzle (chunk c of row r stored at chunk c ^ (r & 7)) is a pure
 // XOR on the shared address: row_addr_swz = row_addr ^ ((r & 7) << 4), chunk c at row_addr_swz ^ (c << 4).
 template <int FW>
-__device__ __forceinline__ void fold_step(uint32_t (&win)[FW], int base, uint32_t row_addr_swz) {
+__device__ __forceinline__ void fold_step(uint32_t (&win)[FW], FoldAux &aux, int base, uint32_t row_addr_swz) {
 #pragma unroll
 	for (int c = 0; c < 8; ++c) {
 		const uint4 v = lds128(row_addr_swz ^ (c << 4));
-		fold_word<FW>(win, base + 4 * c + 0, v.x);
-		fold_word<FW>(win, base + 4 * c + 1, v.y);
-		fold_word<FW>(win, base + 4 * c + 2, v.z);
-		fold_word<FW>(win, base + 4 * c + 3, v.w);
+		fold_word<FW>(win, aux, base + 4 * c + 0, v.x);
+		fold_word<FW>(win, aux, base + 4 * c + 1, v.y);
+		fold_word<FW>(win, aux, base + 4 * c + 2, v.z);
+		fold_word<FW>(win, aux, base + 4 * c + 3, v.w);
 	}
 }
 
@@ -369,6 +392,7 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 	const bool warp_reads_stage = cw < n_stage_warps;
 
 	uint32_t win[FW];
+	FoldAux aux;
 	uint32_t it = 0;               // this CTA's global step counter
 	uint32_t st = 0, ph = 0;       // data stage index / phase parity of `it`
 	uint32_t pst = 0, pph = 0;     // parity ring index / phase parity of `it`
@@ -381,6 +405,8 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 		const uint32_t next_c = next_unit / p.units_per_chunk, next_gi = next_unit % p.units_per_chunk;
 #pragma unroll
 		for (int i = 0; i < FW; ++i) win[i] = 0;
+#pragma unroll
+		for (int i = 0; i < 32; ++i) aux.y[i] = 0;
 
 		for (int step0 = 0; step0 < kStepsPerUnit; step0 += FW / 32) {
 #pragma unroll
@@ -465,7 +491,7 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 				if (PC > 0 && warp_has_prow && !LZ_PROBE(2)) mbar_wait(a_pfull + 8 * pst, pph);
 				if (has_stream && !(GENERIC && is_data_row && p.skip_data_crc) && !LZ_PROBE(4)) {
 					const uint32_t rowp = row_addr0 + (is_data_row ? st : pst) * row_stride;
-					fold_step<FW>(win, sub * 32, rowp);
+					fold_step<FW>(win, aux, sub * 32, rowp);
 				}
 				__syncwarp();
 				if (STRIPED) {
@@ -634,6 +660,7 @@ fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 	const bool warp_has_items = cw < n_gf_warps;
 
 	uint32_t win[kRecoverFW];
+	FoldAux aux;
 	uint32_t it = 0, st = 0, ph = 0;
 	for (uint32_t unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
 		const uint32_t c = unit / p.units_per_chunk, gi = unit % p.units_per_chunk;
@@ -642,6 +669,8 @@ fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 		const uint32_t next_c = next_unit / p.units_per_chunk, next_gi = next_unit % p.units_per_chunk;
 #pragma unroll
 		for (int i = 0; i < kRecoverFW; ++i) win[i] = 0;
+#pragma unroll
+		for (int i = 0; i < 32; ++i) aux.y[i] = 0;
 
 		for (int step0 = 0; step0 < kStepsPerUnit; step0 += kRecoverFW / 32) {
 #pragma unroll
@@ -753,7 +782,7 @@ fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 				// ---------------- CRC role: linear CRC of every input row ----------------
 				if (verify) {
 					const uint32_t rowp = row_addr0 + st * stage_bytes;
-					fold_step<kRecoverFW>(win, sub * 32, rowp);
+					fold_step<kRecoverFW>(win, aux, sub * 32, rowp);
 				}
 				__syncwarp();
 				if (lane == 0 && mbar_arrive_is_last(a_empty + 8 * st) && it + kRecoverStages < total_steps) {
