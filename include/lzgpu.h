@@ -42,6 +42,7 @@ extern "C" {
 #define LZGPU_MAX_DATA 32            /* slice_traits::ec::kMaxDataCount */
 #define LZGPU_MAX_PARITY 32          /* slice_traits::ec::kMaxParityCount */
 #define LZGPU_MAX_PARTS 64
+#define LZGPU_FAKE_CRC 0xFEDCBA98u   /* what mycrc32 returns in a reference built without ENABLE_CRC (src/common/crc.cc:28-31) */
 
 /* status codes (0 = OK).  LZGPU_ERR_CRC is what callers map to LIZARDFS_ERROR_CRC
  * (hddspacemgr.cc:1918-1920) / ChunkCrcException (read_operation_executor.cc:262-264). */
@@ -330,6 +331,12 @@ uint32_t lzgpu_mycrc32_zeroblock(uint32_t crc, uint32_t zeros);                 
 uint32_t lzgpu_mycrc32_zeroexpanded(uint32_t crc, const uint8_t *block, uint32_t leng, uint32_t zeros);
 uint32_t lzgpu_mycrc32_xorblocks(uint32_t crc, uint32_t crcblock1, uint32_t crcblock2, uint32_t leng);
 void lzgpu_recompute_crc_if_block_empty(const uint8_t *block, uint32_t *crc);       /* crc.cc:235-243 */
+/* The reference's ENABLE_CRC build switch (src/common/crc.cc:28-41): with CRCs disabled mycrc32 / mycrc32_combine return
+ * LZGPU_FAKE_CRC, every CRC the batched calls emit is that constant and stored CRCs are compared with it (a mismatch can only
+ * come from a peer that does compute CRCs).  Process-wide; default enabled; LZGPU_ENABLE_CRC=0 in the environment disables.
+ * lzgpu_write_blocks* refuse to run (LZGPU_ERR_ARG) while CRCs are disabled. */
+void lzgpu_set_crc_enabled(int enabled);
+int lzgpu_crc_enabled(void);
 /* mycrc32(0, block + from, to - from) from mycrc32 of the whole 64 KiB block when every byte outside [from, to) is zero
  * (host scalar, the combine identity run backwards): lets sub-block writes ride the whole-block batched kernels. */
 uint32_t lzgpu_mycrc32_subrange(uint32_t crc_of_padded_block, uint32_t from, uint32_t to);

@@ -91,6 +91,8 @@ SIGNATURES = {
     "lzgpu_mycrc32_zeroblock": (_u32, [_u32, _u32]),
     "lzgpu_mycrc32_zeroexpanded": (_u32, [_u32, _vp, _u32, _u32]),
     "lzgpu_mycrc32_xorblocks": (_u32, [_u32, _u32, _u32, _u32]),
+    "lzgpu_set_crc_enabled": (None, [_int]),
+    "lzgpu_crc_enabled": (_int, []),
     "lzgpu_mycrc32_subrange": (_u32, [_u32, _u32, _u32]),
     "lzgpu_recompute_crc_if_block_empty": (None, [_vp, C.POINTER(_u32)]),
     "gf_mul": (C.c_ubyte, [C.c_ubyte, C.c_ubyte]),

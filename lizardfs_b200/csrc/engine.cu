@@ -436,6 +436,14 @@ int lz_crc_blocks(lzgpu_ctx *ctx, const void *base, unsigned long long n_blocks,
 	return LZGPU_OK;
 }
 
+static int fill_crc(lzgpu_ctx *ctx, void *d_crc, size_t row_stride, size_t width, size_t rows, cudaStream_t st) {
+	if (!width || !rows) return LZGPU_OK;
+	fill_u32_2d_kernel<<<grid_for(ctx, width * rows, 256, 4), 256, 0, st>>>(static_cast<uint32_t *>(d_crc), row_stride, width, rows, LZGPU_FAKE_CRC);
+	CUDA_TRY(cudaGetLastError());
+	ctx->stats.kernel_launches++;
+	return LZGPU_OK;
+}
+
 static int check_goal(const lzgpu_goal *g) {
 	if (!lzgpu_goal_valid(g)) {
 		lz_set_error("invalid goal");
@@ -500,6 +508,7 @@ static int encode_enqueue(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chu
 	rc = lz_fused_encode(ctx, goal, n_chunks, nb, d_data, chunk_stride, d_parity, parity_stride, d_crc, crc_stride, st);
 	if (rc != LZGPU_NOT_HANDLED) {
 		if (rc == LZGPU_OK) ctx->stats.chunks_encoded += n_chunks;
+		if (rc == LZGPU_OK && !lzgpu_crc_enabled()) rc = fill_crc(ctx, d_crc, crc_stride, nb + static_cast<size_t>(goal->m) * pb, n_chunks, st);
 		return rc;
 	}
 	// generic route: GF dot product over the chunk-order layout, then CRC of data and parity blocks
@@ -529,6 +538,7 @@ static int encode_enqueue(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chu
 	                   parity_stride, B, B, static_cast<uint32_t *>(d_crc) + nb, crc_stride, st);
 	if (rc) return rc;
 	ctx->stats.chunks_encoded += n_chunks;
+	if (!lzgpu_crc_enabled()) return fill_crc(ctx, d_crc, crc_stride, nb + static_cast<size_t>(goal->m) * pb, n_chunks, st);
 	return LZGPU_OK;
 }
 
@@ -666,19 +676,32 @@ static int recover_enqueue(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_ch
 		if ((rc = lz_status_acquire(ctx, &tk->slot))) return rc;
 		CUDA_TRY(cudaMemsetAsync(tk->slot.d, 0xff, sizeof(unsigned long long) * LZGPU_MAX_PARTS, st));
 	}
+	const void *const *crc_for_kernels = d_part_crc;
+	if (any_crc && !lzgpu_crc_enabled()) {
+		// CRC-disabled build mode: a stored CRC is valid iff it is the constant; the kernels then run without verification
+		const unsigned long long nblk = static_cast<unsigned long long>(n_chunks) * pb;
+		for (int i = 0; i < n; ++i) {
+			if (erased[i] || !d_part_crc[i]) continue;
+			crc_compare_const_kernel<<<grid_for(ctx, nblk, 256, 4), 256, 0, st>>>(static_cast<const uint32_t *>(d_part_crc[i]), nblk, LZGPU_FAKE_CRC, 0, tk->slot.d + i);
+			CUDA_TRY(cudaGetLastError());
+			ctx->stats.kernel_launches++;
+		}
+		crc_for_kernels = nullptr;
+	}
 
 	// 0. fused route: verify + rebuild the erased data parts + chunk-order image in one pass over the inputs
 	{
 		bool fused_verifying = false;
-		rc = lz_fused_recover(ctx, goal, n_chunks, nb, d_parts, part_stride, d_part_crc, want, d_out, d_chunk_out, chunk_out_stride, st,
+		rc = lz_fused_recover(ctx, goal, n_chunks, nb, d_parts, part_stride, crc_for_kernels, want, d_out, d_chunk_out, chunk_out_stride, st,
 		                      tk->slot.d, &fused_verifying);
 		if (rc != LZGPU_NOT_HANDLED) {
 			if (rc) { ticket_drop(ctx, tk); return rc; }
 			ctx->stats.chunks_recovered += n_chunks;
 			if (any_crc) {
-				tk->fused = true;
-				tk->n_words = 1;
-				CUDA_TRY(cudaMemcpyAsync(tk->slot.h, tk->slot.d, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+				tk->fused = crc_for_kernels != nullptr;
+				tk->n_words = tk->fused ? 1 : n;
+				tk->blocks = pb;
+				CUDA_TRY(cudaMemcpyAsync(tk->slot.h, tk->slot.d, sizeof(unsigned long long) * tk->n_words, cudaMemcpyDeviceToHost, st));
 			}
 			return LZGPU_OK;
 		}
@@ -686,7 +709,7 @@ static int recover_enqueue(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_ch
 
 	// 1. verify the stored CRC of every block of every part that is read
 	TmpBuf tmp_crc(ctx, st);
-	if (any_crc) {
+	if (any_crc && crc_for_kernels) {
 		const unsigned long long nblk = static_cast<unsigned long long>(n_chunks) * pb;
 		if ((rc = tmp_crc.alloc(nblk * 4))) { ticket_drop(ctx, tk); return rc; }
 		for (int i = 0; i < n; ++i) {
@@ -1014,9 +1037,13 @@ static int convert_enqueue(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_go
 				if ((rc = t_vcrc.alloc(nblk * 4))) return rc;
 				if ((rc = lz_status_acquire(ctx, &tk->slot))) return rc;
 				CUDA_TRY(cudaMemsetAsync(tk->slot.d, 0xff, sizeof(unsigned long long) * LZGPU_MAX_PARTS, st));
-				if ((rc = crc_of_parts(ctx, image, n_chunks, nb, image_stride, t_vcrc.p, st))) { ticket_drop(ctx, tk); return rc; }
-				crc_compare_kernel<<<grid_for(ctx, nblk, 256, 4), 256, 0, st>>>(static_cast<const uint32_t *>(t_vcrc.p), static_cast<const uint32_t *>(d_part_crc[0]),
-				                                                              nblk, kCrcZeroBlock64K, 0, 0, tk->slot.d);
+				if (!lzgpu_crc_enabled()) {
+					crc_compare_const_kernel<<<grid_for(ctx, nblk, 256, 4), 256, 0, st>>>(static_cast<const uint32_t *>(d_part_crc[0]), nblk, LZGPU_FAKE_CRC, 0, tk->slot.d);
+				} else {
+					if ((rc = crc_of_parts(ctx, image, n_chunks, nb, image_stride, t_vcrc.p, st))) { ticket_drop(ctx, tk); return rc; }
+					crc_compare_kernel<<<grid_for(ctx, nblk, 256, 4), 256, 0, st>>>(static_cast<const uint32_t *>(t_vcrc.p), static_cast<const uint32_t *>(d_part_crc[0]),
+					                                                              nblk, kCrcZeroBlock64K, 0, 0, tk->slot.d);
+				}
 				CUDA_TRY(cudaGetLastError());
 				ctx->stats.kernel_launches++;
 				tk->fused = false;
@@ -1084,7 +1111,10 @@ static int convert_enqueue(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_go
 		}
 	}
 	// ChunkReplicator::replicate computes mycrc32 of every rebuilt block (chunk_replicator.cc:186-192)
-	if (d_out_crc) {
+	if (d_out_crc && !lzgpu_crc_enabled()) {
+		for (int i = 0; i < nd; ++i)
+			if (want[i] && d_out_crc[i] && (rc = fill_crc(ctx, d_out_crc[i], pbd, pbd, n_chunks, st))) { ticket_drop(ctx, tk); return rc; }
+	} else if (d_out_crc) {
 		if (d_encode_crc) {
 			// the encode pass that produced the parity already checksummed every data and parity block of the destination slice
 			CrcPartsArgs a{};
@@ -1360,6 +1390,7 @@ extern "C" int lzgpu_crc_blocks_dev(lzgpu_ctx *ctx, const void *d_data, size_t n
 	if (block_len == 0 || block_len > LZGPU_BLOCK_SIZE || block_stride < block_len) { lz_set_error("crc_blocks: bad block_len/stride"); return LZGPU_ERR_ARG; }
 	DeviceGuard g(ctx->device);
 	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+	if (!lzgpu_crc_enabled()) return fill_crc(ctx, d_crc_out, n_blocks, n_blocks, 1, st);
 	if (block_len == LZGPU_BLOCK_SIZE && block_stride == LZGPU_BLOCK_SIZE) {
 		int rc = lz_fused_crc(ctx, d_data, n_blocks, n_blocks, 0, d_crc_out, 0, st);
 		if (rc != LZGPU_NOT_HANDLED) return rc;
@@ -1429,11 +1460,22 @@ static int verify_common(lzgpu_ctx *ctx, const uint8_t *h_data, size_t n_blocks,
 		CUDA_TRY(cudaMemcpy2DAsync(d_s, 4, reinterpret_cast<const uint8_t *>(h_stored) + b0 * stored_stride_bytes, stored_stride_bytes, 4, n,
 		                           cudaMemcpyDefault, st));
 		CUDA_TRY(cudaMemsetAsync(slot.d, 0xff, sizeof(unsigned long long), st));
-		if ((rc = lzgpu_crc_blocks_dev(ctx, d_in, n, block_len, dstride, d_c, st))) return rc;
-		crc_compare_kernel<<<grid_for(ctx, n, 256, 4), 256, 0, st>>>(static_cast<const uint32_t *>(d_c), static_cast<const uint32_t *>(d_s), n,
-		                                                            lz::crc_of_zeros(block_len), sparse_rule, big_endian, slot.d);
-		CUDA_TRY(cudaGetLastError());
-		ctx->stats.kernel_launches++;
+		const int crc_off = lzgpu_crc_enabled() ? 0 : 1;
+		if (crc_off && !sparse_rule) {
+			crc_compare_const_kernel<<<grid_for(ctx, n, 256, 4), 256, 0, st>>>(static_cast<const uint32_t *>(d_s), n, LZGPU_FAKE_CRC, big_endian, slot.d);
+			CUDA_TRY(cudaGetLastError());
+			ctx->stats.kernel_launches++;
+		} else {
+			// (with CRCs disabled and the sparse rule on, the real CRCs are still needed to find the all-zero candidates)
+			rc = LZGPU_NOT_HANDLED;
+			if (block_len == LZGPU_BLOCK_SIZE && dstride == LZGPU_BLOCK_SIZE) rc = lz_fused_crc(ctx, d_in, n, n, 0, d_c, 0, st);
+			if (rc == LZGPU_NOT_HANDLED) rc = lz_crc_blocks(ctx, d_in, n, n, 0, dstride, block_len, d_c, 0, st);
+			if (rc) return rc;
+			crc_compare_kernel<<<grid_for(ctx, n, 256, 4), 256, 0, st>>>(static_cast<const uint32_t *>(d_c), static_cast<const uint32_t *>(d_s), n,
+			                                                            lz::crc_of_zeros(block_len), sparse_rule, big_endian, slot.d, crc_off);
+			CUDA_TRY(cudaGetLastError());
+			ctx->stats.kernel_launches++;
+		}
 		if (sparse_rule) {
 			// holes accepted on their CRC are re-read and must really be all zero (crc.cc:235-243)
 			const unsigned grid = static_cast<unsigned>(std::min<size_t>(n, static_cast<size_t>(ctx->sm_count) * 8));
@@ -1497,6 +1539,7 @@ extern "C" int lzgpu_write_blocks_dev(lzgpu_ctx *ctx, void *d_blocks, void *d_st
                                        int sparse_rule, void *stream) {
 	NvtxScope nvtx_scope("lzgpu::write_blocks_dev");
 	if (!ctx || !d_blocks || !d_stored_crc || !d_writes || (reinterpret_cast<uintptr_t>(d_blocks) & 15)) return LZGPU_ERR_ARG;
+	if (!lzgpu_crc_enabled()) { lz_set_error("write_blocks: not available while CRCs are disabled (lzgpu_set_crc_enabled)"); return LZGPU_ERR_ARG; }
 	if (n_writes == 0) return LZGPU_OK;
 	DeviceGuard g(ctx->device);
 	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
@@ -1721,6 +1764,7 @@ extern "C" void lzgpu_block_xor(uint8_t *dest, const uint8_t *source, size_t siz
 }
 
 extern "C" uint32_t lzgpu_mycrc32(uint32_t crc, const uint8_t *block, uint32_t leng) {
+	if (!lzgpu_crc_enabled()) return LZGPU_FAKE_CRC;  // crc.cc:30-32
 	if (leng == 0) return crc;
 	lzgpu_ctx *ctx = need_default("mycrc32");
 	// split into 64 KiB pieces (one warp each), then fold the pieces together with the

@@ -2,6 +2,8 @@
 // checked against the oracle and the compiled reference in tests/test_host_math.py.
 #include "host_math.h"
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
 
 #include "fused_plan.h"
 
@@ -239,7 +241,25 @@ int lzgpu_rs_recovery_matrix(int k, int m, const uint8_t *erased, const uint8_t 
 	return lz::rs_recovery_matrix(k, m, erased, wanted, matrix, nullptr);
 }
 
+// A reference built without ENABLE_CRC (src/common/crc.cc:28-41) has mycrc32() and mycrc32_combine() return the constant
+// 0xFEDCBA98 and never catches a mismatch; lzgpu_set_crc_enabled(0) (or LZGPU_ENABLE_CRC=0 in the environment) is that build
+// mode here: the scalar calls return the constant, every CRC the batched calls emit is the constant, and stored CRCs are
+// compared with it.  Process-wide, like the compile-time switch it mirrors; meant to be set once at start-up.
+static std::atomic<int> g_crc_mode{-1};  // -1: not decided yet (environment), 0 disabled, 1 enabled
+int lzgpu_crc_enabled(void) {
+	int m = g_crc_mode.load();
+	if (m < 0) {
+		const char *e = std::getenv("LZGPU_ENABLE_CRC");
+		m = (e && std::atoi(e) == 0) ? 0 : 1;
+		g_crc_mode.store(m);
+	}
+	return m;
+}
+void lzgpu_set_crc_enabled(int enabled) { g_crc_mode.store(enabled ? 1 : 0); }
+
 uint32_t lzgpu_mycrc32_combine(uint32_t crc1, uint32_t crc2, uint32_t leng2) {
+	if (!lzgpu_crc_enabled()) return LZGPU_FAKE_CRC;
+
 	return lz::crc_combine(crc1, crc2, leng2);
 }
 uint32_t lzgpu_mycrc32_zeroblock(uint32_t crc, uint32_t zeros) {

@@ -115,3 +115,40 @@ def test_isal_ec_encode_data(oracle):
         got = L.ec_encode_data(ln, tables, src, dests)
         want = oracle.ec_encode_data(tables, src, dests)
         assert all((a == b).all() for a, b in zip(got, want))
+
+
+def test_crc_disabled_build_mode(oracle):
+    """The reference's ENABLE_CRC switch (src/common/crc.cc:28-41): without it mycrc32 / mycrc32_combine return 0xFEDCBA98.
+    lzgpu_set_crc_enabled(0) is that build mode: scalar calls return the constant, batched calls emit it for every block and
+    accept exactly it as a stored CRC; parity bytes are unaffected."""
+    lib = L._lib.load()
+    eng = L.Engine(0)
+    try:
+        lib.lzgpu_set_crc_enabled(0)
+        assert lib.lzgpu_crc_enabled() == 0
+        data = np.random.default_rng(7).integers(0, 256, size=(2, 16 * 65536), dtype=np.uint8)
+        assert L.mycrc32(0, data[0, :1000]) == 0xFEDCBA98 and L.mycrc32_combine(1, 2, 3) == 0xFEDCBA98
+        goal = L.SliceType("ec(3,2)")
+        parity, crc = eng.encode_chunks(goal, data)
+        assert (crc == 0xFEDCBA98).all()
+        p_ref, _ = oracle.encode_chunk(1, 3, 2, data[0])
+        assert (parity[0] == p_ref).all()
+        assert (eng.crc_blocks(data[0].reshape(-1, 65536)) == 0xFEDCBA98).all()
+        # degraded read: stored CRCs equal to the constant pass, anything else is a mismatch
+        from tests import _oracle as O
+        pb = 6
+        per = [O.split_parts(data[c], 3)[0] for c in range(2)]
+        parts = [np.stack([per[c][j] for c in range(2)]) for j in range(3)] + [np.ascontiguousarray(parity[:, r]) for r in range(2)]
+        good = [np.full((2, pb), 0xFEDCBA98, dtype=np.uint32) for _ in range(5)]
+        avail = [None, parts[1], parts[2], parts[3], None]
+        out, _ = eng.recover_chunks(goal, 16, avail, part_crc=[None, good[1], good[2], good[3], None])
+        assert (out[0] == parts[0]).all()
+        bad = [g.copy() for g in good]
+        bad[2][1, 4] = 0x12345678
+        with pytest.raises(L.ChunkCrcError) as e:
+            eng.recover_chunks(goal, 16, avail, part_crc=[None, bad[1], bad[2], bad[3], None])
+        assert e.value.where == (1, 2, 4)
+    finally:
+        lib.lzgpu_set_crc_enabled(1)
+        eng.close()
+    assert L.mycrc32(0, b"a") == 0xE8B7BE43
