@@ -151,4 +151,4 @@ def test_crc_disabled_build_mode(oracle):
     finally:
         lib.lzgpu_set_crc_enabled(1)
         eng.close()
-    assert L.mycrc32(0, b"a") == 0xE8B7BE43
+    assert L.mycrc32(0, np.frombuffer(b"a", dtype=np.uint8)) == 0xE8B7BE43
