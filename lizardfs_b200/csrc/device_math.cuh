@@ -84,8 +84,9 @@ __device__ __forceinline__ uint32_t gf_x8_add(uint32_t v, uint32_t d) { return g
 // Per packed word and coefficient: 8 LOP3 (masks) + 4 LOP3 (3-input XORs) on the ALU pipe and 15 IMAD/IMAD.HI on the FMA pipe;
 // some bits may use a funnel shift instead (template parameter NS below) to level the two pipes.
 struct CoefPlanes {
-	uint32_t lo[8];  // lo[0] = 0
-	uint32_t hi[8];  // hi[0] = c
+	uint32_t lo[8];     // lo[0] = 0
+	uint32_t hi[8];     // hi[0] = c
+	uint32_t plane[8];  // P_b itself, for the funnel-shift form
 };
 
 // host or device: fill the planes of coefficient c (x^8 = x^4+x^3+x^2+1, reference galois_coeff.h:30-32)
@@ -94,6 +95,7 @@ __host__ __device__ inline void coef_planes_set(CoefPlanes &out, uint32_t c) {
 	for (int b = 0; b < 8; ++b) {
 		out.lo[b] = b ? ((v & ((1u << b) - 1u)) << (32 - b)) : 0u;
 		out.hi[b] = v >> b;
+		out.plane[b] = v;
 		v = ((v << 1) ^ ((v & 0x80u) ? 0x1du : 0u)) & 0xffu;
 	}
 }
@@ -105,7 +107,7 @@ __host__ __device__ inline void coef_planes_set(CoefPlanes &out, uint32_t c) {
 template <int NS>
 __device__ __forceinline__ uint32_t gf_mac_term(uint32_t v, const CoefPlanes &c, int b) {
 	if (b == 0) return (v & 0x01010101u) * c.hi[0];
-	if (b >= 8 - NS) return ((v >> b) & 0x01010101u) * ((c.hi[b] << b) | (c.lo[b] >> (32 - b)));
+	if (b >= 8 - NS) return ((v >> b) & 0x01010101u) * c.plane[b];
 	const uint32_t x = v & (0x01010101u << b);
 	uint32_t up, r;
 	asm("mul.lo.u32 %0, %1, %2;" : "=r"(up) : "r"(x), "r"(c.hi[b]));

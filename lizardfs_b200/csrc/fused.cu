@@ -602,7 +602,11 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 	}
 	if (*verifying && !d_first_bad) return LZGPU_NOT_HANDLED;  // (callers that pass stored CRCs always pass the result word, initialised to ~0)
 	const size_t smem = static_cast<size_t>(n_stages) * K * G * 4 * kStepBytes + 16 * n_stages + 64;
-	const bool row0 = p.par_row[0] == 0, row01 = row0 && e >= 2 && p.par_row[1] == 1;
+	// "rows 0, 1, .., e-1 in use" (the first e parity parts are the available ones — the common case): instantiations that
+	// multiply row r by 2^r in one step
+	bool consecutive = true;
+	for (uint32_t r = 0; r < e; ++r) consecutive &= p.par_row[r] == r;
+	const bool row0 = p.par_row[0] == 0, row01 = e >= 2 && consecutive;
 	switch (e) {
 		case 1:
 			if (row0) return k8 ? launch_recover<1, 8, 0>(ctx, maps, p, smem, st, geo) : launch_recover<1, 0, 0>(ctx, maps, p, smem, st, geo);

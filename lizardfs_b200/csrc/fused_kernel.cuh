@@ -212,9 +212,9 @@ struct FoldAux {
 #define LZ_FOLD_AUX 1
 #endif
 
-template <int FW>
+template <int FW, bool AUX = true>
 __device__ __forceinline__ void fold_word(uint32_t (&win)[FW], FoldAux &aux, int S, uint32_t w) {
-	if constexpr (FW == 64 && LZ_FOLD_AUX) {
+	if constexpr (FW == 64 && LZ_FOLD_AUX && AUX) {
 		uint32_t acc, y;
 		// three 3-input XORs for the word, one for Y (written as LOP3 so that the operand grouping is the intended one)
 		asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(acc) : "r"(w), "r"(win[(S - 15) & 63]), "r"(aux.y[(S - 17) & 31]));
@@ -234,15 +234,15 @@ __device__ __forceinline__ void fold_word(uint32_t (&win)[FW], FoldAux &aux, int
 // one pipeline step of a stream: 8 x 16 bytes of this row, window slots base .. base+31 (base is a multiple of 32).
 // Rows are 128-byte aligned, so the TMA 128-byte swizzle (chunk c of row r stored at chunk c ^ (r & 7)) is a pure
 // XOR on the shared address: row_addr_swz = row_addr ^ ((r & 7) << 4), chunk c at row_addr_swz ^ (c << 4).
-template <int FW>
+template <int FW, bool AUX = true>
 __device__ __forceinline__ void fold_step(uint32_t (&win)[FW], FoldAux &aux, int base, uint32_t row_addr_swz) {
 #pragma unroll
 	for (int c = 0; c < 8; ++c) {
 		const uint4 v = lds128(row_addr_swz ^ (c << 4));
-		fold_word<FW>(win, aux, base + 4 * c + 0, v.x);
-		fold_word<FW>(win, aux, base + 4 * c + 1, v.y);
-		fold_word<FW>(win, aux, base + 4 * c + 2, v.z);
-		fold_word<FW>(win, aux, base + 4 * c + 3, v.w);
+		fold_word<FW, AUX>(win, aux, base + 4 * c + 0, v.x);
+		fold_word<FW, AUX>(win, aux, base + 4 * c + 1, v.y);
+		fold_word<FW, AUX>(win, aux, base + 4 * c + 2, v.z);
+		fold_word<FW, AUX>(win, aux, base + 4 * c + 3, v.w);
 	}
 }
 
@@ -612,7 +612,12 @@ struct RecoverParams {
 __host__ __device__ constexpr int recover_stages(int geo) { return geo == 1 ? 3 : 6; }
 __host__ __device__ constexpr int recover_threads(int geo) { return geo == 2 ? 512 : kFusedThreads; }
 
-template <int E, int KT, int R0, int R1, int kRecoverFW, int GEO = 0>
+#ifndef LZ_RW3
+#define LZ_RW3 2   // words per GF item for three or four erased parts on the 16-warp geometry (narrower items = fewer live accumulators)
+#endif
+__host__ __device__ constexpr int recover_item_words(int e, int geo) { return (geo == 2 && e >= 3) ? LZ_RW3 : 4; }
+
+template <int E, int KT, int R0, int R1, int kRecoverFW, int GEO = 0, int W = recover_item_words(E, GEO)>
 __global__ void __launch_bounds__(recover_threads(GEO), GEO == 1 ? 2 : 1)
 fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_constant__ RecoverParams p) {
 	constexpr int kThreads = recover_threads(GEO);
@@ -628,7 +633,11 @@ fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 	const uint32_t a_full = misc, a_empty = a_full + 8 * kRecoverStages;
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, cw = tid >> 5;
-	const uint32_t n_items = 32 * G;
+	constexpr uint32_t CPI = 32 / W;
+	// form of the bit-plane multiply: the in-place form (NS = 2: 1 ALU + 2 FMA ops per bit) where registers allow, the funnel-shift
+	// form (NS = 7: one temporary less per term) on the two-CTA geometry with its 96 registers
+	constexpr int kMacNS = GEO == 1 ? 7 : 2;
+	const uint32_t n_items = 4 * CPI * G;
 	const uint32_t n_gf_warps = (min(n_items, (uint32_t)kThreads) + 31) / 32;
 	const uint32_t n_stage_warps = max((ROWS + 31) / 32, n_gf_warps);
 	const uint32_t my_units = blockIdx.x < p.total_units ? (p.total_units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -682,34 +691,43 @@ fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 				// ---------------- GF role: syndromes, solve, scatter ----------------
 				if (warp_has_items) {
 					for (uint32_t item = tid; item < n_items; item += kThreads) {
-						const uint32_t col = item & 7, q = (item >> 3) & 3, g = item >> 5;
+						const uint32_t col = item % CPI, q = (item / CPI) & 3, g = item / (4 * CPI);
+						const uint32_t c16 = (col * W) >> 2, sub = ((col * W) & 3) << 2;
 						const uint32_t r0 = g * 4 + q;   // row inside every slot region; region bases are multiples of 8 rows
-						const uint32_t a_item = (stage + r0 * kStepBytes) ^ ((col ^ (r0 & 7)) << 4);
+						const uint32_t a_item = ((stage + r0 * kStepBytes) ^ ((c16 ^ (r0 & 7)) << 4)) + sub;
 						const uint32_t stripe = stripe0 + g;
-						const unsigned long long in_block = (static_cast<unsigned long long>(q) << 14) + step * kStepBytes + (col << 4);
+						const unsigned long long in_block = (static_cast<unsigned long long>(q) << 14) + step * kStepBytes + col * (4 * W);
 						uint8_t *img = p.image ? p.image + c * p.image_stride + in_block : nullptr;
-						uint32_t acc[E][4];
+						uint32_t acc[E][W];
 #pragma unroll
-						for (int r = 0; r < E; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0;
+						for (int r = 0; r < E; ++r)
+#pragma unroll
+							for (int w = 0; w < W; ++w) acc[r][w] = 0;
 #pragma unroll
 						for (int j = static_cast<int>(K) - 1; j >= 0; --j) {
 							const uint32_t sl = p.slot_of_data[j];
-							uint4 v = make_uint4(0, 0, 0, 0);
+							uint32_t v[W];
+#pragma unroll
+							for (int w = 0; w < W; ++w) v[w] = 0;
 							if (sl != 0xff) {
-								v = lds128(a_item + sl * region_bytes);
+								lds_item<W>(a_item + sl * region_bytes, v);
 								const uint32_t b = stripe * K + j;
-								if (img && b < p.nb) st_stream(reinterpret_cast<uint4 *>(img + (static_cast<unsigned long long>(b) << 16)), v);
+								if (img && b < p.nb) stg_item<W>(img + (static_cast<unsigned long long>(b) << 16), v);
 							}
 #pragma unroll
 							for (int r = 0; r < E; ++r) {
-								const int fixed = r == 0 ? R0 : (r == 1 ? R1 : -1);
+								// (R0, R1) = (0, 1): the host guarantees that the parity rows in use are 0, 1, .., E-1, so row r multiplies
+								// by 2^r in one step; otherwise only row 0 may be known at compile time
+								const int fixed = (R0 == 0 && R1 == 1) ? r : (r == 0 ? R0 : -1);
 								const uint32_t dbl = fixed >= 0 ? static_cast<uint32_t>(fixed) : p.par_row[r];
 #pragma unroll
-								for (int w = 0; w < 4; ++w) {
+								for (int w = 0; w < W; ++w) {
 									uint32_t a = acc[r][w];
-									const uint32_t d = (w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w);
+									const uint32_t d = v[w];
 									if (fixed == 0) a ^= d;
 									else if (fixed == 1) a = gf_x2_add(a, d);
+									else if (fixed == 2) a = gf_x4_add(a, d);
+									else if (fixed == 3) a = gf_x8_add(a, d);
 									else {
 										for (uint32_t t = 0; t < dbl; ++t) a = gf_x2(a);
 										a ^= d;
@@ -721,60 +739,69 @@ fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 						// S_r = acc_r ^ p_r
 #pragma unroll
 						for (int r = 0; r < E; ++r) {
-							const uint4 pv = lds128(a_item + p.par_slot[r] * region_bytes);
-							acc[r][0] ^= pv.x; acc[r][1] ^= pv.y; acc[r][2] ^= pv.z; acc[r][3] ^= pv.w;
+							uint32_t pv[W];
+							lds_item<W>(a_item + p.par_slot[r] * region_bytes, pv);
+#pragma unroll
+							for (int w = 0; w < W; ++w) acc[r][w] ^= pv[w];
 						}
 						if (E == 2 && R0 == 0 && R1 == 1 && KT == 0) {
 							// (runtime-k shapes only: for the k = 8 instantiation the two bit-plane multiplies measured 5 % faster)
 							// RAID-6 elimination: S0 = d0 ^ d1, S1 = 2^x0 d0 ^ 2^x1 d1  =>  (2^x0 ^ 2^x1) d1 = S1 ^ 2^x0 S0, d0 = S0 ^ d1:
 							// ONE general multiply per word (w[1] = planes of (2^x0 ^ 2^x1)^-1) and x0 doublings (x0 is the smaller
 							// index; more than four doublings cost more than the bit-plane multiply by 2^x0, w[0]).
-							uint32_t d0[4], d1[4];
+							uint32_t d0[W], d1[W];
 #pragma unroll
-							for (int w = 0; w < 4; ++w) {
+							for (int w = 0; w < W; ++w) {
 								uint32_t t = acc[0][w];
 								if (p.raid6_dbl != 0xffu) {
 									for (uint32_t i = 0; i < p.raid6_dbl; ++i) t = gf_x2(t);
 								} else {
-									t = gf_mac(0u, t, p.w[0]);
+									t = gf_mac<kMacNS>(0u, t, p.w[0]);
 								}
-								d1[w] = gf_mac(0u, acc[1][w] ^ t, p.w[1]);
+								d1[w] = gf_mac<kMacNS>(0u, acc[1][w] ^ t, p.w[1]);
 								d0[w] = acc[0][w] ^ d1[w];
 							}
 #pragma unroll
 							for (int x = 0; x < 2; ++x) {
-								const uint4 dv = x == 0 ? make_uint4(d0[0], d0[1], d0[2], d0[3]) : make_uint4(d1[0], d1[1], d1[2], d1[3]);
-								if (p.out[x] && stripe < p.pb)
-									st_stream(reinterpret_cast<uint4 *>(p.out[x] + c * p.out_stride + (static_cast<unsigned long long>(stripe) << 16) + in_block), dv);
+								if (p.out[x] && stripe < p.pb) {
+									uint8_t *o = p.out[x] + c * p.out_stride + (static_cast<unsigned long long>(stripe) << 16) + in_block;
+									if (x == 0) stg_item<W>(o, d0);
+									else stg_item<W>(o, d1);
+								}
 								const uint32_t b = stripe * K + p.erased_idx[x];
-								if (img && b < p.nb) st_stream(reinterpret_cast<uint4 *>(img + (static_cast<unsigned long long>(b) << 16)), dv);
+								if (img && b < p.nb) {
+									if (x == 0) stg_item<W>(img + (static_cast<unsigned long long>(b) << 16), d0);
+									else stg_item<W>(img + (static_cast<unsigned long long>(b) << 16), d1);
+								}
 							}
 							continue;
 						}
 						// d_x = sum_r W[x][r] * S_r.  When parity row 0 (all ones) is in use, S_0 = xor of all unknowns,
 						// so the last unknown is S_0 ^ (the others) and needs no multiply.
-						uint32_t others[4] = {0, 0, 0, 0};
+						uint32_t others[W];
+#pragma unroll
+						for (int w = 0; w < W; ++w) others[w] = 0;
 #pragma unroll
 						for (int x = 0; x < E; ++x) {
-							uint32_t d[4] = {0, 0, 0, 0};
+							uint32_t d[W];
+#pragma unroll
+							for (int w = 0; w < W; ++w) d[w] = 0;
 							if (R0 == 0 && x == E - 1) {
 #pragma unroll
-								for (int w = 0; w < 4; ++w) d[w] = acc[0][w] ^ others[w];
+								for (int w = 0; w < W; ++w) d[w] = acc[0][w] ^ others[w];
 							} else {
 #pragma unroll
 								for (int r = 0; r < E; ++r) {
 									const CoefPlanes &cp = p.w[x * 4 + r];
 #pragma unroll
-									for (int w = 0; w < 4; ++w) d[w] = gf_mac(d[w], acc[r][w], cp);
+									for (int w = 0; w < W; ++w) d[w] = gf_mac<kMacNS>(d[w], acc[r][w], cp);
 								}
 #pragma unroll
-								for (int w = 0; w < 4; ++w) others[w] ^= d[w];
+								for (int w = 0; w < W; ++w) others[w] ^= d[w];
 							}
-							const uint4 dv = make_uint4(d[0], d[1], d[2], d[3]);
-							if (p.out[x] && stripe < p.pb)
-								st_stream(reinterpret_cast<uint4 *>(p.out[x] + c * p.out_stride + (static_cast<unsigned long long>(stripe) << 16) + in_block), dv);
+							if (p.out[x] && stripe < p.pb) stg_item<W>(p.out[x] + c * p.out_stride + (static_cast<unsigned long long>(stripe) << 16) + in_block, d);
 							const uint32_t b = stripe * K + p.erased_idx[x];
-							if (img && b < p.nb) st_stream(reinterpret_cast<uint4 *>(img + (static_cast<unsigned long long>(b) << 16)), dv);
+							if (img && b < p.nb) stg_item<W>(img + (static_cast<unsigned long long>(b) << 16), d);
 						}
 					}
 				}
@@ -782,7 +809,8 @@ fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 				// ---------------- CRC role: linear CRC of every input row ----------------
 				if (verify) {
 					const uint32_t rowp = row_addr0 + st * stage_bytes;
-					fold_step<kRecoverFW>(win, aux, sub * 32, rowp);
+					// the auxiliary sequence costs ~18 registers: not on the two-CTA geometry (96 registers), nor next to a 3x3 / 4x4 solve
+					fold_step<kRecoverFW, (GEO == 0 && E <= 2)>(win, aux, sub * 32, rowp);
 				}
 				__syncwarp();
 				if (lane == 0 && mbar_arrive_is_last(a_empty + 8 * st) && it + kRecoverStages < total_steps) {

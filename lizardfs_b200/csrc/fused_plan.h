@@ -31,7 +31,7 @@ constexpr int kSmemCap = 113 * 1024;                   // dynamic shared memory 
 //   M == 3            two 8-warp CTAs per SM, 128 registers (12 Horner accumulators next to the 64-word CRC window spill at 96)
 //   M == 4            ONE 16-warp CTA per SM (ec(8,4): G = 8, every scheduler gets two item warps and three row warps; +11 % over
 //                     two 8-warp CTAs whose five item warps load the schedulers 2:1:1:1), deeper stage ring instead
-//   generic (Cauchy)  two 8-warp CTAs, narrow items (LZ_WGEN words): k > 20 leaves G <= 3, so 16-byte items would put all the
+//   generic (Cauchy)  two 9-warp CTAs, narrow items (LZ_WGEN words): k > 20 leaves G <= 3, so 16-byte items would put all the
 //                     coefficient multiplies on two or three warps
 // Every value can be overridden at build time (-DLZ_T2=..., experiment builds next to the production library).
 #ifndef LZ_T2
@@ -44,7 +44,7 @@ constexpr int kSmemCap = 113 * 1024;                   // dynamic shared memory 
 #define LZ_T4 512
 #endif
 #ifndef LZ_TGEN
-#define LZ_TGEN 256
+#define LZ_TGEN 288      // nine warps: ec(29,4) and ec(31,4) need 2 stripes x (4k data + 16 parity) rows = 264 / 280 threads
 #endif
 #ifndef LZ_W3
 #define LZ_W3 4

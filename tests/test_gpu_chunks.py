@@ -220,6 +220,26 @@ def test_encode_full_size_ec32_tail_stripe(eng, oracle):
     assert (parity[0] == p_ref).all() and (crc[0] == c_ref).all()
 
 
+@pytest.mark.parametrize("text,nblocks,n_chunks", [("ec(8,6)", 40, 3), ("ec(4,5)", 16, 5), ("ec(16,8)", 64, 2), ("ec(5,7)", 23, 2),
+                                                   ("ec(32,32)", 64, 2), ("ec(21,4)", 63, 3), ("ec(31,4)", 62, 2), ("ec(29,4)", 60, 2)])
+def test_encode_many_parity_goals_in_passes(eng, oracle, text, nblocks, n_chunks):
+    """More than four parity parts (always a Cauchy generator, reed_solomon.h:168-172) are encoded in passes of four rows through
+    the bit-plane instantiation of the fused kernel (data CRCs from the first pass only); ec(k > 20, 4) is the single-pass Cauchy
+    case and the odd-k four-parity shapes need the 16-warp CTA.  Parity of every part and every CRC vs the oracle, ragged chunks
+    included; the plan must say the shape stays on the fused path."""
+    goal = L.SliceType(text)
+    plan = eng.plan_encode(goal, n_chunks, nblocks)
+    assert plan["fused"] == 1 and plan["passes"] == (-(-goal.m // 4) if goal.m > 4 else 1), plan
+    data = rnd((n_chunks, nblocks * BLOCK), hash(text) & 0xfff)
+    before = eng.stats()["kernel_launches"]
+    parity, crc = eng.encode_chunks(goal, data)
+    assert eng.stats()["kernel_launches"] - before == plan["passes"]      # one fused launch per pass, nothing else
+    for c in range(n_chunks):
+        p_ref, c_ref = oracle.encode_chunk(goal.kind, goal.k, goal.m, data[c])
+        assert (parity[c] == p_ref).all(), (text, c)
+        assert (crc[c] == c_ref).all(), (text, c)
+
+
 @pytest.mark.parametrize("text", ["xor2", "xor3", "ec(5,3)", "ec(8,4)", "ec(3,2)", "ec(8,2)"])
 def test_encode_full_size_chunk_every_bench_goal_vs_reference(eng, oracle, ref, text):
     """BASELINE configs[1], [2], [4] at the size the numbers are quoted on: one full 64 MiB chunk per goal of the mixed sweep,

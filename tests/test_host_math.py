@@ -195,7 +195,7 @@ def test_encode_unit_geometry_decisions():
     # Cauchy goal (m = 4, k > 20) runs the bit-plane instantiation with 8 warps; more than four parity parts are encoded in
     # passes of four Cauchy rows over the same data (ec(4,5): 4 + 1 rows, ec(8,6): 4 + 2, ec(32,32): eight passes)
     p = _plan("ec(21,4)", 10, 63)
-    assert p.fused == 1 and p.threads_per_cta == 256 and p.passes == 1
+    assert p.fused == 1 and p.threads_per_cta == 288 and p.passes == 1
     assert (_plan("ec(4,5)", 10, 64).fused, _plan("ec(4,5)", 10, 64).passes) == (1, 2)
     assert (_plan("ec(8,6)", 64, 1024).fused, _plan("ec(8,6)", 64, 1024).passes) == (1, 2)
     assert (_plan("ec(32,32)", 4, 1024).fused, _plan("ec(32,32)", 4, 1024).passes) == (1, 8)
@@ -211,12 +211,12 @@ def test_encode_unit_geometry_invariants_for_every_goal():
         cauchy = g.m == 4 and g.k > 20
         for n_chunks, nb, stride in [(1, 1024, None), (64, 1024, None), (500, 16, None), (33, 597, None), (7, 13, 16), (1000, 1, None), (3, g.k, None)]:
             p = _plan(text, n_chunks, nb, stride)
-            threads = 512 if (g.m == 4 and not cauchy) else 256
+            threads = 512 if (g.m == 4 and not cauchy) else 288 if cauchy else 256
             pc0 = g.m if cauchy else g.m - 1
             if p.fused == 0:
                 # only when no unit fits: an odd k needs TWO stripes per unit for the 8-row alignment of the stage, and
-                # 2*k*4 data rows + 2*pc*4 parity-CRC rows exceed the CTA (ec(31,3): 264 > 256; the 16-warp CTA of four parity
-                # rows takes ec(29,4) and ec(31,4)): generic kernels
+                # 2*k*4 data rows + 2*pc*4 parity-CRC rows exceed the CTA: only ec(31,3) (264 > 256) is left — the Cauchy shapes
+                # ec(29,4) / ec(31,4) fit the nine-warp CTA of the generic-coefficient instantiation
                 assert g.k % 2 == 1 and 2 * g.k * 4 + 2 * pc0 * 4 > threads, text
                 continue
             G, rows = p.stripes_per_unit, p.stage_rows
