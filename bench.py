@@ -369,7 +369,12 @@ class Extras:
         dc = [0 if i in lost else pcrc[i].data_ptr() for i in range(k + m)]
         do = [outs[i].data_ptr() if i in lost else 0 for i in range(k + m)]
         want = [1 if i in lost else 0 for i in range(k + m)]
+        # back-to-back launches: the verdict of every verifying call is collected by eng.sync() (deferred verification), which
+        # raises on a CRC mismatch
+        eng.set_deferred_verify(True)
         ms = self._time(lambda: eng.recover_chunks_dev(g, n, nb, dp, ps, dc, want, do, img.data_ptr(), clen, stream=self.sp))
+        eng.sync()
+        eng.set_deferred_verify(False)
         # exact on the device for the whole batch (rebuilt parts == the parts that were withheld, image == the chunks) ...
         for i in lost:
             assert torch.equal(outs[i], parts[i]), f"bench parity check failed: recover {goal_text} part {i}"

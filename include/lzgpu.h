@@ -161,7 +161,7 @@ void lzgpu_pool_get_stats(lzgpu_pool *pool, lzgpu_stats *out); /* counters summe
  * The *_dev variants take device pointers of the context's device, enqueue on `stream`
  * (a cudaStream_t passed as void*, NULL = the context's stream) and do not synchronise — with one exception: a call that
  * is given stored CRCs to verify (d_part_crc) waits for its stream and returns LZGPU_ERR_CRC on a mismatch, whether or not
- * `bad` is supplied, so corrupt input can never pass unnoticed.
+ * `bad` is supplied, so corrupt input can never pass unnoticed (lzgpu_ctx_set_deferred_verify moves that wait to lzgpu_dev_sync).
  * Threading: any number of threads may call *_dev functions on one context concurrently (temporaries come from a
  * stream-ordered pool, results from per-call slots); use a different stream per thread for overlap.  The host-pointer
  * variants share the context's staging buffers and serialise on an internal lock.
@@ -372,6 +372,12 @@ int lzgpu_dev_free(lzgpu_ctx *ctx, void *d_ptr);
 int lzgpu_dev_upload(lzgpu_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
 int lzgpu_dev_download(lzgpu_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
 int lzgpu_dev_sync(lzgpu_ctx *ctx);
+/* Deferred verification: a *_dev call that is given stored CRCs normally waits for its stream to report the verdict.  While
+ * deferred mode is on it only enqueues (back-to-back calls keep the GPU busy), and the verdicts are collected by the next
+ * lzgpu_dev_sync(ctx): LZGPU_ERR_CRC if any deferred call found a mismatch — the first one in call order, whose chunk / part /
+ * block (relative to that call) lzgpu_last_bad returns.  Nothing is ever dropped: results must not be used before the sync. */
+int lzgpu_ctx_set_deferred_verify(lzgpu_ctx *ctx, int enabled);
+int lzgpu_last_bad(lzgpu_ctx *ctx, int64_t *bad /* [3] */);
 /* page-locked host memory for staging buffers that feed the host-pointer entry points (H2D/D2H at full PCIe rate) */
 int lzgpu_host_alloc(lzgpu_ctx *ctx, size_t bytes, void **h_ptr);
 int lzgpu_host_free(lzgpu_ctx *ctx, void *h_ptr);

@@ -118,6 +118,8 @@ SIGNATURES = {
     "lzgpu_host_register": (_int, [_vp, _vp, _sz]),
     "lzgpu_host_unregister": (_int, [_vp, _vp]),
     "lzgpu_dev_sync": (_int, [_vp]),
+    "lzgpu_ctx_set_deferred_verify": (_int, [_vp, _int]),
+    "lzgpu_last_bad": (_int, [_vp, _vp]),
     "lzgpu_pool_create": (_int, [_u64, C.POINTER(_vp)]),
     "lzgpu_pool_create_list": (_int, [C.POINTER(_int), _int, C.POINTER(_vp)]),
     "lzgpu_pool_destroy": (None, [_vp]),

@@ -599,16 +599,6 @@ extern "C" int lzgpu_encode_chunks(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint3
 // ------------------------------------------------------------------------------------------------
 // batched recover
 // ------------------------------------------------------------------------------------------------
-// What a verifying call leaves behind: the result words are copied to the slot's pinned mirror on the call's stream and
-// decoded once that stream has been synchronised (by the public *_dev wrapper, or by the host pipelines when they retire a tile).
-struct VerifyTicket {
-	StatusSlot slot;       // index < 0: nothing was verified
-	bool fused = false;    // fused route: one word (chunk*64 + part)*1024 + block; otherwise one word per part: chunk*blocks + block
-	int n_words = 0;
-	uint32_t blocks = 0;   // blocks per chunk of a verified part (generic encoding)
-	bool active() const { return slot.index >= 0; }
-};
-
 // after the stream of the call has been synchronised: LZGPU_OK or LZGPU_ERR_CRC (+ first bad chunk / part / block); returns the slot
 static int ticket_result(lzgpu_ctx *ctx, VerifyTicket *tk, int64_t *bad) {
 	if (!tk->active()) return LZGPU_OK;
@@ -830,6 +820,11 @@ extern "C" int lzgpu_recover_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *goal, 
 			return rc;
 	}
 	if (!tk.active()) return LZGPU_OK;
+	if (ctx->deferred_verify.load()) {  // the verdict is collected by lzgpu_dev_sync
+		std::lock_guard<std::mutex> lk(ctx->pending_mu);
+		ctx->pending.push_back(tk);
+		return LZGPU_OK;
+	}
 	// stored CRCs were supplied: the call reports their verdict itself (with or without `bad`)
 	cudaError_t e = cudaStreamSynchronize(st);
 	if (e != cudaSuccess) {
@@ -1163,6 +1158,11 @@ extern "C" int lzgpu_convert_chunks_dev(lzgpu_ctx *ctx, const lzgpu_goal *src, c
 		if ((rc = convert_enqueue(ctx, src, dst, n_chunks, nb, d_parts, part_stride, d_part_crc, want, d_out, out_stride, d_out_crc, st, &tk))) return rc;
 	}
 	if (!tk.active()) return LZGPU_OK;
+	if (ctx->deferred_verify.load()) {
+		std::lock_guard<std::mutex> lk(ctx->pending_mu);
+		ctx->pending.push_back(tk);
+		return LZGPU_OK;
+	}
 	cudaError_t e = cudaStreamSynchronize(st);
 	if (e != cudaSuccess) {
 		ticket_drop(ctx, &tk);
@@ -1867,9 +1867,32 @@ extern "C" int lzgpu_dev_download(lzgpu_ctx *ctx, void *h_dst, const void *d_src
 	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
 	return LZGPU_OK;
 }
+extern "C" int lzgpu_ctx_set_deferred_verify(lzgpu_ctx *ctx, int enabled) {
+	if (!ctx) return LZGPU_ERR_ARG;
+	ctx->deferred_verify.store(enabled ? 1 : 0);
+	return LZGPU_OK;
+}
+extern "C" int lzgpu_last_bad(lzgpu_ctx *ctx, int64_t *bad) {
+	if (!ctx || !bad) return LZGPU_ERR_ARG;
+	std::lock_guard<std::mutex> lk(ctx->pending_mu);
+	bad[0] = ctx->last_bad[0]; bad[1] = ctx->last_bad[1]; bad[2] = ctx->last_bad[2];
+	return LZGPU_OK;
+}
 extern "C" int lzgpu_dev_sync(lzgpu_ctx *ctx) {
 	if (!ctx) return LZGPU_ERR_ARG;
 	DeviceGuard g(ctx->device);
 	CUDA_TRY(cudaDeviceSynchronize());
-	return LZGPU_OK;
+	// deferred verdicts, in call order: the first mismatch is the one reported, every slot is returned
+	std::lock_guard<std::mutex> lk(ctx->pending_mu);
+	int rc = LZGPU_OK;
+	for (VerifyTicket &tk : ctx->pending) {
+		int64_t bad[3] = {-1, -1, -1};
+		const int r = ticket_result(ctx, &tk, bad);
+		if (r != LZGPU_OK && rc == LZGPU_OK) {
+			rc = r;
+			ctx->last_bad[0] = bad[0]; ctx->last_bad[1] = bad[1]; ctx->last_bad[2] = bad[2];
+		}
+	}
+	ctx->pending.clear();
+	return rc;
 }

@@ -56,6 +56,17 @@ struct StatusSlot {
 	int index = -1;
 };
 
+// What a verifying call leaves behind: the result words are copied to the slot's pinned mirror on the call's stream and
+// decoded once that stream has been synchronised (by the public *_dev wrapper, by the host pipelines when they retire a tile, or
+// by lzgpu_dev_sync in deferred mode).
+struct VerifyTicket {
+	StatusSlot slot;       // index < 0: nothing was verified
+	bool fused = false;    // fused route: one word (chunk*64 + part)*1024 + block; otherwise one word per part: chunk*blocks + block
+	int n_words = 0;
+	uint32_t blocks = 0;   // blocks per chunk of a verified part (generic encoding)
+	bool active() const { return slot.index >= 0; }
+};
+
 // per-batch device timing (lzgpu_stats.batch_*): CUDA events recorded around the kernels of a batched call on its stream,
 // resolved lazily (cudaEventQuery) when the statistics are read — the analogue of the reference's
 // LOG_AVG_TILL_END_OF_SCOPE timers on this path (src/devtools/request_log.h:401-404, write_executor.cc:96)
@@ -86,6 +97,10 @@ struct lzgpu_ctx {
 	int auto_register = 0;                   // LZGPU_AUTO_REGISTER: page-lock pageable caller buffers per host-pointer call
 	uint64_t batches_timed = 0, batch_bytes_last = 0;
 	double batch_ms_total = 0.0, batch_ms_last = 0.0, batch_bytes_total = 0.0;
+	std::atomic<int> deferred_verify{0};     // lzgpu_ctx_set_deferred_verify: *_dev calls leave their verdict for lzgpu_dev_sync
+	std::mutex pending_mu;
+	std::vector<VerifyTicket> pending;       // verdicts not collected yet (deferred mode), in call order
+	int64_t last_bad[3] = {-1, -1, -1};
 	std::mutex mu;                           // serialises the host-pointer entry points (they share the staging slots)
 };
 

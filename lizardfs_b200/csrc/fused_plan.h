@@ -31,8 +31,7 @@ constexpr int kSmemCap = 113 * 1024;                   // dynamic shared memory 
 //   M == 3            two 8-warp CTAs per SM, 128 registers (12 Horner accumulators next to the 64-word CRC window spill at 96)
 //   M == 4            ONE 16-warp CTA per SM (ec(8,4): G = 8, every scheduler gets two item warps and three row warps; +11 % over
 //                     two 8-warp CTAs whose five item warps load the schedulers 2:1:1:1), deeper stage ring instead
-//   generic (Cauchy)  two 9-warp CTAs, narrow items (LZ_WGEN words): k > 20 leaves G <= 3, so 16-byte items would put all the
-//                     coefficient multiplies on two or three warps
+//   generic (Cauchy)  two 9-warp CTAs; item width chosen per launch (fused_generic_item_words)
 // Every value can be overridden at build time (-DLZ_T2=..., experiment builds next to the production library).
 #ifndef LZ_T2
 #define LZ_T2 256
@@ -50,14 +49,16 @@ constexpr int kSmemCap = 113 * 1024;                   // dynamic shared memory 
 #define LZ_W3 4
 #endif
 #ifndef LZ_W4
-#define LZ_W4 4
-#endif
-#ifndef LZ_WGEN
-#define LZ_WGEN 1
+#define LZ_W4 2           // ec(8,4): 512 eight-byte items fill the 16 warps (0.43 -> 0.52 of the HBM peak, profiles/sweep_r2.md)
 #endif
 LZ_HD constexpr int fused_threads(int m, bool generic) { return generic ? LZ_TGEN : m <= 2 ? LZ_T2 : m == 3 ? LZ_T3 : LZ_T4; }
 // packed words per GF item (4 = 16 bytes); narrower items = more, lighter items per step
-LZ_HD constexpr int fused_item_words(int m, bool generic) { return generic ? LZ_WGEN : m == 3 ? LZ_W3 : m == 4 ? LZ_W4 : 4; }
+// (generic coefficients: chosen per launch by fused_generic_item_words — both widths are instantiated)
+LZ_HD constexpr int fused_item_words(int m, bool generic) { return generic ? 4 : m == 3 ? LZ_W3 : m == 4 ? LZ_W4 : 4; }
+// Generic (Cauchy) coefficients: 16-byte items when a step has at least six warps of them (k <= 12 or so: the fixed cost per item —
+// addresses, narrow loads and stores — dominates otherwise: ec(8,6) 0.07 -> 0.12 of the HBM peak with 16-byte items), 4-byte items
+// when k > 20 leaves only two or three stripes per unit (ec(21,4): 64 sixteen-byte items would put every multiply on two warps)
+LZ_HD constexpr int fused_generic_item_words(uint32_t G) { return 32 * G >= 192 ? 4 : 1; }
 // CTAs per SM: two, except for the 128-word fold window and for CTAs of more than nine warps (16 warps x 128 registers fill the
 // register file on their own; their stage ring is deeper instead)
 LZ_HD constexpr int fused_ctas_per_sm(int m, bool generic, int fw) { return (fw != 64 || fused_threads(m, generic) > 288) ? 1 : 2; }

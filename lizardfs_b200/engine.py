@@ -379,7 +379,17 @@ class Engine:
         return {f[0]: getattr(s, f[0]) for f in LzStats._fields_}
 
     def sync(self):
-        _check(self.lib.lzgpu_dev_sync(self.h), "dev_sync")
+        """waits for the device; in deferred-verification mode also collects the verdicts of the *_dev calls issued since the last
+        sync and raises ChunkCrcError for the first mismatch"""
+        rc = self.lib.lzgpu_dev_sync(self.h)
+        if rc == _lib.ERR_CRC:
+            bad = (C.c_int64 * 3)(-1, -1, -1)
+            self.lib.lzgpu_last_bad(self.h, bad)
+            raise ChunkCrcError(rc, "dev_sync (deferred verification)", (bad[0], bad[1], bad[2]))
+        _check(rc, "dev_sync")
+
+    def set_deferred_verify(self, enabled):
+        _check(self.lib.lzgpu_ctx_set_deferred_verify(self.h, 1 if enabled else 0), "set_deferred_verify")
 
     # ---- geometry helpers -------------------------------------------------------------------
     @staticmethod

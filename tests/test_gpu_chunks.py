@@ -233,7 +233,8 @@ def test_encode_many_parity_goals_in_passes(eng, oracle, text, nblocks, n_chunks
     data = rnd((n_chunks, nblocks * BLOCK), hash(text) & 0xfff)
     before = eng.stats()["kernel_launches"]
     parity, crc = eng.encode_chunks(goal, data)
-    assert eng.stats()["kernel_launches"] - before == plan["passes"]      # one fused launch per pass, nothing else
+    tiles = -(-n_chunks // 2)        # the host path stages two chunk slots (128 MiB) per tile
+    assert eng.stats()["kernel_launches"] - before == plan["passes"] * tiles      # one fused launch per pass and tile, nothing else
     for c in range(n_chunks):
         p_ref, c_ref = oracle.encode_chunk(goal.kind, goal.k, goal.m, data[c])
         assert (parity[c] == p_ref).all(), (text, c)
@@ -534,3 +535,45 @@ def test_device_resident_api_and_generator(eng, oracle):
         assert (parity[c] == p_ref).all() and (crc[c] == c_ref).all()
     for p in (d_data, d_par, d_crc):
         eng.dev_free(p)
+
+
+def test_deferred_verification_reports_at_sync(eng, oracle):
+    """lzgpu_ctx_set_deferred_verify: device-pointer calls with stored CRCs only enqueue; lzgpu_dev_sync collects the verdicts and
+    reports the first mismatch in call order — nothing passes unnoticed, nothing waits per call."""
+    import torch
+    dev = torch.device("cuda", 0)
+    goal = L.SliceType("ec(8,2)")
+    n, nb, pb = 3, 32, 4
+    data = rnd((n, nb * BLOCK), 991)
+    parity, crc = eng.encode_chunks(goal, data)
+    parts = all_parts(data, parity, 8)
+    pcrc = [np.ascontiguousarray(crc[:, :nb].reshape(n, pb, 8)[:, :, j]) for j in range(8)]
+    pcrc += [np.ascontiguousarray(crc[:, nb + r * pb: nb + (r + 1) * pb]) for r in range(2)]
+    lost = (1, 4)
+    d_parts = [None if i in lost else torch.from_numpy(parts[i]).to(dev) for i in range(10)]
+    good = [None if i in lost else torch.from_numpy(pcrc[i].view(np.int32)).to(dev) for i in range(10)]
+    bad_crc = pcrc[6].copy()
+    bad_crc[2, 1] ^= 1
+    bad = list(good)
+    bad[6] = torch.from_numpy(bad_crc.view(np.int32)).to(dev)
+    outs = [torch.empty(n * pb * BLOCK, dtype=torch.uint8, device=dev) if i in lost else None for i in range(10)]
+    torch.cuda.synchronize()
+
+    def call(crcs):
+        eng.recover_chunks_dev(goal, n, nb, [0 if p is None else p.data_ptr() for p in d_parts], pb * BLOCK,
+                               [0 if c is None else c.data_ptr() for c in crcs], [1 if i in lost else 0 for i in range(10)],
+                               [0 if o is None else o.data_ptr() for o in outs])
+    eng.set_deferred_verify(True)
+    try:
+        call(good); call(good)
+        eng.sync()                                   # all verdicts good
+        assert (outs[1].cpu().numpy().reshape(n, -1) == parts[1]).all()
+        call(good); call(bad); call(good)            # returns at once; the mismatch surfaces at the sync
+        with pytest.raises(L.ChunkCrcError) as e:
+            eng.sync()
+        assert e.value.where == (2, 6, 1)
+        eng.sync()                                   # collected: nothing pending any more
+    finally:
+        eng.set_deferred_verify(False)
+    with pytest.raises(L.ChunkCrcError):             # immediate mode again
+        call(bad)

@@ -24,6 +24,9 @@ def alg_bytes_encode(k, m, chunk_len):
     return chunk_len + m * pb * BLOCK + 4 * (nb + m * pb)
 
 
+ENGINE = None
+
+
 def time_steps(fn, steps, warmup, stream):
     for _ in range(warmup):
         fn()
@@ -34,6 +37,8 @@ def time_steps(fn, steps, warmup, stream):
         fn()
     ev[1].record(stream)
     torch.cuda.synchronize()
+    if ENGINE is not None:
+        ENGINE.sync()   # raises if a deferred verification failed
     return ev[0].elapsed_time(ev[1]) / steps
 
 
@@ -54,6 +59,10 @@ def main():
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     eng = L.Engine(0)
+    # the timed launches are issued back to back: verdicts of the verifying calls are collected by eng.sync() after each loop
+    eng.set_deferred_verify(True)
+    global ENGINE
+    ENGINE = eng
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
     sp = stream.cuda_stream
