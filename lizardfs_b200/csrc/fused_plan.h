@@ -83,9 +83,14 @@ inline size_t fused_smem_bytes(uint32_t rows, uint32_t prows, int fw, int m, boo
 
 // Largest stripe group G such that data + parity-CRC rows fit the consumer threads, the data rows fit
 // one TMA box (<= 256 rows, a multiple of 8 for the 1024-byte stage alignment) and the stages fit shared memory.
+#ifndef LZ_GCAP
+#define LZ_GCAP 0         // 1: on the one-CTA shapes never plan more GF items per step than the CTA has threads
+#endif
 inline uint32_t pick_group(uint32_t K, uint32_t PC, int max_smem_per_cta, int fw, uint32_t threads, int m, bool generic) {
 	uint32_t best = 0;
+	const uint32_t items_per_stripe = 128u / static_cast<uint32_t>(fused_item_words(m, generic));
 	for (uint32_t g = 1; g <= 64; ++g) {
+		if (LZ_GCAP && threads > 288 && m > 0 && best && g * items_per_stripe > threads) break;
 		const uint32_t rows = g * K * 4, prows = g * PC * 4;
 		if (rows > kMaxRows || rows + prows > threads || prows > kMaxParityRows || g * K > 64) break;
 		if (rows % 8) continue;
