@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--e2e-chunks", type=int, default=64, help="chunks per host-buffer call in the e2e leg (configs are quoted on >= 64)")
     ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configurations (extra[])")
     ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--pool-gpus", type=int, default=0, help="ONE process, N GPUs through lzgpu_pool: prints the e2e rate of the host-buffer call (not the contract line)")
     ap.add_argument("--cpu-chunks", type=int, default=0, help="chunks in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -421,10 +422,62 @@ def copy_roofline(torch, dev, in_bytes, out_bytes, dist, reps=3):
     return best
 
 
+def run_pool(args):
+    """Single-process multi-GPU: lzgpu_pool_encode_chunks over N devices from pinned host buffers (the in-process form the mount and
+    the chunkserver need).  Same workload and timing rule as the e2e leg of the torchrun arm."""
+    import ctypes as C
+
+    import torch
+
+    import lizardfs_b200 as L
+    n_dev = args.pool_gpus
+    pool = L.Pool(list(range(n_dev)))
+    goal = L.SliceType(args.goal)
+    k, m = goal.k, goal.m
+    nb = CHUNK // BLOCK
+    pb = (nb + k - 1) // k
+    E = args.e2e_chunks * n_dev
+    par_stride, crc_stride = m * pb * BLOCK, nb + m * pb
+    h_in = torch.empty(E * CHUNK, dtype=torch.uint8).pin_memory()
+    h_par = torch.empty(E * par_stride, dtype=torch.uint8).pin_memory()
+    h_crc = torch.empty(E * crc_stride, dtype=torch.int32).pin_memory()
+    # the same synthetic chunks on every device share (seed 12345): filled on GPU 0 and copied out
+    eng = L.Engine(0)
+    one = torch.empty(args.e2e_chunks * CHUNK, dtype=torch.uint8, device="cuda:0")
+    eng.fill_chunks_dev(one.data_ptr(), args.e2e_chunks, CHUNK, CHUNK, seed=12345)
+    torch.cuda.synchronize()
+    for d in range(n_dev):
+        h_in[d * args.e2e_chunks * CHUNK:(d + 1) * args.e2e_chunks * CHUNK].copy_(one)
+    del one
+    eng.close()
+    lib = pool.lib
+    a_in, a_par, a_crc = h_in.data_ptr(), h_par.data_ptr(), h_crc.data_ptr()
+
+    def step():
+        rc = lib.lzgpu_pool_encode_chunks(pool.h, C.byref(goal.c), E, CHUNK, a_in, CHUNK, a_par, par_stride, a_crc, crc_stride)
+        assert rc == 0, L._lib.last_error()
+    for _ in range(2):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    crc = h_crc.numpy().view(np.uint32).reshape(E, crc_stride)
+    assert (crc[0] == crc[args.e2e_chunks]).all() if n_dev > 1 else True   # same chunks on device 0 and 1 -> same CRCs
+    st = pool.stats()
+    print(json.dumps({"mode": "single-process pool", "n_gpus": n_dev, "e2e_value": E * args.steps * CHUNK / GIB / dt, "unit": "GiB/s of chunk data",
+                      "chunks_per_call": E, "steps": args.steps, "h2d_bytes_per_step": E * CHUNK, "d2h_bytes_per_step": E * (par_stride + 4 * crc_stride),
+                      "kernel_launches": st["kernel_launches"], "device_gbps_mean_per_batch": st["batch_gbps_mean"]}), flush=True)
+    pool.close()
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+        return
+    if args.pool_gpus:
+        run_pool(args)
         return
 
     import torch
