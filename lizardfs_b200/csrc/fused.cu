@@ -401,7 +401,15 @@ int lz_fused_encode(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, u
 	}
 	if (M > 4) return LZGPU_NOT_HANDLED;
 	// xorN is ec(N,1): parity row 0 of the Vandermonde generator is all ones (chunk_writer.cc:373-381)
-	return fused_run(ctx, M, false, nullptr, K, n_chunks, nb, d_data, chunk_stride, d_parity, parity_stride, d_crc, crc_stride, st);
+	int rc = fused_run(ctx, M, false, nullptr, K, n_chunks, nb, d_data, chunk_stride, d_parity, parity_stride, d_crc, crc_stride, st);
+	if (rc == LZGPU_NOT_HANDLED && goal->kind == LZGPU_KIND_EC) {
+		// a Vandermonde shape whose two-stripe unit does not fit the 8-warp CTA (ec(31,3): 264 rows) still fits the nine warps of
+		// the generic-coefficient instantiation: same rows, taken as general coefficients (slower multiplies, same TMA stream)
+		uint8_t gen[LZGPU_MAX_PARTS * LZGPU_MAX_DATA];
+		lz::rs_generator(K, M, gen);
+		rc = fused_run(ctx, M, true, gen + K * K, K, n_chunks, nb, d_data, chunk_stride, d_parity, parity_stride, d_crc, crc_stride, st, nullptr, 0, 0, false, 0);
+	}
+	return rc;
 }
 
 // conversion form of the encode (SliceRecoveryPlanner: BlockConverter for the data parts + RecoverParity for the parity parts in

@@ -359,14 +359,18 @@ int lzgpu_plan_encode(const lzgpu_goal *g, uint32_t n_chunks, uint32_t nb, size_
 		if (last && !lzd::fused_plan(last, true, static_cast<uint32_t>(g->k), n_chunks, nb, chunk_stride, lzd::fused_smem_cap(last, true, 64), 64, 0).ok) return LZGPU_OK;
 	}
 	const lzd::FusedPlan pl = lzd::fused_plan(first, cauchy, static_cast<uint32_t>(g->k), n_chunks, nb, chunk_stride, lzd::fused_smem_cap(first, cauchy, 64), 64, striped_policy);
-	if (!pl.ok) return LZGPU_OK;
+	lzd::FusedPlan plg = pl;
+	if (!pl.ok && !cauchy && g->kind == LZGPU_KIND_EC && g->m <= 4)  // the nine-warp generic-coefficient CTA as the second chance (ec(31,3))
+		plg = lzd::fused_plan(g->m, true, static_cast<uint32_t>(g->k), n_chunks, nb, chunk_stride, lzd::fused_smem_cap(g->m, true, 64), 64, 0);
+	if (!plg.ok) return LZGPU_OK;
+	const lzd::FusedPlan &plr = plg;
 	out->fused = 1;
-	out->mode = static_cast<int>(pl.mode);
-	out->stripes_per_unit = pl.G;
-	out->threads_per_cta = pl.threads;
-	out->units = pl.total_units;
-	out->stage_rows = pl.rows;
-	out->smem_bytes = static_cast<uint32_t>(pl.smem);
+	out->mode = static_cast<int>(plr.mode);
+	out->stripes_per_unit = plr.G;
+	out->threads_per_cta = plr.threads;
+	out->units = plr.total_units;
+	out->stage_rows = plr.rows;
+	out->smem_bytes = static_cast<uint32_t>(plr.smem);
 	out->passes = static_cast<uint32_t>((g->m + 3) / 4 > 1 && cauchy ? (g->m + 3) / 4 : 1);
 	return LZGPU_OK;
 }

@@ -221,7 +221,7 @@ def test_encode_full_size_ec32_tail_stripe(eng, oracle):
 
 
 @pytest.mark.parametrize("text,nblocks,n_chunks", [("ec(8,6)", 40, 3), ("ec(4,5)", 16, 5), ("ec(16,8)", 64, 2), ("ec(5,7)", 23, 2),
-                                                   ("ec(32,32)", 64, 2), ("ec(21,4)", 63, 3), ("ec(31,4)", 62, 2), ("ec(29,4)", 60, 2)])
+                                                   ("ec(32,32)", 64, 2), ("ec(21,4)", 63, 3), ("ec(31,4)", 62, 2), ("ec(29,4)", 60, 2), ("ec(31,3)", 62, 2)])
 def test_encode_many_parity_goals_in_passes(eng, oracle, text, nblocks, n_chunks):
     """More than four parity parts (always a Cauchy generator, reed_solomon.h:168-172) are encoded in passes of four rows through
     the bit-plane instantiation of the fused kernel (data CRCs from the first pass only); ec(k > 20, 4) is the single-pass Cauchy

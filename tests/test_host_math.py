@@ -213,11 +213,9 @@ def test_encode_unit_geometry_invariants_for_every_goal():
             p = _plan(text, n_chunks, nb, stride)
             threads = 512 if (g.m == 4 and not cauchy) else 288 if cauchy else 256
             pc0 = g.m if cauchy else g.m - 1
-            if p.fused == 0:
-                # only when no unit fits: an odd k needs TWO stripes per unit for the 8-row alignment of the stage, and
-                # 2*k*4 data rows + 2*pc*4 parity-CRC rows exceed the CTA: only ec(31,3) (264 > 256) is left — the Cauchy shapes
-                # ec(29,4) / ec(31,4) fit the nine-warp CTA of the generic-coefficient instantiation
-                assert g.k % 2 == 1 and 2 * g.k * 4 + 2 * pc0 * 4 > threads, text
+            assert p.fused == 1, text   # every goal has a fused geometry; ec(31,3) through the nine-warp generic-coefficient CTA
+            if text == "ec(31,3)":
+                assert p.threads_per_cta == 288 and p.stripes_per_unit == 2
                 continue
             G, rows = p.stripes_per_unit, p.stage_rows
             pc = g.m if cauchy else g.m - 1
