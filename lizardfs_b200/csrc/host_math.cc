@@ -329,13 +329,19 @@ int lzgpu_chunk_part_id(const lzgpu_goal *g, int part) {
 	return lzgpu_goal_slice_type(g) * 64 + ref_part;
 }
 
+// (an invalid goal or part index yields 0 — these helpers have no status channel)
+static bool geometry_args_ok(const lzgpu_goal *g, int part) {
+	return g && (lzgpu_goal_valid(g) || (g->kind == LZGPU_KIND_STD && g->k == 1 && g->m == 0)) && part >= 0 && part < g->k + g->m;
+}
 uint32_t lzgpu_part_blocks(const lzgpu_goal *g, int part, uint32_t nb) {
+	if (!geometry_args_ok(g, part)) return 0;
 	const uint32_t k = static_cast<uint32_t>(g->k);
 	const uint32_t idx = part < g->k ? static_cast<uint32_t>(part) : 0u;  // parity counts like data part 0
 	return (nb + (k - idx - 1)) / k;
 }
 
 uint32_t lzgpu_part_length(const lzgpu_goal *g, int part, uint32_t chunk_length) {
+	if (!geometry_args_ok(g, part)) return 0;
 	const uint32_t k = static_cast<uint32_t>(g->k), B = LZGPU_BLOCK_SIZE;
 	const uint32_t idx = part < g->k ? static_cast<uint32_t>(part) : 0u;
 	const uint32_t whole = chunk_length / (k * B);

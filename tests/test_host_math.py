@@ -230,3 +230,15 @@ def test_encode_unit_geometry_invariants_for_every_goal():
                 if p.mode == 1:
                     assert nb % g.k == 0 and (stride is None or stride == nb) and n_chunks > 1
             assert p.units * G >= n_chunks * pb
+
+
+def test_geometry_helpers_reject_invalid_goals():
+    """lzgpu_part_blocks / lzgpu_part_length have no status channel: a goal with k = 0 (or any invalid goal / part index) gives 0
+    instead of a division by zero"""
+    lib = L._lib.load()
+    g = L._lib.LzGoal()
+    g.kind, g.k, g.m = 1, 0, 2
+    assert lib.lzgpu_part_blocks(C.byref(g), 0, 1024) == 0 and lib.lzgpu_part_length(C.byref(g), 0, 1 << 26) == 0
+    ok = L.SliceType("ec(3,2)")
+    assert lib.lzgpu_part_blocks(C.byref(ok.c), 5, 1024) == 0 and lib.lzgpu_part_blocks(C.byref(ok.c), -1, 1024) == 0
+    assert lib.lzgpu_part_blocks(C.byref(ok.c), 4, 1024) == 342
