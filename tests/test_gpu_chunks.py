@@ -577,3 +577,29 @@ def test_deferred_verification_reports_at_sync(eng, oracle):
         eng.set_deferred_verify(False)
     with pytest.raises(L.ChunkCrcError):             # immediate mode again
         call(bad)
+
+
+def test_only_the_parts_that_are_read_are_verified(eng, oracle):
+    """One rule on every route: the first k available parts are the inputs (ec_read_plan.h:126-133) and only they are checked
+    against their stored CRCs (the reference checks the blocks it receives, read_operation_executor.cc:257-269; a surplus part is
+    never requested).  A corrupt stored CRC on a surplus part passes on the fused route (a data part rebuilt) and on the generic
+    route (a parity part rebuilt) alike; the same corruption on a part that is read is caught on both."""
+    goal = L.SliceType("ec(3,2)")
+    n, nb, pb = 2, 12, 4
+    data = rnd((n, nb * BLOCK), 4711)
+    parity, crc = eng.encode_chunks(goal, data)
+    parts = all_parts(data, parity, 3)
+    pcrc = [np.ascontiguousarray(crc[:, :nb].reshape(n, pb, 3)[:, :, j]) for j in range(3)]
+    pcrc += [np.ascontiguousarray(crc[:, nb + r * pb: nb + (r + 1) * pb]) for r in range(2)]
+    for missing, surplus in ((0, 4), (3, 4)):       # data part 0 rebuilt: fused route; parity part 3 rebuilt: generic route
+        avail = [None if i == missing else parts[i] for i in range(5)]
+        want = [1 if i == missing else 0 for i in range(5)]
+        crcs = [None if i == missing else pcrc[i].copy() for i in range(5)]
+        crcs[surplus][1, 2] ^= 0x10                 # surplus part: the first three available ones are 1,2,3 resp. 0,1,2
+        out, _ = eng.recover_chunks(goal, nb, avail, part_crc=crcs, want=want)
+        assert (out[missing] == parts[missing]).all(), missing
+        used = 2
+        crcs[used][1, 2] ^= 0x10
+        with pytest.raises(L.ChunkCrcError) as e:
+            eng.recover_chunks(goal, nb, avail, part_crc=crcs, want=want)
+        assert e.value.where == (1, used, 2), (missing, e.value.where)
