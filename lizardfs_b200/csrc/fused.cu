@@ -605,6 +605,27 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 		coef_planes_set(p.w[1], lz::gf_inv_host(gx0 ^ gx1));
 		if (p.erased_idx[0] <= 4) p.raid6_dbl = p.erased_idx[0];
 	}
+	// "rows 0, 1, .., e-1 in use" (the first e parity parts are the available ones — the common case): instantiations that
+	// multiply row r by 2^r in one step
+	bool consecutive = true;
+	for (uint32_t r = 0; r < e; ++r) consecutive &= p.par_row[r] == r;
+	p.elim3_dbl = 0xffu;
+	if (e == 3 && consecutive) {
+		// three unknowns, parity rows 0, 1, 2: the elimination of the kernel comment (w[0..3] = alpha, beta, gamma, delta; w[4], w[5]
+		// = 2^a, 4^a when a > 3).  p, q, p^q are non-zero because 2 has order 255 and the positions differ by less than 32.
+		auto pw2 = [](int t) { uint8_t v = 1; for (int i = 0; i < t; ++i) v = lz::gf_mul_host(v, 2); return v; };
+		const uint8_t A = pw2(p.erased_idx[0]), B = pw2(p.erased_idx[1]), C = pw2(p.erased_idx[2]);
+		const uint8_t pp = A ^ B, qq = A ^ C;
+		const uint8_t alpha = lz::gf_inv_host(lz::gf_mul_host(qq, pp ^ qq)), beta = lz::gf_mul_host(pp, alpha);
+		const uint8_t gamma = lz::gf_inv_host(pp), delta = lz::gf_mul_host(qq, gamma);
+		coef_planes_set(p.w[0], alpha);
+		coef_planes_set(p.w[1], beta);
+		coef_planes_set(p.w[2], gamma);
+		coef_planes_set(p.w[3], delta);
+		coef_planes_set(p.w[4], A);
+		coef_planes_set(p.w[5], lz::gf_mul_host(A, A));
+		if (p.erased_idx[0] <= 3) p.elim3_dbl = p.erased_idx[0];
+	}
 	TmapArray maps;
 	for (int a = 0; a < K; ++a) {
 		const cuuint64_t dims[3] = {static_cast<cuuint64_t>(kRowBytes), static_cast<cuuint64_t>(pb) * 4, n_chunks};
@@ -618,10 +639,6 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 	}
 	if (*verifying && !d_first_bad) return LZGPU_NOT_HANDLED;  // (callers that pass stored CRCs always pass the result word, initialised to ~0)
 	const size_t smem = static_cast<size_t>(n_stages) * K * G * 4 * kStepBytes + 16 * n_stages + 64;
-	// "rows 0, 1, .., e-1 in use" (the first e parity parts are the available ones — the common case): instantiations that
-	// multiply row r by 2^r in one step
-	bool consecutive = true;
-	for (uint32_t r = 0; r < e; ++r) consecutive &= p.par_row[r] == r;
 	const bool row0 = p.par_row[0] == 0, row01 = e >= 2 && consecutive;
 	switch (e) {
 		case 1:

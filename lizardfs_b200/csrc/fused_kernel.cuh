@@ -590,6 +590,7 @@ struct RecoverParams {
 	uint32_t e;                    // erased data parts (1..4)
 	uint32_t n_stages;             // BIG geometry only: depth of the stage ring (as many stages as fit 200 KiB)
 	uint32_t raid6_dbl;            // E = 2 with parity rows 0 and 1 (the RAID-6 shape): doublings for 2^x0 * S0, 0xff = use w[0]
+	uint32_t elim3_dbl;            // E = 3 with parity rows 0, 1, 2: x0 (doublings for 2^x0 * S0 and 4^x0 * S0) or 0xff = use w[4], w[5]
 	uint8_t slot_of_data[32];      // data index j -> slot, 0xff = erased
 	uint8_t erased_idx[4];         // data index of erased part x
 	uint8_t par_slot[4], par_row[4];  // parity rows in use: slot and generator row r
@@ -773,6 +774,37 @@ fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 									if (x == 0) stg_item<W>(img + (static_cast<unsigned long long>(b) << 16), d0);
 									else stg_item<W>(img + (static_cast<unsigned long long>(b) << 16), d1);
 								}
+							}
+							continue;
+						}
+						if (E == 3 && R0 == 0 && R1 == 1) {
+							// Vandermonde elimination for three unknowns at positions a < b < c with rows 1, 2^j, 4^j (A = 2^a, B, C; p = A^B,
+							// q = A^C):  T1 = S1 ^ A S0 = p db ^ q dc,  T2 = S2 ^ A^2 S0 = p^2 db ^ q^2 dc,  so
+							//   dc = alpha T2 ^ beta T1   (alpha = 1/(q (p^q)), beta = p alpha),   db = gamma T1 ^ delta dc   (gamma = 1/p,
+							//   delta = q/p),   da = S0 ^ db ^ dc:  FOUR general multiplies (w[0..3]) instead of six, T1 shared by two of them;
+							// A S0 and A^2 S0 are a doublings / a fourfold steps when a <= 3 (a = 0: nothing), else two more multiplies.
+							uint32_t da[W], db[W], dc[W];
+#pragma unroll
+							for (int w = 0; w < W; ++w) {
+								uint32_t t1 = acc[0][w], t2 = acc[0][w];
+								if (p.elim3_dbl != 0xffu) {
+									for (uint32_t i = 0; i < p.elim3_dbl; ++i) { t1 = gf_x2(t1); t2 = gf_x4_add(t2, 0u); }
+								} else {
+									t1 = gf_mac<kMacNS>(0u, t1, p.w[4]);
+									t2 = gf_mac<kMacNS>(0u, t2, p.w[5]);
+								}
+								t1 ^= acc[1][w];
+								t2 ^= acc[2][w];
+								dc[w] = gf_mac<kMacNS>(gf_mac<kMacNS>(0u, t2, p.w[0]), t1, p.w[1]);
+								db[w] = gf_mac<kMacNS>(gf_mac<kMacNS>(0u, t1, p.w[2]), dc[w], p.w[3]);
+								da[w] = acc[0][w] ^ db[w] ^ dc[w];
+							}
+#pragma unroll
+							for (int x = 0; x < 3; ++x) {
+								const uint32_t (&dv)[W] = x == 0 ? da : x == 1 ? db : dc;
+								if (p.out[x] && stripe < p.pb) stg_item<W>(p.out[x] + c * p.out_stride + (static_cast<unsigned long long>(stripe) << 16) + in_block, dv);
+								const uint32_t b = stripe * K + p.erased_idx[x];
+								if (img && b < p.nb) stg_item<W>(img + (static_cast<unsigned long long>(b) << 16), dv);
 							}
 							continue;
 						}
