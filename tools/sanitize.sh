@@ -61,6 +61,37 @@ for i, (off, size) in enumerate([(0, 65536), (1, 1), (100, 4097), (65535, 1), (0
     ws.append(dict(block=i, offset=off, data=d, crc=zlib.crc32(d.tobytes()), exists=i != 4))
 st = eng.write_blocks(blocks, stored, ws)
 assert st == [0] * 6 and all(stored[i] == zlib.crc32(blocks[i].tobytes()) for i in range(6))
+# round-2 additions: the 16-warp CTA with 8-byte items (four parity rows), Cauchy rows in passes and with narrow items, the
+# nine-warp generic CTA (ec(31,3)), the 16-warp recover geometry incl. the three-unknown elimination, the SPLIT encode of the
+# slice conversion, a pool of two contexts
+os.environ.pop("LZGPU_STRIPED", None); os.environ.pop("LZGPU_RECOVER_TWO", None)
+for geo in ("2", "0"):
+    os.environ["LZGPU_RECOVER_GEO"] = geo
+    e3 = L.Engine(0)
+    for text, nblk, n, lost in [("ec(8,4)", 21, 3, (0, 5)), ("ec(8,6)", 19, 2, (1,)), ("ec(21,4)", 45, 2, (3,)), ("ec(31,3)", 62, 2, (0, 7, 30)),
+                                ("ec(5,3)", 23, 4, (0, 1, 4)), ("ec(3,2)", 11, 5, (0, 2))]:
+        g = L.SliceType(text)
+        data = np.stack([O.fill_chunk(o, nblk * 65536, 17, c) for c in range(n)])
+        par, crc = e3.encode_chunks(g, data)
+        for c in range(n):
+            p_ref, c_ref = o.encode_chunk(g.kind, g.k, g.m, data[c])
+            assert (par[c] == p_ref).all() and (crc[c] == c_ref).all(), text
+        if geo == "0" and g.m > 4:
+            continue
+        parts = [np.stack([O.split_parts(data[c], g.k)[0][j] for c in range(n)]) for j in range(g.k)] + [np.ascontiguousarray(par[:, r]) for r in range(g.m)]
+        avail = [None if i in lost else parts[i] for i in range(g.k + g.m)]
+        out, img = e3.recover_chunks(g, nblk, avail, chunk_image=True)
+        assert all((out[i] == parts[i]).all() for i in lost) and (img == data).all(), text
+    e3.close()
+os.environ.pop("LZGPU_RECOVER_GEO", None)
+pool = L.Pool([0, 0])
+g = L.SliceType("ec(8,2)")
+data = np.stack([O.fill_chunk(o, 16 * 65536, 19, c) for c in range(5)])
+par, crc = pool.encode_chunks(g, data)
+for c in range(5):
+    p_ref, c_ref = o.encode_chunk(g.kind, g.k, g.m, data[c])
+    assert (par[c] == p_ref).all() and (crc[c] == c_ref).all()
+pool.close()
 print("sanitizer case OK")
 PY
 for tool in ${TOOLS:-memcheck racecheck synccheck}; do
