@@ -55,10 +55,11 @@ LZ_HD constexpr int fused_threads(int m, bool generic) { return generic ? LZ_TGE
 // packed words per GF item (4 = 16 bytes); narrower items = more, lighter items per step
 // (generic coefficients: chosen per launch by fused_generic_item_words — both widths are instantiated)
 LZ_HD constexpr int fused_item_words(int m, bool generic) { return generic ? 4 : m == 3 ? LZ_W3 : m == 4 ? LZ_W4 : 4; }
-// Generic (Cauchy) coefficients: 16-byte items when a step has at least six warps of them (k <= 12 or so: the fixed cost per item —
-// addresses, narrow loads and stores — dominates otherwise: ec(8,6) 0.07 -> 0.12 of the HBM peak with 16-byte items), 4-byte items
-// when k > 20 leaves only two or three stripes per unit (ec(21,4): 64 sixteen-byte items would put every multiply on two warps)
-LZ_HD constexpr int fused_generic_item_words(uint32_t G) { return 32 * G >= 192 ? 4 : 1; }
+// Generic (Cauchy) coefficients: 16-byte items when a step has at least three warps of them (the fixed cost per item — addresses,
+// narrow loads and stores — dominates otherwise: ec(8,6) 0.07 -> 0.12, ec(16,8) 0.04 -> 0.06 of the HBM peak with 16-byte items),
+// 4-byte items when k > 20 leaves only two stripes per unit (ec(21,4): 64 sixteen-byte items would put every multiply on two warps;
+// 0.068 -> 0.076)
+LZ_HD constexpr int fused_generic_item_words(uint32_t G) { return 32 * G >= 96 ? 4 : 1; }
 // CTAs per SM: two, except for the 128-word fold window and for CTAs of more than nine warps (16 warps x 128 registers fill the
 // register file on their own; their stage ring is deeper instead)
 LZ_HD constexpr int fused_ctas_per_sm(int m, bool generic, int fw) { return (fw != 64 || fused_threads(m, generic) > 288) ? 1 : 2; }
@@ -84,8 +85,8 @@ inline size_t fused_smem_bytes(uint32_t rows, uint32_t prows, int fw, int m, boo
 // Largest stripe group G such that data + parity-CRC rows fit the consumer threads, the data rows fit
 // one TMA box (<= 256 rows, a multiple of 8 for the 1024-byte stage alignment) and the stages fit shared memory.
 #ifndef LZ_GCAP
-#define LZ_GCAP 0         // 1: on the one-CTA shapes never plan more GF items per step than the CTA has threads
-#endif
+#define LZ_GCAP 1         // on the one-CTA shapes never plan more GF items per step than the CTA has threads (ec(4,4): G = 16 would
+#endif                    // give every thread two items and leave half the warps without a stream: 0.35 -> 0.38 with G = 8)
 inline uint32_t pick_group(uint32_t K, uint32_t PC, int max_smem_per_cta, int fw, uint32_t threads, int m, bool generic) {
 	uint32_t best = 0;
 	const uint32_t items_per_stripe = 128u / static_cast<uint32_t>(fused_item_words(m, generic));
