@@ -52,6 +52,10 @@ __device__ __forceinline__ uint32_t gf_x2_add(uint32_t v, uint32_t d) {
 // the constants come out as 0x74000000 for x4 and 0xE8000000 for x8); the lane shift is (v - hi) * 4 = v*4 + hi*(-4) on the FMA pipe.
 // ALU ops per word: 5 (x4) and 6 (x8) instead of 6 and 10 for chained doublings, same number of FMA-pipe ops.
 #ifndef LZ_CHAINED_DOUBLINGS
+#ifdef LZ_X4_CHAINED
+// experiment: two chained doublings for x4 (4 ALU + 6 FMA ops per word instead of 5 + 4) — one ALU op less where the ALU pipe binds
+__device__ __forceinline__ uint32_t gf_x4_add(uint32_t v, uint32_t d) { return gf_x2_add(gf_x2_add(v, 0u), d); }
+#else
 __device__ __forceinline__ uint32_t gf_x4_add(uint32_t v, uint32_t d) {
 	const uint32_t hi = v & 0xC0C0C0C0u;
 	uint32_t lo;
@@ -60,6 +64,7 @@ __device__ __forceinline__ uint32_t gf_x4_add(uint32_t v, uint32_t d) {
 	const uint32_t r6 = __umulhi(v & 0x40404040u, 0x74000000u);  // bit 6 -> x^8  = 0x1d
 	return (lo ^ r7) ^ (r6 ^ d);
 }
+#endif
 __device__ __forceinline__ uint32_t gf_x8_add(uint32_t v, uint32_t d) {
 	const uint32_t hi = v & 0xE0E0E0E0u;
 	uint32_t lo;
