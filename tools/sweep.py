@@ -25,6 +25,24 @@ def alg_bytes_encode(k, m, chunk_len):
 
 
 ENGINE = None
+NVML = None
+
+
+def sm_clock():
+    """current SM clock (MHz) right after a timed loop: long sweeps run into the power cap and the kernels that are not purely
+    DRAM-bound follow the clock — the column attributes row-to-row differences of the same shape"""
+    global NVML
+    try:
+        import pynvml
+        if NVML is None:
+            pynvml.nvmlInit()
+            NVML = pynvml.nvmlDeviceGetHandleByIndex(0)
+        return pynvml.nvmlDeviceGetClockInfo(NVML, pynvml.NVML_CLOCK_SM)
+    except Exception:
+        return 0
+
+
+LAST = {"mhz": 0}
 
 
 def time_steps(fn, steps, warmup, stream):
@@ -36,6 +54,9 @@ def time_steps(fn, steps, warmup, stream):
     for _ in range(steps):
         fn()
     ev[1].record(stream)
+    for _ in range(2):
+        fn()            # keep the device busy while the clock is read
+    LAST["mhz"] = sm_clock()
     torch.cuda.synchronize()
     if ENGINE is not None:
         ENGINE.sync()   # raises if a deferred verification failed
@@ -71,7 +92,7 @@ def main():
     lines = ["# Mixed-goal sweep, 1 x B200, inputs resident in HBM", "",
              f"`python tools/sweep.py` — {args.bytes / GIB:.0f} GiB of chunk data per launch, {args.steps} timed launches, CUDA events; "
              f"frac = algorithmic bytes / time / {peak:.1f} GB/s (measured HBM copy peak).", "",
-             "## encode + per-block CRC32", "", "| goal | chunk | chunks/launch | ms | GiB/s data | GB/s algorithmic | frac of measured HBM |", "|---|---|---|---|---|---|---|"]
+             "## encode + per-block CRC32", "", "| goal | chunk | chunks/launch | ms | GiB/s data | GB/s algorithmic | frac of measured HBM | SM MHz |", "|---|---|---|---|---|---|---|---|"]
     goals = ["xor2", "xor3", "ec(3,2)", "ec(5,3)", "ec(8,2)", "ec(8,4)"]
     sizes = [1 << 20, 4 << 20, 16 << 20, 64 << 20, (37 << 20) + 5 * BLOCK]
     if args.quick:
@@ -99,7 +120,7 @@ def main():
             gibs = n * clen / GIB / (ms / 1e3)
             gbs = n * alg_bytes_encode(g.k, g.m, clen) / (ms / 1e3) / 1e9
             label = f"{clen / (1 << 20):.2f} MiB"
-            lines.append(f"| {text} | {label} | {n} | {ms:.3f} | {gibs:.0f} | {gbs:.0f} | {gbs / peak:.3f} |")
+            lines.append(f"| {text} | {label} | {n} | {ms:.3f} | {gibs:.0f} | {gbs:.0f} | {gbs / peak:.3f} | {LAST['mhz']} |")
             del d_par, d_crc
     # scrub: CRC32 of every 64 KiB block of the resident buffer (hdd_int_test, hddspacemgr.cc:2174-2190)
     nblk = args.bytes // BLOCK
@@ -112,7 +133,7 @@ def main():
         del d_c
     # degraded read: ec(8,2), data parts 1 and 4 lost (BASELINE configs[3]); also ec(3,2) / ec(5,3) / xor3
     lines += ["", "## degraded-read recover (stored CRCs verified, chunk-order image written)", "",
-              "| goal | lost parts | chunks/launch | variant | ms | GiB/s chunk data | GB/s algorithmic | frac |", "|---|---|---|---|---|---|---|---|"]
+              "| goal | lost parts | chunks/launch | variant | ms | GiB/s chunk data | GB/s algorithmic | frac | SM MHz |", "|---|---|---|---|---|---|---|---|---|"]
     cases = [("ec(8,2)", (1, 4)), ("ec(8,2)", (0,)), ("ec(3,2)", (0, 2)), ("ec(5,3)", (0, 1, 4)), ("xor3", (1,))]
     if args.quick:
         cases = cases[:1]
@@ -166,7 +187,7 @@ def main():
             alg = k * pb * BLOCK + e * pb * BLOCK + (4 * k * pb + nb * BLOCK if crcs is not None else 0)
             gibs = n * clen / GIB / (ms / 1e3)
             gbs = n * alg / (ms / 1e3) / 1e9
-            lines.append(f"| {text} | {list(lost)} | {n} | {variant} | {ms:.3f} | {gibs:.0f} | {gbs:.0f} | {gbs / peak:.3f} |")
+            lines.append(f"| {text} | {list(lost)} | {n} | {variant} | {ms:.3f} | {gibs:.0f} | {gbs:.0f} | {gbs / peak:.3f} | {LAST['mhz']} |")
         # correctness spot check of the timed outputs
         torch.cuda.synchronize()
         for i in lost:
