@@ -438,17 +438,43 @@ def run_pool(args):
     pb = (nb + k - 1) // k
     E = args.e2e_chunks * n_dev
     par_stride, crc_stride = m * pb * BLOCK, nb + m * pb
-    h_in = torch.empty(E * CHUNK, dtype=torch.uint8).pin_memory()
-    h_par = torch.empty(E * par_stride, dtype=torch.uint8).pin_memory()
-    h_crc = torch.empty(E * crc_stride, dtype=torch.int32).pin_memory()
-    # the same synthetic chunks on every device share (seed 12345): filled on GPU 0 and copied out
+    # One contiguous caller buffer per array, as the C ABI wants; each device's share of it is first-touched from a thread bound
+    # to the CPUs local to that GPU (so its pages live on that GPU's NUMA node, what a torchrun rank gets for free), then the
+    # whole buffer is page-locked in place with lzgpu_host_register.
+    import threading
+    h_in = torch.empty(E * CHUNK, dtype=torch.uint8)
+    h_par = torch.empty(E * par_stride, dtype=torch.uint8)
+    h_crc = torch.empty(E * crc_stride, dtype=torch.int32)
     eng = L.Engine(0)
     one = torch.empty(args.e2e_chunks * CHUNK, dtype=torch.uint8, device="cuda:0")
     eng.fill_chunks_dev(one.data_ptr(), args.e2e_chunks, CHUNK, CHUNK, seed=12345)
     torch.cuda.synchronize()
-    for d in range(n_dev):
-        h_in[d * args.e2e_chunks * CHUNK:(d + 1) * args.e2e_chunks * CHUNK].copy_(one)
+    one_h = one.cpu()
     del one
+    placement = []
+
+    def touch(d):
+        note = "unbound"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(d))   # affinity of THIS thread (Linux: per thread)
+            note = f"{len(os.sched_getaffinity(0))} local CPUs"
+        except Exception as exc:
+            note = f"unbound ({type(exc).__name__})"
+        n = args.e2e_chunks
+        h_in[d * n * CHUNK:(d + 1) * n * CHUNK].copy_(one_h)            # first touch = placement
+        h_par[d * n * par_stride:(d + 1) * n * par_stride].zero_()
+        h_crc[d * n * crc_stride:(d + 1) * n * crc_stride].zero_()
+        placement.append((d, note))
+    ths = [threading.Thread(target=touch, args=(d,)) for d in range(n_dev)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    for t_ in (h_in, h_par, h_crc):
+        rc = eng.lib.lzgpu_host_register(eng.h, t_.data_ptr(), t_.numel() * t_.element_size())
+        assert rc == 0, L._lib.last_error()
     eng.close()
     lib = pool.lib
     a_in, a_par, a_crc = h_in.data_ptr(), h_par.data_ptr(), h_crc.data_ptr()
@@ -467,7 +493,8 @@ def run_pool(args):
     st = pool.stats()
     print(json.dumps({"mode": "single-process pool", "n_gpus": n_dev, "e2e_value": E * args.steps * CHUNK / GIB / dt, "unit": "GiB/s of chunk data",
                       "chunks_per_call": E, "steps": args.steps, "h2d_bytes_per_step": E * CHUNK, "d2h_bytes_per_step": E * (par_stride + 4 * crc_stride),
-                      "kernel_launches": st["kernel_launches"], "device_gbps_mean_per_batch": st["batch_gbps_mean"]}), flush=True)
+                      "kernel_launches": st["kernel_launches"], "device_gbps_mean_per_batch": st["batch_gbps_mean"],
+                      "host_placement": sorted(placement)}), flush=True)
     pool.close()
 
 

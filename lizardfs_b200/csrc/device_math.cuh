@@ -52,8 +52,10 @@ __device__ __forceinline__ uint32_t gf_x2_add(uint32_t v, uint32_t d) {
 // the constants come out as 0x74000000 for x4 and 0xE8000000 for x8); the lane shift is (v - hi) * 4 = v*4 + hi*(-4) on the FMA pipe.
 // ALU ops per word: 5 (x4) and 6 (x8) instead of 6 and 10 for chained doublings, same number of FMA-pipe ops.
 #ifndef LZ_CHAINED_DOUBLINGS
-#ifdef LZ_X4_CHAINED
-// experiment: two chained doublings for x4 (4 ALU + 6 FMA ops per word instead of 5 + 4) — one ALU op less where the ALU pipe binds
+#ifndef LZ_X4_FUSED
+// x4 as two chained doublings: 4 ALU + 6 FMA-pipe ops per word instead of the 5 + 4 of the one-step form below — one ALU op less
+// where the ALU pipe binds and the FMA pipe idles (round 2, same box: ec(5,3) 0.765 -> 0.792, ec(6,3) 0.762 -> 0.793 of the HBM
+// peak; ec(8,4) unchanged).  -DLZ_X4_FUSED selects the one-step form.
 __device__ __forceinline__ uint32_t gf_x4_add(uint32_t v, uint32_t d) { return gf_x2_add(gf_x2_add(v, 0u), d); }
 #else
 __device__ __forceinline__ uint32_t gf_x4_add(uint32_t v, uint32_t d) {

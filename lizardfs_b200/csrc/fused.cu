@@ -153,7 +153,7 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 #if LZ_T2 == 288
 	if ((rc = set_smem_attr<2, false, 8, 8>(smem))) return rc;
 #endif
-#if LZ_T4 == 256
+#if LZ_T4 != 512
 	if ((rc = set_smem_attr<4, false, 8, 5>(smem))) return rc;
 #endif
 #if LZ_T3 == 512
@@ -355,7 +355,7 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 #if LZ_T2 == 288
 	LZ_FOLDED(2, 8, 8)    // experiment builds with the nine-warp CTA of round 1
 #endif
-#if LZ_T4 == 256
+#if LZ_T4 != 512
 	LZ_FOLDED(4, 8, 5)
 #endif
 #if LZ_T3 == 512

@@ -491,7 +491,8 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 				if (PC > 0 && warp_has_prow && !LZ_PROBE(2)) mbar_wait(a_pfull + 8 * pst, pph);
 				if (has_stream && !(GENERIC && is_data_row && p.skip_data_crc) && !LZ_PROBE(4)) {
 					const uint32_t rowp = row_addr0 + (is_data_row ? st : pst) * row_stride;
-					fold_step<FW>(win, aux, sub * 32, rowp);
+					// (the auxiliary sequence needs ~18 registers: only where a thread has more than 112)
+					fold_step<FW, (NT * fused_ctas_per_sm(M, GENERIC, FW) <= 512)>(win, aux, sub * 32, rowp);
 				}
 				__syncwarp();
 				if (STRIPED) {

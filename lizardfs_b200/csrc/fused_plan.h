@@ -62,7 +62,7 @@ LZ_HD constexpr int fused_item_words(int m, bool generic) { return generic ? 4 :
 LZ_HD constexpr int fused_generic_item_words(uint32_t G) { return 32 * G >= 96 ? 4 : 1; }
 // CTAs per SM: two, except for the 128-word fold window and for CTAs of more than nine warps (16 warps x 128 registers fill the
 // register file on their own; their stage ring is deeper instead)
-LZ_HD constexpr int fused_ctas_per_sm(int m, bool generic, int fw) { return (fw != 64 || fused_threads(m, generic) > 288) ? 1 : 2; }
+LZ_HD constexpr int fused_ctas_per_sm(int m, bool generic, int fw) { return (fw != 64 || fused_threads(m, generic) > 320) ? 1 : 2; }
 
 // pipeline depth by fold window: FW = 64 -> 2 CTAs/SM (96-128 registers), 3 data stages + 4-deep parity ring (4 stages for the
 // one-CTA shapes); FW = 128 -> 1 CTA/SM (the 128-word window needs ~170 registers), 6 data stages + 6-deep parity ring
@@ -91,7 +91,7 @@ inline uint32_t pick_group(uint32_t K, uint32_t PC, int max_smem_per_cta, int fw
 	uint32_t best = 0;
 	const uint32_t items_per_stripe = 128u / static_cast<uint32_t>(fused_item_words(m, generic));
 	for (uint32_t g = 1; g <= 64; ++g) {
-		if (LZ_GCAP && threads > 288 && m > 0 && best && g * items_per_stripe > threads) break;
+		if (LZ_GCAP && (threads > 288 || m >= 3) && m > 0 && best && g * items_per_stripe > threads) break;
 		const uint32_t rows = g * K * 4, prows = g * PC * 4;
 		if (rows > kMaxRows || rows + prows > threads || prows > kMaxParityRows || g * K > 64) break;
 		if (rows % 8) continue;
