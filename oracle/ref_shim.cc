@@ -207,4 +207,53 @@ int ref_recover_chunk(int kind, int k, int m, const uint8_t *const *parts,
 	return 0;
 }
 
+
+// hdd_write (src/chunkserver/hddspacemgr.cc:1898-2008) cannot be compiled without the chunkserver (Chunk objects, file I/O), so its
+// body is transcribed here with the SAME sequence of calls into the reference's own crc.cc — mycrc32, mycrc32_combine,
+// mycrc32_zeroblock, recompute_crc_if_block_empty (the interleaved-format reader applies it, :1779) — and the block file replaced by a
+// 64 KiB memory buffer.  Every CRC value is therefore computed by reference code; only the I/O is stood in for.  Return codes as
+// lzo_hdd_write_block: 0 ok, -1 wrong size / offset (:1911-1916), -3 packet CRC (:1917-1919), -4 stored block fails (:1962-1971).
+int ref_hdd_write_block(uint8_t *block /* nullptr: blocknum >= chunk->blocks */, uint32_t *stored_crc, uint32_t offset, uint32_t size,
+                        uint32_t crc, const uint8_t *buffer, uint8_t *new_block) {
+	uint32_t precrc, postcrc, combinedcrc, chcrc;
+	if (size > MFSBLOCKSIZE) return -1;
+	if ((offset >= MFSBLOCKSIZE) || (offset + size > MFSBLOCKSIZE)) return -1;
+	if (crc != mycrc32(0, buffer, size)) return -3;
+	if (offset == 0 && size == MFSBLOCKSIZE) {
+		std::memcpy(block ? block : new_block, buffer, MFSBLOCKSIZE);
+		*stored_crc = crc;
+		return 0;
+	}
+	uint8_t *data_in_buffer;
+	if (block) {
+		uint32_t have = *stored_crc;
+		recompute_crc_if_block_empty(block, have);
+		data_in_buffer = block;
+		precrc = mycrc32(0, data_in_buffer, offset);
+		chcrc = mycrc32(0, data_in_buffer + offset, size);
+		postcrc = mycrc32(0, data_in_buffer + offset + size, MFSBLOCKSIZE - (offset + size));
+		if (offset == 0) {
+			combinedcrc = mycrc32_combine(chcrc, postcrc, MFSBLOCKSIZE - (offset + size));
+		} else {
+			combinedcrc = mycrc32_combine(precrc, chcrc, size);
+			if ((offset + size) < MFSBLOCKSIZE) combinedcrc = mycrc32_combine(combinedcrc, postcrc, MFSBLOCKSIZE - (offset + size));
+		}
+		if (have != combinedcrc) return -4;
+	} else {
+		data_in_buffer = new_block;
+		std::memset(data_in_buffer, 0, MFSBLOCKSIZE);   // ftruncate: the block comes into being as zeros
+		precrc = mycrc32_zeroblock(0, offset);
+		postcrc = mycrc32_zeroblock(0, MFSBLOCKSIZE - (offset + size));
+	}
+	if (offset == 0) {
+		combinedcrc = mycrc32_combine(crc, postcrc, MFSBLOCKSIZE - (offset + size));
+	} else {
+		combinedcrc = mycrc32_combine(precrc, crc, size);
+		if ((offset + size) < MFSBLOCKSIZE) combinedcrc = mycrc32_combine(combinedcrc, postcrc, MFSBLOCKSIZE - (offset + size));
+	}
+	std::memcpy(data_in_buffer + offset, buffer, size);
+	*stored_crc = combinedcrc;
+	return 0;
+}
+
 }  // extern "C"
