@@ -286,7 +286,8 @@ def hdd_write_block(oracle, block, stored_crc, offset, size, crc, buffer):
     work = None if block is None else np.array(block, dtype=np.uint8, copy=True)
     c = C.c_uint32(stored_crc)
     buf = np.ascontiguousarray(buffer, dtype=np.uint8)
-    f = oracle.dll.lzo_hdd_write_block
+    # the compiled reference exposes the same transcription built on ITS crc.cc (oracle/ref_shim.cc ref_hdd_write_block)
+    f = oracle.dll.ref_hdd_write_block if oracle.is_ref else oracle.dll.lzo_hdd_write_block
     f.restype = C.c_int
     rc = f(_ptr(work) if work is not None else None, C.byref(c), C.c_uint32(offset), C.c_uint32(size), C.c_uint32(crc), _ptr(buf), _ptr(new_block))
     return rc, (work if work is not None else new_block), c.value

@@ -181,7 +181,7 @@ def test_scrub_moosefs_format(eng, oracle, data_parts):
     assert ei.value.where == (0,)
 
 
-def test_write_blocks_matches_hdd_write(eng, oracle):
+def test_write_blocks_matches_hdd_write(eng, oracle, ref):
     """batched chunkserver block writes against the restated hdd_write (hddspacemgr.cc:1898-2008), request by request"""
     rng = np.random.default_rng(11)
     shapes = [(0, 65536), (0, 1), (0, 4096), (1, 65535), (65535, 1), (100, 1000), (4096, 61440), (12345, 1), (1, 1), (32768, 32768),
@@ -202,7 +202,9 @@ def test_write_blocks_matches_hdd_write(eng, oracle):
         if variant == 2 and i % 4 == 1 and exists:
             stored[i] ^= 1                                            # damaged stored block
         writes.append(dict(block=i, offset=off, data=data, crc=crc, exists=exists))
-        expect.append(O.hdd_write_block(oracle, blocks[i] if exists else None, int(stored[i]), off, size, crc, data if size else np.zeros(1, np.uint8)))
+        # checker: the transcription of hdd_write onto the compiled reference's crc.cc where oracle/_ref exists, else the restatement
+        expect.append(O.hdd_write_block(ref if ref is not None else oracle, blocks[i] if exists else None, int(stored[i]), off, size, crc,
+                                        data if size else np.zeros(1, np.uint8)))
     before_blocks, before_crc = blocks.copy(), stored.copy()
     status = eng.write_blocks(blocks, stored, writes)
     code = {0: 0, -3: L._lib.ERR_CRC, -4: L._lib.ERR_DAMAGED, -1: L._lib.ERR_ARG}

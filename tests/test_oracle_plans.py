@@ -215,3 +215,34 @@ def test_convert_restatement_matches_committed_reference_vectors(oracle, idx):
     rc, out, ocrc, _ = O.convert_chunk(oracle, src, avail, None, dst, [1] * (dst[1] + dst[2]), nb)
     assert rc == 0
     check_against_golden_case(case, out, ocrc)
+
+
+@pytest.mark.parametrize("offset,size", [(0, 65536), (0, 1), (0, 4096), (1, 65535), (65535, 1), (100, 1000), (4096, 61440), (12345, 1), (32768, 32768)])
+@pytest.mark.parametrize("case", ["existing", "hole", "new", "bad_packet", "damaged"])
+def test_hdd_write_restatement_matches_the_reference_crc_calls(oracle, ref, offset, size, case):
+    """`lzo_hdd_write_block` (the restatement the GPU's `block_write_kernel` is tested against) vs `ref_hdd_write_block`: the body
+    of hdd_write (hddspacemgr.cc:1898-2008) transcribed onto the REFERENCE's own mycrc32 / mycrc32_combine / mycrc32_zeroblock /
+    recompute_crc_if_block_empty — every CRC value computed by the compiled reference, only the file replaced by memory."""
+    if ref is None:
+        pytest.skip("oracle/_ref/liblzref.so was not built (no /root/reference)")
+    rng = np.random.default_rng(offset * 31 + size + len(case))
+    old = rng.integers(0, 256, BLOCK, dtype=np.uint8)
+    buf = rng.integers(0, 256, size, dtype=np.uint8)
+    crc = zlib.crc32(buf.tobytes())
+    stored = zlib.crc32(old.tobytes())
+    block = old
+    if case == "hole":
+        old[:] = 0
+        stored = 0                       # sparse block: stored CRC 0 counts as the CRC of zeros (crc.cc:235-243)
+    elif case == "new":
+        block = None
+    elif case == "bad_packet":
+        crc ^= 0x40
+    elif case == "damaged":
+        stored ^= 0x100
+    a = O.hdd_write_block(oracle, block, stored, offset, size, crc, buf)
+    b = O.hdd_write_block(ref, block, stored, offset, size, crc, buf)
+    assert a[0] == b[0], (case, a[0], b[0])
+    if a[0] == 0:
+        assert (a[1] == b[1]).all() and a[2] == b[2]
+        assert a[2] == zlib.crc32(a[1].tobytes())
