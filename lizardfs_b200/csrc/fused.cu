@@ -36,6 +36,7 @@ struct FusedState {
 	int striped = -1;
 	int recover_two = -1;  // LZGPU_RECOVER_TWO: -1 automatic, 0 one CTA per SM (6 stages), 1 two CTAs (3 stages) for e <= 2
 	int recover_geo = -1;  // LZGPU_RECOVER_GEO: -1 automatic, 0 / 1 as above, 2 one 16-warp CTA per SM
+	int direct_wide = -1;  // LZGPU_DIRECT_WIDE: item width of the DIRECT (Cauchy) degraded read, -1 by item count, 0 = 4 bytes, 1 = 16 bytes
 	int promo = 3;  // CU_TENSOR_MAP_L2_PROMOTION_L2_256B: +12% streaming bandwidth over 128B/none (profiles/probe_r1.md)
 };
 
@@ -71,6 +72,15 @@ static int set_recover_attr() {
 	return LZGPU_OK;
 }
 
+// wide items of the DIRECT degraded read: 16 bytes for one rebuilt part, 8 for more (e x 4 accumulators next to the CRC window spill at 128 registers)
+template <int E> constexpr int kDirectWide = E >= 2 ? 2 : 4;
+template <int E>
+static int set_direct_attr() {
+	CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<E, 0, kRecoverDirect, -1, 64, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCapBig));
+	CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<E, 0, kRecoverDirect, -1, 64, 2, kDirectWide<E>>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCapBig));
+	return LZGPU_OK;
+}
+
 // function attributes are per device: done once per context
 static int set_all_recover_attrs() {
 	int rc;
@@ -84,6 +94,8 @@ static int set_all_recover_attrs() {
 	if ((rc = set_recover_attr<3, 0>())) return rc;
 	if ((rc = set_recover_attr<4, 0, 0, 1>())) return rc;
 	if ((rc = set_recover_attr<4, 0>())) return rc;
+	// DIRECT (any generator; Cauchy codes): 16-warp geometry, 4-byte items
+	if ((rc = set_direct_attr<1>()) || (rc = set_direct_attr<2>()) || (rc = set_direct_attr<3>()) || (rc = set_direct_attr<4>())) return rc;
 	return LZGPU_OK;
 }
 
@@ -96,6 +108,7 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if (const char *e = std::getenv("LZGPU_EVICT_FIRST")) fs->evict_first = std::atoi(e);
 	if (const char *e = std::getenv("LZGPU_RECOVER_TWO")) fs->recover_two = std::atoi(e);
 	if (const char *e = std::getenv("LZGPU_RECOVER_GEO")) fs->recover_geo = std::atoi(e);
+	if (const char *e = std::getenv("LZGPU_DIRECT_WIDE")) fs->direct_wide = std::atoi(e);
 	if (const char *e = std::getenv("LZGPU_STRIPED")) fs->striped = std::atoi(e);  // 0 never, 1 whenever possible, unset = automatic
 	void *fn = nullptr;
 	cudaDriverEntryPointQueryResult qres;
@@ -449,6 +462,18 @@ int lz_fused_crc(lzgpu_ctx *ctx, const void *base, unsigned long long n_blocks, 
 // ---------------------------------------------------------------------------------------------------
 // fused degraded read
 // ---------------------------------------------------------------------------------------------------
+// DIRECT form of the degraded read (any generator; the Cauchy codes): 16-warp CTA, runtime k, 16- or 4-byte items
+constexpr uint32_t kDirectWideItems = 192;
+template <int E>
+static int launch_direct(lzgpu_ctx *ctx, const TmapArray &maps, const RecoverParams &p, size_t smem, cudaStream_t st, bool wide) {
+	const int grid = static_cast<int>(std::min<uint64_t>(p.total_units, static_cast<uint64_t>(ctx->sm_count)));
+	if (wide) fused_recover_kernel<E, 0, kRecoverDirect, -1, 64, 2, kDirectWide<E>><<<grid, recover_threads(2), smem, st>>>(maps, p);
+	else fused_recover_kernel<E, 0, kRecoverDirect, -1, 64, 2, 1><<<grid, recover_threads(2), smem, st>>>(maps, p);
+	CUDA_TRY(cudaGetLastError());
+	ctx->stats.kernel_launches++;
+	return LZGPU_OK;
+}
+
 template <int E, int KT, int R0 = -1, int R1 = -1>
 static int launch_recover(lzgpu_ctx *ctx, const TmapArray &maps, const RecoverParams &p, size_t smem, cudaStream_t st, int geo) {
 	if (geo == 2) {
@@ -483,7 +508,7 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 	*verifying = false;
 	if (!fs || fs->disabled) return LZGPU_NOT_HANDLED;
 	const int K = goal->k, M = goal->m, N = K + M;
-	if (lz::uses_cauchy(K, M)) return LZGPU_NOT_HANDLED;
+	const bool direct = lz::uses_cauchy(K, M);   // no Horner syndromes for a Cauchy generator: general rows over the k inputs
 	if ((part_stride % 16) || (chunk_out_stride % 16)) return LZGPU_NOT_HANDLED;
 	// inputs: the first k available parts (ec_read_plan.h:126-133)
 	int used[LZGPU_MAX_DATA], n_used = 0;
@@ -496,6 +521,7 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 	for (int a = 0; a < K; ++a) {
 		const int idx = used[a];
 		p.part_id[a] = static_cast<uint8_t>(idx);
+		p.data_of_slot[a] = idx < K ? static_cast<uint8_t>(idx) : 0xff;
 		if (idx < K) p.slot_of_data[idx] = static_cast<uint8_t>(a);
 		else if (n_par < 4) { p.par_slot[n_par] = static_cast<uint8_t>(a); p.par_row[n_par] = static_cast<uint8_t>(idx - K); ++n_par; }
 		else return LZGPU_NOT_HANDLED;
@@ -521,6 +547,7 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 	// three lost 0.29 / 0.42 against 0.23 / 0.32 and two lost 0.59 / 0.74 against 0.46 / 0.65 on one — while the k = 8 instantiation
 	// keeps one 9-warp CTA with six stages (two lost: 0.81 with verification and image against 0.70).  LZGPU_RECOVER_GEO=0|1|2 forces one.
 	int geo = fs->recover_geo >= 0 ? fs->recover_geo : (K != 8 && e >= 2) ? 2 : (two ? 1 : 0);
+	if (direct) geo = 2;
 	if (geo == 1 && e > 2) geo = 0;
 	uint32_t G = 0, n_stages = 0;
 	if (geo == 2) {
@@ -589,7 +616,19 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 			V[r * e + x] = v;
 		}
 	}
-	if (gf_invert_matrix(V, W, static_cast<int>(e)) != 0) return LZGPU_NOT_HANDLED;  // generic path reports the singular case
+	if (!direct && gf_invert_matrix(V, W, static_cast<int>(e)) != 0) return LZGPU_NOT_HANDLED;  // generic path reports the singular case
+	if (direct) {
+		// rows of the reference's inverted k x k system for the erased data parts, over the k used parts in slot order
+		uint8_t erased_flags[LZGPU_MAX_PARTS] = {0}, wanted[LZGPU_MAX_PARTS] = {0}, rows[LZGPU_MAX_PARITY * LZGPU_MAX_DATA];
+		for (int i = 0; i < N; ++i) erased_flags[i] = 1;
+		for (int a = 0; a < K; ++a) erased_flags[used[a]] = 0;
+		for (uint32_t x = 0; x < e; ++x) wanted[p.erased_idx[x]] = 1;
+		bool singular = false;
+		if (lz::rs_recovery_matrix(K, M, erased_flags, wanted, rows, &singular) != static_cast<int>(e)) return LZGPU_NOT_HANDLED;
+		for (uint32_t x = 0; x < e; ++x)   // rs_recovery_matrix emits its rows in ascending part order = erased_idx order
+			for (int a = 0; a < K; ++a) coef_planes_set(p.rw[x * 32 + a], rows[x * K + a]);
+		std::memset(W, 0, sizeof(W));
+	}
 	for (uint32_t x = 0; x < e; ++x)
 		for (uint32_t r = 0; r < e; ++r) {
 			coef_planes_set(p.w[x * 4 + r], W[x * e + r]);
@@ -640,6 +679,16 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 	if (*verifying && !d_first_bad) return LZGPU_NOT_HANDLED;  // (callers that pass stored CRCs always pass the result word, initialised to ~0)
 	const size_t smem = static_cast<size_t>(n_stages) * K * G * 4 * kStepBytes + 16 * n_stages + 64;
 	const bool row0 = p.par_row[0] == 0, row01 = e >= 2 && consecutive;
+	if (direct) {
+		// item width: 16-byte items leave most of the 16 warps without work when k is large (G small)
+		const bool wide = fs->direct_wide >= 0 ? fs->direct_wide != 0 : 32 * G >= kDirectWideItems;   // 32 G = the number of 16-byte items per step
+		switch (e) {
+			case 1: return launch_direct<1>(ctx, maps, p, smem, st, wide);
+			case 2: return launch_direct<2>(ctx, maps, p, smem, st, wide);
+			case 3: return launch_direct<3>(ctx, maps, p, smem, st, wide);
+			default: return launch_direct<4>(ctx, maps, p, smem, st, wide);
+		}
+	}
 	switch (e) {
 		case 1:
 			if (row0) return k8 ? launch_recover<1, 8, 0>(ctx, maps, p, smem, st, geo) : launch_recover<1, 0, 0>(ctx, maps, p, smem, st, geo);

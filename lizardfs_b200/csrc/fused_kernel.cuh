@@ -599,6 +599,10 @@ struct RecoverParams {
 	uint32_t qmult[4];
 	uint32_t zconst;
 	CoefPlanes w[16];              // W = V^-1, w[x*4 + r]
+	// DIRECT instantiations (R0 = -2: any generator, used for Cauchy codes): d_x = sum over the k used slots of rw[x*32 + a] * in_a,
+	// the rows of the reference's inverted matrix that belong to the erased data parts (reed_solomon.h:229-281)
+	uint8_t data_of_slot[32];      // slot -> data index, 0xff = a parity part
+	CoefPlanes rw[4 * 32];
 };
 
 // E = erased data parts; KT = compile-time K (0 = runtime); R0, R1 = generator rows of the first two parity
@@ -618,7 +622,11 @@ __host__ __device__ constexpr int recover_threads(int geo) { return geo == 2 ? 5
 #define LZ_RW3 2   // words per GF item for three or four erased parts on the 16-warp geometry (narrower items = fewer live accumulators)
 #endif
 __host__ __device__ constexpr int recover_item_words(int e, int geo) { return (geo == 2 && e >= 3) ? LZ_RW3 : 4; }
+constexpr int kRecoverDirect = -2;   // value of R0 that selects the DIRECT form (4-byte items on the 16-warp geometry: k > 20 leaves G = 4)
 
+// the elimination forms end their item with `continue` under a template-constant condition: the general solve below them is
+// dead code in those instantiations (warning 128)
+#pragma nv_diag_suppress 128
 template <int E, int KT, int R0, int R1, int kRecoverFW, int GEO = 0, int W = recover_item_words(E, GEO)>
 __global__ void __launch_bounds__(recover_threads(GEO), GEO == 1 ? 2 : 1)
 fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_constant__ RecoverParams p) {
@@ -705,6 +713,32 @@ fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 						for (int r = 0; r < E; ++r)
 #pragma unroll
 							for (int w = 0; w < W; ++w) acc[r][w] = 0;
+						if (R0 == kRecoverDirect) {
+							// DIRECT form: the rebuilt parts are general combinations of the k inputs (e x k bit-plane multiplies per column) —
+							// the route for Cauchy generators, whose syndromes have no cheap Horner form.  Surviving data columns go to the image.
+							for (uint32_t a = 0; a < K; ++a) {
+								uint32_t v[W];
+								lds_item<W>(a_item + a * region_bytes, v);
+								const uint32_t j = p.data_of_slot[a];
+								if (j != 0xffu) {
+									const uint32_t b = stripe * K + j;
+									if (img && b < p.nb) stg_item<W>(img + (static_cast<unsigned long long>(b) << 16), v);
+								}
+#pragma unroll
+								for (int x = 0; x < E; ++x) {
+									const CoefPlanes &cp = p.rw[x * 32 + a];
+#pragma unroll
+									for (int w = 0; w < W; ++w) acc[x][w] = gf_mac<kMacNS>(acc[x][w], v[w], cp);
+								}
+							}
+#pragma unroll
+							for (int x = 0; x < E; ++x) {
+								if (p.out[x] && stripe < p.pb) stg_item<W>(p.out[x] + c * p.out_stride + (static_cast<unsigned long long>(stripe) << 16) + in_block, acc[x]);
+								const uint32_t b = stripe * K + p.erased_idx[x];
+								if (img && b < p.nb) stg_item<W>(img + (static_cast<unsigned long long>(b) << 16), acc[x]);
+							}
+							continue;
+						}
 #pragma unroll
 						for (int j = static_cast<int>(K) - 1; j >= 0; --j) {
 							const uint32_t sl = p.slot_of_data[j];

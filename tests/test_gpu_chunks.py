@@ -410,6 +410,60 @@ def test_recover_one_and_two_ctas_per_sm(oracle, two, text, nblocks, lost):
         assert (out[i][2] == o_ref[i]).all()
 
 
+@pytest.mark.parametrize("wide", ["0", "1", None])
+@pytest.mark.parametrize("text,nblocks,lost", [("ec(8,6)", 40, (1, 4, 7)), ("ec(8,6)", 17, (0, 2, 3, 5)), ("ec(4,5)", 19, (3,)), ("ec(21,4)", 50, (0, 20)),
+                                               ("ec(16,8)", 64, (2, 9, 15)), ("ec(32,4)", 70, (5, 6, 30, 31)), ("ec(12,5)", 24, (11, 13, 14))])
+def test_recover_cauchy_goals_in_one_fused_pass(oracle, wide, text, nblocks, lost):
+    """the goals whose generator is the Cauchy matrix (reed_solomon.h:229-281) are rebuilt by the DIRECT form of the fused degraded read:
+    one launch that verifies the inputs, rebuilds the erased data parts and writes the chunk image — both item widths, against the
+    oracle, with a flipped bit found at its (chunk, part, block)"""
+    if wide is not None:
+        os.environ["LZGPU_DIRECT_WIDE"] = wide
+    try:
+        e = L.Engine()
+    finally:
+        os.environ.pop("LZGPU_DIRECT_WIDE", None)
+    goal = L.SliceType(text)
+    k, m = goal.k, goal.m
+    n_chunks = 3
+    data = rnd((n_chunks, nblocks * BLOCK), 91)
+    parity, crc = e.encode_chunks(goal, data)
+    parts = all_parts(data, parity, k)
+    pb = parts[0].shape[1] // BLOCK
+    part_crc = []
+    for j in range(k):
+        c = np.full((n_chunks, pb), 0xD7978EEB, dtype=np.uint32)
+        mine = crc[:, j:nblocks:k]
+        c[:, : mine.shape[1]] = mine
+        part_crc.append(c)
+    for r in range(m):
+        part_crc.append(np.ascontiguousarray(crc[:, nblocks + r * pb: nblocks + (r + 1) * pb]))
+    lost = tuple(i for i in lost if i < k + m)
+    avail = [None if i in lost else parts[i] for i in range(k + m)]
+    acrc = [None if i in lost else part_crc[i] for i in range(k + m)]
+    want = [1 if i in lost else 0 for i in range(k + m)]
+    for crcs, image in [(acrc, True), (None, False), (acrc, False), (None, True)]:
+        before = e.stats()["kernel_launches"]
+        out, img = e.recover_chunks(goal, nblocks, avail, part_crc=crcs, want=want, chunk_image=image)
+        assert e.stats()["kernel_launches"] - before == 1, "the Cauchy degraded read left the fused kernel"
+        for i in lost:
+            if i < k:
+                assert (out[i] == parts[i]).all(), (text, lost, i)
+        if image:
+            assert (img == data).all()
+    rc, o_ref, _ = oracle.recover_chunk(goal.kind, k, m, [None if a is None else a[1] for a in avail], None, want, pb)
+    for i in lost:
+        assert (out[i][1] == o_ref[i]).all()
+    # a flipped bit in a part that is read (the first k available parts) is reported at its place
+    used = [i for i in range(k + m) if i not in lost][:k]
+    victim = used[len(used) // 2]
+    bad = [None if a is None else a.copy() for a in avail]
+    bad[victim][2, (pb - 1) * BLOCK + 77] ^= 0x10
+    with pytest.raises(L.ChunkCrcError) as ei:
+        e.recover_chunks(goal, nblocks, bad, part_crc=acrc, want=want, chunk_image=True)
+    assert ei.value.where == (2, victim, pb - 1)
+
+
 def test_recover_verifies_crc(eng):
     goal = L.SliceType("ec(8,2)")
     nblocks = 24
