@@ -36,7 +36,7 @@ struct FusedState {
 	int striped = -1;
 	int recover_two = -1;  // LZGPU_RECOVER_TWO: -1 automatic, 0 one CTA per SM (6 stages), 1 two CTAs (3 stages) for e <= 2
 	int recover_geo = -1;  // LZGPU_RECOVER_GEO: -1 automatic, 0 / 1 as above, 2 one 16-warp CTA per SM
-	int direct_wide = -1;  // LZGPU_DIRECT_WIDE: item width of the DIRECT (Cauchy) degraded read, -1 by item count, 0 = 4 bytes, 1 = 16 bytes
+	int direct_wide = -1;  // LZGPU_DIRECT_WIDE: item width of the DIRECT (Cauchy) degraded read, -1 by item count, 0 = 4 bytes, 1 = 8 / 16 bytes, -2 = route off
 	int promo = 3;  // CU_TENSOR_MAP_L2_PROMOTION_L2_256B: +12% streaming bandwidth over 128B/none (profiles/probe_r1.md)
 };
 
@@ -509,6 +509,7 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 	if (!fs || fs->disabled) return LZGPU_NOT_HANDLED;
 	const int K = goal->k, M = goal->m, N = K + M;
 	const bool direct = lz::uses_cauchy(K, M);   // no Horner syndromes for a Cauchy generator: general rows over the k inputs
+	if (direct && fs->direct_wide == -2) return LZGPU_NOT_HANDLED;   // LZGPU_DIRECT_WIDE=-2: A/B against the generic route
 	if ((part_stride % 16) || (chunk_out_stride % 16)) return LZGPU_NOT_HANDLED;
 	// inputs: the first k available parts (ec_read_plan.h:126-133)
 	int used[LZGPU_MAX_DATA], n_used = 0;
