@@ -983,6 +983,52 @@ static int convert_check_args(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu
 }
 
 // everything enqueued on `st`, nothing synchronised; *tk = pending verification of the source parts (if any)
+// The one-pass route of a slice conversion.  Handled (lz_fused_convert): sources on a Vandermonde generator with at most two data
+// parts lost (their parity rows 0, 1 in use), destinations with up to three parity parts, at least one parity part wanted (data
+// parts alone are BlockConverter picks, served by the degraded read + split).  LZGPU_OK: every wanted part is enqueued, *t_crc
+// holds the destination slice's block CRCs in chunk order and *tk the pending verification; LZGPU_NOT_HANDLED: nothing was enqueued.
+static int try_fused_convert(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_goal *dst, uint32_t n_chunks, uint32_t nb, const void *const *d_parts,
+                             size_t part_stride, const void *const *d_part_crc, const uint8_t *want, void *const *d_out, size_t out_stride,
+                             cudaStream_t st, VerifyTicket *tk, TmpBuf *t_crc, size_t *crc_stride_out) {
+	const int ks = src->k, kd = dst->k, nd = dst->k + dst->m;
+	const uint32_t pbs = (nb + ks - 1) / ks, pbd = (nb + kd - 1) / kd;
+	bool any_crc = false, parity_wanted = false;
+	int used = 0;
+	for (int i = 0; i < ks + src->m && used < ks; ++i)
+		if (d_parts[i]) { ++used; any_crc |= d_part_crc && d_part_crc[i]; }
+	if (used < ks) return LZGPU_NOT_HANDLED;                    // the two-pass route reports the error
+	if (any_crc && !lzgpu_crc_enabled()) return LZGPU_NOT_HANDLED;  // the CRC-disabled build mode keeps its own checks
+	for (int i = kd; i < nd; ++i) parity_wanted |= want[i] != 0;
+	if (!parity_wanted) return LZGPU_NOT_HANDLED;
+	int rc;
+	const size_t crc_stride = (nb + static_cast<size_t>(dst->m) * pbd + 3) & ~size_t(3);
+	if ((rc = t_crc->alloc(n_chunks * crc_stride * 4))) return rc;
+	if (any_crc) {
+		if ((rc = lz_status_acquire(ctx, &tk->slot))) return rc;
+		if (cudaMemsetAsync(tk->slot.d, 0xff, sizeof(unsigned long long) * LZGPU_MAX_PARTS, st) != cudaSuccess) { ticket_drop(ctx, tk); return LZGPU_ERR_CUDA; }
+	}
+	void *outs[LZGPU_MAX_PARTS] = {nullptr};
+	for (int i = 0; i < nd; ++i) outs[i] = want[i] ? d_out[i] : nullptr;
+	bool verifying = false;
+	rc = lz_fused_convert(ctx, src, dst, n_chunks, nb, d_parts, part_stride, any_crc ? d_part_crc : nullptr, outs, out_stride, t_crc->p, crc_stride, st,
+	                      any_crc ? tk->slot.d : nullptr, &verifying);
+	if (rc != LZGPU_OK) {
+		if (any_crc) ticket_drop(ctx, tk);
+		t_crc->release();
+		return rc;
+	}
+	if (any_crc) {
+		tk->fused = true;
+		tk->n_words = 1;
+		tk->blocks = pbs;
+		if (cudaMemcpyAsync(tk->slot.h, tk->slot.d, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st) != cudaSuccess) { ticket_drop(ctx, tk); return LZGPU_ERR_CUDA; }
+	}
+	*crc_stride_out = crc_stride;
+	ctx->stats.chunks_recovered += n_chunks;
+	ctx->stats.chunks_encoded += n_chunks;
+	return LZGPU_OK;
+}
+
 static int convert_enqueue(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_goal *dst, uint32_t n_chunks, uint32_t nb,
                            const void *const *d_parts, size_t part_stride, const void *const *d_part_crc, const uint8_t *want,
                            void *const *d_out, size_t out_stride, void *const *d_out_crc, cudaStream_t st, VerifyTicket *tk) {
@@ -1020,8 +1066,9 @@ static int convert_enqueue(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_go
 		}
 	} else {
 		// kRecoverDataPart / kRecoverParityPart (:102-119): chunk data first (ChunkReadPlanner), then BlockConverter or RecoverParity
-		const uint8_t *image;
-		size_t image_stride;
+		const uint8_t *image = nullptr;
+		size_t image_stride = 0;
+		bool converted = false;   // the one-pass route produced every wanted destination part
 		void *direct_image = (goal_is_std(dst) && want[0]) ? d_out[0] : nullptr;  // a standard destination IS the chunk image
 		if (goal_is_std(src)) {
 			if (!d_parts[0]) { lz_set_error("convert: the standard chunk is not available"); return LZGPU_ERR_TOO_FEW_PARTS; }
@@ -1049,6 +1096,18 @@ static int convert_enqueue(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_go
 			if (direct_image && direct_image != image)
 				CUDA_TRY(cudaMemcpy2DAsync(direct_image, out_stride, image, image_stride, static_cast<size_t>(nb) * B, n_chunks, cudaMemcpyDeviceToDevice, st));
 		} else {
+			// One pass (convert_kernel.cuh): source parts -> destination parts + their CRCs, no chunk image
+			if (!goal_is_std(dst)) {
+				rc = try_fused_convert(ctx, src, dst, n_chunks, nb, d_parts, part_stride, d_part_crc, want, d_out, out_stride, st, tk, &t_crc, &encode_crc_stride);
+				if (rc == LZGPU_OK) {
+					converted = true;
+					d_encode_crc = t_crc.p;
+				} else if (rc != LZGPU_NOT_HANDLED) {
+					return rc;
+				}
+			}
+		}
+		if (!goal_is_std(src) && !converted) {
 			void *d_img = direct_image;
 			image_stride = direct_image ? out_stride : static_cast<size_t>(nb) * B;
 			if (!d_img) {
@@ -1060,7 +1119,7 @@ static int convert_enqueue(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_go
 				return rc;
 			image = static_cast<const uint8_t *>(d_img);
 		}
-		if (!goal_is_std(dst)) {
+		if (!goal_is_std(dst) && !converted) {
 			bool data_wanted = false, parity_wanted = false;
 			void *dp[LZGPU_MAX_DATA] = {nullptr};
 			for (int i = 0; i < nd; ++i) {

@@ -118,6 +118,10 @@ struct TmpBuf {
 		if (p) cudaFreeAsync(p, st);
 	}
 	int alloc(size_t bytes);
+	void release() {
+		if (p) cudaFreeAsync(p, st);
+		p = nullptr;
+	}
 };
 
 int lz_status_acquire(lzgpu_ctx *ctx, StatusSlot *out);
@@ -158,6 +162,12 @@ int lz_fused_encode_split(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chu
 // owns that word (a StatusSlot) and must pass it whenever d_part_crc is given.
 int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, uint32_t nb, const void *const *d_parts, size_t part_stride,
                      const void *const *d_part_crc, const uint8_t *want, void *const *d_out, void *d_chunk_out, size_t chunk_out_stride,
+                     cudaStream_t st, unsigned long long *d_first_bad, bool *verifying);
+// Fused slice conversion (convert_kernel.cuh): k parts of the source slice -> every wanted part of the destination slice (d_out[i],
+// nullptr = not wanted) + the destination slice's block CRCs in chunk order (nb data blocks, then m x pbd parity blocks per chunk),
+// one pass; verification as in lz_fused_recover.  LZGPU_NOT_HANDLED = take the two-pass route.
+int lz_fused_convert(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_goal *dst, uint32_t n_chunks, uint32_t nb, const void *const *d_parts,
+                     size_t part_stride, const void *const *d_part_crc, void *const *d_out, size_t out_stride, void *d_crc, size_t crc_stride,
                      cudaStream_t st, unsigned long long *d_first_bad, bool *verifying);
 // CRC of 64 KiB blocks: block (c, b) at base + c*chunk_stride + b*65536, out[c*out_chunk_stride + b]
 int lz_fused_crc(lzgpu_ctx *ctx, const void *base, unsigned long long n_blocks, unsigned long long blocks_per_chunk,

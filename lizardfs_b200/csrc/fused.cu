@@ -5,11 +5,13 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <numeric>
 #include <cstdlib>
 #include <cstring>
 
 #include "engine_internal.h"
 #include "fused_kernel.cuh"
+#include "convert_kernel.cuh"
 #include "host_math.h"
 
 using namespace lzd;
@@ -36,6 +38,7 @@ struct FusedState {
 	int striped = -1;
 	int recover_two = -1;  // LZGPU_RECOVER_TWO: -1 automatic, 0 one CTA per SM (6 stages), 1 two CTAs (3 stages) for e <= 2
 	int recover_geo = -1;  // LZGPU_RECOVER_GEO: -1 automatic, 0 / 1 as above, 2 one 16-warp CTA per SM
+	int convert_off = 0;   // LZGPU_CONVERT_FUSED=0: slice conversion through the two-pass route (image, then SPLIT encode)
 	int direct_wide = -1;  // LZGPU_DIRECT_WIDE: item width of the DIRECT (Cauchy) degraded read, -1 by item count, 0 = 4 bytes, 1 = 8 / 16 bytes, -2 = route off
 	int promo = 3;  // CU_TENSOR_MAP_L2_PROMOTION_L2_256B: +12% streaming bandwidth over 128B/none (profiles/probe_r1.md)
 };
@@ -81,6 +84,19 @@ static int set_direct_attr() {
 	return LZGPU_OK;
 }
 
+template <int M>
+static int set_convert_attr() {
+	CUDA_TRY(cudaFuncSetAttribute(fused_convert_kernel<M, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap));
+	CUDA_TRY(cudaFuncSetAttribute(fused_convert_kernel<M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap));
+	CUDA_TRY(cudaFuncSetAttribute(fused_convert_kernel<M, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap));
+	return LZGPU_OK;
+}
+static int set_all_convert_attrs() {
+	int rc;
+	if ((rc = set_convert_attr<1>()) || (rc = set_convert_attr<2>()) || (rc = set_convert_attr<3>())) return rc;
+	return LZGPU_OK;
+}
+
 // function attributes are per device: done once per context
 static int set_all_recover_attrs() {
 	int rc;
@@ -109,6 +125,7 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if (const char *e = std::getenv("LZGPU_RECOVER_TWO")) fs->recover_two = std::atoi(e);
 	if (const char *e = std::getenv("LZGPU_RECOVER_GEO")) fs->recover_geo = std::atoi(e);
 	if (const char *e = std::getenv("LZGPU_DIRECT_WIDE")) fs->direct_wide = std::atoi(e);
+	if (const char *e = std::getenv("LZGPU_CONVERT_FUSED")) fs->convert_off = std::atoi(e) == 0;
 	if (const char *e = std::getenv("LZGPU_STRIPED")) fs->striped = std::atoi(e);  // 0 never, 1 whenever possible, unset = automatic
 	void *fn = nullptr;
 	cudaDriverEntryPointQueryResult qres;
@@ -185,6 +202,7 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if ((rc = set_smem_attr<3, false, 5, 8, 128>(smem128))) return rc;
 #endif
 	if ((rc = set_all_recover_attrs())) return rc;
+	if ((rc = set_all_convert_attrs())) return rc;
 	return LZGPU_OK;
 }
 
@@ -510,6 +528,7 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 	const int K = goal->k, M = goal->m, N = K + M;
 	const bool direct = lz::uses_cauchy(K, M);   // no Horner syndromes for a Cauchy generator: general rows over the k inputs
 	if (direct && fs->direct_wide == -2) return LZGPU_NOT_HANDLED;   // LZGPU_DIRECT_WIDE=-2: A/B against the generic route
+	const bool direct_forced = direct && fs->direct_wide >= 0;
 	if ((part_stride % 16) || (chunk_out_stride % 16)) return LZGPU_NOT_HANDLED;
 	// inputs: the first k available parts (ec_read_plan.h:126-133)
 	int used[LZGPU_MAX_DATA], n_used = 0;
@@ -533,6 +552,12 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 			p.erased_idx[e++] = static_cast<uint8_t>(j);
 		}
 	if (e == 0 || e != n_par) return LZGPU_NOT_HANDLED;
+	// Measured (profiles/sweep_r2.md, run 8): with general coefficients the rebuild is bound by the bit-plane multiplies, not by HBM, and
+	// the grid-stride gf_dot_kernel (full occupancy, no stage barriers) does e >= 2 rows faster than this kernel's 16 warps per SM
+	// even though it needs separate CRC and image passes: ec(8,6) three lost 2.7 ms against 6.2 ms per 64 chunks.  One lost part
+	// (ec(8,6): 2.45 ms against 3.98 with verification and image), and two lost parts when the call verifies and wants the image
+	// (ec(4,5) 4.39 against 4.87, ec(21,4) 5.05 against 5.38), stay here.
+	if (direct && !direct_forced && !(e == 1 || (e == 2 && d_part_crc && d_chunk_out))) return LZGPU_NOT_HANDLED;
 	// every requested missing part must be a data part
 	for (int i = K; i < N; ++i)
 		if (want[i] && !d_parts[i] && d_out && d_out[i]) return LZGPU_NOT_HANDLED;
@@ -704,4 +729,127 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 			if (row01) return launch_recover<4, 0, 0, 1>(ctx, maps, p, smem, st, geo);
 			return launch_recover<4, 0>(ctx, maps, p, smem, st, geo);
 	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fused slice conversion (convert_kernel.cuh)
+// ---------------------------------------------------------------------------------------------------
+template <int M, int E>
+static int launch_convert(lzgpu_ctx *ctx, const TmapArray &maps, const ConvertParams &p, size_t smem, cudaStream_t st) {
+	const int grid = static_cast<int>(std::min<uint64_t>(p.total_units, static_cast<uint64_t>(ctx->sm_count) * 2));
+	fused_convert_kernel<M, E><<<grid, kConvertThreads, smem, st>>>(maps, p);
+	CUDA_TRY(cudaGetLastError());
+	ctx->stats.kernel_launches++;
+	return LZGPU_OK;
+}
+
+// Source slice `src` (k of its parts available in d_parts, at most two data parts lost, the parity parts in use being its rows
+// 0 .. e-1) -> every wanted part of the destination slice `dst` in d_out (nullptr = not wanted) + the destination slice's block
+// CRCs in chunk order (d_crc: nb data blocks, then m x pbd parity blocks per chunk), one pass.  LZGPU_NOT_HANDLED = use the two-pass route.
+int lz_fused_convert(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_goal *dst, uint32_t n_chunks, uint32_t nb, const void *const *d_parts,
+                     size_t part_stride, const void *const *d_part_crc, void *const *d_out, size_t out_stride, void *d_crc, size_t crc_stride,
+                     cudaStream_t st, unsigned long long *d_first_bad, bool *verifying) {
+	FusedState *fs = ctx->fused;
+	*verifying = false;
+	if (!fs || fs->disabled || fs->convert_off) return LZGPU_NOT_HANDLED;
+	const int Ks = src->k, Ms = src->m, Kd = dst->k, Md = dst->m;
+	if (src->kind == LZGPU_KIND_STD || dst->kind == LZGPU_KIND_STD) return LZGPU_NOT_HANDLED;
+	if (lz::uses_cauchy(Ks, Ms) || lz::uses_cauchy(Kd, Md) || Md > 3 || Md < 1) return LZGPU_NOT_HANDLED;
+	if ((part_stride % 16) || (out_stride % 16) || n_chunks == 0 || nb == 0) return LZGPU_NOT_HANDLED;
+	// inputs: the first k available parts (ec_read_plan.h:126-133)
+	ConvertParams p{};
+	int used[LZGPU_MAX_DATA], n_used = 0;
+	for (int i = 0; i < Ks + Ms && n_used < Ks; ++i)
+		if (d_parts[i]) used[n_used++] = i;
+	if (n_used < Ks) return LZGPU_NOT_HANDLED;
+	uint32_t e = 0, n_par = 0;
+	for (int a = 0; a < Ks; ++a) {
+		const int idx = used[a];
+		if (idx < Ks) p.slot_present[idx] = 1;
+		else if (idx == Ks + static_cast<int>(n_par) && n_par < 2) ++n_par;   // parity rows 0, 1 in this order only
+		else return LZGPU_NOT_HANDLED;
+	}
+	for (int j = 0; j < Ks; ++j)
+		if (!p.slot_present[j]) {
+			if (e >= 2) return LZGPU_NOT_HANDLED;
+			p.erased_idx[e++] = static_cast<uint8_t>(j);
+		}
+	if (e != n_par) return LZGPU_NOT_HANDLED;
+	// geometry: G destination stripes = T source stripes per unit
+	const uint32_t g0 = static_cast<uint32_t>(Ks / std::gcd(Ks, Kd));
+	const uint32_t PC = static_cast<uint32_t>(Md - 1);
+	uint32_t G = 0, T = 0, RR = 0, n_stages = 0;
+	size_t smem = 0;
+	for (uint32_t g = g0; g <= 64; g += g0) {
+		const uint32_t R = g * Kd, t = R / Ks;
+		if (R > 64 || R * 4 + e * t * 4 + g * PC * 4 > static_cast<uint32_t>(kConvertThreads) || t * 4 > 256) break;
+		const uint32_t rr = (t * 4 + 7) & ~7u;
+		const size_t stage = static_cast<size_t>(Ks + e) * rr * kStepBytes;
+		const size_t pstage = (static_cast<size_t>(g) * PC * 4 * kStepBytes + 1023) & ~size_t(1023);
+		const size_t fixed = kConvertNPST * pstage + 520 + 8 * (2 * kConvertNPST) + 64;
+		uint32_t ns = 0;
+		for (uint32_t n = 4; n >= 2; --n)
+			if (n * stage + 24 * n + fixed <= static_cast<size_t>(std::min<int>(fs->max_smem, kSmemCap))) { ns = n; break; }
+		if (!ns) break;
+		G = g; T = t; RR = rr; n_stages = ns;
+		smem = ns * stage + 24 * ns + fixed;
+	}
+	if (G == 0) return LZGPU_NOT_HANDLED;
+	const uint32_t pbs = (nb + Ks - 1) / Ks, pbd = (nb + Kd - 1) / Kd;
+	const uint32_t R = G * Kd;
+	p.Kd = Kd; p.G = G; p.pbd = pbd; p.Ks = Ks; p.T = T; p.pbs = pbs; p.region_rows = RR;
+	p.n_chunks = n_chunks; p.nb = nb; p.n_stages = n_stages;
+	p.units_per_chunk = (nb + R - 1) / R;
+	const uint64_t total = static_cast<uint64_t>(p.units_per_chunk) * n_chunks;
+	if (total > 0x7fffffffull) return LZGPU_NOT_HANDLED;
+	p.total_units = static_cast<uint32_t>(total);
+	for (int j = 0; j < Kd; ++j) p.data_out[j] = static_cast<uint8_t *>(d_out[j]);
+	for (int r = 0; r < Md; ++r) p.par_out[r] = static_cast<uint8_t *>(d_out[Kd + r]);
+	p.part_out_stride = out_stride;
+	p.crc = static_cast<uint32_t *>(d_crc);
+	p.crc_stride = crc_stride;
+	p.tables = ctx->d_crc_tables;
+	p.first_bad = d_first_bad;
+	std::memcpy(p.qmult, fs->qmult64, sizeof(p.qmult));
+	p.zconst = lz::crc_of_zeros(LZGPU_BLOCK_SIZE);
+	TmapArray maps;
+	uint32_t n_par_seen = 0;
+	for (int a = 0; a < Ks; ++a) {
+		const int idx = used[a];
+		const uint32_t slot = idx < Ks ? static_cast<uint32_t>(idx) : static_cast<uint32_t>(Ks) + n_par_seen++;
+		p.loaded_slot[a] = static_cast<uint8_t>(slot);
+		p.part_id[slot] = static_cast<uint8_t>(idx);
+		p.stored[slot] = d_part_crc ? static_cast<const uint32_t *>(d_part_crc[idx]) : nullptr;
+		if (p.stored[slot]) *verifying = true;
+		const cuuint64_t dims[3] = {static_cast<cuuint64_t>(kRowBytes), static_cast<cuuint64_t>(pbs) * 4, n_chunks};
+		const cuuint64_t strides[2] = {static_cast<cuuint64_t>(kRowBytes), part_stride};
+		const cuuint32_t box[3] = {kStepBytes, T * 4, 1};
+		const cuuint32_t estr[3] = {1, 1, 1};
+		if (reinterpret_cast<uintptr_t>(d_parts[idx]) % 16) return LZGPU_NOT_HANDLED;
+		CUresult r = fs->encode_tiled(&maps.m[a], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(d_parts[idx]), dims, strides, box, estr,
+		                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, static_cast<CUtensorMapL2promotion>(fs->promo),
+		                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+		if (r != CUDA_SUCCESS) return LZGPU_NOT_HANDLED;
+	}
+	p.n_loaded = static_cast<uint32_t>(Ks);
+	for (uint32_t x = 0; x < e; ++x) p.part_id[Ks + x] = static_cast<uint8_t>(Ks + x);
+	if (*verifying && !d_first_bad) return LZGPU_NOT_HANDLED;
+	if (e == 2) {
+		uint8_t gx0 = 1, gx1 = 1;
+		for (int t = 0; t < p.erased_idx[0]; ++t) gx0 = lz::gf_mul_host(gx0, 2);
+		for (int t = 0; t < p.erased_idx[1]; ++t) gx1 = lz::gf_mul_host(gx1, 2);
+		coef_planes_set(p.w[0], gx0);
+		coef_planes_set(p.w[1], lz::gf_inv_host(gx0 ^ gx1));
+	}
+	p.dbl0 = (e == 2 && p.erased_idx[0] <= 4) ? p.erased_idx[0] : 0xffu;
+#define LZ_CONVERT_CASE(MM) \
+	case MM: \
+		return e == 0 ? launch_convert<MM, 0>(ctx, maps, p, smem, st) : e == 1 ? launch_convert<MM, 1>(ctx, maps, p, smem, st) : launch_convert<MM, 2>(ctx, maps, p, smem, st);
+	switch (Md) {
+		LZ_CONVERT_CASE(1)
+		LZ_CONVERT_CASE(2)
+		LZ_CONVERT_CASE(3)
+	}
+#undef LZ_CONVERT_CASE
+	return LZGPU_NOT_HANDLED;
 }

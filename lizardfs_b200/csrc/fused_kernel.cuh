@@ -646,7 +646,9 @@ fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 	constexpr uint32_t CPI = 32 / W;
 	// form of the bit-plane multiply: the in-place form (NS = 2: 1 ALU + 2 FMA ops per bit) where registers allow, the funnel-shift
 	// form (NS = 7: one temporary less per term) on the two-CTA geometry with its 96 registers
-	constexpr int kMacNS = GEO == 1 ? 7 : 2;
+	// funnel-shift bits of the general multiply: levels the ALU pipe (8 + NS + 4 E ops per word) against the FMA pipe (E (15 - NS)) when E
+	// coefficients share every loaded word (DIRECT form), as in gf_dot_kernel
+	constexpr int kMacNS = R0 == kRecoverDirect ? (E == 1 ? 3 : E == 2 ? 5 : 7) : GEO == 1 ? 7 : 2;
 	const uint32_t n_items = 4 * CPI * G;
 	const uint32_t n_gf_warps = (min(n_items, (uint32_t)kThreads) + 31) / 32;
 	const uint32_t n_stage_warps = max((ROWS + 31) / 32, n_gf_warps);

@@ -114,6 +114,97 @@ def test_convert_full_size_round_trip(eng, oracle):
     assert pb == -(-nb // 3)
 
 
+FUSED_CONVERSIONS = [
+    # source, lost parts, blocks, destination: every pair the one-pass kernel takes (Vandermonde source, <= 2 data parts lost with parity
+    # rows 0, 1 in use, destination with <= 3 parity parts), ragged block counts on both stripings, and two that must fall back
+    ("ec(8,2)", (1, 4), 48, "ec(3,2)", True), ("ec(8,2)", (1, 4), 61, "ec(3,2)", True), ("ec(8,2)", (0,), 35, "ec(3,2)", True),
+    ("ec(8,2)", (), 50, "ec(3,2)", True), ("ec(8,2)", (7, 8), 29, "ec(5,3)", False),        # parity row 1 alone in use: two passes
+    ("ec(3,2)", (0, 2), 31, "ec(8,2)", True), ("ec(3,2)", (1,), 10, "xor3", True), ("xor3", (2,), 25, "ec(3,2)", True),
+    ("xor2", (), 9, "ec(5,3)", True), ("ec(5,3)", (0, 3), 23, "xor2", True), ("ec(5,3)", (0, 1, 4), 11, "ec(3,2)", False),  # three lost: two passes
+    ("ec(8,2)", (2, 5), 70, "ec(8,2)", None),                                               # same slice type: a plain rebuild
+]
+
+
+@pytest.mark.parametrize("src_name,lost,nb,dst_name,fused", FUSED_CONVERSIONS)
+def test_convert_in_one_pass_matches_two_passes_and_oracle(oracle, src_name, lost, nb, dst_name, fused):
+    """slice conversion without the chunk image (convert_kernel.cuh): same bytes and CRCs as the two-pass route (LZGPU_CONVERT_FUSED=0) and
+    as the oracle's restatement of SliceRecoveryPlanner; two launches (the kernel + the CRC scatter); a flipped bit is reported at its
+    (chunk, part, block) on both routes"""
+    import os
+    src, dst = GOALS[src_name], GOALS[dst_name]
+    n = 3
+    chunks = [O.fill_chunk(oracle, nb * BLOCK, 53, c) for c in range(n)]
+    slices = [make_slice(oracle, src, ch) for ch in chunks]
+    ns, nd = src[1] + src[2], dst[1] + dst[2]
+    parts = [None if i in lost else np.stack([slices[c][0][i] for c in range(n)]) for i in range(ns)]
+    crcs = [None if i in lost else np.stack([slices[c][1][i] for c in range(n)]) for i in range(ns)]
+    e1 = L.Engine()
+    os.environ["LZGPU_CONVERT_FUSED"] = "0"
+    try:
+        e2 = L.Engine()
+    finally:
+        del os.environ["LZGPU_CONVERT_FUSED"]
+    for with_crc in (True, False):
+        before = e1.stats()["kernel_launches"]
+        out, ocrc = e1.convert_chunks(slice_of(src_name), slice_of(dst_name), nb, parts, [1] * nd, part_crc=crcs if with_crc else None)
+        launches = e1.stats()["kernel_launches"] - before
+        if fused is True:
+            assert launches == 2, (launches, "the conversion left the one-pass kernel")
+        elif fused is False:
+            assert launches > 2
+        out2, ocrc2 = e2.convert_chunks(slice_of(src_name), slice_of(dst_name), nb, parts, [1] * nd, part_crc=crcs if with_crc else None)
+        for i in range(nd):
+            assert (out[i] == out2[i]).all() and (ocrc[i] == ocrc2[i]).all(), (src_name, dst_name, i)
+    for c in range(n):
+        avail = [None if p is None else p[c] for p in parts]
+        avail_crc = [None if x is None else x[c] for x in crcs]
+        rc, want_out, want_crc, _ = O.convert_chunk(oracle, src, avail, avail_crc, dst, [1] * nd, nb)
+        assert rc == 0
+        for i in range(nd):
+            assert (out[i][c] == want_out[i]).all(), (src_name, dst_name, c, i)
+            assert (ocrc[i][c] == want_crc[i]).all(), (src_name, dst_name, c, i)
+    # one wanted parity part only (what a replication job asks for)
+    want = [0] * nd
+    want[nd - 1] = 1
+    o1, c1 = e1.convert_chunks(slice_of(src_name), slice_of(dst_name), nb, parts, want, part_crc=crcs)
+    assert all(o1[i] is None for i in range(nd - 1)) and (o1[nd - 1] == out[nd - 1]).all() and (c1[nd - 1] == ocrc[nd - 1]).all()
+    # a flipped bit in a part that is read
+    used = [i for i in range(ns) if parts[i] is not None][:src[1]]
+    victim = used[-1]
+    bad = [None if p is None else p.copy() for p in parts]
+    pbs = -(-nb // src[1])
+    bad[victim][1, (pbs - 1) * BLOCK + 4321] ^= 0x08
+    for e in (e1, e2):
+        with pytest.raises(L.ChunkCrcError) as ei:
+            e.convert_chunks(slice_of(src_name), slice_of(dst_name), nb, bad, [1] * nd, part_crc=crcs)
+        assert ei.value.where == (1, victim, pbs - 1)
+
+
+def test_convert_full_size_in_one_pass_vs_encode(eng):
+    """64 MiB chunks: ec(8,2) with data parts 1 and 4 lost -> every ec(3,2) part, against a direct ec(3,2) encode of the same chunks"""
+    nb, n = 1024, 3
+    rng = np.random.default_rng(77)
+    chunks = rng.integers(0, 256, (n, nb * BLOCK), dtype=np.uint8)
+    s82, s32 = slice_of("ec(8,2)"), slice_of("ec(3,2)")
+    p82, c82 = eng.encode_chunks(s82, chunks)
+    d82 = eng.split_chunks(s82, chunks)
+    parts = [None if j in (1, 4) else d82[j] for j in range(8)] + [p82[:, 0], p82[:, 1]]
+    crcs = [None if j in (1, 4) else np.ascontiguousarray(c82[:, j:nb:8]) for j in range(8)] + [np.ascontiguousarray(c82[:, nb + r * 128: nb + (r + 1) * 128]) for r in range(2)]
+    before = eng.stats()["kernel_launches"]
+    out, ocrc = eng.convert_chunks(s82, s32, nb, parts, [1] * 5, part_crc=crcs)
+    assert eng.stats()["kernel_launches"] - before == 2 * -(-n // 2) or eng.stats()["kernel_launches"] - before == 2
+    p32, c32 = eng.encode_chunks(s32, chunks)
+    d32 = eng.split_chunks(s32, chunks)
+    pb = 342
+    for j in range(3):
+        assert (out[j] == d32[j]).all()
+        mine = c32[:, j:nb:3]
+        assert (ocrc[j][:, : mine.shape[1]] == mine).all()
+    for r in range(2):
+        assert (out[3 + r] == p32[:, r]).all()
+        assert (ocrc[3 + r] == c32[:, nb + r * pb: nb + (r + 1) * pb]).all()
+
+
 def test_scrub_exact_sparse_rule(eng, oracle):
     rng = np.random.default_rng(3)
     n = 9
