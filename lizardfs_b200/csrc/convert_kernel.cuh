@@ -18,8 +18,9 @@
 // (bl = 0 .. R-1) is row (bl % Ks) * region_rows + (bl / Ks) * 4 + q.
 //
 // Roles per 128-byte step (every warp walks all of them in this order; barriers are mbarriers, no CTA-wide sync):
-//   REBUILD  (E > 0; the last T warps) item (source stripe t, quarter q, 16-byte column): syndromes by Horner over the surviving
-//            data columns + the parity columns, RAID-6 solve, rebuilt words stored into the lost slots' rows; arrive `rfull`.
+//   REBUILD  (E > 0; the last T warps, ONE STEP AHEAD of everybody) item (source stripe t, quarter q, 16-byte column): syndromes by
+//            Horner over the surviving data columns + the parity columns, RAID-6 solve, rebuilt words stored into the lost slots'
+//            rows of the next step's stage; arrive `rfull`.
 //   GF       (after `rfull`) item (destination stripe g, quarter q, column): walks the Kd blocks of the stripe, stores them
 //            part-major into the destination data parts, Horner-evaluates the destination parity rows, stores them and stages
 //            rows 1.. for their CRC.
@@ -137,9 +138,73 @@ fused_convert_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 	const bool is_rb_warp = E > 0 && warp >= first_rb_warp;
 	const uint32_t rb_tid = tid - first_rb_warp * 32;
 
+	// REBUILD role for the stage at shared address `stage` (E > 0, rebuild warps only): the lost source data parts of every source stripe
+	auto rebuild_stage = [&](uint32_t stage, uint32_t rfull_bar) {
+		for (uint32_t item = rb_tid; item < n_rb_items; item += n_rb_warps * 32) {
+			const uint32_t col = item % CPI, q = (item / CPI) & 3, t = item / (4 * CPI);
+			const uint32_t r0 = t * 4 + q;      // row inside every slot region (regions start on multiples of 8 rows)
+			const uint32_t a_item = ((stage + r0 * kStepBytes) ^ ((col ^ (r0 & 7)) << 4));
+			uint32_t s0[W], s1[W];
+#pragma unroll
+			for (int w = 0; w < W; ++w) s0[w] = s1[w] = 0;
+			for (int j = static_cast<int>(Ks) - 1; j >= 0; --j) {
+				uint32_t v[W];
+#pragma unroll
+				for (int w = 0; w < W; ++w) v[w] = 0;
+				if (p.slot_present[j]) lds_item<W>(a_item + j * RR * kStepBytes, v);
+#pragma unroll
+				for (int w = 0; w < W; ++w) {
+					s0[w] ^= v[w];
+					if (E == 2) s1[w] = gf_x2_add(s1[w], v[w]);
+				}
+			}
+			{
+				uint32_t v[W];
+				lds_item<W>(a_item + Ks * RR * kStepBytes, v);
+#pragma unroll
+				for (int w = 0; w < W; ++w) s0[w] ^= v[w];
+				if (E == 2) {
+					lds_item<W>(a_item + (Ks + 1) * RR * kStepBytes, v);
+#pragma unroll
+					for (int w = 0; w < W; ++w) s1[w] ^= v[w];
+				}
+			}
+			if (E == 2) {
+				// S0 = d0 ^ d1, S1 = 2^x0 d0 ^ 2^x1 d1  ->  d1 = (S1 ^ 2^x0 S0) / (2^x0 ^ 2^x1), d0 = S0 ^ d1: the unique
+				// solution, i.e. the bytes of the reference's inverted matrix (reed_solomon.h:229-281)
+				uint32_t tt[W];
+#pragma unroll
+				for (int w = 0; w < W; ++w) tt[w] = s0[w];
+				if (p.dbl0 != 0xffu) {
+					for (uint32_t i = 0; i < p.dbl0; ++i)
+#pragma unroll
+						for (int w = 0; w < W; ++w) tt[w] = gf_x2_add(tt[w], 0u);
+				} else {
+#pragma unroll
+					for (int w = 0; w < W; ++w) tt[w] = gf_mac<2>(0u, tt[w], p.w[0]);
+				}
+#pragma unroll
+				for (int w = 0; w < W; ++w) {
+					s1[w] = gf_mac<2>(0u, s1[w] ^ tt[w], p.w[1]);
+					s0[w] ^= s1[w];
+				}
+				sts_item<W>(a_item + p.erased_idx[1] * RR * kStepBytes, s1);
+			}
+			sts_item<W>(a_item + p.erased_idx[0] * RR * kStepBytes, s0);
+		}
+		__syncwarp();
+		if (lane == 0) mbar_arrive(rfull_bar);
+	};
+
 	uint32_t win[FW];
 	FoldAux aux;
 	uint32_t it = 0, st = 0, ph = 0, pst = 0, pph = 0, unit_parity = 0;
+	if constexpr (E > 0) {
+		if (is_rb_warp && total_steps) {   // the first step's stage (every later one is rebuilt one step ahead, inside the loop)
+			mbar_wait(a_full, 0);
+			rebuild_stage(sbase, a_rfull);
+		}
+	}
 
 	for (uint32_t unit = blockIdx.x; unit < p.total_units; unit += gridDim.x, unit_parity ^= 1) {
 		const uint32_t c = unit / p.units_per_chunk, ui = unit % p.units_per_chunk;
@@ -159,58 +224,15 @@ fused_convert_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 				const uint32_t pstage = pstage0 + pst * pstage_bytes;
 				mbar_wait(a_full + 8 * st, ph);
 
-				// ---------------- REBUILD role: the lost source data parts of every source stripe of the unit ----------------
+				// ---------------- REBUILD role, one stage ahead ----------------
+				// The rebuild warps fill the lost rows of the NEXT step's stage before they take their share of this step, so the other
+				// warps find `rfull` complete when they get there (the rebuild runs beside their GF / CRC work of the previous step instead
+				// of in front of everybody).  The stage of step it+1 is loaded: its refill was issued when step it+1-NST was released.
 				if constexpr (E > 0) {
-					if (is_rb_warp) {
-						for (uint32_t item = rb_tid; item < n_rb_items; item += n_rb_warps * 32) {
-							const uint32_t col = item % CPI, q = (item / CPI) & 3, t = item / (4 * CPI);
-							const uint32_t r0 = t * 4 + q;      // row inside every slot region (regions start on multiples of 8 rows)
-							const uint32_t a_item = ((stage + r0 * kStepBytes) ^ ((col ^ (r0 & 7)) << 4));
-							uint32_t s0[W], s1[W];
-#pragma unroll
-							for (int w = 0; w < W; ++w) s0[w] = s1[w] = 0;
-							for (int j = static_cast<int>(Ks) - 1; j >= 0; --j) {
-								uint32_t v[W];
-#pragma unroll
-								for (int w = 0; w < W; ++w) v[w] = 0;
-								if (p.slot_present[j]) lds_item<W>(a_item + j * RR * kStepBytes, v);
-#pragma unroll
-								for (int w = 0; w < W; ++w) {
-									s0[w] ^= v[w];
-									if (E == 2) s1[w] = gf_x2_add(s1[w], v[w]);
-								}
-							}
-							{
-								uint32_t v[W];
-								lds_item<W>(a_item + Ks * RR * kStepBytes, v);
-#pragma unroll
-								for (int w = 0; w < W; ++w) s0[w] ^= v[w];
-								if (E == 2) {
-									lds_item<W>(a_item + (Ks + 1) * RR * kStepBytes, v);
-#pragma unroll
-									for (int w = 0; w < W; ++w) s1[w] ^= v[w];
-								}
-							}
-							if (E == 2) {
-								// S0 = d0 ^ d1, S1 = 2^x0 d0 ^ 2^x1 d1  ->  d1 = (S1 ^ 2^x0 S0) / (2^x0 ^ 2^x1), d0 = S0 ^ d1: the unique
-								// solution, i.e. the bytes of the reference's inverted matrix (reed_solomon.h:229-281)
-#pragma unroll
-								for (int w = 0; w < W; ++w) {
-									uint32_t tt = s0[w];
-									if (p.dbl0 != 0xffu) {
-										for (uint32_t i = 0; i < p.dbl0; ++i) tt = gf_x2_add(tt, 0u);
-									} else {
-										tt = gf_mac<2>(0u, tt, p.w[0]);
-									}
-									s1[w] = gf_mac<2>(0u, s1[w] ^ tt, p.w[1]);
-									s0[w] ^= s1[w];
-								}
-								sts_item<W>(a_item + p.erased_idx[1] * RR * kStepBytes, s1);
-							}
-							sts_item<W>(a_item + p.erased_idx[0] * RR * kStepBytes, s0);
-						}
-						__syncwarp();
-						if (lane == 0) mbar_arrive(a_rfull + 8 * st);
+					if (is_rb_warp && it + 1 < total_steps) {
+						const uint32_t st1 = st + 1 == NST ? 0 : st + 1, ph1 = st + 1 == NST ? ph ^ 1 : ph;
+						mbar_wait(a_full + 8 * st1, ph1);
+						rebuild_stage(sbase + st1 * stage_bytes, a_rfull + 8 * st1);
 					}
 					mbar_wait(a_rfull + 8 * st, ph);
 				}

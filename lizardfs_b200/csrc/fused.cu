@@ -38,6 +38,7 @@ struct FusedState {
 	int striped = -1;
 	int recover_two = -1;  // LZGPU_RECOVER_TWO: -1 automatic, 0 one CTA per SM (6 stages), 1 two CTAs (3 stages) for e <= 2
 	int recover_geo = -1;  // LZGPU_RECOVER_GEO: -1 automatic, 0 / 1 as above, 2 one 16-warp CTA per SM
+	int cauchy_encode_off = 0;   // LZGPU_CAUCHY_FUSED=0: Cauchy-generator encodes on gf_dot_kernel + CRC passes instead of the fused kernel
 	int convert_off = 0;   // LZGPU_CONVERT_FUSED=0: slice conversion through the two-pass route (image, then SPLIT encode)
 	int direct_wide = -1;  // LZGPU_DIRECT_WIDE: item width of the DIRECT (Cauchy) degraded read, -1 by item count, 0 = 4 bytes, 1 = 8 / 16 bytes, -2 = route off
 	int promo = 3;  // CU_TENSOR_MAP_L2_PROMOTION_L2_256B: +12% streaming bandwidth over 128B/none (profiles/probe_r1.md)
@@ -126,6 +127,7 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if (const char *e = std::getenv("LZGPU_RECOVER_GEO")) fs->recover_geo = std::atoi(e);
 	if (const char *e = std::getenv("LZGPU_DIRECT_WIDE")) fs->direct_wide = std::atoi(e);
 	if (const char *e = std::getenv("LZGPU_CONVERT_FUSED")) fs->convert_off = std::atoi(e) == 0;
+	if (const char *e = std::getenv("LZGPU_CAUCHY_FUSED")) fs->cauchy_encode_off = std::atoi(e) == 0;
 	if (const char *e = std::getenv("LZGPU_STRIPED")) fs->striped = std::atoi(e);  // 0 never, 1 whenever possible, unset = automatic
 	void *fn = nullptr;
 	cudaDriverEntryPointQueryResult qres;
@@ -410,6 +412,7 @@ int lz_fused_encode(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, u
 	if (!fs || fs->disabled) return LZGPU_NOT_HANDLED;
 	const int K = goal->k, M = goal->m;
 	if (lz::uses_cauchy(K, M)) {
+		if (fs->cauchy_encode_off) return LZGPU_NOT_HANDLED;   // LZGPU_CAUCHY_FUSED=0: gf_dot_kernel + the fused CRC kernel (A/B)
 		// Cauchy generator (m >= 5, or m == 4 and k > 20; reed_solomon.h:168-172): arbitrary coefficients, bit-plane multiply inside
 		// the fused kernel, in passes of up to four parity rows over the same data (the TMA stream, the fused parity CRCs and the
 		// part-major stores stay; the first pass also checksums the data blocks).  A shape one pass cannot take leaves the whole
@@ -481,7 +484,6 @@ int lz_fused_crc(lzgpu_ctx *ctx, const void *base, unsigned long long n_blocks, 
 // fused degraded read
 // ---------------------------------------------------------------------------------------------------
 // DIRECT form of the degraded read (any generator; the Cauchy codes): 16-warp CTA, runtime k, 16- or 4-byte items
-constexpr uint32_t kDirectWideItems = 192;
 template <int E>
 static int launch_direct(lzgpu_ctx *ctx, const TmapArray &maps, const RecoverParams &p, size_t smem, cudaStream_t st, bool wide) {
 	const int grid = static_cast<int>(std::min<uint64_t>(p.total_units, static_cast<uint64_t>(ctx->sm_count)));
@@ -707,7 +709,8 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 	const bool row0 = p.par_row[0] == 0, row01 = e >= 2 && consecutive;
 	if (direct) {
 		// item width: 16-byte items leave most of the 16 warps without work when k is large (G small)
-		const bool wide = fs->direct_wide >= 0 ? fs->direct_wide != 0 : 32 * G >= kDirectWideItems;   // 32 G = the number of 16-byte items per step
+		// run 8: the 8 / 16-byte items win on every shape (ec(32,4) four lost: 12.0 ms against 38.0 per 64 chunks); 4-byte items stay for A/B
+		const bool wide = fs->direct_wide >= 0 ? fs->direct_wide != 0 : true;
 		switch (e) {
 			case 1: return launch_direct<1>(ctx, maps, p, smem, st, wide);
 			case 2: return launch_direct<2>(ctx, maps, p, smem, st, wide);
