@@ -84,22 +84,38 @@ fused_convert_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 	               a_pempty = a_pfull + 8 * kConvertNPST;
 
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	// Warp roles.  WORKER warps (the first n_wk) own the CRC streams and the GF items; with lost parts the remaining warps are
+	// REBUILD warps and do nothing else: they run ahead of the workers by as many stages as are loaded, so the workers find the
+	// lost rows in place (`rfull`) when a stage's turn comes.  (Measured, runs 9 / 10: with the rebuild in front of — or inside — warps
+	// that also carry GF items every step waited for it, profiles/probe_r2.md section 11.)
+	const uint32_t n_rows = DROWS + SPROWS + PROWS;
+	const uint32_t n_wk = E ? (n_rows + 31) / 32 : NT / 32;        // the host guarantees n_wk < NT / 32 when E > 0
+	const uint32_t n_wk_threads = n_wk * 32;
+	const uint32_t n_rb_warps = NT / 32 - n_wk;
 	const uint32_t n_items = 4 * CPI * G;
-	const uint32_t n_gf_warps = (min(n_items, (uint32_t)NT) + 31) / 32;
+	const uint32_t n_gf_warps = min((n_items + 31) / 32, n_wk);
 	const uint32_t n_rb_items = 4 * CPI * T;
-	const uint32_t n_rb_warps = E ? min((n_rb_items + 31) / 32, (uint32_t)(NT / 32)) : 0;
-	const uint32_t first_rb_warp = NT / 32 - n_rb_warps;
-	const uint32_t first_pwarp = (DROWS + SPROWS) / 32, last_pwarp = PROWS ? (DROWS + SPROWS + PROWS - 1) / 32 : 0;
+	const uint32_t first_pwarp = (DROWS + SPROWS) / 32, last_pwarp = PROWS ? (n_rows - 1) / 32 : 0;
 
 	const uint32_t my_units = blockIdx.x < p.total_units ? (p.total_units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 	const uint32_t total_steps = my_units * kStepsPerUnit;
 
-	// load of step `step` of unit (chunk c, unit ui of the chunk) into stage st: one box of T*4 rows per part that is read
-	auto issue_load = [&](uint32_t c, uint32_t ui, uint32_t step, uint32_t st) {
+	// load of this CTA's step number `n` (unit blockIdx.x + (n / 128) * gridDim.x, step n % 128) into stage st: one box of T*4 rows per
+	// part that is read
+	auto issue_load = [&](uint32_t n, uint32_t st) {
+		const uint32_t unit = blockIdx.x + (n / kStepsPerUnit) * gridDim.x, step = n % kStepsPerUnit;
+		const uint32_t c = unit / p.units_per_chunk, ui = unit % p.units_per_chunk;
 		mbar_expect_tx(a_full + 8 * st, p.n_loaded * box_bytes);
 		for (uint32_t i = 0; i < p.n_loaded; ++i)
 			tma_load_3d(sbase + st * stage_bytes + p.loaded_slot[i] * RR * kStepBytes, &tmaps.m[i], static_cast<int>(step * kStepBytes),
 			            static_cast<int>(ui * T * 4), static_cast<int>(c), a_full + 8 * st);
+	};
+	// release stage st after step n; the arrival that completes the phase refills it with step n + NST
+	auto release_stage = [&](uint32_t n, uint32_t st) {
+		if (lane == 0 && mbar_arrive_is_last(a_empty + 8 * st) && n + NST < total_steps) {
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			issue_load(n + NST, st);
+		}
 	};
 
 	if (tid == 0) {
@@ -113,34 +129,13 @@ fused_convert_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 			mbar_init(a_pempty + 8 * s, (PROWS ? (last_pwarp - first_pwarp + 1) : 1) * LZ_RING_ARRIVERS);
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-		for (uint32_t g0 = 0; g0 < NST && g0 < total_steps; ++g0)
-			issue_load(blockIdx.x / p.units_per_chunk, blockIdx.x % p.units_per_chunk, g0, g0);
+		for (uint32_t g0 = 0; g0 < NST && g0 < total_steps; ++g0) issue_load(g0, g0);
 	}
 	__syncthreads();
 
-	// ===================== role assignment =====================
-	const bool is_data_row = tid < DROWS;
-	const bool is_sp_row = E > 0 && tid >= DROWS && tid < DROWS + SPROWS;
-	const bool is_parity_row = PC > 0 && tid >= DROWS + SPROWS && tid < DROWS + SPROWS + PROWS;
-	// data stream: chunk block bl of the unit, quarter q
-	const uint32_t my_q = tid & 3;                              // DROWS and SPROWS are multiples of 4
-	const uint32_t my_bl = tid >> 2;
-	const uint32_t my_a = is_data_row ? my_bl % Ks : (is_sp_row ? Ks + (tid - DROWS) / (T * 4) : 0);
-	const uint32_t my_t = is_data_row ? my_bl / Ks : (is_sp_row ? ((tid - DROWS) >> 2) % T : 0);
-	const uint32_t prow = tid - DROWS - SPROWS;                 // staged destination parity row (g*PC + r')*4 + q
-	const uint32_t my_row = is_parity_row ? prow : my_a * RR + my_t * 4 + my_q;
-	const uint32_t row_addr0 = ((is_parity_row ? pstage0 : sbase) + my_row * kStepBytes) ^ ((my_row & 7) << 4);
-	const uint32_t row_stride = is_parity_row ? pstage_bytes : stage_bytes;
-	// a source parity row is only folded when its stored CRC is to be checked; data rows always (their CRC is an output)
-	const bool has_stream = is_data_row || is_parity_row || (is_sp_row && p.stored[my_a] != nullptr);
-	const bool warp_has_items = warp < n_gf_warps;
-	const bool warp_has_prow = PROWS && warp >= first_pwarp && warp <= last_pwarp;
-	const bool is_rb_warp = E > 0 && warp >= first_rb_warp;
-	const uint32_t rb_tid = tid - first_rb_warp * 32;
-
-	// REBUILD role for the stage at shared address `stage` (E > 0, rebuild warps only): the lost source data parts of every source stripe
+	// REBUILD role for the stage at shared address `stage`: the lost source data parts of every source stripe of the unit
 	auto rebuild_stage = [&](uint32_t stage, uint32_t rfull_bar) {
-		for (uint32_t item = rb_tid; item < n_rb_items; item += n_rb_warps * 32) {
+		for (uint32_t item = tid - n_wk_threads; item < n_rb_items; item += n_rb_warps * 32) {
 			const uint32_t col = item % CPI, q = (item / CPI) & 3, t = item / (4 * CPI);
 			const uint32_t r0 = t * 4 + q;      // row inside every slot region (regions start on multiples of 8 rows)
 			const uint32_t a_item = ((stage + r0 * kStepBytes) ^ ((col ^ (r0 & 7)) << 4));
@@ -196,21 +191,45 @@ fused_convert_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 		if (lane == 0) mbar_arrive(rfull_bar);
 	};
 
+	if constexpr (E > 0) {
+		if (warp >= n_wk) {
+			// ===================== REBUILD warps =====================
+			uint32_t st = 0, ph = 0;
+			for (uint32_t n = 0; n < total_steps; ++n) {
+				mbar_wait(a_full + 8 * st, ph);
+				rebuild_stage(sbase + st * stage_bytes, a_rfull + 8 * st);   // (ends with __syncwarp: every lane's reads are done)
+				release_stage(n, st);
+				if (++st == NST) { st = 0; ph ^= 1; }
+			}
+			return;
+		}
+	}
+
+	// ===================== WORKER warps: stream / item assignment =====================
+	const bool is_data_row = tid < DROWS;
+	const bool is_sp_row = E > 0 && tid >= DROWS && tid < DROWS + SPROWS;
+	const bool is_parity_row = PC > 0 && tid >= DROWS + SPROWS && tid < n_rows;
+	// data stream: chunk block bl of the unit, quarter q
+	const uint32_t my_q = tid & 3;                              // DROWS and SPROWS are multiples of 4
+	const uint32_t my_bl = tid >> 2;
+	const uint32_t my_a = is_data_row ? my_bl % Ks : (is_sp_row ? Ks + (tid - DROWS) / (T * 4) : 0);
+	const uint32_t my_t = is_data_row ? my_bl / Ks : (is_sp_row ? ((tid - DROWS) >> 2) % T : 0);
+	const uint32_t prow = tid - DROWS - SPROWS;                 // staged destination parity row (g*PC + r')*4 + q
+	const uint32_t my_row = is_parity_row ? prow : my_a * RR + my_t * 4 + my_q;
+	const uint32_t row_addr0 = ((is_parity_row ? pstage0 : sbase) + my_row * kStepBytes) ^ ((my_row & 7) << 4);
+	const uint32_t row_stride = is_parity_row ? pstage_bytes : stage_bytes;
+	// a source parity row is only folded when its stored CRC is to be checked; data rows always (their CRC is an output)
+	const bool has_stream = is_data_row || is_parity_row || (is_sp_row && p.stored[my_a] != nullptr);
+	const bool warp_has_items = warp < n_gf_warps;
+	const bool warp_has_prow = PROWS && warp >= first_pwarp && warp <= last_pwarp;
+
 	uint32_t win[FW];
 	FoldAux aux;
 	uint32_t it = 0, st = 0, ph = 0, pst = 0, pph = 0, unit_parity = 0;
-	if constexpr (E > 0) {
-		if (is_rb_warp && total_steps) {   // the first step's stage (every later one is rebuilt one step ahead, inside the loop)
-			mbar_wait(a_full, 0);
-			rebuild_stage(sbase, a_rfull);
-		}
-	}
 
 	for (uint32_t unit = blockIdx.x; unit < p.total_units; unit += gridDim.x, unit_parity ^= 1) {
 		const uint32_t c = unit / p.units_per_chunk, ui = unit % p.units_per_chunk;
 		const uint32_t stripe0 = ui * G;                        // first destination stripe of the unit
-		const uint32_t next_unit = unit + gridDim.x;
-		const uint32_t next_c = next_unit / p.units_per_chunk, next_ui = next_unit % p.units_per_chunk;
 #pragma unroll
 		for (int i = 0; i < FW; ++i) win[i] = 0;
 #pragma unroll
@@ -224,23 +243,12 @@ fused_convert_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 				const uint32_t pstage = pstage0 + pst * pstage_bytes;
 				mbar_wait(a_full + 8 * st, ph);
 
-				// ---------------- REBUILD role, one stage ahead ----------------
-				// The rebuild warps fill the lost rows of the NEXT step's stage before they take their share of this step, so the other
-				// warps find `rfull` complete when they get there (the rebuild runs beside their GF / CRC work of the previous step instead
-				// of in front of everybody).  The stage of step it+1 is loaded: its refill was issued when step it+1-NST was released.
-				if constexpr (E > 0) {
-					if (is_rb_warp && it + 1 < total_steps) {
-						const uint32_t st1 = st + 1 == NST ? 0 : st + 1, ph1 = st + 1 == NST ? ph ^ 1 : ph;
-						mbar_wait(a_full + 8 * st1, ph1);
-						rebuild_stage(sbase + st1 * stage_bytes, a_rfull + 8 * st1);
-					}
-					mbar_wait(a_rfull + 8 * st, ph);
-				}
+				if constexpr (E > 0) mbar_wait(a_rfull + 8 * st, ph);   // the lost rows of this stage are in place
 
 				// ---------------- GF role: destination stripes ----------------
 				if (warp_has_items) {
 					if (PC > 0) mbar_wait(a_pempty + 8 * pst, pph ^ 1);
-					for (uint32_t item = tid; item < n_items; item += NT) {
+					for (uint32_t item = tid; item < n_items; item += n_wk_threads) {
 						const uint32_t col = item % CPI, q = (item / CPI) & 3, g = item / (4 * CPI);
 						uint32_t acc[M][W];
 #pragma unroll
@@ -290,11 +298,7 @@ fused_convert_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 				if (PC > 0 && warp_has_prow) mbar_wait(a_pfull + 8 * pst, pph);
 				if (has_stream) fold_step<FW, true>(win, aux, sub_step * 32, row_addr0 + (is_parity_row ? pst : st) * row_stride);
 				__syncwarp();
-				if (lane == 0 && mbar_arrive_is_last(a_empty + 8 * st) && it + NST < total_steps) {
-					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-					if (step + NST < kStepsPerUnit) issue_load(c, ui, step + NST, st);
-					else issue_load(next_c, next_ui, step + NST - kStepsPerUnit, st);
-				}
+				release_stage(it, st);
 				if (PC > 0 && warp_has_prow && LZ_RING_LANE(lane)) mbar_arrive(a_pempty + 8 * pst);
 				++it;
 				if (++st == NST) { st = 0; ph ^= 1; }
@@ -331,7 +335,7 @@ fused_convert_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 			if (stripe < p.pbd) p.crc[c * p.crc_stride + p.nb + r * p.pbd + stripe] = lin ^ p.zconst;
 		}
 		// CRC of destination parity row 0 (plain XOR of the stripe): xor of the data blocks' linear CRCs (crc.h:29 mycrc32_xorblocks)
-		asm volatile("bar.sync 1, %0;" ::"r"(NT) : "memory");
+		asm volatile("bar.sync 1, %0;" ::"r"(n_wk_threads) : "memory");   // worker warps only
 		if (tid < G) {
 			uint32_t x = 0;
 			for (uint32_t j = 0; j < Kd; ++j) {

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <numeric>
 #include <cstdlib>
 #include <cstring>
@@ -783,9 +784,12 @@ int lz_fused_convert(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_goal *ds
 	const uint32_t PC = static_cast<uint32_t>(Md - 1);
 	uint32_t G = 0, T = 0, RR = 0, n_stages = 0;
 	size_t smem = 0;
+	double best_cost = 0;
 	for (uint32_t g = g0; g <= 64; g += g0) {
 		const uint32_t R = g * Kd, t = R / Ks;
-		if (R > 64 || R * 4 + e * t * 4 + g * PC * 4 > static_cast<uint32_t>(kConvertThreads) || t * 4 > 256) break;
+		const uint32_t rows = R * 4 + e * t * 4 + g * PC * 4;
+		// worker warps own the rows; with lost parts at least one warp is left for the rebuild (convert_kernel.cuh)
+		if (R > 64 || t * 4 > 256 || rows > static_cast<uint32_t>(kConvertThreads) - (e ? 32u : 0u)) break;
 		const uint32_t rr = (t * 4 + 7) & ~7u;
 		const size_t stage = static_cast<size_t>(Ks + e) * rr * kStepBytes;
 		const size_t pstage = (static_cast<size_t>(g) * PC * 4 * kStepBytes + 1023) & ~size_t(1023);
@@ -794,8 +798,18 @@ int lz_fused_convert(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_goal *ds
 		for (uint32_t n = 4; n >= 2; --n)
 			if (n * stage + 24 * n + fixed <= static_cast<size_t>(std::min<int>(fs->max_smem, kSmemCap))) { ns = n; break; }
 		if (!ns) break;
-		G = g; T = t; RR = rr; n_stages = ns;
-		smem = ns * stage + 24 * ns + fixed;
+		// instructions per thread and step of the busier role, per chunk block of the unit (rough counts; only the ordering matters):
+		// a worker thread folds one row (~140) and takes its share of the 32 g destination items (~35 per block of the stripe + stores),
+		// a rebuild thread its share of the 32 t source-stripe items (Horner over Ks columns; two syndromes and the solve when e = 2)
+		const uint32_t n_wk = e ? (rows + 31) / 32 : kConvertThreads / 32, n_rb = kConvertThreads / 32 - n_wk;
+		const double worker = 140.0 + std::ceil(32.0 * g / (32.0 * n_wk)) * (35.0 * Kd + 20.0);
+		const double rebuild = e ? std::ceil(static_cast<double>(t) / n_rb) * (e == 2 ? 30.0 * Ks + 150.0 : 6.0 * Ks + 20.0) : 0.0;
+		const double cost = std::max(worker, rebuild) / R;
+		if (G == 0 || cost < best_cost) {
+			best_cost = cost;
+			G = g; T = t; RR = rr; n_stages = ns;
+			smem = ns * stage + 24 * ns + fixed;
+		}
 	}
 	if (G == 0) return LZGPU_NOT_HANDLED;
 	const uint32_t pbs = (nb + Ks - 1) / Ks, pbd = (nb + Kd - 1) / Kd;
