@@ -35,6 +35,24 @@ namespace lzd {
 constexpr int kConvertThreads = 256;
 constexpr int kConvertNPST = 4;
 
+// mbar_wait for warps that mostly find the phase incomplete (the rebuild warps run ahead of the TMA loads): sleep between the polls so
+// that the loop does not take issue slots from the worker warps of the same scheduler (ncu, run 12: the polling loops were 22 % of all
+// executed instructions)
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t addr, uint32_t parity) {
+	uint32_t done;
+	for (;;) {
+		asm volatile(
+		    "{\n\t.reg .pred p;\n\t"
+		    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+		    "selp.u32 %0, 1, 0, p;\n\t}"
+		    : "=r"(done)
+		    : "r"(addr), "r"(parity), "r"(0x989680u)
+		    : "memory");
+		if (done) break;
+		__nanosleep(400);
+	}
+}
+
 struct ConvertParams {
 	// destination slice
 	uint8_t *data_out[32];        // destination data part j (chunk c at + c*part_out_stride), nullptr = not wanted
@@ -48,6 +66,9 @@ struct ConvertParams {
 	uint32_t region_rows;         // rows per slot region in a stage: T*4 rounded up to a multiple of 8
 	uint32_t n_loaded;            // tensor maps in use (one per part that is read)
 	uint8_t loaded_slot[32];      // tensor map i -> slot
+	uint16_t bl_entry[64];        // chunk block bl of a unit -> byte offset of its quarter-0 row in a stage, with the swizzle phase of that
+	                              // row in bit 6: row0 = (bl % Ks) * region_rows + (bl / Ks) * 4, entry = row0 * 128 + (row0 & 4 ? 64 : 0);
+	                              // the 16-byte column col of quarter q is at (stage + entry + q*128) ^ ((col ^ q) << 4)
 	uint8_t slot_present[36];     // slot a < Ks: 1 = read from the part, 0 = lost (rebuilt)
 	uint8_t erased_idx[4];        // data indices of the lost parts, ascending
 	uint8_t part_id[36];          // slot -> source part index (error reporting)
@@ -196,7 +217,7 @@ fused_convert_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 			// ===================== REBUILD warps =====================
 			uint32_t st = 0, ph = 0;
 			for (uint32_t n = 0; n < total_steps; ++n) {
-				mbar_wait(a_full + 8 * st, ph);
+				mbar_wait_relaxed(a_full + 8 * st, ph);   // these warps are ahead of the loads most of the time: poll slowly
 				rebuild_stage(sbase + st * stage_bytes, a_rfull + 8 * st);   // (ends with __syncwarp: every lane's reads are done)
 				release_stage(n, st);
 				if (++st == NST) { st = 0; ph ^= 1; }
@@ -222,6 +243,10 @@ fused_convert_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 	const bool has_stream = is_data_row || is_parity_row || (is_sp_row && p.stored[my_a] != nullptr);
 	const bool warp_has_items = warp < n_gf_warps;
 	const bool warp_has_prow = PROWS && warp >= first_pwarp && warp <= last_pwarp;
+	// GF items of this thread: column and quarter are fixed (see the GF role)
+	const uint32_t gf_col = tid % CPI, gf_q = (tid / CPI) & 3;
+	const uint32_t gf_cx = (gf_col ^ gf_q) << 4, gf_qoff = gf_q * kStepBytes;
+	const uint32_t gf_ip0 = (gf_q << 14) + gf_col * (4 * W);
 
 	uint32_t win[FW];
 	FoldAux aux;
@@ -230,6 +255,7 @@ fused_convert_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 	for (uint32_t unit = blockIdx.x; unit < p.total_units; unit += gridDim.x, unit_parity ^= 1) {
 		const uint32_t c = unit / p.units_per_chunk, ui = unit % p.units_per_chunk;
 		const uint32_t stripe0 = ui * G;                        // first destination stripe of the unit
+		const unsigned long long c_off = static_cast<unsigned long long>(c) * p.part_out_stride;
 #pragma unroll
 		for (int i = 0; i < FW; ++i) win[i] = 0;
 #pragma unroll
@@ -246,10 +272,14 @@ fused_convert_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 				if constexpr (E > 0) mbar_wait(a_rfull + 8 * st, ph);   // the lost rows of this stage are in place
 
 				// ---------------- GF role: destination stripes ----------------
+				// item (stripe g, quarter q, 16-byte column col): col and q are the same for every item of a thread (the worker thread
+				// count is a multiple of 32), g advances by the number of worker warps.  All addresses are "constant + table entry":
+				// the swizzled offset of chunk block bl inside a stage comes from p.bl_entry (no division, no per-block address maths).
 				if (warp_has_items) {
 					if (PC > 0) mbar_wait(a_pempty + 8 * pst, pph ^ 1);
-					for (uint32_t item = tid; item < n_items; item += n_wk_threads) {
-						const uint32_t col = item % CPI, q = (item / CPI) & 3, g = item / (4 * CPI);
+					const uint32_t pre = stage + gf_qoff;
+					const unsigned long long off_step = c_off + gf_ip0 + static_cast<uint32_t>(step) * kStepBytes;
+					for (uint32_t g = warp; g < G; g += n_wk) {
 						uint32_t acc[M][W];
 #pragma unroll
 						for (int r = 0; r < M; ++r)
@@ -257,17 +287,15 @@ fused_convert_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 							for (int w = 0; w < W; ++w) acc[r][w] = 0;
 						const uint32_t stripe = stripe0 + g;
 						const bool live = stripe < p.pbd;
-						const unsigned long long in_part = (static_cast<unsigned long long>(stripe) << 16) + (q << 14) + step * kStepBytes + col * (4 * W);
-						// chunk block of the unit, walked downwards: bl = g*Kd + j -> slot a = bl % Ks, source stripe t = bl / Ks
-						const uint32_t bl_hi = g * Kd + Kd - 1;
-						uint32_t a = bl_hi % Ks, t = bl_hi / Ks;
-						for (int j = static_cast<int>(Kd) - 1; j >= 0; --j) {
-							const uint32_t row = a * RR + t * 4 + q;
+						const unsigned long long off = off_step + (static_cast<unsigned long long>(stripe) << 16);
+						// chunk blocks of the stripe, walked downwards (Horner): bl = g*Kd + j
+						uint32_t bl = g * Kd + Kd - 1;
+						for (int j = static_cast<int>(Kd) - 1; j >= 0; --j, --bl) {
 							uint32_t v[W];
-							lds_item<W>((stage + row * kStepBytes) ^ ((col ^ (row & 7)) << 4), v);
+							lds_item<W>((pre + p.bl_entry[bl]) ^ gf_cx, v);
 							// BlockConverter (slice_recovery_planner.h:41-57): chunk block stripe*Kd + j is block `stripe` of data part j
 							uint8_t *dp = p.data_out[j];
-							if (dp && live) stg_item<W>(dp + c * p.part_out_stride + in_part, v);
+							if (dp && live) stg_item<W>(dp + off, v);
 #pragma unroll
 							for (int r = 0; r < M; ++r)
 #pragma unroll
@@ -275,17 +303,17 @@ fused_convert_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 									const uint32_t aa = acc[r][w], d = v[w];
 									acc[r][w] = r == 0 ? (aa ^ d) : r == 1 ? gf_x2_add(aa, d) : gf_x4_add(aa, d);
 								}
-							if (a == 0) { a = Ks - 1; --t; } else --a;
 						}
 						if (live) {
 #pragma unroll
 							for (int r = 0; r < M; ++r)
-								if (p.par_out[r]) stg_item<W>(p.par_out[r] + c * p.part_out_stride + in_part, acc[r]);
+								if (p.par_out[r]) stg_item<W>(p.par_out[r] + off, acc[r]);
 						}
 #pragma unroll
 						for (int r = 1; r < M; ++r) {
-							const uint32_t pr = (g * PC + (r - 1)) * 4 + q;
-							sts_item<W>((pstage + pr * kStepBytes) ^ ((col ^ (pr & 7)) << 4), acc[r]);
+							// staged row (g*PC + r-1)*4 + q: its swizzle (row & 7) = 4*((g*PC + r-1) & 1) + q
+							const uint32_t pr4 = g * PC + (r - 1);
+							sts_item<W>(((pstage + pr4 * (4 * kStepBytes) + gf_qoff) ^ gf_cx) ^ ((pr4 & 1) << 6), acc[r]);
 						}
 					}
 					if (PC > 0) {

@@ -849,6 +849,10 @@ int lz_fused_convert(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_goal *ds
 		if (r != CUDA_SUCCESS) return LZGPU_NOT_HANDLED;
 	}
 	p.n_loaded = static_cast<uint32_t>(Ks);
+	for (uint32_t bl = 0; bl < R; ++bl) {
+		const uint32_t row0 = (bl % Ks) * RR + (bl / Ks) * 4;
+		p.bl_entry[bl] = static_cast<uint16_t>(row0 * kStepBytes + ((row0 & 4) ? 64 : 0));
+	}
 	for (uint32_t x = 0; x < e; ++x) p.part_id[Ks + x] = static_cast<uint8_t>(Ks + x);
 	if (*verifying && !d_first_bad) return LZGPU_NOT_HANDLED;
 	if (e == 2) {
