@@ -84,6 +84,43 @@ for geo in ("2", "0"):
         assert all((out[i] == parts[i]).all() for i in lost) and (img == data).all(), text
     e3.close()
 os.environ.pop("LZGPU_RECOVER_GEO", None)
+# round 2, later: the one-pass slice conversion (convert_kernel.cuh: dedicated rebuild warps, table-driven block addressing) and the
+# DIRECT form of the degraded read for Cauchy goals, both with CRC verification
+def slice_parts(eng_, g, data, nblk):
+    par, crc = eng_.encode_chunks(g, data)
+    n = data.shape[0]
+    parts = [np.stack([O.split_parts(data[c], g.k)[0][j] for c in range(n)]) for j in range(g.k)] + [np.ascontiguousarray(par[:, r]) for r in range(g.m)]
+    pb = parts[0].shape[1] // 65536
+    crcs = []
+    for j in range(g.k):
+        cj = np.full((n, pb), 0xD7978EEB, dtype=np.uint32)
+        mine = crc[:, j:nblk:g.k]
+        cj[:, : mine.shape[1]] = mine
+        crcs.append(cj)
+    crcs += [np.ascontiguousarray(crc[:, nblk + r * pb: nblk + (r + 1) * pb]) for r in range(g.m)]
+    return parts, crcs, par, crc
+e4 = L.Engine(0)
+for src, lost, nblk, dst in [("ec(8,2)", (1, 4), 29, "ec(3,2)"), ("ec(3,2)", (0,), 10, "ec(5,3)"), ("xor3", (), 13, "xor2"), ("ec(5,3)", (0, 3), 23, "ec(8,2)")]:
+    gs, gd = L.SliceType(src), L.SliceType(dst)
+    data = np.stack([O.fill_chunk(o, nblk * 65536, 23, c) for c in range(3)])
+    parts, crcs, _, _ = slice_parts(e4, gs, data, nblk)
+    avail = [None if i in lost else parts[i] for i in range(gs.k + gs.m)]
+    acrc = [None if i in lost else crcs[i] for i in range(gs.k + gs.m)]
+    out, ocrc = e4.convert_chunks(gs, gd, nblk, avail, [1] * (gd.k + gd.m), part_crc=acrc)
+    dparts, dcrcs, _, _ = slice_parts(e4, gd, data, nblk)
+    for i in range(gd.k + gd.m):
+        assert (out[i] == dparts[i]).all(), (src, dst, i)
+        nreal = gd.part_blocks(i, nblk)
+        assert (ocrc[i][:, :nreal] == dcrcs[i][:, :nreal]).all(), (src, dst, i)
+for text, nblk, lost in [("ec(8,6)", 19, (2,)), ("ec(4,5)", 9, (0, 3)), ("ec(21,4)", 43, (5,))]:
+    g = L.SliceType(text)
+    data = np.stack([O.fill_chunk(o, nblk * 65536, 29, c) for c in range(2)])
+    parts, crcs, _, _ = slice_parts(e4, g, data, nblk)
+    avail = [None if i in lost else parts[i] for i in range(g.k + g.m)]
+    acrc = [None if i in lost else crcs[i] for i in range(g.k + g.m)]
+    out, img = e4.recover_chunks(g, nblk, avail, part_crc=acrc, want=[1 if i in lost else 0 for i in range(g.k + g.m)], chunk_image=True)
+    assert all((out[i] == parts[i]).all() for i in lost) and (img == data).all(), text
+e4.close()
 pool = L.Pool([0, 0])
 g = L.SliceType("ec(8,2)")
 data = np.stack([O.fill_chunk(o, 16 * 65536, 19, c) for c in range(5)])

@@ -202,7 +202,7 @@ def main():
 
     # ---- replication: slice-type conversion (SliceRecoveryPlanner) --------------------------------------------------
     lines += ["", "## slice-type conversion for replication (source CRCs verified, destination block CRCs produced)", "",
-              "| source | destination parts | chunks/launch | ms | GiB/s chunk data |", "|---|---|---|---|---|"]
+              "| source | destination parts | chunks/launch | ms | GiB/s chunk data | GB/s algorithmic | frac |", "|---|---|---|---|---|---|---|"]
     conv_cases = [("ec(3,2)", "all"), ("ec(3,2)", "one parity"), ("std", "all"), ("xor3", "all")]
     if "conv" not in sections or conv_src is None:
         conv_cases = []
@@ -218,7 +218,10 @@ def main():
         ms = time_steps(lambda: eng.convert_chunks_dev(g, d, n, nb, dp, pb * BLOCK, want, [o.data_ptr() if o is not None else 0 for o in outs], pbd * BLOCK,
                                                        d_part_crc=dc, d_out_crc=[o.data_ptr() if o is not None else 0 for o in ocrc], stream=sp),
                         args.steps, args.warmup, stream)
-        lines.append(f"| ec(8,2), data parts 1 and 4 lost | {dst_text}: {want_parts} | {n} | {ms:.3f} | {n * clen / GIB / (ms / 1e3):.0f} |")
+        # algorithmic bytes: the k source parts that are read + their stored CRCs, every wanted destination part + its CRCs, once
+        alg = n * (g.k * pb * (BLOCK + 4) + sum(want) * pbd * (BLOCK + 4))
+        gbs = alg / (ms / 1e3) / 1e9
+        lines.append(f"| ec(8,2), data parts 1 and 4 lost | {dst_text}: {want_parts} | {n} | {ms:.3f} | {n * clen / GIB / (ms / 1e3):.0f} | {gbs:.0f} | {gbs / peak:.3f} |")
         torch.cuda.synchronize()
         if dst_text == "std":
             assert torch.equal(outs[0].view(n, nb, BLOCK), chunks)
