@@ -83,8 +83,9 @@ struct ConvertParams {
 };
 
 // M = destination parity parts (1..3, Vandermonde rows 1, 2^j, 4^j), E = lost source data parts (0..2; the parity parts in use
-// are source parity rows 0 .. E-1)
-template <int M, int E>
+// are source parity rows 0 .. E-1), KD = compile-time number of destination data parts (0 = p.Kd at run time): the walk over a
+// destination stripe unrolls and its parameter loads become immediates (ec(3,2) destinations: 125 instead of 166 instructions per item)
+template <int M, int E, int KD = 0>
 __global__ void __launch_bounds__(kConvertThreads, 2)
 fused_convert_kernel(const __grid_constant__ TmapArray tmaps, const __grid_constant__ ConvertParams p) {
 	constexpr int NT = kConvertThreads, FW = 64, W = 4;
@@ -92,7 +93,7 @@ fused_convert_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 	constexpr int PC = M - 1;
 	extern __shared__ __align__(1024) uint8_t smem[];
 	const uint32_t sbase = smem_u32(smem);
-	const uint32_t Ks = p.Ks, Kd = p.Kd, G = p.G, T = p.T, RR = p.region_rows, NST = p.n_stages;
+	const uint32_t Ks = p.Ks, Kd = KD ? KD : p.Kd, G = p.G, T = p.T, RR = p.region_rows, NST = p.n_stages;
 	const uint32_t R = G * Kd;                                  // chunk blocks per unit
 	const uint32_t stage_bytes = (Ks + E) * RR * kStepBytes;    // multiple of 1024
 	const uint32_t box_bytes = T * 4 * kStepBytes;
@@ -290,6 +291,7 @@ fused_convert_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 						const unsigned long long off = off_step + (static_cast<unsigned long long>(stripe) << 16);
 						// chunk blocks of the stripe, walked downwards (Horner): bl = g*Kd + j
 						uint32_t bl = g * Kd + Kd - 1;
+#pragma unroll
 						for (int j = static_cast<int>(Kd) - 1; j >= 0; --j, --bl) {
 							uint32_t v[W];
 							lds_item<W>((pre + p.bl_entry[bl]) ^ gf_cx, v);
