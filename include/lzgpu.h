@@ -91,6 +91,22 @@ typedef struct lzgpu_encode_plan {
 } lzgpu_encode_plan;
 int lzgpu_plan_encode(const lzgpu_goal *g, uint32_t n_chunks, uint32_t nb, size_t chunk_stride, int striped_policy, lzgpu_encode_plan *out);
 
+/* How lzgpu_convert_chunks* will turn parts of slice type `src` into the wanted parts of slice type `dst` (SliceRecoveryPlanner,
+ * slice_recovery_planner.h:87-204) — pure host logic, no GPU needed.  available[i] / want[i]: flags per source / destination part
+ * (data parts first).  one_pass = 1: ONE kernel reads the k source parts, verifies them, rebuilds the lost data parts and writes
+ * every wanted destination part with its block CRCs (Vandermonde source with at most two data parts lost and parity rows 0, 1 in
+ * use; destination with one to three parity parts, at least one of them wanted; no standard slice on either side);
+ * one_pass = 0: the chunk image is materialised first (degraded read), then split / encoded (two passes), or the request is a
+ * plain rebuild inside one slice type. */
+typedef struct lzgpu_convert_plan {
+	int one_pass;
+	uint32_t lost_data_parts;         /* of the source slice, among the first k available parts */
+	uint32_t stripes_per_unit;        /* destination stripes per work unit (one_pass only, as the fields below) */
+	uint32_t source_stripes_per_unit; /* stripes_per_unit * k_dst == source_stripes_per_unit * k_src chunk blocks */
+	uint32_t stages, worker_warps, rebuild_warps, smem_bytes;
+} lzgpu_convert_plan;
+int lzgpu_plan_convert(const lzgpu_goal *src, const lzgpu_goal *dst, const uint8_t *available, const uint8_t *want, lzgpu_convert_plan *out);
+
 /* ---------------------------------------------------------------------------------------------
  * Engine context: one per (process, device).  Owns streams, pinned staging and device scratch.
  * lzgpu_default_ctx() lazily creates a context on the current device (LZGPU_DEVICE env or 0) for

@@ -34,6 +34,11 @@ class LzEncodePlan(C.Structure):
                 ("units", C.c_uint32), ("stage_rows", C.c_uint32), ("smem_bytes", C.c_uint32), ("passes", C.c_uint32)]
 
 
+class LzConvertPlan(C.Structure):
+    _fields_ = [("one_pass", C.c_int), ("lost_data_parts", C.c_uint32), ("stripes_per_unit", C.c_uint32), ("source_stripes_per_unit", C.c_uint32),
+                ("stages", C.c_uint32), ("worker_warps", C.c_uint32), ("rebuild_warps", C.c_uint32), ("smem_bytes", C.c_uint32)]
+
+
 class LzBlockWrite(C.Structure):
     _fields_ = [("block", C.c_uint32), ("offset", C.c_uint32), ("size", C.c_uint32), ("crc", C.c_uint32),
                 ("payload_off", C.c_uint64), ("exists", C.c_uint32), ("status", C.c_int32)]
@@ -48,6 +53,7 @@ SIGNATURES = {
     "lzgpu_goal_parse": (_int, [C.c_char_p, _goalp]),
     "lzgpu_goal_valid": (_int, [_goalp]),
     "lzgpu_plan_encode": (_int, [_goalp, _u32, _u32, _sz, _int, _vp]),
+    "lzgpu_plan_convert": (_int, [_goalp, _goalp, _vp, _vp, _vp]),
     "lzgpu_goal_slice_type": (_int, [_goalp]),
     "lzgpu_goal_from_slice_type": (_int, [_int, _goalp]),
     "lzgpu_ref_part_index": (_int, [_goalp, _int]),

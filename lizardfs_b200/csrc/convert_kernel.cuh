@@ -32,8 +32,7 @@
 
 namespace lzd {
 
-constexpr int kConvertThreads = 256;
-constexpr int kConvertNPST = 4;
+// kConvertThreads (256) and kConvertNPST (4 staging stages) live in fused_plan.h next to convert_plan()
 
 // mbar_wait for warps that mostly find the phase incomplete (the rebuild warps run ahead of the TMA loads): sleep between the polls so
 // that the loop does not take issue slots from the worker warps of the same scheduler (ncu, run 12: the polling loops were 22 % of all

@@ -765,60 +765,23 @@ int lz_fused_convert(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_goal *ds
 	if (!fs || fs->disabled || fs->convert_off) return LZGPU_NOT_HANDLED;
 	const int Ks = src->k, Ms = src->m, Kd = dst->k, Md = dst->m;
 	if (src->kind == LZGPU_KIND_STD || dst->kind == LZGPU_KIND_STD) return LZGPU_NOT_HANDLED;
-	if (lz::uses_cauchy(Ks, Ms) || lz::uses_cauchy(Kd, Md) || Md > 3 || Md < 1) return LZGPU_NOT_HANDLED;
 	if ((part_stride % 16) || (out_stride % 16) || n_chunks == 0 || nb == 0) return LZGPU_NOT_HANDLED;
-	// inputs: the first k available parts (ec_read_plan.h:126-133)
+	// inputs: the first k available parts (ec_read_plan.h:126-133); geometry from the shared plan (fused_plan.h, unit-tested on the CPU)
 	ConvertParams p{};
+	uint8_t avail[LZGPU_MAX_PARTS] = {0};
+	for (int i = 0; i < Ks + Ms; ++i) avail[i] = d_parts[i] ? 1 : 0;
+	const ConvertPlan pl = convert_plan(Ks, Ms, lz::uses_cauchy(Ks, Ms), Kd, Md, lz::uses_cauchy(Kd, Md), avail, fs->max_smem);
+	if (!pl.ok) return LZGPU_NOT_HANDLED;
 	int used[LZGPU_MAX_DATA], n_used = 0;
 	for (int i = 0; i < Ks + Ms && n_used < Ks; ++i)
 		if (d_parts[i]) used[n_used++] = i;
-	if (n_used < Ks) return LZGPU_NOT_HANDLED;
-	uint32_t e = 0, n_par = 0;
-	for (int a = 0; a < Ks; ++a) {
-		const int idx = used[a];
-		if (idx < Ks) p.slot_present[idx] = 1;
-		else if (idx == Ks + static_cast<int>(n_par) && n_par < 2) ++n_par;   // parity rows 0, 1 in this order only
-		else return LZGPU_NOT_HANDLED;
-	}
-	for (int j = 0; j < Ks; ++j)
-		if (!p.slot_present[j]) {
-			if (e >= 2) return LZGPU_NOT_HANDLED;
-			p.erased_idx[e++] = static_cast<uint8_t>(j);
-		}
-	if (e != n_par) return LZGPU_NOT_HANDLED;
-	// geometry: G destination stripes = T source stripes per unit
-	const uint32_t g0 = static_cast<uint32_t>(Ks / std::gcd(Ks, Kd));
-	const uint32_t PC = static_cast<uint32_t>(Md - 1);
-	uint32_t G = 0, T = 0, RR = 0, n_stages = 0;
-	size_t smem = 0;
-	double best_cost = 0;
-	for (uint32_t g = g0; g <= 64; g += g0) {
-		const uint32_t R = g * Kd, t = R / Ks;
-		const uint32_t rows = R * 4 + e * t * 4 + g * PC * 4;
-		// worker warps own the rows; with lost parts at least one warp is left for the rebuild (convert_kernel.cuh)
-		if (R > 64 || t * 4 > 256 || rows > static_cast<uint32_t>(kConvertThreads) - (e ? 32u : 0u)) break;
-		const uint32_t rr = (t * 4 + 7) & ~7u;
-		const size_t stage = static_cast<size_t>(Ks + e) * rr * kStepBytes;
-		const size_t pstage = (static_cast<size_t>(g) * PC * 4 * kStepBytes + 1023) & ~size_t(1023);
-		const size_t fixed = kConvertNPST * pstage + 520 + 8 * (2 * kConvertNPST) + 64;
-		uint32_t ns = 0;
-		for (uint32_t n = 4; n >= 2; --n)
-			if (n * stage + 24 * n + fixed <= static_cast<size_t>(std::min<int>(fs->max_smem, kSmemCap))) { ns = n; break; }
-		if (!ns) break;
-		// instructions per thread and step of the busier role, per chunk block of the unit (rough counts; only the ordering matters):
-		// a worker thread folds one row (~140) and takes its share of the 32 g destination items (~35 per block of the stripe + stores),
-		// a rebuild thread its share of the 32 t source-stripe items (Horner over Ks columns; two syndromes and the solve when e = 2)
-		const uint32_t n_wk = e ? (rows + 31) / 32 : kConvertThreads / 32, n_rb = kConvertThreads / 32 - n_wk;
-		const double worker = 140.0 + std::ceil(32.0 * g / (32.0 * n_wk)) * (35.0 * Kd + 20.0);
-		const double rebuild = e ? std::ceil(static_cast<double>(t) / n_rb) * (e == 2 ? 30.0 * Ks + 150.0 : 6.0 * Ks + 20.0) : 0.0;
-		const double cost = std::max(worker, rebuild) / R;
-		if (G == 0 || cost < best_cost) {
-			best_cost = cost;
-			G = g; T = t; RR = rr; n_stages = ns;
-			smem = ns * stage + 24 * ns + fixed;
-		}
-	}
-	if (G == 0) return LZGPU_NOT_HANDLED;
+	const uint32_t e = pl.e;
+	for (int a = 0; a < Ks; ++a)
+		if (used[a] < Ks) p.slot_present[used[a]] = 1;
+	p.erased_idx[0] = pl.erased[0];
+	p.erased_idx[1] = pl.erased[1];
+	const uint32_t G = pl.G, T = pl.T, RR = pl.region_rows, n_stages = pl.n_stages;
+	const size_t smem = pl.smem;
 	const uint32_t pbs = (nb + Ks - 1) / Ks, pbd = (nb + Kd - 1) / Kd;
 	const uint32_t R = G * Kd;
 	p.Kd = Kd; p.G = G; p.pbd = pbd; p.Ks = Ks; p.T = T; p.pbs = pbs; p.region_rows = RR;

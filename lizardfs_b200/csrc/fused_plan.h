@@ -148,4 +148,80 @@ inline FusedPlan fused_plan(int M, bool generic, uint32_t K, uint32_t n_chunks, 
 	return pl;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// One-pass slice conversion (convert_kernel.cuh): geometry as a pure function, shared by lz_fused_convert and lzgpu_plan_convert.
+// A unit is G destination stripes = T source stripes (G*Kd == T*Ks chunk blocks); worker warps own one CRC row per thread (the R*4
+// data rows, e*T*4 source parity rows, G*(Md-1)*4 staged destination parity rows) and the 32 G destination items, with lost parts
+// the remaining warps only rebuild.  G is the candidate with the lowest estimated instruction count per chunk block on the busier role.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kConvertThreads = 256;
+constexpr int kConvertNPST = 4;
+
+struct ConvertPlan {
+	bool ok = false;
+	uint32_t G = 0, T = 0, region_rows = 0, n_stages = 0, n_workers = 0;
+	uint32_t e = 0;            // lost source data parts (0..2)
+	uint8_t erased[2] = {0, 0};
+	size_t smem = 0;
+};
+
+// available[i] != 0: part i of the source slice (data parts first, then parity parts) can be read.  The kernel takes Vandermonde
+// sources with at most two data parts lost whose first-k-available rule (ec_read_plan.h:126-133) brings in parity rows 0 .. e-1 in
+// this order, and Vandermonde destinations with one to three parity parts.
+inline ConvertPlan convert_plan(int Ks, int Ms, bool src_cauchy, int Kd, int Md, bool dst_cauchy, const uint8_t *available, int max_smem) {
+	ConvertPlan pl;
+	if (src_cauchy || dst_cauchy || Md < 1 || Md > 3 || Ks < 1 || Ks > 32 || Kd < 1 || Kd > 32) return pl;
+	int n_used = 0, n_par = 0;
+	bool present[32] = {false};
+	for (int i = 0; i < Ks + Ms && n_used < Ks; ++i) {
+		if (!available[i]) continue;
+		++n_used;
+		if (i < Ks) present[i] = true;
+		else if (i == Ks + n_par && n_par < 2) ++n_par;   // parity rows 0, 1 in this order only
+		else return pl;
+	}
+	if (n_used < Ks) return pl;
+	uint32_t e = 0;
+	for (int j = 0; j < Ks; ++j)
+		if (!present[j]) {
+			if (e >= 2) return pl;
+			pl.erased[e++] = static_cast<uint8_t>(j);
+		}
+	if (static_cast<int>(e) != n_par) return pl;
+	pl.e = e;
+	uint32_t a = static_cast<uint32_t>(Ks), b = static_cast<uint32_t>(Kd);
+	while (b) { const uint32_t t = a % b; a = b; b = t; }
+	const uint32_t g0 = static_cast<uint32_t>(Ks) / a, PC = static_cast<uint32_t>(Md - 1);
+	const size_t cap = static_cast<size_t>(max_smem < kSmemCap ? max_smem : kSmemCap);
+	double best_cost = 0;
+	for (uint32_t g = g0; g <= 64; g += g0) {
+		const uint32_t R = g * Kd, t = R / Ks;
+		const uint32_t rows = R * 4 + e * t * 4 + g * PC * 4;
+		// worker warps own the rows; with lost parts at least one warp is left for the rebuild
+		if (R > 64 || t * 4 > 256 || rows > static_cast<uint32_t>(kConvertThreads) - (e ? 32u : 0u)) break;
+		const uint32_t rr = (t * 4 + 7) & ~7u;
+		const size_t stage = static_cast<size_t>(Ks + e) * rr * kStepBytes;
+		const size_t pstage = (static_cast<size_t>(g) * PC * 4 * kStepBytes + 1023) & ~size_t(1023);
+		const size_t fixed = kConvertNPST * pstage + 520 + 8 * (2 * kConvertNPST) + 64;
+		uint32_t ns = 0;
+		for (uint32_t n = 4; n >= 2; --n)
+			if (n * stage + 24 * n + fixed <= cap) { ns = n; break; }
+		if (!ns) break;
+		// instructions per thread and step of the busier role, per chunk block of the unit (rough counts; only the ordering matters):
+		// a worker thread folds one row (~140) and takes its share of the 32 g destination items (~35 per block of the stripe + stores),
+		// a rebuild thread its share of the 32 t source-stripe items (Horner over Ks columns; two syndromes and the solve when e = 2)
+		const uint32_t n_wk = e ? (rows + 31) / 32 : kConvertThreads / 32, n_rb = kConvertThreads / 32 - n_wk;
+		const double worker = 140.0 + static_cast<double>((g + n_wk - 1) / n_wk) * (35.0 * Kd + 20.0);
+		const double rebuild = e ? static_cast<double>((t + n_rb - 1) / n_rb) * (e == 2 ? 30.0 * Ks + 150.0 : 6.0 * Ks + 20.0) : 0.0;
+		const double cost = (worker > rebuild ? worker : rebuild) / R;
+		if (!pl.ok || cost < best_cost) {
+			best_cost = cost;
+			pl.ok = true;
+			pl.G = g; pl.T = t; pl.region_rows = rr; pl.n_stages = ns; pl.n_workers = n_wk;
+			pl.smem = ns * stage + 24 * ns + fixed;
+		}
+	}
+	return pl;
+}
+
 }  // namespace lzd

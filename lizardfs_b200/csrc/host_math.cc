@@ -381,6 +381,34 @@ int lzgpu_plan_encode(const lzgpu_goal *g, uint32_t n_chunks, uint32_t nb, size_
 	return LZGPU_OK;
 }
 
+int lzgpu_plan_convert(const lzgpu_goal *src, const lzgpu_goal *dst, const uint8_t *available, const uint8_t *want, lzgpu_convert_plan *out) {
+	if (!out || !src || !dst || !available || !want) return LZGPU_ERR_ARG;
+	const bool src_std = src->kind == LZGPU_KIND_STD, dst_std = dst->kind == LZGPU_KIND_STD;
+	if ((!src_std && !lzgpu_goal_valid(src)) || (!dst_std && !lzgpu_goal_valid(dst))) return LZGPU_ERR_ARG;
+	*out = lzgpu_convert_plan{};
+	if (!src_std) {
+		int used = 0;
+		for (int i = 0; i < src->k + src->m && used < src->k; ++i)
+			if (available[i]) { ++used; if (i >= src->k) ++out->lost_data_parts; }
+		if (used < src->k) return LZGPU_ERR_TOO_FEW_PARTS;
+	}
+	if (src_std || dst_std || (src->kind == dst->kind && src->k == dst->k && src->m == dst->m)) return LZGPU_OK;
+	bool parity_wanted = false;
+	for (int i = dst->k; i < dst->k + dst->m; ++i) parity_wanted |= want[i] != 0;
+	if (!parity_wanted) return LZGPU_OK;   // data parts alone are BlockConverter picks from the image
+	const lzd::ConvertPlan pl = lzd::convert_plan(src->k, src->m, lz::uses_cauchy(src->k, src->m), dst->k, dst->m, lz::uses_cauchy(dst->k, dst->m),
+	                                              available, lzd::kSmemCap);
+	if (!pl.ok) return LZGPU_OK;
+	out->one_pass = 1;
+	out->stripes_per_unit = pl.G;
+	out->source_stripes_per_unit = pl.T;
+	out->stages = pl.n_stages;
+	out->worker_warps = pl.n_workers;
+	out->rebuild_warps = lzd::kConvertThreads / 32 - pl.n_workers;
+	out->smem_bytes = static_cast<uint32_t>(pl.smem);
+	return LZGPU_OK;
+}
+
 const char *lzgpu_version(void) { return "lizardfs_b200 0.1 (sm_100a)"; }
 
 }  // extern "C"

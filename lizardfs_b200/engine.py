@@ -507,6 +507,17 @@ class Engine:
         return {f: getattr(out, f) for f, _ in _lib.LzEncodePlan._fields_}
 
     # ---- replication / slice-type conversion ----------------------------------------------------
+    @staticmethod
+    def plan_convert(src, dst, available, want):
+        """how convert_chunks would serve the request (pure host logic, csrc/fused_plan.h convert_plan; no GPU needed): dict with
+        one_pass (1 = ONE kernel from the source parts to the wanted destination parts), lost_data_parts, stripes_per_unit, ..."""
+        out = _lib.LzConvertPlan()
+        a = np.asarray(available, dtype=np.uint8)
+        w = np.asarray(want, dtype=np.uint8)
+        assert a.size == src.k + src.m and w.size == dst.k + dst.m
+        _check(_lib.load().lzgpu_plan_convert(C.byref(src.c), C.byref(dst.c), _p(a), _p(w), C.byref(out)), "plan_convert")
+        return {f: getattr(out, f) for f, _ in _lib.LzConvertPlan._fields_}
+
     def convert_chunks(self, src, dst, nb, parts, want, part_crc=None, with_crc=True):
         """Rebuild the `want`ed parts of slice type `dst` from the available `parts` of slice type `src`
         (SliceRecoveryPlanner, slice_recovery_planner.h:87-204).  parts[i]: (n_chunks, pb_src*65536) uint8 or None.

@@ -242,3 +242,57 @@ def test_geometry_helpers_reject_invalid_goals():
     ok = L.SliceType("ec(3,2)")
     assert lib.lzgpu_part_blocks(C.byref(ok.c), 5, 1024) == 0 and lib.lzgpu_part_blocks(C.byref(ok.c), -1, 1024) == 0
     assert lib.lzgpu_part_blocks(C.byref(ok.c), 4, 1024) == 342
+
+
+def test_convert_plan_decisions():
+    """Which slice conversions run as ONE kernel and with which unit geometry (csrc/fused_plan.h convert_plan, the host logic of
+    lz_fused_convert) — without a GPU.  A unit is G destination stripes = T source stripes; the rows (one CRC stream per thread:
+    R*4 data rows, e*T*4 source parity rows, G*(m_dst-1)*4 staged parity rows) belong to the worker warps, and with lost parts at
+    least one warp of the 8 is left for the rebuild."""
+    def plan(src, lost, dst, want=None):
+        s, d = L.SliceType(src), L.SliceType(dst)
+        avail = [0 if i in lost else 1 for i in range(s.k + s.m)]
+        return L.Engine.plan_convert(s, d, avail, want if want is not None else [1] * (d.k + d.m)), s, d
+
+    # the measured case (profiles/probe_r2.md section 12): lcm(8, 3) = 24 blocks per unit, 152 rows on five warps, three rebuild warps
+    p, s, d = plan("ec(8,2)", (1, 4), "ec(3,2)")
+    assert (p["one_pass"], p["lost_data_parts"], p["stripes_per_unit"], p["source_stripes_per_unit"], p["worker_warps"], p["rebuild_warps"]) == (1, 2, 8, 3, 5, 3)
+    assert p["stages"] == 4 and p["smem_bytes"] <= 113 * 1024
+    # nothing lost: every warp is a worker
+    p, _, _ = plan("ec(8,2)", (), "ec(3,2)")
+    assert (p["one_pass"], p["lost_data_parts"], p["rebuild_warps"]) == (1, 0, 0)
+    # invariants over every pair of the goals the tests use, every loss pattern of up to two data parts
+    import itertools
+    names = ["xor2", "xor3", "xor7", "ec(3,2)", "ec(4,2)", "ec(5,3)", "ec(6,3)", "ec(8,2)", "ec(8,3)", "ec(12,2)", "ec(16,3)"]
+    n_one_pass = 0
+    for sn, dn in itertools.product(names, names):
+        if sn == dn:
+            continue
+        s0 = L.SliceType(sn)
+        for lost in [()] + [(a,) for a in range(s0.k)][:3] + ([(0, s0.k - 1)] if s0.m >= 2 else []):
+            p, s, d = plan(sn, lost, dn)
+            assert p["lost_data_parts"] == len(lost)
+            if not p["one_pass"]:
+                continue
+            n_one_pass += 1
+            G, T = p["stripes_per_unit"], p["source_stripes_per_unit"]
+            assert G * d.k == T * s.k and G * d.k <= 64
+            rows = G * d.k * 4 + len(lost) * T * 4 + G * (d.m - 1) * 4
+            assert rows <= 32 * p["worker_warps"] and p["worker_warps"] + p["rebuild_warps"] == 8
+            assert (p["rebuild_warps"] >= 1) == (len(lost) > 0)
+            assert 2 <= p["stages"] <= 4 and p["smem_bytes"] <= 113 * 1024
+    assert n_one_pass > 150
+    # what stays on two passes: three lost parts, a parity row other than 0 / 1 in use, Cauchy generators on either side, four parity
+    # parts to produce, only data parts wanted, a standard slice on either side, the same slice type (a plain rebuild)
+    assert plan("ec(5,3)", (0, 1, 4), "ec(3,2)")[0]["one_pass"] == 0
+    assert plan("ec(8,2)", (7, 8), "ec(3,2)")[0]["one_pass"] == 0          # data part 7 and parity 0 lost: parity row 1 alone is read
+    assert plan("ec(8,6)", (1,), "ec(3,2)")[0]["one_pass"] == 0
+    assert plan("ec(3,2)", (1,), "ec(8,6)")[0]["one_pass"] == 0
+    assert plan("ec(3,2)", (1,), "ec(8,4)")[0]["one_pass"] == 0
+    assert plan("ec(8,2)", (1,), "ec(3,2)", want=[1, 1, 1, 0, 0])[0]["one_pass"] == 0
+    assert plan("ec(8,2)", (1,), "ec(8,2)")[0]["one_pass"] == 0
+    std = L.SliceType("std")
+    assert L.Engine.plan_convert(std, L.SliceType("ec(3,2)"), [1], [1] * 5)["one_pass"] == 0
+    # too few parts: the error of the call itself
+    with pytest.raises(L.LzGpuError):
+        plan("ec(3,2)", (0, 1, 2), "ec(8,2)")
