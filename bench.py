@@ -394,6 +394,71 @@ class Extras:
         del parts, pcrc, outs, img, d_par, d_crc
 
 
+    def convert(self, src_text, lost, dst_text, config, n=64, n_check=2):
+        """slice-type conversion for replication (SliceRecoveryPlanner): `n` 64 MiB chunks of slice type `src` with the
+        `lost` parts missing -> every part of slice type `dst` + its block CRCs, source CRCs verified"""
+        torch, L, eng = self.torch, self.L, self.eng
+        gs, gd = L.SliceType(src_text), L.SliceType(dst_text)
+        clen, nb = CHUNK, CHUNK // BLOCK
+
+        def slice_of(g):
+            k, m = g.k, g.m
+            pb = (nb + k - 1) // k
+            ps = pb * BLOCK
+            d_par = torch.empty(n * m * ps, dtype=torch.uint8, device=self.dev)
+            d_crc = torch.empty(n * (nb + m * pb), dtype=torch.int32, device=self.dev)
+            eng.encode_chunks_dev(g, n, clen, self.d_data.data_ptr(), clen, d_par.data_ptr(), m * ps, d_crc.data_ptr(), nb + m * pb, stream=self.sp)
+            parts = [torch.zeros(n * ps, dtype=torch.uint8, device=self.dev) for _ in range(k)]
+            eng.split_chunks_dev(g, n, nb, self.d_data.data_ptr(), clen, [p.data_ptr() for p in parts], ps, stream=self.sp)
+            torch.cuda.synchronize(self.dev)
+            crc_all = d_crc.view(n, nb + m * pb)
+            pcrc = []
+            for j in range(k):
+                cj = torch.full((n, pb), -0x28687115, dtype=torch.int32, device=self.dev)  # 0xD7978EEB: zero padding blocks
+                sub = crc_all[:, j:nb:k]
+                cj[:, : sub.shape[1]] = sub
+                pcrc.append(cj.contiguous())
+            for r in range(m):
+                parts.append(d_par.view(n, m, ps)[:, r].contiguous().view(-1))
+                pcrc.append(crc_all[:, nb + r * pb: nb + (r + 1) * pb].contiguous())
+            return parts, pcrc, pb, ps
+
+        sparts, scrc, pbs, pss = slice_of(gs)
+        ns, nd = gs.k + gs.m, gd.k + gd.m
+        pbd = (nb + gd.k - 1) // gd.k
+        psd = pbd * BLOCK
+        outs = [torch.empty(n * psd, dtype=torch.uint8, device=self.dev) for _ in range(nd)]
+        ocrc = [torch.empty((n, pbd), dtype=torch.int32, device=self.dev) for _ in range(nd)]
+        dp = [0 if i in lost else sparts[i].data_ptr() for i in range(ns)]
+        dc = [0 if i in lost else scrc[i].data_ptr() for i in range(ns)]
+        eng.set_deferred_verify(True)
+        ms = self._time(lambda: eng.convert_chunks_dev(gs, gd, n, nb, dp, pss, [1] * nd, [o.data_ptr() for o in outs], psd, d_part_crc=dc,
+                                                       d_out_crc=[o.data_ptr() for o in ocrc], stream=self.sp))
+        eng.sync()
+        eng.set_deferred_verify(False)
+        plan = L.Engine.plan_convert(gs, gd, [0 if i in lost else 1 for i in range(ns)], [1] * nd)
+        del sparts, scrc
+        # exact on the device for the whole batch: every destination part and CRC equals a direct encode / split of the same chunks ...
+        dparts, dcrc, _, _ = slice_of(gd)
+        for i in range(nd):
+            assert torch.equal(outs[i], dparts[i]), f"bench parity check failed: convert {src_text} -> {dst_text} part {i}"
+            nreal = gd.part_blocks(i, nb)
+            assert torch.equal(ocrc[i][:, :nreal], dcrc[i][:, :nreal]), f"bench parity check failed: convert {src_text} -> {dst_text} CRCs of part {i}"
+        # ... and the parity parts against the reference's own encoder for a few chunks
+        for c in sorted({0, n - 1})[:n_check]:
+            chunk = self.d_data[c * clen: (c + 1) * clen].cpu().numpy()
+            p_ref, c_ref = self.checker.encode_chunk(gd.kind, gd.k, gd.m, chunk)
+            for r in range(gd.m):
+                assert (outs[gd.k + r][c * psd: (c + 1) * psd].cpu().numpy() == p_ref[r]).all(), f"bench parity check failed: convert parity {r} chunk {c} vs reference"
+                assert (ocrc[gd.k + r][c].cpu().numpy().view(np.uint32) == c_ref[nb + r * pbd: nb + (r + 1) * pbd]).all()
+        # algorithmic bytes (DESIGN.md 4.5): the k source parts that are read + their stored CRCs, every destination part + its CRCs, once
+        alg = gs.k * pbs * (BLOCK + 4) + nd * pbd * (BLOCK + 4)
+        self._entry(f"convert {src_text} parts {sorted(lost)} lost -> {dst_text} (verify + all parts + CRCs)", config, n, clen, alg, ms, n,
+                    f"all destination parts and CRCs identical on the device to a direct encode / split for all {n} chunks; parity parts of "
+                    f"{min(n_check, 2)} chunk(s) also vs the reference's encoder; route: {'one pass' if plan['one_pass'] else 'two passes'}")
+        del outs, ocrc, dparts, dcrc
+
+
 def copy_roofline(torch, dev, in_bytes, out_bytes, dist, reps=3):
     """e2e ceiling of this host/GPU pair: pinned H2D of `in_bytes` and D2H of `out_bytes` issued together on two streams (what the
     3-slot pipeline overlaps), all ranks at once.  Returns seconds (max over ranks) for one such exchange."""
@@ -624,6 +689,7 @@ def main():
         ex = Extras(torch, L, eng, dev, stream, d_data, T * CHUNK, peak, world, dist, rank, steps=5, warmup=3)
         ex.encode("ec(3,2)", CHUNK, "BASELINE.json configs[1]: ec(3,2) encode + CRC, 64 MiB chunks", max_chunks=512)
         ex.recover("ec(8,2)", (1, 4), "BASELINE.json configs[3]: ec(8,2) degraded read, data parts 1 and 4 lost", n=128)
+        ex.convert("ec(8,2)", (1, 4), "ec(3,2)", "SURVEY.md 8(f1): slice conversion for replication, ec(8,2) with data parts 1 and 4 lost -> ec(3,2)", n=64)
         for gt in ("xor2", "xor3", "ec(5,3)", "ec(8,4)"):
             for clen in (1 << 20, 4 << 20, 16 << 20, 64 << 20, (37 << 20) + 5 * BLOCK):
                 ex.encode(gt, clen, "BASELINE.json configs[4]: mixed-goal sweep", max_chunks=8192, n_check=3 if clen >= (16 << 20) else 4)
