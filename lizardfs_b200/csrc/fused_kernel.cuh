@@ -782,8 +782,8 @@ fused_recover_kernel(const __grid_constant__ TmapArray tmaps, const __grid_const
 #pragma unroll
 							for (int w = 0; w < W; ++w) acc[r][w] ^= pv[w];
 						}
-						if (E == 2 && R0 == 0 && R1 == 1 && KT == 0) {
-							// (runtime-k shapes only: for the k = 8 instantiation the two bit-plane multiplies measured 5 % faster)
+						if (E == 2 && R0 == 0 && R1 == 1 && KT != 8) {
+							// (not the k = 8 instantiation: there the two bit-plane multiplies measured 5 % faster)
 							// RAID-6 elimination: S0 = d0 ^ d1, S1 = 2^x0 d0 ^ 2^x1 d1  =>  (2^x0 ^ 2^x1) d1 = S1 ^ 2^x0 S0, d0 = S0 ^ d1:
 							// ONE general multiply per word (w[1] = planes of (2^x0 ^ 2^x1)^-1) and x0 doublings (x0 is the smaller
 							// index; more than four doublings cost more than the bit-plane multiply by 2^x0, w[0]).
