@@ -39,7 +39,7 @@ struct FusedState {
 	int striped = -1;
 	int recover_two = -1;  // LZGPU_RECOVER_TWO: -1 automatic, 0 one CTA per SM (6 stages), 1 two CTAs (3 stages) for e <= 2
 	int recover_geo = -1;  // LZGPU_RECOVER_GEO: -1 automatic, 0 / 1 as above, 2 one 16-warp CTA per SM
-	int recover_k3 = 1;          // LZGPU_RECOVER_K3=0: the runtime-k instantiation for k = 3 (A/B)
+	int recover_k3 = 1;          // LZGPU_RECOVER_K3=0: the runtime-k instantiations for k = 3 and k = 5 (A/B)
 	int cauchy_encode_off = 0;   // LZGPU_CAUCHY_FUSED=0: Cauchy-generator encodes on gf_dot_kernel + CRC passes instead of the fused kernel
 	int convert_off = 0;   // LZGPU_CONVERT_FUSED=0: slice conversion through the two-pass route (image, then SPLIT encode)
 	int direct_wide = -1;  // LZGPU_DIRECT_WIDE: item width of the DIRECT (Cauchy) degraded read, -1 by item count, 0 = 4 bytes, 1 = 8 / 16 bytes, -2 = route off
@@ -121,6 +121,8 @@ static int set_all_recover_attrs() {
 	if ((rc = set_recover_attr<4, 0>())) return rc;
 	CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<1, 3, 0, -1, 64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCapBig));
 	CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<2, 3, 0, 1, 64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCapBig));
+	CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<2, 5, 0, 1, 64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCapBig));
+	CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<3, 5, 0, 1, 64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCapBig));
 	// DIRECT (any generator; Cauchy codes): 16-warp geometry, 4-byte items
 	if ((rc = set_direct_attr<1>()) || (rc = set_direct_attr<2>()) || (rc = set_direct_attr<3>()) || (rc = set_direct_attr<4>())) return rc;
 	return LZGPU_OK;
@@ -739,9 +741,15 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 			default: return launch_direct<4>(ctx, maps, p, smem, st, wide);
 		}
 	}
-	if (K == 3 && geo == 2 && fs->recover_k3) {   // ec(3,2) / xor3 on the 16-warp geometry: compile-time k (the walk over the columns unrolls)
+	// ec(3,2) / ec(5,3) on the 16-warp geometry: compile-time k (the walk over the columns unrolls, parameter loads become immediates).
+	// Measured (run 18): ec(3,2) two lost, rebuild only 0.689 -> 0.827 of the HBM peak; with verification and image 0.692 -> 0.703.
+	if (K == 3 && geo == 2 && fs->recover_k3) {
 		if (e == 1 && row0) return launch_recover_geo2<1, 3, 0, -1>(ctx, maps, p, smem, st);
 		if (e == 2 && row01) return launch_recover_geo2<2, 3, 0, 1>(ctx, maps, p, smem, st);
+	}
+	if (K == 5 && geo == 2 && fs->recover_k3) {
+		if (e == 2 && row01) return launch_recover_geo2<2, 5, 0, 1>(ctx, maps, p, smem, st);
+		if (e == 3 && row01) return launch_recover_geo2<3, 5, 0, 1>(ctx, maps, p, smem, st);
 	}
 	switch (e) {
 		case 1:
