@@ -747,8 +747,10 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 		if (e == 1 && row0) return launch_recover_geo2<1, 3, 0, -1>(ctx, maps, p, smem, st);
 		if (e == 2 && row01) return launch_recover_geo2<2, 3, 0, 1>(ctx, maps, p, smem, st);
 	}
+	// ec(5,3) (run 19): two lost, rebuild only 0.585 -> 0.682 but with verification and image 0.749 -> 0.717 (the unrolled walk costs the CRC
+	// role registers), so that combination keeps the runtime-k kernel; three lost 0.329 -> 0.373 and 0.471 -> 0.519
 	if (K == 5 && geo == 2 && fs->recover_k3) {
-		if (e == 2 && row01) return launch_recover_geo2<2, 5, 0, 1>(ctx, maps, p, smem, st);
+		if (e == 2 && row01 && !(*verifying && d_chunk_out)) return launch_recover_geo2<2, 5, 0, 1>(ctx, maps, p, smem, st);
 		if (e == 3 && row01) return launch_recover_geo2<3, 5, 0, 1>(ctx, maps, p, smem, st);
 	}
 	switch (e) {
