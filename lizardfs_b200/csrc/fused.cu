@@ -195,6 +195,9 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if ((rc = set_smem_attr<3, false, 5, 8>(smem))) return rc;
 	if ((rc = set_smem_attr<3, false, 6, 8>(smem))) return rc;
 	if ((rc = set_smem_attr<4, false, 8, 8>(smem))) return rc;
+	if ((rc = set_smem_attr<3, false, 8, 6>(smem))) return rc;
+	if ((rc = set_smem_attr<4, false, 6, 8>(smem))) return rc;
+	if ((rc = set_smem_attr<4, false, 4, 8>(smem))) return rc;
 #if LZ_T2 == 288
 	if ((rc = set_smem_attr<2, false, 8, 8>(smem))) return rc;
 #endif
@@ -398,6 +401,9 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	LZ_FOLDED(3, 5, 8)    // ec(5,3)
 	LZ_FOLDED(3, 6, 8)    // ec(6,3)
 	LZ_FOLDED(4, 8, 8)    // ec(8,4) on one 16-warp CTA per SM
+	LZ_FOLDED(3, 8, 6)    // ec(8,3)
+	LZ_FOLDED(4, 6, 8)    // ec(6,4)
+	LZ_FOLDED(4, 4, 8)    // ec(4,4)
 #if LZ_T2 == 288
 	LZ_FOLDED(2, 8, 8)    // experiment builds with the nine-warp CTA of round 1
 #endif
