@@ -196,6 +196,12 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if ((rc = set_smem_attr<3, false, 6, 8>(smem))) return rc;
 	if ((rc = set_smem_attr<4, false, 8, 8>(smem))) return rc;
 	if ((rc = set_smem_attr<3, false, 8, 6>(smem))) return rc;
+	if ((rc = set_smem_attr<1, false, 4, 16>(smem))) return rc;
+	if ((rc = set_smem_attr<2, false, 5, 10>(smem))) return rc;
+	if ((rc = set_smem_attr<2, false, 10, 5>(smem))) return rc;
+	if ((rc = set_smem_attr<3, false, 4, 8>(smem))) return rc;
+	if ((rc = set_smem_attr<4, false, 10, 6>(smem))) return rc;
+	if ((rc = set_smem_attr<4, false, 12, 5>(smem))) return rc;
 	if ((rc = set_smem_attr<4, false, 6, 8>(smem))) return rc;
 	if ((rc = set_smem_attr<4, false, 4, 8>(smem))) return rc;
 #if LZ_T2 == 288
@@ -401,7 +407,15 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	LZ_FOLDED(3, 5, 8)    // ec(5,3)
 	LZ_FOLDED(3, 6, 8)    // ec(6,3)
 	LZ_FOLDED(4, 8, 8)    // ec(8,4) on one 16-warp CTA per SM
+	// more goals folded in round 2 (run 21: the runtime-k instantiation costs 25-40 %: ec(8,3) 0.455 -> 0.570, ec(6,4) 0.370 -> 0.495,
+	// ec(4,4) 0.388 -> 0.548 of the HBM peak)
 	LZ_FOLDED(3, 8, 6)    // ec(8,3)
+	LZ_FOLDED(1, 4, 16)   // xor4 / ec(4,1)
+	LZ_FOLDED(2, 5, 10)   // ec(5,2)
+	LZ_FOLDED(2, 10, 5)   // ec(10,2)
+	LZ_FOLDED(3, 4, 8)    // ec(4,3)
+	LZ_FOLDED(4, 10, 6)   // ec(10,4)
+	LZ_FOLDED(4, 12, 5)   // ec(12,4)
 	LZ_FOLDED(4, 6, 8)    // ec(6,4)
 	LZ_FOLDED(4, 4, 8)    // ec(4,4)
 #if LZ_T2 == 288

@@ -241,7 +241,8 @@ def test_encode_many_parity_goals_in_passes(eng, oracle, text, nblocks, n_chunks
         assert (crc[c] == c_ref).all(), (text, c)
 
 
-@pytest.mark.parametrize("text", ["xor2", "xor3", "ec(5,3)", "ec(8,4)", "ec(3,2)", "ec(8,2)"])
+@pytest.mark.parametrize("text", ["xor2", "xor3", "ec(5,3)", "ec(8,4)", "ec(3,2)", "ec(8,2)", "ec(8,3)", "ec(6,4)", "ec(4,4)", "ec(6,3)", "ec(4,2)", "ec(6,2)",
+                                  "xor4", "ec(5,2)", "ec(10,2)", "ec(4,3)", "ec(10,4)", "ec(12,4)"])
 def test_encode_full_size_chunk_every_bench_goal_vs_reference(eng, oracle, ref, text):
     """BASELINE configs[1], [2], [4] at the size the numbers are quoted on: one full 64 MiB chunk per goal of the mixed sweep,
     parity parts and all block CRCs bit-exact against the compiled reference (oracle/_ref; the restatement where it is absent).
