@@ -17,16 +17,19 @@
 // a multiple of 8 rows (1024 B) so that every TMA box starts on a swizzle-pattern boundary.  Chunk block bl of the unit
 // (bl = 0 .. R-1) is row (bl % Ks) * region_rows + (bl / Ks) * 4 + q.
 //
-// Roles per 128-byte step (every warp walks all of them in this order; barriers are mbarriers, no CTA-wide sync):
-//   REBUILD  (E > 0; the last T warps, ONE STEP AHEAD of everybody) item (source stripe t, quarter q, 16-byte column): syndromes by
-//            Horner over the surviving data columns + the parity columns, RAID-6 solve, rebuilt words stored into the lost slots'
-//            rows of the next step's stage; arrive `rfull`.
-//   GF       (after `rfull`) item (destination stripe g, quarter q, column): walks the Kd blocks of the stripe, stores them
-//            part-major into the destination data parts, Horner-evaluates the destination parity rows, stores them and stages
-//            rows 1.. for their CRC.
-//   CRC      thread-per-row streams: R*4 data rows (verify against the stored CRC when the row was read from a part, and emit
-//            as the destination data part's CRC either way), E*T*4 source parity rows (verify only), G*(M-1)*4 staged
-//            destination parity rows; the CRC of destination parity row 0 comes from linearity as in the encoder.
+// Warp roles (hand-offs are mbarriers; no CTA-wide sync inside the stream of steps):
+//   REBUILD warps (only with lost parts: the warps the CRC rows do not need) do nothing else and run ahead of the workers by as many
+//            stages as are loaded.  Item (source stripe t, quarter q, 16-byte column): syndromes by Horner over the surviving data
+//            columns + the parity columns, RAID-6 elimination, rebuilt words stored into the lost slots' rows of the stage; arrive
+//            `rfull`, release the stage.
+//   WORKER warps, per 128-byte step, after `full` and `rfull`:
+//     GF     item (destination stripe g, quarter q, column): walks the Kd blocks of the stripe (block -> stage offset from a table in
+//            the kernel parameters), stores them part-major into the destination data parts, Horner-evaluates the destination parity
+//            rows, stores them and stages rows 1.. for their CRC.
+//     CRC    one row per thread: R*4 data rows (verified against the stored CRC when the row was read from a part, emitted as the
+//            destination data part's CRC either way), E*T*4 source parity rows (verified only), G*(M-1)*4 staged destination
+//            parity rows; the CRC of destination parity row 0 comes from linearity as in the encoder.
+// Measured history of this structure: profiles/probe_r2.md section 12.
 #pragma once
 #include "fused_kernel.cuh"
 

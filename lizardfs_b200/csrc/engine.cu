@@ -1001,6 +1001,14 @@ static int try_fused_convert(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_
 	for (int i = kd; i < nd; ++i) parity_wanted |= want[i] != 0;
 	if (!parity_wanted) return LZGPU_NOT_HANDLED;
 	int rc;
+	{
+		// the route is decided by pure host logic BEFORE anything is acquired or enqueued (a status slot that was memset on this stream
+		// must not go back to the pool while that memset is pending)
+		uint8_t avail[LZGPU_MAX_PARTS] = {0};
+		for (int i = 0; i < ks + src->m; ++i) avail[i] = d_parts[i] ? 1 : 0;
+		lzgpu_convert_plan plan;
+		if (lzgpu_plan_convert(src, dst, avail, want, &plan) != LZGPU_OK || !plan.one_pass) return LZGPU_NOT_HANDLED;
+	}
 	const size_t crc_stride = (nb + static_cast<size_t>(dst->m) * pbd + 3) & ~size_t(3);
 	if ((rc = t_crc->alloc(n_chunks * crc_stride * 4))) return rc;
 	if (any_crc) {
@@ -1013,7 +1021,12 @@ static int try_fused_convert(lzgpu_ctx *ctx, const lzgpu_goal *src, const lzgpu_
 	rc = lz_fused_convert(ctx, src, dst, n_chunks, nb, d_parts, part_stride, any_crc ? d_part_crc : nullptr, outs, out_stride, t_crc->p, crc_stride, st,
 	                      any_crc ? tk->slot.d : nullptr, &verifying);
 	if (rc != LZGPU_OK) {
-		if (any_crc) ticket_drop(ctx, tk);
+		// (a launch-time refusal — misaligned part pointers, a tensor map the driver rejects: rare)  The slot's memset is already on the
+		// stream: let it finish before the slot can be handed to another call
+		if (any_crc) {
+			cudaStreamSynchronize(st);
+			ticket_drop(ctx, tk);
+		}
 		t_crc->release();
 		return rc;
 	}
