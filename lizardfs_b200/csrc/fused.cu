@@ -123,6 +123,9 @@ static int set_all_recover_attrs() {
 	CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<2, 3, 0, 1, 64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCapBig));
 	CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<2, 5, 0, 1, 64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCapBig));
 	CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<3, 5, 0, 1, 64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCapBig));
+	CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<2, 4, 0, 1, 64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCapBig));
+	CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<2, 6, 0, 1, 64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCapBig));
+	CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<3, 6, 0, 1, 64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCapBig));
 	// DIRECT (any generator; Cauchy codes): 16-warp geometry, 4-byte items
 	if ((rc = set_direct_attr<1>()) || (rc = set_direct_attr<2>()) || (rc = set_direct_attr<3>()) || (rc = set_direct_attr<4>())) return rc;
 	return LZGPU_OK;
@@ -772,6 +775,12 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 	if (K == 5 && geo == 2 && fs->recover_k3) {
 		if (e == 2 && row01 && !(*verifying && d_chunk_out)) return launch_recover_geo2<2, 5, 0, 1>(ctx, maps, p, smem, st);
 		if (e == 3 && row01) return launch_recover_geo2<3, 5, 0, 1>(ctx, maps, p, smem, st);
+	}
+	// ec(4,2), ec(6,2), ec(6,3): the same rule as for k = 5
+	if (K == 4 && geo == 2 && fs->recover_k3 && e == 2 && row01 && !(*verifying && d_chunk_out)) return launch_recover_geo2<2, 4, 0, 1>(ctx, maps, p, smem, st);
+	if (K == 6 && geo == 2 && fs->recover_k3) {
+		if (e == 2 && row01 && !(*verifying && d_chunk_out)) return launch_recover_geo2<2, 6, 0, 1>(ctx, maps, p, smem, st);
+		if (e == 3 && row01) return launch_recover_geo2<3, 6, 0, 1>(ctx, maps, p, smem, st);
 	}
 	switch (e) {
 		case 1:
