@@ -223,6 +223,48 @@ extern "C" int lzgpu_pool_recover_chunks(lzgpu_pool *pool, const lzgpu_goal *goa
 	return rc;
 }
 
+// Slice-type conversion (replication) over the devices of the pool: same arguments as lzgpu_convert_chunks, chunks dealt in runs
+extern "C" int lzgpu_pool_convert_chunks(lzgpu_pool *pool, const lzgpu_goal *src, const lzgpu_goal *dst, uint32_t n_chunks, uint32_t nb,
+                                          const uint8_t *const *parts, size_t part_stride, const uint32_t *const *part_crc, const uint8_t *want,
+                                          uint8_t *const *out, size_t out_stride, uint32_t *const *out_crc, int64_t *bad) {
+	if (!pool || !src || !dst || !parts || !want || !out) return LZGPU_ERR_ARG;
+	if (src->k < 1 || src->k > LZGPU_MAX_DATA || src->m < 0 || src->m > LZGPU_MAX_PARITY || dst->k < 1 || dst->k > LZGPU_MAX_DATA || dst->m < 0 ||
+	    dst->m > LZGPU_MAX_PARITY)
+		return LZGPU_ERR_ARG;
+	if (n_chunks == 0) return LZGPU_OK;
+	const int G = static_cast<int>(pool->workers.size()), ns = src->k + src->m, nd = dst->k + dst->m;
+	// blocks per chunk of a source / destination part (a standard slice has the single part 0 = the chunk itself)
+	const uint32_t pbs = src->kind == LZGPU_KIND_STD ? nb : (nb + src->k - 1) / src->k, pbd = dst->kind == LZGPU_KIND_STD ? nb : (nb + dst->k - 1) / dst->k;
+	std::vector<int64_t> bads(static_cast<size_t>(G) * 3, -1);
+	std::vector<std::string> errs;
+	int rc = pool_run(pool, n_chunks, [&](int i, uint32_t first, uint32_t count) {
+		std::vector<const uint8_t *> p(ns, nullptr);
+		std::vector<const uint32_t *> pc(ns, nullptr);
+		std::vector<uint8_t *> o(nd, nullptr);
+		std::vector<uint32_t *> oc(nd, nullptr);
+		for (int j = 0; j < ns; ++j) {
+			if (parts[j]) p[j] = parts[j] + static_cast<size_t>(first) * part_stride;
+			if (part_crc && part_crc[j]) pc[j] = part_crc[j] + static_cast<size_t>(first) * pbs;
+		}
+		for (int j = 0; j < nd; ++j) {
+			if (out[j]) o[j] = out[j] + static_cast<size_t>(first) * out_stride;
+			if (out_crc && out_crc[j]) oc[j] = out_crc[j] + static_cast<size_t>(first) * pbd;
+		}
+		int r = lzgpu_convert_chunks(pool->workers[i]->ctx, src, dst, count, nb, p.data(), part_stride, part_crc ? pc.data() : nullptr, want, o.data(),
+		                             out_stride, out_crc ? oc.data() : nullptr, &bads[static_cast<size_t>(i) * 3]);
+		if (r == LZGPU_ERR_CRC && bads[static_cast<size_t>(i) * 3] >= 0) bads[static_cast<size_t>(i) * 3] += first;
+		return r;
+	}, &errs);
+	if (rc == LZGPU_ERR_CRC && bad) {
+		for (int i = 0; i < G; ++i)
+			if (bads[static_cast<size_t>(i) * 3] >= 0) {
+				std::memcpy(bad, &bads[static_cast<size_t>(i) * 3], 3 * sizeof(int64_t));
+				break;
+			}
+	}
+	return rc;
+}
+
 extern "C" int lzgpu_pool_crc_blocks(lzgpu_pool *pool, const uint8_t *data, size_t n_blocks, uint32_t block_len, size_t block_stride,
                                       uint32_t *crc_out) {
 	if (!pool || !data || !crc_out) return LZGPU_ERR_ARG;

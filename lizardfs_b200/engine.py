@@ -288,6 +288,28 @@ class Pool:
         _check(rc, "pool_recover_chunks")
         return out, img
 
+    def convert_chunks(self, src, dst, nb, parts, want, part_crc=None, with_crc=True):
+        """Engine.convert_chunks over every device of the pool (lzgpu_pool_convert_chunks)"""
+        ns, nd = src.k + src.m, dst.k + dst.m
+        pbs, pbd = -(-nb // src.k), -(-nb // dst.k)
+        arrs = [None if p is None else _u8(p).reshape(-1, pbs * BLOCK_SIZE) for p in parts]
+        n = next(a.shape[0] for a in arrs if a is not None)
+        crcs = None
+        if part_crc is not None:
+            crcs = [None if c is None else np.ascontiguousarray(c, dtype=np.uint32).reshape(n, pbs) for c in part_crc]
+        w = np.asarray(want, dtype=np.uint8)
+        assert len(arrs) == ns and w.size == nd
+        out = [np.zeros((n, pbd * BLOCK_SIZE), dtype=np.uint8) if w[i] else None for i in range(nd)]
+        ocrc = [np.zeros((n, pbd), dtype=np.uint32) if (w[i] and with_crc) else None for i in range(nd)]
+        bad = (C.c_int64 * 3)(-1, -1, -1)
+        rc = self.lib.lzgpu_pool_convert_chunks(self.h, C.byref(src.c), C.byref(dst.c), n, nb, _ptr_array(arrs), pbs * BLOCK_SIZE,
+                                                _ptr_array(crcs) if crcs is not None else None, _p(w), _ptr_array(out), pbd * BLOCK_SIZE,
+                                                _ptr_array(ocrc) if with_crc else None, bad)
+        if rc == _lib.ERR_CRC:
+            raise ChunkCrcError(rc, "pool_convert_chunks", tuple(bad))
+        _check(rc, "pool_convert_chunks")
+        return out, ocrc
+
     def crc_blocks(self, data, block_len=BLOCK_SIZE):
         data = _u8(data).reshape(-1, block_len)
         out = np.empty(data.shape[0], dtype=np.uint32)

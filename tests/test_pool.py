@@ -78,6 +78,22 @@ def test_pool_encode_and_recover_vs_oracle(oracle):
     with pytest.raises(L.ChunkCrcError) as e:
         pool.recover_chunks(goal, nblocks, bad, part_crc=[None if a is None else pcrc[i] for i, a in enumerate(avail)])
     assert e.value.where == (5, 6, 2)
+    # replication through the pool (lzgpu_pool_convert_chunks): the same degraded slice -> every ec(3,2) part + CRCs, the shares of
+    # the two devices stitched back in chunk order; a corrupt block again reported with its index in the whole batch
+    g32 = L.SliceType("ec(3,2)")
+    acrc = [None if a is None else pcrc[i] for i, a in enumerate(avail)]
+    conv, ccrc = pool.convert_chunks(goal, g32, nblocks, avail, [1] * 5, part_crc=acrc)
+    p32, c32 = pool.encode_chunks(g32, data)
+    per32 = [O.split_parts(data[c], 3)[0] for c in range(n)]
+    pb32 = nblocks // 3
+    for j in range(3):
+        assert (conv[j] == np.stack([per32[c][j] for c in range(n)])).all(), j
+        assert (ccrc[j] == c32[:, j:nblocks:3]).all(), j
+    for r in range(2):
+        assert (conv[3 + r] == p32[:, r]).all() and (ccrc[3 + r] == c32[:, nblocks + r * pb32: nblocks + (r + 1) * pb32]).all(), r
+    with pytest.raises(L.ChunkCrcError) as e:
+        pool.convert_chunks(goal, g32, nblocks, bad, [1] * 5, part_crc=acrc)
+    assert e.value.where == (5, 6, 2)
     blocks = _rnd((37, BLOCK), 5)
     got = pool.crc_blocks(blocks)
     import zlib
