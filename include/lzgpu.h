@@ -107,6 +107,11 @@ typedef struct lzgpu_convert_plan {
 } lzgpu_convert_plan;
 int lzgpu_plan_convert(const lzgpu_goal *src, const lzgpu_goal *dst, const uint8_t *available, const uint8_t *want, lzgpu_convert_plan *out);
 
+/* Diagnostics (pure host logic, no GPU needed): the host build of the bit-plane arithmetic the four-parity-row encoder runs per
+ * item (csrc/bitslice.cuh).  data = k columns of 32 bytes (column j = 32 bytes of data part j, k <= 32); parity receives the
+ * 4 x 32 bytes of the Vandermonde parity rows 0..3 (coefficient of column j in row r: (2^r)^j, galois_field_isal.cc:53-69). */
+int lzgpu_debug_bitslice_rows(int k, const uint8_t *data, uint8_t *parity);
+
 /* ---------------------------------------------------------------------------------------------
  * Engine context: one per (process, device).  Owns streams, pinned staging and device scratch.
  * lzgpu_default_ctx() lazily creates a context on the current device (LZGPU_DEVICE env or 0) for

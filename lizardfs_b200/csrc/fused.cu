@@ -27,6 +27,10 @@ constexpr int kRecoverSmemCap = 200 * 1024;  // recover kernel: one CTA per SM, 
 constexpr int kRecoverSmemCap2 = 100 * 1024; // two CTAs per SM, 3 stages (E <= 2)
 constexpr int kRecoverSmemCapBig = 208 * 1024; // one 16-warp CTA per SM (GEO 2)
 
+#ifndef LZ_BITSLICE_DEFAULT
+#define LZ_BITSLICE_DEFAULT 1
+#endif
+
 struct FusedState {
 	EncodeTiledFn encode_tiled = nullptr;
 	uint32_t qmult64[4], qmult128[4];
@@ -43,6 +47,7 @@ struct FusedState {
 	int cauchy_encode_off = 0;   // LZGPU_CAUCHY_FUSED=0: Cauchy-generator encodes on gf_dot_kernel + CRC passes instead of the fused kernel
 	int convert_off = 0;   // LZGPU_CONVERT_FUSED=0: slice conversion through the two-pass route (image, then SPLIT encode)
 	int direct_wide = -1;  // LZGPU_DIRECT_WIDE: item width of the DIRECT (Cauchy) degraded read, -1 by item count, 0 = 4 bytes, 1 = 8 / 16 bytes, -2 = route off
+	int bitslice = LZ_BITSLICE_DEFAULT;  // LZGPU_BITSLICE: four Vandermonde parity rows on bit planes (W = 8 items, bitslice.cuh); 0 = packed-byte Horner
 	int promo = 3;  // CU_TENSOR_MAP_L2_PROMOTION_L2_256B: +12% streaming bandwidth over 128B/none (profiles/probe_r1.md)
 };
 
@@ -64,6 +69,7 @@ static int set_smem_attr(int bytes) {
 	if (FW == 64) bytes = std::max(bytes, fused_smem_cap(M, GENERIC, FW));  // one-CTA-per-SM shapes use a deeper ring
 	CUDA_TRY(cudaFuncSetAttribute(fused_stream_kernel<M, GENERIC, KT, GT, FW, STRIPED, SPLIT, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
 	if constexpr (GENERIC && W == 4) return set_smem_attr<M, GENERIC, KT, GT, FW, STRIPED, SPLIT, 1>(bytes);  // the narrow-item twin
+	if constexpr (M == 4 && !GENERIC && !SPLIT && FW == 64 && W != 8) return set_smem_attr<M, GENERIC, KT, GT, FW, STRIPED, SPLIT, 8>(bytes);  // the bit-sliced twin
 	return LZGPU_OK;
 }
 
@@ -145,6 +151,7 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if (const char *e = std::getenv("LZGPU_CAUCHY_FUSED")) fs->cauchy_encode_off = std::atoi(e) == 0;
 	if (const char *e = std::getenv("LZGPU_RECOVER_K3")) fs->recover_k3 = std::atoi(e) != 0;
 	if (const char *e = std::getenv("LZGPU_STRIPED")) fs->striped = std::atoi(e);  // 0 never, 1 whenever possible, unset = automatic
+	if (const char *e = std::getenv("LZGPU_BITSLICE")) fs->bitslice = std::atoi(e);
 	void *fn = nullptr;
 	cudaDriverEntryPointQueryResult qres;
 	cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -263,6 +270,9 @@ static int launch(lzgpu_ctx *ctx, const CUtensorMap &map, const FusedParams &p, 
 	const int grid = static_cast<int>(std::min<uint64_t>(p.total_units, static_cast<uint64_t>(ctx->sm_count) * per_sm));
 	if (GENERIC && fused_generic_item_words(p.G) == 1)
 		fused_stream_kernel<M, GENERIC, KT, GT, FW, STRIPED, SPLIT, GENERIC ? 1 : fused_item_words(M, GENERIC)><<<grid, fused_threads(M, GENERIC), smem, st>>>(map, p);
+	else if (M == 4 && !GENERIC && !SPLIT && FW == 64 && ctx->fused->bitslice && p.G * 16 <= 128 && p.G * (p.K + 3) * 4 <= static_cast<uint32_t>(fused_threads(M, GENERIC)) - 128)
+		// bit-sliced twin: warps 0..3 take the 16 G items of a step, the other twelve the G (K + 3) * 4 streams
+		fused_stream_kernel<M, GENERIC, KT, GT, FW, STRIPED, SPLIT, (M == 4 && !GENERIC && !SPLIT) ? 8 : fused_item_words(M, GENERIC)><<<grid, fused_threads(M, GENERIC), smem, st>>>(map, p);
 	else
 		fused_stream_kernel<M, GENERIC, KT, GT, FW, STRIPED, SPLIT><<<grid, fused_threads(M, GENERIC), smem, st>>>(map, p);
 	CUDA_TRY(cudaGetLastError());

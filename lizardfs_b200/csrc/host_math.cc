@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdlib>
 
+#include "bitslice.cuh"
 #include "fused_plan.h"
 
 #include <cctype>
@@ -378,6 +379,22 @@ int lzgpu_plan_encode(const lzgpu_goal *g, uint32_t n_chunks, uint32_t nb, size_
 	out->stage_rows = plr.rows;
 	out->smem_bytes = static_cast<uint32_t>(plr.smem);
 	out->passes = static_cast<uint32_t>((g->m + 3) / 4 > 1 && cauchy ? (g->m + 3) / 4 : 1);
+	return LZGPU_OK;
+}
+
+// Diagnostics: the host build of the per-item arithmetic of the bit-sliced encoder (bitslice.cuh), column k-1 first as the kernel does.
+int lzgpu_debug_bitslice_rows(int k, const uint8_t *data, uint8_t *parity) {
+	if (k < 1 || k > LZGPU_MAX_DATA || !data || !parity) return LZGPU_ERR_ARG;
+	lzd::BsRows4 rows;
+	lzd::bs_rows_clear(rows);
+	for (int j = k - 1; j >= 0; --j) {
+		uint32_t v[8];
+		std::memcpy(v, data + 32 * j, 32);
+		lzd::bs_rows_add_column(rows, v);
+	}
+	lzd::bs_rows_finish(rows);
+	std::memcpy(parity, rows.p0, 32);
+	for (int r = 1; r < 4; ++r) std::memcpy(parity + 32 * r, rows.p[r - 1], 32);
 	return LZGPU_OK;
 }
 

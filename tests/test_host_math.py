@@ -296,3 +296,31 @@ def test_convert_plan_decisions():
     # too few parts: the error of the call itself
     with pytest.raises(L.LzGpuError):
         plan("ec(3,2)", (0, 1, 2), "ec(8,2)")
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 8, 12, 20, 32])
+def test_bitslice_rows_match_the_generator(oracle, k):
+    """The bit-plane arithmetic of the four-parity-row encoder (csrc/bitslice.cuh, host build of the very functions the kernel
+    inlines): 32 bytes per data part through bytes -> planes -> Horner rows 1..3 -> bytes must equal the parity rows of the
+    reference's Vandermonde generator (gf_gen_rs_matrix, galois_field_isal.cc:53-69) applied byte by byte with the oracle's
+    field multiplication — for random columns and for the unit vectors (every bit of every byte lane once)."""
+    from lizardfs_b200 import _lib
+    lib = _lib.load()
+    gen = oracle.gen_rs_matrix(k + 4, k)[k:]          # [4][k]
+    rng = np.random.default_rng(50 + k)
+    cases = [rng.integers(0, 256, size=(k, 32), dtype=np.uint8) for _ in range(8)]
+    for j in range(k):
+        for bit in range(0, 256, 37):
+            d = np.zeros((k, 32), dtype=np.uint8)
+            d[j, bit // 8] = 1 << (bit % 8)
+            cases.append(d)
+    for d in cases:
+        out = np.zeros((4, 32), dtype=np.uint8)
+        assert lib.lzgpu_debug_bitslice_rows(k, d.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)) == 0
+        want = np.zeros((4, 32), dtype=np.uint8)
+        for r in range(4):
+            for j in range(k):
+                c = int(gen[r][j])
+                if c:
+                    want[r] ^= np.array([oracle.gf_mul(c, int(x)) for x in d[j]], dtype=np.uint8)
+        assert (out == want).all(), k
