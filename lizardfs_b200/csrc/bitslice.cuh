@@ -1,4 +1,4 @@
-// bitslice.cuh — GF(2^8) on BIT PLANES: the arithmetic of the four-parity-row encoder (fused_kernel.cuh, items of W = 8 words).
+// bitslice.cuh — GF(2^8) on BIT PLANES: the arithmetic of the three- and four-parity-row encoders (fused_kernel.cuh, items of W = 8 words).
 //
 // A group is 8 packed words (32 bytes) of ONE part.  bs_transpose turns it into 8 planes: plane i holds bit i of each of the 32
 // bytes (plane i, byte lane B, bit w  <-  word w, byte lane B, bit i) with three rounds of masked exchanges between register pairs
@@ -113,26 +113,33 @@ LZ_HD inline void bs_horner(uint32_t (&a)[8], const uint32_t (&d)[8]) {
 	}
 }
 
-// The GF role of one item of the four-row encoder, as the kernel runs it: column j = k-1 .. 0 of the stripe arrives as 8 packed
-// words, row 0 accumulates on bytes, rows 1..3 on planes; bs_rows_finish turns the three plane accumulators back into bytes.
-struct BsRows4 {
-	uint32_t p0[8];      // row 0 (XOR), bytes
-	uint32_t p[3][8];    // rows 1..3, planes until bs_rows_finish
+// The GF role of one item of the M-row encoder (M = 3, 4), as the kernel runs it: column j = k-1 .. 0 of the stripe arrives as 8
+// packed words, row 0 accumulates on bytes, rows 1..M-1 on planes; bs_rows_finish turns the plane accumulators back into bytes.
+template <int M>
+struct BsRows {
+	static_assert(M == 3 || M == 4, "three or four Vandermonde rows");
+	uint32_t p0[8];          // row 0 (XOR), bytes
+	uint32_t p[M - 1][8];    // rows 1..M-1, planes until bs_rows_finish
 };
-LZ_HD inline void bs_rows_clear(BsRows4 &s) {
-	for (int i = 0; i < 8; ++i) s.p0[i] = s.p[0][i] = s.p[1][i] = s.p[2][i] = 0;
+template <int M>
+LZ_HD inline void bs_rows_clear(BsRows<M> &s) {
+	for (int i = 0; i < 8; ++i) {
+		s.p0[i] = 0;
+		for (int r = 0; r < M - 1; ++r) s.p[r][i] = 0;
+	}
 }
-LZ_HD inline void bs_rows_add_column(BsRows4 &s, uint32_t (&v)[8]) {
+template <int M>
+LZ_HD inline void bs_rows_add_column(BsRows<M> &s, uint32_t (&v)[8]) {
 	for (int i = 0; i < 8; ++i) s.p0[i] ^= v[i];
 	bs_transpose(v);
 	bs_horner<1>(s.p[0], v);
 	bs_horner<2>(s.p[1], v);
-	bs_horner<3>(s.p[2], v);
+	if constexpr (M == 4) bs_horner<3>(s.p[2], v);
 }
-LZ_HD inline void bs_rows_finish(BsRows4 &s) {
-	bs_transpose(s.p[0]);
-	bs_transpose(s.p[1]);
-	bs_transpose(s.p[2]);
+template <int M>
+LZ_HD inline void bs_rows_finish(BsRows<M> &s) {
+	for (int r = 0; r < M - 1; ++r) bs_transpose(s.p[r]);
 }
+using BsRows4 = BsRows<4>;
 
 }  // namespace lzd

@@ -27,10 +27,6 @@ constexpr int kRecoverSmemCap = 200 * 1024;  // recover kernel: one CTA per SM, 
 constexpr int kRecoverSmemCap2 = 100 * 1024; // two CTAs per SM, 3 stages (E <= 2)
 constexpr int kRecoverSmemCapBig = 208 * 1024; // one 16-warp CTA per SM (GEO 2)
 
-#ifndef LZ_BITSLICE_DEFAULT
-#define LZ_BITSLICE_DEFAULT 1
-#endif
-
 struct FusedState {
 	EncodeTiledFn encode_tiled = nullptr;
 	uint32_t qmult64[4], qmult128[4];
@@ -47,7 +43,7 @@ struct FusedState {
 	int cauchy_encode_off = 0;   // LZGPU_CAUCHY_FUSED=0: Cauchy-generator encodes on gf_dot_kernel + CRC passes instead of the fused kernel
 	int convert_off = 0;   // LZGPU_CONVERT_FUSED=0: slice conversion through the two-pass route (image, then SPLIT encode)
 	int direct_wide = -1;  // LZGPU_DIRECT_WIDE: item width of the DIRECT (Cauchy) degraded read, -1 by item count, 0 = 4 bytes, 1 = 8 / 16 bytes, -2 = route off
-	int bitslice = LZ_BITSLICE_DEFAULT;  // LZGPU_BITSLICE: four Vandermonde parity rows on bit planes (W = 8 items, bitslice.cuh); 0 = packed-byte Horner
+	int bitslice = LZ_BITSLICE_DEFAULT;  // LZGPU_BITSLICE: bit 0 = four, bit 1 = three Vandermonde parity rows on bit planes (W = 8 items, bitslice.cuh); 0 = packed-byte Horner
 	int promo = 3;  // CU_TENSOR_MAP_L2_PROMOTION_L2_256B: +12% streaming bandwidth over 128B/none (profiles/probe_r1.md)
 };
 
@@ -69,7 +65,6 @@ static int set_smem_attr(int bytes) {
 	if (FW == 64) bytes = std::max(bytes, fused_smem_cap(M, GENERIC, FW));  // one-CTA-per-SM shapes use a deeper ring
 	CUDA_TRY(cudaFuncSetAttribute(fused_stream_kernel<M, GENERIC, KT, GT, FW, STRIPED, SPLIT, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
 	if constexpr (GENERIC && W == 4) return set_smem_attr<M, GENERIC, KT, GT, FW, STRIPED, SPLIT, 1>(bytes);  // the narrow-item twin
-	if constexpr (M == 4 && !GENERIC && !SPLIT && FW == 64 && W != 8) return set_smem_attr<M, GENERIC, KT, GT, FW, STRIPED, SPLIT, 8>(bytes);  // the bit-sliced twin
 	return LZGPU_OK;
 }
 
@@ -136,6 +131,8 @@ static int set_all_recover_attrs() {
 	if ((rc = set_direct_attr<1>()) || (rc = set_direct_attr<2>()) || (rc = set_direct_attr<3>()) || (rc = set_direct_attr<4>())) return rc;
 	return LZGPU_OK;
 }
+
+static int set_all_bs_attrs();
 
 int lz_fused_init(lzgpu_ctx *ctx) {
 	auto *fs = new FusedState();
@@ -235,6 +232,7 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if ((rc = set_smem_attr<4, false, 8, 5, 128>(smem128))) return rc;
 	if ((rc = set_smem_attr<3, false, 5, 8, 128>(smem128))) return rc;
 #endif
+	if ((rc = set_all_bs_attrs())) return rc;
 	if ((rc = set_all_recover_attrs())) return rc;
 	if ((rc = set_all_convert_attrs())) return rc;
 	return LZGPU_OK;
@@ -270,13 +268,40 @@ static int launch(lzgpu_ctx *ctx, const CUtensorMap &map, const FusedParams &p, 
 	const int grid = static_cast<int>(std::min<uint64_t>(p.total_units, static_cast<uint64_t>(ctx->sm_count) * per_sm));
 	if (GENERIC && fused_generic_item_words(p.G) == 1)
 		fused_stream_kernel<M, GENERIC, KT, GT, FW, STRIPED, SPLIT, GENERIC ? 1 : fused_item_words(M, GENERIC)><<<grid, fused_threads(M, GENERIC), smem, st>>>(map, p);
-	else if (M == 4 && !GENERIC && !SPLIT && FW == 64 && ctx->fused->bitslice && p.G * 16 <= 128 && p.G * (p.K + 3) * 4 <= static_cast<uint32_t>(fused_threads(M, GENERIC)) - 128)
-		// bit-sliced twin: warps 0..3 take the 16 G items of a step, the other twelve the G (K + 3) * 4 streams
-		fused_stream_kernel<M, GENERIC, KT, GT, FW, STRIPED, SPLIT, (M == 4 && !GENERIC && !SPLIT) ? 8 : fused_item_words(M, GENERIC)><<<grid, fused_threads(M, GENERIC), smem, st>>>(map, p);
 	else
 		fused_stream_kernel<M, GENERIC, KT, GT, FW, STRIPED, SPLIT><<<grid, fused_threads(M, GENERIC), smem, st>>>(map, p);
 	CUDA_TRY(cudaGetLastError());
 	ctx->stats.kernel_launches++;
+	return LZGPU_OK;
+}
+
+// bit-sliced instantiations (W = 8: one 16-warp CTA per SM, the last four warps take the 16 G items of a step, the first twelve the
+// G (K + M - 1) * 4 streams; the plan made with bs = true guarantees both fit)
+template <int M, int KT = 0, int GT = 0, bool STRIPED = false>
+static int set_bs_attr() {
+	CUDA_TRY(cudaFuncSetAttribute(fused_stream_kernel<M, false, KT, GT, 64, STRIPED, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem_cap(M, false, 64, true)));
+	return LZGPU_OK;
+}
+template <int M, int KT = 0, int GT = 0, bool STRIPED = false>
+static int launch_bs(lzgpu_ctx *ctx, const CUtensorMap &map, const FusedParams &p, size_t smem, cudaStream_t st) {
+	const int grid = static_cast<int>(std::min<uint64_t>(p.total_units, static_cast<uint64_t>(ctx->sm_count)));
+	fused_stream_kernel<M, false, KT, GT, 64, STRIPED, false, 8><<<grid, kBsThreads, smem, st>>>(map, p);
+	CUDA_TRY(cudaGetLastError());
+	ctx->stats.kernel_launches++;
+	return LZGPU_OK;
+}
+// the constant-folded (M, K, G) of the bit-sliced route: G from pick_group(.., bs = true)
+#define LZ_BS_FOLDED_LIST(X) X(4, 8, 8) X(4, 10, 6) X(4, 12, 5) X(4, 6, 8) X(4, 4, 8) X(3, 5, 8) X(3, 6, 8) X(3, 8, 8) X(3, 4, 8)
+#define LZ_BS_FOLDED_STRIPED_LIST(X) X(4, 8, 8) X(3, 5, 8)
+static int set_all_bs_attrs() {
+	int rc;
+#define LZ_X(MM, KK, GG) if ((rc = set_bs_attr<MM, KK, GG>())) return rc;
+	LZ_BS_FOLDED_LIST(LZ_X)
+#undef LZ_X
+#define LZ_X(MM, KK, GG) if ((rc = set_bs_attr<MM, KK, GG, true>())) return rc;
+	LZ_BS_FOLDED_STRIPED_LIST(LZ_X)
+#undef LZ_X
+	if ((rc = set_bs_attr<3>()) || (rc = set_bs_attr<4>()) || (rc = set_bs_attr<3, 0, 0, true>()) || (rc = set_bs_attr<4, 0, 0, true>())) return rc;
 	return LZGPU_OK;
 }
 
@@ -305,9 +330,13 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	FusedState *fs = ctx->fused;
 	const uint32_t PC = M == 0 ? 0 : (generic ? M : M - 1);
 	const int fw = choose_fold(fs, M, generic);
-	const int smem_cap = std::min(fs->max_smem, fw == 64 ? fused_smem_cap(M, generic, fw) : kSmemCap128);
-	// unit geometry: per-chunk, flat or striped units, stripes per unit (fused_plan.h; unit-tested without a GPU)
-	const FusedPlan pl = fused_plan(M, generic, K, n_chunks, nb, chunk_stride, smem_cap, fw, split_out ? 0 : (striped_policy == -2 ? fs->striped : striped_policy));
+	// unit geometry: per-chunk, flat or striped units, stripes per unit (fused_plan.h; unit-tested without a GPU); the bit-sliced
+	// geometry first where it is switched on, the packed-byte one if a shape does not fit it
+	const int spol = split_out ? 0 : (striped_policy == -2 ? fs->striped : striped_policy);
+	FusedPlan pl;
+	if (!split_out && fw == 64 && fused_bitslice(M, generic, fs->bitslice))
+		pl = fused_plan(M, generic, K, n_chunks, nb, chunk_stride, std::min(fs->max_smem, fused_smem_cap(M, generic, fw, true)), fw, spol, true);
+	if (!pl.ok) pl = fused_plan(M, generic, K, n_chunks, nb, chunk_stride, std::min(fs->max_smem, fw == 64 ? fused_smem_cap(M, generic, fw) : kSmemCap128), fw, spol);
 	if (!pl.ok || (reinterpret_cast<uintptr_t>(d_data) % 16)) return LZGPU_NOT_HANDLED;
 	const uint32_t G = pl.G;
 	const bool flat = pl.mode == 1u, striped = pl.mode == 2u;
@@ -361,6 +390,18 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 			case 4: return launch<4, false, 0, 0, 64, false, true>(ctx, map, p, smem, st);
 		}
 		return LZGPU_NOT_HANDLED;
+	}
+	if (pl.bs) {
+		if (striped) {
+#define LZ_X(MM, KK, GG) if (M == MM && K == KK && G == GG) return launch_bs<MM, KK, GG, true>(ctx, map, p, smem, st);
+			LZ_BS_FOLDED_STRIPED_LIST(LZ_X)
+#undef LZ_X
+			return M == 3 ? launch_bs<3, 0, 0, true>(ctx, map, p, smem, st) : launch_bs<4, 0, 0, true>(ctx, map, p, smem, st);
+		}
+#define LZ_X(MM, KK, GG) if (M == MM && K == KK && G == GG) return launch_bs<MM, KK, GG>(ctx, map, p, smem, st);
+		LZ_BS_FOLDED_LIST(LZ_X)
+#undef LZ_X
+		return M == 3 ? launch_bs<3>(ctx, map, p, smem, st) : launch_bs<4>(ctx, map, p, smem, st);
 	}
 	if (striped) {
 		if (generic) {

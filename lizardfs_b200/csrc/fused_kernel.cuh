@@ -20,7 +20,7 @@
 //   GF role    item (stripe g, quarter q, 16-byte column i): reads the K data blocks of the stripe at
 //              that column, Horner-evaluates the Vandermonde parity rows (row r: acc = acc*2^r + d_j,
 //              reference generator galois_field_isal.cc:53-69) on packed words, stores 16 B per parity.
-//   GF role, bit-sliced (W = 8, four parity rows): item (stripe g, quarter pair h, 16-byte column c) = the 16 bytes at column c
+//   GF role, bit-sliced (W = 8, three or four parity rows): item (stripe g, quarter pair h, 16-byte column c) = the 16 bytes at column c
 //              of quarters h and h + 2 of every data block of the stripe; rows 1..3 are Horner-evaluated on BIT PLANES
 //              (bitslice.cuh: multiplying 32 bytes by 2^r is a register renaming + a few XORs), row 0 on bytes.  A step has only
 //              16 G <= 128 such items: the LAST four warps (one per scheduler; the arbiter prefers the highest warp slot, so the
@@ -293,14 +293,14 @@ __device__ __forceinline__ uint32_t fold_finish(uint32_t (&win)[FW], const uint3
 // (An explicit __maxnreg__(96) instead of the launch bounds produced a 5 % slower kernel on the same box: ptxas
 // schedules differently when it does not know the block size.)
 template <int M, bool GENERIC, int KT, int GT, int FW, bool STRIPED = false, bool SPLIT = false, int W = fused_item_words(M, GENERIC)>
-__global__ void __launch_bounds__(fused_threads(M, GENERIC), fused_ctas_per_sm(M, GENERIC, FW))
+__global__ void __launch_bounds__(fused_threads(M, GENERIC, W == 8), fused_ctas_per_sm(M, GENERIC, FW, W == 8))
 fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
-	constexpr int kNST = fused_nst(FW, M, GENERIC), kNPST = fused_npst(FW, M, GENERIC);
-	constexpr int NT = fused_threads(M, GENERIC);
+	constexpr int kNST = fused_nst(FW, M, GENERIC, W == 8), kNPST = fused_npst(FW, M, GENERIC);
+	constexpr int NT = fused_threads(M, GENERIC, W == 8);
 	constexpr int PC = (M == 0) ? 0 : (GENERIC ? M : M - 1);  // parity parts whose CRC is computed from bytes
 	constexpr int P0 = GENERIC ? 0 : 1;                       // first such parity part
 	constexpr bool BS = W == 8;                               // bit-sliced GF role (header comment)
-	static_assert(!BS || (M == 4 && !GENERIC && !SPLIT), "bit-sliced items: four Vandermonde rows, plain encode");
+	static_assert(!BS || ((M == 3 || M == 4) && !GENERIC && !SPLIT && FW == 64), "bit-sliced items: three or four Vandermonde rows, plain encode");
 
 	extern __shared__ __align__(1024) uint8_t smem[];
 	const uint32_t sbase = smem_u32(smem);
@@ -437,7 +437,7 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 					if (cw - kBsGfWarp0 < n_gf_warps && !LZ_PROBE(2)) {
 						mbar_wait(a_pempty + 8 * pst, pph ^ 1);
 						if (has_item) {
-							BsRows4 rows4;
+							BsRows<BS ? M : 4> rows4;
 							bs_rows_clear(rows4);
 #pragma unroll
 							for (int j = static_cast<int>(K) - 1; j >= 0; --j) {
@@ -452,14 +452,14 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 								st_stream(reinterpret_cast<uint4 *>(dst), make_uint4(rows4.p0[0], rows4.p0[1], rows4.p0[2], rows4.p0[3]));
 								st_stream(reinterpret_cast<uint4 *>(dst + 32768), make_uint4(rows4.p0[4], rows4.p0[5], rows4.p0[6], rows4.p0[7]));
 #pragma unroll
-								for (int r = 1; r < 4; ++r) {
+								for (int r = 1; r < M; ++r) {
 									const uint32_t (&w)[8] = rows4.p[r - 1];
 									st_stream(reinterpret_cast<uint4 *>(dst + r * part_bytes), make_uint4(w[0], w[1], w[2], w[3]));
 									st_stream(reinterpret_cast<uint4 *>(dst + r * part_bytes + 32768), make_uint4(w[4], w[5], w[6], w[7]));
 								}
 							}
 #pragma unroll
-							for (int r = 1; r < 4; ++r) {
+							for (int r = 1; r < M; ++r) {
 								const uint32_t (&w)[8] = rows4.p[r - 1];
 								const uint32_t pr = (g * PC + (r - 1)) * 4 + h;
 								const uint32_t pa = (pstage + pr * kStepBytes) ^ ((col ^ (pr & 7)) << 4);
@@ -596,7 +596,7 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 				if (has_stream && !(GENERIC && is_data_row && p.skip_data_crc) && !LZ_PROBE(4)) {
 					const uint32_t rowp = row_addr0 + (is_data_row ? st : pst) * row_stride;
 					// (the auxiliary sequence needs ~18 registers: only where a thread has more than 112)
-					fold_step<FW, (NT * fused_ctas_per_sm(M, GENERIC, FW) <= 512)>(win, aux, sub * 32, rowp);
+					fold_step<FW, (NT * fused_ctas_per_sm(M, GENERIC, FW, BS) <= 512)>(win, aux, sub * 32, rowp);
 				}
 				__syncwarp();
 				if (STRIPED) {

@@ -51,7 +51,15 @@ constexpr int kSmemCap = 113 * 1024;                   // dynamic shared memory 
 #ifndef LZ_W4
 #define LZ_W4 2           // ec(8,4): 512 eight-byte items fill the 16 warps (0.43 -> 0.52 of the HBM peak, profiles/sweep_r2.md)
 #endif
-LZ_HD constexpr int fused_threads(int m, bool generic) { return generic ? LZ_TGEN : m <= 2 ? LZ_T2 : m == 3 ? LZ_T3 : LZ_T4; }
+// Bit-sliced GF role (bitslice.cuh; round 2, run 26: ec(8,4) 0.52 -> 0.79, ec(6,4) 0.50 -> 0.71, ec(10,4) 0.42 -> 0.60 of the HBM peak):
+// three or four Vandermonde rows on ONE 16-warp CTA per SM whose last four warps only do the GF items (32-byte items on bit
+// planes) and whose first twelve own the CRC streams.  LZGPU_BITSLICE / LZ_BITSLICE_DEFAULT: bit 0 = four parity rows, bit 1 = three.
+#ifndef LZ_BITSLICE_DEFAULT
+#define LZ_BITSLICE_DEFAULT 3
+#endif
+constexpr int kBsThreads = 512, kBsGfThreads = 128;
+LZ_HD constexpr bool fused_bitslice(int m, bool generic, int mask) { return !generic && ((m == 4 && (mask & 1)) || (m == 3 && (mask & 2))); }
+LZ_HD constexpr int fused_threads(int m, bool generic, bool bs = false) { return bs ? kBsThreads : generic ? LZ_TGEN : m <= 2 ? LZ_T2 : m == 3 ? LZ_T3 : LZ_T4; }
 // packed words per GF item (4 = 16 bytes); narrower items = more, lighter items per step
 // (generic coefficients: chosen per launch by fused_generic_item_words — both widths are instantiated)
 LZ_HD constexpr int fused_item_words(int m, bool generic) { return generic ? 4 : m == 3 ? LZ_W3 : m == 4 ? LZ_W4 : 4; }
@@ -62,7 +70,7 @@ LZ_HD constexpr int fused_item_words(int m, bool generic) { return generic ? 4 :
 LZ_HD constexpr int fused_generic_item_words(uint32_t G) { return 32 * G >= 96 ? 4 : 1; }
 // CTAs per SM: two, except for the 128-word fold window and for CTAs of more than nine warps (16 warps x 128 registers fill the
 // register file on their own; their stage ring is deeper instead)
-LZ_HD constexpr int fused_ctas_per_sm(int m, bool generic, int fw) { return (fw != 64 || fused_threads(m, generic) > 320) ? 1 : 2; }
+LZ_HD constexpr int fused_ctas_per_sm(int m, bool generic, int fw, bool bs = false) { return (fw != 64 || fused_threads(m, generic, bs) > 320) ? 1 : 2; }
 
 // pipeline depth by fold window: FW = 64 -> 2 CTAs/SM (96-128 registers), 3 data stages + 4-deep parity ring (4 stages for the
 // one-CTA shapes); FW = 128 -> 1 CTA/SM (the 128-word window needs ~170 registers), 6 data stages + 6-deep parity ring
@@ -72,13 +80,13 @@ LZ_HD constexpr int fused_ctas_per_sm(int m, bool generic, int fw) { return (fw 
 #ifndef LZ_NST_BIG
 #define LZ_NST_BIG 4
 #endif
-LZ_HD constexpr int fused_nst(int fw, int m, bool generic) { return fw != 64 ? 6 : (fused_ctas_per_sm(m, generic, fw) == 1 ? LZ_NST_BIG : 3); }
+LZ_HD constexpr int fused_nst(int fw, int m, bool generic, bool bs = false) { return fw != 64 ? 6 : (fused_ctas_per_sm(m, generic, fw, bs) == 1 ? LZ_NST_BIG : 3); }
 LZ_HD constexpr int fused_npst(int fw, int m, bool generic) { return fw == 64 ? LZ_NPST : 6; }
-LZ_HD constexpr int fused_smem_cap(int m, bool generic, int fw) { return fused_ctas_per_sm(m, generic, fw) == 1 ? 200 * 1024 : kSmemCap; }
+LZ_HD constexpr int fused_smem_cap(int m, bool generic, int fw, bool bs = false) { return fused_ctas_per_sm(m, generic, fw, bs) == 1 ? 200 * 1024 : kSmemCap; }
 
-inline size_t fused_smem_bytes(uint32_t rows, uint32_t prows, int fw, int m, bool generic) {
+inline size_t fused_smem_bytes(uint32_t rows, uint32_t prows, int fw, int m, bool generic, bool bs = false) {
 	const size_t pstage = (static_cast<size_t>(prows) * kStepBytes + 1023) & ~size_t(1023);
-	const size_t nst = fused_nst(fw, m, generic), npst = fused_npst(fw, m, generic);
+	const size_t nst = fused_nst(fw, m, generic, bs), npst = fused_npst(fw, m, generic);
 	return nst * rows * kStepBytes + npst * pstage + 520 + 8 * (2 * nst + 2 * npst);
 }
 
@@ -87,15 +95,17 @@ inline size_t fused_smem_bytes(uint32_t rows, uint32_t prows, int fw, int m, boo
 #ifndef LZ_GCAP
 #define LZ_GCAP 1         // on the one-CTA shapes never plan more GF items per step than the CTA has threads (ec(4,4): G = 16 would
 #endif                    // give every thread two items and leave half the warps without a stream: 0.35 -> 0.38 with G = 8)
-inline uint32_t pick_group(uint32_t K, uint32_t PC, int max_smem_per_cta, int fw, uint32_t threads, int m, bool generic) {
+// (bit-sliced: 16 items of 32 bytes per stripe and step, all of them on the four GF warps; the streams on the other twelve)
+inline uint32_t pick_group(uint32_t K, uint32_t PC, int max_smem_per_cta, int fw, uint32_t threads, int m, bool generic, bool bs = false) {
 	uint32_t best = 0;
-	const uint32_t items_per_stripe = 128u / static_cast<uint32_t>(fused_item_words(m, generic));
+	const uint32_t items_per_stripe = bs ? 16u : 128u / static_cast<uint32_t>(fused_item_words(m, generic));
+	const uint32_t item_threads = bs ? static_cast<uint32_t>(kBsGfThreads) : threads, stream_threads = bs ? threads - kBsGfThreads : threads;
 	for (uint32_t g = 1; g <= 64; ++g) {
-		if (LZ_GCAP && (threads > 288 || m >= 3) && m > 0 && best && g * items_per_stripe > threads) break;
+		if ((bs || (LZ_GCAP && (threads > 288 || m >= 3) && m > 0 && best)) && g * items_per_stripe > item_threads) break;
 		const uint32_t rows = g * K * 4, prows = g * PC * 4;
-		if (rows > kMaxRows || rows + prows > threads || prows > kMaxParityRows || g * K > 64) break;
+		if (rows > kMaxRows || rows + prows > stream_threads || prows > kMaxParityRows || g * K > 64) break;
 		if (rows % 8) continue;
-		if (fused_smem_bytes(rows, prows, fw, m, generic) > static_cast<size_t>(max_smem_per_cta)) break;
+		if (fused_smem_bytes(rows, prows, fw, m, generic, bs) > static_cast<size_t>(max_smem_per_cta)) break;
 		best = g;
 	}
 	return best;
@@ -108,17 +118,19 @@ struct FusedPlan {
 	uint32_t G = 0, pb = 0, mode = 0, units_per_chunk = 0, total_units = 0, threads = 0, rows = 0, prows = 0;
 	size_t smem = 0;
 	bool ok = false;  // false: the fused kernel does not take this shape (generic kernels do)
+	bool bs = false;  // bit-sliced geometry (16 warps, four of them GF warps)
 };
 
 // striped_policy: -1 automatic (striped when per-chunk units would leave more than 12 % of their stripe slots empty — measured,
 // profiles/sweep_r1.md: G boxes per step instead of one cost 2-10 % at 64 MiB and win up to 2.4x at 1-4 MiB), 0 never, 1 always
 inline FusedPlan fused_plan(int M, bool generic, uint32_t K, uint32_t n_chunks, uint32_t nb, size_t chunk_stride, int smem_cap, int fw,
-                            int striped_policy) {
+                            int striped_policy, bool bs = false) {
 	FusedPlan pl;
 	const uint32_t PC = M == 0 ? 0 : (generic ? M : M - 1);
 	const int mm = M;  // the instantiation's M (thread count, stage depth); a Cauchy generator is encoded in passes of <= 4 rows
-	pl.threads = static_cast<uint32_t>(fused_threads(mm, generic));
-	pl.G = pick_group(K, PC, smem_cap, fw, pl.threads, mm, generic);
+	pl.threads = static_cast<uint32_t>(fused_threads(mm, generic, bs));
+	pl.bs = bs;
+	pl.G = pick_group(K, PC, smem_cap, fw, pl.threads, mm, generic, bs);
 	if (pl.G == 0 || (chunk_stride % 16)) return pl;
 	const uint32_t G = pl.G;
 	pl.pb = (nb + K - 1) / K;
@@ -143,7 +155,7 @@ inline FusedPlan fused_plan(int M, bool generic, uint32_t K, uint32_t n_chunks, 
 	pl.total_units = static_cast<uint32_t>(total);
 	pl.rows = G * K * 4;
 	pl.prows = G * PC * 4;
-	pl.smem = fused_smem_bytes(pl.rows, pl.prows, fw, mm, generic);
+	pl.smem = fused_smem_bytes(pl.rows, pl.prows, fw, mm, generic, bs);
 	pl.ok = true;
 	return pl;
 }

@@ -1,7 +1,7 @@
-"""GPU parity tests of the BIT-SLICED four-parity-row encoder (fused_stream_kernel, W = 8 items, csrc/bitslice.cuh) against the
-oracle / the compiled reference: every Vandermonde ec(k,4) (k <= 20; larger k use Cauchy rows, reed_solomon.h:168-172) in all
-three unit modes (per-chunk, flat, striped), tail stripes, padded strides, full 64 MiB chunks — and, both ways round, that the
-packed-byte Horner route (LZGPU_BITSLICE=0) and the bit-plane route (LZGPU_BITSLICE=1) give the same bytes."""
+"""GPU parity tests of the BIT-SLICED three- and four-parity-row encoders (fused_stream_kernel, W = 8 items, csrc/bitslice.cuh)
+against the oracle / the compiled reference: every Vandermonde ec(k,4) (k <= 20; larger k use Cauchy rows,
+reed_solomon.h:168-172) and ec(k,3) in all three unit modes (per-chunk, flat, striped), tail stripes, padded strides, full 64 MiB chunks — and, both ways round, that the
+packed-byte Horner route (LZGPU_BITSLICE=0) and the bit-plane route (LZGPU_BITSLICE=3) give the same bytes."""
 import os
 
 import numpy as np
@@ -29,7 +29,7 @@ def engine_with(**env):
 
 @pytest.fixture(scope="module")
 def eng_bs():
-    e = engine_with(LZGPU_BITSLICE=1)
+    e = engine_with(LZGPU_BITSLICE=3)
     yield e
     e.close()
 
@@ -45,11 +45,12 @@ def rnd(shape, seed):
     return np.random.default_rng(seed).integers(0, 256, size=shape, dtype=np.uint8)
 
 
-@pytest.mark.parametrize("k", [2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 16, 17, 20])
-def test_every_vandermonde_k_with_four_parity_parts(eng_bs, oracle, k):
-    """per-chunk units with a tail stripe (nb = 3k + 1, or 2k + 1 for the widest) and a second chunk that starts a new unit"""
-    goal = L.SliceType(f"ec({k},4)")
-    nb = min(3 * k + 1, 61)
+@pytest.mark.parametrize("k,m", [(k, 4) for k in (2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 16, 17, 20)] +
+                         [(k, 3) for k in (2, 3, 4, 5, 6, 7, 8, 9, 11, 12, 16, 21, 25, 31, 32)])
+def test_every_vandermonde_k_with_three_and_four_parity_parts(eng_bs, oracle, k, m):
+    """per-chunk units with a tail stripe (nb = 3k + 1, fewer for the widest) and more chunks that start new units"""
+    goal = L.SliceType(f"ec({k},{m})")
+    nb = min(3 * k + 1, 2 * k + 3 if k > 20 else 61)
     data = rnd((3, nb * BLOCK), 1000 + k)
     parity, crc = eng_bs.encode_chunks(goal, data)
     for c in range(3):
@@ -58,7 +59,8 @@ def test_every_vandermonde_k_with_four_parity_parts(eng_bs, oracle, k):
         assert (crc[c] == c_ref).all(), (k, c)
 
 
-@pytest.mark.parametrize("text,nblocks,n_chunks", [("ec(8,4)", 16, 9), ("ec(4,4)", 8, 21), ("ec(6,4)", 12, 7), ("ec(10,4)", 20, 5), ("ec(12,4)", 24, 4), ("ec(8,4)", 64, 5)])
+@pytest.mark.parametrize("text,nblocks,n_chunks", [("ec(8,4)", 16, 9), ("ec(4,4)", 8, 21), ("ec(6,4)", 12, 7), ("ec(10,4)", 20, 5), ("ec(12,4)", 24, 4), ("ec(8,4)", 64, 5),
+                                                    ("ec(5,3)", 10, 13), ("ec(8,3)", 16, 6), ("ec(6,3)", 18, 5), ("ec(4,3)", 4, 30)])
 def test_flat_units_many_small_chunks(eng_bs, oracle, text, nblocks, n_chunks):
     """chunks of whole stripes, contiguous: 'flat' units run across chunk boundaries"""
     goal = L.SliceType(text)
@@ -72,10 +74,10 @@ def test_flat_units_many_small_chunks(eng_bs, oracle, text, nblocks, n_chunks):
 
 @pytest.mark.parametrize("striped", ["0", "1"])
 @pytest.mark.parametrize("text,nblocks,n_chunks,stride_blocks", [("ec(8,4)", 19, 7, 24), ("ec(8,4)", 13, 11, 13), ("ec(5,4)", 11, 9, 11), ("ec(12,4)", 30, 4, 30),
-                                                                  ("ec(8,4)", 1, 20, 1), ("ec(6,4)", 7, 6, 10)])
+                                                                  ("ec(8,4)", 1, 20, 1), ("ec(6,4)", 7, 6, 10), ("ec(5,3)", 11, 17, 11), ("ec(5,3)", 7, 9, 12), ("ec(31,3)", 40, 3, 40)])
 def test_ragged_chunks_striped_and_per_chunk_units(oracle, striped, text, nblocks, n_chunks, stride_blocks):
     """ragged chunks (nb not a multiple of k) and padded strides, striped and per-chunk units, host and device-resident entry points"""
-    e = engine_with(LZGPU_BITSLICE=1, LZGPU_STRIPED=striped)
+    e = engine_with(LZGPU_BITSLICE=3, LZGPU_STRIPED=striped)
     goal = L.SliceType(text)
     data = rnd((n_chunks, stride_blocks * BLOCK), (hash(text) ^ nblocks) & 0xffff)
     parity, crc = e.encode_chunks(goal, data, chunk_len=nblocks * BLOCK)
@@ -99,7 +101,7 @@ def test_ragged_chunks_striped_and_per_chunk_units(oracle, striped, text, nblock
     e.close()
 
 
-@pytest.mark.parametrize("text", ["ec(8,4)", "ec(6,4)", "ec(4,4)", "ec(10,4)", "ec(12,4)", "ec(7,4)", "ec(20,4)"])
+@pytest.mark.parametrize("text", ["ec(8,4)", "ec(6,4)", "ec(4,4)", "ec(10,4)", "ec(12,4)", "ec(7,4)", "ec(20,4)", "ec(5,3)", "ec(6,3)", "ec(8,3)", "ec(4,3)", "ec(9,3)", "ec(31,3)"])
 def test_full_size_chunks_vs_reference(eng_bs, oracle, ref, text):
     """the size the numbers are quoted on: two full 64 MiB chunks per goal (the second one starts in the unit that straddles the
     chunk boundary), parity parts and all block CRCs bit-exact against the compiled reference (the restatement where it is absent)"""
@@ -114,35 +116,37 @@ def test_full_size_chunks_vs_reference(eng_bs, oracle, ref, text):
 
 
 @pytest.mark.parametrize("clen_blocks", [16, 64, 256, 597])
-def test_sweep_chunk_sizes_ec84(eng_bs, oracle, ref, clen_blocks):
-    """the other chunk sizes of the mixed sweep (1, 4, 16 and 37.31 MiB) for the four-parity goal of BASELINE configs[4]"""
-    goal = L.SliceType("ec(8,4)")
+@pytest.mark.parametrize("text", ["ec(8,4)", "ec(5,3)"])
+def test_sweep_chunk_sizes(eng_bs, oracle, ref, text, clen_blocks):
+    """the other chunk sizes of the mixed sweep (1, 4, 16 and 37.31 MiB) for the three- and four-parity goals of BASELINE configs[4]"""
+    goal = L.SliceType(text)
     n = 5
     data = np.stack([O.fill_chunk(oracle, clen_blocks * BLOCK, 778, c) for c in range(n)])
     parity, crc = eng_bs.encode_chunks(goal, data)
     checker = ref if ref is not None else oracle
     for c in (0, n // 2, n - 1):
         p_ref, c_ref = checker.encode_chunk(goal.kind, goal.k, goal.m, data[c])
-        assert (parity[c] == p_ref).all() and (crc[c] == c_ref).all(), (clen_blocks, c)
+        assert (parity[c] == p_ref).all() and (crc[c] == c_ref).all(), (text, clen_blocks, c)
 
 
-def test_both_routes_give_the_same_bytes_on_a_resident_batch(eng_bs, eng_bytes):
-    """a device-resident batch of 24 full chunks through both routes (no host copy of the 2.3 GiB of parity: compared by CRC of the
+@pytest.mark.parametrize("text", ["ec(8,4)", "ec(5,3)"])
+def test_both_routes_give_the_same_bytes_on_a_resident_batch(eng_bs, eng_bytes, text):
+    """a device-resident batch of 24 full chunks through both routes (no host copy of the parity: compared by CRC of the
     parity parts, which both routes produce, and by the parity bytes of three chunks)"""
-    goal = L.SliceType("ec(8,4)")
-    n, nb = 24, 1024
-    pb = nb // 8
-    n_crc = nb + 4 * pb
+    goal = L.SliceType(text)
+    n, nb, m = 24, 1024, goal.m
+    pb = -(-nb // goal.k)
+    n_crc = nb + m * pb
     outs = []
     for e in (eng_bs, eng_bytes):
         d_data = e.dev_alloc(n * nb * BLOCK)
-        d_par = e.dev_alloc(n * 4 * pb * BLOCK)
+        d_par = e.dev_alloc(n * m * pb * BLOCK)
         d_crc = e.dev_alloc(n * n_crc * 4)
         e.fill_chunks_dev(d_data, n, nb * BLOCK, nb * BLOCK, 99)
-        e.encode_chunks_dev(goal, n, nb * BLOCK, d_data, nb * BLOCK, d_par, 4 * pb * BLOCK, d_crc, n_crc)
+        e.encode_chunks_dev(goal, n, nb * BLOCK, d_data, nb * BLOCK, d_par, m * pb * BLOCK, d_crc, n_crc)
         e.sync()
         crc = e.download(d_crc, n * n_crc * 4, dtype=np.uint32).reshape(n, n_crc)
-        par = np.stack([e.download(d_par + c * 4 * pb * BLOCK, 4 * pb * BLOCK) for c in (0, 11, 23)])
+        par = np.stack([e.download(d_par + c * m * pb * BLOCK, m * pb * BLOCK) for c in (0, 11, 23)])
         outs.append((crc, par))
         for ptr in (d_data, d_par, d_crc):
             e.dev_free(ptr)

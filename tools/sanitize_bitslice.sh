@@ -1,4 +1,4 @@
-# compute-sanitizer memcheck over the bit-sliced four-parity-row encoder only (run under gpurun; the long case list is tools/sanitize.sh).
+# compute-sanitizer memcheck over the bit-sliced three- / four-parity-row encoders only (run under gpurun; the long case list is tools/sanitize.sh).
 mkdir -p gpurun_out
 cat > /tmp/san_bs.py <<'PY'
 import os, sys
@@ -8,10 +8,10 @@ import lizardfs_b200 as L
 from tests import _oracle as O
 o = O.load_oracle()
 # dedicated GF warps (csrc/bitslice.cuh): per-chunk units with a tail stripe, flat units, striped units; then the packed-byte route
-for bs, striped in (("1", "0"), ("1", "1"), ("0", "0")):
+for bs, striped in (("3", "0"), ("3", "1"), ("0", "0")):
     os.environ["LZGPU_BITSLICE"] = bs; os.environ["LZGPU_STRIPED"] = striped
     e = L.Engine(0)
-    for text, nblk, n in [("ec(8,4)", 19, 3), ("ec(8,4)", 16, 5), ("ec(5,4)", 11, 4), ("ec(12,4)", 25, 2)]:
+    for text, nblk, n in [("ec(8,4)", 19, 3), ("ec(8,4)", 16, 5), ("ec(5,4)", 11, 4), ("ec(12,4)", 25, 2), ("ec(5,3)", 11, 4), ("ec(8,3)", 16, 3), ("ec(31,3)", 63, 2)]:
         g = L.SliceType(text)
         data = np.stack([O.fill_chunk(o, nblk * 65536, 17, c) for c in range(n)])
         par, crc = e.encode_chunks(g, data)
@@ -19,7 +19,7 @@ for bs, striped in (("1", "0"), ("1", "1"), ("0", "0")):
             p_ref, c_ref = o.encode_chunk(g.kind, g.k, g.m, data[c])
             assert (par[c] == p_ref).all() and (crc[c] == c_ref).all(), (text, bs, striped)
     e.close()
-    print("four parity rows, bitslice", bs, "striped", striped, "OK")
+    print("three / four parity rows, bitslice", bs, "striped", striped, "OK")
 print("sanitizer case OK")
 PY
 for tool in ${TOOLS:-memcheck}; do
