@@ -85,6 +85,7 @@ struct FusedParams {
 	// SPLIT instantiations only (slice conversion, SliceRecoveryPlanner::BlockConverter fused into the encode pass): the data
 	// blocks are also stored part-major (data part j of chunk c at data_out[j] + c*part_out_stride, nullptr = not wanted), and
 	// the parity parts go to separate buffers par_out[r] + c*part_out_stride (nullptr = not wanted) instead of p.parity
+	uint32_t n_stages;               // bit-sliced instantiations: depth of the data stage ring
 	uint32_t skip_data_crc;          // later passes of a many-parity encode: the data-block CRCs were produced by the first pass
 	uint32_t crc_row_base;           // parity row r of this launch is parity part crc_row_base + r in the CRC array
 	uint8_t *data_out[32];
@@ -295,7 +296,8 @@ __device__ __forceinline__ uint32_t fold_finish(uint32_t (&win)[FW], const uint3
 template <int M, bool GENERIC, int KT, int GT, int FW, bool STRIPED = false, bool SPLIT = false, int W = fused_item_words(M, GENERIC)>
 __global__ void __launch_bounds__(fused_threads(M, GENERIC, W == 8), fused_ctas_per_sm(M, GENERIC, FW, W == 8))
 fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
-	constexpr int kNST = fused_nst(FW, M, GENERIC, W == 8), kNPST = fused_npst(FW, M, GENERIC);
+	constexpr int kNSTc = fused_nst(FW, M, GENERIC, W == 8), kNPST = fused_npst(FW, M, GENERIC);
+	const uint32_t kNST = (W == 8) ? p.n_stages : static_cast<uint32_t>(kNSTc);   // bit-sliced: as many stages as fit (host: FusedPlan::n_stages)
 	constexpr int NT = fused_threads(M, GENERIC, W == 8);
 	constexpr int PC = (M == 0) ? 0 : (GENERIC ? M : M - 1);  // parity parts whose CRC is computed from bytes
 	constexpr int P0 = GENERIC ? 0 : 1;                       // first such parity part
@@ -375,7 +377,7 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 	const uint32_t stripes_total = p.flat ? p.n_chunks * p.pb : p.pb;  // bound on the (global) stripe index
 
 	if (tid == 0) {
-		for (int s = 0; s < kNST; ++s) {
+		for (uint32_t s = 0; s < kNST; ++s) {
 			mbar_init(a_full + 8 * s, 1);
 			mbar_init(a_empty + 8 * s, n_stage_warps);
 		}

@@ -84,11 +84,18 @@ LZ_HD constexpr int fused_nst(int fw, int m, bool generic, bool bs = false) { re
 LZ_HD constexpr int fused_npst(int fw, int m, bool generic) { return fw == 64 ? LZ_NPST : 6; }
 LZ_HD constexpr int fused_smem_cap(int m, bool generic, int fw, bool bs = false) { return fused_ctas_per_sm(m, generic, fw, bs) == 1 ? 200 * 1024 : kSmemCap; }
 
-inline size_t fused_smem_bytes(uint32_t rows, uint32_t prows, int fw, int m, bool generic, bool bs = false) {
+inline size_t fused_smem_bytes_n(uint32_t rows, uint32_t prows, size_t nst, size_t npst) {
 	const size_t pstage = (static_cast<size_t>(prows) * kStepBytes + 1023) & ~size_t(1023);
-	const size_t nst = fused_nst(fw, m, generic, bs), npst = fused_npst(fw, m, generic);
 	return nst * rows * kStepBytes + npst * pstage + 520 + 8 * (2 * nst + 2 * npst);
 }
+inline size_t fused_smem_bytes(uint32_t rows, uint32_t prows, int fw, int m, bool generic, bool bs = false) {
+	return fused_smem_bytes_n(rows, prows, fused_nst(fw, m, generic, bs), fused_npst(fw, m, generic));
+}
+// The bit-sliced kernels take their stage count at run time: as many stages as fit (their G is capped at 8 by the 128 GF threads,
+// so narrow stripes leave shared memory for a deeper ring — more bytes in flight per SM)
+#ifndef LZ_BS_MAX_STAGES
+#define LZ_BS_MAX_STAGES 8
+#endif
 
 // Largest stripe group G such that data + parity-CRC rows fit the consumer threads, the data rows fit
 // one TMA box (<= 256 rows, a multiple of 8 for the 1024-byte stage alignment) and the stages fit shared memory.
@@ -115,7 +122,7 @@ inline uint32_t pick_group(uint32_t K, uint32_t PC, int max_smem_per_cta, int fw
 // mode 1 ("flat"): chunks are contiguous and made of whole stripes, the batch is one run of n_chunks*pb stripes in one
 // 2-D tensor; mode 2 ("striped"): the same run of global stripes for any nb / stride, one TMA box per stripe.
 struct FusedPlan {
-	uint32_t G = 0, pb = 0, mode = 0, units_per_chunk = 0, total_units = 0, threads = 0, rows = 0, prows = 0;
+	uint32_t G = 0, pb = 0, mode = 0, units_per_chunk = 0, total_units = 0, threads = 0, rows = 0, prows = 0, n_stages = 0;
 	size_t smem = 0;
 	bool ok = false;  // false: the fused kernel does not take this shape (generic kernels do)
 	bool bs = false;  // bit-sliced geometry (16 warps, four of them GF warps)
@@ -124,7 +131,7 @@ struct FusedPlan {
 // striped_policy: -1 automatic (striped when per-chunk units would leave more than 12 % of their stripe slots empty — measured,
 // profiles/sweep_r1.md: G boxes per step instead of one cost 2-10 % at 64 MiB and win up to 2.4x at 1-4 MiB), 0 never, 1 always
 inline FusedPlan fused_plan(int M, bool generic, uint32_t K, uint32_t n_chunks, uint32_t nb, size_t chunk_stride, int smem_cap, int fw,
-                            int striped_policy, bool bs = false) {
+                            int striped_policy, bool bs = false, int bs_max_stages = LZ_BS_MAX_STAGES) {
 	FusedPlan pl;
 	const uint32_t PC = M == 0 ? 0 : (generic ? M : M - 1);
 	const int mm = M;  // the instantiation's M (thread count, stage depth); a Cauchy generator is encoded in passes of <= 4 rows
@@ -155,7 +162,11 @@ inline FusedPlan fused_plan(int M, bool generic, uint32_t K, uint32_t n_chunks, 
 	pl.total_units = static_cast<uint32_t>(total);
 	pl.rows = G * K * 4;
 	pl.prows = G * PC * 4;
-	pl.smem = fused_smem_bytes(pl.rows, pl.prows, fw, mm, generic, bs);
+	pl.n_stages = static_cast<uint32_t>(fused_nst(fw, mm, generic, bs));
+	const size_t npst = fused_npst(fw, mm, generic);
+	if (bs)
+		while (static_cast<int>(pl.n_stages) < bs_max_stages && fused_smem_bytes_n(pl.rows, pl.prows, pl.n_stages + 1, npst) <= static_cast<size_t>(smem_cap)) ++pl.n_stages;
+	pl.smem = fused_smem_bytes_n(pl.rows, pl.prows, pl.n_stages, npst);
 	pl.ok = true;
 	return pl;
 }

@@ -1,35 +1,17 @@
 #!/bin/bash
-# round-2 run 28 (1 GPU): the final library of the round (bit-sliced four-parity-row encoder as measured in runs 26 and 27) — the encode tests of
-# the chunk suite on the default route, bench (every timed buffer checked against the reference in the run), pool tests
-# (lzgpu_pool_convert_chunks), smoke, ncu --set full of the ec(8,4) kernel
+# round-2 run 28 (1 GPU): run-time stage count of the bit-sliced kernels (as many stages as fit: narrow stripes get a deeper ring) —
+# parity tests, then A/B: 4 stages (run 27's geometry) / up to 8 in 200 KB / up to 8 in 224 KB
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_chunks.py -m gpu -x -q -k "golden or batch_vs_oracle or flat_units or ragged or every_goal or fuzz or many_parity or sweep_chunk_sizes" > gpurun_out/r28_pytest_chunks4.log 2>&1; tail -2 gpurun_out/r28_pytest_chunks4.log
-timeout 300 python bench.py > gpurun_out/r28_bench.json 2> gpurun_out/r28_bench.err; python - <<'PY'
-import json
-try:
-    d = json.loads(open("gpurun_out/r28_bench.json").read().strip().splitlines()[-1])
-    print("bench", round(d["value"]), "GiB/s frac", round(d["roofline"]["frac"], 3), "e2e", round(d["e2e"]["value"], 1))
-    for e in d.get("extra", []):
-        if "ec(8,4)" in e["name"] or "ec(5,3) 64" in e["name"]:
-            print(" ", e["name"], round(e["frac_of_measured_hbm"], 3), e["parity"][:40])
-except Exception as ex:
-    print("bench parse failed", ex)
-PY
-timeout 240 python -m pytest tests/test_pool.py -m gpu -x -q > gpurun_out/r28_pytest_pool.log 2>&1; tail -2 gpurun_out/r28_pytest_pool.log
-cat > /tmp/ncu_bs.py <<'PY'
-import sys
-sys.path.insert(0, '.')
-import lizardfs_b200 as L
-e = L.Engine(0)
-g = L.SliceType("ec(8,4)")
-n, nb, B = 32, 1024, 65536
-pb = nb // 8
-d = e.dev_alloc(n * nb * B); p = e.dev_alloc(n * 4 * pb * B); c = e.dev_alloc(n * (nb + 4 * pb) * 4)
-e.fill_chunks_dev(d, n, nb * B, nb * B, 5)
-for _ in range(2):
-    e.encode_chunks_dev(g, n, nb * B, d, nb * B, p, 4 * pb * B, c, nb + 4 * pb)
-e.sync()
-PY
-timeout 240 ncu --set full --clock-control none --import-source on -k regex:fused_stream_kernel -s 1 -c 1 -o gpurun_out/r28_ec84_bs -f python /tmp/ncu_bs.py > gpurun_out/r28_ncu.log 2>&1; tail -1 gpurun_out/r28_ncu.log
-timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke OK')" > gpurun_out/r28_smoke.log 2>&1; tail -1 gpurun_out/r28_smoke.log
+timeout 300 python -m pytest tests/test_gpu_bitslice.py -m gpu -x -q > gpurun_out/r28_pytest_bs.log 2>&1; tail -1 gpurun_out/r28_pytest_bs.log
+LZGPU_BS_SMEM_KB=224 timeout 300 python -m pytest tests/test_gpu_bitslice.py -m gpu -x -q -k "every_vandermonde or flat_units or ragged" > gpurun_out/r28_pytest_bs224.log 2>&1; tail -1 gpurun_out/r28_pytest_bs224.log
+GG='ec(5,3);ec(6,3);ec(4,3);ec(8,3);ec(9,3);ec(8,4);ec(6,4);ec(4,4);ec(10,4);ec(12,4);ec(7,4)'
+run() {  # label, env...
+  local label=$1; shift
+  env "$@" timeout 200 python tools/sweep.py --full-size-only --sections enc --goals "$GG" --bytes $((4<<30)) --out gpurun_out/r28_$label.md > /dev/null 2> gpurun_out/r28_$label.err
+  echo "== $label"; grep -h "^| ec(" gpurun_out/r28_$label.md | cut -c1-100
+}
+run st4 LZGPU_BS_STAGES=4
+run st8_200 LZGPU_BS_STAGES=8
+run st8_224 LZGPU_BS_STAGES=8 LZGPU_BS_SMEM_KB=224
+run st6_224 LZGPU_BS_STAGES=6 LZGPU_BS_SMEM_KB=224
