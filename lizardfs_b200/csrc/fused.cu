@@ -45,7 +45,7 @@ struct FusedState {
 	int direct_wide = -1;  // LZGPU_DIRECT_WIDE: item width of the DIRECT (Cauchy) degraded read, -1 by item count, 0 = 4 bytes, 1 = 8 / 16 bytes, -2 = route off
 	int bs_max_stages = LZ_BS_MAX_STAGES;  // LZGPU_BS_STAGES: deepest data stage ring of the bit-sliced kernels
 	int bs_smem_cap = 200 * 1024;          // LZGPU_BS_SMEM_KB: their shared memory budget (one CTA per SM)
-	int bitslice = LZ_BITSLICE_DEFAULT;  // LZGPU_BITSLICE: bit 0 = four, bit 1 = three Vandermonde parity rows on bit planes (W = 8 items, bitslice.cuh); 0 = packed-byte Horner
+	int bitslice = LZ_BITSLICE_DEFAULT;  // LZGPU_BITSLICE: Vandermonde parity rows on bit planes (W = 8 items, bitslice.cuh) — bit 0: four rows, bit 1: three rows with k >= 7, bit 2: three rows with any k; 0 = packed-byte Horner
 	int promo = 3;  // CU_TENSOR_MAP_L2_PROMOTION_L2_256B: +12% streaming bandwidth over 128B/none (profiles/probe_r1.md)
 };
 
@@ -295,8 +295,8 @@ static int launch_bs(lzgpu_ctx *ctx, const CUtensorMap &map, const FusedParams &
 	return LZGPU_OK;
 }
 // the constant-folded (M, K, G) of the bit-sliced route: G from pick_group(.., bs = true)
-#define LZ_BS_FOLDED_LIST(X) X(4, 8, 8) X(4, 10, 6) X(4, 12, 5) X(4, 6, 8) X(4, 4, 8) X(3, 5, 8) X(3, 6, 8) X(3, 8, 8) X(3, 4, 8)
-#define LZ_BS_FOLDED_STRIPED_LIST(X) X(4, 8, 8) X(3, 5, 8)
+#define LZ_BS_FOLDED_LIST(X) X(4, 8, 8) X(4, 10, 6) X(4, 12, 5) X(4, 6, 8) X(4, 4, 8) X(3, 8, 8) X(3, 9, 6) X(3, 10, 6) X(3, 12, 5)
+#define LZ_BS_FOLDED_STRIPED_LIST(X) X(4, 8, 8)
 static int set_all_bs_attrs() {
 	int rc;
 #define LZ_X(MM, KK, GG) if ((rc = set_bs_attr<MM, KK, GG>())) return rc;
@@ -338,7 +338,7 @@ static int fused_run(lzgpu_ctx *ctx, int M, bool generic, const uint8_t *coef_ro
 	// geometry first where it is switched on, the packed-byte one if a shape does not fit it
 	const int spol = split_out ? 0 : (striped_policy == -2 ? fs->striped : striped_policy);
 	FusedPlan pl;
-	if (!split_out && fw == 64 && fused_bitslice(M, generic, fs->bitslice))
+	if (!split_out && fw == 64 && fused_bitslice(M, generic, fs->bitslice, K))
 		pl = fused_plan(M, generic, K, n_chunks, nb, chunk_stride, std::min(fs->max_smem, fs->bs_smem_cap), fw, spol, true, fs->bs_max_stages);
 	if (!pl.ok) pl = fused_plan(M, generic, K, n_chunks, nb, chunk_stride, std::min(fs->max_smem, fw == 64 ? fused_smem_cap(M, generic, fw) : kSmemCap128), fw, spol);
 	if (!pl.ok || (reinterpret_cast<uintptr_t>(d_data) % 16)) return LZGPU_NOT_HANDLED;

@@ -51,14 +51,19 @@ constexpr int kSmemCap = 113 * 1024;                   // dynamic shared memory 
 #ifndef LZ_W4
 #define LZ_W4 2           // ec(8,4): 512 eight-byte items fill the 16 warps (0.43 -> 0.52 of the HBM peak, profiles/sweep_r2.md)
 #endif
-// Bit-sliced GF role (bitslice.cuh; round 2, run 26: ec(8,4) 0.52 -> 0.79, ec(6,4) 0.50 -> 0.71, ec(10,4) 0.42 -> 0.60 of the HBM peak):
-// three or four Vandermonde rows on ONE 16-warp CTA per SM whose last four warps only do the GF items (32-byte items on bit
-// planes) and whose first twelve own the CRC streams.  LZGPU_BITSLICE / LZ_BITSLICE_DEFAULT: bit 0 = four parity rows, bit 1 = three.
+// Bit-sliced GF role (bitslice.cuh; round 2, runs 26-28: ec(8,4) 0.52 -> 0.79, ec(6,4) 0.50 -> 0.71, ec(10,4) 0.42 -> 0.60, ec(8,3)
+// 0.57 -> 0.82, ec(31,3) 0.08 -> 0.23 of the HBM peak): three or four Vandermonde rows on ONE 16-warp CTA per SM whose last four
+// warps only do the GF items (32-byte items on bit planes) and whose first twelve own the CRC streams.
+// LZGPU_BITSLICE / LZ_BITSLICE_DEFAULT: bit 0 = four parity rows, bit 1 = three parity rows with k >= 7 (narrower stripes measured
+// 3-5 % slower than the two 8-warp CTAs of the packed-byte route: ec(5,3) 0.750 / 0.731, ec(6,3) 0.784 / 0.746, ec(4,3) 0.778 / 0.770),
+// bit 2 = three parity rows with any k (A/B).
 #ifndef LZ_BITSLICE_DEFAULT
 #define LZ_BITSLICE_DEFAULT 3
 #endif
 constexpr int kBsThreads = 512, kBsGfThreads = 128;
-LZ_HD constexpr bool fused_bitslice(int m, bool generic, int mask) { return !generic && ((m == 4 && (mask & 1)) || (m == 3 && (mask & 2))); }
+LZ_HD constexpr bool fused_bitslice(int m, bool generic, int mask, uint32_t k) {
+	return !generic && ((m == 4 && (mask & 1)) || (m == 3 && (((mask & 2) && k >= 7) || (mask & 4))));
+}
 LZ_HD constexpr int fused_threads(int m, bool generic, bool bs = false) { return bs ? kBsThreads : generic ? LZ_TGEN : m <= 2 ? LZ_T2 : m == 3 ? LZ_T3 : LZ_T4; }
 // packed words per GF item (4 = 16 bytes); narrower items = more, lighter items per step
 // (generic coefficients: chosen per launch by fused_generic_item_words — both widths are instantiated)
@@ -94,7 +99,7 @@ inline size_t fused_smem_bytes(uint32_t rows, uint32_t prows, int fw, int m, boo
 // The bit-sliced kernels take their stage count at run time: as many stages as fit (their G is capped at 8 by the 128 GF threads,
 // so narrow stripes leave shared memory for a deeper ring — more bytes in flight per SM)
 #ifndef LZ_BS_MAX_STAGES
-#define LZ_BS_MAX_STAGES 8
+#define LZ_BS_MAX_STAGES 4   // (run 28: 4 / 6 / 8 stages, 200 / 224 KB — within 1 % of each other for every goal; LZGPU_BS_STAGES, LZGPU_BS_SMEM_KB)
 #endif
 
 // Largest stripe group G such that data + parity-CRC rows fit the consumer threads, the data rows fit

@@ -1,7 +1,8 @@
 """GPU parity tests of the BIT-SLICED three- and four-parity-row encoders (fused_stream_kernel, W = 8 items, csrc/bitslice.cuh)
 against the oracle / the compiled reference: every Vandermonde ec(k,4) (k <= 20; larger k use Cauchy rows,
 reed_solomon.h:168-172) and ec(k,3) in all three unit modes (per-chunk, flat, striped), tail stripes, padded strides, full 64 MiB chunks — and, both ways round, that the
-packed-byte Horner route (LZGPU_BITSLICE=0) and the bit-plane route (LZGPU_BITSLICE=3) give the same bytes."""
+packed-byte Horner route (LZGPU_BITSLICE=0) and the bit-plane route (LZGPU_BITSLICE=7: also the three-row goals with k < 7, which
+the default routes to the packed-byte kernels) give the same bytes."""
 import os
 
 import numpy as np
@@ -29,7 +30,7 @@ def engine_with(**env):
 
 @pytest.fixture(scope="module")
 def eng_bs():
-    e = engine_with(LZGPU_BITSLICE=3)
+    e = engine_with(LZGPU_BITSLICE=7)
     yield e
     e.close()
 
@@ -77,7 +78,7 @@ def test_flat_units_many_small_chunks(eng_bs, oracle, text, nblocks, n_chunks):
                                                                   ("ec(8,4)", 1, 20, 1), ("ec(6,4)", 7, 6, 10), ("ec(5,3)", 11, 17, 11), ("ec(5,3)", 7, 9, 12), ("ec(31,3)", 40, 3, 40)])
 def test_ragged_chunks_striped_and_per_chunk_units(oracle, striped, text, nblocks, n_chunks, stride_blocks):
     """ragged chunks (nb not a multiple of k) and padded strides, striped and per-chunk units, host and device-resident entry points"""
-    e = engine_with(LZGPU_BITSLICE=3, LZGPU_STRIPED=striped)
+    e = engine_with(LZGPU_BITSLICE=7, LZGPU_STRIPED=striped)
     goal = L.SliceType(text)
     data = rnd((n_chunks, stride_blocks * BLOCK), (hash(text) ^ nblocks) & 0xffff)
     parity, crc = e.encode_chunks(goal, data, chunk_len=nblocks * BLOCK)

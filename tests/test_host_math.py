@@ -170,13 +170,17 @@ def test_encode_unit_geometry_decisions():
     """The launcher's host logic (csrc/fused_plan.h) without a GPU: stripes per unit, CTA size, and which unit mode a batch gets
     (per-chunk / flat / striped) for the BASELINE.json configurations and the ragged cases the sweep measures."""
     # stripes per unit: rows = G*k*4 <= 256 (one TMA box), data + parity-CRC rows <= threads, stages fit 113 KB (two CTAs per SM)
-    # or 200 KB (the one-CTA shape of four parity rows)
+    # or 200 KB (the one-CTA bit-sliced shape of four parity rows, and of three with k >= 7: 16 G <= 128 items on its four GF
+    # warps, the streams on the other twelve)
     for text, G, threads in [("ec(8,2)", 7, 256), ("xor2", 32, 256), ("xor3", 20, 256), ("ec(3,2)", 16, 256), ("ec(4,2)", 12, 256),
-                             ("ec(6,2)", 9, 256), ("ec(5,3)", 8, 256), ("ec(6,3)", 8, 256), ("ec(8,4)", 8, 512)]:
+                             ("ec(6,2)", 9, 256), ("ec(5,3)", 8, 256), ("ec(6,3)", 8, 256), ("ec(8,4)", 8, 512), ("ec(8,3)", 8, 512),
+                             ("ec(4,4)", 8, 512), ("ec(10,4)", 6, 512), ("ec(12,4)", 5, 512), ("ec(31,3)", 2, 512), ("ec(7,3)", 8, 512)]:
         p = _plan(text, 128, 1024)
         assert (p.fused, p.stripes_per_unit, p.threads_per_cta) == (1, G, threads), text
-        k = L.SliceType(text).k
-        assert p.stage_rows == G * k * 4 and p.stage_rows % 8 == 0 and p.smem_bytes <= (200 if threads == 512 else 113) * 1024
+        g = L.SliceType(text)
+        assert p.stage_rows == G * g.k * 4 and p.stage_rows % 8 == 0 and p.smem_bytes <= (200 if threads == 512 else 113) * 1024
+        if threads == 512:
+            assert 16 * G <= 128 and G * (g.k + g.m - 1) * 4 <= 384, text
     # configs[2]: 512 contiguous 64 MiB chunks of ec(8,2) are whole stripes -> one flat run of 512*128 stripes
     p = _plan("ec(8,2)", 512, 1024)
     assert (p.mode, p.units) == (1, -(-512 * 128 // 7))
@@ -203,24 +207,22 @@ def test_encode_unit_geometry_decisions():
 
 def test_encode_unit_geometry_invariants_for_every_goal():
     """every xor / ec(k, m <= 4) goal, several chunk lengths and batch sizes: the planned geometry always satisfies what the
-    kernel assumes (one TMA box <= 256 rows and a multiple of 8, data + parity-CRC rows fit the CTA, stages fit 113 KB — 200 KB
-    for the one-CTA shape of four Vandermonde parity rows —, the units cover every stripe exactly once)"""
+    kernel assumes (one TMA box <= 256 rows and a multiple of 8, data + parity-CRC rows fit the CTA's stream threads, stages fit
+    113 KB — 200 KB for the one-CTA bit-sliced shapes —, the units cover every stripe exactly once)"""
     goals = [f"xor{n}" for n in range(2, 10)] + [f"ec({k},{m})" for k in range(2, 33) for m in range(1, 5)]
     for text in goals:
         g = L.SliceType(text)
         cauchy = g.m == 4 and g.k > 20
         for n_chunks, nb, stride in [(1, 1024, None), (64, 1024, None), (500, 16, None), (33, 597, None), (7, 13, 16), (1000, 1, None), (3, g.k, None)]:
             p = _plan(text, n_chunks, nb, stride)
-            threads = 512 if (g.m == 4 and not cauchy) else 288 if cauchy else 256
-            pc0 = g.m if cauchy else g.m - 1
-            assert p.fused == 1, text   # every goal has a fused geometry; ec(31,3) through the nine-warp generic-coefficient CTA
-            if text == "ec(31,3)":
-                assert p.threads_per_cta == 288 and p.stripes_per_unit == 2
-                continue
+            bitsliced = not cauchy and (g.m == 4 or (g.m == 3 and g.k >= 7))
+            threads = 512 if bitsliced else 288 if cauchy else 256
+            assert p.fused == 1, text   # every goal has a fused geometry (ec(31,3): the bit-sliced 16-warp CTA holds its two-stripe unit)
             G, rows = p.stripes_per_unit, p.stage_rows
             pc = g.m if cauchy else g.m - 1
             assert G >= 1 and rows == G * g.k * 4 and rows <= 256 and rows % 8 == 0 and G * g.k <= 64
-            assert rows + G * pc * 4 <= p.threads_per_cta and p.threads_per_cta == threads
+            assert rows + G * pc * 4 <= p.threads_per_cta - (128 if bitsliced else 0) and p.threads_per_cta == threads
+            assert not bitsliced or 16 * G <= 128
             assert p.smem_bytes <= (200 if threads == 512 else 113) * 1024
             pb = -(-nb // g.k)
             if p.mode == 0:

@@ -8,7 +8,7 @@ import lizardfs_b200 as L
 from tests import _oracle as O
 o = O.load_oracle()
 # dedicated GF warps (csrc/bitslice.cuh): per-chunk units with a tail stripe, flat units, striped units; then the packed-byte route
-for bs, striped in (("3", "0"), ("3", "1"), ("0", "0")):
+for bs, striped in (("7", "0"), ("7", "1"), ("0", "0")):
     os.environ["LZGPU_BITSLICE"] = bs; os.environ["LZGPU_STRIPED"] = striped
     e = L.Engine(0)
     for text, nblk, n in [("ec(8,4)", 19, 3), ("ec(8,4)", 16, 5), ("ec(5,4)", 11, 4), ("ec(12,4)", 25, 2), ("ec(5,3)", 11, 4), ("ec(8,3)", 16, 3), ("ec(31,3)", 63, 2)]:
