@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 run 30 (1 GPU): bench of the final library (every timed buffer checked against the reference in the run), ncu --set full of
-# the bit-sliced ec(8,4) kernel, the encode sweep of the goals the bit-sliced routes touch, launch list of the bench command
+# the bit-sliced ec(8,4) kernel, the encode sweep of the goals the bit-sliced routes touch
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
 timeout 300 python bench.py > gpurun_out/r30_bench.json 2> gpurun_out/r30_bench.err; python - <<'PY'
@@ -31,4 +31,3 @@ PY
 timeout 240 ncu --set full --clock-control none --import-source on -k regex:fused_stream_kernel -s 1 -c 1 -o gpurun_out/r30_ec84_bs -f python /tmp/ncu_bs.py > gpurun_out/r30_ncu.log 2>&1; tail -1 gpurun_out/r30_ncu.log
 GG='xor2;xor3;ec(3,2);ec(5,3);ec(8,2);ec(8,4);ec(6,3);ec(8,3);ec(4,3);ec(9,3);ec(12,3);ec(31,3);ec(4,4);ec(6,4);ec(10,4);ec(12,4);ec(7,4);ec(16,4);ec(20,4)'
 timeout 300 python tools/sweep.py --full-size-only --sections enc --goals "$GG" --bytes $((8<<30)) --out gpurun_out/r30_sweep_enc.md > /dev/null 2> gpurun_out/r30_sweep_enc.err; grep -h "^| ec(\|^| xor" gpurun_out/r30_sweep_enc.md | cut -c1-100
-timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r30_launches.csv python bench.py --steps 2 --warmup 1 > gpurun_out/r30_launches_bench.log 2>&1; tail -1 gpurun_out/r30_launches_bench.log | cut -c1-200
