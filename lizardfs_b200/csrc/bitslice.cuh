@@ -22,6 +22,13 @@
 #endif
 #endif
 
+// the loops below must be unrolled in device code (register arrays, constant-bank masks); host compilers do not know the pragma
+#ifdef __CUDA_ARCH__
+#define LZ_UNROLL _Pragma("unroll")
+#else
+#define LZ_UNROLL
+#endif
+
 namespace lzd {
 
 // logical right shift; the device build may take it from the FMA pipe (IMAD.HI by 2^(32-s)) instead of the ALU pipe's funnel shift
@@ -113,6 +120,63 @@ LZ_HD inline void bs_horner(uint32_t (&a)[8], const uint32_t (&d)[8]) {
 	}
 }
 
+// a <- a * 2^R on planes, nothing added (a column the degraded read does not have)
+template <int R>
+LZ_HD inline void bs_mulpow(uint32_t (&a)[8]) {
+	static_assert(R >= 1 && R <= 3, "2, 4 or 8");
+	const uint32_t a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3], a4 = a[4], a5 = a[5], a6 = a[6], a7 = a[7];
+	if (R == 1) {
+		a[0] = a7; a[1] = a0; a[2] = a1 ^ a7; a[3] = a2 ^ a7; a[4] = a3 ^ a7; a[5] = a4; a[6] = a5; a[7] = a6;
+	} else if (R == 2) {
+		const uint32_t t67 = a6 ^ a7;
+		a[0] = a6; a[1] = a7; a[2] = a0 ^ a6; a[3] = a1 ^ t67; a[4] = a2 ^ t67; a[5] = a3 ^ a7; a[6] = a4; a[7] = a5;
+	} else {
+		const uint32_t t67 = a6 ^ a7, t56 = a5 ^ a6;
+		a[0] = a5; a[1] = a6; a[2] = a5 ^ a7; a[3] = a0 ^ t56; a[4] = a1 ^ t67 ^ a5; a[5] = a2 ^ t67; a[6] = a3 ^ a7; a[7] = a4;
+	}
+}
+
+// Multiplication by an arbitrary constant c on planes: the 8 x 8 bit matrix of x -> c x as 64 words that are all-ones or zero,
+// mask[8 i + b] = bit i of c * 2^b (bs_mask_set, host).  out_i (^)= XOR_b mask[8 i + b] & in_b — on the device each term is ONE LOP3
+// whose mask operand comes straight from the constant bank (the masks live in the kernel parameters): 64 instructions per
+// product of 32 bytes, against ~20 per 4 bytes for the bit-plane multiply on packed words (device_math.cuh gf_mac).
+LZ_HD inline void bs_mask_set(uint32_t (&mask)[64], uint32_t c) {
+	uint32_t v = c & 0xffu;
+LZ_UNROLL
+	for (int b = 0; b < 8; ++b) {
+LZ_UNROLL
+		for (int i = 0; i < 8; ++i) mask[8 * i + b] = ((v >> i) & 1u) ? 0xffffffffu : 0u;
+		v = ((v << 1) ^ ((v & 0x80u) ? 0x1du : 0u)) & 0xffu;
+	}
+}
+template <bool ACCUMULATE>
+LZ_HD inline void bs_mul_mask(uint32_t (&out)[8], const uint32_t (&in)[8], const uint32_t (&mask)[64]) {
+LZ_UNROLL
+	for (int i = 0; i < 8; ++i) {
+		uint32_t o = ACCUMULATE ? out[i] : 0u;
+LZ_UNROLL
+		for (int b = 0; b < 8; ++b) o ^= mask[8 * i + b] & in[b];
+		out[i] = o;
+	}
+}
+
+// Three unknowns a < b < c of a Vandermonde code with parity rows 1, 2^j, 4^j (the elimination of fused_recover_kernel, E = 3), on
+// planes: s0, s1, s2 are the syndromes, ta = A s0 and tb = A^2 s0 (A = 2^a) come from the caller (doublings or two more masked
+// multiplies); masks: alpha, beta, gamma, delta of the kernel comment.  Results: da, db, dc (planes).
+LZ_HD inline void bs_solve3(const uint32_t (&s0)[8], const uint32_t (&s1)[8], const uint32_t (&s2)[8], const uint32_t (&ta)[8], const uint32_t (&tb)[8],
+                            const uint32_t (&m_alpha)[64], const uint32_t (&m_beta)[64], const uint32_t (&m_gamma)[64], const uint32_t (&m_delta)[64],
+                            uint32_t (&da)[8], uint32_t (&db)[8], uint32_t (&dc)[8]) {
+	uint32_t t1[8], t2[8];
+LZ_UNROLL
+	for (int i = 0; i < 8; ++i) { t1[i] = ta[i] ^ s1[i]; t2[i] = tb[i] ^ s2[i]; }
+	bs_mul_mask<false>(dc, t2, m_alpha);
+	bs_mul_mask<true>(dc, t1, m_beta);
+	bs_mul_mask<false>(db, t1, m_gamma);
+	bs_mul_mask<true>(db, dc, m_delta);
+LZ_UNROLL
+	for (int i = 0; i < 8; ++i) da[i] = s0[i] ^ db[i] ^ dc[i];
+}
+
 // The GF role of one item of the M-row encoder (M = 3, 4), as the kernel runs it: column j = k-1 .. 0 of the stripe arrives as 8
 // packed words, row 0 accumulates on bytes, rows 1..M-1 on planes; bs_rows_finish turns the plane accumulators back into bytes.
 template <int M>
@@ -123,13 +187,16 @@ struct BsRows {
 };
 template <int M>
 LZ_HD inline void bs_rows_clear(BsRows<M> &s) {
+LZ_UNROLL
 	for (int i = 0; i < 8; ++i) {
 		s.p0[i] = 0;
+LZ_UNROLL
 		for (int r = 0; r < M - 1; ++r) s.p[r][i] = 0;
 	}
 }
 template <int M>
 LZ_HD inline void bs_rows_add_column(BsRows<M> &s, uint32_t (&v)[8]) {
+LZ_UNROLL
 	for (int i = 0; i < 8; ++i) s.p0[i] ^= v[i];
 	bs_transpose(v);
 	bs_horner<1>(s.p[0], v);
@@ -138,6 +205,7 @@ LZ_HD inline void bs_rows_add_column(BsRows<M> &s, uint32_t (&v)[8]) {
 }
 template <int M>
 LZ_HD inline void bs_rows_finish(BsRows<M> &s) {
+LZ_UNROLL
 	for (int r = 0; r < M - 1; ++r) bs_transpose(s.p[r]);
 }
 using BsRows4 = BsRows<4>;

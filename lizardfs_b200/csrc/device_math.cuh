@@ -10,6 +10,16 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+// Parity / image stores: written once, never read back by the kernel — no L1 allocation.  (-DLZ_STG_CS: the streaming cache
+// operator, -DLZ_STG_PLAIN: default write-back, for A/B runs.)
+#if defined(LZ_STG_CS)
+#define LZ_STG "st.global.cs"
+#elif defined(LZ_STG_PLAIN)
+#define LZ_STG "st.global"
+#else
+#define LZ_STG "st.global.L1::no_allocate"
+#endif
+
 namespace lzd {
 
 constexpr uint32_t kCrcPoly = 0xEDB88320u;
@@ -169,7 +179,7 @@ __device__ __forceinline__ uint4 ld_stream(const uint4 *p) {  // streaming 16-by
 }
 
 __device__ __forceinline__ void st_stream(uint4 *p, const uint4 &v) {
-	asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+	asm volatile(LZ_STG ".v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
 	             "r"(v.w)
 	             : "memory");
 }

@@ -13,6 +13,7 @@
 #include "engine_internal.h"
 #include "fused_kernel.cuh"
 #include "convert_kernel.cuh"
+#include "bs_recover_kernel.cuh"
 #include "host_math.h"
 
 using namespace lzd;
@@ -26,6 +27,10 @@ constexpr int kSmemCap128 = 226 * 1024;       // FW = 128 variant: one CTA per S
 constexpr int kRecoverSmemCap = 200 * 1024;  // recover kernel: one CTA per SM, 6 stages
 constexpr int kRecoverSmemCap2 = 100 * 1024; // two CTAs per SM, 3 stages (E <= 2)
 constexpr int kRecoverSmemCapBig = 208 * 1024; // one 16-warp CTA per SM (GEO 2)
+
+#ifndef LZ_BS_RECOVER_DEFAULT
+#define LZ_BS_RECOVER_DEFAULT 1
+#endif
 
 struct FusedState {
 	EncodeTiledFn encode_tiled = nullptr;
@@ -43,6 +48,7 @@ struct FusedState {
 	int cauchy_encode_off = 0;   // LZGPU_CAUCHY_FUSED=0: Cauchy-generator encodes on gf_dot_kernel + CRC passes instead of the fused kernel
 	int convert_off = 0;   // LZGPU_CONVERT_FUSED=0: slice conversion through the two-pass route (image, then SPLIT encode)
 	int direct_wide = -1;  // LZGPU_DIRECT_WIDE: item width of the DIRECT (Cauchy) degraded read, -1 by item count, 0 = 4 bytes, 1 = 8 / 16 bytes, -2 = route off
+	int bs_recover = LZ_BS_RECOVER_DEFAULT;  // LZGPU_BS_RECOVER: three lost data parts (parity rows 0, 1, 2) on bs_recover3_kernel (bit planes, dedicated GF warps); 0 = fused_recover_kernel
 	int bs_max_stages = LZ_BS_MAX_STAGES;  // LZGPU_BS_STAGES: deepest data stage ring of the bit-sliced kernels
 	int bs_smem_cap = 200 * 1024;          // LZGPU_BS_SMEM_KB: their shared memory budget (one CTA per SM)
 	int bitslice = LZ_BITSLICE_DEFAULT;  // LZGPU_BITSLICE: Vandermonde parity rows on bit planes (W = 8 items, bitslice.cuh) — bit 0: four rows, bit 1: three rows with k >= 7, bit 2: three rows with any k; 0 = packed-byte Horner
@@ -129,6 +135,9 @@ static int set_all_recover_attrs() {
 	CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<2, 4, 0, 1, 64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCapBig));
 	CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<2, 6, 0, 1, 64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCapBig));
 	CUDA_TRY(cudaFuncSetAttribute(fused_recover_kernel<3, 6, 0, 1, 64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCapBig));
+	CUDA_TRY(cudaFuncSetAttribute(bs_recover3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCapBig));
+	CUDA_TRY(cudaFuncSetAttribute(bs_recover3_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCapBig));
+	CUDA_TRY(cudaFuncSetAttribute(bs_recover3_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRecoverSmemCapBig));
 	// DIRECT (any generator; Cauchy codes): 16-warp geometry, 4-byte items
 	if ((rc = set_direct_attr<1>()) || (rc = set_direct_attr<2>()) || (rc = set_direct_attr<3>()) || (rc = set_direct_attr<4>())) return rc;
 	return LZGPU_OK;
@@ -151,6 +160,7 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if (const char *e = std::getenv("LZGPU_RECOVER_K3")) fs->recover_k3 = std::atoi(e) != 0;
 	if (const char *e = std::getenv("LZGPU_STRIPED")) fs->striped = std::atoi(e);  // 0 never, 1 whenever possible, unset = automatic
 	if (const char *e = std::getenv("LZGPU_BITSLICE")) fs->bitslice = std::atoi(e);
+	if (const char *e = std::getenv("LZGPU_BS_RECOVER")) fs->bs_recover = std::atoi(e);
 	if (const char *e = std::getenv("LZGPU_BS_STAGES")) fs->bs_max_stages = std::max(2, std::min(16, std::atoi(e)));
 	if (const char *e = std::getenv("LZGPU_BS_SMEM_KB")) fs->bs_smem_cap = std::max(64, std::min(226, std::atoi(e))) * 1024;
 	void *fn = nullptr;
@@ -679,8 +689,21 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 	int geo = fs->recover_geo >= 0 ? fs->recover_geo : (K != 8 && e >= 2) ? 2 : (two ? 1 : 0);
 	if (direct) geo = 2;
 	if (geo == 1 && e > 2) geo = 0;
+	// three lost data parts with parity rows 0, 1, 2 in use: bit planes + dedicated GF warps (bs_recover_kernel.cuh) — geometry: G even,
+	// 16 G <= 128 items on the four GF warps, the k G 4 input rows on the twelve stream warps, at least three stages
+	bool bs3 = !direct && e == 3 && fs->bs_recover && p.par_row[0] == 0 && p.par_row[1] == 1 && p.par_row[2] == 2;
 	uint32_t G = 0, n_stages = 0;
-	if (geo == 2) {
+	if (bs3) {
+		for (uint32_t g = 2; g <= 8; g += 2) {
+			const size_t stage = static_cast<size_t>(K) * g * 4 * kStepBytes;
+			if (K * g * 4 > static_cast<uint32_t>(kBsRecoverStreamThreads) || 3 * stage + 256 > static_cast<size_t>(kRecoverSmemCapBig)) break;
+			G = g;
+		}
+		if (G) n_stages = static_cast<uint32_t>(std::min<size_t>(6, (kRecoverSmemCapBig - 256) / (static_cast<size_t>(K) * G * 4 * kStepBytes)));
+		else bs3 = false;
+	}
+	if (bs3) {
+	} else if (geo == 2) {
 		// one 16-warp CTA: the largest G whose K*G*4 input rows fit 512 threads (one TMA box per part: G*4 <= 256 rows) and whose
 		// 32*G items fill whole rounds of the CTA (G a multiple of 16) where K allows, with at least three stages in 200 KiB
 		uint32_t best = 0, best16 = 0;
@@ -809,6 +832,28 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 	if (*verifying && !d_first_bad) return LZGPU_NOT_HANDLED;  // (callers that pass stored CRCs always pass the result word, initialised to ~0)
 	const size_t smem = static_cast<size_t>(n_stages) * K * G * 4 * kStepBytes + 16 * n_stages + 64;
 	const bool row0 = p.par_row[0] == 0, row01 = e >= 2 && consecutive;
+	if (bs3) {
+		// the six constants of the elimination (computed above for the packed-word kernel) as 8 x 8 bit matrices of all-ones / zero words
+		BsRecoverMasks mk;
+		auto pw2 = [](int t) { uint8_t v = 1; for (int i = 0; i < t; ++i) v = lz::gf_mul_host(v, 2); return v; };
+		const uint8_t A = pw2(p.erased_idx[0]), B = pw2(p.erased_idx[1]), C = pw2(p.erased_idx[2]);
+		const uint8_t pp = A ^ B, qq = A ^ C;
+		const uint8_t alpha = lz::gf_inv_host(lz::gf_mul_host(qq, pp ^ qq)), beta = lz::gf_mul_host(pp, alpha);
+		const uint8_t gamma = lz::gf_inv_host(pp), delta = lz::gf_mul_host(qq, gamma);
+		bs_mask_set(mk.m[0], alpha);
+		bs_mask_set(mk.m[1], beta);
+		bs_mask_set(mk.m[2], gamma);
+		bs_mask_set(mk.m[3], delta);
+		bs_mask_set(mk.m[4], A);
+		bs_mask_set(mk.m[5], lz::gf_mul_host(A, A));
+		const int grid = static_cast<int>(std::min<uint64_t>(p.total_units, static_cast<uint64_t>(ctx->sm_count)));
+		if (K == 5) bs_recover3_kernel<5><<<grid, kBsRecoverThreads, smem, st>>>(maps, p, mk);
+		else if (K == 8) bs_recover3_kernel<8><<<grid, kBsRecoverThreads, smem, st>>>(maps, p, mk);
+		else bs_recover3_kernel<0><<<grid, kBsRecoverThreads, smem, st>>>(maps, p, mk);
+		CUDA_TRY(cudaGetLastError());
+		ctx->stats.kernel_launches++;
+		return LZGPU_OK;
+	}
 	if (direct) {
 		// item width: 16-byte items leave most of the 16 warps without work when k is large (G small)
 		// run 8: the 8 / 16-byte items win on every shape (ec(32,4) four lost: 12.0 ms against 38.0 per 64 chunks); 4-byte items stay for A/B

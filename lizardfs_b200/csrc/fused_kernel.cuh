@@ -203,9 +203,9 @@ __device__ __forceinline__ void sts_item(uint32_t addr, const uint32_t (&v)[W]) 
 }
 template <int W>
 __device__ __forceinline__ void stg_item(void *p, const uint32_t (&v)[W]) {
-	if constexpr (W == 4) asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
-	else if constexpr (W == 2) asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v[0]), "r"(v[1]) : "memory");
-	else asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v[0]) : "memory");
+	if constexpr (W == 4) asm volatile(LZ_STG ".v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+	else if constexpr (W == 2) asm volatile(LZ_STG ".v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v[0]), "r"(v[1]) : "memory");
+	else asm volatile(LZ_STG ".u32 [%0], %1;" ::"l"(p), "r"(v[0]) : "memory");
 }
 
 // The 64-word polynomial's lags 17, 20, 23, 26 form an arithmetic progression.  Their four pulls are replaced by ONE pull from an

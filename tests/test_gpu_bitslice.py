@@ -153,3 +153,63 @@ def test_both_routes_give_the_same_bytes_on_a_resident_batch(eng_bs, eng_bytes, 
             e.dev_free(ptr)
     assert (outs[0][0] == outs[1][0]).all()
     assert (outs[0][1] == outs[1][1]).all()
+
+
+# ---- degraded read with three lost data parts on bit planes (csrc/bs_recover_kernel.cuh) ----------------------------------
+
+def _parts_and_crcs(eng, goal, data, nblocks):
+    parity, crc = eng.encode_chunks(goal, data)
+    n, k, m = data.shape[0], goal.k, goal.m
+    per = [O.split_parts(data[c], k)[0] for c in range(n)]
+    parts = [np.stack([per[c][j] for c in range(n)]) for j in range(k)] + [np.ascontiguousarray(parity[:, r]) for r in range(m)]
+    pb = parts[0].shape[1] // BLOCK
+    crcs = []
+    for j in range(k):
+        cj = np.full((n, pb), 0xD7978EEB, dtype=np.uint32)     # blocks a short last stripe does not have: zeros
+        mine = crc[:, j:nblocks:k]
+        cj[:, : mine.shape[1]] = mine
+        crcs.append(cj)
+    crcs += [np.ascontiguousarray(crc[:, nblocks + r * pb: nblocks + (r + 1) * pb]) for r in range(m)]
+    return parts, crcs
+
+
+@pytest.mark.parametrize("route", ["1", "0"])
+@pytest.mark.parametrize("text,nblocks,lost", [
+    ("ec(5,3)", 23, (0, 1, 4)), ("ec(5,3)", 25, (2, 3, 4)), ("ec(5,3)", 11, (0, 2, 3)), ("ec(6,3)", 30, (0, 2, 5)), ("ec(8,3)", 40, (1, 4, 6)),
+    ("ec(8,3)", 19, (4, 5, 7)), ("ec(8,4)", 33, (0, 2, 5)), ("ec(8,4)", 16, (5, 6, 7)), ("ec(12,3)", 50, (0, 5, 11)), ("ec(20,3)", 61, (3, 9, 19)),
+    ("ec(32,3)", 70, (0, 1, 31)), ("ec(3,3)", 10, (0, 1, 2)), ("ec(7,3)", 8, (1, 2, 6))])
+def test_recover_three_lost_data_parts(oracle, route, text, nblocks, lost):
+    """three data parts lost, parity rows 0, 1, 2 in use: the bit-plane kernel (route 1) and the packed-word kernel (route 0) must both
+    return the lost parts and the chunk image bit for bit — with verification of the stored CRCs and without, first unknown at a
+    position <= 3 (doublings) and above (two more masked products), ragged last stripes, and a corrupt input must be reported"""
+    e = engine_with(LZGPU_BS_RECOVER=route)
+    goal = L.SliceType(text)
+    k, m = goal.k, goal.m
+    data = rnd((3, nblocks * BLOCK), 4000 + nblocks)
+    parts, crcs = _parts_and_crcs(e, goal, data, nblocks)
+    # the reference reads the first k available parts: with three data parts lost these are the other data parts + parity 0, 1, 2
+    avail = [None if i in lost else parts[i] for i in range(k + m)]
+    want = [1 if i in lost else 0 for i in range(k + m)]
+    out, img = e.recover_chunks(goal, nblocks, avail, want=want, chunk_image=True)
+    for i in lost:
+        assert (out[i] == parts[i]).all(), (text, lost, i)
+    assert (img == data).all()
+    acrc = [None if i in lost else crcs[i] for i in range(k + m)]
+    out2, img2 = e.recover_chunks(goal, nblocks, avail, part_crc=acrc, want=want, chunk_image=True)
+    for i in lost:
+        assert (out2[i] == parts[i]).all(), (text, lost, i)
+    assert (img2 == data).all()
+    out3, _ = e.recover_chunks(goal, nblocks, avail, want=want)
+    for i in lost:
+        assert (out3[i] == parts[i]).all(), (text, lost, i)
+    rc, o_ref, _ = oracle.recover_chunk(goal.kind, k, m, [None if a is None else a[0] for a in avail], None, want, parts[0].shape[1] // BLOCK)
+    for i in lost:
+        assert (out[i][0] == o_ref[i]).all()
+    # one flipped byte in a used part: the verifying call must name chunk, part and block
+    victim = next(i for i in range(k + m) if i not in lost)
+    bad = [None if a is None else a.copy() for a in avail]
+    bad[victim][1, BLOCK + 5] ^= 0x40
+    with pytest.raises(L.ChunkCrcError) as ei:
+        e.recover_chunks(goal, nblocks, bad, part_crc=acrc, want=want, chunk_image=True)
+    assert ei.value.where == (1, victim, 1)
+    e.close()
