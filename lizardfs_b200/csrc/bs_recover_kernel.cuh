@@ -8,8 +8,9 @@
 // On bit planes (bitslice.cuh) a product with a constant is 64 LOP3 for 32 bytes, each taking its all-ones / zero mask straight
 // from the constant bank (the masks of the six constants of the elimination are kernel parameters), the syndromes are Horner steps
 // of 8-9 LOP3 per column and 32 bytes, and a column the read does not have costs 3-5 XORs.  Geometry as in the bit-sliced encoder:
-// one 16-warp CTA per SM, the last four warps take the 16 G <= 128 items of a step (32 bytes of every input at one position of a
-// stripe), the first twelve own one input row each and checksum it; no thread holds both plane accumulators and a CRC window.
+// one 16-warp CTA per SM, the last ceil(16 G / 32) warps take the 16 G items of a step (32 bytes of every input at one position of
+// a stripe), the warps before them own one input row each and checksum it (none when the call does not verify); no thread holds
+// both plane accumulators and a CRC window.
 #pragma once
 #include "bitslice.cuh"
 #include "fused_kernel.cuh"
@@ -20,7 +21,7 @@ struct BsRecoverMasks {
 	uint32_t m[6][64];   // alpha, beta, gamma, delta of the three-unknown elimination (fused_recover_kernel, E = 3); A = 2^a, A^2
 };
 
-constexpr int kBsRecoverThreads = 512, kBsRecoverGfWarp0 = 12, kBsRecoverStreamThreads = 384;
+constexpr int kBsRecoverThreads = 512;
 
 template <int KT>
 __global__ void __launch_bounds__(kBsRecoverThreads, 1)
@@ -63,7 +64,9 @@ bs_recover3_kernel(const __grid_constant__ TmapArray tmaps, const __grid_constan
 			for (uint32_t g0 = 0; g0 < n_stages; ++g0) issue_load(blockIdx.x / p.units_per_chunk, blockIdx.x % p.units_per_chunk, g0, g0);
 	}
 	__syncthreads();
-	const bool is_gf = cw >= kBsRecoverGfWarp0 && cw - kBsRecoverGfWarp0 < n_gf_warps;
+	// the LAST n_gf_warps warps take the items; the host's geometry keeps the stream warps (the first n_stream_warps) off them
+	const uint32_t gf_warp0 = kBsRecoverThreads / 32 - n_gf_warps;
+	const bool is_gf = cw >= gf_warp0;
 	if (!is_gf && cw >= n_stream_warps) return;
 
 	// the stage is released by every warp after its last read; the releaser that completes the phase refills it
@@ -78,7 +81,7 @@ bs_recover3_kernel(const __grid_constant__ TmapArray tmaps, const __grid_constan
 
 	if (is_gf) {
 		// ===================== GF warps: syndromes, elimination, scatter =====================
-		const uint32_t item = tid - 32 * kBsRecoverGfWarp0;
+		const uint32_t item = tid - 32 * gf_warp0;
 		const bool has_item = item < n_items;
 		const uint32_t col = item & 7, h = (item >> 3) & 1, g = item >> 4;
 		// row g*4 + h (and + 2) of every slot region; region bases are multiples of 8 rows, so the swizzle is that of the row alone

@@ -23,9 +23,8 @@
 //   GF role, bit-sliced (W = 8, three or four parity rows): item (stripe g, quarter pair h, 16-byte column c) = the 16 bytes at column c
 //              of quarters h and h + 2 of every data block of the stripe; rows 1..3 are Horner-evaluated on BIT PLANES
 //              (bitslice.cuh: multiplying 32 bytes by 2^r is a register renaming + a few XORs), row 0 on bytes.  A step has only
-//              16 G <= 128 such items: the LAST four warps (one per scheduler; the arbiter prefers the highest warp slot, so the
-//              warps every stream waits for issue first) are GF warps in a loop of their own and carry no stream — the 32 plane
-//              accumulators and the 64-word CRC window never live in the same thread.
+//              16 G such items: the LAST ceil(16 G / 32) warps are GF warps in a loop of their own and carry no stream — the 32
+//              plane accumulators and the 64-word CRC window never live in the same thread.
 //
 // CRC without tables or carry-less multiply
 //   CRC is GF(2)-linear, so the kernel computes lin(M) = M(x)*x^32 mod P and the host constant
@@ -321,16 +320,12 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 	constexpr uint32_t CPI = 32 / W;                               // items per 128-byte row step (columns of 4*W bytes)
 	const uint32_t n_items = 4 * CPI * G * (M > 0 ? 1 : 0);
 	const uint32_t n_gf_warps = (min(n_items, (uint32_t)NT) + 31) / 32;
-	// (bit-sliced: the last four warps are the GF warps; the host keeps the streams off them.  -DLZ_BS_GF_FIRST puts them first
-	// instead, for A/B runs of the arbiter's preference)
-#ifdef LZ_BS_GF_FIRST
-	constexpr uint32_t kBsGfWarps = BS ? 4 : 0, kBsGfWarp0 = 0, kBsStreamWarp0 = kBsGfWarps;
-#else
-	constexpr uint32_t kBsGfWarps = BS ? 4 : 0, kBsGfWarp0 = NT / 32 - kBsGfWarps, kBsStreamWarp0 = 0;
-#endif
-	const uint32_t first_pwarp = kBsStreamWarp0 + ROWS / 32, last_pwarp = PROWS ? kBsStreamWarp0 + (ROWS + PROWS - 1) / 32 : 0;
+	// (bit-sliced: the LAST n_gf_warps warps are the GF warps — as many as the 16 G items of a step fill; the host's plan keeps the
+	// streams on the warps before them: ceil(16 G / 32) + ceil((ROWS + PROWS) / 32) <= 16)
+	const uint32_t bs_gf_warps = BS ? n_gf_warps : 0, bs_gf_warp0 = NT / 32 - bs_gf_warps;
+	const uint32_t first_pwarp = ROWS / 32, last_pwarp = PROWS ? (ROWS + PROWS - 1) / 32 : 0;
 	// warps that read the TMA data stages (data streams or GF items); pure parity-CRC warps do not gate the refill
-	const uint32_t n_stage_warps = BS ? kBsGfWarps + (ROWS + 31) / 32 : max((ROWS + 31) / 32, n_gf_warps);
+	const uint32_t n_stage_warps = BS ? bs_gf_warps + (ROWS + 31) / 32 : max((ROWS + 31) / 32, n_gf_warps);
 
 	const uint32_t my_units = blockIdx.x < p.total_units ? (p.total_units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 	const uint32_t total_steps = my_units * kStepsPerUnit;
@@ -396,7 +391,7 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 
 	// ===================== role assignment =====================
 	const uint32_t cw = warp;                                 // consumer warp index 0..8
-	const uint32_t vt = tid - 32 * kBsStreamWarp0;            // stream index of this thread (= tid but for the LZ_BS_GF_FIRST experiment)
+	const uint32_t vt = tid;                                  // consumer thread index 0..287
 	const bool is_data_row = vt < ROWS;
 	const bool is_parity_row = vt >= ROWS && vt < ROWS + PROWS;
 	const bool has_stream = is_data_row || is_parity_row;
@@ -407,15 +402,15 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 	const uint32_t row_stride = is_data_row ? stage_bytes : pstage_bytes;
 	const bool warp_has_items = !BS && cw < n_gf_warps;        // (bit-sliced: the GF warps have left for their own loop by then)
 	const bool warp_has_prow = PROWS && cw >= first_pwarp && cw <= last_pwarp;
-	const bool warp_reads_stage = BS ? cw - kBsStreamWarp0 < (ROWS + 31) / 32 : cw < n_stage_warps;
+	const bool warp_reads_stage = BS ? cw < (ROWS + 31) / 32 : cw < n_stage_warps;
 
 	if constexpr (BS) {
 		// ===================== bit-sliced: the GF warps' own loop =====================
 		// Same barrier protocol as below (wait `full`, wait for the parity ring slot, fill it, release the stage — the last releaser
 		// refills), but in a loop of their own so that the plane accumulators never share a live range with the CRC window.
-		if (cw - kBsGfWarp0 < kBsGfWarps) {
+		if (cw >= bs_gf_warp0) {
 			uint32_t it = 0, st = 0, ph = 0, pst = 0, pph = 0;
-			const uint32_t item = tid - 32 * kBsGfWarp0;
+			const uint32_t item = tid - 32 * bs_gf_warp0;
 			const bool has_item = item < n_items;
 			const uint32_t col = item & 7, h = (item >> 3) & 1, g = item >> 4;
 			// rows (g*K + j)*4 + h and + 2: their swizzles (row & 7) differ in bit 1 only, and alternate in bit 2 with j
@@ -436,7 +431,7 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 					const uint32_t stage = sbase + st * stage_bytes;
 					const uint32_t pstage = pstage0 + pst * pstage_bytes;
 					mbar_wait(a_full + 8 * st, ph);
-					if (cw - kBsGfWarp0 < n_gf_warps && !LZ_PROBE(2)) {
+					if (!LZ_PROBE(2)) {
 						mbar_wait(a_pempty + 8 * pst, pph ^ 1);
 						if (has_item) {
 							BsRows<BS ? M : 4> rows4;
@@ -650,7 +645,7 @@ fused_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams 
 		}
 		if (M > 0 && !GENERIC) {
 			// CRC of parity row 0 (plain XOR of the stripe): xor of the data blocks' linear CRCs
-			asm volatile("bar.sync 1, %0;" ::"r"(NT - 32 * static_cast<int>(kBsGfWarps)) : "memory");   // (the stream warps: the bit-sliced GF warps are not here)
+			asm volatile("bar.sync 1, %0;" ::"r"(NT - 32 * static_cast<int>(bs_gf_warps)) : "memory");   // (the stream warps: the bit-sliced GF warps are not here)
 			if (vt < G) {
 				uint32_t x = 0;
 				for (uint32_t j = 0; j < K; ++j) {

@@ -60,7 +60,7 @@ constexpr int kSmemCap = 113 * 1024;                   // dynamic shared memory 
 #ifndef LZ_BITSLICE_DEFAULT
 #define LZ_BITSLICE_DEFAULT 3
 #endif
-constexpr int kBsThreads = 512, kBsGfThreads = 128;
+constexpr int kBsThreads = 512;
 LZ_HD constexpr bool fused_bitslice(int m, bool generic, int mask, uint32_t k) {
 	return !generic && ((m == 4 && (mask & 1)) || (m == 3 && (((mask & 2) && k >= 7) || (mask & 4))));
 }
@@ -107,15 +107,20 @@ inline size_t fused_smem_bytes(uint32_t rows, uint32_t prows, int fw, int m, boo
 #ifndef LZ_GCAP
 #define LZ_GCAP 1         // on the one-CTA shapes never plan more GF items per step than the CTA has threads (ec(4,4): G = 16 would
 #endif                    // give every thread two items and leave half the warps without a stream: 0.35 -> 0.38 with G = 8)
-// (bit-sliced: 16 items of 32 bytes per stripe and step, all of them on the four GF warps; the streams on the other twelve)
-inline uint32_t pick_group(uint32_t K, uint32_t PC, int max_smem_per_cta, int fw, uint32_t threads, int m, bool generic, bool bs = false) {
+// (bit-sliced: 16 items of 32 bytes per stripe and step on the last ceil(16 g / 32) warps — at most bs_max_gf_warps of them —, the
+// streams on the warps before them)
+#ifndef LZ_BS_MAX_GF_WARPS
+#define LZ_BS_MAX_GF_WARPS 8
+#endif
+inline uint32_t pick_group(uint32_t K, uint32_t PC, int max_smem_per_cta, int fw, uint32_t threads, int m, bool generic, bool bs = false,
+                           int bs_max_gf_warps = LZ_BS_MAX_GF_WARPS) {
 	uint32_t best = 0;
 	const uint32_t items_per_stripe = bs ? 16u : 128u / static_cast<uint32_t>(fused_item_words(m, generic));
-	const uint32_t item_threads = bs ? static_cast<uint32_t>(kBsGfThreads) : threads, stream_threads = bs ? threads - kBsGfThreads : threads;
 	for (uint32_t g = 1; g <= 64; ++g) {
-		if ((bs || (LZ_GCAP && (threads > 288 || m >= 3) && m > 0 && best)) && g * items_per_stripe > item_threads) break;
+		const uint32_t gf_warps = bs ? (g * items_per_stripe + 31) / 32 : 0;
+		if (bs ? gf_warps > static_cast<uint32_t>(bs_max_gf_warps) : (LZ_GCAP && (threads > 288 || m >= 3) && m > 0 && best && g * items_per_stripe > threads)) break;
 		const uint32_t rows = g * K * 4, prows = g * PC * 4;
-		if (rows > kMaxRows || rows + prows > stream_threads || prows > kMaxParityRows || g * K > 64) break;
+		if (rows > kMaxRows || rows + prows > threads - 32 * gf_warps || prows > kMaxParityRows || g * K > 64) break;
 		if (rows % 8) continue;
 		if (fused_smem_bytes(rows, prows, fw, m, generic, bs) > static_cast<size_t>(max_smem_per_cta)) break;
 		best = g;
@@ -136,13 +141,13 @@ struct FusedPlan {
 // striped_policy: -1 automatic (striped when per-chunk units would leave more than 12 % of their stripe slots empty — measured,
 // profiles/sweep_r1.md: G boxes per step instead of one cost 2-10 % at 64 MiB and win up to 2.4x at 1-4 MiB), 0 never, 1 always
 inline FusedPlan fused_plan(int M, bool generic, uint32_t K, uint32_t n_chunks, uint32_t nb, size_t chunk_stride, int smem_cap, int fw,
-                            int striped_policy, bool bs = false, int bs_max_stages = LZ_BS_MAX_STAGES) {
+                            int striped_policy, bool bs = false, int bs_max_stages = LZ_BS_MAX_STAGES, int bs_max_gf_warps = LZ_BS_MAX_GF_WARPS) {
 	FusedPlan pl;
 	const uint32_t PC = M == 0 ? 0 : (generic ? M : M - 1);
 	const int mm = M;  // the instantiation's M (thread count, stage depth); a Cauchy generator is encoded in passes of <= 4 rows
 	pl.threads = static_cast<uint32_t>(fused_threads(mm, generic, bs));
 	pl.bs = bs;
-	pl.G = pick_group(K, PC, smem_cap, fw, pl.threads, mm, generic, bs);
+	pl.G = pick_group(K, PC, smem_cap, fw, pl.threads, mm, generic, bs, bs_max_gf_warps);
 	if (pl.G == 0 || (chunk_stride % 16)) return pl;
 	const uint32_t G = pl.G;
 	pl.pb = (nb + K - 1) / K;
