@@ -49,7 +49,8 @@ struct FusedState {
 	int convert_off = 0;   // LZGPU_CONVERT_FUSED=0: slice conversion through the two-pass route (image, then SPLIT encode)
 	int direct_wide = -1;  // LZGPU_DIRECT_WIDE: item width of the DIRECT (Cauchy) degraded read, -1 by item count, 0 = 4 bytes, 1 = 8 / 16 bytes, -2 = route off
 	int bs_recover = LZ_BS_RECOVER_DEFAULT;  // LZGPU_BS_RECOVER: three lost data parts (parity rows 0, 1, 2) on bs_recover3_kernel (bit planes, dedicated GF warps); 0 = fused_recover_kernel
-	int bs_max_gf_warps = LZ_BS_MAX_GF_WARPS;  // LZGPU_BS_GFW: most GF warps of a bit-sliced CTA (4 = the geometry of runs 26-32)
+	int bs_max_gf_warps = LZ_BS_MAX_GF_WARPS;  // LZGPU_BS_GFW: most GF warps of a bit-sliced encoder CTA (default 4, fused_plan.h)
+	int bs_recover_gf_warps = 8;               // LZGPU_BS_RECOVER_GFW: most GF warps of bs_recover3_kernel (its GF role is latency bound: more warps pay)
 	int bs_max_stages = LZ_BS_MAX_STAGES;  // LZGPU_BS_STAGES: deepest data stage ring of the bit-sliced kernels
 	int bs_smem_cap = 200 * 1024;          // LZGPU_BS_SMEM_KB: their shared memory budget (one CTA per SM)
 	int bitslice = LZ_BITSLICE_DEFAULT;  // LZGPU_BITSLICE: Vandermonde parity rows on bit planes (W = 8 items, bitslice.cuh) — bit 0: four rows, bit 1: three rows with k >= 7, bit 2: three rows with any k; 0 = packed-byte Horner
@@ -163,6 +164,7 @@ int lz_fused_init(lzgpu_ctx *ctx) {
 	if (const char *e = std::getenv("LZGPU_BITSLICE")) fs->bitslice = std::atoi(e);
 	if (const char *e = std::getenv("LZGPU_BS_RECOVER")) fs->bs_recover = std::atoi(e);
 	if (const char *e = std::getenv("LZGPU_BS_GFW")) fs->bs_max_gf_warps = std::max(1, std::min(12, std::atoi(e)));
+	if (const char *e = std::getenv("LZGPU_BS_RECOVER_GFW")) fs->bs_recover_gf_warps = std::max(1, std::min(16, std::atoi(e)));
 	if (const char *e = std::getenv("LZGPU_BS_STAGES")) fs->bs_max_stages = std::max(2, std::min(16, std::atoi(e)));
 	if (const char *e = std::getenv("LZGPU_BS_SMEM_KB")) fs->bs_smem_cap = std::max(64, std::min(226, std::atoi(e))) * 1024;
 	void *fn = nullptr;
@@ -307,7 +309,7 @@ static int launch_bs(lzgpu_ctx *ctx, const CUtensorMap &map, const FusedParams &
 	return LZGPU_OK;
 }
 // the constant-folded (M, K, G) of the bit-sliced route: G from pick_group(.., bs = true)
-#define LZ_BS_FOLDED_LIST(X) X(4, 8, 8) X(4, 10, 6) X(4, 12, 5) X(4, 6, 9) X(4, 4, 10) X(3, 8, 8) X(3, 9, 6) X(3, 10, 6) X(3, 12, 5) X(3, 5, 10) X(3, 6, 10) X(3, 4, 12)
+#define LZ_BS_FOLDED_LIST(X) X(4, 8, 8) X(4, 10, 6) X(4, 12, 5) X(4, 6, 8) X(4, 4, 8) X(3, 8, 8) X(3, 9, 6) X(3, 10, 6) X(3, 12, 5)
 #define LZ_BS_FOLDED_STRIPED_LIST(X) X(4, 8, 8)
 static int set_all_bs_attrs() {
 	int rc;
@@ -697,14 +699,21 @@ int lz_fused_recover(lzgpu_ctx *ctx, const lzgpu_goal *goal, uint32_t n_chunks, 
 	bool bs3 = !direct && e == 3 && fs->bs_recover && p.par_row[0] == 0 && p.par_row[1] == 1 && p.par_row[2] == 2;
 	uint32_t G = 0, n_stages = 0;
 	if (bs3) {
+		// Run 33 (fraction of the HBM peak, at most four / at most eight GF warps): rebuild only — no stream warps, G = 16, eight GF warps —
+		// ec(5,3) 0.440 / 0.682, ec(6,3) 0.388 / 0.628, ec(8,3) 0.452 / 0.648; with verification and image ec(5,3) 0.589 / 0.722 (seven GF
+		// warps), ec(6,3) 0.570 / 0.640 (six), but ec(8,3) 0.689 / 0.658 (five: one scheduler gets two of them).  So: the largest G, unless
+		// it only buys a fifth GF warp.
 		bool any_crc = false;
 		for (int a = 0; a < K; ++a) any_crc |= d_part_crc && d_part_crc[used[a]];
+		uint32_t g4 = 0;
 		for (uint32_t g = 2; g <= 64; g += 2) {
 			const size_t stage = static_cast<size_t>(K) * g * 4 * kStepBytes;
 			const uint32_t gf_warps = (16 * g + 31) / 32, stream_warps = any_crc ? (K * g * 4 + 31) / 32 : 0;
-			if (gf_warps > static_cast<uint32_t>(fs->bs_max_gf_warps) || gf_warps + stream_warps > kBsRecoverThreads / 32 || 3 * stage + 256 > static_cast<size_t>(kRecoverSmemCapBig)) break;
+			if (gf_warps > static_cast<uint32_t>(fs->bs_recover_gf_warps) || gf_warps + stream_warps > kBsRecoverThreads / 32 || 3 * stage + 256 > static_cast<size_t>(kRecoverSmemCapBig)) break;
 			G = g;
+			if (gf_warps <= 4) g4 = g;
 		}
+		if (G && g4 && (16 * G + 31) / 32 == 5) G = g4;
 		if (G) n_stages = static_cast<uint32_t>(std::min<size_t>(6, (kRecoverSmemCapBig - 256) / (static_cast<size_t>(K) * G * 4 * kStepBytes)));
 		else bs3 = false;
 	}

@@ -108,9 +108,11 @@ inline size_t fused_smem_bytes(uint32_t rows, uint32_t prows, int fw, int m, boo
 #define LZ_GCAP 1         // on the one-CTA shapes never plan more GF items per step than the CTA has threads (ec(4,4): G = 16 would
 #endif                    // give every thread two items and leave half the warps without a stream: 0.35 -> 0.38 with G = 8)
 // (bit-sliced: 16 items of 32 bytes per stripe and step on the last ceil(16 g / 32) warps — at most bs_max_gf_warps of them —, the
-// streams on the warps before them)
+// streams on the warps before them.  Run 33: the encoders are ALU bound, a fifth or sixth GF warp only unbalances the four
+// schedulers — ec(4,4) G = 10 / five GF warps 0.66 against G = 8 / four 0.77, ec(6,4) 0.60 against 0.71 — so four is the default;
+// LZGPU_BS_GFW raises it for A/B runs.)
 #ifndef LZ_BS_MAX_GF_WARPS
-#define LZ_BS_MAX_GF_WARPS 8
+#define LZ_BS_MAX_GF_WARPS 4
 #endif
 inline uint32_t pick_group(uint32_t K, uint32_t PC, int max_smem_per_cta, int fw, uint32_t threads, int m, bool generic, bool bs = false,
                            int bs_max_gf_warps = LZ_BS_MAX_GF_WARPS) {

@@ -171,17 +171,17 @@ def test_encode_unit_geometry_decisions():
     (per-chunk / flat / striped) for the BASELINE.json configurations and the ragged cases the sweep measures."""
     # stripes per unit: rows = G*k*4 <= 256 (one TMA box), data + parity-CRC rows <= threads, stages fit 113 KB (two CTAs per SM)
     # or 200 KB (the one-CTA bit-sliced shape of four parity rows, and of three with k >= 7: the 16 G items of a step on its last
-    # ceil(16 G / 32) <= 8 warps, the streams on the warps before them)
+    # ceil(16 G / 32) <= 4 warps, the streams on the warps before them)
     for text, G, threads in [("ec(8,2)", 7, 256), ("xor2", 32, 256), ("xor3", 20, 256), ("ec(3,2)", 16, 256), ("ec(4,2)", 12, 256),
                              ("ec(6,2)", 9, 256), ("ec(5,3)", 8, 256), ("ec(6,3)", 8, 256), ("ec(8,4)", 8, 512), ("ec(8,3)", 8, 512),
-                             ("ec(4,4)", 10, 512), ("ec(6,4)", 9, 512), ("ec(10,4)", 6, 512), ("ec(12,4)", 5, 512), ("ec(31,3)", 2, 512), ("ec(7,3)", 8, 512)]:
+                             ("ec(4,4)", 8, 512), ("ec(6,4)", 8, 512), ("ec(10,4)", 6, 512), ("ec(12,4)", 5, 512), ("ec(31,3)", 2, 512), ("ec(7,3)", 8, 512)]:
         p = _plan(text, 128, 1024)
         assert (p.fused, p.stripes_per_unit, p.threads_per_cta) == (1, G, threads), text
         g = L.SliceType(text)
         assert p.stage_rows == G * g.k * 4 and p.stage_rows % 8 == 0 and p.smem_bytes <= (200 if threads == 512 else 113) * 1024
         if threads == 512:
             gf_warps, stream_warps = -(-16 * G // 32), -(-G * (g.k + g.m - 1) * 4 // 32)
-            assert gf_warps <= 8 and gf_warps + stream_warps <= 16, text
+            assert gf_warps <= 4 and gf_warps + stream_warps <= 16, text
     # configs[2]: 512 contiguous 64 MiB chunks of ec(8,2) are whole stripes -> one flat run of 512*128 stripes
     p = _plan("ec(8,2)", 512, 1024)
     assert (p.mode, p.units) == (1, -(-512 * 128 // 7))
@@ -223,7 +223,7 @@ def test_encode_unit_geometry_invariants_for_every_goal():
             pc = g.m if cauchy else g.m - 1
             assert G >= 1 and rows == G * g.k * 4 and rows <= 256 and rows % 8 == 0 and G * g.k <= 64
             gf_warps = -(-16 * G // 32) if bitsliced else 0
-            assert rows + G * pc * 4 <= p.threads_per_cta - 32 * gf_warps and p.threads_per_cta == threads and gf_warps <= 8
+            assert rows + G * pc * 4 <= p.threads_per_cta - 32 * gf_warps and p.threads_per_cta == threads and gf_warps <= 4
             assert p.smem_bytes <= (200 if threads == 512 else 113) * 1024
             pb = -(-nb // g.k)
             if p.mode == 0:
