@@ -55,6 +55,7 @@ SIGNATURES = {
     "lzgpu_plan_encode": (_int, [_goalp, _u32, _u32, _sz, _int, _vp]),
     "lzgpu_plan_convert": (_int, [_goalp, _goalp, _vp, _vp, _vp]),
     "lzgpu_debug_bitslice_rows": (_int, [_int, _vp, _vp]),
+    "lzgpu_debug_bitslice_recover3": (_int, [_int, _vp, _vp, _int, _vp]),
     "lzgpu_goal_slice_type": (_int, [_goalp]),
     "lzgpu_goal_from_slice_type": (_int, [_int, _goalp]),
     "lzgpu_ref_part_index": (_int, [_goalp, _int]),

@@ -293,7 +293,7 @@ static int launch(lzgpu_ctx *ctx, const CUtensorMap &map, const FusedParams &p, 
 	return LZGPU_OK;
 }
 
-// bit-sliced instantiations (W = 8: one 16-warp CTA per SM, the last four warps take the 16 G items of a step, the first twelve the
+// bit-sliced instantiations (W = 8: one 16-warp CTA per SM, the last ceil(16 G / 32) warps take the 16 G items of a step, the warps before them the
 // G (K + M - 1) * 4 streams; the plan made with bs = true guarantees both fit)
 template <int M, int KT = 0, int GT = 0, bool STRIPED = false>
 static int set_bs_attr() {

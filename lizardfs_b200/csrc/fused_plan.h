@@ -52,8 +52,8 @@ constexpr int kSmemCap = 113 * 1024;                   // dynamic shared memory 
 #define LZ_W4 2           // ec(8,4): 512 eight-byte items fill the 16 warps (0.43 -> 0.52 of the HBM peak, profiles/sweep_r2.md)
 #endif
 // Bit-sliced GF role (bitslice.cuh; round 2, runs 26-28: ec(8,4) 0.52 -> 0.79, ec(6,4) 0.50 -> 0.71, ec(10,4) 0.42 -> 0.60, ec(8,3)
-// 0.57 -> 0.82, ec(31,3) 0.08 -> 0.23 of the HBM peak): three or four Vandermonde rows on ONE 16-warp CTA per SM whose last four
-// warps only do the GF items (32-byte items on bit planes) and whose first twelve own the CRC streams.
+// 0.57 -> 0.82, ec(31,3) 0.08 -> 0.23 of the HBM peak): three or four Vandermonde rows on ONE 16-warp CTA per SM whose last
+// ceil(16 G / 32) <= 4 warps only do the GF items (32-byte items on bit planes); the warps before them own the CRC streams.
 // LZGPU_BITSLICE / LZ_BITSLICE_DEFAULT: bit 0 = four parity rows, bit 1 = three parity rows with k >= 7 (narrower stripes measured
 // 3-5 % slower than the two 8-warp CTAs of the packed-byte route: ec(5,3) 0.750 / 0.731, ec(6,3) 0.784 / 0.746, ec(4,3) 0.778 / 0.770),
 // bit 2 = three parity rows with any k (A/B).

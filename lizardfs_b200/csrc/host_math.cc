@@ -402,6 +402,63 @@ int lzgpu_debug_bitslice_rows(int k, const uint8_t *data, uint8_t *parity) {
 	return LZGPU_OK;
 }
 
+// Diagnostics: the host build of the GF role of bs_recover3_kernel for one item (same order of operations as the kernel: columns
+// k-1 .. 0, then the parity rows, then the elimination with the constants lz_fused_recover derives).
+int lzgpu_debug_bitslice_recover3(int k, const int *lost, const uint8_t *cols, int use_doublings, uint8_t *out) {
+	if (k < 3 || k > LZGPU_MAX_DATA || !lost || !cols || !out || !(0 <= lost[0] && lost[0] < lost[1] && lost[1] < lost[2] && lost[2] < k)) return LZGPU_ERR_ARG;
+	uint32_t s0[8] = {0}, s1[8] = {0}, s2[8] = {0};
+	for (int j = k - 1; j >= 0; --j) {
+		if (j == lost[0] || j == lost[1] || j == lost[2]) {
+			lzd::bs_mulpow<1>(s1);
+			lzd::bs_mulpow<2>(s2);
+			continue;
+		}
+		uint32_t v[8];
+		std::memcpy(v, cols + 32 * j, 32);
+		lzd::bs_transpose(v);
+		for (int i = 0; i < 8; ++i) s0[i] ^= v[i];
+		lzd::bs_horner<1>(s1, v);
+		lzd::bs_horner<2>(s2, v);
+	}
+	for (int r = 0; r < 3; ++r) {
+		uint32_t v[8];
+		std::memcpy(v, cols + 32 * (k + r), 32);
+		lzd::bs_transpose(v);
+		uint32_t (&s)[8] = r == 0 ? s0 : r == 1 ? s1 : s2;
+		for (int i = 0; i < 8; ++i) s[i] ^= v[i];
+	}
+	auto pw2 = [](int t) { uint8_t v = 1; for (int i = 0; i < t; ++i) v = lz::gf_mul_host(v, 2); return v; };
+	const uint8_t A = pw2(lost[0]), B = pw2(lost[1]), C = pw2(lost[2]);
+	const uint8_t pp = A ^ B, qq = A ^ C;
+	const uint8_t alpha = lz::gf_inv_host(lz::gf_mul_host(qq, pp ^ qq)), beta = lz::gf_mul_host(pp, alpha);
+	const uint8_t gamma = lz::gf_inv_host(pp), delta = lz::gf_mul_host(qq, gamma);
+	uint32_t m[6][64];
+	lzd::bs_mask_set(m[0], alpha);
+	lzd::bs_mask_set(m[1], beta);
+	lzd::bs_mask_set(m[2], gamma);
+	lzd::bs_mask_set(m[3], delta);
+	lzd::bs_mask_set(m[4], A);
+	lzd::bs_mask_set(m[5], lz::gf_mul_host(A, A));
+	uint32_t ta[8], tb[8];
+	if (use_doublings && lost[0] <= 3) {
+		for (int i = 0; i < 8; ++i) ta[i] = tb[i] = s0[i];
+		for (int i = 0; i < lost[0]; ++i) {
+			lzd::bs_mulpow<1>(ta);
+			lzd::bs_mulpow<2>(tb);
+		}
+	} else {
+		lzd::bs_mul_mask<false>(ta, s0, m[4]);
+		lzd::bs_mul_mask<false>(tb, s0, m[5]);
+	}
+	uint32_t d[3][8];
+	lzd::bs_solve3(s0, s1, s2, ta, tb, m[0], m[1], m[2], m[3], d[0], d[1], d[2]);
+	for (int x = 0; x < 3; ++x) {
+		lzd::bs_transpose(d[x]);
+		std::memcpy(out + 32 * x, d[x], 32);
+	}
+	return LZGPU_OK;
+}
+
 int lzgpu_plan_convert(const lzgpu_goal *src, const lzgpu_goal *dst, const uint8_t *available, const uint8_t *want, lzgpu_convert_plan *out) {
 	if (!out || !src || !dst || !available || !want) return LZGPU_ERR_ARG;
 	const bool src_std = src->kind == LZGPU_KIND_STD, dst_std = dst->kind == LZGPU_KIND_STD;

@@ -327,3 +327,35 @@ def test_bitslice_rows_match_the_generator(oracle, k):
                 if c:
                     want[r] ^= np.array([oracle.gf_mul(c, int(x)) for x in d[j]], dtype=np.uint8)
         assert (out == want).all(), k
+
+
+@pytest.mark.parametrize("k", [3, 4, 5, 6, 8, 12, 21, 32])
+def test_bitslice_three_lost_matches_the_reference_recovery(oracle, k):
+    """The plane arithmetic of the three-lost degraded read (csrc/bs_recover_kernel.cuh: Horner syndromes with skipped columns,
+    masked-XOR products, the three-unknown elimination; host build of the kernel's functions): 32 bytes per part must come back
+    exactly — parity rows 0, 1, 2 from the oracle's generator, several triples of lost positions per k including first unknowns
+    above position 3 (two more masked products instead of doublings), both forms where both apply."""
+    from lizardfs_b200 import _lib
+    lib = _lib.load()
+    gen = oracle.gen_rs_matrix(k + 3, k)[k:]
+    rng = np.random.default_rng(700 + k)
+    triples = {(0, 1, 2), (k - 3, k - 2, k - 1), (0, k // 2, k - 1)} if k > 3 else {(0, 1, 2)}
+    while len(triples) < min(8, k * (k - 1) * (k - 2) // 6):
+        triples.add(tuple(sorted(rng.choice(k, size=3, replace=False).tolist())))
+    for lost in sorted(triples):
+        data = rng.integers(0, 256, size=(k, 32), dtype=np.uint8)
+        par = np.zeros((3, 32), dtype=np.uint8)
+        for r in range(3):
+            for j in range(k):
+                par[r] ^= np.array([oracle.gf_mul(int(gen[r][j]), int(x)) for x in data[j]], dtype=np.uint8)
+        cols = np.concatenate([data, par]).copy()
+        for j in lost:
+            cols[j] = 0xEE    # must be ignored
+        lost_arr = (C.c_int * 3)(*lost)
+        for dbl in (0, 1):
+            out = np.zeros((3, 32), dtype=np.uint8)
+            assert lib.lzgpu_debug_bitslice_recover3(k, lost_arr, cols.ctypes.data_as(C.c_void_p), dbl, out.ctypes.data_as(C.c_void_p)) == 0
+            for x, j in enumerate(lost):
+                assert (out[x] == data[j]).all(), (k, lost, dbl, x)
+    bad = (C.c_int * 3)(2, 1, 0)
+    assert lib.lzgpu_debug_bitslice_recover3(k, bad, cols.ctypes.data_as(C.c_void_p), 0, out.ctypes.data_as(C.c_void_p)) != 0
