@@ -693,6 +693,12 @@ def main():
         for gt in ("xor2", "xor3", "ec(5,3)", "ec(8,4)"):
             for clen in (1 << 20, 4 << 20, 16 << 20, 64 << 20, (37 << 20) + 5 * BLOCK):
                 ex.encode(gt, clen, "BASELINE.json configs[4]: mixed-goal sweep", max_chunks=8192, n_check=3 if clen >= (16 << 20) else 4)
+        # beyond BASELINE.json: the degraded read with THREE lost data parts (bs_recover_kernel.cuh), same in-run checks; reported as an
+        # entry of its own and never allowed to take the line down
+        try:
+            ex.recover("ec(5,3)", (0, 1, 4), "SURVEY.md 8(a10): ec(5,3) degraded read, data parts 0, 1 and 4 lost", n=64)
+        except Exception as exc:  # noqa: BLE001
+            ex.out.append({"name": "recover ec(5,3) parts [0, 1, 4] lost (verify + rebuild + image)", "error": f"{type(exc).__name__}: {exc}"[:300]})
         extra, extra_launches = ex.out, ex.launches
 
     # ---- end-to-end through the host-buffer C-ABI call (pinned memory, copies inside the timed region)
