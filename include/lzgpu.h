@@ -83,7 +83,10 @@ uint32_t lzgpu_part_length(const lzgpu_goal *g, int part, uint32_t chunk_length)
  * mode 0: a unit is `stripes_per_unit` stripes of one chunk; 1 ("flat"): contiguous whole-stripe chunks are one run of stripes;
  * 2 ("striped"): a run of global stripes for any chunk length / stride, one TMA box per stripe.  striped_policy: -1 automatic
  * (what the library does unless LZGPU_STRIPED is set), 0 never, 1 always.  fused = 0: the generic kernels take the shape.
- * The geometry of a multi-pass encode (passes > 1) is that of its first pass. */
+ * The geometry of a multi-pass encode (passes > 1) is that of its first pass.  threads_per_cta = 512: the bit-sliced geometry
+ * (four Vandermonde parity rows, three with k >= 7: the last ceil(16 * stripes_per_unit / 32) warps of the CTA evaluate the parity
+ * rows on bit planes, the warps before them checksum the stage_rows data rows and the parity rows).  The routes are the build's
+ * defaults; the LZGPU_BITSLICE / LZGPU_BS_* overrides a context may have read from the environment are not reflected. */
 typedef struct lzgpu_encode_plan {
 	int fused, mode;
 	uint32_t stripes_per_unit, threads_per_cta, units, stage_rows, smem_bytes;
